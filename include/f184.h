@@ -1,0 +1,279 @@
+/* f184.h — C-ABI of libf184: the voxel global-illumination hot path of tobyc11/Final184 on B200.
+ *
+ * The reference has no plugin/FFI boundary: the path is a run of C++ member calls inside
+ * CMegaPipeline::Render() (Foreground/Renderer/MegaPipeline.cpp:148-342).  This header is the boundary
+ * a maintainer would cut there — every entry point names the reference call site it replaces — so
+ * that the rest of the Vulkan renderer stays as it is (INTEGRATION.md shows the patch).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, POD structs only; no exceptions cross the boundary.
+ *   - every call returns 0 (F184_OK) or a negative f184_status; f184_last_error() gives the text.
+ *   - one host thread per context.  Pass calls enqueue on the context's CUDA stream and return
+ *     immediately; only calls documented as synchronous wait for the device.
+ *   - matrices are 16 floats in the order the reference uploads them (tc::Matrix4 transposed before
+ *     upload, SceneView.cpp:28-30) = column-major, what GLSL `mat4` reads.
+ *   - images are pitch-linear device memory (x fastest); 3D volumes are x, then y, then z.
+ *   - there is no CPU fallback: without a CUDA device f184_create fails with F184_ERR_NO_DEVICE.
+ *
+ * Two contracts live behind the same calls:
+ *   F184_MODE_REFERENCE  what the shipped shaders compute: centre-sample voxelization with a last-
+ *                        writer-wins RG16UI store, 4x2 stochastic 60-step ray marches, GTAO, blur.
+ *   F184_MODE_NORTHSTAR  the design BASELINE.json names: conservative voxelization into sum+count
+ *                        accumulators, normalise, light injection, six-direction mips, cone tracing.
+ */
+#ifndef F184_H
+#define F184_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F184_ABI_VERSION 1
+
+typedef struct f184_ctx f184_ctx;
+
+typedef enum f184_status {
+    F184_OK = 0,
+    F184_ERR_INVALID_ARGUMENT = -1,
+    F184_ERR_NO_DEVICE = -2,
+    F184_ERR_CUDA = -3,
+    F184_ERR_OUT_OF_MEMORY = -4,
+    F184_ERR_NOT_READY = -5,       /* a required image/scene has not been provided */
+    F184_ERR_UNIMPLEMENTED = -6
+} f184_status;
+
+typedef enum f184_mode {
+    F184_MODE_REFERENCE = 0,
+    F184_MODE_NORTHSTAR = 1
+} f184_mode;
+
+/* Image slots: the images the reference binds by name through CMaterial::setImageView
+ * (MegaPipeline.cpp:227-229, 254-258, 272-273, 280-281) and CVoxelizeRenderer's VoxelDS
+ * (VoxelizeRenderer.cpp:98), plus the volumes the north-star stages add. */
+typedef enum f184_slot {
+    F184_SLOT_DEPTH = 0,            /* GBufferDepth, depth aspect as R32_SFLOAT            W x H  */
+    F184_SLOT_NORMALS = 1,          /* GBuffer1, R16G16B16A16_UNORM view-space n*0.5+0.5   W x H  */
+    F184_SLOT_ALBEDO = 2,           /* GBuffer0, R8G8B8A8_UNORM (bound by GTAO, unused)    W x H  */
+    F184_SLOT_MATERIAL = 3,         /* GBuffer2, R8G8B8A8_UNORM (0, roughness, metallic,0) W x H  */
+    F184_SLOT_SHADOW = 4,           /* ShadowDepth as R32_SFLOAT                            S x S  */
+    F184_SLOT_VOXELS = 5,           /* VoxelImage, R16G16_UINT (albedo565, normal565)       N^3    */
+    F184_SLOT_INDIRECT_OUT = 6,     /* indirectImage, R16G16B16A16_SFLOAT (rgb, -viewZ)     W x H  */
+    F184_SLOT_INDIRECT_HISTORY = 7, /* indirectTemporalImage, R16G16B16A16_SFLOAT           W x H  */
+    F184_SLOT_AO_RAW = 8,           /* gtao_visibility target, R16G16B16A16_SFLOAT          W x H  */
+    F184_SLOT_AO_OUT = 9,           /* gtao_blur target, R16G16B16A16_SFLOAT                W x H  */
+    F184_SLOT_INDIRECT_BLUR_X = 10, /* indirect_blurX target, R16G16B16A16_SFLOAT           W x H  */
+    F184_SLOT_INDIRECT_FINAL = 11,  /* indirect_blurY target, R16G16B16A16_SFLOAT           W x H  */
+    /* north-star volumes (no reference image behind them) */
+    F184_SLOT_ACCUM_COLOR = 12,     /* float4 (sum r, sum g, sum b, count), brick-major     N^3    */
+    F184_SLOT_ACCUM_NORMAL = 13,    /* float4 (sum nx, sum ny, sum nz, 0), brick-major      N^3    */
+    F184_SLOT_VOX_ALBEDO = 14,      /* R8G8B8A8_UNORM mean albedo, a = 255*occupied         N^3    */
+    F184_SLOT_VOX_NORMAL = 15,      /* R8G8B8A8_SNORM normalised mean normal                N^3    */
+    F184_SLOT_RADIANCE = 16,        /* R8G8B8A8_UNORM premultiplied radiance/exposure, mip 0 N^3   */
+    F184_SLOT_MIPS = 17,            /* all levels >= 1, six directions each, one allocation        */
+    F184_SLOT_BRICK_FLAGS = 18,     /* u32 per 8^3 brick: touched this frame                (N/8)^3 */
+    F184_SLOT_COUNT = 19
+} f184_slot;
+
+typedef enum f184_format {
+    F184_FMT_UNDEFINED = 0,
+    F184_FMT_R32_SFLOAT = 1,
+    F184_FMT_R16G16B16A16_UNORM = 2,
+    F184_FMT_R8G8B8A8_UNORM = 3,
+    F184_FMT_R16G16B16A16_SFLOAT = 4,
+    F184_FMT_R16G16_UINT = 5,
+    F184_FMT_R32G32B32A32_SFLOAT = 6,
+    F184_FMT_R8G8B8A8_SNORM = 7,
+    F184_FMT_R32_UINT = 8
+} f184_format;
+
+typedef struct f184_image_desc {
+    void* device_ptr;        /* CUDA device pointer (or mapped external memory); NULL = let the context own it */
+    uint32_t format;         /* f184_format */
+    uint32_t width, height, depth;
+    uint32_t row_pitch_bytes;   /* 0 = tightly packed */
+    uint64_t size_bytes;     /* filled by f184_image_info */
+} f184_image_desc;
+
+/* Creation parameters.  Replaces the literals the reference hard-codes: volume 128
+ * (MegaPipeline.cpp:475-476, 486-487; indirect.frag:133,143,146), window 1280x720 (App/Game.cpp:29-31),
+ * shadow 2048 (MegaPipeline.cpp:392-394; indirect.frag:164), step 0.2 x 60 (indirect.frag:109,138). */
+typedef struct f184_config {
+    uint32_t struct_size;    /* sizeof(f184_config), for ABI growth */
+    int32_t device;          /* CUDA ordinal */
+    uint32_t mode;           /* f184_mode */
+    uint32_t grid_n;         /* voxel grid edge; power of two, 32..1024 */
+    uint32_t width, height;  /* G-buffer / output resolution */
+    uint32_t shadow_res;     /* shadow map edge */
+    uint32_t march_steps;    /* 60 */
+    float step_size;         /* 0.2 world units */
+    /* north-star cone parameters */
+    float cone_max_distance; /* 32 m */
+    float radiance_exposure; /* RGBA8 radiance = radiance / exposure, clamped; 0 = default 8.0 */
+    /* sharding over one NVLink box; rank/nranks = 0/1 for a single GPU */
+    uint32_t rank, nranks;
+    uint32_t flags;          /* f184_flags */
+} f184_config;
+
+typedef enum f184_flags {
+    F184_FLAG_NONE = 0,
+    F184_FLAG_EXTERNAL_RANDS = 1   /* mode R trace: rands come from a bound buffer (march-only parity) */
+} f184_flags;
+
+/* CViewConstants, Foreground/SceneGraph/SceneView.h:8-14 = GlobalConstants, Shader/EngineCommon.h:7-13. 208 B. */
+typedef struct f184_view_constants {
+    float CameraPos[4];
+    float ViewMat[16];
+    float ProjMat[16];
+    float InvProj[16];
+} f184_view_constants;
+
+/* ExtendedMatricesConstants, MegaPipeline.cpp:132-139 = ExtendedMatrices, indirect.frag:18-24. 320 B. */
+typedef struct f184_extended_matrices {
+    float InvModelView[16];
+    float ShadowView[16];
+    float ShadowProj[16];
+    float VoxelView[16];
+    float VoxelProj[16];
+} f184_extended_matrices;
+
+/* PreviousProjections, MegaPipeline.h:16-20 = prevProj, indirect.frag:31-34. 128 B. */
+typedef struct f184_prev_proj {
+    float PrevProjection[16];
+    float PrevModelView[16];
+} f184_prev_proj;
+
+/* PerLightConstants, MegaPipeline.cpp:95-99 = Sun, indirect.frag:26-29 (std140: vec3 @0, vec3 @16). 32 B.
+ * `position` holds the light's forward DIRECTION for a directional light (MegaPipeline.cpp:110,120). */
+typedef struct f184_sun {
+    float luminance[3];
+    float _pad0;
+    float position[3];
+    float _pad1;
+} f184_sun;
+
+/* EngineCommonMiscs, MegaPipeline.cpp:141-146 = indirect.frag:36-40. 16 B. */
+typedef struct f184_engine_miscs {
+    float resolution[2];
+    uint32_t frameCount;
+    float frameTime;
+} f184_engine_miscs;
+
+/* Everything lighting_indirect binds with setStruct (MegaPipeline.cpp:259-266). */
+typedef struct f184_trace_constants {
+    f184_view_constants view;
+    f184_extended_matrices ext;
+    f184_prev_proj prev;
+    f184_sun sun;
+    f184_engine_miscs miscs;
+    uint32_t reset_history;   /* 1 on the first frame / after resize (MegaPipeline.cpp:197-204, 92) */
+    uint32_t _pad[3];
+} f184_trace_constants;
+
+/* Flat scene: replaces the per-primitive vertex/index buffers of glTFSceneImporter.cpp:210-326 and the
+ * per-primitive ModelMat of VoxelizeRenderer.cpp:100-106. */
+typedef struct f184_scene_desc {
+    const float* positions;       /* n_verts x 3, object space */
+    const float* normals;         /* n_verts x 3 */
+    const float* uvs;             /* n_verts x 2 */
+    const uint32_t* indices;      /* n_tris x 3 */
+    const uint16_t* tri_material; /* n_tris */
+    const uint16_t* tri_model;    /* n_tris: index into model_mats */
+    const float* model_mats;      /* n_models x 16, upload order */
+    uint32_t n_verts, n_tris, n_models;
+} f184_scene_desc;
+
+typedef enum f184_stage_id {
+    F184_STAGE_CLEAR = 0,
+    F184_STAGE_VOXELIZE = 1,
+    F184_STAGE_NORMALISE = 2,
+    F184_STAGE_INJECT = 3,
+    F184_STAGE_MIPS = 4,
+    F184_STAGE_TRACE = 5,
+    F184_STAGE_GTAO = 6,
+    F184_STAGE_BLUR = 7,
+    F184_STAGE_COUNT = 8
+} f184_stage_id;
+
+typedef enum f184_counter_id {
+    F184_COUNTER_FRAGMENTS = 0,     /* voxel fragments stored/accumulated by the last f184_voxelize */
+    F184_COUNTER_MARCH_STEPS = 1,   /* cone-samples (march iterations) of the last f184_trace_indirect */
+    F184_COUNTER_OCCUPIED = 2,      /* occupied voxels after the last normalise */
+    F184_COUNTER_KERNEL_LAUNCHES = 3, /* kernels launched by this context since creation */
+    F184_COUNTER_BRICKS = 4,        /* touched 8^3 bricks in the last f184_voxelize (mode N) */
+    F184_COUNTER_COUNT = 5
+} f184_counter_id;
+
+/* ---- lifetime: CMegaPipeline ctor + CreateVoxelizePass/CreateScreenPass, MegaPipeline.cpp:27-60, 470-590 */
+int f184_abi_version(void);
+int f184_create(const f184_config* config, f184_ctx** out_ctx);
+void f184_destroy(f184_ctx* ctx);
+const char* f184_last_error(const f184_ctx* ctx);   /* ctx may be NULL: error of a failed f184_create */
+
+/* ---- scene: CVoxelizeRenderer::PreparePrimitiveResources (VoxelizeRenderer.cpp:32-67),
+ *      CBasicMaterial::Bind (BasicMaterial.cpp:9-39), image upload + mip generation (DeviceVk.cpp:317-484).
+ *      Synchronous. */
+int f184_scene_upload(f184_ctx* ctx, const f184_scene_desc* scene);
+int f184_texture_upload(f184_ctx* ctx, uint32_t tex_id, const uint8_t* rgba8, uint32_t width, uint32_t height);
+int f184_material_set(f184_ctx* ctx, uint32_t material_id, const float base_color_factor[4],
+                      int32_t base_color_tex, uint32_t use_textures);
+/* mip level of an uploaded texture, as built on the device (testing; synchronous) */
+int f184_texture_readback(f184_ctx* ctx, uint32_t tex_id, uint32_t level, uint8_t* rgba8, size_t bytes);
+
+/* ---- images: CMaterial::setImageView / BindImageView.  Context-owned by default; bind to share
+ *      torch tensors or imported Vulkan memory. */
+int f184_bind_image(f184_ctx* ctx, uint32_t slot, const f184_image_desc* desc);
+int f184_image_info(f184_ctx* ctx, uint32_t slot, f184_image_desc* out_desc);
+int f184_upload_image(f184_ctx* ctx, uint32_t slot, const void* host, size_t bytes);      /* async H2D on the stream */
+int f184_readback(f184_ctx* ctx, uint32_t slot, void* host, size_t bytes);                /* synchronous D2H */
+int f184_readback_async(f184_ctx* ctx, uint32_t slot, void* pinned_host, size_t bytes);   /* async D2H on the stream */
+
+/* Vulkan interop: import an exported VkDeviceMemory (opaque fd) as a slot, and
+ * the section wait/signal semaphores (RHI/Private/Vulkan/CommandListVk.h:17-24). */
+int f184_import_external_memory_fd(f184_ctx* ctx, uint32_t slot, int fd, uint64_t alloc_size,
+                                   uint64_t offset, const f184_image_desc* layout);
+int f184_import_semaphores_fd(f184_ctx* ctx, int wait_fd, int signal_fd);
+int f184_frame_begin(f184_ctx* ctx);   /* waits the imported semaphore on the stream (no-op without one) */
+int f184_frame_end(f184_ctx* ctx);     /* signals the imported semaphore on the stream (no-op without one) */
+
+/* ---- stream plumbing */
+int f184_set_stream(f184_ctx* ctx, void* cuda_stream);   /* NULL = context's own stream */
+int f184_sync(f184_ctx* ctx);
+
+/* ---- passes */
+/* ClearImage(VoxelImage) MegaPipeline.cpp:196 + the voxelization pass :218-223
+ * (CVoxelizeRenderer::RenderList, VoxelizeRenderer.cpp:19-30, 81-127; shaders Pipelang/Internal/main.lua:60-75,
+ * 83-144, 179-206, 242-275).  Mode R fills F184_SLOT_VOXELS; mode N fills the accumulators and normalises
+ * into VOX_ALBEDO / VOX_NORMAL. */
+int f184_voxelize(f184_ctx* ctx, const f184_view_constants* voxel_cam);
+/* Mode N only: hoists the first-bounce lighting of indirect.frag:157-169 into the volume. */
+int f184_inject(f184_ctx* ctx, const f184_sun* sun, const f184_extended_matrices* matrices);
+/* Mode N only: six-direction anisotropic mip chain. */
+int f184_build_mips(f184_ctx* ctx);
+/* lighting_indirect pass, MegaPipeline.cpp:252-268 (Shader/Lighting/indirect.frag). */
+int f184_trace_indirect(f184_ctx* ctx, const f184_trace_constants* constants);
+/* gtao_visibility + gtao_blur, MegaPipeline.cpp:225-239 (Shader/GTAO/gtao.frag, blur.frag). */
+int f184_gtao(f184_ctx* ctx, const f184_view_constants* view);
+/* indirect_blurX + indirect_blurY, MegaPipeline.cpp:270-284 (Shader/Lighting/bilateralBlur.inc). */
+int f184_blur_indirect(f184_ctx* ctx, const f184_engine_miscs* miscs);
+/* CopyImage(indirectImage -> indirectTemporalImage), MegaPipeline.cpp:211-214. */
+int f184_copy_indirect_to_history(f184_ctx* ctx);
+
+/* mode R trace with F184_FLAG_EXTERNAL_RANDS: 8 x (u, v) floats per pixel, seed-major (parity aid) */
+int f184_bind_rands(f184_ctx* ctx, const float* device_rands, size_t count);
+
+/* ---- sharding.  A rank voxelizes triangles [first, first+count), owns Z-slab
+ * [z0, z1) of every volume level and traces rows [y0, y1).  Defaults are derived from rank/nranks. */
+int f184_set_triangle_range(f184_ctx* ctx, uint32_t first, uint32_t count);
+int f184_set_trace_rows(f184_ctx* ctx, uint32_t y0, uint32_t y1);
+
+/* ---- measurement */
+int f184_stage_time_ms(f184_ctx* ctx, uint32_t stage, float* out_ms);   /* last run of the stage; synchronous */
+int f184_counter_get(f184_ctx* ctx, uint32_t which, uint64_t* out_value);    /* synchronous */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F184_H */
