@@ -1,0 +1,321 @@
+"""ctypes binding of the libf184 C-ABI (include/f184.h) and the host-side mirror of the reference's
+frame section that drives it.
+
+`VoxelGI` is deliberately written against a *(library, symbol prefix)* pair: the product is
+(`libf184.so`, "f184_").  The test-suite points the same class at the CPU oracle's mirror API
+(`libf184_oracle.so`, "f184o_") so both sides are driven by identical host code; nothing in this
+package ever loads the oracle.
+
+There is no CPU fallback: `load_library()` raises if the CUDA library has not been built, and
+`f184_create` fails without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import scene as S
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libf184.so")
+
+# ---- enums (include/f184.h) ------------------------------------------------------------------
+MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
+(SLOT_DEPTH, SLOT_NORMALS, SLOT_ALBEDO, SLOT_MATERIAL, SLOT_SHADOW, SLOT_VOXELS, SLOT_INDIRECT_OUT,
+ SLOT_INDIRECT_HISTORY, SLOT_AO_RAW, SLOT_AO_OUT, SLOT_INDIRECT_BLUR_X, SLOT_INDIRECT_FINAL,
+ SLOT_ACCUM_COLOR, SLOT_ACCUM_NORMAL, SLOT_VOX_ALBEDO, SLOT_VOX_NORMAL, SLOT_RADIANCE, SLOT_MIPS,
+ SLOT_BRICK_FLAGS, SLOT_COUNT) = range(20)
+(STAGE_CLEAR, STAGE_VOXELIZE, STAGE_NORMALISE, STAGE_INJECT, STAGE_MIPS, STAGE_TRACE, STAGE_GTAO,
+ STAGE_BLUR, STAGE_COUNT) = range(9)
+STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur"]
+(COUNTER_FRAGMENTS, COUNTER_MARCH_STEPS, COUNTER_OCCUPIED, COUNTER_KERNEL_LAUNCHES, COUNTER_BRICKS) = range(5)
+FLAG_EXTERNAL_RANDS = 1
+
+(FMT_UNDEFINED, FMT_R32_SFLOAT, FMT_R16G16B16A16_UNORM, FMT_R8G8B8A8_UNORM, FMT_R16G16B16A16_SFLOAT,
+ FMT_R16G16_UINT, FMT_R32G32B32A32_SFLOAT, FMT_R8G8B8A8_SNORM, FMT_R32_UINT) = range(9)
+_FMT_NP = {FMT_R32_SFLOAT: (np.float32, 1), FMT_R16G16B16A16_UNORM: (np.uint16, 4),
+           FMT_R8G8B8A8_UNORM: (np.uint8, 4), FMT_R16G16B16A16_SFLOAT: (np.float16, 4),
+           FMT_R16G16_UINT: (np.uint16, 2), FMT_R32G32B32A32_SFLOAT: (np.float32, 4),
+           FMT_R8G8B8A8_SNORM: (np.int8, 4), FMT_R32_UINT: (np.uint32, 1)}
+
+
+# ---- POD structs -------------------------------------------------------------------------------
+class Config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("mode", C.c_uint32), ("grid_n", C.c_uint32),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("shadow_res", C.c_uint32),
+                ("march_steps", C.c_uint32), ("step_size", C.c_float), ("cone_max_distance", C.c_float),
+                ("radiance_exposure", C.c_float), ("rank", C.c_uint32), ("nranks", C.c_uint32),
+                ("flags", C.c_uint32)]
+
+
+class ImageDesc(C.Structure):
+    _fields_ = [("device_ptr", C.c_void_p), ("format", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("depth", C.c_uint32), ("row_pitch_bytes", C.c_uint32), ("size_bytes", C.c_uint64)]
+
+
+class ViewConstantsC(C.Structure):
+    _fields_ = [("CameraPos", C.c_float * 4), ("ViewMat", C.c_float * 16), ("ProjMat", C.c_float * 16),
+                ("InvProj", C.c_float * 16)]
+
+
+class ExtendedMatricesC(C.Structure):
+    _fields_ = [("InvModelView", C.c_float * 16), ("ShadowView", C.c_float * 16), ("ShadowProj", C.c_float * 16),
+                ("VoxelView", C.c_float * 16), ("VoxelProj", C.c_float * 16)]
+
+
+class PrevProjC(C.Structure):
+    _fields_ = [("PrevProjection", C.c_float * 16), ("PrevModelView", C.c_float * 16)]
+
+
+class SunC(C.Structure):
+    _fields_ = [("luminance", C.c_float * 3), ("_pad0", C.c_float), ("position", C.c_float * 3), ("_pad1", C.c_float)]
+
+
+class EngineMiscsC(C.Structure):
+    _fields_ = [("resolution", C.c_float * 2), ("frameCount", C.c_uint32), ("frameTime", C.c_float)]
+
+
+class TraceConstantsC(C.Structure):
+    _fields_ = [("view", ViewConstantsC), ("ext", ExtendedMatricesC), ("prev", PrevProjC), ("sun", SunC),
+                ("miscs", EngineMiscsC), ("reset_history", C.c_uint32), ("_pad", C.c_uint32 * 3)]
+
+
+class SceneDescC(C.Structure):
+    _fields_ = [("positions", C.c_void_p), ("normals", C.c_void_p), ("uvs", C.c_void_p), ("indices", C.c_void_p),
+                ("tri_material", C.c_void_p), ("tri_model", C.c_void_p), ("model_mats", C.c_void_p),
+                ("n_verts", C.c_uint32), ("n_tris", C.c_uint32), ("n_models", C.c_uint32)]
+
+
+assert C.sizeof(ViewConstantsC) == 208 and C.sizeof(ExtendedMatricesC) == 320 and C.sizeof(PrevProjC) == 128
+assert C.sizeof(SunC) == 32 and C.sizeof(EngineMiscsC) == 16
+
+
+def _m16(m):
+    return (C.c_float * 16)(*S.to_glsl(m))
+
+
+def view_constants_c(v: S.ViewConstants) -> ViewConstantsC:
+    return ViewConstantsC((C.c_float * 4)(*np.asarray(v.camera_pos, np.float32)), _m16(v.view), _m16(v.proj), _m16(v.inv_proj))
+
+
+def trace_constants_c(main: S.ViewConstants, shadow: S.ViewConstants, voxel: S.ViewConstants, width, height,
+                      frame_count=0, reset_history=True, prev: S.ViewConstants | None = None,
+                      sun_luminance=S.SUN_LUMINANCE) -> TraceConstantsC:
+    """The five uniform blocks lighting_indirect binds (MegaPipeline.cpp:241-250, 259-266)."""
+    prev = prev or main
+    k = TraceConstantsC()
+    k.view = view_constants_c(main)
+    k.ext = ExtendedMatricesC(_m16(main.inv_view), _m16(shadow.view), _m16(shadow.proj), _m16(voxel.view), _m16(voxel.proj))
+    k.prev = PrevProjC(_m16(prev.proj), _m16(prev.view))
+    k.sun = SunC((C.c_float * 3)(*sun_luminance), 0.0, (C.c_float * 3)(*np.asarray(shadow.forward, np.float32)), 0.0)
+    k.miscs = EngineMiscsC((C.c_float * 2)(float(width), float(height)), int(frame_count), 0.0)
+    k.reset_history = 1 if reset_history else 0
+    return k
+
+
+# ---- library -----------------------------------------------------------------------------------
+_SIGS = {
+    "abi_version": (C.c_int, []),
+    "create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "destroy": (None, [C.c_void_p]),
+    "last_error": (C.c_char_p, [C.c_void_p]),
+    "scene_upload": (C.c_int, [C.c_void_p, C.POINTER(SceneDescC)]),
+    "texture_upload": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "material_set": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.c_int32, C.c_uint32]),
+    "texture_readback": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "bind_image": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ImageDesc)]),
+    "image_info": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ImageDesc)]),
+    "upload_image": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "readback": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "readback_async": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sync": (C.c_int, [C.c_void_p]),
+    "frame_begin": (C.c_int, [C.c_void_p]),
+    "frame_end": (C.c_int, [C.c_void_p]),
+    "voxelize": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC)]),
+    "inject": (C.c_int, [C.c_void_p, C.POINTER(SunC), C.POINTER(ExtendedMatricesC)]),
+    "build_mips": (C.c_int, [C.c_void_p]),
+    "trace_indirect": (C.c_int, [C.c_void_p, C.POINTER(TraceConstantsC)]),
+    "gtao": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC)]),
+    "blur_indirect": (C.c_int, [C.c_void_p, C.POINTER(EngineMiscsC)]),
+    "copy_indirect_to_history": (C.c_int, [C.c_void_p]),
+    "bind_rands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "set_triangle_range": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "set_trace_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "stage_time_ms": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]),
+    "counter_get": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
+}
+# product-only entry points (no oracle mirror)
+_PRODUCT_ONLY = {
+    "import_external_memory_fd": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(ImageDesc)]),
+    "import_semaphores_fd": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "debug_detmath": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+}
+EXPORTS = sorted(list(_SIGS) + list(_PRODUCT_ONLY))
+
+
+class F184Error(RuntimeError):
+    pass
+
+
+class Library:
+    def __init__(self, path: str, prefix: str = "f184_", product: bool = True):
+        if not os.path.exists(path):
+            raise F184Error(f"{path} not found: build it first (python -c 'import __graft_entry__ as g; g.build()'). "
+                            "There is no CPU fallback for the CUDA path.")
+        self.path, self.prefix = path, prefix
+        self.dll = C.CDLL(path)
+        sigs = dict(_SIGS)
+        if product:
+            sigs.update(_PRODUCT_ONLY)
+        for name, (res, args) in sigs.items():
+            fn = getattr(self.dll, prefix + name)
+            fn.restype, fn.argtypes = res, args
+            setattr(self, name, fn)
+
+
+_lib = None
+
+
+def load_library() -> Library:
+    """The CUDA library.  Raises if it is not built — never falls back to anything else."""
+    global _lib
+    if _lib is None:
+        _lib = Library(LIB_PATH, "f184_", product=True)
+    return _lib
+
+
+class VoxelGI:
+    """One voxel-GI context = the voxel/indirect/GTAO section of CMegaPipeline (MegaPipeline.cpp:195-284)."""
+
+    def __init__(self, grid_n=128, width=1280, height=720, mode=MODE_REFERENCE, shadow_res=2048, device=0,
+                 march_steps=60, step_size=0.2, flags=0, rank=0, nranks=1, lib: Library | None = None):
+        self.lib = lib or load_library()
+        self.cfg = Config(C.sizeof(Config), device, mode, grid_n, width, height, shadow_res, march_steps, step_size,
+                          32.0, 8.0, rank, nranks, flags)
+        self.h = C.c_void_p()
+        rc = self.lib.create(C.byref(self.cfg), C.byref(self.h))
+        if rc != 0:
+            raise F184Error(f"{self.lib.prefix}create failed ({rc}): {self.lib.last_error(None).decode()}")
+        self._keep = []
+
+    # -- helpers
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise F184Error(f"{self.lib.prefix}{what} failed ({rc}): {self.lib.last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- scene
+    def upload_scene(self, sc: S.Scene):
+        arrs = dict(pos=np.ascontiguousarray(sc.pos, np.float32), nrm=np.ascontiguousarray(sc.nrm, np.float32),
+                    uv=np.ascontiguousarray(sc.uv, np.float32), idx=np.ascontiguousarray(sc.idx, np.uint32),
+                    tm=np.ascontiguousarray(sc.tri_mat, np.uint16), tmod=np.ascontiguousarray(sc.tri_model, np.uint16),
+                    mm=np.ascontiguousarray(np.stack([S.to_glsl(m) for m in sc.model_mats]), np.float32))
+        d = SceneDescC(*[a.ctypes.data for a in arrs.values()], len(arrs["pos"]), len(arrs["idx"]), len(arrs["mm"]))
+        self._ck(self.lib.scene_upload(self.h, C.byref(d)), "scene_upload")
+        for k, t in enumerate(sc.textures):
+            t = np.ascontiguousarray(t, np.uint8)
+            self._ck(self.lib.texture_upload(self.h, k, t.ctypes.data, t.shape[1], t.shape[0]), "texture_upload")
+        for k in range(len(sc.mat_tex)):
+            f = (C.c_float * 4)(*sc.mat_factor[k])
+            self._ck(self.lib.material_set(self.h, k, f, int(sc.mat_tex[k]), 1), "material_set")
+        self.n_tris = sc.n_tris
+
+    def texture_level(self, tex_id, level, w, h):
+        out = np.empty((h, w, 4), np.uint8)
+        self._ck(self.lib.texture_readback(self.h, tex_id, level, out.ctypes.data, out.nbytes), "texture_readback")
+        return out
+
+    # -- images
+    def image_info(self, slot) -> ImageDesc:
+        d = ImageDesc()
+        self._ck(self.lib.image_info(self.h, slot, C.byref(d)), "image_info")
+        return d
+
+    def upload(self, slot, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        self._keep.append(arr)
+        self._ck(self.lib.upload_image(self.h, slot, arr.ctypes.data, arr.nbytes), "upload_image")
+
+    def upload_ptr(self, slot, host_ptr, nbytes):
+        self._ck(self.lib.upload_image(self.h, slot, host_ptr, nbytes), "upload_image")
+
+    def readback(self, slot) -> np.ndarray:
+        d = self.image_info(slot)
+        dt, nc = _FMT_NP[d.format]
+        shape = [d.depth, d.height, d.width, nc] if d.depth > 1 else [d.height, d.width, nc]
+        if nc == 1:
+            shape = shape[:-1]
+        out = np.empty(shape, dt)
+        assert out.nbytes == d.size_bytes, (out.nbytes, d.size_bytes)
+        self._ck(self.lib.readback(self.h, slot, out.ctypes.data, out.nbytes), "readback")
+        return out
+
+    def readback_async_ptr(self, slot, host_ptr, nbytes):
+        self._ck(self.lib.readback_async(self.h, slot, host_ptr, nbytes), "readback_async")
+
+    def bind(self, slot, device_ptr, fmt, width, height, depth=1):
+        d = ImageDesc(device_ptr, fmt, width, height, depth, 0, 0)
+        self._ck(self.lib.bind_image(self.h, slot, C.byref(d)), "bind_image")
+
+    def set_stream(self, stream_ptr):
+        self._ck(self.lib.set_stream(self.h, stream_ptr), "set_stream")
+
+    def sync(self):
+        self._ck(self.lib.sync(self.h), "sync")
+
+    # -- passes
+    def voxelize(self, voxel_cam: S.ViewConstants | ViewConstantsC):
+        v = voxel_cam if isinstance(voxel_cam, ViewConstantsC) else view_constants_c(voxel_cam)
+        self._ck(self.lib.voxelize(self.h, C.byref(v)), "voxelize")
+
+    def inject(self, k: TraceConstantsC):
+        self._ck(self.lib.inject(self.h, C.byref(k.sun), C.byref(k.ext)), "inject")
+
+    def build_mips(self):
+        self._ck(self.lib.build_mips(self.h), "build_mips")
+
+    def trace_indirect(self, k: TraceConstantsC):
+        self._ck(self.lib.trace_indirect(self.h, C.byref(k)), "trace_indirect")
+
+    def gtao(self, view: S.ViewConstants | ViewConstantsC):
+        v = view if isinstance(view, ViewConstantsC) else view_constants_c(view)
+        self._ck(self.lib.gtao(self.h, C.byref(v)), "gtao")
+
+    def blur_indirect(self, k: TraceConstantsC):
+        self._ck(self.lib.blur_indirect(self.h, C.byref(k.miscs)), "blur_indirect")
+
+    def copy_indirect_to_history(self):
+        self._ck(self.lib.copy_indirect_to_history(self.h), "copy_indirect_to_history")
+
+    def bind_rands(self, ptr, count):
+        self._ck(self.lib.bind_rands(self.h, ptr, count), "bind_rands")
+
+    def set_triangle_range(self, first, count):
+        self._ck(self.lib.set_triangle_range(self.h, first, count), "set_triangle_range")
+
+    def set_trace_rows(self, y0, y1):
+        self._ck(self.lib.set_trace_rows(self.h, y0, y1), "set_trace_rows")
+
+    # -- measurement
+    def stage_ms(self, stage) -> float:
+        v = C.c_float()
+        self._ck(self.lib.stage_time_ms(self.h, stage, C.byref(v)), "stage_time_ms")
+        return v.value
+
+    def counter(self, which) -> int:
+        v = C.c_uint64()
+        self._ck(self.lib.counter_get(self.h, which, C.byref(v)), "counter_get")
+        return v.value

@@ -1,0 +1,40 @@
+// debug_hooks.cu — test hook: evaluate f184_detmath.h ON THE DEVICE so tests can show it is bit-identical
+// to the host evaluation (the premise of the bit-exact parity tests).  Host pointers in, host pointers out.
+#include "f184_device.cuh"
+
+namespace {
+__global__ void k_detmath(uint32_t op, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r = 0.f;
+    switch (op)
+    {
+    case 0: r = dm_sin(x[i]); break;
+    case 1: r = dm_cos(x[i]); break;
+    case 2: r = dm_log(x[i]); break;
+    case 3: r = dm_log2(x[i]); break;
+    case 4: r = dm_exp2(x[i]); break;
+    case 5: r = dm_pow(x[i], y[i]); break;
+    case 6: r = dm_f16_to_f32(dm_f32_to_f16(x[i])); break;
+    }
+    out[i] = r;
+}
+}  // namespace
+
+extern "C" int f184_debug_detmath(f184_ctx* c, uint32_t op, const float* x, const float* y, float* out, size_t n)
+{
+    if (!c || op > 6 || !x || !out) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_detmath: bad argument");
+    float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    CK(c, cudaMalloc(&dx, n * 4));
+    CK(c, cudaMalloc(&dy, n * 4));
+    CK(c, cudaMalloc(&dout, n * 4));
+    CK(c, cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(dy, y ? y : x, n * 4, cudaMemcpyHostToDevice));
+    k_detmath<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(op, dx, dy, dout, n);
+    CK_LAUNCH(c);
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return F184_OK;
+}

@@ -1,0 +1,535 @@
+// f184_api.cu — the C-ABI of libf184 (include/f184.h): context, scene/texture upload, image slots,
+// stream/interop plumbing, stage timing.  The passes themselves live in the mode_*.cu / gtao.cu / blur.cu
+// translation units.  There is deliberately no host fallback anywhere in this library.
+#include <cstdarg>
+
+#include "f184_internal.h"
+
+static std::string g_create_err;
+
+int f184_fail(f184_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_err = buf;
+    return code;
+}
+
+static uint32_t fmt_bytes(uint32_t f)
+{
+    switch (f)
+    {
+    case F184_FMT_R32_SFLOAT: return 4;
+    case F184_FMT_R16G16B16A16_UNORM: return 8;
+    case F184_FMT_R8G8B8A8_UNORM: return 4;
+    case F184_FMT_R16G16B16A16_SFLOAT: return 8;
+    case F184_FMT_R16G16_UINT: return 4;
+    case F184_FMT_R32G32B32A32_SFLOAT: return 16;
+    case F184_FMT_R8G8B8A8_SNORM: return 4;
+    case F184_FMT_R32_UINT: return 4;
+    }
+    return 0;
+}
+
+static uint64_t mips_total_texels(uint32_t n)
+{
+    uint64_t t = 0;
+    for (uint32_t s = n / 2; s >= 1; s /= 2) t += 6ull * s * s * s;
+    return t;
+}
+
+static bool default_desc(const f184_config& c, int slot, f184_image_desc* d)
+{
+    memset(d, 0, sizeof(*d));
+    const uint32_t W = c.width, H = c.height, S = c.shadow_res, N = c.grid_n;
+    auto set = [&](uint32_t f, uint32_t w, uint32_t h, uint32_t dep) {
+        d->format = f; d->width = w; d->height = h; d->depth = dep;
+        d->row_pitch_bytes = w * fmt_bytes(f);
+        d->size_bytes = (uint64_t)w * h * dep * fmt_bytes(f);
+    };
+    switch (slot)
+    {
+    case F184_SLOT_DEPTH: set(F184_FMT_R32_SFLOAT, W, H, 1); break;
+    case F184_SLOT_NORMALS: set(F184_FMT_R16G16B16A16_UNORM, W, H, 1); break;
+    case F184_SLOT_ALBEDO:
+    case F184_SLOT_MATERIAL: set(F184_FMT_R8G8B8A8_UNORM, W, H, 1); break;
+    case F184_SLOT_SHADOW: set(F184_FMT_R32_SFLOAT, S, S, 1); break;
+    case F184_SLOT_VOXELS: set(F184_FMT_R16G16_UINT, N, N, N); break;
+    case F184_SLOT_INDIRECT_OUT:
+    case F184_SLOT_INDIRECT_HISTORY:
+    case F184_SLOT_AO_RAW:
+    case F184_SLOT_AO_OUT:
+    case F184_SLOT_INDIRECT_BLUR_X:
+    case F184_SLOT_INDIRECT_FINAL: set(F184_FMT_R16G16B16A16_SFLOAT, W, H, 1); break;
+    case F184_SLOT_ACCUM_COLOR:
+    case F184_SLOT_ACCUM_NORMAL: set(F184_FMT_R32G32B32A32_SFLOAT, N, N, N); break;
+    case F184_SLOT_VOX_ALBEDO: set(F184_FMT_R8G8B8A8_UNORM, N, N, N); break;
+    case F184_SLOT_VOX_NORMAL: set(F184_FMT_R8G8B8A8_SNORM, N, N, N); break;
+    case F184_SLOT_RADIANCE: set(F184_FMT_R8G8B8A8_UNORM, N, N, N); break;
+    case F184_SLOT_MIPS:
+        d->format = F184_FMT_R8G8B8A8_UNORM; d->width = (uint32_t)mips_total_texels(N); d->height = 1; d->depth = 1;
+        d->row_pitch_bytes = 0; d->size_bytes = mips_total_texels(N) * 4; break;
+    case F184_SLOT_BRICK_FLAGS: set(F184_FMT_R32_UINT, N / 8, N / 8, N / 8); break;
+    default: return false;
+    }
+    return true;
+}
+
+int f184_ensure_image(f184_ctx* c, int slot)
+{
+    DevImage& im = c->img[slot];
+    if (im.ptr) return F184_OK;
+    f184_image_desc d;
+    if (!default_desc(c->cfg, slot, &d)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "bad slot %d", slot);
+    CK(c, cudaMalloc(&im.ptr, d.size_bytes));
+    CK(c, cudaMemsetAsync(im.ptr, 0, d.size_bytes, c->stream));
+    im.owned = true;
+    im.desc = d;
+    im.desc.device_ptr = im.ptr;
+    return F184_OK;
+}
+
+int f184_stage_begin(f184_ctx* c, int stage)
+{
+    CK(c, cudaEventRecord(c->ev[stage][0], c->stream));
+    return F184_OK;
+}
+int f184_stage_end(f184_ctx* c, int stage)
+{
+    CK(c, cudaEventRecord(c->ev[stage][1], c->stream));
+    c->ev_valid[stage] = true;
+    return F184_OK;
+}
+
+// ---- texture mip chain on the device ------------------------------------------------------------
+// One level per launch: mean of the 2x2 source block, rounded half-to-even back to UNORM8 — what a linear
+// 2:1 vkCmdBlitImage computes (RHI/Private/Vulkan/DeviceVk.cpp:437-465).
+__global__ void k_tex_downsample(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t sw, uint32_t dw, uint32_t dh)
+{
+    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const uchar4* s = reinterpret_cast<const uchar4*>(src);
+    uchar4 a = s[(size_t)(2 * y) * sw + 2 * x], b = s[(size_t)(2 * y) * sw + 2 * x + 1];
+    uchar4 cc = s[(size_t)(2 * y + 1) * sw + 2 * x], d = s[(size_t)(2 * y + 1) * sw + 2 * x + 1];
+    auto avg = [](uint32_t p, uint32_t q, uint32_t r, uint32_t t) {
+        uint32_t sum = p + q + r + t, v = sum >> 2, rem = sum & 3;
+        if (rem > 2 || (rem == 2 && (v & 1))) v++;
+        return (unsigned char)v;
+    };
+    uchar4 o = make_uchar4(avg(a.x, b.x, cc.x, d.x), avg(a.y, b.y, cc.y, d.y), avg(a.z, b.z, cc.z, d.z), avg(a.w, b.w, cc.w, d.w));
+    reinterpret_cast<uchar4*>(dst)[(size_t)y * dw + x] = o;
+}
+
+int f184_sync_tables(f184_ctx* c)
+{
+    if (!c->tables_dirty) return F184_OK;
+    if (c->tex_host.size() > c->tex_dev_cap)
+    {
+        if (c->tex_dev) cudaFree(c->tex_dev);
+        c->tex_dev_cap = (uint32_t)c->tex_host.size() + 16;
+        CK(c, cudaMalloc(&c->tex_dev, sizeof(TexDev) * c->tex_dev_cap));
+    }
+    if (c->mat_host.size() > c->mat_dev_cap)
+    {
+        if (c->mat_dev) cudaFree(c->mat_dev);
+        c->mat_dev_cap = (uint32_t)c->mat_host.size() + 16;
+        CK(c, cudaMalloc(&c->mat_dev, sizeof(MatDev) * c->mat_dev_cap));
+    }
+    if (!c->tex_host.empty()) CK(c, cudaMemcpy(c->tex_dev, c->tex_host.data(), sizeof(TexDev) * c->tex_host.size(), cudaMemcpyHostToDevice));
+    if (!c->mat_host.empty()) CK(c, cudaMemcpy(c->mat_dev, c->mat_host.data(), sizeof(MatDev) * c->mat_host.size(), cudaMemcpyHostToDevice));
+    c->tables_dirty = false;
+    return F184_OK;
+}
+
+extern "C" {
+
+int f184_abi_version(void) { return F184_ABI_VERSION; }
+
+int f184_create(const f184_config* config, f184_ctx** out)
+{
+    if (!config || !out || config->struct_size != sizeof(f184_config)) return f184_fail(nullptr, F184_ERR_INVALID_ARGUMENT, "bad config");
+    const uint32_t n = config->grid_n;
+    if (n < 8 || n > 1024 || (n & (n - 1))) return f184_fail(nullptr, F184_ERR_INVALID_ARGUMENT, "grid_n must be a power of two in [8,1024]");
+    if (!config->width || !config->height) return f184_fail(nullptr, F184_ERR_INVALID_ARGUMENT, "width/height must be non-zero");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return f184_fail(nullptr, F184_ERR_NO_DEVICE, "no CUDA device (%s); libf184 has no CPU fallback", cudaGetErrorString(e));
+    if (config->device < 0 || config->device >= ndev) return f184_fail(nullptr, F184_ERR_INVALID_ARGUMENT, "device %d out of range", config->device);
+    e = cudaSetDevice(config->device);
+    if (e != cudaSuccess) return f184_fail(nullptr, F184_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    f184_ctx* c = new f184_ctx();
+    c->cfg = *config;
+    if (c->cfg.march_steps == 0) c->cfg.march_steps = 60;
+    if (c->cfg.step_size == 0.f) c->cfg.step_size = 0.2f;
+    if (c->cfg.shadow_res == 0) c->cfg.shadow_res = 2048;
+    if (c->cfg.cone_max_distance == 0.f) c->cfg.cone_max_distance = 32.f;
+    if (c->cfg.radiance_exposure == 0.f) c->cfg.radiance_exposure = 8.f;
+    if (c->cfg.nranks == 0) c->cfg.nranks = 1;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        delete c;
+        return f184_fail(nullptr, F184_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    c->stream = c->own_stream;
+    for (int s = 0; s < F184_STAGE_COUNT; s++) { cudaEventCreate(&c->ev[s][0]); cudaEventCreate(&c->ev[s][1]); }
+    if (cudaMalloc(&c->counters_dev, sizeof(unsigned long long) * F184_COUNTER_COUNT) != cudaSuccess)
+    {
+        delete c;
+        return f184_fail(nullptr, F184_ERR_OUT_OF_MEMORY, "cudaMalloc counters");
+    }
+    cudaMemset(c->counters_dev, 0, sizeof(unsigned long long) * F184_COUNTER_COUNT);
+    *out = c;
+    return F184_OK;
+}
+
+void f184_destroy(f184_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    cudaStreamSynchronize(c->stream);
+    f184_mode_n_release(c);
+    for (auto& im : c->img)
+    {
+        if (im.owned && im.ptr) cudaFree(im.ptr);
+        if (im.ext) { if (im.ptr) cudaFree(im.ptr); cudaDestroyExternalMemory(im.ext); }
+    }
+    for (void* p : {(void*)c->pos, (void*)c->nrm, (void*)c->uv, (void*)c->model_mats, (void*)c->idx, (void*)c->tri_mat,
+                    (void*)c->tri_model, (void*)c->tex_dev, (void*)c->mat_dev, (void*)c->vox_keys, (void*)c->counters_dev,
+                    (void*)c->brick_prev})
+        if (p) cudaFree(p);
+    for (uint8_t* p : c->tex_alloc) if (p) cudaFree(p);
+    for (int s = 0; s < F184_STAGE_COUNT; s++) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
+    if (c->sem_wait) cudaDestroyExternalSemaphore(c->sem_wait);
+    if (c->sem_signal) cudaDestroyExternalSemaphore(c->sem_signal);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* f184_last_error(const f184_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int f184_scene_upload(f184_ctx* c, const f184_scene_desc* s)
+{
+    if (!c || !s || !s->positions || !s->normals || !s->uvs || !s->indices || !s->tri_material || !s->tri_model || !s->model_mats)
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "scene_upload: null argument");
+    if (!s->n_tris || !s->n_verts || !s->n_models) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "scene_upload: empty scene");
+    for (uint64_t i = 0; i < 3ull * s->n_tris; i++)
+        if (s->indices[i] >= s->n_verts) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "scene_upload: index %llu out of range", (unsigned long long)i);
+    for (uint32_t i = 0; i < s->n_tris; i++)
+        if (s->tri_model[i] >= s->n_models) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "scene_upload: tri_model out of range");
+    CK(c, cudaSetDevice(c->cfg.device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (void* p : {(void*)c->pos, (void*)c->nrm, (void*)c->uv, (void*)c->model_mats, (void*)c->idx, (void*)c->tri_mat, (void*)c->tri_model})
+        if (p) cudaFree(p);
+    auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    CK(c, up((void**)&c->pos, s->positions, 12ull * s->n_verts));
+    CK(c, up((void**)&c->nrm, s->normals, 12ull * s->n_verts));
+    CK(c, up((void**)&c->uv, s->uvs, 8ull * s->n_verts));
+    CK(c, up((void**)&c->idx, s->indices, 12ull * s->n_tris));
+    CK(c, up((void**)&c->tri_mat, s->tri_material, 2ull * s->n_tris));
+    CK(c, up((void**)&c->tri_model, s->tri_model, 2ull * s->n_tris));
+    CK(c, up((void**)&c->model_mats, s->model_mats, 64ull * s->n_models));
+    c->model_mats_host.resize(s->n_models);
+    memcpy(c->model_mats_host.data(), s->model_mats, 64ull * s->n_models);
+    c->n_verts = s->n_verts; c->n_tris = s->n_tris; c->n_models = s->n_models;
+    return F184_OK;
+}
+
+int f184_texture_upload(f184_ctx* c, uint32_t id, const uint8_t* rgba, uint32_t w, uint32_t h)
+{
+    if (!c || !rgba || !w || !h || (w & (w - 1)) || (h & (h - 1)) || id > 65535)
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "texture_upload: need power-of-two RGBA8 image");
+    CK(c, cudaSetDevice(c->cfg.device));
+    if (c->tex_host.size() <= id) { c->tex_host.resize(id + 1, TexDev{}); c->tex_alloc.resize(id + 1, nullptr); }
+    TexDev t{};
+    t.w = w; t.h = h;
+    uint32_t nl = 1;
+    for (uint32_t m = (w < h ? w : h); m > 1; m >>= 1) nl++;      // DeviceVk.cpp:504-509
+    if (nl > F184_MAX_TEX_LEVELS) nl = F184_MAX_TEX_LEVELS;
+    t.nlevels = nl;
+    uint64_t total = 0;
+    for (uint32_t l = 0; l < nl; l++)
+    {
+        t.off[l] = (uint32_t)total;
+        total += 4ull * ((w >> l) ? (w >> l) : 1) * ((h >> l) ? (h >> l) : 1);
+    }
+    uint8_t* dev = nullptr;
+    CK(c, cudaMalloc(&dev, total));
+    CK(c, cudaMemcpyAsync(dev, rgba, 4ull * w * h, cudaMemcpyHostToDevice, c->stream));
+    uint32_t sw = w, sh = h;
+    for (uint32_t l = 1; l < nl; l++)
+    {
+        uint32_t dw = sw > 1 ? sw / 2 : 1, dh = sh > 1 ? sh / 2 : 1;
+        dim3 b(16, 16), g((dw + 15) / 16, (dh + 15) / 16);
+        k_tex_downsample<<<g, b, 0, c->stream>>>(dev + t.off[l - 1], dev + t.off[l], sw, dw, dh);
+        CK_LAUNCH(c);
+        sw = dw; sh = dh;
+    }
+    CK(c, cudaStreamSynchronize(c->stream));     // `rgba` may be freed by the caller on return
+    if (c->tex_alloc[id]) cudaFree(c->tex_alloc[id]);
+    c->tex_alloc[id] = dev;
+    t.base = dev;
+    c->tex_host[id] = t;
+    c->tables_dirty = true;
+    return F184_OK;
+}
+
+int f184_texture_readback(f184_ctx* c, uint32_t id, uint32_t level, uint8_t* out, size_t bytes)
+{
+    if (!c || id >= c->tex_host.size() || !c->tex_host[id].base || level >= c->tex_host[id].nlevels)
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "texture_readback: bad id/level");
+    const TexDev& t = c->tex_host[id];
+    size_t want = 4ull * ((t.w >> level) ? (t.w >> level) : 1) * ((t.h >> level) ? (t.h >> level) : 1);
+    if (bytes != want) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "texture_readback: size mismatch");
+    CK(c, cudaMemcpy(out, t.base + t.off[level], bytes, cudaMemcpyDeviceToHost));
+    return F184_OK;
+}
+
+int f184_material_set(f184_ctx* c, uint32_t id, const float factor[4], int32_t tex, uint32_t use_textures)
+{
+    if (!c || !factor || id > 65535) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "material_set: bad argument");
+    if (c->mat_host.size() <= id) c->mat_host.resize(id + 1, MatDev{{1, 1, 1, 1}, -1, 1});
+    MatDev m;
+    memcpy(m.factor, factor, 16);
+    m.tex = tex; m.use_textures = use_textures;
+    c->mat_host[id] = m;
+    c->tables_dirty = true;
+    return F184_OK;
+}
+
+int f184_bind_image(f184_ctx* c, uint32_t slot, const f184_image_desc* d)
+{
+    if (!c || slot >= F184_SLOT_COUNT || !d) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "bind_image: bad argument");
+    f184_image_desc want;
+    default_desc(c->cfg, slot, &want);
+    DevImage& im = c->img[slot];
+    if (d->device_ptr == nullptr)
+    {   // unbind: back to a context-owned image on next use
+        if (im.owned && im.ptr) return F184_OK;
+        im = DevImage{};
+        return F184_OK;
+    }
+    if (d->format != want.format || d->width != want.width || d->height != want.height || d->depth != want.depth)
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "bind_image: slot %u expects format %u %ux%ux%u", slot, want.format, want.width, want.height, want.depth);
+    if (d->row_pitch_bytes != 0 && d->row_pitch_bytes != want.row_pitch_bytes)
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "bind_image: only tightly packed rows are supported");
+    if (im.owned && im.ptr) { cudaStreamSynchronize(c->stream); cudaFree(im.ptr); }
+    im.ptr = d->device_ptr;
+    im.owned = false;
+    im.desc = want;
+    im.desc.device_ptr = d->device_ptr;
+    return F184_OK;
+}
+
+int f184_image_info(f184_ctx* c, uint32_t slot, f184_image_desc* out)
+{
+    if (!c || slot >= F184_SLOT_COUNT || !out) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "image_info: bad argument");
+    int rc = f184_ensure_image(c, slot);
+    if (rc) return rc;
+    *out = c->img[slot].desc;
+    return F184_OK;
+}
+
+int f184_upload_image(f184_ctx* c, uint32_t slot, const void* host, size_t bytes)
+{
+    if (!c || slot >= F184_SLOT_COUNT || !host) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "upload_image: bad argument");
+    int rc = f184_ensure_image(c, slot);
+    if (rc) return rc;
+    if (bytes != c->img[slot].desc.size_bytes) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "upload_image: slot %u is %llu bytes, got %zu", slot, (unsigned long long)c->img[slot].desc.size_bytes, bytes);
+    CK(c, cudaMemcpyAsync(c->img[slot].ptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    return F184_OK;
+}
+
+int f184_readback_async(f184_ctx* c, uint32_t slot, void* host, size_t bytes)
+{
+    if (!c || slot >= F184_SLOT_COUNT || !host) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "readback: bad argument");
+    int rc = f184_ensure_image(c, slot);
+    if (rc) return rc;
+    if (bytes > c->img[slot].desc.size_bytes) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "readback: slot %u is %llu bytes, got %zu", slot, (unsigned long long)c->img[slot].desc.size_bytes, bytes);
+    CK(c, cudaMemcpyAsync(host, c->img[slot].ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return F184_OK;
+}
+
+int f184_readback(f184_ctx* c, uint32_t slot, void* host, size_t bytes)
+{
+    if (c && slot < F184_SLOT_COUNT && c->img[slot].ptr && bytes != c->img[slot].desc.size_bytes)
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "readback: slot %u is %llu bytes, got %zu", slot, (unsigned long long)c->img[slot].desc.size_bytes, bytes);
+    int rc = f184_readback_async(c, slot, host, bytes);
+    if (rc) return rc;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return F184_OK;
+}
+
+// ---- Vulkan interop: exported VkDeviceMemory / VkSemaphore file descriptors ----------------------
+int f184_import_external_memory_fd(f184_ctx* c, uint32_t slot, int fd, uint64_t alloc_size, uint64_t offset, const f184_image_desc* layout)
+{
+    if (!c || slot >= F184_SLOT_COUNT || fd < 0 || !layout) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "import_external_memory_fd: bad argument");
+    f184_image_desc want;
+    default_desc(c->cfg, slot, &want);
+    if (layout->format != want.format || layout->width != want.width || layout->height != want.height || layout->depth != want.depth)
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "import_external_memory_fd: layout does not match slot %u", slot);
+    if (offset + want.size_bytes > alloc_size) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "import_external_memory_fd: allocation too small");
+    cudaExternalMemoryHandleDesc hd{};
+    hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+    hd.handle.fd = fd;
+    hd.size = alloc_size;
+    cudaExternalMemory_t ext = nullptr;
+    CK(c, cudaImportExternalMemory(&ext, &hd));
+    cudaExternalMemoryBufferDesc bd{};
+    bd.offset = offset;
+    bd.size = want.size_bytes;
+    void* ptr = nullptr;
+    cudaError_t e = cudaExternalMemoryGetMappedBuffer(&ptr, ext, &bd);
+    if (e != cudaSuccess) { cudaDestroyExternalMemory(ext); return f184_fail(c, F184_ERR_CUDA, "cudaExternalMemoryGetMappedBuffer: %s", cudaGetErrorString(e)); }
+    DevImage& im = c->img[slot];
+    if (im.owned && im.ptr) { cudaStreamSynchronize(c->stream); cudaFree(im.ptr); }
+    im.ptr = ptr; im.owned = false; im.ext = ext; im.desc = want; im.desc.device_ptr = ptr;
+    return F184_OK;
+}
+
+int f184_import_semaphores_fd(f184_ctx* c, int wait_fd, int signal_fd)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    auto imp = [&](int fd, cudaExternalSemaphore_t* out) -> cudaError_t {
+        cudaExternalSemaphoreHandleDesc d{};
+        d.type = cudaExternalSemaphoreHandleTypeOpaqueFd;
+        d.handle.fd = fd;
+        return cudaImportExternalSemaphore(out, &d);
+    };
+    if (wait_fd >= 0) CK(c, imp(wait_fd, &c->sem_wait));
+    if (signal_fd >= 0) CK(c, imp(signal_fd, &c->sem_signal));
+    return F184_OK;
+}
+
+int f184_frame_begin(f184_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    if (c->sem_wait)
+    {
+        cudaExternalSemaphoreWaitParams p{};
+        CK(c, cudaWaitExternalSemaphoresAsync(&c->sem_wait, &p, 1, c->stream));
+    }
+    return F184_OK;
+}
+int f184_frame_end(f184_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    if (c->sem_signal)
+    {
+        cudaExternalSemaphoreSignalParams p{};
+        CK(c, cudaSignalExternalSemaphoresAsync(&c->sem_signal, &p, 1, c->stream));
+    }
+    return F184_OK;
+}
+
+int f184_set_stream(f184_ctx* c, void* s)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(c->stream);
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return F184_OK;
+}
+int f184_sync(f184_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return F184_OK;
+}
+
+// ---- passes (dispatch on mode) ------------------------------------------------------------------
+int f184_voxelize(f184_ctx* c, const f184_view_constants* cam)
+{
+    if (!c || !cam) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "voxelize: null argument");
+    if (!c->n_tris) return f184_fail(c, F184_ERR_NOT_READY, "voxelize: no scene uploaded");
+    CK(c, cudaSetDevice(c->cfg.device));
+    int rc = f184_sync_tables(c);
+    if (rc) return rc;
+    return c->cfg.mode == F184_MODE_REFERENCE ? f184_voxelize_r(c, cam) : f184_voxelize_n(c, cam);
+}
+int f184_inject(f184_ctx* c, const f184_sun* sun, const f184_extended_matrices* m)
+{
+    if (!c || !sun || !m) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "inject: null argument");
+    if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "inject is a north-star stage");
+    CK(c, cudaSetDevice(c->cfg.device));
+    return f184_inject_n(c, sun, m);
+}
+int f184_build_mips(f184_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "mips are a north-star stage");
+    CK(c, cudaSetDevice(c->cfg.device));
+    return f184_mips_n(c);
+}
+int f184_trace_indirect(f184_ctx* c, const f184_trace_constants* k)
+{
+    if (!c || !k) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "trace_indirect: null argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    return c->cfg.mode == F184_MODE_REFERENCE ? f184_trace_r(c, k) : f184_trace_n(c, k);
+}
+int f184_gtao(f184_ctx* c, const f184_view_constants* view)
+{
+    if (!c || !view) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "gtao: null argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    return f184_gtao_impl(c, view);
+}
+int f184_blur_indirect(f184_ctx* c, const f184_engine_miscs* miscs)
+{
+    if (!c || !miscs) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "blur_indirect: null argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    return f184_blur_impl(c, miscs);
+}
+int f184_copy_indirect_to_history(f184_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    int rc = f184_ensure_image(c, F184_SLOT_INDIRECT_OUT); if (rc) return rc;
+    rc = f184_ensure_image(c, F184_SLOT_INDIRECT_HISTORY); if (rc) return rc;
+    CK(c, cudaMemcpyAsync(c->img[F184_SLOT_INDIRECT_HISTORY].ptr, c->img[F184_SLOT_INDIRECT_OUT].ptr,
+                          c->img[F184_SLOT_INDIRECT_OUT].desc.size_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return F184_OK;
+}
+int f184_bind_rands(f184_ctx* c, const float* r, size_t n)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    c->rands = r; c->n_rands = n;
+    return F184_OK;
+}
+int f184_set_triangle_range(f184_ctx* c, uint32_t first, uint32_t count)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    c->tri_first = first; c->tri_count = count;
+    return F184_OK;
+}
+int f184_set_trace_rows(f184_ctx* c, uint32_t y0, uint32_t y1)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    c->row0 = y0; c->row1 = y1;
+    return F184_OK;
+}
+
+int f184_stage_time_ms(f184_ctx* c, uint32_t stage, float* ms)
+{
+    if (!c || stage >= F184_STAGE_COUNT || !ms) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "stage_time_ms: bad argument");
+    if (!c->ev_valid[stage]) { *ms = 0.f; return F184_OK; }
+    CK(c, cudaEventSynchronize(c->ev[stage][1]));
+    CK(c, cudaEventElapsedTime(ms, c->ev[stage][0], c->ev[stage][1]));
+    return F184_OK;
+}
+int f184_counter_get(f184_ctx* c, uint32_t which, uint64_t* v)
+{
+    if (!c || which >= F184_COUNTER_COUNT || !v) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "counter_get: bad argument");
+    if (which == F184_COUNTER_KERNEL_LAUNCHES) { *v = c->launches; return F184_OK; }
+    unsigned long long t = 0;
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaMemcpy(&t, c->counters_dev + which, sizeof(t), cudaMemcpyDeviceToHost));
+    *v = t;
+    return F184_OK;
+}
+
+}  // extern "C"

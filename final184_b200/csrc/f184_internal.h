@@ -1,0 +1,140 @@
+// f184_internal.h — context and helpers shared by the libf184 translation units (not installed).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/f184.h"
+
+#define F184_MAX_TEX_LEVELS 12
+
+// Device-side descriptors -------------------------------------------------------------------------
+struct TexDev
+{
+    const uint8_t* base;                    // RGBA8, all levels back to back
+    uint32_t w, h, nlevels;
+    uint32_t off[F184_MAX_TEX_LEVELS];      // byte offset of each level
+};
+struct MatDev
+{
+    float factor[4];
+    int32_t tex;
+    uint32_t use_textures;
+};
+// mat4 in upload order (column-major): m[c*4+r]
+struct M4 { float m[16]; };
+
+struct DevImage
+{
+    void* ptr = nullptr;
+    bool owned = false;
+    f184_image_desc desc{};
+    cudaExternalMemory_t ext = nullptr;
+};
+
+struct MipLevelInfo
+{
+    uint32_t n;               // edge of this level
+    uint64_t offset_texels;   // offset of direction 0 inside F184_SLOT_MIPS (directions are consecutive)
+};
+
+struct f184_ctx
+{
+    f184_config cfg{};
+    std::string err;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    // scene (device)
+    float *pos = nullptr, *nrm = nullptr, *uv = nullptr;
+    M4* model_mats = nullptr;
+    uint32_t* idx = nullptr;
+    uint16_t *tri_mat = nullptr, *tri_model = nullptr;
+    uint32_t n_verts = 0, n_tris = 0, n_models = 0;
+    std::vector<M4> model_mats_host;
+    // textures / materials
+    std::vector<TexDev> tex_host;
+    std::vector<uint8_t*> tex_alloc;
+    std::vector<MatDev> mat_host;
+    TexDev* tex_dev = nullptr;
+    MatDev* mat_dev = nullptr;
+    bool tables_dirty = true;
+    uint32_t tex_dev_cap = 0, mat_dev_cap = 0;
+    // images
+    DevImage img[F184_SLOT_COUNT];
+    // mode R: ordered-store keys, (draw order + 1) << 32 | texel
+    unsigned long long* vox_keys = nullptr;
+    // mode N
+    std::vector<MipLevelInfo> mip_levels;     // index 0 = level 1
+    cudaArray_t rad_array = nullptr;          // level-0 radiance as a 3D array for hardware filtering
+    cudaMipmappedArray_t dir_arrays[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaTextureObject_t rad_tex = 0, dir_tex[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t* brick_prev = nullptr;           // bricks written last frame (to clear what became empty)
+    // sharding
+    uint32_t tri_first = 0, tri_count = 0xffffffffu;
+    uint32_t row0 = 0, row1 = 0xffffffffu;
+    const float* rands = nullptr;
+    size_t n_rands = 0;
+    // measurement
+    unsigned long long* counters_dev = nullptr;   // F184_COUNTER_COUNT
+    uint64_t launches = 0;
+    cudaEvent_t ev[F184_STAGE_COUNT][2] = {};
+    bool ev_valid[F184_STAGE_COUNT] = {};
+    // interop
+    cudaExternalSemaphore_t sem_wait = nullptr, sem_signal = nullptr;
+};
+
+// Error plumbing ----------------------------------------------------------------------------------
+int f184_fail(f184_ctx* c, int code, const char* fmt, ...);
+#define CK(c, call)                                                                                         \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            return f184_fail((c), e__ == cudaErrorMemoryAllocation ? F184_ERR_OUT_OF_MEMORY : F184_ERR_CUDA, \
+                             "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));           \
+    } while (0)
+#define CK_LAUNCH(c)                                                                                        \
+    do {                                                                                                    \
+        (c)->launches++;                                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                                               \
+        if (e__ != cudaSuccess)                                                                             \
+            return f184_fail((c), F184_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    } while (0)
+
+int f184_ensure_image(f184_ctx* c, int slot);
+int f184_sync_tables(f184_ctx* c);
+int f184_stage_begin(f184_ctx* c, int stage);
+int f184_stage_end(f184_ctx* c, int stage);
+template <class T> static inline T* img_ptr(f184_ctx* c, int slot) { return reinterpret_cast<T*>(c->img[slot].ptr); }
+
+static inline M4 host_matmul(const M4& A, const M4& B)
+{
+    // same association as the GLSL `A * B` then `M * v`: C[:,j] = A * B[:,j], each row ((a0*x + a1*y) + a2*z) + a3*w
+    M4 C;
+    for (int j = 0; j < 4; j++)
+        for (int r = 0; r < 4; r++)
+        {
+            volatile float t0 = A.m[0 + r] * B.m[4 * j + 0];
+            volatile float t1 = A.m[4 + r] * B.m[4 * j + 1];
+            volatile float t2 = A.m[8 + r] * B.m[4 * j + 2];
+            volatile float t3 = A.m[12 + r] * B.m[4 * j + 3];
+            volatile float s = t0 + t1;
+            s = s + t2;
+            s = s + t3;
+            C.m[4 * j + r] = s;
+        }
+    return C;
+}
+
+// pass implementations (one per translation unit)
+int f184_voxelize_r(f184_ctx* c, const f184_view_constants* cam);
+int f184_trace_r(f184_ctx* c, const f184_trace_constants* k);
+int f184_gtao_impl(f184_ctx* c, const f184_view_constants* view);
+int f184_blur_impl(f184_ctx* c, const f184_engine_miscs* miscs);
+int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam);
+int f184_inject_n(f184_ctx* c, const f184_sun* sun, const f184_extended_matrices* m);
+int f184_mips_n(f184_ctx* c);
+int f184_trace_n(f184_ctx* c, const f184_trace_constants* k);
+int f184_mode_n_release(f184_ctx* c);

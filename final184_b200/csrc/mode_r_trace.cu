@@ -1,0 +1,279 @@
+// mode_r_trace.cu — reference-faithful indirect pass (F184_MODE_REFERENCE).
+//
+// Replaces the lighting_indirect full-screen pass (Foreground/Renderer/MegaPipeline.cpp:252-268), i.e.
+// Shader/Lighting/indirect.frag: per pixel 4 cosine-weighted hemisphere rays, each with an optional second
+// bounce, each a 60-step fixed-step march through the RG16UI voxel volume with first-hit termination, a
+// shadow-map lookup at the hit, then the temporal reprojection blend.  Noise is Shader/math.inc:83-87,
+// 107-110, 189-194, 214-219 evaluated with f184_detmath.h (see that header for why).
+//
+// B200 design: one thread per pixel, warps own 8x4 pixel tiles so the rays of a warp start from
+// neighbouring surface points and walk through neighbouring voxels (the 8 MiB..512 MiB volume is served
+// by L2/L1, 4-byte nearest fetches only when the integer voxel changes, as in the shader).  The march
+// itself is ALU: the affine world->voxel transform is applied per step exactly as the shader does (the
+// arithmetic order is part of the parity contract), so the kernel is bound by fp32 issue rate and by the
+// divergence of first-hit termination; the warp leaves a march as soon as every lane has hit, left the
+// volume or run out of steps (hardware reconvergence of the loop exit = the vote the shader cannot do).
+#include "f184_device.cuh"
+
+namespace {
+
+struct TraceParams
+{
+    M4 InvProj, InvModelView, ShadowView, ShadowProj, w2voxel, prevModelView, prevProjection;
+    const float* depth;
+    const uint16_t* normals;
+    const float* shadow;
+    const uint32_t* vox;
+    const uint16_t* hist;
+    uint16_t* out;
+    const float* rands;
+    uint32_t W, H, S, N, steps, y0, y1;
+    float step_size, iiTime, resx, resy;
+    f3 sunLum, sunPos;
+};
+
+// math.inc:83-87
+__device__ __forceinline__ float glsl_hash(float px, float py)
+{
+    float p3x = dm_fract(px * 0.2031f), p3y = dm_fract(py * 0.2031f), p3z = dm_fract(px * 0.2031f);
+    float d = (p3x * (p3y + 19.19f) + p3y * (p3z + 19.19f)) + p3z * (p3x + 19.19f);
+    p3x += d; p3y += d; p3z += d;
+    return dm_fract((p3x + p3y) * p3z);
+}
+// math.inc:107-110
+__device__ __forceinline__ float nrand(float nx, float ny) { return dm_fract(dm_sin(nx * 12.9898f + ny * 78.233f) * 43758.5453f); }
+// math.inc:189-194
+__device__ __forceinline__ float n4rand_ss(float nx, float ny, float t0, float t1)
+{
+    float nrnd0 = nrand(nx + t0, ny + t0);
+    float nrnd1 = nrand(nx + t1, ny + t1);
+    return 0.23f * __fsqrt_rn(-dm_log(nrnd0 + 0.00001f)) * dm_cos(2.0f * 3.141592f * nrnd1) + 0.5f;
+}
+// math.inc:214-219
+__device__ __forceinline__ float blugausnoise2(float cx, float cy, float t0, float t1)
+{
+    float nrand1 = n4rand_ss(cx, cy, t0, t1);
+    float nrand0 = n4rand_ss(cx - 1.0f, cy, t0, t1);
+    float nrand2 = n4rand_ss(cx + 1.0f, cy, t0, t1);
+    return 2.0f * nrand1 - 0.5f * (nrand0 + nrand2);
+}
+
+struct Hit { f3 wpos, wnorm, brdf; bool hit; };
+
+__device__ __forceinline__ f3 voxel_pos(const M4& w2v, f3 p, float Nf)
+{
+    f3 v = mul43(w2v, p, 1.0f);
+    return {(v.x * 0.5f + 0.5f) * Nf, (v.y * 0.5f + 0.5f) * Nf, v.z * Nf};
+}
+
+// indirect.frag:104-184
+__device__ f3 get_indirect(const TraceParams& P, f3 wpos, f3 wnorm, float seed, float uvx, float uvy, const float* ext,
+                           Hit& hit, unsigned int& steps_taken)
+{
+    hit.hit = false;
+    f3 Lo = {0.f, 0.f, 0.f};
+    const float step_size = P.step_size;
+    float rx, ry;
+    if (ext) { rx = ext[0]; ry = ext[1]; }
+    else
+    {
+        const float t0 = 0.07f * dm_fract(P.iiTime), t1 = 0.11f * dm_fract(P.iiTime + 0.573953f);
+        float ra = glsl_hash(seed, seed);
+        float ax = (uvx + ra) * P.resx, ay = (uvy + ra) * P.resy;
+        rx = blugausnoise2(-ax, -ay, t0, t1);
+        ry = blugausnoise2(ax, ay, t0, t1);
+    }
+    // hemisphereSample_cos, math.inc:76-81
+    float phi = ry * 2.0f * 3.1415926f;
+    float cosTheta = __fsqrt_rn(1.0f - rx);
+    float sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
+    f3 d = {dm_cos(phi) * sinTheta, dm_sin(phi) * sinTheta, cosTheta};
+    // make_coord_space, indirect.frag:71-86
+    f3 z = wnorm, h = wnorm;
+    if (fabsf(h.x) <= fabsf(h.y) && fabsf(h.x) <= fabsf(h.z)) h.x = 1.0f;
+    else if (fabsf(h.y) <= fabsf(h.x) && fabsf(h.y) <= fabsf(h.z)) h.y = 1.0f;
+    else h.z = 1.0f;
+    z = normalize3(z);
+    f3 y = normalize3(cross3(h, z));
+    f3 x = normalize3(cross3(z, y));
+    f3 dir = {(x.x * d.x + y.x * d.y) + z.x * d.z, (x.y * d.x + y.y * d.y) + z.y * d.z, (x.z * d.x + y.z * d.y) + z.z * d.z};
+    if (dot3(dir, wnorm) < 0.0f) dir = neg3(dir);
+    const float NdotD = dot3(dir, wnorm);
+    const float s1 = 1.0f + ry;
+    f3 march_pos = {wpos.x + dir.x * s1 * step_size / NdotD, wpos.y + dir.y * s1 * step_size / NdotD, wpos.z + dir.z * s1 * step_size / NdotD};
+
+    const float Nf = (float)P.N, hi = (float)(P.N - 1);
+    f3 sv = voxel_pos(P.w2voxel, wpos, Nf);
+    int pvx = dm_f2i(sv.x), pvy = dm_f2i(sv.y), pvz = dm_f2i(sv.z);
+    uint32_t i = 0;
+    for (; i < P.steps; i++)
+    {
+        steps_taken++;
+        march_pos = {march_pos.x + dir.x * step_size, march_pos.y + dir.y * step_size, march_pos.z + dir.z * step_size};
+        f3 vp = voxel_pos(P.w2voxel, march_pos, Nf);
+        if (vp.x < 0.f || vp.y < 0.f || vp.z < 0.f || vp.x > hi || vp.y > hi || vp.z > hi) break;
+        const int ix = dm_f2i(vp.x), iy = dm_f2i(vp.y), iz = dm_f2i(vp.z);       // NaN -> 0
+        if (pvx != ix || pvy != iy || pvz != iz)
+        {
+            uint32_t texel = 0;
+            if (ix >= 0 && iy >= 0 && iz >= 0 && ix < (int)P.N && iy < (int)P.N && iz < (int)P.N)
+                texel = __ldg(P.vox + (((size_t)iz * P.N + iy) * P.N + ix));
+            pvx = ix; pvy = iy; pvz = iz;
+            const uint32_t r = texel & 0xffffu, g = texel >> 16;
+            if (r != 0)
+            {
+                f3 col = {dm_pow((float)((r & 0xF800u) >> 11) / 31.0f, 2.2f), dm_pow((float)((r & 0x7E0u) >> 5) / 63.0f, 2.2f),
+                          dm_pow((float)(r & 0x1Fu) / 31.0f, 2.2f)};
+                f3 vn = normalize3(f3{(float)(g & 0x1Fu) / 16.0f - 1.0f, (float)((g & 0x7E0u) >> 5) / 32.0f - 1.0f,
+                                      (float)((g & 0xF800u) >> 11) / 16.0f - 1.0f});
+                f3 sp = {march_pos.x + vn.x * 0.06f, march_pos.y + vn.y * 0.06f, march_pos.z + vn.z * 0.06f};
+                f4 sv4 = mul44(P.ShadowProj, mul44(P.ShadowView, f4{sp.x, sp.y, sp.z, 1.0f}));
+                float spx = sv4.x / sv4.w, spy = sv4.y / sv4.w, spz = sv4.z / sv4.w;
+                spx = spx * 0.5f + 0.5f; spy = spy * 0.5f + 0.5f;
+                const int tx = dm_f2i(spx * (float)P.S), ty = dm_f2i(spy * (float)P.S);
+                float shadowZ = 0.0f;
+                if (tx >= 0 && ty >= 0 && tx < (int)P.S && ty < (int)P.S) shadowZ = __ldg(P.shadow + (size_t)ty * P.S + tx);
+                const float shade = dm_step(spz + 0.005f, shadowZ);
+                const float l = fabsf(dot3(neg3(P.sunPos), vn));
+                const float den = dm_max(0.01f, NdotD);
+                f3 rr = {l * col.x / den, l * col.y / den, l * col.z / den};
+                hit.brdf = rr;
+                Lo = {Lo.x + P.sunLum.x * shade * rr.x, Lo.y + P.sunLum.y * shade * rr.y, Lo.z + P.sunLum.z * shade * rr.z};
+                hit.wpos = march_pos; hit.wnorm = vn; hit.hit = true;
+                break;
+            }
+        }
+    }
+    if (!hit.hit && i == P.steps)
+    {
+        const float den = dm_max(0.01f, NdotD);
+        const float sm = dm_smoothstep(0.0f, 0.01f, NdotD);
+        Lo = {Lo.x + 0.7f * 0.4f / den * sm, Lo.y + 0.8f * 0.4f / den * sm, Lo.z + 1.0f * 0.4f / den * sm};
+    }
+    return Lo;
+}
+
+__device__ __forceinline__ float unorm16(uint16_t v) { return (float)v / 65535.0f; }
+__device__ __forceinline__ int wrapn(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
+
+// 128 threads = 2x2 warps of 8x4 pixels -> a 16x8 pixel tile per block
+__global__ void __launch_bounds__(128) k_trace_r(const TraceParams P, unsigned long long* __restrict__ step_counter)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const uint32_t y = P.y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    unsigned int steps_taken = 0;
+    if (x < P.W && y < P.y1)
+    {
+        const uint32_t W = P.W, H = P.H;
+        const float uvx = ((float)x + 0.5f) / (float)W, uvy = ((float)y + 0.5f) / (float)H;
+        // getCSpos, indirect.frag:44-53
+        const int dx = dm_f2i(uvx * (float)W), dy = dm_f2i(uvy * (float)H);
+        const float depth = (dx >= 0 && dy >= 0 && dx < (int)W && dy < (int)H) ? __ldg(P.depth + (size_t)dy * W + dx) : 0.0f;
+        f4 cp = mul44(P.InvProj, f4{uvx * 2.0f - 1.0f, uvy * 2.0f - 1.0f, depth, 1.0f});
+        const f3 cspos = {cp.x / cp.w, cp.y / cp.w, cp.z / cp.w};
+        const f3 wpos = mul43(P.InvModelView, cspos, 1.0f);
+        // getNormal, indirect.frag:55-58 (texel-centre fetch)
+        const ushort4 nq = __ldg(reinterpret_cast<const ushort4*>(P.normals) + (size_t)y * W + x);
+        const f3 raw = {fmaf(unorm16(nq.x), 2.0f, -1.0f), fmaf(unorm16(nq.y), 2.0f, -1.0f), fmaf(unorm16(nq.z), 2.0f, -1.0f)};
+        const f3 csnorm = normalize3(raw);
+        const f3 wnorm = mul33(P.InvModelView, csnorm);
+
+        Hit st;
+        st.hit = false; st.brdf = {0.f, 0.f, 0.f}; st.wpos = {0.f, 0.f, 0.f}; st.wnorm = {0.f, 0.f, 0.f};
+        f3 ind = {0.f, 0.f, 0.f};
+        const float* er = P.rands ? P.rands + 16 * ((size_t)y * W + x) : nullptr;
+#pragma unroll 1
+        for (int pair = 0; pair < 4; pair++)
+        {
+            f3 a = get_indirect(P, wpos, wnorm, (float)(2 * pair), uvx, uvy, er ? er + 4 * pair : nullptr, st, steps_taken);
+            ind = ind + a;
+            if (st.hit)
+            {
+                const f3 brdf = st.brdf, hw = st.wpos, hn = st.wnorm;     // left operand read before the call (indirect.frag:204)
+                f3 b = get_indirect(P, hw, hn, (float)(2 * pair + 1), uvx, uvy, er ? er + 4 * pair + 2 : nullptr, st, steps_taken);
+                ind = ind + brdf * b;
+            }
+        }
+        ind = ind * 0.25f;
+        // temporal reprojection, indirect.frag:225-240
+        f4 pc = mul44(P.prevModelView, f4{wpos.x, wpos.y, wpos.z, 1.0f});
+        f4 pp = mul44(P.prevProjection, pc);
+        float ru = pp.x / pp.w, rv = pp.y / pp.w;
+        ru = ru * 0.5f + 0.5f; rv = rv * 0.5f + 0.5f;
+        if (dm_clamp(ru, 0.0f, 1.0f) == ru && dm_clamp(rv, 0.0f, 1.0f) == rv)
+        {
+            const float fx = ru * (float)W - 0.5f, fy = rv * (float)H - 0.5f;
+            const float x0f = floorf(fx), y0f = floorf(fy);
+            const float wx = fx - x0f, wy = fy - y0f;
+            const int xi0 = dm_f2i(x0f), yi0 = dm_f2i(y0f);
+            const int xa = wrapn(xi0, (int)W), xb = wrapn(xi0 + 1, (int)W), ya = wrapn(yi0, (int)H), yb = wrapn(yi0 + 1, (int)H);
+            const ushort4 h00 = __ldg(reinterpret_cast<const ushort4*>(P.hist) + (size_t)ya * W + xa);
+            const ushort4 h10 = __ldg(reinterpret_cast<const ushort4*>(P.hist) + (size_t)ya * W + xb);
+            const ushort4 h01 = __ldg(reinterpret_cast<const ushort4*>(P.hist) + (size_t)yb * W + xa);
+            const ushort4 h11 = __ldg(reinterpret_cast<const ushort4*>(P.hist) + (size_t)yb * W + xb);
+            auto bil = [&](uint16_t a, uint16_t b, uint16_t c, uint16_t d) {
+                const float fa = dm_f16_to_f32(a), fb = dm_f16_to_f32(b), fc = dm_f16_to_f32(c), fd = dm_f16_to_f32(d);
+                return (fa * (1.0f - wx) + fb * wx) * (1.0f - wy) + (fc * (1.0f - wx) + fd * wx) * wy;
+            };
+            const float p0 = bil(h00.x, h10.x, h01.x, h11.x), p1 = bil(h00.y, h10.y, h01.y, h11.y);
+            const float p2 = bil(h00.z, h10.z, h01.z, h11.z), p3 = bil(h00.w, h10.w, h01.w, h11.w);
+            const float bw = 0.95f * dm_smoothstep(0.0f, 1.0f, 1.0f - fabsf(p3 + cspos.z));
+            ind = {dm_clamp(dm_mix(ind.x, p0, bw), 0.0f, 16.0f), dm_clamp(dm_mix(ind.y, p1, bw), 0.0f, 16.0f),
+                   dm_clamp(dm_mix(ind.z, p2, bw), 0.0f, 16.0f)};
+        }
+        ushort4 o = make_ushort4(dm_f32_to_f16(ind.x), dm_f32_to_f16(ind.y), dm_f32_to_f16(ind.z), dm_f32_to_f16(-cspos.z));
+        reinterpret_cast<ushort4*>(P.out)[(size_t)y * W + x] = o;
+    }
+    warp_count_add(step_counter, steps_taken);
+}
+
+}  // namespace
+
+int f184_trace_r(f184_ctx* c, const f184_trace_constants* k)
+{
+    for (int s : {F184_SLOT_DEPTH, F184_SLOT_NORMALS, F184_SLOT_SHADOW, F184_SLOT_VOXELS, F184_SLOT_INDIRECT_OUT, F184_SLOT_INDIRECT_HISTORY})
+    {
+        int rc = f184_ensure_image(c, s);
+        if (rc) return rc;
+    }
+    TraceParams P{};
+    memcpy(P.InvProj.m, k->view.InvProj, 64);
+    memcpy(P.InvModelView.m, k->ext.InvModelView, 64);
+    memcpy(P.ShadowView.m, k->ext.ShadowView, 64);
+    memcpy(P.ShadowProj.m, k->ext.ShadowProj, 64);
+    M4 vp, vv;
+    memcpy(vp.m, k->ext.VoxelProj, 64);
+    memcpy(vv.m, k->ext.VoxelView, 64);
+    P.w2voxel = host_matmul(vp, vv);                                  // indirect.frag:127
+    memcpy(P.prevModelView.m, k->prev.PrevModelView, 64);
+    memcpy(P.prevProjection.m, k->prev.PrevProjection, 64);
+    P.depth = img_ptr<float>(c, F184_SLOT_DEPTH);
+    P.normals = img_ptr<uint16_t>(c, F184_SLOT_NORMALS);
+    P.shadow = img_ptr<float>(c, F184_SLOT_SHADOW);
+    P.vox = img_ptr<uint32_t>(c, F184_SLOT_VOXELS);
+    P.hist = img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_HISTORY);
+    P.out = img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_OUT);
+    P.rands = (c->cfg.flags & F184_FLAG_EXTERNAL_RANDS) ? c->rands : nullptr;
+    P.W = c->cfg.width; P.H = c->cfg.height; P.S = c->cfg.shadow_res; P.N = c->cfg.grid_n; P.steps = c->cfg.march_steps;
+    P.y0 = c->row0 < P.H ? c->row0 : P.H;
+    P.y1 = c->row1 < P.H ? c->row1 : P.H;
+    P.step_size = c->cfg.step_size;
+    P.iiTime = (float)k->miscs.frameCount * 0.03125f;                 // indirect.frag:111
+    P.resx = k->miscs.resolution[0]; P.resy = k->miscs.resolution[1];
+    P.sunLum = {k->sun.luminance[0], k->sun.luminance[1], k->sun.luminance[2]};
+    P.sunPos = {k->sun.position[0], k->sun.position[1], k->sun.position[2]};
+
+    int rc = f184_stage_begin(c, F184_STAGE_TRACE);
+    if (rc) return rc;
+    if (k->reset_history)     // first frame: history cleared (MegaPipeline.cpp:197-204)
+        CK(c, cudaMemsetAsync(c->img[F184_SLOT_INDIRECT_HISTORY].ptr, 0, c->img[F184_SLOT_INDIRECT_HISTORY].desc.size_bytes, c->stream));
+    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_MARCH_STEPS, 0, 8, c->stream));
+    if (P.y1 > P.y0)
+    {
+        dim3 grid((P.W + 15) / 16, (P.y1 - P.y0 + 7) / 8);
+        k_trace_r<<<grid, 128, 0, c->stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+        CK_LAUNCH(c);
+    }
+    return f184_stage_end(c, F184_STAGE_TRACE);
+}

@@ -273,6 +273,10 @@ int f184_set_trace_rows(f184_ctx* ctx, uint32_t y0, uint32_t y1);
 int f184_stage_time_ms(f184_ctx* ctx, uint32_t stage, float* out_ms);   /* last run of the stage; synchronous */
 int f184_counter_get(f184_ctx* ctx, uint32_t which, uint64_t* out_value);    /* synchronous */
 
+/* ---- test hook: evaluate csrc/f184_detmath.h on the device (op: 0 sin, 1 cos, 2 log, 3 log2, 4 exp2,
+ * 5 pow(x,y), 6 f32->f16->f32); host pointers; synchronous */
+int f184_debug_detmath(f184_ctx* ctx, uint32_t op, const float* x, const float* y, float* out, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -279,3 +279,23 @@ int f184o_trace_indirect(f184o_ctx* c, const f184_trace_constants* k)
 }
 
 }  // extern "C"
+
+// ---- test hook: evaluate f184_detmath.h on the host (tests/test_detmath.py) ----------------------
+extern "C" int f184o_debug_detmath(uint32_t op, const float* x, const float* y, float* out, size_t n)
+{
+    for (size_t i = 0; i < n; i++)
+    {
+        switch (op)
+        {
+        case 0: out[i] = dm_sin(x[i]); break;
+        case 1: out[i] = dm_cos(x[i]); break;
+        case 2: out[i] = dm_log(x[i]); break;
+        case 3: out[i] = dm_log2(x[i]); break;
+        case 4: out[i] = dm_exp2(x[i]); break;
+        case 5: out[i] = dm_pow(x[i], y[i]); break;
+        case 6: out[i] = dm_f16_to_f32(dm_f32_to_f16(x[i])); break;
+        default: return F184_ERR_INVALID_ARGUMENT;
+        }
+    }
+    return F184_OK;
+}
