@@ -32,6 +32,7 @@ MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
 STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur"]
 (COUNTER_FRAGMENTS, COUNTER_MARCH_STEPS, COUNTER_OCCUPIED, COUNTER_KERNEL_LAUNCHES, COUNTER_BRICKS) = range(5)
 FLAG_EXTERNAL_RANDS = 1
+FLAG_NO_TMA = 2
 
 (FMT_UNDEFINED, FMT_R32_SFLOAT, FMT_R16G16B16A16_UNORM, FMT_R8G8B8A8_UNORM, FMT_R16G16B16A16_SFLOAT,
  FMT_R16G16_UINT, FMT_R32G32B32A32_SFLOAT, FMT_R8G8B8A8_SNORM, FMT_R32_UINT) = range(9)
@@ -194,7 +195,7 @@ class VoxelGI:
                  march_steps=60, step_size=0.2, flags=0, rank=0, nranks=1, lib: Library | None = None):
         self.lib = lib or load_library()
         self.cfg = Config(C.sizeof(Config), device, mode, grid_n, width, height, shadow_res, march_steps, step_size,
-                          32.0, 8.0, rank, nranks, flags)
+                          32.0, 0.0, rank, nranks, flags)
         self.h = C.c_void_p()
         rc = self.lib.create(C.byref(self.cfg), C.byref(self.h))
         if rc != 0:

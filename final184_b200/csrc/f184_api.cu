@@ -167,7 +167,6 @@ int f184_create(const f184_config* config, f184_ctx** out)
     if (c->cfg.step_size == 0.f) c->cfg.step_size = 0.2f;
     if (c->cfg.shadow_res == 0) c->cfg.shadow_res = 2048;
     if (c->cfg.cone_max_distance == 0.f) c->cfg.cone_max_distance = 32.f;
-    if (c->cfg.radiance_exposure == 0.f) c->cfg.radiance_exposure = 8.f;
     if (c->cfg.nranks == 0) c->cfg.nranks = 1;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
     {
@@ -176,12 +175,12 @@ int f184_create(const f184_config* config, f184_ctx** out)
     }
     c->stream = c->own_stream;
     for (int s = 0; s < F184_STAGE_COUNT; s++) { cudaEventCreate(&c->ev[s][0]); cudaEventCreate(&c->ev[s][1]); }
-    if (cudaMalloc(&c->counters_dev, sizeof(unsigned long long) * F184_COUNTER_COUNT) != cudaSuccess)
+    if (cudaMalloc(&c->counters_dev, sizeof(unsigned long long) * (F184_COUNTER_COUNT + 4)) != cudaSuccess)
     {
         delete c;
         return f184_fail(nullptr, F184_ERR_OUT_OF_MEMORY, "cudaMalloc counters");
     }
-    cudaMemset(c->counters_dev, 0, sizeof(unsigned long long) * F184_COUNTER_COUNT);
+    cudaMemset(c->counters_dev, 0, sizeof(unsigned long long) * (F184_COUNTER_COUNT + 4));
     *out = c;
     return F184_OK;
 }
@@ -199,7 +198,7 @@ void f184_destroy(f184_ctx* c)
     }
     for (void* p : {(void*)c->pos, (void*)c->nrm, (void*)c->uv, (void*)c->model_mats, (void*)c->idx, (void*)c->tri_mat,
                     (void*)c->tri_model, (void*)c->tex_dev, (void*)c->mat_dev, (void*)c->vox_keys, (void*)c->counters_dev,
-                    (void*)c->brick_prev})
+                    (void*)c->brick_prev, (void*)c->brick_list})
         if (p) cudaFree(p);
     for (uint8_t* p : c->tex_alloc) if (p) cudaFree(p);
     for (int s = 0; s < F184_STAGE_COUNT; s++) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }

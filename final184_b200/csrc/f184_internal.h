@@ -72,6 +72,12 @@ struct f184_ctx
     cudaMipmappedArray_t dir_arrays[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaTextureObject_t rad_tex = 0, dir_tex[6] = {0, 0, 0, 0, 0, 0};
     uint32_t* brick_prev = nullptr;           // bricks written last frame (to clear what became empty)
+    uint32_t* brick_list = nullptr;           // bricks processed this frame (touched now or last frame)
+    bool defer_normalise = false;             // multi-GPU: f184_voxelize stops after accumulation
+    cudaSurfaceObject_t rad_surf = 0;
+    cudaSurfaceObject_t dir_surf[6][12] = {};
+    uint32_t n_mip_levels = 0;                // levels >= 1
+    void* tma_maps = nullptr;                 // host array of CUtensorMap (mode_n_mips.cu)
     // sharding
     uint32_t tri_first = 0, tri_count = 0xffffffffu;
     uint32_t row0 = 0, row1 = 0xffffffffu;
@@ -138,3 +144,7 @@ int f184_inject_n(f184_ctx* c, const f184_sun* sun, const f184_extended_matrices
 int f184_mips_n(f184_ctx* c);
 int f184_trace_n(f184_ctx* c, const f184_trace_constants* k);
 int f184_mode_n_release(f184_ctx* c);
+int f184_mode_n_alloc(f184_ctx* c);
+int f184_normalise_n(f184_ctx* c);
+M4 f184_invert_m4(const M4& A);
+float f184_exposure(const f184_ctx* c, const f184_sun* sun);

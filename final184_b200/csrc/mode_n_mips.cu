@@ -1,0 +1,283 @@
+// mode_n_mips.cu — six-direction anisotropic mip chain of the radiance volume (DESIGN.md "Mode N" B.4).
+//
+// The reference has no mip levels at all (Foreground/Renderer/MegaPipeline.cpp:478-482 creates one level and
+// no compute shader exists); this is the north-star stage BASELINE.json names: a bandwidth-bound 2x2x2
+// reduction, one volume per ray direction (+x,-x,+y,-y,+z,-z), "what a ray travelling along d sees":
+//   per 2x2x2 block and axis, each of the 4 columns composites front over back (premultiplied alpha),
+//   the 4 columns are averaged.  Integer arithmetic on the 8-bit texels, so it is bit-exact by construction:
+//       col = f*255 + (255 - f.a)*b          out = (sum of 4 cols + 510) / 1020
+//
+// B200 design (HBM-bound: level 1 reads N^3 texels once and writes 6 x (N/2)^3):
+//   * TMA path (levels whose source edge >= 64): persistent CTAs, one per SM slot, walk output tiles of
+//     32x4x4; the 64x8x8 source box (16 KB) is fetched by ONE cp.async.bulk.tensor.3d into shared memory,
+//     3-stage ring, mbarrier complete_tx; every thread then reduces a 8x2x2 strip into 4 x-adjacent
+//     outputs per direction and writes them as one 16-byte vector store.  Level 1 produces all six
+//     directions from the same tile (the isotropic source is read once).
+//   * the small tail levels (source edge < 64, < 0.1 % of the bytes) use a plain per-thread kernel.
+//   * each output is written twice: to the linear chain (source of the next level's TMA) and through a
+//     surface into the mipmapped 3D arrays the tracer's texture units filter (+12 % write traffic; level 0
+//     is never copied).
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "f184_device.cuh"
+
+namespace {
+
+__device__ __forceinline__ void acc_col(uint32_t f, uint32_t b, uint32_t sum[4])
+{
+    const uint32_t fa = f >> 24, ia = 255u - fa;
+    sum[0] += (f & 0xffu) * 255u + ia * (b & 0xffu);
+    sum[1] += ((f >> 8) & 0xffu) * 255u + ia * ((b >> 8) & 0xffu);
+    sum[2] += ((f >> 16) & 0xffu) * 255u + ia * ((b >> 16) & 0xffu);
+    sum[3] += fa * 255u + ia * (b >> 24);
+}
+__device__ __forceinline__ uint32_t finish(const uint32_t sum[4])
+{
+    return ((sum[0] + 510u) / 1020u) | (((sum[1] + 510u) / 1020u) << 8) | (((sum[2] + 510u) / 1020u) << 16) | (((sum[3] + 510u) / 1020u) << 24);
+}
+// t[z][y][x] = the 2x2x2 block; direction d = 2*axis + (travelling negative)
+__device__ __forceinline__ uint32_t reduce_dir(const uint32_t t[2][2][2], int d)
+{
+    uint32_t sum[4] = {0, 0, 0, 0};
+    const int axis = d >> 1, neg = d & 1;
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+        {
+            uint32_t f, b;
+            if (axis == 0) { f = t[j][i][neg]; b = t[j][i][neg ^ 1]; }          // columns along x: (y=i, z=j)
+            else if (axis == 1) { f = t[i][neg][j]; b = t[i][neg ^ 1][j]; }     // along y: (z=i, x=j)
+            else { f = t[neg][j][i]; b = t[neg ^ 1][j][i]; }                    // along z: (x=i, y=j)
+            acc_col(f, b, sum);
+        }
+    return finish(sum);
+}
+
+struct MipOut
+{
+    uint32_t* lin[6];
+    cudaSurfaceObject_t surf[6];
+};
+
+// ---- plain kernel: one thread per output texel (tail levels, and the cross-check for the TMA path) ----
+// iso = 1: all six directions from one source (level 1); iso = 0: direction d reads src[d].
+__global__ void __launch_bounds__(256) k_mips_simple(const uint32_t* __restrict__ src0, uint64_t src_dir_stride, MipOut out, int n, int iso)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    if (x >= n) return;
+    const int sn = 2 * n;
+    for (int d0 = 0; d0 < 6; d0 += (iso ? 6 : 1))
+    {
+        const uint32_t* src = src0 + (iso ? 0 : (size_t)d0 * src_dir_stride);
+        uint32_t t[2][2][2];
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+            {
+                const uint2 r = *reinterpret_cast<const uint2*>(src + (((size_t)(2 * z + k)) * sn + (2 * y + j)) * sn + 2 * x);
+                t[k][j][0] = r.x; t[k][j][1] = r.y;
+            }
+        for (int d = d0; d < (iso ? 6 : d0 + 1); d++)
+        {
+            const uint32_t v = reduce_dir(t, d);
+            out.lin[d][((size_t)z * n + y) * n + x] = v;
+            surf3Dwrite(v, out.surf[d], x * 4, y, z);
+        }
+    }
+}
+
+// ---- TMA path -----------------------------------------------------------------------------------------
+constexpr int TX = 32, TY = 4, TZ = 4;                 // output tile
+constexpr int SX = 2 * TX, SY = 2 * TY, SZ = 2 * TZ;   // source box 64x8x8 texels
+constexpr int TILE_BYTES = SX * SY * SZ * 4;           // 16 KB
+constexpr int STAGES = 3;
+constexpr int MIPS_THREADS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z, int w)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+// Source tensor: 4-D (x, y, z, dir) of uint32 texels; dir extent is 1 for the isotropic level 0.
+// Work items: (dir_src, tile).  iso: one item yields six outputs; else item's dir yields one.
+__global__ void __launch_bounds__(MIPS_THREADS)
+k_mips_tma(const __grid_constant__ CUtensorMap src_map, MipOut out, int n, int iso, int tiles_x, int tiles_y, int tiles_z, int n_items)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint32_t* tiles = reinterpret_cast<uint32_t*>(smem_raw);                     // STAGES x 16 KB
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * TILE_BYTES);
+
+    const int tid = threadIdx.x;
+    if (tid == 0)
+    {
+        for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int tiles_per_dir = tiles_x * tiles_y * tiles_z;
+    auto issue = [&](int item, int stage) {
+        const int dir = item / tiles_per_dir, tl = item % tiles_per_dir;
+        const int tx = tl % tiles_x, ty = (tl / tiles_x) % tiles_y, tz = tl / (tiles_x * tiles_y);
+        mbar_expect_tx(&full[stage], TILE_BYTES);
+        tma_load_4d(tiles + stage * (TILE_BYTES / 4), &src_map, &full[stage], tx * SX, ty * SY, tz * SZ, dir);
+    };
+    // prologue: fill the ring
+    if (tid == 0)
+        for (int s = 0; s < STAGES; s++)
+        {
+            const int item = blockIdx.x + s * gridDim.x;
+            if (item < n_items) issue(item, s);
+        }
+    // thread -> 4 x-adjacent outputs: ox = 4*(tid & 7), oy = (tid >> 3) & 3, oz = tid >> 5
+    const int ox = (tid & 7) * 4, oy = (tid >> 3) & 3, oz = tid >> 5;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++)
+    {
+        const int stage = it % STAGES;
+        const uint32_t parity = (it / STAGES) & 1;
+        mbar_wait(&full[stage], parity);
+        const uint32_t* tile = tiles + stage * (TILE_BYTES / 4);
+        // 8x2x2 source strip -> registers
+        uint32_t srcv[2][2][8];
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+            {
+                const uint4* row = reinterpret_cast<const uint4*>(tile + ((2 * oz + k) * SY + (2 * oy + j)) * SX + 2 * ox);
+                const uint4 a = row[0], b = row[1];
+                srcv[k][j][0] = a.x; srcv[k][j][1] = a.y; srcv[k][j][2] = a.z; srcv[k][j][3] = a.w;
+                srcv[k][j][4] = b.x; srcv[k][j][5] = b.y; srcv[k][j][6] = b.z; srcv[k][j][7] = b.w;
+            }
+        const int dir = item / tiles_per_dir, tl = item % tiles_per_dir;
+        const int tx = tl % tiles_x, ty = (tl / tiles_x) % tiles_y, tz = tl / (tiles_x * tiles_y);
+        const int gx = tx * TX + ox, gy = ty * TY + oy, gz = tz * TZ + oz;
+        const int d_begin = iso ? 0 : dir, d_end = iso ? 6 : dir + 1;
+        for (int d = d_begin; d < d_end; d++)
+        {
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                uint32_t t[2][2][2];
+#pragma unroll
+                for (int k = 0; k < 2; k++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) { t[k][j][0] = srcv[k][j][2 * q]; t[k][j][1] = srcv[k][j][2 * q + 1]; }
+                o[q] = reduce_dir(t, d);
+            }
+            if (gx < n && gy < n && gz < n)
+            {
+                *reinterpret_cast<uint4*>(out.lin[d] + ((size_t)gz * n + gy) * n + gx) = make_uint4(o[0], o[1], o[2], o[3]);   // 16-byte store
+#pragma unroll
+                for (int q = 0; q < 4; q++) surf3Dwrite(o[q], out.surf[d], (gx + q) * 4, gy, gz);
+            }
+        }
+        __syncthreads();                       // everyone is done with this stage's tile
+        if (tid == 0)
+        {
+            const int next = item + STAGES * gridDim.x;
+            if (next < n_items) issue(next, stage);
+        }
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn)
+    {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+int f184_mips_n(f184_ctx* c)
+{
+    int rc = f184_ensure_image(c, F184_SLOT_RADIANCE); if (rc) return rc;
+    rc = f184_ensure_image(c, F184_SLOT_MIPS); if (rc) return rc;
+    rc = f184_mode_n_alloc(c); if (rc) return rc;
+    const int N = (int)c->cfg.grid_n;
+    uint32_t* mips = img_ptr<uint32_t>(c, F184_SLOT_MIPS);
+    const uint32_t* level0 = img_ptr<uint32_t>(c, F184_SLOT_RADIANCE);
+    const bool use_tma = !(c->cfg.flags & F184_FLAG_NO_TMA) && get_encode() != nullptr;
+    static bool attr_set = false;
+    const int smem = STAGES * TILE_BYTES + 64;
+    if (use_tma && !attr_set)
+    {
+        CK(c, cudaFuncSetAttribute(k_mips_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    rc = f184_stage_begin(c, F184_STAGE_MIPS);
+    if (rc) return rc;
+    for (uint32_t li = 0; li < c->n_mip_levels; li++)
+    {
+        const int n = (int)c->mip_levels[li].n, sn = 2 * n;
+        const int iso = (li == 0);
+        const uint32_t* src = iso ? level0 : mips + c->mip_levels[li - 1].offset_texels;
+        const uint64_t src_dir_stride = (uint64_t)sn * sn * sn;
+        MipOut out;
+        for (int d = 0; d < 6; d++)
+        {
+            out.lin[d] = mips + c->mip_levels[li].offset_texels + (uint64_t)d * n * n * n;
+            out.surf[d] = c->dir_surf[d][li];
+        }
+        if (use_tma && sn >= 64)
+        {
+            CUtensorMap map;
+            const cuuint64_t gdim[4] = {(cuuint64_t)sn, (cuuint64_t)sn, (cuuint64_t)sn, (cuuint64_t)(iso ? 1 : 6)};
+            const cuuint64_t gstride[3] = {(cuuint64_t)sn * 4, (cuuint64_t)sn * sn * 4, (cuuint64_t)sn * sn * sn * 4};
+            const cuuint32_t box[4] = {SX, SY, SZ, 1};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = get_encode()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void*)src, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return f184_fail(c, F184_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for level %u", (int)r, li + 1);
+            const int tiles_x = (n + TX - 1) / TX, tiles_y = (n + TY - 1) / TY, tiles_z = (n + TZ - 1) / TZ;
+            const int n_items = tiles_x * tiles_y * tiles_z * (iso ? 1 : 6);
+            const int grid = std::min(n_items, 148 * 4);
+            k_mips_tma<<<grid, MIPS_THREADS, smem, c->stream>>>(map, out, n, iso, tiles_x, tiles_y, tiles_z, n_items);
+            CK_LAUNCH(c);
+        }
+        else
+        {
+            const int bx = std::min(n, 256);
+            dim3 grid((n + bx - 1) / bx, n, n);
+            k_mips_simple<<<grid, bx, 0, c->stream>>>(src, src_dir_stride, out, n, iso);
+            CK_LAUNCH(c);
+        }
+    }
+    return f184_stage_end(c, F184_STAGE_MIPS);
+}

@@ -1,0 +1,241 @@
+// mode_n_trace.cu — north-star indirect pass: per-pixel diffuse + specular voxel cone tracing over the
+// G-buffer (DESIGN.md "Mode N" B.5).
+//
+// Takes the place of the reference's lighting_indirect pass (Foreground/Renderer/MegaPipeline.cpp:252-268,
+// Shader/Lighting/indirect.frag), which marches 8 stochastic rays of 60 fixed steps through a single-level
+// volume.  Here each pixel traces 6 diffuse cones (60 deg aperture) and 1 specular cone through the
+// injected radiance volume and its six-direction mip chain, front-to-back, and ends with the reference's
+// temporal reprojection blend (indirect.frag:225-240) so the output image is a drop-in for indirectImage.
+//
+// B200 design
+//   * tile-per-warp: a warp owns an 8x4 pixel tile, so its 32 cones of the same index leave neighbouring
+//     surface points in nearly the same direction and their texel footprints overlap in L1/tex cache.
+//   * all volume reads are hardware-filtered: level 0 is a 3D array (trilinear), levels >= 1 are six
+//     mipmapped 3D arrays (trilinear + mip-linear in ONE tex3DLod), so a cone sample is 3 texture
+//     instructions (direction-weighted x/y/z faces), 4 while the cone is still thinner than two voxels.
+//   * early termination: a cone stops at alpha >= 0.95, on leaving the volume or at max distance; the loop
+//     exit reconverges per warp, i.e. the warp leaves as soon as its last lane is done (the vote).
+//   * cone-samples are counted (one warp-aggregated atomic per warp) because Gcone-samples/s is a metric.
+#include "f184_device.cuh"
+
+namespace {
+
+struct ConeParams
+{
+    M4 InvProj, InvModelView, w2v, prevModelView, prevProjection;
+    cudaTextureObject_t level0;
+    cudaTextureObject_t dir[6];
+    const float* depth;
+    const uint16_t* normals;
+    const uchar4* material;
+    const uint16_t* hist;
+    uint16_t* out;
+    float h, max_dist, exposure, max_lod;
+    f3 cam;
+    uint32_t W, H, y0, y1;
+};
+
+__constant__ float kDiffuseDirs[6][3] = {
+    {0.0f, 0.0f, 1.0f},
+    {0.8660254f, 0.0f, 0.5f},
+    {0.26761657f, 0.82363910f, 0.5f},
+    {-0.70062927f, 0.50903696f, 0.5f},
+    {-0.70062927f, -0.50903696f, 0.5f},
+    {0.26761657f, -0.82363910f, 0.5f}};
+__constant__ float kDiffuseW[6] = {0.25f, 0.15f, 0.15f, 0.15f, 0.15f, 0.15f};
+constexpr float kTanHalfDiffuse = 0.57735027f;
+
+__device__ __forceinline__ float4 tex_dir(const ConeParams& P, const float w[3], const int face[3], float qx, float qy, float qz, float lod)
+{
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+    {
+        if (w[a] == 0.0f) continue;
+        const float4 s = tex3DLod<float4>(P.dir[face[a]], qx, qy, qz, lod);
+        r.x += w[a] * s.x; r.y += w[a] * s.y; r.z += w[a] * s.z; r.w += w[a] * s.w;
+    }
+    return r;
+}
+
+__device__ f3 trace_cone(const ConeParams& P, f3 origin, f3 dir, float tan_half, unsigned int& samples)
+{
+    const float h = P.h;
+    // direction through the voxel lattice (the voxel camera is a signed axis permutation + scale)
+    const f3 dv = {(P.w2v.m[0] * dir.x + P.w2v.m[4] * dir.y + P.w2v.m[8] * dir.z) * 0.5f,
+                   (P.w2v.m[1] * dir.x + P.w2v.m[5] * dir.y + P.w2v.m[9] * dir.z) * 0.5f,
+                   (P.w2v.m[2] * dir.x + P.w2v.m[6] * dir.y + P.w2v.m[10] * dir.z)};
+    const float dl = length3(dv);
+    const f3 du = {dv.x / dl, dv.y / dl, dv.z / dl};
+    const float w[3] = {du.x * du.x, du.y * du.y, du.z * du.z};
+    const int face[3] = {du.x < 0.0f ? 1 : 0, du.y < 0.0f ? 3 : 2, du.z < 0.0f ? 5 : 4};
+    // normalised volume coordinate of the origin; q(t) = q0 + dv * t (affine)
+    const f3 o3 = mul43(P.w2v, origin, 1.0f);
+    const f3 q0 = {o3.x * 0.5f + 0.5f, o3.y * 0.5f + 0.5f, o3.z};
+    float t = 2.0f * h, A = 0.0f;
+    f3 acc = {0.f, 0.f, 0.f};
+    const float inv_h = 1.0f / h;
+    while (A < 0.95f && t < P.max_dist)
+    {
+        const float diam = fmaxf(h, 2.0f * t * tan_half);
+        const float lod = __log2f(diam * inv_h);
+        const float qx = q0.x + dv.x * t, qy = q0.y + dv.y * t, qz = q0.z + dv.z * t;
+        if (!(qx >= 0.0f && qx <= 1.0f && qy >= 0.0f && qy <= 1.0f && qz >= 0.0f && qz <= 1.0f)) break;
+        samples++;
+        float4 s;
+        if (lod < 1.0f)
+        {
+            const float4 s0 = tex3D<float4>(P.level0, qx, qy, qz);
+            const float4 s1 = tex_dir(P, w, face, qx, qy, qz, 0.0f);
+            s = make_float4(s0.x + (s1.x - s0.x) * lod, s0.y + (s1.y - s0.y) * lod, s0.z + (s1.z - s0.z) * lod, s0.w + (s1.w - s0.w) * lod);
+        }
+        else s = tex_dir(P, w, face, qx, qy, qz, fminf(lod - 1.0f, P.max_lod));
+        const float k = 1.0f - A;
+        acc = {acc.x + k * s.x, acc.y + k * s.y, acc.z + k * s.z};
+        A += k * s.w;
+        t += 0.5f * diam;
+    }
+    const float rem = fmaxf(0.0f, 1.0f - A);
+    return {acc.x * P.exposure + 0.7f * 0.4f * rem, acc.y * P.exposure + 0.8f * 0.4f * rem, acc.z * P.exposure + 1.0f * 0.4f * rem};
+}
+
+__device__ __forceinline__ float unorm16(uint16_t v) { return (float)v / 65535.0f; }
+__device__ __forceinline__ int wrapn(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
+
+__global__ void __launch_bounds__(128) k_trace_n(const ConeParams P, unsigned long long* __restrict__ sample_counter)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const uint32_t y = P.y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    unsigned int samples = 0;
+    if (x < P.W && y < P.y1)
+    {
+        const uint32_t W = P.W, H = P.H;
+        const float uvx = ((float)x + 0.5f) / (float)W, uvy = ((float)y + 0.5f) / (float)H;
+        const float depth = __ldg(P.depth + (size_t)y * W + x);
+        const f4 cp = mul44(P.InvProj, f4{uvx * 2.0f - 1.0f, uvy * 2.0f - 1.0f, depth, 1.0f});
+        const f3 cspos = {cp.x / cp.w, cp.y / cp.w, cp.z / cp.w};
+        ushort4 o;
+        if (depth >= 1.0f) o = make_ushort4(0, 0, 0, dm_f32_to_f16(-cspos.z));
+        else
+        {
+            const f3 wpos = mul43(P.InvModelView, cspos, 1.0f);
+            const ushort4 nq = __ldg(reinterpret_cast<const ushort4*>(P.normals) + (size_t)y * W + x);
+            const f3 csnorm = normalize3(f3{fmaf(unorm16(nq.x), 2.0f, -1.0f), fmaf(unorm16(nq.y), 2.0f, -1.0f), fmaf(unorm16(nq.z), 2.0f, -1.0f)});
+            const f3 wnorm = mul33(P.InvModelView, csnorm);
+            f3 z = wnorm, hh = wnorm;
+            if (fabsf(hh.x) <= fabsf(hh.y) && fabsf(hh.x) <= fabsf(hh.z)) hh.x = 1.0f;
+            else if (fabsf(hh.y) <= fabsf(hh.x) && fabsf(hh.y) <= fabsf(hh.z)) hh.y = 1.0f;
+            else hh.z = 1.0f;
+            z = normalize3(z);
+            const f3 ty = normalize3(cross3(hh, z));
+            const f3 tx = normalize3(cross3(z, ty));
+            const f3 origin = {wpos.x + z.x * P.h, wpos.y + z.y * P.h, wpos.z + z.z * P.h};
+            f3 ind = {0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int i = 0; i < 6; i++)
+            {
+                const float d0 = kDiffuseDirs[i][0], d1 = kDiffuseDirs[i][1], d2 = kDiffuseDirs[i][2];
+                const f3 dir = {(tx.x * d0 + ty.x * d1) + z.x * d2, (tx.y * d0 + ty.y * d1) + z.y * d2, (tx.z * d0 + ty.z * d1) + z.z * d2};
+                const f3 r = trace_cone(P, origin, dir, kTanHalfDiffuse, samples);
+                const float wgt = kDiffuseW[i];
+                ind = {ind.x + wgt * r.x, ind.y + wgt * r.y, ind.z + wgt * r.z};
+            }
+            {
+                const float rough = (float)__ldg(P.material + (size_t)y * W + x).y / 255.0f;
+                const float tan_half = dm_clamp(rough * rough, 0.02f, 0.6f);
+                const f3 I = normalize3(wpos - P.cam);
+                const float ndi = dot3(z, I);
+                const f3 R = {I.x - 2.0f * ndi * z.x, I.y - 2.0f * ndi * z.y, I.z - 2.0f * ndi * z.z};
+                if (dot3(R, z) > 0.0f)
+                {
+                    const f3 r = trace_cone(P, origin, R, tan_half, samples);
+                    const float om = 1.0f - fmaxf(-ndi, 0.0f);
+                    const float F = 0.04f + 0.96f * (om * om * om * om * om);
+                    ind = {ind.x + F * r.x, ind.y + F * r.y, ind.z + F * r.z};
+                }
+            }
+            // temporal reprojection, indirect.frag:225-240
+            const f4 pc = mul44(P.prevModelView, f4{wpos.x, wpos.y, wpos.z, 1.0f});
+            const f4 pp = mul44(P.prevProjection, pc);
+            float ru = pp.x / pp.w, rv = pp.y / pp.w;
+            ru = ru * 0.5f + 0.5f; rv = rv * 0.5f + 0.5f;
+            if (dm_clamp(ru, 0.0f, 1.0f) == ru && dm_clamp(rv, 0.0f, 1.0f) == rv)
+            {
+                const float fx = ru * (float)W - 0.5f, fy = rv * (float)H - 0.5f;
+                const float x0f = floorf(fx), y0f = floorf(fy);
+                const float wx = fx - x0f, wy = fy - y0f;
+                const int xi0 = dm_f2i(x0f), yi0 = dm_f2i(y0f);
+                const int xa = wrapn(xi0, (int)W), xb = wrapn(xi0 + 1, (int)W), ya = wrapn(yi0, (int)H), yb = wrapn(yi0 + 1, (int)H);
+                const ushort4 h00 = __ldg(reinterpret_cast<const ushort4*>(P.hist) + (size_t)ya * W + xa);
+                const ushort4 h10 = __ldg(reinterpret_cast<const ushort4*>(P.hist) + (size_t)ya * W + xb);
+                const ushort4 h01 = __ldg(reinterpret_cast<const ushort4*>(P.hist) + (size_t)yb * W + xa);
+                const ushort4 h11 = __ldg(reinterpret_cast<const ushort4*>(P.hist) + (size_t)yb * W + xb);
+                auto bil = [&](uint16_t a, uint16_t b, uint16_t c, uint16_t d) {
+                    const float fa = dm_f16_to_f32(a), fb = dm_f16_to_f32(b), fc = dm_f16_to_f32(c), fd = dm_f16_to_f32(d);
+                    return (fa * (1.0f - wx) + fb * wx) * (1.0f - wy) + (fc * (1.0f - wx) + fd * wx) * wy;
+                };
+                const float p0 = bil(h00.x, h10.x, h01.x, h11.x), p1 = bil(h00.y, h10.y, h01.y, h11.y);
+                const float p2 = bil(h00.z, h10.z, h01.z, h11.z), p3 = bil(h00.w, h10.w, h01.w, h11.w);
+                const float bw = 0.95f * dm_smoothstep(0.0f, 1.0f, 1.0f - fabsf(p3 + cspos.z));
+                ind = {dm_clamp(dm_mix(ind.x, p0, bw), 0.0f, 16.0f), dm_clamp(dm_mix(ind.y, p1, bw), 0.0f, 16.0f), dm_clamp(dm_mix(ind.z, p2, bw), 0.0f, 16.0f)};
+            }
+            o = make_ushort4(dm_f32_to_f16(ind.x), dm_f32_to_f16(ind.y), dm_f32_to_f16(ind.z), dm_f32_to_f16(-cspos.z));
+        }
+        reinterpret_cast<ushort4*>(P.out)[(size_t)y * W + x] = o;
+    }
+    warp_count_add(sample_counter, samples);
+}
+
+}  // namespace
+
+int f184_trace_n(f184_ctx* c, const f184_trace_constants* k)
+{
+    for (int s : {F184_SLOT_DEPTH, F184_SLOT_NORMALS, F184_SLOT_MATERIAL, F184_SLOT_INDIRECT_OUT, F184_SLOT_INDIRECT_HISTORY})
+    {
+        int rc = f184_ensure_image(c, s);
+        if (rc) return rc;
+    }
+    if (!c->rad_array) return f184_fail(c, F184_ERR_NOT_READY, "trace: call f184_inject and f184_build_mips first");
+    ConeParams P{};
+    memcpy(P.InvProj.m, k->view.InvProj, 64);
+    memcpy(P.InvModelView.m, k->ext.InvModelView, 64);
+    M4 vp, vv;
+    memcpy(vp.m, k->ext.VoxelProj, 64);
+    memcpy(vv.m, k->ext.VoxelView, 64);
+    P.w2v = host_matmul(vp, vv);
+    memcpy(P.prevModelView.m, k->prev.PrevModelView, 64);
+    memcpy(P.prevProjection.m, k->prev.PrevProjection, 64);
+    {
+        const M4 v2w = f184_invert_m4(P.w2v);
+        const float s = 2.0f / (float)c->cfg.grid_n;
+        const float ax = v2w.m[0] * s, ay = v2w.m[1] * s, az = v2w.m[2] * s;
+        P.h = sqrtf((ax * ax + ay * ay) + az * az);
+    }
+    P.level0 = c->rad_tex;
+    for (int d = 0; d < 6; d++) P.dir[d] = c->dir_tex[d];
+    P.depth = img_ptr<float>(c, F184_SLOT_DEPTH);
+    P.normals = img_ptr<uint16_t>(c, F184_SLOT_NORMALS);
+    P.material = img_ptr<uchar4>(c, F184_SLOT_MATERIAL);
+    P.hist = img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_HISTORY);
+    P.out = img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_OUT);
+    P.max_dist = c->cfg.cone_max_distance;
+    P.exposure = f184_exposure(c, &k->sun);
+    P.max_lod = (float)(c->n_mip_levels - 1);
+    P.cam = {P.InvModelView.m[12], P.InvModelView.m[13], P.InvModelView.m[14]};
+    P.W = c->cfg.width; P.H = c->cfg.height;
+    P.y0 = c->row0 < P.H ? c->row0 : P.H;
+    P.y1 = c->row1 < P.H ? c->row1 : P.H;
+    int rc = f184_stage_begin(c, F184_STAGE_TRACE);
+    if (rc) return rc;
+    if (k->reset_history)
+        CK(c, cudaMemsetAsync(c->img[F184_SLOT_INDIRECT_HISTORY].ptr, 0, c->img[F184_SLOT_INDIRECT_HISTORY].desc.size_bytes, c->stream));
+    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_MARCH_STEPS, 0, 8, c->stream));
+    if (P.y1 > P.y0)
+    {
+        dim3 grid((P.W + 15) / 16, (P.y1 - P.y0 + 7) / 8);
+        k_trace_n<<<grid, 128, 0, c->stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+        CK_LAUNCH(c);
+    }
+    return f184_stage_end(c, F184_STAGE_TRACE);
+}

@@ -111,7 +111,7 @@ typedef struct f184_config {
     float step_size;         /* 0.2 world units */
     /* north-star cone parameters */
     float cone_max_distance; /* 32 m */
-    float radiance_exposure; /* RGBA8 radiance = radiance / exposure, clamped; 0 = default 8.0 */
+    float radiance_exposure; /* RGBA8 radiance = radiance / exposure, clamped; 0 = auto: largest sun luminance component */
     /* sharding over one NVLink box; rank/nranks = 0/1 for a single GPU */
     uint32_t rank, nranks;
     uint32_t flags;          /* f184_flags */
@@ -119,7 +119,8 @@ typedef struct f184_config {
 
 typedef enum f184_flags {
     F184_FLAG_NONE = 0,
-    F184_FLAG_EXTERNAL_RANDS = 1   /* mode R trace: rands come from a bound buffer (march-only parity) */
+    F184_FLAG_EXTERNAL_RANDS = 1,  /* mode R trace: rands come from a bound buffer (march-only parity) */
+    F184_FLAG_NO_TMA = 2           /* mode N mips: use the plain kernel for every level (cross-check of the TMA path) */
 } f184_flags;
 
 /* CViewConstants, Foreground/SceneGraph/SceneView.h:8-14 = GlobalConstants, Shader/EngineCommon.h:7-13. 208 B. */

@@ -107,7 +107,6 @@ int f184o_create(const f184_config* config, f184o_ctx** out)
     if (c->cfg.step_size == 0.f) c->cfg.step_size = 0.2f;
     if (c->cfg.shadow_res == 0) c->cfg.shadow_res = 2048;
     if (c->cfg.cone_max_distance == 0.f) c->cfg.cone_max_distance = 32.f;
-    if (c->cfg.radiance_exposure == 0.f) c->cfg.radiance_exposure = 8.f;
     if (c->cfg.nranks == 0) c->cfg.nranks = 1;
     *out = c;
     return F184_OK;
