@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — the voxel-GI hot path of Final184 on B200, measured the way BASELINE.json names it:
+ms/frame for voxelize(+normalise) + inject + six-direction mips + diffuse/specular cone trace.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--grid 512] [--width 3840] [--height 2160]
+
+One "step" = one frame of the path over the Sponza fixture (App/MainBehaviour.cpp:19-76; the procedural
+atrium of final184_b200/scene.py if the Sponza pack is not staged — config.workload says which).
+
+  value          device time per frame, inputs resident in HBM, CUDA events on the context's stream, K frames
+                 bracketed by barrier + synchronize, max over ranks
+  e2e            the same frame through the C-ABI with HOST buffers: depth / normals / material / shadow copied
+                 from pinned host memory and the traced image read back, every frame, inside the timed region
+  roofline       the dominant kernel of the step (chosen from the per-stage device times accumulated over the same
+                 timed region) against the measured HBM peak; roofline_stages lists every stage the same way
+  cpu_baseline   the CPU oracle (oracle/, the "straight C++ transcription") on a bounded sample
+  --impl reference   the same metric from the CPU oracle alone (rank 0), each step a bounded sample
+
+N > 1 (torchrun, one rank per GPU): see DESIGN.md "Multi-GPU".
+The product path is libf184.so only; the oracle is loaded solely for the cpu_baseline / reference legs.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ms/frame voxelize+inject+mip+cone-trace"
+UNIT = "ms/frame"
+ORACLE_SO = os.path.join(REPO, "oracle", "_build", "libf184_oracle.so")
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--grid", type=int, default=512)
+    p.add_argument("--width", type=int, default=3840)
+    p.add_argument("--height", type=int, default=2160)
+    p.add_argument("--shadow", type=int, default=2048)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-budget-s", type=float, default=20.0, help="target CPU seconds of the cpu_baseline sample")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------------
+def make_workload(args):
+    from final184_b200 import scene as S
+    from final184_b200.fixture import frame_inputs
+    sc = S.get_scene(prefer_sponza=True, seed=1, n_boxes=48, tex_size=256, subdiv=8)
+    cams = {n: S.fixture_constants(n) for n in ("main", "shadow", "voxel")}
+    fi = frame_inputs(sc, cams["main"], cams["shadow"], args.width, args.height, args.shadow, 0)
+    name = ("Sponza" if sc.name == "sponza" else sc.name) + f" {args.grid}^3 voxel GI (voxelize+normalise+inject+6-dir mips+" \
+        f"6 diffuse/1 specular cones) at {args.width}x{args.height}, north-star mode"
+    return sc, cams, fi, name
+
+
+def mip_chain_bytes(n, b=4):
+    """bytes the six-direction chain must move (read source once, write six outputs)."""
+    total = b * n ** 3 + 6 * b * (n // 2) ** 3
+    s = n // 2
+    while s >= 2:
+        total += 6 * b * s ** 3 + 6 * b * (s // 2) ** 3
+        s //= 2
+    return total
+
+
+def algorithmic_bytes(stage, args, sc, counters):
+    """Per-launch algorithmic bytes of each stage (DESIGN.md "Roofline").  counters: fragments, bricks, occupied."""
+    N, P = args.grid, args.width * args.height
+    V, T = len(sc.pos), sc.n_tris
+    if stage == "voxelize":      # indexed triangle fetch + two 16-byte reductions per fragment
+        return 32 * V + 12 * T + 32 * counters["fragments"]
+    if stage == "normalise":     # touched bricks: read+zero 32 B accumulators, write 8 B albedo+normal
+        return (32 + 32 + 8) * 512 * counters["bricks"]
+    if stage == "inject":        # listed bricks: read 8 B, write 4 B linear + 4 B array
+        return (8 + 8) * 512 * counters["bricks"]
+    if stage == "mips":
+        return mip_chain_bytes(N)
+    if stage == "trace":         # per-pixel fixed I/O (depth 4, normal 8, material 4, history 8, out 8) + one pass over the volume chain
+        return 32 * P + 4 * N ** 3 + 4 * 6 * sum((N >> l) ** 3 for l in range(1, N.bit_length()))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx, self.rows, self.proc = device_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle: test infrastructure, loaded ONLY here)
+# ------------------------------------------------------------------------------------------------------
+class CpuPath:
+    """Bounded sample of one frame on the host cores through the oracle's mirror API.
+    A frame = voxelize(all triangles) + inject + mips + trace(all rows).  The sample runs voxelize on one
+    triangle chunk out of `vchunks` (rotating per step) and the trace on `bands` stratified bands covering
+    1/`tfrac` of the rows, against a FULL volume built once at set-up; inject and mips run in full."""
+
+    def __init__(self, args, sc, cams, fi, vchunks=1, tfrac=16, bands=2):
+        from final184_b200 import api as A
+        self.A, self.args, self.sc, self.cams = A, args, sc, cams
+        if not os.path.exists(ORACLE_SO):
+            subprocess.check_call(["make", "-C", os.path.join(REPO, "oracle")], stdout=subprocess.DEVNULL)
+        self.lib = A.Library(ORACLE_SO, "f184o_", product=False)
+        self.vchunks, self.tfrac, self.bands = vchunks, tfrac, bands
+        self.k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], args.width, args.height, 0, True)
+        mk = lambda: A.VoxelGI(args.grid, args.width, args.height, A.MODE_NORTHSTAR, shadow_res=args.shadow, lib=self.lib)
+        self.full, self.part = mk(), mk()
+        for c in (self.full, self.part):
+            c.upload_scene(sc)
+            for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_SHADOW, "shadow"), (A.SLOT_MATERIAL, "material")):
+                c.upload(slot, fi[key])
+        # full volume for the trace sample (set-up, untimed)
+        self.full.voxelize(cams["voxel"]); self.full.inject(self.k); self.full.build_mips()
+        self.step_no = 0
+        self.cores = os.cpu_count() or 1
+
+    def describe(self):
+        return (f"oracle (C++/OpenMP) on {self.cores} threads; per step: voxelize+normalise of triangle chunk k/{self.vchunks} (rotating, x{self.vchunks}), "
+                f"inject + mips in full, trace of {self.bands} stratified bands = 1/{self.tfrac} of the rows (x{self.tfrac}) against the full volume")
+
+    def step(self):
+        """-> (estimated full-frame ms, wall ms of the sample, stage dict)"""
+        A, a = self.A, self.args
+        T = self.sc.n_tris
+        ch = self.step_no % self.vchunks
+        self.step_no += 1
+        first = ch * T // self.vchunks
+        count = (ch + 1) * T // self.vchunks - first
+        t0 = time.perf_counter()
+        self.part.set_triangle_range(first, count)
+        self.part.voxelize(self.cams["voxel"])
+        t1 = time.perf_counter()
+        self.part.inject(self.k)
+        t2 = time.perf_counter()
+        self.part.build_mips()
+        t3 = time.perf_counter()
+        rows_per_band = max(1, a.height // (self.tfrac * self.bands))
+        traced = 0
+        for b in range(self.bands):
+            y0 = b * a.height // self.bands + (self.step_no * rows_per_band) % max(1, a.height // self.bands - rows_per_band)
+            self.full.set_trace_rows(y0, y0 + rows_per_band)
+            self.full.trace_indirect(self.k)
+            traced += rows_per_band
+        t4 = time.perf_counter()
+        st = {"voxelize+normalise": (t1 - t0) * 1e3 * self.vchunks, "inject": (t2 - t1) * 1e3, "mips": (t3 - t2) * 1e3,
+              "trace": (t4 - t3) * 1e3 * a.height / traced}
+        return sum(st.values()), (t4 - t0) * 1e3, st
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the path, rank 0 only."""
+    if rank != 0:
+        return
+    sc, cams, fi, wname = make_workload(args)
+    per_step_budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    # size the sample from the budget: one chunk of voxelize (~6 s / vchunks at 512^3 on 16 cores) + mips + trace fraction
+    # (512^3 / 4K on 16 cores: full voxelize ~4 s, inject+mips ~2 s, 1/16 of the trace ~3 s)
+    small = per_step_budget < 8
+    cpu = CpuPath(args, sc, cams, fi, vchunks=4 if small else 1, tfrac=32 if small else 16, bands=2)
+    for _ in range(args.warmup):
+        cpu.step()
+    est, wall, stages = [], [], []
+    for _ in range(args.steps):
+        e, w, s = cpu.step()
+        est.append(e); wall.append(w); stages.append(s)
+    v = float(np.mean(est))
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": float(np.mean(wall)), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u8/i64/f32",
+           "data": "synthetic", "config": {"workload": wname, "grid": args.grid, "width": args.width, "height": args.height},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": cpu.describe()},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "stages_ms": {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from final184_b200 import api as A
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sc, cams, fi, wname = make_workload(args)
+    W, H, N = args.width, args.height, args.grid
+    peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else None
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if peaks else (6650.0, "fallback (B200_PROFILING.md)")
+
+    from final184_b200.dist import ShardedVoxelGI
+    g = ShardedVoxelGI(grid_n=N, width=W, height=H, shadow_res=args.shadow, device=local_rank, rank=rank, nranks=world, scene=sc)
+    stream = torch.cuda.Stream(device=local_rank)
+    g.ctx.set_stream(stream.cuda_stream)
+    k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
+    slots = ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_MATERIAL, "material"), (A.SLOT_SHADOW, "shadow"))
+    # pinned host copies of the per-frame inputs and of the result (e2e leg)
+    pinned = {}
+    for slot, key in slots:
+        t = torch.from_numpy(np.ascontiguousarray(fi[key]).view(np.uint8).reshape(-1)).pin_memory()
+        pinned[slot] = t
+    out_info = g.ctx.image_info(A.SLOT_INDIRECT_OUT)
+    out_host = torch.empty(out_info.size_bytes, dtype=torch.uint8).pin_memory()
+    h2d = sum(int(t.numel()) for t in pinned.values())
+    d2h = int(out_host.numel())
+
+    def upload_inputs():
+        for slot, t in pinned.items():
+            g.ctx.upload_ptr(slot, t.data_ptr(), t.numel())
+
+    def frame():
+        g.frame(cams["voxel"], k)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    upload_inputs()
+    g.ctx.sync()
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            frame()
+        # ---- timed region: device-resident inputs
+        g.ctx.stage_time_reset(True)
+        l0 = g.ctx.counter(A.COUNTER_KERNEL_LAUNCHES)
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            frame()
+        ev1.record(stream)
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        clk = clocks.stop()
+        launches = g.ctx.counter(A.COUNTER_KERNEL_LAUNCHES) - l0
+        stage_ms = {}
+        for s in range(A.STAGE_COUNT):
+            tot, runs = g.ctx.stage_total_ms(s)
+            if runs:
+                stage_ms[A.STAGE_NAMES[s]] = tot / runs
+        comm_ms = g.comm_ms_per_frame()
+        g.ctx.stage_time_reset(False)
+        counters = {"fragments": g.ctx.counter(A.COUNTER_FRAGMENTS), "bricks": g.ctx.counter(A.COUNTER_BRICKS),
+                    "occupied": g.ctx.counter(A.COUNTER_OCCUPIED), "cone_samples": g.ctx.counter(A.COUNTER_MARCH_STEPS)}
+        # ---- timed region: end to end with host buffers
+        for _ in range(2):
+            upload_inputs(); frame(); g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_host.data_ptr(), d2h); g.ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_wall0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            upload_inputs()
+            frame()
+            g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_host.data_ptr(), d2h)
+            g.ctx.sync()                       # the caller consumes the image every frame
+        e1.record(stream)
+        barrier()
+        e2e_ms_dev = e0.elapsed_time(e1)
+        e2e_ms_wall = (time.perf_counter() - t_wall0) * 1e3
+        e2e_ms = max(e2e_ms_dev, e2e_ms_wall)
+        # secondary pass, reported beside the metric (not part of it): GTAO + its blur, and the indirect blur tail
+        for _ in range(3):
+            g.ctx.gtao(cams["main"]); g.ctx.blur_indirect(k)
+        g.ctx.sync()
+        extra_ms = {"gtao": g.ctx.stage_ms(A.STAGE_GTAO), "blur": g.ctx.stage_ms(A.STAGE_BLUR)}
+
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    cs = torch.tensor([float(counters["cone_samples"]), float(launches)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    total_samples, launches_all = float(cs[0]), int(cs[1])
+    ms_frame = ms_total / args.steps
+    if rank == 0:
+        # roofline: dominant kernel = the stage with the largest mean device time in the timed region
+        rstages = {}
+        for name, ms in stage_ms.items():
+            b = algorithmic_bytes(name, args, sc, counters)
+            if name == "trace" and world > 1:
+                b = b  # each rank reads the whole chain; per-rank pixels differ but the volume term dominates
+            if b and ms > 0:
+                ach = b / (ms * 1e-3) / 1e9
+                rstages[name] = {"ms": round(ms, 4), "algorithmic_bytes": int(b), "achieved": round(ach, 1), "frac": round(ach / hbm_peak, 4)}
+        dom = max(stage_ms, key=stage_ms.get)
+        traffic = None
+        tp = os.path.join(REPO, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(f"{dom}@{N}")
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": rstages[dom]["achieved"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": rstages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "note": "trace is bound by the texture units, not HBM: see tex_rate" if dom == "trace" else ""}
+        out = {"metric": METRIC, "value": ms_frame, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_frame, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+               "dtype": "u8 volumes / i64 overlap tests / f32 shading", "data": "synthetic",
+               "config": {"workload": wname, "grid": N, "width": W, "height": H, "shadow": args.shadow, "triangles": sc.n_tris,
+                          "parallelism": g.describe(), "l2": "inputs larger than L2 (volume chain %.0f MB + accumulators; no flush)" % (algorithmic_bytes("trace", args, sc, counters) / 1e6)},
+               "gvoxel_per_s": N ** 3 / (ms_frame * 1e-3) / 1e9,
+               "gcone_samples_per_s": total_samples / (stage_ms.get("trace", ms_frame) * 1e-3) / 1e9,
+               "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "comm_ms": comm_ms, "secondary_ms": extra_ms, "counters": counters,
+               "roofline": roofline, "roofline_stages": rstages,
+               "e2e": {"value": e2e_ms / args.steps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": launches_all, "clocks": clk}
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = CpuPath(args, sc, cams, fi, vchunks=1, tfrac=16, bands=2)
+            cpu.step()
+            est, wall = [], []
+            t0 = time.perf_counter()
+            while (time.perf_counter() - t0 < args.cpu_budget_s and len(est) < 8) or not est:
+                e, w, _ = cpu.step()
+                est.append(e); wall.append(w)
+            out["cpu_baseline"] = {"value": float(np.mean(est)), "unit": UNIT, "cores": cpu.cores, "kind": "port",
+                                   "sample": cpu.describe() + f"; {len(est)} samples, {np.mean(wall) / 1e3:.1f} s each"}
+        print(json.dumps(out), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        # convenience: `python bench.py --gpus N` relaunches itself under torchrun
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

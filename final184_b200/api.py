@@ -152,6 +152,8 @@ _SIGS = {
 _PRODUCT_ONLY = {
     "import_external_memory_fd": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(ImageDesc)]),
     "import_semaphores_fd": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "stage_time_reset": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "stage_time_total": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "debug_detmath": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
 }
 EXPORTS = sorted(list(_SIGS) + list(_PRODUCT_ONLY))
@@ -315,6 +317,15 @@ class VoxelGI:
         v = C.c_float()
         self._ck(self.lib.stage_time_ms(self.h, stage, C.byref(v)), "stage_time_ms")
         return v.value
+
+    def stage_time_reset(self, accumulate=True):
+        self._ck(self.lib.stage_time_reset(self.h, 1 if accumulate else 0), "stage_time_reset")
+
+    def stage_total_ms(self, stage):
+        """(sum of the stage's device time, runs) since stage_time_reset(True)."""
+        v, n = C.c_float(), C.c_uint32()
+        self._ck(self.lib.stage_time_total(self.h, stage, C.byref(v), C.byref(n)), "stage_time_total")
+        return v.value, n.value
 
     def counter(self, which) -> int:
         v = C.c_uint64()

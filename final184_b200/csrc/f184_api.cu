@@ -94,6 +94,21 @@ int f184_ensure_image(f184_ctx* c, int slot)
 
 int f184_stage_begin(f184_ctx* c, int stage)
 {
+    if (c->ev_accumulate)
+    {   // a fresh event pair per run so the whole timed region can be summed afterwards without a sync inside it
+        auto& pool = c->ev_pool[stage];
+        const uint32_t run = c->ev_runs[stage];
+        if (pool.size() < 2ull * (run + 1))
+        {
+            cudaEvent_t a, b;
+            CK(c, cudaEventCreate(&a));
+            CK(c, cudaEventCreate(&b));
+            pool.push_back(a); pool.push_back(b);
+        }
+        c->ev[stage][0] = pool[2 * run];
+        c->ev[stage][1] = pool[2 * run + 1];
+        c->ev_runs[stage] = run + 1;
+    }
     CK(c, cudaEventRecord(c->ev[stage][0], c->stream));
     return F184_OK;
 }
@@ -174,7 +189,13 @@ int f184_create(const f184_config* config, f184_ctx** out)
         return f184_fail(nullptr, F184_ERR_CUDA, "cudaStreamCreate failed");
     }
     c->stream = c->own_stream;
-    for (int s = 0; s < F184_STAGE_COUNT; s++) { cudaEventCreate(&c->ev[s][0]); cudaEventCreate(&c->ev[s][1]); }
+    for (int s = 0; s < F184_STAGE_COUNT; s++)
+    {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        c->ev_pool[s].push_back(a); c->ev_pool[s].push_back(b);
+        c->ev[s][0] = a; c->ev[s][1] = b;
+    }
     if (cudaMalloc(&c->counters_dev, sizeof(unsigned long long) * (F184_COUNTER_COUNT + 4)) != cudaSuccess)
     {
         delete c;
@@ -201,7 +222,8 @@ void f184_destroy(f184_ctx* c)
                     (void*)c->brick_prev, (void*)c->brick_list})
         if (p) cudaFree(p);
     for (uint8_t* p : c->tex_alloc) if (p) cudaFree(p);
-    for (int s = 0; s < F184_STAGE_COUNT; s++) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
+    for (int s = 0; s < F184_STAGE_COUNT; s++)
+        for (cudaEvent_t e : c->ev_pool[s]) cudaEventDestroy(e);
     if (c->sem_wait) cudaDestroyExternalSemaphore(c->sem_wait);
     if (c->sem_signal) cudaDestroyExternalSemaphore(c->sem_signal);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -518,6 +540,35 @@ int f184_stage_time_ms(f184_ctx* c, uint32_t stage, float* ms)
     if (!c->ev_valid[stage]) { *ms = 0.f; return F184_OK; }
     CK(c, cudaEventSynchronize(c->ev[stage][1]));
     CK(c, cudaEventElapsedTime(ms, c->ev[stage][0], c->ev[stage][1]));
+    return F184_OK;
+}
+int f184_stage_time_reset(f184_ctx* c, uint32_t accumulate)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->ev_accumulate = accumulate != 0;
+    for (int s = 0; s < F184_STAGE_COUNT; s++)
+    {
+        c->ev_runs[s] = 0;
+        c->ev_valid[s] = false;
+        c->ev[s][0] = c->ev_pool[s][0];
+        c->ev[s][1] = c->ev_pool[s][1];
+    }
+    return F184_OK;
+}
+int f184_stage_time_total(f184_ctx* c, uint32_t stage, float* ms_sum, uint32_t* runs)
+{
+    if (!c || stage >= F184_STAGE_COUNT || !ms_sum || !runs) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "stage_time_total: bad argument");
+    *ms_sum = 0.f; *runs = 0;
+    if (!c->ev_accumulate) return f184_fail(c, F184_ERR_NOT_READY, "stage_time_total: call f184_stage_time_reset(ctx, 1) first");
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (uint32_t r = 0; r < c->ev_runs[stage]; r++)
+    {
+        float ms = 0.f;
+        CK(c, cudaEventElapsedTime(&ms, c->ev_pool[stage][2 * r], c->ev_pool[stage][2 * r + 1]));
+        *ms_sum += ms;
+    }
+    *runs = c->ev_runs[stage];
     return F184_OK;
 }
 int f184_counter_get(f184_ctx* c, uint32_t which, uint64_t* v)

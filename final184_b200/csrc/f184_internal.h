@@ -86,8 +86,12 @@ struct f184_ctx
     // measurement
     unsigned long long* counters_dev = nullptr;   // F184_COUNTER_COUNT
     uint64_t launches = 0;
-    cudaEvent_t ev[F184_STAGE_COUNT][2] = {};
+    cudaEvent_t ev[F184_STAGE_COUNT][2] = {};     // event pair of the stage's LAST run (aliases the pool while accumulating)
     bool ev_valid[F184_STAGE_COUNT] = {};
+    // accumulation over a timed region (f184_stage_time_reset / f184_stage_time_total): one event pair per run
+    bool ev_accumulate = false;
+    std::vector<cudaEvent_t> ev_pool[F184_STAGE_COUNT];   // 2 events per run, created on demand, reused after reset
+    uint32_t ev_runs[F184_STAGE_COUNT] = {};
     // interop
     cudaExternalSemaphore_t sem_wait = nullptr, sem_signal = nullptr;
 };

@@ -273,6 +273,11 @@ int f184_set_trace_rows(f184_ctx* ctx, uint32_t y0, uint32_t y1);
 /* ---- measurement */
 int f184_stage_time_ms(f184_ctx* ctx, uint32_t stage, float* out_ms);   /* last run of the stage; synchronous */
 int f184_counter_get(f184_ctx* ctx, uint32_t which, uint64_t* out_value);    /* synchronous */
+/* Timing over a region of many frames without a sync inside it: after f184_stage_time_reset(ctx, 1) every
+ * run of a stage records its own CUDA event pair on the stream; f184_stage_time_total sums them (synchronous).
+ * f184_stage_time_reset(ctx, 0) returns to "last run only". */
+int f184_stage_time_reset(f184_ctx* ctx, uint32_t accumulate);
+int f184_stage_time_total(f184_ctx* ctx, uint32_t stage, float* out_ms_sum, uint32_t* out_runs);
 
 /* ---- test hook: evaluate csrc/f184_detmath.h on the device (op: 0 sin, 1 cos, 2 log, 3 log2, 4 exp2,
  * 5 pow(x,y), 6 f32->f16->f32); host pointers; synchronous */

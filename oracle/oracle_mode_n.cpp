@@ -157,6 +157,9 @@ extern "C" int orc_voxelize_n(f184o_ctx* c, const f184_view_constants* cam)
     uint64_t frags = 0;
     const uint32_t first = c->tri_first, last = (uint32_t)std::min<uint64_t>((uint64_t)c->tri_first + c->tri_count, c->n_tris);
 
+    // Triangles in parallel: every addend is an integer-valued float and the per-voxel sums stay below 2^24, so
+    // the atomic adds are exact and the result does not depend on the order (same argument as on the device).
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : frags)
     for (uint32_t t = first; t < last; t++)
     {
         const uint32_t* id = &c->idx[3 * t];
@@ -265,8 +268,17 @@ extern "C" int orc_voxelize_n(f184o_ctx* c, const f184_view_constants* cam)
                     const float nx8 = rintf(dm_clamp(nn.x, -1.0f, 1.0f) * 127.0f), ny8 = rintf(dm_clamp(nn.y, -1.0f, 1.0f) * 127.0f),
                                 nz8 = rintf(dm_clamp(nn.z, -1.0f, 1.0f) * 127.0f);
                     const size_t o = ((size_t)box[2] * N + box[1]) * N + box[0];
-                    accC[4 * o] += r8; accC[4 * o + 1] += g8; accC[4 * o + 2] += b8; accC[4 * o + 3] += 1.0f;
-                    accN[4 * o] += nx8; accN[4 * o + 1] += ny8; accN[4 * o + 2] += nz8;
+                    const float add[7] = {r8, g8, b8, 1.0f, nx8, ny8, nz8};
+                    for (int q = 0; q < 4; q++)
+                    {
+#pragma omp atomic
+                        accC[4 * o + q] += add[q];
+                    }
+                    for (int q = 0; q < 3; q++)
+                    {
+#pragma omp atomic
+                        accN[4 * o + q] += add[4 + q];
+                    }
                     frags++;
                 }
     }
@@ -279,6 +291,7 @@ extern "C" int orc_voxelize_n(f184o_ctx* c, const f184_view_constants* cam)
     int8_t* nrm = image_ptr<int8_t>(c, F184_SLOT_VOX_NORMAL);
     uint64_t occ = 0;
     std::vector<uint8_t> brick((size_t)(N / 8) * (N / 8) * (N / 8), 0);
+#pragma omp parallel for schedule(static) reduction(+ : occ)
     for (size_t o = 0; o < nvox; o++)
     {
         const float cnt = accC[4 * o + 3];
@@ -298,7 +311,9 @@ extern "C" int orc_voxelize_n(f184o_ctx* c, const f184_view_constants* cam)
             nrm[4 * o + 3] = 0;
             occ++;
             size_t x = o % N, y = (o / N) % N, z = o / ((size_t)N * N);
-            brick[((z / 8) * (N / 8) + (y / 8)) * (N / 8) + (x / 8)] = 1;
+            uint8_t& flag = brick[((z / 8) * (N / 8) + (y / 8)) * (N / 8) + (x / 8)];
+#pragma omp atomic write
+            flag = 1;
         }
         else { memset(&alb[4 * o], 0, 4); memset(&nrm[4 * o], 0, 4); }
     }
