@@ -73,6 +73,10 @@ struct f184_ctx
     cudaTextureObject_t rad_tex = 0, dir_tex[6] = {0, 0, 0, 0, 0, 0};
     uint32_t* brick_prev = nullptr;           // bricks written last frame (to clear what became empty)
     uint32_t* brick_list = nullptr;           // bricks processed this frame (touched now or last frame)
+    uint32_t* vox_queue = nullptr;            // voxelizer pass-2 queue: uint2 (triangle, first task) per large triangle
+    uint32_t vox_queue_cap = 0;
+    M4* vm_dev = nullptr;                     // View * Model per model matrix
+    uint32_t vm_cap = 0;
     bool defer_normalise = false;             // multi-GPU: f184_voxelize stops after accumulation
     cudaSurfaceObject_t rad_surf = 0;
     cudaSurfaceObject_t dir_surf[6][12] = {};

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_inject_n(const InjectParams P)
     const float Nf = (float)N;
     for (uint32_t i = warp_global; i < count; i += n_warps)
     {
-        const uint32_t b = P.brick_list[i];
+        const uint32_t b = P.brick_list[i] & 0x7fffffffu;      // bit 31 = touched this frame (normalise)
         const int bx = (b % NB) << 3, by = ((b / NB) % NB) << 3, bz = (b / (NB * NB)) << 3;
 #pragma unroll 2
         for (int pass = 0; pass < 16; pass++)

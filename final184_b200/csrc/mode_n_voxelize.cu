@@ -7,39 +7,28 @@
 // averaged, and the result does not depend on scheduling.
 //
 // B200 design
-//   * triangle-parallel, one launch: each lane sets one triangle up (transform, snap to the 1/256-voxel
-//     lattice, integer normal, dominant axis); the warp then drains its 32 triangles one at a time with
-//     lanes striding over the COLUMNS of the dominant-axis projection (work ~ projected area, so a wall
-//     spanning 10^4 columns costs the same per column as a sub-voxel triangle), 1-4 candidate voxels per
-//     column decided by an exact int64 separating-axis test.
+//   * triangle-parallel binning + rasterisation in two launches.  Pass 1 (one thread per triangle) transforms,
+//     snaps to the 1/256-voxel lattice and takes the integer normal / dominant axis; triangles whose
+//     dominant-axis projection covers <= 8 columns (the bulk of a detailed mesh) are finished by that thread,
+//     larger ones are queued as equal 256-column tasks.  Pass 2 (persistent warps) drains the tasks with
+//     lanes striding the columns, so work ~ projected area and a wall spanning 10^5 columns is spread over
+//     the chip instead of serialising a warp (the first version of this kernel took 168 ms on Sponza 512^3
+//     for exactly that reason).  The triangle set-up lives in registers, in the triangle's own (u, v, w)
+//     frame, so the exact int64 separating-axis test runs on IMAD.WIDE with no local-memory indexing;
+//     the three axes in the projection plane are tested once per column, the other ten per candidate depth.
 //   * accumulation uses the sm_90+ 16-byte vector reduction red.global.add.v4.f32 (atomicAdd(float4*)):
 //     two of them per fragment (colour+count, normal) instead of seven scalar atomics.  Every addend is an
 //     integer (8-bit colour, 8-bit signed normal, 1) so the fp32 sums are exact for < 2^16 fragments per
 //     voxel: order-independent, bit-reproducible, and a multi-GPU sum of partial volumes is exact too.
 //   * accumulators are brick-major (8^3 voxels contiguous, 8 KB per brick per volume); a per-brick flag
-//     records what was touched so normalise reads, converts and re-zeroes only touched bricks — the dense
-//     32 B/voxel volume is never streamed (at 512^3 that alone would be 1.3 ms of HBM time).
+//     records what was touched; a compaction pass turns the flags into a brick list and normalise (one warp
+//     per listed brick) reads, converts and re-zeroes only those — the dense 32 B/voxel volume is never
+//     streamed (at 512^3 that alone would be 1.3 ms of HBM time).
 #include <algorithm>
 
 #include "f184_device.cuh"
 
 namespace {
-
-constexpr int WARPS_PER_BLOCK = 4;
-
-struct TriN
-{
-    int v[3][3];             // snapped vertices (1/256 voxel)
-    long long n[3];          // integer normal
-    long long eu[3], ev[3];  // sign-normalised 2D edges in the projection
-    long long area;
-    int lo[3], hi[3];
-    float u[3], vv[3];
-    f3 nrm[3];
-    float dudx, dvdx, dudy, dvdy;
-    uint16_t mat;
-    uint8_t d, pad;
-};
 
 __device__ __forceinline__ f4 bilinear_level(const TexDev& t, uint32_t level, float u, float v)
 {
@@ -79,54 +68,10 @@ __device__ __forceinline__ f4 sample_trilinear(const TexDev& t, float u, float v
     return {c0.x * (1.0f - f) + c1.x * f, c0.y * (1.0f - f) + c1.y * f, c0.z * (1.0f - f) + c1.z * f, c0.w * (1.0f - f) + c1.w * f};
 }
 
-__device__ __forceinline__ long long lmin3(long long a, long long b, long long c) { return min(a, min(b, c)); }
-__device__ __forceinline__ long long lmax3(long long a, long long b, long long c) { return max(a, max(b, c)); }
-
-// Exact triangle / closed-box overlap on the integer lattice (Akenine-Moller SAT, 13 axes).
-__device__ bool tri_box_overlap(const TriN& s, int bx, int by, int bz)
-{
-    long long p[3][3];
-    const int c[3] = {256 * bx + 128, 256 * by + 128, 256 * bz + 128};
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-#pragma unroll
-        for (int a = 0; a < 3; a++) p[k][a] = (long long)(s.v[k][a] - c[a]);
-    const long long hs = 128;
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-    {
-        if (lmin3(p[0][a], p[1][a], p[2][a]) > hs || lmax3(p[0][a], p[1][a], p[2][a]) < -hs) return false;
-    }
-    {
-        const long long d = s.n[0] * p[0][0] + s.n[1] * p[0][1] + s.n[2] * p[0][2];
-        const long long r = hs * (llabs(s.n[0]) + llabs(s.n[1]) + llabs(s.n[2]));
-        if (d > r || d < -r) return false;
-    }
-#pragma unroll
-    for (int e = 0; e < 3; e++)
-    {
-        const int e1 = (e + 1) % 3;
-        const long long ex = p[e1][0] - p[e][0], ey = p[e1][1] - p[e][1], ez = p[e1][2] - p[e][2];
-        {   // axis (0, -ez, ey)
-            const long long q0 = -ez * p[0][1] + ey * p[0][2], q1 = -ez * p[1][1] + ey * p[1][2], q2 = -ez * p[2][1] + ey * p[2][2];
-            const long long r = hs * (llabs(ez) + llabs(ey));
-            if (lmin3(q0, q1, q2) > r || lmax3(q0, q1, q2) < -r) return false;
-        }
-        {   // axis (ez, 0, -ex)
-            const long long q0 = ez * p[0][0] - ex * p[0][2], q1 = ez * p[1][0] - ex * p[1][2], q2 = ez * p[2][0] - ex * p[2][2];
-            const long long r = hs * (llabs(ez) + llabs(ex));
-            if (lmin3(q0, q1, q2) > r || lmax3(q0, q1, q2) < -r) return false;
-        }
-        {   // axis (-ey, ex, 0)
-            const long long q0 = -ey * p[0][0] + ex * p[0][1], q1 = -ey * p[1][0] + ex * p[1][1], q2 = -ey * p[2][0] + ex * p[2][1];
-            const long long r = hs * (llabs(ey) + llabs(ex));
-            if (lmin3(q0, q1, q2) > r || lmax3(q0, q1, q2) < -r) return false;
-        }
-    }
-    return true;
-}
-
 __device__ __forceinline__ int floor_div256(int a) { return a >> 8; }
+__device__ __forceinline__ int pick3(int a0, int a1, int a2, int k) { return k == 0 ? a0 : (k == 1 ? a1 : a2); }
+__device__ __forceinline__ long long pick3l(long long a0, long long a1, long long a2, int k) { return k == 0 ? a0 : (k == 1 ? a1 : a2); }
+__device__ __forceinline__ long long wide(int a, int b) { return (long long)a * (long long)b; }   // one IMAD.WIDE
 
 __device__ __forceinline__ size_t brick_major(int x, int y, int z, int NB)
 {
@@ -134,173 +79,317 @@ __device__ __forceinline__ size_t brick_major(int x, int y, int z, int NB)
     return brick * 512 + ((z & 7) << 6) + ((y & 7) << 3) + (x & 7);
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_voxelize_n(const float* __restrict__ pos, const float* __restrict__ nrm, const float* __restrict__ uv,
-             const uint32_t* __restrict__ idx, const uint16_t* __restrict__ tri_mat, const uint16_t* __restrict__ tri_model,
-             const M4* __restrict__ model_mats, const M4* __restrict__ vm_mats, M4 Proj, const TexDev* __restrict__ texs,
-             const MatDev* __restrict__ mats, uint32_t tri_first, uint32_t tri_end, int N,
-             float4* __restrict__ accC, float4* __restrict__ accN, uint32_t* __restrict__ brick_flags,
-             unsigned long long* __restrict__ frag_counter)
+// Triangle set-up, held in REGISTERS.  Everything is stored in the triangle's own frame (u, v, w) =
+// (axis d+1, axis d+2, dominant axis d): a cyclic relabelling of x, y, z, under which the 13 separating axes of
+// the triangle/box test map onto themselves — so the exact integer predicate below is the oracle's
+// tri_box_overlap() evaluated in other coordinates — and every index is a compile-time constant.
+struct TriS
 {
-    __shared__ TriN sh[WARPS_PER_BLOCK][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t t = tri_first + (blockIdx.x * WARPS_PER_BLOCK + warp) * 32 + lane;
-    const float Nf = (float)N;
-    const int NB = N >> 3;
-    bool active = false;
+    int v[3][3];             // snapped vertices (1/256 voxel), [vertex][u,v,w]
+    long long n[3];          // integer normal (u, v, w components); n[2] is the largest in magnitude
+    long long area;          // |n[2]|
+    int sg;                  // sign of n[2]
+    int lo[3], hi[3];        // candidate voxel range per axis (u, v, w), clipped to the grid
+    float u[3], vv[3];
+    f3 nrm[3];
+    float dudx, dvdx, dudy, dvdy;
+    uint32_t mat;
+    int d;
+};
 
-    if (t < tri_end)
+struct VoxArgs
+{
+    const float *pos, *nrm, *uv;
+    const uint32_t* idx;
+    const uint16_t *tri_mat, *tri_model;
+    const M4 *model_mats, *vm_mats;
+    M4 Proj;
+    const TexDev* texs;
+    const MatDev* mats;
+    uint32_t tri_first, tri_end;
+    int N;
+    float4 *accC, *accN;
+    uint32_t* brick_flags;
+    unsigned long long* frag_counter;
+    unsigned long long* queue_state;   // (entries << 40) | tasks, one 64-bit word so both advance together
+    uint2* queue;                      // per large triangle: (triangle, first task)
+};
+
+constexpr int SETUP_THREADS = 128;
+constexpr int SMALL_COLS = 8;          // triangles up to this many projection columns are finished by their set-up thread
+constexpr int TASK_COLS = 256;         // columns per warp task for the larger ones
+constexpr int RASTER_THREADS = 128;
+
+// Returns false when the triangle produces nothing (outside the guard band, zero area after snapping, off-grid).
+__device__ __forceinline__ bool setup_triangle(const VoxArgs& A, uint32_t t, TriS& s)
+{
+    const float Nf = (float)A.N;
+    const uint32_t id0 = __ldg(A.idx + 3 * t), id1 = __ldg(A.idx + 3 * t + 1), id2 = __ldg(A.idx + 3 * t + 2);
+    const uint32_t id[3] = {id0, id1, id2};
+    const uint32_t model = __ldg(A.tri_model + t);
+    const M4& vm = A.vm_mats[model];
+    int vi[3][3];
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
     {
-        const uint32_t id[3] = {idx[3 * t], idx[3 * t + 1], idx[3 * t + 2]};
-        const uint32_t model = tri_model[t];
-        const M4& vm = vm_mats[model];
-        TriN& s = sh[warp][lane];
-        bool bad = false;
+        f3 q = mul43(vm, f3{__ldg(A.pos + 3 * id[i]), __ldg(A.pos + 3 * id[i] + 1), __ldg(A.pos + 3 * id[i] + 2)}, 1.0f);
+        f4 g = mul44(A.Proj, f4{q.x, q.y, q.z, 1.0f});
+        const float gx = g.x / g.w, gy = g.y / g.w, gz = g.z / g.w;
+        const float vx = (gx * 0.5f + 0.5f) * Nf, vy = (gy * 0.5f + 0.5f) * Nf, vz = gz * Nf;
+        if (!(vx >= -Nf && vx < 2.0f * Nf) || !(vy >= -Nf && vy < 2.0f * Nf) || !(vz >= -Nf && vz < 2.0f * Nf)) bad = true;
+        vi[i][0] = (int)rintf(vx * 256.0f); vi[i][1] = (int)rintf(vy * 256.0f); vi[i][2] = (int)rintf(vz * 256.0f);
+    }
+    if (bad) return false;
+    int e1[3], e2[3];
 #pragma unroll
-        for (int i = 0; i < 3; i++)
+    for (int a = 0; a < 3; a++) { e1[a] = vi[1][a] - vi[0][a]; e2[a] = vi[2][a] - vi[0][a]; }
+    const long long n0 = wide(e1[1], e2[2]) - wide(e1[2], e2[1]);
+    const long long n1 = wide(e1[2], e2[0]) - wide(e1[0], e2[2]);
+    const long long n2 = wide(e1[0], e2[1]) - wide(e1[1], e2[0]);
+    if (n0 == 0 && n1 == 0 && n2 == 0) return false;
+    const long long anx = llabs(n0), any = llabs(n1), anz = llabs(n2);
+    int d;
+    if (anx > any) d = (anx > anz) ? 0 : 2;
+    else d = (any > anz) ? 1 : 2;
+    const int ua = (d + 1) % 3, va = (d + 2) % 3;
+    bool empty = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+    {
+        s.v[k][0] = pick3(vi[k][0], vi[k][1], vi[k][2], ua);
+        s.v[k][1] = pick3(vi[k][0], vi[k][1], vi[k][2], va);
+        s.v[k][2] = pick3(vi[k][0], vi[k][1], vi[k][2], d);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+    {
+        const int mn = min(s.v[0][a], min(s.v[1][a], s.v[2][a])), mx = max(s.v[0][a], max(s.v[1][a], s.v[2][a]));
+        s.lo[a] = max(0, floor_div256(mn - 1));
+        s.hi[a] = min(A.N - 1, floor_div256(mx));
+        if (s.lo[a] > s.hi[a]) empty = true;
+    }
+    if (empty) return false;
+    s.n[0] = pick3l(n0, n1, n2, ua); s.n[1] = pick3l(n0, n1, n2, va); s.n[2] = pick3l(n0, n1, n2, d);
+    s.sg = s.n[2] < 0 ? -1 : 1;
+    s.area = s.n[2] * s.sg;
+    s.d = d;
+    const M4& mm = A.model_mats[model];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        s.u[i] = __ldg(A.uv + 2 * id[i]); s.vv[i] = __ldg(A.uv + 2 * id[i] + 1);
+        s.nrm[i] = normalize3(mul33(mm, f3{__ldg(A.nrm + 3 * id[i]), __ldg(A.nrm + 3 * id[i] + 1), __ldg(A.nrm + 3 * id[i] + 2)}));
+    }
+    const float areaf = (float)s.area;
+    float dbdu[3], dbdv[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+    {
+        const int a = (k + 1) % 3, b = (k + 2) % 3;
+        const long long eu = (long long)s.sg * (s.v[b][0] - s.v[a][0]), ev = (long long)s.sg * (s.v[b][1] - s.v[a][1]);
+        dbdu[k] = (float)(-ev * 256) / areaf; dbdv[k] = (float)(eu * 256) / areaf;
+    }
+    s.dudx = (s.u[0] * dbdu[0] + s.u[1] * dbdu[1]) + s.u[2] * dbdu[2];
+    s.dvdx = (s.vv[0] * dbdu[0] + s.vv[1] * dbdu[1]) + s.vv[2] * dbdu[2];
+    s.dudy = (s.u[0] * dbdv[0] + s.u[1] * dbdv[1]) + s.u[2] * dbdv[2];
+    s.dvdy = (s.vv[0] * dbdv[0] + s.vv[1] * dbdv[1]) + s.vv[2] * dbdv[2];
+    s.mat = __ldg(A.tri_mat + t);
+    return true;
+}
+
+// One column (iu, iv) of the triangle's dominant-axis projection: exact closed-box overlap (Akenine-Moller SAT on
+// the integer lattice, all 13 axes) for every candidate depth, shading and accumulation of the voxels that pass.
+__device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const TriS& s, const MatDev& mat, int iu, int iv)
+{
+    const int hs = 128;
+    const int cu = 256 * iu + 128, cv = 256 * iv + 128;
+    // -- the three axes that live in the (u, v) plane do not depend on the depth: test them once per column.
+    //    W[k] = edge function of edge (k+1 -> k+2) at the column centre, orientation-normalised (inside >= 0);
+    //    the separating-axis interval test for that edge reads  -r <= W <= area + r,  r = hs (|eu| + |ev|).
+    long long Wk[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+    {
+        const int a = (k + 1) % 3, b = (k + 2) % 3;
+        const int eu = s.sg * (s.v[b][0] - s.v[a][0]), ev = s.sg * (s.v[b][1] - s.v[a][1]);
+        const long long w = wide(eu, cv - s.v[a][1]) - wide(ev, cu - s.v[a][0]);
+        const long long r = (long long)hs * (abs(eu) + abs(ev));
+        if (w < -r || w > s.area + r) return 0;
+        Wk[k] = w;
+    }
+    // -- depth candidates: the plane over the column footprint, in float, widened by a voxel; the integer tests decide
+    float dmin = 3.0e38f, dmax = -3.0e38f;
+    {
+        const float inv_nw = 1.0f / (float)s.n[2];
+        const float su = (float)s.n[0] * inv_nw, sv = (float)s.n[1] * inv_nw;
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++)
         {
-            f3 q = mul43(vm, f3{pos[3 * id[i]], pos[3 * id[i] + 1], pos[3 * id[i] + 2]}, 1.0f);
-            f4 g = mul44(Proj, f4{q.x, q.y, q.z, 1.0f});
-            const float gx = g.x / g.w, gy = g.y / g.w, gz = g.z / g.w;
-            const float vx = (gx * 0.5f + 0.5f) * Nf, vy = (gy * 0.5f + 0.5f) * Nf, vz = gz * Nf;
-            if (!(vx >= -Nf && vx < 2.0f * Nf) || !(vy >= -Nf && vy < 2.0f * Nf) || !(vz >= -Nf && vz < 2.0f * Nf)) bad = true;
-            s.v[i][0] = (int)rintf(vx * 256.0f); s.v[i][1] = (int)rintf(vy * 256.0f); s.v[i][2] = (int)rintf(vz * 256.0f);
-        }
-        if (!bad)
-        {
-            long long e1[3], e2[3];
-#pragma unroll
-            for (int a = 0; a < 3; a++) { e1[a] = (long long)s.v[1][a] - s.v[0][a]; e2[a] = (long long)s.v[2][a] - s.v[0][a]; }
-            s.n[0] = e1[1] * e2[2] - e1[2] * e2[1];
-            s.n[1] = e1[2] * e2[0] - e1[0] * e2[2];
-            s.n[2] = e1[0] * e2[1] - e1[1] * e2[0];
-            if (s.n[0] != 0 || s.n[1] != 0 || s.n[2] != 0)
-            {
-                const long long anx = llabs(s.n[0]), any = llabs(s.n[1]), anz = llabs(s.n[2]);
-                int d;
-                if (anx > any) d = (anx > anz) ? 0 : 2;
-                else d = (any > anz) ? 1 : 2;
-                const int ua = (d + 1) % 3, va = (d + 2) % 3;
-                bool empty = false;
-#pragma unroll
-                for (int a = 0; a < 3; a++)
-                {
-                    const int mn = min(s.v[0][a], min(s.v[1][a], s.v[2][a])), mx = max(s.v[0][a], max(s.v[1][a], s.v[2][a]));
-                    s.lo[a] = max(0, floor_div256(mn - 1));
-                    s.hi[a] = min(N - 1, floor_div256(mx));
-                    if (s.lo[a] > s.hi[a]) empty = true;
-                }
-                if (!empty)
-                {
-                    active = true;
-                    long long area = s.n[d];
-                    const long long sg = area < 0 ? -1 : 1;
-                    area *= sg;
-                    s.area = area;
-#pragma unroll
-                    for (int k = 0; k < 3; k++)
-                    {
-                        const int a = (k + 1) % 3, b = (k + 2) % 3;
-                        s.eu[k] = sg * ((long long)s.v[b][ua] - s.v[a][ua]);
-                        s.ev[k] = sg * ((long long)s.v[b][va] - s.v[a][va]);
-                    }
-                    const M4& mm = model_mats[model];
-#pragma unroll
-                    for (int i = 0; i < 3; i++)
-                    {
-                        s.u[i] = uv[2 * id[i]]; s.vv[i] = uv[2 * id[i] + 1];
-                        s.nrm[i] = normalize3(mul33(mm, f3{nrm[3 * id[i]], nrm[3 * id[i] + 1], nrm[3 * id[i] + 2]}));
-                    }
-                    const float areaf = (float)area;
-                    float dbdu[3], dbdv[3];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) { dbdu[k] = (float)(-s.ev[k] * 256) / areaf; dbdv[k] = (float)(s.eu[k] * 256) / areaf; }
-                    s.dudx = (s.u[0] * dbdu[0] + s.u[1] * dbdu[1]) + s.u[2] * dbdu[2];
-                    s.dvdx = (s.vv[0] * dbdu[0] + s.vv[1] * dbdu[1]) + s.vv[2] * dbdu[2];
-                    s.dudy = (s.u[0] * dbdv[0] + s.u[1] * dbdv[1]) + s.u[2] * dbdv[2];
-                    s.dvdy = (s.vv[0] * dbdv[0] + s.vv[1] * dbdv[1]) + s.vv[2] * dbdv[2];
-                    s.mat = tri_mat[t];
-                    s.d = (uint8_t)d;
-                }
-            }
+            const float xu = (float)(256 * (iu + (cc & 1)) - s.v[0][0]), xv = (float)(256 * (iv + (cc >> 1)) - s.v[0][1]);
+            const float xd = (float)s.v[0][2] - (su * xu + sv * xv);
+            dmin = fminf(dmin, xd); dmax = fmaxf(dmax, xd);
         }
     }
-    unsigned int pending = __ballot_sync(0xffffffffu, active);
-    __syncwarp();
+    const int k0 = max(s.lo[2], (int)floorf(dmin * (1.0f / 256.0f)) - 1), k1 = min(s.hi[2], (int)floorf(dmax * (1.0f / 256.0f)) + 1);
+    if (k0 > k1) return 0;
+    // plane: n . (v0 - c) = base - n_w * cw ; |.| <= hs (|n_u| + |n_v| + |n_w|)
+    const long long plane_r = (long long)hs * (llabs(s.n[0]) + llabs(s.n[1]) + llabs(s.n[2]));
+    const long long plane_uv = s.n[0] * (long long)(s.v[0][0] - cu) + s.n[1] * (long long)(s.v[0][1] - cv);
     unsigned int frags = 0;
-    while (pending)
+    float bc[3];
+    bool shaded = false;
+    float u = 0.f, v = 0.f;
+    f3 nn = {0.f, 0.f, 0.f};
+    f4 base = {0.f, 0.f, 0.f, 0.f};
+    for (int kd = k0; kd <= k1; kd++)
     {
-        const int src = __ffs(pending) - 1;
-        pending &= pending - 1;
-        const TriN& s = sh[warp][src];
-        const int d = s.d, ua = (d + 1) % 3, va = (d + 2) % 3;
-        const int bu = s.hi[ua] - s.lo[ua] + 1, bv = s.hi[va] - s.lo[va] + 1;
-        const int ncols = bu * bv;
-        const float areaf = (float)s.area;
-        const MatDev mat = mats[s.mat];
-        // plane: x_d = v0_d - (n_u (x_u - v0_u) + n_v (x_v - v0_v)) / n_d   (|n_d| is the largest component)
-        const double inv_nd = 1.0 / (double)s.n[d];
-        for (int col = lane; col < ncols; col += 32)
+        const int cw = 256 * kd + 128;
         {
-            const int iu = s.lo[ua] + col % bu, iv = s.lo[va] + col / bu;
-            // depth interval of the plane over the column footprint, widened by one voxel; the exact SAT decides
-            double dmin = 1e300, dmax = -1e300;
+            const long long dist = plane_uv + s.n[2] * (long long)(s.v[0][2] - cw);
+            if (dist > plane_r || dist < -plane_r) continue;
+        }
+        bool sep = false;
 #pragma unroll
-            for (int cc = 0; cc < 4; cc++)
-            {
-                const double xu = (double)(256 * (iu + (cc & 1)) - s.v[0][ua]), xv = (double)(256 * (iv + (cc >> 1)) - s.v[0][va]);
-                const double xd = (double)s.v[0][d] - ((double)s.n[ua] * xu + (double)s.n[va] * xv) * inv_nd;
-                dmin = fmin(dmin, xd); dmax = fmax(dmax, xd);
+        for (int e = 0; e < 3; e++)
+        {
+            const int e1 = (e + 1) % 3, o = (e + 2) % 3;
+            const int ex = s.v[e1][0] - s.v[e][0], ey = s.v[e1][1] - s.v[e][1], ez = s.v[e1][2] - s.v[e][2];
+            const int pe_u = s.v[e][0] - cu, pe_v = s.v[e][1] - cv, pe_w = s.v[e][2] - cw;
+            const int po_u = s.v[o][0] - cu, po_v = s.v[o][1] - cv, po_w = s.v[o][2] - cw;
+            {   // axis (0, -ez, ey): the edge's two end points project to the same value
+                const long long qa = wide(ey, pe_w) - wide(ez, pe_v), qo = wide(ey, po_w) - wide(ez, po_v);
+                const long long r = (long long)hs * (abs(ez) + abs(ey));
+                if (min(qa, qo) > r || max(qa, qo) < -r) sep = true;
             }
-            int k0 = max(s.lo[d], (int)floor(dmin / 256.0) - 1), k1 = min(s.hi[d], (int)floor(dmax / 256.0) + 1);
-            for (int kd = k0; kd <= k1; kd++)
-            {
-                int b[3];
-                b[ua] = iu; b[va] = iv; b[d] = kd;
-                if (!tri_box_overlap(s, b[0], b[1], b[2])) continue;
-                // barycentrics of the voxel centre in the projection, clamped into the triangle
-                const long long cu = 256 * iu + 128, cv = 256 * iv + 128;
-                float bc[3];
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                {
-                    const int a = (k + 1) % 3;
-                    const long long w = s.eu[k] * (cv - s.v[a][va]) - s.ev[k] * (cu - s.v[a][ua]);
-                    bc[k] = (float)w / areaf;
-                    if (bc[k] < 0.0f) bc[k] = 0.0f;
-                }
-                const float sum = (bc[0] + bc[1]) + bc[2];
-                bc[0] = bc[0] / sum; bc[1] = bc[1] / sum; bc[2] = bc[2] / sum;
-                const float u = (s.u[0] * bc[0] + s.u[1] * bc[1]) + s.u[2] * bc[2];
-                const float v = (s.vv[0] * bc[0] + s.vv[1] * bc[1]) + s.vv[2] * bc[2];
-                f3 nn = {(s.nrm[0].x * bc[0] + s.nrm[1].x * bc[1]) + s.nrm[2].x * bc[2], (s.nrm[0].y * bc[0] + s.nrm[1].y * bc[1]) + s.nrm[2].y * bc[2],
-                         (s.nrm[0].z * bc[0] + s.nrm[1].z * bc[1]) + s.nrm[2].z * bc[2]};
-                f4 base;
-                if (!mat.use_textures) base = {mat.factor[0], mat.factor[1], mat.factor[2], mat.factor[3]};
-                else
-                {
-                    f4 sc = {0.f, 0.f, 0.f, 0.f};
-                    if (mat.tex >= 0) sc = sample_trilinear(texs[mat.tex], u, v, s.dudx, s.dvdx, s.dudy, s.dvdy);
-                    base = {sc.x * mat.factor[0], sc.y * mat.factor[1], sc.z * mat.factor[2], sc.w * mat.factor[3]};
-                    if (base.w < 0.05f) continue;                       // main.lua:199
-                }
-                const float ax = fabsf(nn.x), ay = fabsf(nn.y), az = fabsf(nn.z);
-                const float lead = (ax >= ay && ax >= az) ? nn.x : ((ay >= az) ? nn.y : nn.z);
-                if (lead < 0.0f) nn = neg3(nn);
-                const float r8 = floorf(dm_clamp(base.x, 0.0f, 1.0f) * 255.0f + 0.5f);
-                const float g8 = floorf(dm_clamp(base.y, 0.0f, 1.0f) * 255.0f + 0.5f);
-                const float b8 = floorf(dm_clamp(base.z, 0.0f, 1.0f) * 255.0f + 0.5f);
-                const float nx8 = rintf(dm_clamp(nn.x, -1.0f, 1.0f) * 127.0f), ny8 = rintf(dm_clamp(nn.y, -1.0f, 1.0f) * 127.0f),
-                            nz8 = rintf(dm_clamp(nn.z, -1.0f, 1.0f) * 127.0f);
-                const size_t o = brick_major(b[0], b[1], b[2], NB);
-                atomicAdd(accC + o, make_float4(r8, g8, b8, 1.0f));     // red.global.add.v4.f32
-                atomicAdd(accN + o, make_float4(nx8, ny8, nz8, 0.0f));
-                brick_flags[o >> 9] = 1u;
-                frags++;
+            {   // axis (ez, 0, -ex)
+                const long long qa = wide(ez, pe_u) - wide(ex, pe_w), qo = wide(ez, po_u) - wide(ex, po_w);
+                const long long r = (long long)hs * (abs(ez) + abs(ex));
+                if (min(qa, qo) > r || max(qa, qo) < -r) sep = true;
             }
         }
+        if (sep) continue;
+        if (!shaded)
+        {   // attributes depend on the column only: barycentrics of the column centre, clamped into the triangle
+            shaded = true;
+            const float areaf = (float)s.area;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+            {
+                bc[k] = (float)Wk[k] / areaf;
+                if (bc[k] < 0.0f) bc[k] = 0.0f;
+            }
+            const float sum = (bc[0] + bc[1]) + bc[2];
+            bc[0] = bc[0] / sum; bc[1] = bc[1] / sum; bc[2] = bc[2] / sum;
+            u = (s.u[0] * bc[0] + s.u[1] * bc[1]) + s.u[2] * bc[2];
+            v = (s.vv[0] * bc[0] + s.vv[1] * bc[1]) + s.vv[2] * bc[2];
+            nn = {(s.nrm[0].x * bc[0] + s.nrm[1].x * bc[1]) + s.nrm[2].x * bc[2], (s.nrm[0].y * bc[0] + s.nrm[1].y * bc[1]) + s.nrm[2].y * bc[2],
+                  (s.nrm[0].z * bc[0] + s.nrm[1].z * bc[1]) + s.nrm[2].z * bc[2]};
+            if (!mat.use_textures) base = {mat.factor[0], mat.factor[1], mat.factor[2], mat.factor[3]};
+            else
+            {
+                f4 sc = {0.f, 0.f, 0.f, 0.f};
+                if (mat.tex >= 0) sc = sample_trilinear(A.texs[mat.tex], u, v, s.dudx, s.dvdx, s.dudy, s.dvdy);
+                base = {sc.x * mat.factor[0], sc.y * mat.factor[1], sc.z * mat.factor[2], sc.w * mat.factor[3]};
+                if (base.w < 0.05f) return frags;                   // main.lua:199 (alpha cut-out): nothing in this column
+            }
+            const float ax = fabsf(nn.x), ay = fabsf(nn.y), az = fabsf(nn.z);
+            const float lead = (ax >= ay && ax >= az) ? nn.x : ((ay >= az) ? nn.y : nn.z);
+            if (lead < 0.0f) nn = neg3(nn);
+        }
+        const float r8 = floorf(dm_clamp(base.x, 0.0f, 1.0f) * 255.0f + 0.5f);
+        const float g8 = floorf(dm_clamp(base.y, 0.0f, 1.0f) * 255.0f + 0.5f);
+        const float b8 = floorf(dm_clamp(base.z, 0.0f, 1.0f) * 255.0f + 0.5f);
+        const float nx8 = rintf(dm_clamp(nn.x, -1.0f, 1.0f) * 127.0f), ny8 = rintf(dm_clamp(nn.y, -1.0f, 1.0f) * 127.0f),
+                    nz8 = rintf(dm_clamp(nn.z, -1.0f, 1.0f) * 127.0f);
+        // back to x, y, z: axis (d+1)%3 = u, (d+2)%3 = v, d = w
+        const int bx = s.d == 0 ? kd : (s.d == 1 ? iv : iu);
+        const int by = s.d == 0 ? iu : (s.d == 1 ? kd : iv);
+        const int bz = s.d == 0 ? iv : (s.d == 1 ? iu : kd);
+        const size_t o = brick_major(bx, by, bz, A.N >> 3);
+        atomicAdd(A.accC + o, make_float4(r8, g8, b8, 1.0f));     // red.global.add.v4.f32
+        atomicAdd(A.accN + o, make_float4(nx8, ny8, nz8, 0.0f));
+        A.brick_flags[o >> 9] = 1u;
+        frags++;
     }
-    warp_count_add(frag_counter, frags);
+    return frags;
+}
+
+// ---- pass 1: one thread per triangle.  Sets the triangle up; finishes it on the spot when its projection is at
+// most SMALL_COLS columns (most of a detailed mesh at any practical grid), otherwise queues it as
+// ceil(columns / TASK_COLS) equal tasks for pass 2, so that a wall spanning 10^5 columns is spread over the
+// whole chip instead of serialising one warp.  Queue slots and task numbers are reserved by ONE 64-bit atomic per
+// warp, (entries << 40) | tasks, which keeps `first task` monotone in the entry index: pass 2 finds the triangle of
+// a task by binary search, no prefix-sum pass needed.
+__global__ void __launch_bounds__(SETUP_THREADS) k_voxelize_setup(const VoxArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t t = A.tri_first + blockIdx.x * SETUP_THREADS + threadIdx.x;
+    TriS s;
+    bool active = false;
+    if (t < A.tri_end) active = setup_triangle(A, t, s);
+    unsigned int frags = 0;
+    uint32_t ntasks = 0;
+    if (active)
+    {
+        const int bu = s.hi[0] - s.lo[0] + 1, bv = s.hi[1] - s.lo[1] + 1;
+        const int ncols = bu * bv;
+        if (ncols <= SMALL_COLS)
+        {
+            const MatDev mat = A.mats[s.mat];
+            for (int col = 0; col < ncols; col++) frags += process_column(A, s, mat, s.lo[0] + col % bu, s.lo[1] + col / bu);
+        }
+        else ntasks = (uint32_t)((ncols + TASK_COLS - 1) / TASK_COLS);
+    }
+    const unsigned int big = __ballot_sync(0xffffffffu, ntasks != 0);
+    if (big)
+    {
+        uint32_t incl = ntasks;                         // inclusive warp scan of the task counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long old = 0;
+        if (lane == 0) old = atomicAdd(A.queue_state, ((unsigned long long)__popc(big) << 40) | total);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (ntasks)
+        {
+            const uint32_t slot = (uint32_t)(old >> 40) + __popc(big & ((1u << lane) - 1u));
+            A.queue[slot] = make_uint2(t, (uint32_t)(old & 0xffffffffffull) + incl - ntasks);
+        }
+    }
+    warp_count_add(A.frag_counter, frags);
+}
+
+// ---- pass 2: persistent warps, one task (TASK_COLS columns of one triangle) at a time; lanes stride the columns.
+__global__ void __launch_bounds__(RASTER_THREADS, 4) k_voxelize_raster(const VoxArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t gwarp = (blockIdx.x * RASTER_THREADS + threadIdx.x) >> 5, nwarps = (gridDim.x * RASTER_THREADS) >> 5;
+    const unsigned long long st = *A.queue_state;
+    const uint32_t n_entries = (uint32_t)(st >> 40), n_tasks = (uint32_t)(st & 0xffffffffffull);
+    unsigned int frags = 0;
+    for (uint32_t task = gwarp; task < n_tasks; task += nwarps)
+    {
+        uint32_t lo = 0, hi = n_entries;                // last entry whose first task <= task
+        while (hi - lo > 1)
+        {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&A.queue[mid].y) <= task) lo = mid; else hi = mid;
+        }
+        const uint2 e = __ldg(A.queue + lo);
+        TriS s;
+        if (!setup_triangle(A, e.x, s)) continue;       // cannot happen (it was queued); keeps the compiler honest
+        const MatDev mat = A.mats[s.mat];
+        const int bu = s.hi[0] - s.lo[0] + 1, bv = s.hi[1] - s.lo[1] + 1;
+        const int ncols = bu * bv;
+        const int c0 = (int)(task - e.y) * TASK_COLS, c1 = min(ncols, c0 + TASK_COLS);
+        for (int col = c0 + lane; col < c1; col += 32) frags += process_column(A, s, mat, s.lo[0] + col % bu, s.lo[1] + col / bu);
+    }
+    warp_count_add(A.frag_counter, frags);
 }
 
 // vm[m] = View * Model[m] (same association as mode R)
@@ -313,74 +402,84 @@ __global__ void k_view_model_n(M4 View, const M4* __restrict__ model, M4* __rest
     vm[m].m[4 * j + r] = ((View.m[r] * B.m[4 * j] + View.m[4 + r] * B.m[4 * j + 1]) + View.m[8 + r] * B.m[4 * j + 2]) + View.m[12 + r] * B.m[4 * j + 3];
 }
 
-// ---- B.2 normalise: touched (or previously occupied) bricks only ----------------------------------------
-// One warp per brick, 16 passes of 32 voxels: 512 B coalesced accumulator reads, 32 B output runs.
-// Reads the sums, writes mean albedo / unit normal as RGBA8, re-zeroes the accumulators (= next frame's
-// clear) and appends the brick to the frame's brick list for the stages downstream.
+// ---- B.2 normalise, sparse: only bricks touched this frame or last frame ---------------------------------
+// pass 1: one thread per brick flag -> compact list (warp-aggregated append).  Entry = brick | touched << 31.
 __global__ void __launch_bounds__(256)
-k_normalise_n(float4* __restrict__ accC, float4* __restrict__ accN, uint32_t* __restrict__ brick_flags, uint32_t* __restrict__ brick_prev,
-              uchar4* __restrict__ alb, char4* __restrict__ nrm, uint32_t* __restrict__ brick_list, unsigned long long* __restrict__ counters,
-              int N, uint32_t n_bricks)
+k_brick_compact(uint32_t* __restrict__ brick_flags, uint32_t* __restrict__ brick_prev, uint32_t* __restrict__ brick_list,
+                unsigned long long* __restrict__ counters, uint32_t n_bricks)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t flag = 0, prev = 0;
+    if (bi < n_bricks) { flag = brick_flags[bi]; prev = brick_prev[bi]; }
+    if (flag | prev) { brick_flags[bi] = 0; brick_prev[bi] = flag; }
+    const unsigned int todo = __ballot_sync(0xffffffffu, (flag | prev) != 0);
+    const unsigned int touched = __ballot_sync(0xffffffffu, flag != 0);
+    if (!todo) return;
+    unsigned long long slot = 0;
+    if (lane == 0)
+    {
+        slot = atomicAdd(counters + F184_COUNTER_COUNT, (unsigned long long)__popc(todo));   // list cursor lives past the public counters
+        if (touched) atomicAdd(counters + F184_COUNTER_BRICKS, (unsigned long long)__popc(touched));
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (flag | prev) brick_list[(uint32_t)slot + __popc(todo & ((1u << lane) - 1u))] = bi | (flag ? 0x80000000u : 0u);
+}
+
+// pass 2: one warp per listed brick, 16 passes of 32 voxels: 512 B coalesced accumulator reads, 32 B output runs.
+// Reads the sums, writes mean albedo / unit normal as RGBA8 and re-zeroes the accumulators (= next frame's clear).
+__global__ void __launch_bounds__(256)
+k_normalise_n(float4* __restrict__ accC, float4* __restrict__ accN, uchar4* __restrict__ alb, char4* __restrict__ nrm,
+              const uint32_t* __restrict__ brick_list, unsigned long long* __restrict__ counters, int N)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t count = (uint32_t)counters[F184_COUNTER_COUNT];
     const int NB = N >> 3;
-    unsigned int occ = 0, nbricks = 0;
-    for (uint32_t base = warp_global * 32; base < n_bricks; base += n_warps * 32)
+    unsigned int occ = 0;
+    for (uint32_t i = warp_global; i < count; i += n_warps)
     {
-        const uint32_t bi = base + lane;
-        uint32_t flag = 0, prev = 0;
-        if (bi < n_bricks) { flag = brick_flags[bi]; prev = brick_prev[bi]; }
-        if (bi < n_bricks && (flag | prev)) { brick_flags[bi] = 0; brick_prev[bi] = flag; }
-        unsigned int todo = __ballot_sync(0xffffffffu, (flag | prev) != 0);
-        const unsigned int touched = __ballot_sync(0xffffffffu, flag != 0);
-        nbricks += (lane == 0) ? __popc(touched) : 0;
-        if (lane == 0 && todo)
+        const uint32_t entry = __ldg(brick_list + i);
+        const uint32_t b = entry & 0x7fffffffu;
+        const bool is_touched = (entry >> 31) != 0;
+        const int bx = (b % NB) << 3, by = ((b / NB) % NB) << 3, bz = (b / (NB * NB)) << 3;
+        float4 cs[16];
+        if (is_touched)
         {
-            const uint32_t cnt = __popc(todo);
-            const uint32_t slot = (uint32_t)atomicAdd(counters + F184_COUNTER_COUNT, (unsigned long long)cnt);   // list cursor lives past the counters
-            uint32_t k = 0;
-            for (unsigned int m = todo; m; m &= m - 1) brick_list[slot + k++] = base + (__ffs(m) - 1);
+#pragma unroll
+            for (int pass = 0; pass < 16; pass++) cs[pass] = accC[(size_t)b * 512 + pass * 32 + lane];
         }
-        while (todo)
+#pragma unroll
+        for (int pass = 0; pass < 16; pass++)
         {
-            const uint32_t b = base + (__ffs(todo) - 1);
-            const bool is_touched = (touched >> (__ffs(todo) - 1)) & 1u;
-            todo &= todo - 1;
-            const int bx = (b % NB) << 3, by = ((b / NB) % NB) << 3, bz = (b / (NB * NB)) << 3;
-#pragma unroll 4
-            for (int pass = 0; pass < 16; pass++)
+            const int local = pass * 32 + lane;                 // (z&7)<<6 | (y&7)<<3 | (x&7)
+            const size_t o = (size_t)b * 512 + local;
+            uchar4 a8 = make_uchar4(0, 0, 0, 0);
+            char4 n8 = make_char4(0, 0, 0, 0);
+            if (is_touched)
             {
-                const int local = pass * 32 + lane;                 // (z&7)<<6 | (y&7)<<3 | (x&7)
-                const size_t o = (size_t)b * 512 + local;
-                uchar4 a8 = make_uchar4(0, 0, 0, 0);
-                char4 n8 = make_char4(0, 0, 0, 0);
-                if (is_touched)
+                const float4 c = cs[pass];
+                if (c.w > 0.0f)
                 {
-                    const float4 c = accC[o];
-                    if (c.w > 0.0f)
-                    {
-                        const float4 nn = accN[o];
-                        a8 = make_uchar4((unsigned char)floorf(c.x / c.w + 0.5f), (unsigned char)floorf(c.y / c.w + 0.5f),
-                                         (unsigned char)floorf(c.z / c.w + 0.5f), 255);
-                        const float len = __fsqrt_rn((nn.x * nn.x + nn.y * nn.y) + nn.z * nn.z);
-                        if (len > 0.0f)
-                            n8 = make_char4((signed char)rintf(nn.x / len * 127.0f), (signed char)rintf(nn.y / len * 127.0f),
-                                            (signed char)rintf(nn.z / len * 127.0f), 0);
-                        accC[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        accN[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        occ++;
-                    }
+                    const float4 nn = accN[o];
+                    a8 = make_uchar4((unsigned char)floorf(c.x / c.w + 0.5f), (unsigned char)floorf(c.y / c.w + 0.5f),
+                                     (unsigned char)floorf(c.z / c.w + 0.5f), 255);
+                    const float len = __fsqrt_rn((nn.x * nn.x + nn.y * nn.y) + nn.z * nn.z);
+                    if (len > 0.0f)
+                        n8 = make_char4((signed char)rintf(nn.x / len * 127.0f), (signed char)rintf(nn.y / len * 127.0f),
+                                        (signed char)rintf(nn.z / len * 127.0f), 0);
+                    accC[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    accN[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    occ++;
                 }
-                const int x = bx + (local & 7), y = by + ((local >> 3) & 7), z = bz + (local >> 6);
-                const size_t lin = ((size_t)z * N + y) * N + x;
-                alb[lin] = a8;
-                nrm[lin] = n8;
             }
+            const int x = bx + (local & 7), y = by + ((local >> 3) & 7), z = bz + (local >> 6);
+            const size_t lin = ((size_t)z * N + y) * N + x;
+            alb[lin] = a8;
+            nrm[lin] = n8;
         }
     }
     warp_count_add(counters + F184_COUNTER_OCCUPIED, occ);
-    warp_count_add(counters + F184_COUNTER_BRICKS, nbricks);
 }
 
 }  // namespace
@@ -400,12 +499,21 @@ int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
         CK(c, cudaMemsetAsync(c->brick_prev, 0, 4ull * n_bricks, c->stream));
         CK(c, cudaMalloc(&c->brick_list, 4ull * n_bricks));
     }
-    M4 View, Proj;
+    if (c->vox_queue_cap < c->n_tris)
+    {
+        if (c->vox_queue) cudaFree(c->vox_queue);
+        CK(c, cudaMalloc(&c->vox_queue, 8ull * c->n_tris));
+        c->vox_queue_cap = c->n_tris;
+    }
+    if (c->vm_cap < c->n_models)
+    {
+        if (c->vm_dev) cudaFree(c->vm_dev);
+        CK(c, cudaMalloc(&c->vm_dev, sizeof(M4) * c->n_models));
+        c->vm_cap = c->n_models;
+    }
+    M4 View;
     memcpy(View.m, cam->ViewMat, 64);
-    memcpy(Proj.m, cam->ProjMat, 64);
-    M4* vm_dev = nullptr;
-    CK(c, cudaMallocAsync(&vm_dev, sizeof(M4) * c->n_models, c->stream));
-    k_view_model_n<<<(c->n_models * 16 + 127) / 128, 128, 0, c->stream>>>(View, c->model_mats, vm_dev, c->n_models);
+    k_view_model_n<<<(c->n_models * 16 + 127) / 128, 128, 0, c->stream>>>(View, c->model_mats, c->vm_dev, c->n_models);
     CK_LAUNCH(c);
 
     const uint32_t first = c->tri_first < c->n_tris ? c->tri_first : c->n_tris;
@@ -414,24 +522,31 @@ int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
 
     int rc = f184_stage_begin(c, F184_STAGE_VOXELIZE);
     if (rc) return rc;
-    // counters: fragments, occupied, bricks, and the brick-list cursor (stored right after the public counters)
+    // counters: fragments, occupied, bricks | brick-list cursor, voxelizer queue state (stored right after the public counters)
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_FRAGMENTS, 0, 8, c->stream));
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_OCCUPIED, 0, 8, c->stream));
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_BRICKS, 0, 8, c->stream));
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_COUNT, 0, 8, c->stream));
+    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_BRICKS, 0, 8 * 3, c->stream));   // BRICKS, list cursor, queue state
     if (end > first)
     {
+        VoxArgs A{};
+        A.pos = c->pos; A.nrm = c->nrm; A.uv = c->uv; A.idx = c->idx; A.tri_mat = c->tri_mat; A.tri_model = c->tri_model;
+        A.model_mats = c->model_mats; A.vm_mats = c->vm_dev;
+        memcpy(A.Proj.m, cam->ProjMat, 64);
+        A.texs = c->tex_dev; A.mats = c->mat_dev;
+        A.tri_first = first; A.tri_end = end; A.N = N;
+        A.accC = img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR); A.accN = img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL);
+        A.brick_flags = img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS);
+        A.frag_counter = c->counters_dev + F184_COUNTER_FRAGMENTS;
+        A.queue_state = c->counters_dev + F184_COUNTER_COUNT + 1;
+        A.queue = reinterpret_cast<uint2*>(c->vox_queue);
         const uint32_t tris = end - first;
-        const uint32_t blocks = (tris + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32);
-        k_voxelize_n<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->pos, c->nrm, c->uv, c->idx, c->tri_mat, c->tri_model, c->model_mats,
-                                                                     vm_dev, Proj, c->tex_dev, c->mat_dev, first, end, N,
-                                                                     img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
-                                                                     img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->counters_dev + F184_COUNTER_FRAGMENTS);
+        k_voxelize_setup<<<(tris + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, c->stream>>>(A);
+        CK_LAUNCH(c);
+        k_voxelize_raster<<<148 * 4 * 4, RASTER_THREADS, 0, c->stream>>>(A);
         CK_LAUNCH(c);
     }
     rc = f184_stage_end(c, F184_STAGE_VOXELIZE);
     if (rc) return rc;
-    CK(c, cudaFreeAsync(vm_dev, c->stream));
     if (c->defer_normalise) return F184_OK;      // multi-GPU: partial volumes are summed across ranks first
     return f184_normalise_n(c);
 }
@@ -442,11 +557,12 @@ int f184_normalise_n(f184_ctx* c)
     const uint32_t n_bricks = (uint32_t)(N / 8) * (N / 8) * (N / 8);
     int rc = f184_stage_begin(c, F184_STAGE_NORMALISE);
     if (rc) return rc;
-    const int blocks = (int)std::min<uint32_t>((n_bricks + 255) / 256, 148 * 8);
-    k_normalise_n<<<blocks, 256, 0, c->stream>>>(img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
-                                                 img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev,
-                                                 img_ptr<uchar4>(c, F184_SLOT_VOX_ALBEDO), img_ptr<char4>(c, F184_SLOT_VOX_NORMAL),
-                                                 c->brick_list, c->counters_dev, N, n_bricks);
+    k_brick_compact<<<(n_bricks + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,
+                                                                  c->counters_dev, n_bricks);
+    CK_LAUNCH(c);
+    k_normalise_n<<<148 * 8, 256, 0, c->stream>>>(img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
+                                                  img_ptr<uchar4>(c, F184_SLOT_VOX_ALBEDO), img_ptr<char4>(c, F184_SLOT_VOX_NORMAL),
+                                                  c->brick_list, c->counters_dev, N);
     CK_LAUNCH(c);
     return f184_stage_end(c, F184_STAGE_NORMALISE);
 }
