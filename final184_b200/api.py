@@ -154,6 +154,7 @@ _PRODUCT_ONLY = {
     "import_semaphores_fd": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "stage_time_reset": (C.c_int, [C.c_void_p, C.c_uint32]),
     "stage_time_total": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "debug_read_array": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "debug_detmath": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
 }
 EXPORTS = sorted(list(_SIGS) + list(_PRODUCT_ONLY))
@@ -268,6 +269,12 @@ class VoxelGI:
 
     def readback_async_ptr(self, slot, host_ptr, nbytes):
         self._ck(self.lib.readback_async(self.h, slot, host_ptr, nbytes), "readback_async")
+
+    def read_array(self, direction, level, n):
+        """Texture-side storage (what the tracer samples): direction < 0 -> level-0 radiance array, else mip `level`+1."""
+        out = np.empty((n, n, n, 4), np.uint8)
+        self._ck(self.lib.debug_read_array(self.h, direction, level, out.ctypes.data, out.nbytes), "debug_read_array")
+        return out
 
     def bind(self, slot, device_ptr, fmt, width, height, depth=1):
         d = ImageDesc(device_ptr, fmt, width, height, depth, 0, 0)

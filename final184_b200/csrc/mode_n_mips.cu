@@ -193,8 +193,7 @@ k_mips_tma(const __grid_constant__ CUtensorMap src_map, MipOut out, int n, int i
             if (gx < n && gy < n && gz < n)
             {
                 *reinterpret_cast<uint4*>(out.lin[d] + ((size_t)gz * n + gy) * n + gx) = make_uint4(o[0], o[1], o[2], o[3]);   // 16-byte store
-#pragma unroll
-                for (int q = 0; q < 4; q++) surf3Dwrite(o[q], out.surf[d], (gx + q) * 4, gy, gz);
+                surf3Dwrite(make_uint4(o[0], o[1], o[2], o[3]), out.surf[d], gx * 4, gy, gz);   // one 16-byte surface store = 4 texels
             }
         }
         __syncthreads();                       // everyone is done with this stage's tile
@@ -203,6 +202,128 @@ k_mips_tma(const __grid_constant__ CUtensorMap src_map, MipOut out, int n, int i
             const int next = item + STAGES * gridDim.x;
             if (next < n_items) issue(next, stage);
         }
+    }
+}
+
+
+// ---- sparse path: levels 1-3 straight from the listed 8^3 bricks ------------------------------------------
+// A 2x2x2 reduction never crosses an 8^3 brick boundary for three levels (8 -> 4 -> 2 -> 1), so one warp takes a
+// listed brick (touched this frame or last frame, normalise's list) from the level-0 radiance to its 4^3 x 6
+// level-1 texels, 2^3 x 6 level-2 texels and 1 x 6 level-3 texels without any halo; everything not listed is
+// zero at every level and is never read or written.  Sponza at 512^3 lists 12 % of the bricks, so this moves
+// ~0.1 GB where the dense chain moves 1.4 GB.  Levels >= 4 (edge N/16 and smaller) stay dense.
+struct BrickMipOut
+{
+    uint32_t* lin[3][6];               // level 1..3, six directions, linear chain
+    cudaSurfaceObject_t surf[3][6];
+};
+constexpr int BRICK_WARPS = 8;
+
+__global__ void __launch_bounds__(BRICK_WARPS * 32)
+k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ brick_list, const unsigned long long* __restrict__ brick_count,
+              BrickMipOut out, int N)
+{
+    __shared__ __align__(16) uint32_t sh0[BRICK_WARPS][512];       // the brick, [z][y][x]
+    __shared__ __align__(16) uint32_t sh1[BRICK_WARPS][6][64];     // level 1 per direction, [z][y][x] 4^3
+    __shared__ __align__(16) uint32_t sh2[BRICK_WARPS][6][8];      // level 2 per direction, 2^3
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warp_global = blockIdx.x * BRICK_WARPS + warp, n_warps = gridDim.x * BRICK_WARPS;
+    const uint32_t count = (uint32_t)*brick_count;
+    const int NB = N >> 3, n1 = N >> 1, n2 = N >> 2, n3 = N >> 3;
+    uint32_t* s0 = sh0[warp];
+    for (uint32_t i = warp_global; i < count; i += n_warps)
+    {
+        const uint32_t b = __ldg(brick_list + i) & 0x7fffffffu;
+        const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
+        // level 0: 64 rows of 8 texels (one 32-byte sector each) = 128 uint4, four per lane
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const int q = lane + 32 * k, row = q >> 1, half = q & 1;
+            const int y = row & 7, z = row >> 3;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(level0 + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4));
+            *reinterpret_cast<uint4*>(s0 + row * 8 + half * 4) = v;
+        }
+        __syncwarp();
+        {   // level 1: lane -> output row (oy, oz) = lane & 15 and three of the six directions
+            const int p = lane & 15, oy = p & 3, oz = p >> 2, d0 = (lane >> 4) * 3;
+            uint32_t src[2][2][8];
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+                {
+                    const uint4* row = reinterpret_cast<const uint4*>(s0 + ((2 * oz + k) * 8 + (2 * oy + j)) * 8);
+                    const uint4 a = row[0], c = row[1];
+                    src[k][j][0] = a.x; src[k][j][1] = a.y; src[k][j][2] = a.z; src[k][j][3] = a.w;
+                    src[k][j][4] = c.x; src[k][j][5] = c.y; src[k][j][6] = c.z; src[k][j][7] = c.w;
+                }
+            const int gx = bx * 4, gy = by * 4 + oy, gz = bz * 4 + oz;
+#pragma unroll
+            for (int dd = 0; dd < 3; dd++)
+            {
+                const int d = d0 + dd;
+                uint32_t o[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    uint32_t t[2][2][2];
+#pragma unroll
+                    for (int k = 0; k < 2; k++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++) { t[k][j][0] = src[k][j][2 * q]; t[k][j][1] = src[k][j][2 * q + 1]; }
+                    o[q] = reduce_dir(t, d);
+                }
+                const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(&sh1[warp][d][(oz * 4 + oy) * 4]) = v;
+                *reinterpret_cast<uint4*>(out.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = v;
+                surf3Dwrite(v, out.surf[0][d], gx * 4, gy, gz);
+            }
+        }
+        __syncwarp();
+        if (lane < 24)
+        {   // level 2: lane -> (direction, output row of 2): reads only its own direction's level 1
+            const int d = lane >> 2, p = lane & 3, oy = p & 1, oz = p >> 1;
+            uint32_t o[2];
+            uint32_t src[2][2][4];
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+                {
+                    const uint4 a = *reinterpret_cast<const uint4*>(&sh1[warp][d][((2 * oz + k) * 4 + (2 * oy + j)) * 4]);
+                    src[k][j][0] = a.x; src[k][j][1] = a.y; src[k][j][2] = a.z; src[k][j][3] = a.w;
+                }
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+            {
+                uint32_t t[2][2][2];
+#pragma unroll
+                for (int k = 0; k < 2; k++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) { t[k][j][0] = src[k][j][2 * q]; t[k][j][1] = src[k][j][2 * q + 1]; }
+                o[q] = reduce_dir(t, d);
+            }
+            const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
+            const uint2 v = make_uint2(o[0], o[1]);
+            *reinterpret_cast<uint2*>(&sh2[warp][d][(oz * 2 + oy) * 2]) = v;
+            *reinterpret_cast<uint2*>(out.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = v;
+            surf3Dwrite(v, out.surf[1][d], gx * 4, gy, gz);
+        }
+        __syncwarp();
+        if (lane < 6)
+        {   // level 3: one texel per direction
+            const int d = lane;
+            uint32_t t[2][2][2];
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) { t[k][j][0] = sh2[warp][d][(k * 2 + j) * 2]; t[k][j][1] = sh2[warp][d][(k * 2 + j) * 2 + 1]; }
+            const uint32_t v = reduce_dir(t, d);
+            out.lin[2][d][((size_t)bz * n3 + by) * n3 + bx] = v;
+            surf3Dwrite(v, out.surf[2][d], bx * 4, by, bz);
+        }
+        __syncwarp();
     }
 }
 
@@ -243,7 +364,22 @@ int f184_mips_n(f184_ctx* c)
     }
     rc = f184_stage_begin(c, F184_STAGE_MIPS);
     if (rc) return rc;
-    for (uint32_t li = 0; li < c->n_mip_levels; li++)
+    uint32_t first_dense = 0;
+    if (!(c->cfg.flags & F184_FLAG_NO_TMA) && c->brick_list && c->n_mip_levels >= 3)
+    {   // levels 1-3 from the brick list (F184_FLAG_NO_TMA keeps the all-dense plain path as the cross-check)
+        BrickMipOut bo;
+        for (int l = 0; l < 3; l++)
+            for (int d = 0; d < 6; d++)
+            {
+                const uint64_t n = c->mip_levels[l].n;
+                bo.lin[l][d] = mips + c->mip_levels[l].offset_texels + (uint64_t)d * n * n * n;
+                bo.surf[l][d] = c->dir_surf[d][l];
+            }
+        k_mips_bricks<<<148 * 4, BRICK_WARPS * 32, 0, c->stream>>>(level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N);
+        CK_LAUNCH(c);
+        first_dense = 3;
+    }
+    for (uint32_t li = first_dense; li < c->n_mip_levels; li++)
     {
         const int n = (int)c->mip_levels[li].n, sn = 2 * n;
         const int iso = (li == 0);

@@ -41,9 +41,10 @@ __device__ __forceinline__ f4 bilinear_level(const TexDev& t, uint32_t level, fl
     int x1 = wrap_pow2(x0 + 1, (int)w), y1 = wrap_pow2(y0 + 1, (int)h);
     uchar4 t00 = __ldg(px + (size_t)y0 * w + x0), t10 = __ldg(px + (size_t)y0 * w + x1);
     uchar4 t01 = __ldg(px + (size_t)y1 * w + x0), t11 = __ldg(px + (size_t)y1 * w + x1);
+    // filtered in 8-bit units: bytes enter as 0..255 floats, the result stays on that scale (see the oracle)
     auto lerp2 = [&](unsigned char a, unsigned char b, unsigned char c, unsigned char d) {
-        float fa = (float)a / 255.0f, fb = (float)b / 255.0f, fc = (float)c / 255.0f, fd = (float)d / 255.0f;
-        float top = fa * (1.0f - fx) + fb * fx, bot = fc * (1.0f - fx) + fd * fx;
+        const float fa = (float)a, fb = (float)b, fc = (float)c, fd = (float)d;
+        const float top = fa * (1.0f - fx) + fb * fx, bot = fc * (1.0f - fx) + fd * fx;
         return top * (1.0f - fy) + bot * fy;
     };
     return {lerp2(t00.x, t10.x, t01.x, t11.x), lerp2(t00.y, t10.y, t01.y, t11.y), lerp2(t00.z, t10.z, t01.z, t11.z),
@@ -83,11 +84,11 @@ __device__ __forceinline__ size_t brick_major(int x, int y, int z, int NB)
 // (axis d+1, axis d+2, dominant axis d): a cyclic relabelling of x, y, z, under which the 13 separating axes of
 // the triangle/box test map onto themselves — so the exact integer predicate below is the oracle's
 // tri_box_overlap() evaluated in other coordinates — and every index is a compile-time constant.
-struct TriS
+struct alignas(16) TriS
 {
-    int v[3][3];             // snapped vertices (1/256 voxel), [vertex][u,v,w]
     long long n[3];          // integer normal (u, v, w components); n[2] is the largest in magnitude
     long long area;          // |n[2]|
+    int v[3][3];             // snapped vertices (1/256 voxel), [vertex][u,v,w]
     int sg;                  // sign of n[2]
     int lo[3], hi[3];        // candidate voxel range per axis (u, v, w), clipped to the grid
     float u[3], vv[3];
@@ -95,7 +96,9 @@ struct TriS
     float dudx, dvdx, dudy, dvdy;
     uint32_t mat;
     int d;
+    int pad[3];
 };
+static_assert(sizeof(TriS) == 192, "TriS is spilled to the pass-2 queue as 12 x 16 bytes");
 
 struct VoxArgs
 {
@@ -113,6 +116,7 @@ struct VoxArgs
     unsigned long long* frag_counter;
     unsigned long long* queue_state;   // (entries << 40) | tasks, one 64-bit word so both advance together
     uint2* queue;                      // per large triangle: (triangle, first task)
+    uint4* queue_tris;                 // its set-up (TriS, 12 x uint4), same index
 };
 
 constexpr int SETUP_THREADS = 128;
@@ -285,21 +289,22 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
             v = (s.vv[0] * bc[0] + s.vv[1] * bc[1]) + s.vv[2] * bc[2];
             nn = {(s.nrm[0].x * bc[0] + s.nrm[1].x * bc[1]) + s.nrm[2].x * bc[2], (s.nrm[0].y * bc[0] + s.nrm[1].y * bc[1]) + s.nrm[2].y * bc[2],
                   (s.nrm[0].z * bc[0] + s.nrm[1].z * bc[1]) + s.nrm[2].z * bc[2]};
-            if (!mat.use_textures) base = {mat.factor[0], mat.factor[1], mat.factor[2], mat.factor[3]};
+            // base colour in 8-bit units (0..255)
+            if (!mat.use_textures) base = {mat.factor[0] * 255.0f, mat.factor[1] * 255.0f, mat.factor[2] * 255.0f, mat.factor[3] * 255.0f};
             else
             {
                 f4 sc = {0.f, 0.f, 0.f, 0.f};
                 if (mat.tex >= 0) sc = sample_trilinear(A.texs[mat.tex], u, v, s.dudx, s.dvdx, s.dudy, s.dvdy);
                 base = {sc.x * mat.factor[0], sc.y * mat.factor[1], sc.z * mat.factor[2], sc.w * mat.factor[3]};
-                if (base.w < 0.05f) return frags;                   // main.lua:199 (alpha cut-out): nothing in this column
+                if (base.w < 12.75f) return frags;                  // main.lua:199 (alpha < 0.05 cut-out): nothing in this column
             }
             const float ax = fabsf(nn.x), ay = fabsf(nn.y), az = fabsf(nn.z);
             const float lead = (ax >= ay && ax >= az) ? nn.x : ((ay >= az) ? nn.y : nn.z);
             if (lead < 0.0f) nn = neg3(nn);
         }
-        const float r8 = floorf(dm_clamp(base.x, 0.0f, 1.0f) * 255.0f + 0.5f);
-        const float g8 = floorf(dm_clamp(base.y, 0.0f, 1.0f) * 255.0f + 0.5f);
-        const float b8 = floorf(dm_clamp(base.z, 0.0f, 1.0f) * 255.0f + 0.5f);
+        const float r8 = floorf(dm_clamp(base.x, 0.0f, 255.0f) + 0.5f);
+        const float g8 = floorf(dm_clamp(base.y, 0.0f, 255.0f) + 0.5f);
+        const float b8 = floorf(dm_clamp(base.z, 0.0f, 255.0f) + 0.5f);
         const float nx8 = rintf(dm_clamp(nn.x, -1.0f, 1.0f) * 127.0f), ny8 = rintf(dm_clamp(nn.y, -1.0f, 1.0f) * 127.0f),
                     nz8 = rintf(dm_clamp(nn.z, -1.0f, 1.0f) * 127.0f);
         // back to x, y, z: axis (d+1)%3 = u, (d+2)%3 = v, d = w
@@ -320,7 +325,7 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
 // ceil(columns / TASK_COLS) equal tasks for pass 2, so that a wall spanning 10^5 columns is spread over the
 // whole chip instead of serialising one warp.  Queue slots and task numbers are reserved by ONE 64-bit atomic per
 // warp, (entries << 40) | tasks, which keeps `first task` monotone in the entry index: pass 2 finds the triangle of
-// a task by binary search, no prefix-sum pass needed.
+// a task by binary search, no prefix-sum pass needed.  The set-up travels with the queue entry (192 B).
 __global__ void __launch_bounds__(SETUP_THREADS) k_voxelize_setup(const VoxArgs A)
 {
     const int lane = threadIdx.x & 31;
@@ -359,6 +364,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_voxelize_setup(const VoxArgs 
         {
             const uint32_t slot = (uint32_t)(old >> 40) + __popc(big & ((1u << lane) - 1u));
             A.queue[slot] = make_uint2(t, (uint32_t)(old & 0xffffffffffull) + incl - ntasks);
+            uint4 w[12];
+            memcpy(w, &s, sizeof(TriS));
+#pragma unroll
+            for (int i = 0; i < 12; i++) A.queue_tris[(size_t)slot * 12 + i] = w[i];
         }
     }
     warp_count_add(A.frag_counter, frags);
@@ -382,7 +391,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_voxelize_raster(const Vox
         }
         const uint2 e = __ldg(A.queue + lo);
         TriS s;
-        if (!setup_triangle(A, e.x, s)) continue;       // cannot happen (it was queued); keeps the compiler honest
+        {
+            uint4 w[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) w[i] = A.queue_tris[(size_t)lo * 12 + i];
+            memcpy(&s, w, sizeof(TriS));
+        }
         const MatDev mat = A.mats[s.mat];
         const int bu = s.hi[0] - s.lo[0] + 1, bv = s.hi[1] - s.lo[1] + 1;
         const int ncols = bu * bv;
@@ -500,9 +514,9 @@ int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
         CK(c, cudaMalloc(&c->brick_list, 4ull * n_bricks));
     }
     if (c->vox_queue_cap < c->n_tris)
-    {
+    {   // worst case every triangle is large: (8 + 192) B per triangle
         if (c->vox_queue) cudaFree(c->vox_queue);
-        CK(c, cudaMalloc(&c->vox_queue, 8ull * c->n_tris));
+        CK(c, cudaMalloc(&c->vox_queue, (8ull + sizeof(TriS)) * c->n_tris));
         c->vox_queue_cap = c->n_tris;
     }
     if (c->vm_cap < c->n_models)
@@ -539,6 +553,7 @@ int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
         A.frag_counter = c->counters_dev + F184_COUNTER_FRAGMENTS;
         A.queue_state = c->counters_dev + F184_COUNTER_COUNT + 1;
         A.queue = reinterpret_cast<uint2*>(c->vox_queue);
+        A.queue_tris = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(c->vox_queue) + 8ull * c->vox_queue_cap);
         const uint32_t tris = end - first;
         k_voxelize_setup<<<(tris + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, c->stream>>>(A);
         CK_LAUNCH(c);

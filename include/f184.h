@@ -283,6 +283,10 @@ int f184_stage_time_total(f184_ctx* ctx, uint32_t stage, float* out_ms_sum, uint
  * 5 pow(x,y), 6 f32->f16->f32); host pointers; synchronous */
 int f184_debug_detmath(f184_ctx* ctx, uint32_t op, const float* x, const float* y, float* out, size_t n);
 
+/* ---- test hook: one level of the texture-side storage the cone tracer samples (dir < 0: the level-0 radiance
+ * 3D array; dir 0..5: level `level`+1 of that direction's mipmapped 3D array); host pointer; synchronous */
+int f184_debug_read_array(f184_ctx* ctx, int32_t dir, uint32_t level, void* host, size_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,9 @@ using namespace orc;
 
 namespace {
 
-// ---- texture sampling (same sampler as mode R; independent copy on purpose) -----------------------
+// ---- texture sampling: mode R's sampler geometry (wrap addressing, LOD from the uv derivatives, MaxLod 4), but
+// filtered in 8-BIT UNITS: texel bytes enter the lerps as 0..255 floats and the result stays on that scale (the
+// caller quantises to 8 bits anyway), which keeps 32 divisions by 255 out of every fragment on the device.
 inline int wrapi(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
 
 V4 bilinear_level(const Texture& t, uint32_t level, float u, float v)
@@ -33,8 +35,8 @@ V4 bilinear_level(const Texture& t, uint32_t level, float u, float v)
     float r[4];
     for (int c = 0; c < 4; c++)
     {
-        float a = (float)px[4 * ((size_t)y0 * w + x0) + c] / 255.0f, b = (float)px[4 * ((size_t)y0 * w + x1) + c] / 255.0f;
-        float cc = (float)px[4 * ((size_t)y1 * w + x0) + c] / 255.0f, d = (float)px[4 * ((size_t)y1 * w + x1) + c] / 255.0f;
+        float a = (float)px[4 * ((size_t)y0 * w + x0) + c], b = (float)px[4 * ((size_t)y0 * w + x1) + c];
+        float cc = (float)px[4 * ((size_t)y1 * w + x0) + c], d = (float)px[4 * ((size_t)y1 * w + x1) + c];
         float top = a * (1.0f - fx) + b * fx, bot = cc * (1.0f - fx) + d * fx;
         r[c] = top * (1.0f - fy) + bot * fy;
     }
@@ -249,12 +251,13 @@ extern "C" int orc_voxelize_n(f184o_ctx* c, const f184_view_constants* cam)
                     V3 nn = {(at[0].n.x * b[0] + at[1].n.x * b[1]) + at[2].n.x * b[2], (at[0].n.y * b[0] + at[1].n.y * b[1]) + at[2].n.y * b[2],
                              (at[0].n.z * b[0] + at[1].n.z * b[1]) + at[2].n.z * b[2]};
                     V4 base;
-                    if (!mat.use_textures) base = {mat.factor[0], mat.factor[1], mat.factor[2], mat.factor[3]};
+                    // base colour in 8-bit units (0..255)
+                    if (!mat.use_textures) base = {mat.factor[0] * 255.0f, mat.factor[1] * 255.0f, mat.factor[2] * 255.0f, mat.factor[3] * 255.0f};
                     else
                     {
                         V4 sc = tex ? sample_trilinear(*tex, u, vv, dudx, dvdx, dudy, dvdy) : V4{0, 0, 0, 0};
                         base = {sc.x * mat.factor[0], sc.y * mat.factor[1], sc.z * mat.factor[2], sc.w * mat.factor[3]};
-                        if (base.w < 0.05f) continue;                   // main.lua:199
+                        if (base.w < 12.75f) continue;                  // main.lua:199, alpha < 0.05
                     }
                     // two-sided lighting downstream (indirect.frag:60-62): fold the normal into one hemisphere so
                     // the two faces of a thin wall add up instead of cancelling
@@ -262,9 +265,9 @@ extern "C" int orc_voxelize_n(f184o_ctx* c, const f184_view_constants* cam)
                     float lead = (fx >= fy && fx >= fz) ? nn.x : ((fy >= fz) ? nn.y : nn.z);
                     if (lead < 0.0f) nn = neg(nn);
                     // quantise so the fp32 sums are exact integers (order-independent, exact across GPUs)
-                    const float r8 = floorf(dm_clamp(base.x, 0.0f, 1.0f) * 255.0f + 0.5f);
-                    const float g8 = floorf(dm_clamp(base.y, 0.0f, 1.0f) * 255.0f + 0.5f);
-                    const float b8 = floorf(dm_clamp(base.z, 0.0f, 1.0f) * 255.0f + 0.5f);
+                    const float r8 = floorf(dm_clamp(base.x, 0.0f, 255.0f) + 0.5f);
+                    const float g8 = floorf(dm_clamp(base.y, 0.0f, 255.0f) + 0.5f);
+                    const float b8 = floorf(dm_clamp(base.z, 0.0f, 255.0f) + 0.5f);
                     const float nx8 = rintf(dm_clamp(nn.x, -1.0f, 1.0f) * 127.0f), ny8 = rintf(dm_clamp(nn.y, -1.0f, 1.0f) * 127.0f),
                                 nz8 = rintf(dm_clamp(nn.z, -1.0f, 1.0f) * 127.0f);
                     const size_t o = ((size_t)box[2] * N + box[1]) * N + box[0];
@@ -471,24 +474,19 @@ struct ConeCtx
     uint64_t samples;
 };
 
-// direction-weighted fetch from the six-direction chain at fractional level `lod` (>= 0, 0 = level 1)
-V4 fetch_dir(const ConeCtx& C, const float w[3], const int face[3], float qx, float qy, float qz, float lod)
+// direction-weighted fetch from the six-direction chain at mip index `l` (0 = level 1), nearest level: one
+// trilinear fetch per axis.  (The first version blended two levels per fetch, "quadrilinear"; on the device
+// that made the tracer texture-pipe bound at 88 % of the TEX wavefront peak, so the spec now takes the level
+// whose voxel size is nearest the cone diameter — DESIGN.md B.5.)
+V4 fetch_dir(const ConeCtx& C, const float w[3], const int face[3], float qx, float qy, float qz, int l)
 {
     const int maxl = (int)C.dir[0].size() - 1;
-    if (lod > (float)maxl) lod = (float)maxl;
-    const float lf = floorf(lod);
-    const int l0 = (int)lf;
-    const float f = q8(lod - lf);
+    if (l > maxl) l = maxl;
     V4 r = {0, 0, 0, 0};
     for (int a = 0; a < 3; a++)
     {
         if (w[a] == 0.0f) continue;
-        V4 s0 = fetch_trilinear(C.dir[face[a]][l0], qx, qy, qz);
-        if (f > 0.0f && l0 < maxl)
-        {
-            V4 s1 = fetch_trilinear(C.dir[face[a]][l0 + 1], qx, qy, qz);
-            s0 = {s0.x + (s1.x - s0.x) * f, s0.y + (s1.y - s0.y) * f, s0.z + (s1.z - s0.z) * f, s0.w + (s1.w - s0.w) * f};
-        }
+        V4 s0 = fetch_trilinear(C.dir[face[a]][l], qx, qy, qz);
         r = {r.x + w[a] * s0.x, r.y + w[a] * s0.y, r.z + w[a] * s0.z, r.w + w[a] * s0.w};
     }
     return r;
@@ -518,14 +516,9 @@ V3 trace_cone(ConeCtx& C, V3 origin, V3 dir, float tan_half)
         const float qx = q4.x * 0.5f + 0.5f, qy = q4.y * 0.5f + 0.5f, qz = q4.z;
         if (!(qx >= 0.0f && qx <= 1.0f && qy >= 0.0f && qy <= 1.0f && qz >= 0.0f && qz <= 1.0f)) break;
         C.samples++;
-        V4 s;
-        if (lod < 1.0f)
-        {
-            V4 s0 = fetch_trilinear(C.level0, qx, qy, qz);
-            V4 s1 = fetch_dir(C, w, face, qx, qy, qz, 0.0f);
-            s = {s0.x + (s1.x - s0.x) * lod, s0.y + (s1.y - s0.y) * lod, s0.z + (s1.z - s0.z) * lod, s0.w + (s1.w - s0.w) * lod};
-        }
-        else s = fetch_dir(C, w, face, qx, qy, qz, lod - 1.0f);
+        // nearest level: 0 = the isotropic radiance volume, L >= 1 = the six-direction chain
+        const int L = (int)floorf(lod + 0.5f);
+        V4 s = (L <= 0) ? fetch_trilinear(C.level0, qx, qy, qz) : fetch_dir(C, w, face, qx, qy, qz, L - 1);
         const float k = 1.0f - A;
         acc = {acc.x + k * s.x, acc.y + k * s.y, acc.z + k * s.z};
         A += k * s.w;

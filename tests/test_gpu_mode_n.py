@@ -60,6 +60,31 @@ def test_inject_and_mips_bit_exact(cuda_lib, oracle_lib, proc_scene, cams, flags
     assert np.array_equal(mg, mo), f"mips: {np.count_nonzero((mg != mo).any(-1))} texels differ"
 
 
+def test_texture_side_storage_matches_linear_volumes(cuda_lib, oracle_lib, proc_scene, cams):
+    """What the tracer's texture units sample (3D arrays written through surfaces, 16-byte surface stores) must be
+    the same bytes as the linear volumes the oracle is compared with — over two frames, the second with half the
+    triangles, so bricks that became empty are cleared at every level of the sparse mip builder."""
+    n = 64
+    g, o, k = _pipeline(cuda_lib, oracle_lib, proc_scene, cams, n, 64, 36, stop_after="mips")
+    for frame in range(2):
+        if frame == 1:
+            for c in (g, o):
+                c.set_triangle_range(0, proc_scene.n_tris // 2)
+                c.voxelize(cams["voxel"]); c.inject(k); c.build_mips()
+        rad, mips = o.readback(A.SLOT_RADIANCE), o.readback(A.SLOT_MIPS)
+        assert np.array_equal(g.readback(A.SLOT_RADIANCE), rad)
+        assert np.array_equal(g.readback(A.SLOT_MIPS), mips), f"frame {frame}"
+        assert np.array_equal(g.read_array(-1, 0, n), rad), f"frame {frame}: level-0 array"
+        off, m, lvl = 0, n // 2, 0
+        while m >= 1:
+            for d in range(6):
+                want = mips[off + d * m ** 3: off + (d + 1) * m ** 3].reshape(m, m, m, 4)
+                assert np.array_equal(g.read_array(d, lvl, m), want), f"frame {frame}: dir {d} level {lvl + 1}"
+            off += 6 * m ** 3
+            m //= 2
+            lvl += 1
+
+
 def test_cone_trace_within_tolerance(cuda_lib, oracle_lib, proc_scene, cams):
     g, o, _ = _pipeline(cuda_lib, oracle_lib, proc_scene, cams, 128, 160, 90)
     ig, io = g.readback(A.SLOT_INDIRECT_OUT).astype(np.float32), o.readback(A.SLOT_INDIRECT_OUT).astype(np.float32)
