@@ -552,8 +552,8 @@ int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
         A.brick_flags = img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS);
         A.frag_counter = c->counters_dev + F184_COUNTER_FRAGMENTS;
         A.queue_state = c->counters_dev + F184_COUNTER_COUNT + 1;
-        A.queue = reinterpret_cast<uint2*>(c->vox_queue);
-        A.queue_tris = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(c->vox_queue) + 8ull * c->vox_queue_cap);
+        A.queue_tris = reinterpret_cast<uint4*>(c->vox_queue);                      // 192 B records first (16-byte aligned)
+        A.queue = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(c->vox_queue) + sizeof(TriS) * (size_t)c->vox_queue_cap);
         const uint32_t tris = end - first;
         k_voxelize_setup<<<(tris + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, c->stream>>>(A);
         CK_LAUNCH(c);
