@@ -33,6 +33,7 @@ STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gta
 (COUNTER_FRAGMENTS, COUNTER_MARCH_STEPS, COUNTER_OCCUPIED, COUNTER_KERNEL_LAUNCHES, COUNTER_BRICKS) = range(5)
 FLAG_EXTERNAL_RANDS = 1
 FLAG_NO_TMA = 2
+FLAG_DENSE_MIPS = 4
 
 (FMT_UNDEFINED, FMT_R32_SFLOAT, FMT_R16G16B16A16_UNORM, FMT_R8G8B8A8_UNORM, FMT_R16G16B16A16_SFLOAT,
  FMT_R16G16_UINT, FMT_R32G32B32A32_SFLOAT, FMT_R8G8B8A8_SNORM, FMT_R32_UINT) = range(9)

@@ -327,6 +327,101 @@ k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ 
     }
 }
 
+// ---- tail: every level below level 3 in ONE launch -------------------------------------------------------------
+// Level 3 has edge N/8 (64 at 512^3): the rest of the chain is < 0.1 % of the bytes, and as one launch per level it was
+// six launch latencies (42 us of a 4 ms frame).  Here a CTA takes a T^3 tile (T = min(16, N/8)) of one direction's
+// level 3 through shared memory down log2(T) levels; whatever is left (edge N/128: 4^3 at 512^3) is finished by the
+// last CTA to arrive (ticket counter, self-resetting).
+struct TailOut
+{
+    cudaSurfaceObject_t surf[6][12];
+    uint64_t level_off[12];                 // texel offset of level l+1, direction 0, inside the chain allocation
+    uint32_t level_n[12];
+    uint32_t n_levels;
+};
+
+__global__ void __launch_bounds__(256)
+k_mips_tail(uint32_t* __restrict__ chain, TailOut out, int T, int tiles, unsigned long long* __restrict__ ticket)
+{
+    __shared__ uint32_t bufA[4096], bufB[512];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x;
+    const int d = blockIdx.x / (tiles * tiles * tiles), tl = blockIdx.x % (tiles * tiles * tiles);
+    const int tx = tl % tiles, ty = (tl / tiles) % tiles, tz = tl / (tiles * tiles);
+    const int n3 = (int)out.level_n[2];
+    {
+        const uint32_t* src = chain + out.level_off[2] + (uint64_t)d * n3 * n3 * n3;
+        for (int i = tid; i < T * T * T; i += 256)
+        {
+            const int x = i % T, y = (i / T) % T, z = i / (T * T);
+            bufA[i] = src[((size_t)(tz * T + z) * n3 + (ty * T + y)) * n3 + tx * T + x];
+        }
+    }
+    __syncthreads();
+    uint32_t *a = bufA, *b = bufB;
+    int lvl = 3;                                            // index of the level being WRITTEN (0 = level 1)
+    for (int s = T; s > 1; s >>= 1, lvl++)
+    {
+        const int m = s >> 1, n = (int)out.level_n[lvl];
+        uint32_t* dst = chain + out.level_off[lvl] + (uint64_t)d * n * n * n;
+        for (int i = tid; i < m * m * m; i += 256)
+        {
+            const int x = i % m, y = (i / m) % m, z = i / (m * m);
+            uint32_t t[2][2][2];
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int q = 0; q < 2; q++) t[k][j][q] = a[((2 * z + k) * s + (2 * y + j)) * s + 2 * x + q];
+            const uint32_t v = reduce_dir(t, d);
+            b[i] = v;
+            const int gx = tx * m + x, gy = ty * m + y, gz = tz * m + z;
+            dst[((size_t)gz * n + gy) * n + gx] = v;
+            surf3Dwrite(v, out.surf[d][lvl], gx * 4, gy, gz);
+        }
+        __syncthreads();
+        uint32_t* tmp = a; a = b; b = tmp;
+    }
+    if ((uint32_t)lvl >= out.n_levels) return;             // the tile reached 1^3: the chain is complete
+    // hand-over: the last CTA finishes the remaining levels from global memory
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+    {
+        const unsigned long long tk = atomicAdd(ticket, 1ull);
+        is_last = (tk == (unsigned long long)gridDim.x - 1ull);
+        if (is_last) *ticket = 0ull;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    for (; (uint32_t)lvl < out.n_levels; lvl++)
+    {
+        const int n = (int)out.level_n[lvl], sn = 2 * n;
+        for (int i = tid; i < 6 * n * n * n; i += 256)
+        {
+            const int dd = i / (n * n * n), r = i % (n * n * n);
+            const int x = r % n, y = (r / n) % n, z = r / (n * n);
+            const uint32_t* src = chain + out.level_off[lvl - 1] + (uint64_t)dd * sn * sn * sn;
+            uint32_t t[2][2][2];
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int q = 0; q < 2; q++) t[k][j][q] = __ldcg(src + ((size_t)(2 * z + k) * sn + (2 * y + j)) * sn + 2 * x + q);
+            uint32_t v = 0;
+#pragma unroll
+            for (int e = 0; e < 6; e++)
+                if (e == dd) v = reduce_dir(t, e);
+            chain[out.level_off[lvl] + (uint64_t)dd * n * n * n + r] = v;
+            surf3Dwrite(v, out.surf[dd][lvl], x * 4, y, z);
+        }
+        __threadfence();
+        __syncthreads();
+    }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -365,7 +460,8 @@ int f184_mips_n(f184_ctx* c)
     rc = f184_stage_begin(c, F184_STAGE_MIPS);
     if (rc) return rc;
     uint32_t first_dense = 0;
-    if (!(c->cfg.flags & F184_FLAG_NO_TMA) && c->brick_list && c->n_mip_levels >= 3)
+    const bool sparse = !(c->cfg.flags & (F184_FLAG_NO_TMA | F184_FLAG_DENSE_MIPS)) && c->brick_list && c->n_mip_levels >= 3;
+    if (sparse)
     {   // levels 1-3 from the brick list (F184_FLAG_NO_TMA keeps the all-dense plain path as the cross-check)
         BrickMipOut bo;
         for (int l = 0; l < 3; l++)
@@ -377,7 +473,18 @@ int f184_mips_n(f184_ctx* c)
             }
         k_mips_bricks<<<148 * 4, BRICK_WARPS * 32, 0, c->stream>>>(level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N);
         CK_LAUNCH(c);
-        first_dense = 3;
+        first_dense = c->n_mip_levels;          // the tail kernel below takes every remaining level
+        if (c->n_mip_levels > 3)
+        {
+            TailOut to{};
+            to.n_levels = c->n_mip_levels;
+            for (uint32_t l = 0; l < c->n_mip_levels; l++) { to.level_off[l] = c->mip_levels[l].offset_texels; to.level_n[l] = c->mip_levels[l].n; }
+            for (int d = 0; d < 6; d++)
+                for (uint32_t l = 0; l < c->n_mip_levels; l++) to.surf[d][l] = c->dir_surf[d][l];
+            const int n3 = (int)c->mip_levels[2].n, T = std::min(16, n3), tiles = n3 / T;
+            k_mips_tail<<<6 * tiles * tiles * tiles, 256, 0, c->stream>>>(mips, to, T, tiles, c->counters_dev + F184_COUNTER_COUNT + 2);
+            CK_LAUNCH(c);
+        }
     }
     for (uint32_t li = first_dense; li < c->n_mip_levels; li++)
     {

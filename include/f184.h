@@ -120,7 +120,9 @@ typedef struct f184_config {
 typedef enum f184_flags {
     F184_FLAG_NONE = 0,
     F184_FLAG_EXTERNAL_RANDS = 1,  /* mode R trace: rands come from a bound buffer (march-only parity) */
-    F184_FLAG_NO_TMA = 2           /* mode N mips: use the plain kernel for every level (cross-check of the TMA path) */
+    F184_FLAG_NO_TMA = 2,          /* mode N mips: dense, plain one-thread-per-texel kernel for every level (cross-check) */
+    F184_FLAG_DENSE_MIPS = 4       /* mode N mips: dense chain, TMA-staged tiles for the large levels (default is the sparse
+                                      brick-list path for levels 1-3 + one fused launch for the rest) */
 } f184_flags;
 
 /* CViewConstants, Foreground/SceneGraph/SceneView.h:8-14 = GlobalConstants, Shader/EngineCommon.h:7-13. 208 B. */

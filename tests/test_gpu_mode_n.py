@@ -50,7 +50,7 @@ def test_voxelize_normalise_bit_exact(cuda_lib, oracle_lib, proc_scene, cams, n)
     assert g.counter(A.COUNTER_OCCUPIED) == o.counter(A.COUNTER_OCCUPIED)
 
 
-@pytest.mark.parametrize("flags", [0, A.FLAG_NO_TMA])
+@pytest.mark.parametrize("flags", [0, A.FLAG_NO_TMA, A.FLAG_DENSE_MIPS])
 def test_inject_and_mips_bit_exact(cuda_lib, oracle_lib, proc_scene, cams, flags):
     g, o, _ = _pipeline(cuda_lib, oracle_lib, proc_scene, cams, 128, 64, 36, flags=flags, stop_after="mips")
     rg, ro = g.readback(A.SLOT_RADIANCE), o.readback(A.SLOT_RADIANCE)
