@@ -51,6 +51,7 @@ def parse():
     p.add_argument("--height", type=int, default=2160)
     p.add_argument("--shadow", type=int, default=2048)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--schedule", default=None, choices=[None, "slab", "replicate"], help="multi-GPU schedule (default: slab)")
     p.add_argument("--cpu-budget-s", type=float, default=20.0, help="target CPU seconds of the cpu_baseline sample")
     return p.parse_args()
 
@@ -251,9 +252,11 @@ def run_b200(args, rank, world, local_rank):
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if peaks else (6650.0, "fallback (B200_PROFILING.md)")
 
     from final184_b200.dist import ShardedVoxelGI
-    g = ShardedVoxelGI(grid_n=N, width=W, height=H, shadow_res=args.shadow, device=local_rank, rank=rank, nranks=world, scene=sc)
+    g = ShardedVoxelGI(grid_n=N, width=W, height=H, shadow_res=args.shadow, device=local_rank, rank=rank, nranks=world, scene=sc,
+                       voxel_cam=cams["voxel"], mode=args.schedule)
     stream = torch.cuda.Stream(device=local_rank)
     g.ctx.set_stream(stream.cuda_stream)
+    g.connect()
     k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
     slots = ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_MATERIAL, "material"), (A.SLOT_SHADOW, "shadow"))
     # pinned host copies of the per-frame inputs and of the result (e2e leg)
@@ -302,8 +305,8 @@ def run_b200(args, rank, world, local_rank):
         for s in range(A.STAGE_COUNT):
             tot, runs = g.ctx.stage_total_ms(s)
             if runs:
-                stage_ms[A.STAGE_NAMES[s]] = tot / runs
-        comm_ms = g.comm_ms_per_frame()
+                stage_ms[A.STAGE_NAMES[s]] = tot / args.steps          # per frame (a stage may run more than once in a frame)
+        comm_ms = stage_ms.get("exchange", 0.0)
         g.ctx.stage_time_reset(False)
         counters = {"fragments": g.ctx.counter(A.COUNTER_FRAGMENTS), "bricks": g.ctx.counter(A.COUNTER_BRICKS),
                     "occupied": g.ctx.counter(A.COUNTER_OCCUPIED), "cone_samples": g.ctx.counter(A.COUNTER_MARCH_STEPS)}
@@ -348,7 +351,7 @@ def run_b200(args, rank, world, local_rank):
             if b and ms > 0:
                 ach = b / (ms * 1e-3) / 1e9
                 rstages[name] = {"ms": round(ms, 4), "algorithmic_bytes": int(b), "achieved": round(ach, 1), "frac": round(ach / hbm_peak, 4)}
-        dom = max(stage_ms, key=stage_ms.get)
+        dom = max(rstages, key=lambda n: rstages[n]["ms"])
         traffic = None
         tp = os.path.join(REPO, "profiles", "traffic.json")
         if os.path.exists(tp):

@@ -28,12 +28,14 @@ MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
  SLOT_ACCUM_COLOR, SLOT_ACCUM_NORMAL, SLOT_VOX_ALBEDO, SLOT_VOX_NORMAL, SLOT_RADIANCE, SLOT_MIPS,
  SLOT_BRICK_FLAGS, SLOT_COUNT) = range(20)
 (STAGE_CLEAR, STAGE_VOXELIZE, STAGE_NORMALISE, STAGE_INJECT, STAGE_MIPS, STAGE_TRACE, STAGE_GTAO,
- STAGE_BLUR, STAGE_COUNT) = range(9)
-STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur"]
+ STAGE_BLUR, STAGE_EXCHANGE, STAGE_COUNT) = range(10)
+STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur", "exchange"]
 (COUNTER_FRAGMENTS, COUNTER_MARCH_STEPS, COUNTER_OCCUPIED, COUNTER_KERNEL_LAUNCHES, COUNTER_BRICKS) = range(5)
+(IPC_ACCUM_COLOR, IPC_ACCUM_NORMAL, IPC_BRICK_FLAGS, IPC_EXPORT, IPC_COUNTERS, IPC_BRICK_LIST, IPC_SYNC, IPC_COUNT) = range(8)
 FLAG_EXTERNAL_RANDS = 1
 FLAG_NO_TMA = 2
 FLAG_DENSE_MIPS = 4
+FLAG_GATHER_LINEAR = 8
 
 (FMT_UNDEFINED, FMT_R32_SFLOAT, FMT_R16G16B16A16_UNORM, FMT_R8G8B8A8_UNORM, FMT_R16G16B16A16_SFLOAT,
  FMT_R16G16_UINT, FMT_R32G32B32A32_SFLOAT, FMT_R8G8B8A8_SNORM, FMT_R32_UINT) = range(9)
@@ -137,6 +139,8 @@ _SIGS = {
     "frame_begin": (C.c_int, [C.c_void_p]),
     "frame_end": (C.c_int, [C.c_void_p]),
     "voxelize": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC)]),
+    "voxelize_accumulate": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC)]),
+    "normalise": (C.c_int, [C.c_void_p]),
     "inject": (C.c_int, [C.c_void_p, C.POINTER(SunC), C.POINTER(ExtendedMatricesC)]),
     "build_mips": (C.c_int, [C.c_void_p]),
     "trace_indirect": (C.c_int, [C.c_void_p, C.POINTER(TraceConstantsC)]),
@@ -153,6 +157,10 @@ _SIGS = {
 _PRODUCT_ONLY = {
     "import_external_memory_fd": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(ImageDesc)]),
     "import_semaphores_fd": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ipc_export": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "ipc_import": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "peer_barrier": (C.c_int, [C.c_void_p]),
+    "gather_volume": (C.c_int, [C.c_void_p]),
     "stage_time_reset": (C.c_int, [C.c_void_p, C.c_uint32]),
     "stage_time_total": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "debug_read_array": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_size_t]),
@@ -291,6 +299,29 @@ class VoxelGI:
     def voxelize(self, voxel_cam: S.ViewConstants | ViewConstantsC):
         v = voxel_cam if isinstance(voxel_cam, ViewConstantsC) else view_constants_c(voxel_cam)
         self._ck(self.lib.voxelize(self.h, C.byref(v)), "voxelize")
+
+    def voxelize_accumulate(self, voxel_cam: S.ViewConstants | ViewConstantsC):
+        v = voxel_cam if isinstance(voxel_cam, ViewConstantsC) else view_constants_c(voxel_cam)
+        self._ck(self.lib.voxelize_accumulate(self.h, C.byref(v)), "voxelize_accumulate")
+
+    def normalise(self):
+        self._ck(self.lib.normalise(self.h), "normalise")
+
+    # -- one NVLink box (product library only)
+    def ipc_export(self, buffer) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self._ck(self.lib.ipc_export(self.h, buffer, h), "ipc_export")
+        return bytes(h)
+
+    def ipc_import(self, peer_rank, buffer, handle: bytes):
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        self._ck(self.lib.ipc_import(self.h, peer_rank, buffer, h), "ipc_import")
+
+    def peer_barrier(self):
+        self._ck(self.lib.peer_barrier(self.h), "peer_barrier")
+
+    def gather_volume(self):
+        self._ck(self.lib.gather_volume(self.h), "gather_volume")
 
     def inject(self, k: TraceConstantsC):
         self._ck(self.lib.inject(self.h, C.byref(k.sun), C.byref(k.ext)), "inject")

@@ -224,6 +224,11 @@ void f184_destroy(f184_ctx* c)
     for (uint8_t* p : c->tex_alloc) if (p) cudaFree(p);
     for (int s = 0; s < F184_STAGE_COUNT; s++)
         for (cudaEvent_t e : c->ev_pool[s]) cudaEventDestroy(e);
+    for (auto& pr : c->peer)
+        for (int b = 0; b < F184_IPC_COUNT; b++)
+            if (pr.imported[b] && pr.buf[b]) cudaIpcCloseMemHandle(pr.buf[b]);
+    if (c->export_buf) cudaFree(c->export_buf);
+    if (c->sync_flags) cudaFree(c->sync_flags);
     if (c->sem_wait) cudaDestroyExternalSemaphore(c->sem_wait);
     if (c->sem_signal) cudaDestroyExternalSemaphore(c->sem_signal);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -474,6 +479,62 @@ int f184_voxelize(f184_ctx* c, const f184_view_constants* cam)
     if (rc) return rc;
     return c->cfg.mode == F184_MODE_REFERENCE ? f184_voxelize_r(c, cam) : f184_voxelize_n(c, cam);
 }
+int f184_voxelize_accumulate(f184_ctx* c, const f184_view_constants* cam)
+{
+    if (!c || !cam) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "voxelize_accumulate: null argument");
+    if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "voxelize_accumulate is a north-star stage");
+    if (!c->n_tris) return f184_fail(c, F184_ERR_NOT_READY, "voxelize_accumulate: no scene uploaded");
+    CK(c, cudaSetDevice(c->cfg.device));
+    int rc = f184_sync_tables(c);
+    if (rc) return rc;
+    return f184_voxelize_accumulate_n(c, cam);
+}
+int f184_normalise(f184_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "normalise is a north-star stage");
+    if (!c->brick_prev) return f184_fail(c, F184_ERR_NOT_READY, "normalise: call f184_voxelize_accumulate first");
+    CK(c, cudaSetDevice(c->cfg.device));
+    return f184_normalise_n(c);
+}
+int f184_gather_volume(f184_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "gather_volume is a north-star stage");
+    CK(c, cudaSetDevice(c->cfg.device));
+    return f184_gather_n(c);
+}
+
+// ---- CUDA IPC: share a context buffer with the other ranks of the box ----------------------------------------
+int f184_ipc_export(f184_ctx* c, uint32_t buffer, f184_ipc_handle* out)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(f184_ipc_handle), "handle size");
+    if (!c || buffer >= F184_IPC_COUNT || !out) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "ipc_export: bad argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    void* p = nullptr;
+    int rc = f184_ipc_buffer_ptr(c, buffer, &p);
+    if (rc) return rc;
+    CK(c, cudaStreamSynchronize(c->stream));      // the allocation's zero-fill has landed before a peer can see it
+    cudaIpcMemHandle_t h;
+    CK(c, cudaIpcGetMemHandle(&h, p));
+    memcpy(out->opaque, &h, sizeof(h));
+    return F184_OK;
+}
+int f184_ipc_import(f184_ctx* c, uint32_t peer_rank, uint32_t buffer, const f184_ipc_handle* in)
+{
+    if (!c || buffer >= F184_IPC_COUNT || !in || peer_rank >= 8 || peer_rank >= c->cfg.nranks)
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "ipc_import: bad argument");
+    if (peer_rank == c->cfg.rank) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "ipc_import: own rank");
+    CK(c, cudaSetDevice(c->cfg.device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, in->opaque, sizeof(h));
+    void* p = nullptr;
+    CK(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer[peer_rank].buf[buffer] = p;
+    c->peer[peer_rank].imported[buffer] = true;
+    return F184_OK;
+}
+
 int f184_inject(f184_ctx* c, const f184_sun* sun, const f184_extended_matrices* m)
 {
     if (!c || !sun || !m) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "inject: null argument");

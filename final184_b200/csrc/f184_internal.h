@@ -83,6 +83,15 @@ struct f184_ctx
     cudaSurfaceObject_t dir_surf[6][12] = {};
     uint32_t n_mip_levels = 0;                // levels >= 1
     void* tma_maps = nullptr;                 // host array of CUtensorMap (mode_n_mips.cu)
+    // one NVLink box: peer-mapped buffers (index = rank; own entry points at own memory)
+    struct Peer
+    {
+        void* buf[F184_IPC_COUNT] = {};
+        bool imported[F184_IPC_COUNT] = {};
+    } peer[8];
+    uint32_t* export_buf = nullptr;           // 1024 words per listed brick of the own slab
+    uint32_t* sync_flags = nullptr;           // [8] barrier epochs written by the peers + [8] scratch
+    uint32_t barrier_epoch = 0;
     // sharding
     uint32_t tri_first = 0, tri_count = 0xffffffffu;
     uint32_t row0 = 0, row1 = 0xffffffffu;
@@ -155,5 +164,8 @@ int f184_trace_n(f184_ctx* c, const f184_trace_constants* k);
 int f184_mode_n_release(f184_ctx* c);
 int f184_mode_n_alloc(f184_ctx* c);
 int f184_normalise_n(f184_ctx* c);
+int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam);
+int f184_gather_n(f184_ctx* c);
+int f184_ipc_buffer_ptr(f184_ctx* c, uint32_t buffer, void** out);
 M4 f184_invert_m4(const M4& A);
 float f184_exposure(const f184_ctx* c, const f184_sun* sun);

@@ -221,7 +221,7 @@ constexpr int BRICK_WARPS = 8;
 
 __global__ void __launch_bounds__(BRICK_WARPS * 32)
 k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ brick_list, const unsigned long long* __restrict__ brick_count,
-              BrickMipOut out, int N)
+              BrickMipOut out, int N, uint32_t* __restrict__ export_buf)
 {
     __shared__ __align__(16) uint32_t sh0[BRICK_WARPS][512];       // the brick, [z][y][x]
     __shared__ __align__(16) uint32_t sh1[BRICK_WARPS][6][64];     // level 1 per direction, [z][y][x] 4^3
@@ -243,7 +243,11 @@ k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ 
             const int y = row & 7, z = row >> 3;
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(level0 + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4));
             *reinterpret_cast<uint4*>(s0 + row * 8 + half * 4) = v;
+            // multi-GPU: the brick's packed record (1024 words: level 0 | level 1 | level 2 | level 3) that the other
+            // ranks pull over NVLink (mode_n_shard.cu)
+            if (export_buf) reinterpret_cast<uint4*>(export_buf + (size_t)i * 1024)[q] = v;
         }
+        uint32_t* rec = export_buf ? export_buf + (size_t)i * 1024 : nullptr;
         __syncwarp();
         {   // level 1: lane -> output row (oy, oz) = lane & 15 and three of the six directions
             const int p = lane & 15, oy = p & 3, oz = p >> 2, d0 = (lane >> 4) * 3;
@@ -276,6 +280,7 @@ k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ 
                 }
                 const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<uint4*>(&sh1[warp][d][(oz * 4 + oy) * 4]) = v;
+                if (rec) *reinterpret_cast<uint4*>(rec + 512 + d * 64 + (oz * 4 + oy) * 4) = v;
                 *reinterpret_cast<uint4*>(out.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = v;
                 surf3Dwrite(v, out.surf[0][d], gx * 4, gy, gz);
             }
@@ -307,6 +312,7 @@ k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ 
             const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
             const uint2 v = make_uint2(o[0], o[1]);
             *reinterpret_cast<uint2*>(&sh2[warp][d][(oz * 2 + oy) * 2]) = v;
+            if (rec) *reinterpret_cast<uint2*>(rec + 896 + d * 8 + (oz * 2 + oy) * 2) = v;
             *reinterpret_cast<uint2*>(out.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = v;
             surf3Dwrite(v, out.surf[1][d], gx * 4, gy, gz);
         }
@@ -321,6 +327,7 @@ k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ 
                 for (int j = 0; j < 2; j++) { t[k][j][0] = sh2[warp][d][(k * 2 + j) * 2]; t[k][j][1] = sh2[warp][d][(k * 2 + j) * 2 + 1]; }
             const uint32_t v = reduce_dir(t, d);
             out.lin[2][d][((size_t)bz * n3 + by) * n3 + bx] = v;
+            if (rec) rec[944 + d] = v;
             surf3Dwrite(v, out.surf[2][d], bx * 4, by, bz);
         }
         __syncwarp();
@@ -441,6 +448,27 @@ PFN_encodeTiled get_encode()
 
 }  // namespace
 
+// every level below level 3, one launch (timed with the mips stage on one GPU, after the gather on several)
+int f184_mips_tail_n(f184_ctx* c, bool own_stage)
+{
+    if (c->n_mip_levels <= 3) return F184_OK;
+    uint32_t* mips = img_ptr<uint32_t>(c, F184_SLOT_MIPS);
+    TailOut to{};
+    to.n_levels = c->n_mip_levels;
+    for (uint32_t l = 0; l < c->n_mip_levels; l++) { to.level_off[l] = c->mip_levels[l].offset_texels; to.level_n[l] = c->mip_levels[l].n; }
+    for (int d = 0; d < 6; d++)
+        for (uint32_t l = 0; l < c->n_mip_levels; l++) to.surf[d][l] = c->dir_surf[d][l];
+    const int n3 = (int)c->mip_levels[2].n, T = std::min(16, n3), tiles = n3 / T;
+    if (own_stage)
+    {
+        int rc = f184_stage_begin(c, F184_STAGE_MIPS);
+        if (rc) return rc;
+    }
+    k_mips_tail<<<6 * tiles * tiles * tiles, 256, 0, c->stream>>>(mips, to, T, tiles, c->counters_dev + F184_COUNTER_COUNT + 2);
+    CK_LAUNCH(c);
+    return own_stage ? f184_stage_end(c, F184_STAGE_MIPS) : F184_OK;
+}
+
 int f184_mips_n(f184_ctx* c)
 {
     int rc = f184_ensure_image(c, F184_SLOT_RADIANCE); if (rc) return rc;
@@ -471,19 +499,21 @@ int f184_mips_n(f184_ctx* c)
                 bo.lin[l][d] = mips + c->mip_levels[l].offset_texels + (uint64_t)d * n * n * n;
                 bo.surf[l][d] = c->dir_surf[d][l];
             }
-        k_mips_bricks<<<148 * 4, BRICK_WARPS * 32, 0, c->stream>>>(level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N);
-        CK_LAUNCH(c);
-        first_dense = c->n_mip_levels;          // the tail kernel below takes every remaining level
-        if (c->n_mip_levels > 3)
+        uint32_t* export_buf = nullptr;
+        if (c->cfg.nranks > 1)
         {
-            TailOut to{};
-            to.n_levels = c->n_mip_levels;
-            for (uint32_t l = 0; l < c->n_mip_levels; l++) { to.level_off[l] = c->mip_levels[l].offset_texels; to.level_n[l] = c->mip_levels[l].n; }
-            for (int d = 0; d < 6; d++)
-                for (uint32_t l = 0; l < c->n_mip_levels; l++) to.surf[d][l] = c->dir_surf[d][l];
-            const int n3 = (int)c->mip_levels[2].n, T = std::min(16, n3), tiles = n3 / T;
-            k_mips_tail<<<6 * tiles * tiles * tiles, 256, 0, c->stream>>>(mips, to, T, tiles, c->counters_dev + F184_COUNTER_COUNT + 2);
-            CK_LAUNCH(c);
+            void* e = nullptr;
+            rc = f184_ipc_buffer_ptr(c, F184_IPC_EXPORT, &e);
+            if (rc) return rc;
+            export_buf = reinterpret_cast<uint32_t*>(e);
+        }
+        k_mips_bricks<<<148 * 4, BRICK_WARPS * 32, 0, c->stream>>>(level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N, export_buf);
+        CK_LAUNCH(c);
+        first_dense = c->n_mip_levels;          // the tail kernel takes every remaining level
+        if (c->cfg.nranks <= 1)                 // (multi-GPU: level 3 is complete only after f184_gather_volume, which runs the tail)
+        {
+            rc = f184_mips_tail_n(c, false);
+            if (rc) return rc;
         }
     }
     for (uint32_t li = first_dense; li < c->n_mip_levels; li++)

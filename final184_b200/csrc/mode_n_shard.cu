@@ -1,0 +1,237 @@
+// mode_n_shard.cu — one NVLink box, one process per GPU: the pieces of the north-star schedule that touch peer memory
+// (include/f184.h "one NVLink box"; DESIGN.md "Multi-GPU").  The reference is single-GPU and single-queue
+// (RHI/Private/Vulkan/DeviceVk.cpp:301-304); nothing here has a counterpart in it.
+//
+//   * the reduce-scatter of the partial volumes is not a separate collective: mode_n_voxelize.cu reduces every fragment
+//     straight into the accumulators of the rank that owns the fragment's Z-slab (red.global.add.v4.f32 on a
+//     peer-mapped pointer, carried by NVLink), so after one barrier each owner holds the exact sum for its slab;
+//   * k_peer_barrier: device-side flag barrier — each rank stores its epoch into every peer's flag array
+//     (st.release.sys over NVLink) and spins on its own array (ld.acquire.sys, local memory): no host round trip and
+//     no NCCL launch on the frame's critical path; a 5 s timeout turns a missing peer into an error instead of a hang;
+//   * k_gather_bricks: the all-gather before tracing — every rank pulls the other ranks' finished bricks, packed by
+//     mode_n_mips.cu into contiguous 4 KB records (level 0 + levels 1-3 of one 8^3 brick), with coalesced 16-byte peer
+//     loads, and writes them through surfaces into its own texture storage; only listed bricks move (Sponza at 512^3:
+//     ~0.12 GB for the whole volume instead of 1.0 GB dense).  Levels >= 4 are then finished locally (k_mips_tail).
+#include "f184_device.cuh"
+
+int f184_mips_tail_n(f184_ctx* c, bool own_stage);      // mode_n_mips.cu
+
+namespace {
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct BarrierArgs
+{
+    uint32_t* flags[8];        // flags[p] = rank p's flag array (own entry: local memory)
+    int rank, nranks;
+    uint32_t epoch;
+};
+
+__global__ void k_peer_barrier(const BarrierArgs B)
+{
+    const int p = threadIdx.x;
+    if (p >= B.nranks || p == B.rank) return;
+    __threadfence_system();                                    // everything this GPU wrote (incl. peer atomics) before the flag
+    st_release_sys(B.flags[p] + B.rank, B.epoch);
+    const uint32_t* mine = B.flags[B.rank] + p;
+    const unsigned long long t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_sys(mine) - B.epoch) < 0)
+    {
+        if (globaltimer_ns() - t0 > 5000000000ull) { B.flags[B.rank][8 + p] = B.epoch; break; }   // timeout marker, no hang
+        __nanosleep(200);
+    }
+}
+
+struct GatherArgs
+{
+    const uint32_t* peer_export[8];
+    const unsigned long long* peer_counters[8];
+    const uint32_t* peer_list[8];
+    int rank, nranks, N, write_linear;
+    cudaSurfaceObject_t rad_surf;
+    uint32_t* rad_lin;
+    uint32_t* lin[3][6];
+    cudaSurfaceObject_t surf[3][6];
+};
+
+constexpr int GATHER_WARPS = 8;
+
+__global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather_bricks(const GatherArgs G)
+{
+    const int p = blockIdx.y;
+    if (p == G.rank) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warp_global = blockIdx.x * GATHER_WARPS + warp, n_warps = gridDim.x * GATHER_WARPS;
+    const uint32_t count = (uint32_t)G.peer_counters[p][F184_COUNTER_COUNT];     // that rank's brick-list cursor
+    const int N = G.N, NB = N >> 3, n1 = N >> 1, n2 = N >> 2, n3 = N >> 3;
+    for (uint32_t i = warp_global; i < count; i += n_warps)
+    {
+        const uint32_t* rec = G.peer_export[p] + (size_t)i * 1024;
+        const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
+        const uint32_t b = G.peer_list[p][i] & 0x7fffffffu;
+        const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
+        uint4 l0[4], l1[3];
+#pragma unroll
+        for (int k = 0; k < 4; k++) l0[k] = rec4[lane + 32 * k];               // 7 independent 16-byte peer loads in flight
+#pragma unroll
+        for (int k = 0; k < 3; k++) l1[k] = rec4[128 + lane + 32 * k];
+        uint2 l2 = make_uint2(0, 0);
+        if (lane < 24) l2 = reinterpret_cast<const uint2*>(rec + 896)[lane];
+        uint32_t l3 = 0;
+        if (lane < 6) l3 = rec[944 + lane];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const int q = lane + 32 * k, row = q >> 1, half = q & 1, y = row & 7, z = row >> 3;
+            surf3Dwrite(l0[k], G.rad_surf, (bx * 8 + half * 4) * 4, by * 8 + y, bz * 8 + z);
+            if (G.write_linear) *reinterpret_cast<uint4*>(G.rad_lin + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4) = l0[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+        {
+            const int j = lane + 32 * k, d = j >> 4, r = j & 15, oy = r & 3, oz = r >> 2;
+            const int gx = bx * 4, gy = by * 4 + oy, gz = bz * 4 + oz;
+            surf3Dwrite(l1[k], G.surf[0][d], gx * 4, gy, gz);
+            if (G.write_linear) *reinterpret_cast<uint4*>(G.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = l1[k];
+        }
+        if (lane < 24)
+        {
+            const int d = lane >> 2, r = lane & 3, oy = r & 1, oz = r >> 1;
+            const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
+            surf3Dwrite(l2, G.surf[1][d], gx * 4, gy, gz);
+            if (G.write_linear) *reinterpret_cast<uint2*>(G.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = l2;
+        }
+        if (lane < 6)
+        {
+            surf3Dwrite(l3, G.surf[2][lane], bx * 4, by, bz);
+            G.lin[2][lane][((size_t)bz * n3 + by) * n3 + bx] = l3;             // level 3 is the source of the local tail: always
+        }
+    }
+}
+
+}  // namespace
+
+// own pointer of a shareable buffer (allocating it on first use)
+int f184_ipc_buffer_ptr(f184_ctx* c, uint32_t buffer, void** out)
+{
+    const uint32_t N = c->cfg.grid_n, n_bricks = (N / 8) * (N / 8) * (N / 8);
+    switch (buffer)
+    {
+    case F184_IPC_ACCUM_COLOR:
+    case F184_IPC_ACCUM_NORMAL:
+    case F184_IPC_BRICK_FLAGS:
+    {
+        const int slot = buffer == F184_IPC_ACCUM_COLOR ? F184_SLOT_ACCUM_COLOR : (buffer == F184_IPC_ACCUM_NORMAL ? F184_SLOT_ACCUM_NORMAL : F184_SLOT_BRICK_FLAGS);
+        int rc = f184_ensure_image(c, slot);
+        if (rc) return rc;
+        if (!c->img[slot].owned) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "ipc: slot %d is bound to caller memory", slot);
+        *out = c->img[slot].ptr;
+        return F184_OK;
+    }
+    case F184_IPC_EXPORT:
+        if (!c->export_buf)
+        {
+            const uint32_t own = n_bricks / (c->cfg.nranks ? c->cfg.nranks : 1);
+            CK(c, cudaMalloc(&c->export_buf, 4096ull * own));
+        }
+        *out = c->export_buf;
+        return F184_OK;
+    case F184_IPC_COUNTERS: *out = c->counters_dev; return F184_OK;
+    case F184_IPC_BRICK_LIST:
+        if (!c->brick_list)
+        {
+            CK(c, cudaMalloc(&c->brick_prev, 4ull * n_bricks));
+            CK(c, cudaMemsetAsync(c->brick_prev, 0, 4ull * n_bricks, c->stream));
+            CK(c, cudaMalloc(&c->brick_list, 4ull * n_bricks));
+        }
+        *out = c->brick_list;
+        return F184_OK;
+    case F184_IPC_SYNC:
+        if (!c->sync_flags)
+        {
+            CK(c, cudaMalloc(&c->sync_flags, 16 * sizeof(uint32_t)));
+            CK(c, cudaMemsetAsync(c->sync_flags, 0, 16 * sizeof(uint32_t), c->stream));
+        }
+        *out = c->sync_flags;
+        return F184_OK;
+    }
+    return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "ipc: unknown buffer %u", buffer);
+}
+
+static int peer_ptr(f184_ctx* c, uint32_t p, uint32_t buffer, void** out)
+{
+    if (p == c->cfg.rank) return f184_ipc_buffer_ptr(c, buffer, out);
+    if (!c->peer[p].buf[buffer]) return f184_fail(c, F184_ERR_NOT_READY, "rank %u: buffer %u of rank %u was not imported (f184_ipc_import)", c->cfg.rank, buffer, p);
+    *out = c->peer[p].buf[buffer];
+    return F184_OK;
+}
+
+extern "C" int f184_peer_barrier(f184_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    if (c->cfg.nranks <= 1) return F184_OK;
+    CK(c, cudaSetDevice(c->cfg.device));
+    BarrierArgs B{};
+    for (uint32_t p = 0; p < c->cfg.nranks; p++)
+    {
+        void* q = nullptr;
+        int rc = peer_ptr(c, p, F184_IPC_SYNC, &q);
+        if (rc) return rc;
+        B.flags[p] = reinterpret_cast<uint32_t*>(q);
+    }
+    B.rank = (int)c->cfg.rank; B.nranks = (int)c->cfg.nranks;
+    B.epoch = ++c->barrier_epoch;
+    int rc = f184_stage_begin(c, F184_STAGE_EXCHANGE);
+    if (rc) return rc;
+    k_peer_barrier<<<1, 32, 0, c->stream>>>(B);
+    CK_LAUNCH(c);
+    return f184_stage_end(c, F184_STAGE_EXCHANGE);
+}
+
+int f184_gather_n(f184_ctx* c)
+{
+    if (c->cfg.nranks <= 1) return F184_OK;
+    int rc = f184_mode_n_alloc(c); if (rc) return rc;
+    rc = f184_ensure_image(c, F184_SLOT_RADIANCE); if (rc) return rc;
+    rc = f184_ensure_image(c, F184_SLOT_MIPS); if (rc) return rc;
+    GatherArgs G{};
+    for (uint32_t p = 0; p < c->cfg.nranks; p++)
+    {
+        void *e = nullptr, *k = nullptr, *l = nullptr;
+        if ((rc = peer_ptr(c, p, F184_IPC_EXPORT, &e)) || (rc = peer_ptr(c, p, F184_IPC_COUNTERS, &k)) || (rc = peer_ptr(c, p, F184_IPC_BRICK_LIST, &l))) return rc;
+        G.peer_export[p] = reinterpret_cast<const uint32_t*>(e);
+        G.peer_counters[p] = reinterpret_cast<const unsigned long long*>(k);
+        G.peer_list[p] = reinterpret_cast<const uint32_t*>(l);
+    }
+    G.rank = (int)c->cfg.rank; G.nranks = (int)c->cfg.nranks; G.N = (int)c->cfg.grid_n;
+    G.write_linear = (c->cfg.flags & F184_FLAG_GATHER_LINEAR) ? 1 : 0;
+    G.rad_surf = c->rad_surf;
+    G.rad_lin = img_ptr<uint32_t>(c, F184_SLOT_RADIANCE);
+    uint32_t* mips = img_ptr<uint32_t>(c, F184_SLOT_MIPS);
+    for (int l = 0; l < 3; l++)
+        for (int d = 0; d < 6; d++)
+        {
+            const uint64_t n = c->mip_levels[l].n;
+            G.lin[l][d] = mips + c->mip_levels[l].offset_texels + (uint64_t)d * n * n * n;
+            G.surf[l][d] = c->dir_surf[d][l];
+        }
+    rc = f184_stage_begin(c, F184_STAGE_EXCHANGE);
+    if (rc) return rc;
+    k_gather_bricks<<<dim3(148, c->cfg.nranks), GATHER_WARPS * 32, 0, c->stream>>>(G);
+    CK_LAUNCH(c);
+    rc = f184_stage_end(c, F184_STAGE_EXCHANGE);
+    if (rc) return rc;
+    return f184_mips_tail_n(c, true);
+}

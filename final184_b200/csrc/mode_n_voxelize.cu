@@ -111,8 +111,12 @@ struct VoxArgs
     const MatDev* mats;
     uint32_t tri_first, tri_end;
     int N;
-    float4 *accC, *accN;
-    uint32_t* brick_flags;
+    // accumulators / brick flags of the rank that owns Z-slab (z >> slab_shift): own memory, or a peer's memory mapped
+    // over NVLink (then the atomics below ARE the reduce-scatter of the partial volumes); one GPU: slab_shift = 31
+    float4* accC[8];
+    float4* accN[8];
+    uint32_t* brick_flags[8];
+    int slab_shift;
     unsigned long long* frag_counter;
     unsigned long long* queue_state;   // (entries << 40) | tasks, one 64-bit word so both advance together
     uint2* queue;                      // per large triangle: (triangle, first task)
@@ -312,9 +316,10 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
         const int by = s.d == 0 ? iu : (s.d == 1 ? kd : iv);
         const int bz = s.d == 0 ? iv : (s.d == 1 ? iu : kd);
         const size_t o = brick_major(bx, by, bz, A.N >> 3);
-        atomicAdd(A.accC + o, make_float4(r8, g8, b8, 1.0f));     // red.global.add.v4.f32
-        atomicAdd(A.accN + o, make_float4(nx8, ny8, nz8, 0.0f));
-        A.brick_flags[o >> 9] = 1u;
+        const int owner = bz >> A.slab_shift;
+        atomicAdd(A.accC[owner] + o, make_float4(r8, g8, b8, 1.0f));     // red.global.add.v4.f32 (peer memory when owner != this rank)
+        atomicAdd(A.accN[owner] + o, make_float4(nx8, ny8, nz8, 0.0f));
+        A.brick_flags[owner][o >> 9] = 1u;
         frags++;
     }
     return frags;
@@ -420,12 +425,12 @@ __global__ void k_view_model_n(M4 View, const M4* __restrict__ model, M4* __rest
 // pass 1: one thread per brick flag -> compact list (warp-aggregated append).  Entry = brick | touched << 31.
 __global__ void __launch_bounds__(256)
 k_brick_compact(uint32_t* __restrict__ brick_flags, uint32_t* __restrict__ brick_prev, uint32_t* __restrict__ brick_list,
-                unsigned long long* __restrict__ counters, uint32_t n_bricks)
+                unsigned long long* __restrict__ counters, uint32_t b0, uint32_t b1)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t bi = b0 + blockIdx.x * blockDim.x + threadIdx.x;       // [b0, b1): the bricks of this rank's Z-slab
     uint32_t flag = 0, prev = 0;
-    if (bi < n_bricks) { flag = brick_flags[bi]; prev = brick_prev[bi]; }
+    if (bi < b1) { flag = brick_flags[bi]; prev = brick_prev[bi]; }
     if (flag | prev) { brick_flags[bi] = 0; brick_prev[bi] = flag; }
     const unsigned int todo = __ballot_sync(0xffffffffu, (flag | prev) != 0);
     const unsigned int touched = __ballot_sync(0xffffffffu, flag != 0);
@@ -498,7 +503,15 @@ k_normalise_n(float4* __restrict__ accC, float4* __restrict__ accN, uchar4* __re
 
 }  // namespace
 
-int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
+static int slab_shift_of(const f184_ctx* c)
+{
+    if (c->cfg.nranks <= 1) return 31;
+    int sh = 0;
+    while ((1u << sh) < c->cfg.grid_n / c->cfg.nranks) sh++;
+    return sh;
+}
+
+int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
 {
     for (int s : {F184_SLOT_ACCUM_COLOR, F184_SLOT_ACCUM_NORMAL, F184_SLOT_VOX_ALBEDO, F184_SLOT_VOX_NORMAL, F184_SLOT_BRICK_FLAGS})
     {
@@ -506,12 +519,12 @@ int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
         if (rc) return rc;
     }
     const int N = (int)c->cfg.grid_n;
-    const uint32_t n_bricks = (uint32_t)(N / 8) * (N / 8) * (N / 8);
-    if (!c->brick_prev)
+    const uint32_t G = c->cfg.nranks;
+    if (G > 1 && ((G & (G - 1)) || G > 8 || N / (int)G < 8)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "nranks must be 1, 2, 4 or 8 with slabs of >= 8 voxels");
     {
-        CK(c, cudaMalloc(&c->brick_prev, 4ull * n_bricks));
-        CK(c, cudaMemsetAsync(c->brick_prev, 0, 4ull * n_bricks, c->stream));
-        CK(c, cudaMalloc(&c->brick_list, 4ull * n_bricks));
+        void* dummy = nullptr;
+        int rc = f184_ipc_buffer_ptr(c, F184_IPC_BRICK_LIST, &dummy);      // brick_prev / brick_list
+        if (rc) return rc;
     }
     if (c->vox_queue_cap < c->n_tris)
     {   // worst case every triangle is large: (8 + 192) B per triangle
@@ -525,6 +538,24 @@ int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
         CK(c, cudaMalloc(&c->vm_dev, sizeof(M4) * c->n_models));
         c->vm_cap = c->n_models;
     }
+    VoxArgs A{};
+    for (uint32_t p = 0; p < (G ? G : 1); p++)
+    {
+        if (p == c->cfg.rank || G <= 1)
+        {
+            A.accC[p] = img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR); A.accN[p] = img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL);
+            A.brick_flags[p] = img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS);
+        }
+        else
+        {
+            if (!c->peer[p].buf[F184_IPC_ACCUM_COLOR] || !c->peer[p].buf[F184_IPC_ACCUM_NORMAL] || !c->peer[p].buf[F184_IPC_BRICK_FLAGS])
+                return f184_fail(c, F184_ERR_NOT_READY, "voxelize: accumulators of rank %u were not imported (f184_ipc_import)", p);
+            A.accC[p] = reinterpret_cast<float4*>(c->peer[p].buf[F184_IPC_ACCUM_COLOR]);
+            A.accN[p] = reinterpret_cast<float4*>(c->peer[p].buf[F184_IPC_ACCUM_NORMAL]);
+            A.brick_flags[p] = reinterpret_cast<uint32_t*>(c->peer[p].buf[F184_IPC_BRICK_FLAGS]);
+        }
+    }
+    A.slab_shift = slab_shift_of(c);
     M4 View;
     memcpy(View.m, cam->ViewMat, 64);
     k_view_model_n<<<(c->n_models * 16 + 127) / 128, 128, 0, c->stream>>>(View, c->model_mats, c->vm_dev, c->n_models);
@@ -536,20 +567,16 @@ int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
 
     int rc = f184_stage_begin(c, F184_STAGE_VOXELIZE);
     if (rc) return rc;
-    // counters: fragments, occupied, bricks | brick-list cursor, voxelizer queue state (stored right after the public counters)
+    // device words after the public counters: [COUNT] brick-list cursor, [COUNT+1] voxelizer queue state, [COUNT+2] mip tail ticket
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_FRAGMENTS, 0, 8, c->stream));
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_OCCUPIED, 0, 8, c->stream));
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_BRICKS, 0, 8 * 3, c->stream));   // BRICKS, list cursor, queue state
+    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_COUNT + 1, 0, 8, c->stream));
     if (end > first)
     {
-        VoxArgs A{};
         A.pos = c->pos; A.nrm = c->nrm; A.uv = c->uv; A.idx = c->idx; A.tri_mat = c->tri_mat; A.tri_model = c->tri_model;
         A.model_mats = c->model_mats; A.vm_mats = c->vm_dev;
         memcpy(A.Proj.m, cam->ProjMat, 64);
         A.texs = c->tex_dev; A.mats = c->mat_dev;
         A.tri_first = first; A.tri_end = end; A.N = N;
-        A.accC = img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR); A.accN = img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL);
-        A.brick_flags = img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS);
         A.frag_counter = c->counters_dev + F184_COUNTER_FRAGMENTS;
         A.queue_state = c->counters_dev + F184_COUNTER_COUNT + 1;
         A.queue_tris = reinterpret_cast<uint4*>(c->vox_queue);                      // 192 B records first (16-byte aligned)
@@ -560,20 +587,28 @@ int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
         k_voxelize_raster<<<148 * 4 * 4, RASTER_THREADS, 0, c->stream>>>(A);
         CK_LAUNCH(c);
     }
-    rc = f184_stage_end(c, F184_STAGE_VOXELIZE);
+    return f184_stage_end(c, F184_STAGE_VOXELIZE);
+}
+
+int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
+{
+    int rc = f184_voxelize_accumulate_n(c, cam);
     if (rc) return rc;
-    if (c->defer_normalise) return F184_OK;      // multi-GPU: partial volumes are summed across ranks first
     return f184_normalise_n(c);
 }
 
+// Normalise this rank's Z-slab (the whole volume on one GPU).
 int f184_normalise_n(f184_ctx* c)
 {
     const int N = (int)c->cfg.grid_n;
-    const uint32_t n_bricks = (uint32_t)(N / 8) * (N / 8) * (N / 8);
+    const uint32_t NB = (uint32_t)N / 8, G = c->cfg.nranks > 1 ? c->cfg.nranks : 1;
+    const uint32_t b0 = (c->cfg.rank % G) * (NB / G) * NB * NB, b1 = b0 + (NB / G) * NB * NB;
     int rc = f184_stage_begin(c, F184_STAGE_NORMALISE);
     if (rc) return rc;
-    k_brick_compact<<<(n_bricks + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,
-                                                                  c->counters_dev, n_bricks);
+    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_OCCUPIED, 0, 8, c->stream));
+    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_BRICKS, 0, 16, c->stream));        // BRICKS + the list cursor
+    k_brick_compact<<<(b1 - b0 + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,
+                                                                c->counters_dev, b0, b1);
     CK_LAUNCH(c);
     k_normalise_n<<<148 * 8, 256, 0, c->stream>>>(img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
                                                   img_ptr<uchar4>(c, F184_SLOT_VOX_ALBEDO), img_ptr<char4>(c, F184_SLOT_VOX_NORMAL),

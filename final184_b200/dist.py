@@ -81,29 +81,108 @@ def view_ranges(n_views: int, nranks: int):
 
 # ---- the sharded frame ------------------------------------------------------------------------------
 class ShardedVoxelGI:
-    """The voxel/indirect section of one frame on rank `rank` of `nranks` GPUs of one NVLink box."""
+    """The voxel/indirect section of one frame on rank `rank` of `nranks` GPUs of one NVLink box.
+
+    mode "single"     one GPU.
+         "slab"       the north-star schedule (include/f184.h "one NVLink box"): triangle-range voxelization with the
+                      reduce-scatter fused into the voxelizer as peer atomics, Z-slab owners normalise / inject / build
+                      levels 1-3, a peer gather of the finished bricks, row-band tracing.  Needs connect().
+         "replicate"  no exchange at all: every rank builds the whole volume, only the trace is split.
+         "host"       the slab schedule's HOST logic with the exchange done by torch.distributed on host arrays
+                      (all_reduce of the partial accumulators): what the CPU tests drive with the gloo backend and the
+                      oracle library; never used on the product path.
+    """
 
     def __init__(self, grid_n, width, height, shadow_res=2048, device=0, rank=0, nranks=1, scene: S.Scene | None = None,
-                 mode="replicate", lib=None):
-        self.rank, self.nranks, self.mode = rank, nranks, mode
+                 mode=None, lib=None, voxel_cam: S.ViewConstants | None = None, flags=0):
+        self.rank, self.nranks = rank, nranks
+        self.mode = mode or ("slab" if nranks > 1 else "single")
+        if nranks == 1:
+            self.mode = "single"
         self.grid_n, self.width, self.height = grid_n, width, height
-        self.ctx = A.VoxelGI(grid_n, width, height, A.MODE_NORTHSTAR, shadow_res=shadow_res, device=device, rank=rank, nranks=nranks, lib=lib)
+        ctx_ranks = (rank, nranks) if self.mode == "slab" else (0, 1)       # only the slab schedule shards the volume
+        self.ctx = A.VoxelGI(grid_n, width, height, A.MODE_NORTHSTAR, shadow_res=shadow_res, device=device, rank=ctx_ranks[0], nranks=ctx_ranks[1],
+                             lib=lib, flags=flags)
         self.rows = row_ranges(height, nranks)[rank]
         self.ctx.set_trace_rows(*self.rows)
+        self.tri_range = None
+        self.connected = False
         if scene is not None:
-            self.ctx.upload_scene(scene)
+            self.upload_scene(scene, voxel_cam)
+
+    def upload_scene(self, scene: S.Scene, voxel_cam: S.ViewConstants | None = None):
+        self.ctx.upload_scene(scene)
+        if self.mode in ("slab", "host"):
+            w = triangle_weights(scene, voxel_cam, self.grid_n) if voxel_cam is not None else np.ones(scene.n_tris)
+            self.tri_range = triangle_ranges(w, self.nranks)[self.rank]
+            self.ctx.set_triangle_range(*self.tri_range)
+
+    def connect(self):
+        """Exchange CUDA IPC handles of the shared buffers with the other ranks (torch.distributed is the rendezvous)."""
+        if self.mode != "slab" or self.connected:
+            return
+        import torch.distributed as dist
+        mine = {b: self.ctx.ipc_export(b) for b in range(A.IPC_COUNT)}
+        everyone = [None] * self.nranks
+        dist.all_gather_object(everyone, mine)
+        for p, handles in enumerate(everyone):
+            if p == self.rank:
+                continue
+            for b, h in handles.items():
+                self.ctx.ipc_import(p, b, h)
+        dist.barrier()
+        self.connected = True
 
     def describe(self):
-        if self.nranks == 1:
+        if self.mode == "single":
             return "1 GPU"
-        return f"{self.nranks} GPUs: volume replicated per rank (no exchange), trace split into {self.nranks} row bands"
+        if self.mode == "replicate":
+            return f"{self.nranks} GPUs: volume replicated per rank (no exchange), trace split into {self.nranks} row bands"
+        return (f"{self.nranks} GPUs: triangle ranges balanced by projected area, fragments reduced into the Z-slab owner's accumulators by peer "
+                f"atomics over NVLink, slab-local normalise/inject/mips, peer gather of the listed bricks, trace split into {self.nranks} row bands")
 
     def frame(self, voxel_cam, k):
         c = self.ctx
-        c.voxelize(voxel_cam)
-        c.inject(k)
-        c.build_mips()
+        if self.mode in ("single", "replicate"):
+            c.voxelize(voxel_cam)
+            c.inject(k)
+            c.build_mips()
+        elif self.mode == "slab":
+            if not self.connected:
+                raise A.F184Error("ShardedVoxelGI.frame: call connect() first (slab mode shares buffers between ranks)")
+            c.voxelize_accumulate(voxel_cam)     # peer atomics: the reduce-scatter happens here
+            c.peer_barrier()                     # every rank's fragments have landed in their owners
+            c.normalise()
+            c.inject(k)
+            c.build_mips()                       # levels 1-3 of the own slab + packed export records
+            c.peer_barrier()
+            c.gather_volume()                    # pull the other slabs' bricks, finish the small levels
+        else:                                    # "host": same order, exchange through torch.distributed on host arrays
+            import torch
+            import torch.distributed as dist
+            c.voxelize_accumulate(voxel_cam)
+            for slot in (A.SLOT_ACCUM_COLOR, A.SLOT_ACCUM_NORMAL):
+                t = torch.from_numpy(c.readback(slot))
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                c.upload(slot, t.numpy())
+            c.normalise()
+            c.inject(k)
+            c.build_mips()
         c.trace_indirect(k)
+
+    def gather_image(self):
+        """The full traced image on every rank (a consumer that wants one image; not part of the frame)."""
+        img = self.ctx.readback(A.SLOT_INDIRECT_OUT)
+        if self.nranks == 1:
+            return img
+        import torch
+        import torch.distributed as dist
+        bands = [None] * self.nranks
+        dist.all_gather_object(bands, (self.rows, img[self.rows[0]:self.rows[1]].copy()))
+        out = np.zeros_like(img)
+        for (y0, y1), band in bands:
+            out[y0:y1] = band
+        return out
 
     def comm_ms_per_frame(self):
         return 0.0

@@ -121,6 +121,7 @@ typedef enum f184_flags {
     F184_FLAG_NONE = 0,
     F184_FLAG_EXTERNAL_RANDS = 1,  /* mode R trace: rands come from a bound buffer (march-only parity) */
     F184_FLAG_NO_TMA = 2,          /* mode N mips: dense, plain one-thread-per-texel kernel for every level (cross-check) */
+    F184_FLAG_GATHER_LINEAR = 8,   /* multi-GPU: f184_gather_volume also fills the linear RADIANCE / MIPS slots (tests) */
     F184_FLAG_DENSE_MIPS = 4       /* mode N mips: dense chain, TMA-staged tiles for the large levels (default is the sparse
                                       brick-list path for levels 1-3 + one fused launch for the rest) */
 } f184_flags;
@@ -197,7 +198,8 @@ typedef enum f184_stage_id {
     F184_STAGE_TRACE = 5,
     F184_STAGE_GTAO = 6,
     F184_STAGE_BLUR = 7,
-    F184_STAGE_COUNT = 8
+    F184_STAGE_EXCHANGE = 8,       /* multi-GPU: peer barriers + gather of the other ranks' bricks */
+    F184_STAGE_COUNT = 9
 } f184_stage_id;
 
 typedef enum f184_counter_id {
@@ -271,6 +273,36 @@ int f184_bind_rands(f184_ctx* ctx, const float* device_rands, size_t count);
  * [z0, z1) of every volume level and traces rows [y0, y1).  Defaults are derived from rank/nranks. */
 int f184_set_triangle_range(f184_ctx* ctx, uint32_t first, uint32_t count);
 int f184_set_trace_rows(f184_ctx* ctx, uint32_t y0, uint32_t y1);
+
+/* ---- one NVLink box, one process per GPU (DESIGN.md "Multi-GPU").  The reference is single-GPU
+ * (RHI/Private/Vulkan/DeviceVk.cpp:301-304); this is the north-star schedule:
+ *   f184_voxelize_accumulate  rank r rasterises ITS triangle range; every fragment is reduced straight into the
+ *                             accumulators of the rank that owns the fragment's Z-slab — red.global.add.v4.f32 on
+ *                             peer memory over NVLink: the reduce-scatter is fused into the voxelizer
+ *   f184_peer_barrier         device-side flag barrier over peer memory (no host round trip, no NCCL launch)
+ *   f184_normalise / f184_inject / f184_build_mips   owner works on its slab's bricks only
+ *   f184_peer_barrier
+ *   f184_gather_volume        every rank pulls the other ranks' finished bricks (packed 4 KB records, levels 0-3) over
+ *                             NVLink straight into its own texture storage, then finishes the small levels locally
+ *   f184_trace_indirect       rows [y0, y1) of the screen
+ * Buffers are shared between processes with CUDA IPC handles, exchanged by the caller (torch.distributed). */
+typedef enum f184_ipc_buffer {
+    F184_IPC_ACCUM_COLOR = 0,
+    F184_IPC_ACCUM_NORMAL = 1,
+    F184_IPC_BRICK_FLAGS = 2,
+    F184_IPC_EXPORT = 3,        /* packed per-brick records written by f184_build_mips */
+    F184_IPC_COUNTERS = 4,
+    F184_IPC_BRICK_LIST = 5,
+    F184_IPC_SYNC = 6,          /* barrier flags */
+    F184_IPC_COUNT = 7
+} f184_ipc_buffer;
+typedef struct f184_ipc_handle { uint8_t opaque[64]; } f184_ipc_handle;
+int f184_ipc_export(f184_ctx* ctx, uint32_t buffer, f184_ipc_handle* out_handle);
+int f184_ipc_import(f184_ctx* ctx, uint32_t peer_rank, uint32_t buffer, const f184_ipc_handle* handle);
+int f184_voxelize_accumulate(f184_ctx* ctx, const f184_view_constants* voxel_cam);   /* f184_voxelize = this + f184_normalise */
+int f184_normalise(f184_ctx* ctx);
+int f184_peer_barrier(f184_ctx* ctx);
+int f184_gather_volume(f184_ctx* ctx);
 
 /* ---- measurement */
 int f184_stage_time_ms(f184_ctx* ctx, uint32_t stage, float* out_ms);   /* last run of the stage; synchronous */

@@ -249,6 +249,8 @@ int f184o_copy_indirect_to_history(f184o_ctx* c)
 int orc_voxelize_r(f184o_ctx*, const f184_view_constants*);
 int orc_trace_r(f184o_ctx*, const f184_trace_constants*);
 int orc_voxelize_n(f184o_ctx*, const f184_view_constants*);
+int orc_voxelize_accumulate_n(f184o_ctx*, const f184_view_constants*);
+int orc_normalise_n(f184o_ctx*);
 int orc_inject_n(f184o_ctx*, const f184_sun*, const f184_extended_matrices*);
 int orc_mips_n(f184o_ctx*);
 int orc_trace_n(f184o_ctx*, const f184_trace_constants*);
@@ -258,6 +260,16 @@ int f184o_voxelize(f184o_ctx* c, const f184_view_constants* cam)
     if (!c || !cam) return F184_ERR_INVALID_ARGUMENT;
     if (!c->n_tris) { c->err = "no scene"; return F184_ERR_NOT_READY; }
     return c->cfg.mode == F184_MODE_REFERENCE ? orc_voxelize_r(c, cam) : orc_voxelize_n(c, cam);
+}
+int f184o_voxelize_accumulate(f184o_ctx* c, const f184_view_constants* cam)
+{
+    if (!c || !cam || c->cfg.mode != F184_MODE_NORTHSTAR) return F184_ERR_INVALID_ARGUMENT;
+    return orc_voxelize_accumulate_n(c, cam);
+}
+int f184o_normalise(f184o_ctx* c)
+{
+    if (!c || c->cfg.mode != F184_MODE_NORTHSTAR) return F184_ERR_INVALID_ARGUMENT;
+    return orc_normalise_n(c);
 }
 int f184o_inject(f184o_ctx* c, const f184_sun* sun, const f184_extended_matrices* m)
 {

@@ -140,7 +140,18 @@ M4 invert(const M4& A)
 // =================================================================================================
 // B.1 conservative voxelization + B.2 normalise
 // =================================================================================================
+extern "C" int orc_normalise_n(f184o_ctx* c);
+extern "C" int orc_voxelize_accumulate_n(f184o_ctx* c, const f184_view_constants* cam);
+
 extern "C" int orc_voxelize_n(f184o_ctx* c, const f184_view_constants* cam)
+{
+    int rc = orc_voxelize_accumulate_n(c, cam);
+    return rc ? rc : orc_normalise_n(c);
+}
+
+// B.1: accumulate the fragments of triangles [tri_first, tri_first + tri_count) into ZEROED accumulators (a partial
+// volume: the multi-GPU schedule sums these across ranks before normalising).
+extern "C" int orc_voxelize_accumulate_n(f184o_ctx* c, const f184_view_constants* cam)
 {
     double t0 = now_ms();
     for (int s : {F184_SLOT_ACCUM_COLOR, F184_SLOT_ACCUM_NORMAL, F184_SLOT_VOX_ALBEDO, F184_SLOT_VOX_NORMAL})
@@ -287,8 +298,18 @@ extern "C" int orc_voxelize_n(f184o_ctx* c, const f184_view_constants* cam)
     }
     c->counters[F184_COUNTER_FRAGMENTS] = frags;
     c->stage_ms[F184_STAGE_VOXELIZE] = (float)(now_ms() - t0);
+    return F184_OK;
+}
 
-    // ---- B.2 normalise
+// B.2 normalise (reads the accumulators as they are: summed partial volumes included)
+extern "C" int orc_normalise_n(f184o_ctx* c)
+{
+    for (int s : {F184_SLOT_ACCUM_COLOR, F184_SLOT_ACCUM_NORMAL, F184_SLOT_VOX_ALBEDO, F184_SLOT_VOX_NORMAL})
+    { int rc = ensure_image(c, s); if (rc) return rc; }
+    const uint32_t N = c->cfg.grid_n;
+    const size_t nvox = (size_t)N * N * N;
+    float* accC = image_ptr<float>(c, F184_SLOT_ACCUM_COLOR);
+    float* accN = image_ptr<float>(c, F184_SLOT_ACCUM_NORMAL);
     double t1 = now_ms();
     uint8_t* alb = image_ptr<uint8_t>(c, F184_SLOT_VOX_ALBEDO);
     int8_t* nrm = image_ptr<int8_t>(c, F184_SLOT_VOX_NORMAL);

@@ -1,0 +1,64 @@
+"""Worker for tests/test_gpu_multi.py (run under torchrun, one rank per GPU): the slab schedule over peer memory must
+give every rank the same volume, texture storage and image rows as one GPU computing the whole frame."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from final184_b200 import api as A, dist as D, scene as S   # noqa: E402
+from final184_b200.fixture import frame_inputs               # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, W, H, SH = 64, 160, 96, 256
+    sc = S.procedural_scene(seed=1)
+    cams = {n: S.fixture_constants(n) for n in ("main", "shadow", "voxel")}
+    fi = frame_inputs(sc, cams["main"], cams["shadow"], W, H, SH, 0, cache=False)
+    k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
+    g = D.ShardedVoxelGI(N, W, H, shadow_res=SH, device=local, rank=rank, nranks=world, scene=sc, voxel_cam=cams["voxel"], flags=A.FLAG_GATHER_LINEAR)
+    one = A.VoxelGI(N, W, H, A.MODE_NORTHSTAR, shadow_res=SH, device=local)
+    one.upload_scene(sc)
+    for c in (g.ctx, one):
+        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_MATERIAL, "material"), (A.SLOT_SHADOW, "shadow")):
+            c.upload(slot, fi[key])
+    g.connect()
+    bad = []
+    for frame in range(3):
+        if frame == 2:      # fewer triangles: bricks that became empty must be cleared on every rank
+            half = sc.n_tris // 2
+            f0, cnt = g.tri_range
+            g.ctx.set_triangle_range(f0, max(0, min(f0 + cnt, half) - f0))
+            one.set_triangle_range(0, half)
+        g.frame(cams["voxel"], k)
+        one.voxelize(cams["voxel"]); one.inject(k); one.build_mips(); one.trace_indirect(k)
+        g.ctx.sync(); one.sync()
+        dist.barrier()       # nobody starts the next frame's atomics while a peer still reads this frame back
+        if not np.array_equal(g.ctx.readback(A.SLOT_RADIANCE), one.readback(A.SLOT_RADIANCE)): bad.append(f"frame {frame}: radiance")
+        if not np.array_equal(g.ctx.readback(A.SLOT_MIPS), one.readback(A.SLOT_MIPS)): bad.append(f"frame {frame}: mips")
+        if not np.array_equal(g.ctx.read_array(-1, 0, N), one.read_array(-1, 0, N)): bad.append(f"frame {frame}: level-0 array")
+        m, lvl = N // 2, 0
+        while m >= 1:
+            for d in range(6):
+                if not np.array_equal(g.ctx.read_array(d, lvl, m), one.read_array(d, lvl, m)): bad.append(f"frame {frame}: array dir {d} level {lvl + 1}")
+            m //= 2; lvl += 1
+        y0, y1 = g.rows
+        a, b = g.ctx.readback(A.SLOT_INDIRECT_OUT)[y0:y1], one.readback(A.SLOT_INDIRECT_OUT)[y0:y1]
+        if not np.array_equal(a.view(np.uint16), b.view(np.uint16)): bad.append(f"frame {frame}: image rows {y0}:{y1}")
+        dist.barrier()
+    frags = torch.tensor([float(g.ctx.counter(A.COUNTER_FRAGMENTS))], device=f"cuda:{local}")
+    dist.all_reduce(frags)
+    print(f"rank {rank}: {'OK' if not bad else 'MISMATCH ' + '; '.join(bad[:6])} (fragments over ranks {int(frags.item())})", flush=True)
+    g.close(); one.close()
+    dist.destroy_process_group()
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+"""Host-side logic of the multi-GPU schedule (final184_b200/dist.py), on CPU: the partitioning helpers, and the
+sharded frame at world_size 2 over the gloo backend with the CPU oracle standing in for the device library —
+triangle ranges + summed partial accumulators + row bands must reproduce the single-process frame bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from final184_b200 import api as A
+from final184_b200 import dist as D
+from final184_b200 import scene as S
+from final184_b200.fixture import frame_inputs
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE = os.path.join(REPO, "oracle", "_build", "libf184_oracle.so")
+W, H, N, SH = 64, 40, 32, 128
+
+
+def test_triangle_ranges_cover_and_balance():
+    rng = np.random.default_rng(0)
+    w = rng.pareto(1.5, 10000) + 1.0                   # heavy tail, like Sponza's triangle areas
+    for n in (1, 2, 3, 8):
+        r = D.triangle_ranges(w, n)
+        assert r[0][0] == 0 and sum(c for _, c in r) == len(w)
+        assert all(r[i][0] + r[i][1] == r[i + 1][0] for i in range(n - 1))
+        loads = [w[f:f + c].sum() for f, c in r]
+        assert max(loads) <= w.sum() / n + w.max() + 1e-9
+    assert D.triangle_ranges(np.ones(0), 4) == [(0, 0)] * 4
+    assert D.triangle_ranges(np.ones(3), 8)[-1][0] == 3
+
+
+def test_slab_row_view_ranges():
+    assert D.slab_ranges(512, 8) == [(64 * r, 64 * (r + 1)) for r in range(8)]
+    assert D.slab_ranges(4, 8)[3] == (1, 2) and D.slab_ranges(4, 8)[0] == (0, 0)       # empty slabs once n < nranks
+    for h, n in ((2160, 8), (1080, 8), (36, 4), (7, 2)):
+        rr = D.row_ranges(h, n)
+        assert rr[0][0] == 0 and rr[-1][1] == h and all(rr[i][1] == rr[i + 1][0] for i in range(n - 1))
+        assert all(y0 % 8 == 0 for y0, _ in rr)
+    assert D.view_ranges(64, 8) == [(8 * r, 8 * r + 8) for r in range(8)]
+
+
+def test_triangle_weights_track_projected_area(proc_scene, cams):
+    w = D.triangle_weights(proc_scene, cams["voxel"], 128)
+    assert w.shape == (proc_scene.n_tris,) and (w >= 4.0).all()
+    big = D.triangle_weights(proc_scene, cams["voxel"], 256)
+    assert big.sum() > 2.5 * w.sum() - 4.0 * len(w) * 3     # columns grow ~4x with the grid edge doubling
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        olib = A.Library(ORACLE, "f184o_", product=False)
+        sc = S.procedural_scene(seed=1)
+        cams = {n: S.fixture_constants(n) for n in ("main", "shadow", "voxel")}
+        fi = frame_inputs(sc, cams["main"], cams["shadow"], W, H, SH, 0, cache=False)
+        g = D.ShardedVoxelGI(N, W, H, shadow_res=SH, rank=rank, nranks=world, scene=sc, mode="host", lib=olib, voxel_cam=cams["voxel"])
+        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_MATERIAL, "material"), (A.SLOT_SHADOW, "shadow")):
+            g.ctx.upload(slot, fi[key])
+        k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
+        g.frame(cams["voxel"], k)
+        img = g.gather_image()
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), img=img, rad=g.ctx.readback(A.SLOT_RADIANCE), tri=np.array(g.tri_range), rows=np.array(g.rows),
+                 frags=g.ctx.counter(A.COUNTER_FRAGMENTS))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_frame_world2_gloo_equals_single_process(tmp_path, oracle_lib, proc_scene, cams):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / f"rank{i}.npz") for i in range(world)]
+    # single-process reference run of the same frame
+    o = A.VoxelGI(N, W, H, A.MODE_NORTHSTAR, shadow_res=SH, lib=oracle_lib)
+    o.upload_scene(proc_scene)
+    fi = frame_inputs(proc_scene, cams["main"], cams["shadow"], W, H, SH, 0, cache=False)
+    for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_MATERIAL, "material"), (A.SLOT_SHADOW, "shadow")):
+        o.upload(slot, fi[key])
+    k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
+    o.voxelize(cams["voxel"]); o.inject(k); o.build_mips(); o.trace_indirect(k)
+    want = o.readback(A.SLOT_INDIRECT_OUT)
+    # the triangle ranges partition the scene, the row bands partition the screen
+    assert r[0]["tri"][0] == 0 and r[0]["tri"].sum() == r[1]["tri"][0] and r[1]["tri"].sum() == proc_scene.n_tris
+    assert r[0]["rows"][1] == r[1]["rows"][0] and r[1]["rows"][1] == H
+    assert int(r[0]["frags"]) + int(r[1]["frags"]) == o.counter(A.COUNTER_FRAGMENTS)
+    for i in range(world):
+        assert np.array_equal(r[i]["rad"], o.readback(A.SLOT_RADIANCE)), f"rank {i}: summed partial volumes differ from the whole"
+        assert np.array_equal(r[i]["img"].view(np.uint16), want.view(np.uint16)), f"rank {i}: assembled image differs"
