@@ -91,7 +91,13 @@ def algorithmic_bytes(stage, args, sc, counters):
     if stage == "inject":        # listed bricks: read 8 B, write 4 B linear + 4 B array
         return (8 + 8) * 512 * counters["bricks"]
     if stage == "mips":
-        return mip_chain_bytes(N)
+        if counters.get("dense_mips"):
+            return mip_chain_bytes(N)
+        # sparse path: per listed brick read 2 KB of level 0, write levels 1-3 (6 x (64 + 8 + 1) texels) twice (linear chain +
+        # texture array); then the dense tail: read level 3 once, write levels >= 4 twice
+        n3 = N // 8
+        tail = 6 * 4 * n3 ** 3 + 2 * 6 * 4 * sum((n3 >> l) ** 3 for l in range(1, n3.bit_length()))
+        return counters["bricks"] * (2048 + 2 * 6 * 73 * 4) + tail
     if stage == "trace":         # per-pixel fixed I/O (depth 4, normal 8, material 4, history 8, out 8) + one pass over the volume chain
         return 32 * P + 4 * N ** 3 + 4 * 6 * sum((N >> l) ** 3 for l in range(1, N.bit_length()))
     return 0
