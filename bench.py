@@ -59,11 +59,17 @@ def parse():
 # ------------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------------
-def make_workload(args):
+def make_workload(args, rank=0, world=1):
     from final184_b200 import scene as S
     from final184_b200.fixture import frame_inputs
     sc = S.get_scene(prefer_sponza=True, seed=1, n_boxes=48, tex_size=256, subdiv=8)
     cams = {n: S.fixture_constants(n) for n in ("main", "shadow", "voxel")}
+    if world > 1:
+        # the G-buffer / shadow-map synthesiser is a CPU rasteriser: rank 0 renders (all cores) into the on-disk cache, the rest load it
+        import torch.distributed as dist
+        if rank == 0:
+            frame_inputs(sc, cams["main"], cams["shadow"], args.width, args.height, args.shadow, 0)
+        dist.barrier()
     fi = frame_inputs(sc, cams["main"], cams["shadow"], args.width, args.height, args.shadow, 0)
     name = ("Sponza" if sc.name == "sponza" else sc.name) + f" {args.grid}^3 voxel GI (voxelize+normalise+inject+6-dir mips+" \
         f"6 diffuse/1 specular cones) at {args.width}x{args.height}, north-star mode"
@@ -237,7 +243,7 @@ def run_reference(args, rank, world):
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": cpu.describe()},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "stages_ms": {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}, "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -252,7 +258,7 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sc, cams, fi, wname = make_workload(args)
+    sc, cams, fi, wname = make_workload(args, rank, world)
     W, H, N = args.width, args.height, args.grid
     peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else None
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if peaks else (6650.0, "fallback (B200_PROFILING.md)")
@@ -386,13 +392,23 @@ def run_b200(args, rank, world, local_rank):
                 est.append(e); wall.append(w)
             out["cpu_baseline"] = {"value": float(np.mean(est)), "unit": UNIT, "cores": cpu.cores, "kind": "port",
                                    "sample": cpu.describe() + f"; {len(est)} samples, {np.mean(wall) / 1e3:.1f} s each"}
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     g.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner lands on
+    stdout) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -403,6 +419,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

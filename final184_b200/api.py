@@ -150,6 +150,7 @@ _SIGS = {
     "bind_rands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "set_triangle_range": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "set_trace_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "set_trace_tiles": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "stage_time_ms": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]),
     "counter_get": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
 }
@@ -350,6 +351,9 @@ class VoxelGI:
 
     def set_trace_rows(self, y0, y1):
         self._ck(self.lib.set_trace_rows(self.h, y0, y1), "set_trace_rows")
+
+    def set_trace_tiles(self, first, stride):
+        self._ck(self.lib.set_trace_tiles(self.h, first, stride), "set_trace_tiles")
 
     # -- measurement
     def stage_ms(self, stage) -> float:

@@ -595,6 +595,13 @@ int f184_set_trace_rows(f184_ctx* c, uint32_t y0, uint32_t y1)
     return F184_OK;
 }
 
+int f184_set_trace_tiles(f184_ctx* c, uint32_t first, uint32_t stride)
+{
+    if (!c || stride == 0 || first >= stride) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "set_trace_tiles: need first < stride");
+    c->tile_first = first; c->tile_stride = stride;
+    return F184_OK;
+}
+
 int f184_stage_time_ms(f184_ctx* c, uint32_t stage, float* ms)
 {
     if (!c || stage >= F184_STAGE_COUNT || !ms) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "stage_time_ms: bad argument");

@@ -95,6 +95,7 @@ struct f184_ctx
     // sharding
     uint32_t tri_first = 0, tri_count = 0xffffffffu;
     uint32_t row0 = 0, row1 = 0xffffffffu;
+    uint32_t tile_first = 0, tile_stride = 1;
     const float* rands = nullptr;
     size_t n_rands = 0;
     // measurement
@@ -169,3 +170,15 @@ int f184_gather_n(f184_ctx* c);
 int f184_ipc_buffer_ptr(f184_ctx* c, uint32_t buffer, void** out);
 M4 f184_invert_m4(const M4& A);
 float f184_exposure(const f184_ctx* c, const f184_sun* sun);
+// rows/tiles selection of the trace passes: y = y0 + (tile0 + blockIdx.y * stride) * 8 + ...; returns grid.y (0 = nothing to do)
+static inline uint32_t f184_trace_tiles(const f184_ctx* c, uint32_t H, uint32_t* y0, uint32_t* y1, uint32_t* tile0, uint32_t* stride)
+{
+    *y0 = c->row0 < H ? c->row0 : H;
+    *y1 = c->row1 < H ? c->row1 : H;
+    *stride = c->tile_stride ? c->tile_stride : 1;
+    if (*y1 <= *y0) return 0;
+    const uint32_t tiles = (*y1 - *y0 + 7) / 8, base = *y0 / 8;
+    *tile0 = (c->tile_first % *stride + *stride - base % *stride) % *stride;
+    if (*tile0 >= tiles) return 0;
+    return (tiles - *tile0 + *stride - 1) / *stride;
+}

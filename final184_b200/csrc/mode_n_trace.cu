@@ -35,7 +35,7 @@ struct ConeParams
     uint16_t* out;
     float h, max_dist, exposure, max_lod;
     f3 cam;
-    uint32_t W, H, y0, y1;
+    uint32_t W, H, y0, y1, tile0, tile_stride;
 };
 
 __constant__ float kDiffuseDirs[6][3] = {
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) k_trace_n(const ConeParams P, unsigned lo
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const uint32_t y = P.y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t y = P.y0 + (P.tile0 + blockIdx.y * P.tile_stride) * 8 + (warp >> 1) * 4 + (lane >> 3);
     unsigned int samples = 0;
     if (x < P.W && y < P.y1)
     {
@@ -224,16 +224,16 @@ int f184_trace_n(f184_ctx* c, const f184_trace_constants* k)
     P.max_lod = (float)(c->n_mip_levels - 1);
     P.cam = {P.InvModelView.m[12], P.InvModelView.m[13], P.InvModelView.m[14]};
     P.W = c->cfg.width; P.H = c->cfg.height;
-    P.y0 = c->row0 < P.H ? c->row0 : P.H;
-    P.y1 = c->row1 < P.H ? c->row1 : P.H;
+    const uint32_t grid_y = f184_trace_tiles(c, P.H, &P.y0, &P.y1, &P.tile0, &P.tile_stride);
+    if (P.tile_stride > 1 && (P.y0 & 7)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "trace: row range must start on a multiple of 8 when tiles are interleaved");
     int rc = f184_stage_begin(c, F184_STAGE_TRACE);
     if (rc) return rc;
     if (k->reset_history)
         CK(c, cudaMemsetAsync(c->img[F184_SLOT_INDIRECT_HISTORY].ptr, 0, c->img[F184_SLOT_INDIRECT_HISTORY].desc.size_bytes, c->stream));
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_MARCH_STEPS, 0, 8, c->stream));
-    if (P.y1 > P.y0)
+    if (grid_y)
     {
-        dim3 grid((P.W + 15) / 16, (P.y1 - P.y0 + 7) / 8);
+        dim3 grid((P.W + 15) / 16, grid_y);
         k_trace_n<<<grid, 128, 0, c->stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
         CK_LAUNCH(c);
     }

@@ -111,12 +111,13 @@ struct VoxArgs
     const MatDev* mats;
     uint32_t tri_first, tri_end;
     int N;
-    // accumulators / brick flags of the rank that owns Z-slab (z >> slab_shift): own memory, or a peer's memory mapped
-    // over NVLink (then the atomics below ARE the reduce-scatter of the partial volumes); one GPU: slab_shift = 31
+    // accumulators / brick flags of the rank that owns the voxel's brick layer, owner = (z / 8) % nranks (layers are
+    // interleaved so every rank gets an even share of the occupied bricks): own memory, or a peer's memory mapped over
+    // NVLink — then the atomics below ARE the reduce-scatter of the partial volumes.  One GPU: owner_mask = 0.
     float4* accC[8];
     float4* accN[8];
     uint32_t* brick_flags[8];
-    int slab_shift;
+    uint32_t owner_mask;
     unsigned long long* frag_counter;
     unsigned long long* queue_state;   // (entries << 40) | tasks, one 64-bit word so both advance together
     uint2* queue;                      // per large triangle: (triangle, first task)
@@ -316,7 +317,7 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
         const int by = s.d == 0 ? iu : (s.d == 1 ? kd : iv);
         const int bz = s.d == 0 ? iv : (s.d == 1 ? iu : kd);
         const size_t o = brick_major(bx, by, bz, A.N >> 3);
-        const int owner = bz >> A.slab_shift;
+        const uint32_t owner = ((uint32_t)bz >> 3) & A.owner_mask;
         atomicAdd(A.accC[owner] + o, make_float4(r8, g8, b8, 1.0f));     // red.global.add.v4.f32 (peer memory when owner != this rank)
         atomicAdd(A.accN[owner] + o, make_float4(nx8, ny8, nz8, 0.0f));
         A.brick_flags[owner][o >> 9] = 1u;
@@ -425,12 +426,13 @@ __global__ void k_view_model_n(M4 View, const M4* __restrict__ model, M4* __rest
 // pass 1: one thread per brick flag -> compact list (warp-aggregated append).  Entry = brick | touched << 31.
 __global__ void __launch_bounds__(256)
 k_brick_compact(uint32_t* __restrict__ brick_flags, uint32_t* __restrict__ brick_prev, uint32_t* __restrict__ brick_list,
-                unsigned long long* __restrict__ counters, uint32_t b0, uint32_t b1)
+                unsigned long long* __restrict__ counters, uint32_t n_own, uint32_t NB2, uint32_t G, uint32_t rank)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t bi = b0 + blockIdx.x * blockDim.x + threadIdx.x;       // [b0, b1): the bricks of this rank's Z-slab
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;             // j-th brick of this rank: layers rank, rank + G, ...
+    const uint32_t bi = ((j / NB2) * G + rank) * NB2 + j % NB2;
     uint32_t flag = 0, prev = 0;
-    if (bi < b1) { flag = brick_flags[bi]; prev = brick_prev[bi]; }
+    if (j < n_own) { flag = brick_flags[bi]; prev = brick_prev[bi]; }
     if (flag | prev) { brick_flags[bi] = 0; brick_prev[bi] = flag; }
     const unsigned int todo = __ballot_sync(0xffffffffu, (flag | prev) != 0);
     const unsigned int touched = __ballot_sync(0xffffffffu, flag != 0);
@@ -503,14 +505,6 @@ k_normalise_n(float4* __restrict__ accC, float4* __restrict__ accN, uchar4* __re
 
 }  // namespace
 
-static int slab_shift_of(const f184_ctx* c)
-{
-    if (c->cfg.nranks <= 1) return 31;
-    int sh = 0;
-    while ((1u << sh) < c->cfg.grid_n / c->cfg.nranks) sh++;
-    return sh;
-}
-
 int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
 {
     for (int s : {F184_SLOT_ACCUM_COLOR, F184_SLOT_ACCUM_NORMAL, F184_SLOT_VOX_ALBEDO, F184_SLOT_VOX_NORMAL, F184_SLOT_BRICK_FLAGS})
@@ -520,7 +514,7 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
     }
     const int N = (int)c->cfg.grid_n;
     const uint32_t G = c->cfg.nranks;
-    if (G > 1 && ((G & (G - 1)) || G > 8 || N / (int)G < 8)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "nranks must be 1, 2, 4 or 8 with slabs of >= 8 voxels");
+    if (G > 1 && ((G & (G - 1)) || G > 8 || N / 8 < (int)G)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "nranks must be 1, 2, 4 or 8 and at most grid_n / 8");
     {
         void* dummy = nullptr;
         int rc = f184_ipc_buffer_ptr(c, F184_IPC_BRICK_LIST, &dummy);      // brick_prev / brick_list
@@ -555,7 +549,7 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
             A.brick_flags[p] = reinterpret_cast<uint32_t*>(c->peer[p].buf[F184_IPC_BRICK_FLAGS]);
         }
     }
-    A.slab_shift = slab_shift_of(c);
+    A.owner_mask = G > 1 ? G - 1 : 0;
     M4 View;
     memcpy(View.m, cam->ViewMat, 64);
     k_view_model_n<<<(c->n_models * 16 + 127) / 128, 128, 0, c->stream>>>(View, c->model_mats, c->vm_dev, c->n_models);
@@ -597,18 +591,18 @@ int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
     return f184_normalise_n(c);
 }
 
-// Normalise this rank's Z-slab (the whole volume on one GPU).
+// Normalise this rank's brick layers (the whole volume on one GPU).
 int f184_normalise_n(f184_ctx* c)
 {
     const int N = (int)c->cfg.grid_n;
     const uint32_t NB = (uint32_t)N / 8, G = c->cfg.nranks > 1 ? c->cfg.nranks : 1;
-    const uint32_t b0 = (c->cfg.rank % G) * (NB / G) * NB * NB, b1 = b0 + (NB / G) * NB * NB;
+    const uint32_t n_own = (NB / G) * NB * NB;
     int rc = f184_stage_begin(c, F184_STAGE_NORMALISE);
     if (rc) return rc;
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_OCCUPIED, 0, 8, c->stream));
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_BRICKS, 0, 16, c->stream));        // BRICKS + the list cursor
-    k_brick_compact<<<(b1 - b0 + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,
-                                                                c->counters_dev, b0, b1);
+    k_brick_compact<<<(n_own + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,
+                                                              c->counters_dev, n_own, NB * NB, G, c->cfg.rank % G);
     CK_LAUNCH(c);
     k_normalise_n<<<148 * 8, 256, 0, c->stream>>>(img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
                                                   img_ptr<uchar4>(c, F184_SLOT_VOX_ALBEDO), img_ptr<char4>(c, F184_SLOT_VOX_NORMAL),

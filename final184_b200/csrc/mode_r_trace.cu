@@ -27,7 +27,7 @@ struct TraceParams
     const uint16_t* hist;
     uint16_t* out;
     const float* rands;
-    uint32_t W, H, S, N, steps, y0, y1;
+    uint32_t W, H, S, N, steps, y0, y1, tile0, tile_stride;
     float step_size, iiTime, resx, resy;
     f3 sunLum, sunPos;
 };
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128) k_trace_r(const TraceParams P, unsigned l
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const uint32_t y = P.y0 + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t y = P.y0 + (P.tile0 + blockIdx.y * P.tile_stride) * 8 + (warp >> 1) * 4 + (lane >> 3);
     unsigned int steps_taken = 0;
     if (x < P.W && y < P.y1)
     {
@@ -256,8 +256,8 @@ int f184_trace_r(f184_ctx* c, const f184_trace_constants* k)
     P.out = img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_OUT);
     P.rands = (c->cfg.flags & F184_FLAG_EXTERNAL_RANDS) ? c->rands : nullptr;
     P.W = c->cfg.width; P.H = c->cfg.height; P.S = c->cfg.shadow_res; P.N = c->cfg.grid_n; P.steps = c->cfg.march_steps;
-    P.y0 = c->row0 < P.H ? c->row0 : P.H;
-    P.y1 = c->row1 < P.H ? c->row1 : P.H;
+    const uint32_t grid_y = f184_trace_tiles(c, P.H, &P.y0, &P.y1, &P.tile0, &P.tile_stride);
+    if (P.tile_stride > 1 && (P.y0 & 7)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "trace: row range must start on a multiple of 8 when tiles are interleaved");
     P.step_size = c->cfg.step_size;
     P.iiTime = (float)k->miscs.frameCount * 0.03125f;                 // indirect.frag:111
     P.resx = k->miscs.resolution[0]; P.resy = k->miscs.resolution[1];
@@ -269,9 +269,9 @@ int f184_trace_r(f184_ctx* c, const f184_trace_constants* k)
     if (k->reset_history)     // first frame: history cleared (MegaPipeline.cpp:197-204)
         CK(c, cudaMemsetAsync(c->img[F184_SLOT_INDIRECT_HISTORY].ptr, 0, c->img[F184_SLOT_INDIRECT_HISTORY].desc.size_bytes, c->stream));
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_MARCH_STEPS, 0, 8, c->stream));
-    if (P.y1 > P.y0)
+    if (grid_y)
     {
-        dim3 grid((P.W + 15) / 16, (P.y1 - P.y0 + 7) / 8);
+        dim3 grid((P.W + 15) / 16, grid_y);
         k_trace_r<<<grid, 128, 0, c->stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
         CK_LAUNCH(c);
     }

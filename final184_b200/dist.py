@@ -11,11 +11,9 @@ Partitioning helpers
   row_ranges(H, n, tile)        screen bands, multiples of the tracer's 8-row tile
   view_ranges(n_views, n)       whole views per rank (probe batches)
 
-Frame schedules (ShardedVoxelGI.mode)
-  "replicate"  every rank voxelizes / injects / builds the whole volume (no data-path collective at all) and
-               traces its own band of rows; the image bands are disjoint, a consumer gathers them only if it wants
-               one image on one rank.  This is the schedule that wins while voxelize+mips are a small part of the
-               frame, because it has no exchange step to pay for.
+  brick_layer_owner(z, n)       owner of voxel layer z when the 8-voxel brick layers are dealt round-robin
+
+Frame schedules: see ShardedVoxelGI.
 """
 from __future__ import annotations
 
@@ -65,8 +63,14 @@ def triangle_weights(sc: S.Scene, voxel_cam: S.ViewConstants, grid_n: int, setup
 
 
 def slab_ranges(n: int, nranks: int):
-    """Z-slab of each rank at a level of edge n (empty slabs once n < nranks)."""
+    """Contiguous Z-slab of each rank at a level of edge n (empty slabs once n < nranks)."""
     return [(r * n // nranks, (r + 1) * n // nranks) for r in range(nranks)]
+
+
+def brick_layer_owner(z: int, nranks: int) -> int:
+    """Rank that owns voxel layer z: 8-voxel brick layers are dealt round-robin, owner = (z // 8) % nranks.  (Contiguous
+    slabs left the ranks holding Sponza's floor and arcades with 40 % of the bricks and the top slab with none.)"""
+    return (z // 8) % nranks
 
 
 def row_ranges(height: int, nranks: int, tile: int = 8):
@@ -85,8 +89,9 @@ class ShardedVoxelGI:
 
     mode "single"     one GPU.
          "slab"       the north-star schedule (include/f184.h "one NVLink box"): triangle-range voxelization with the
-                      reduce-scatter fused into the voxelizer as peer atomics, Z-slab owners normalise / inject / build
-                      levels 1-3, a peer gather of the finished bricks, row-band tracing.  Needs connect().
+                      reduce-scatter fused into the voxelizer as peer atomics, the owners of the (interleaved) Z brick
+                      layers normalise / inject / build levels 1-3, a peer gather of the finished bricks, tracing of
+                      interleaved 8-row screen tiles.  Needs connect().
          "replicate"  no exchange at all: every rank builds the whole volume, only the trace is split.
          "host"       the slab schedule's HOST logic with the exchange done by torch.distributed on host arrays
                       (all_reduce of the partial accumulators): what the CPU tests drive with the gloo backend and the
@@ -103,8 +108,9 @@ class ShardedVoxelGI:
         ctx_ranks = (rank, nranks) if self.mode == "slab" else (0, 1)       # only the slab schedule shards the volume
         self.ctx = A.VoxelGI(grid_n, width, height, A.MODE_NORTHSTAR, shadow_res=shadow_res, device=device, rank=ctx_ranks[0], nranks=ctx_ranks[1],
                              lib=lib, flags=flags)
-        self.rows = row_ranges(height, nranks)[rank]
-        self.ctx.set_trace_rows(*self.rows)
+        self.rows = (0, height)
+        self.tiles = (rank, nranks)              # this rank traces the 8-row tile rows t with t % nranks == rank
+        self.ctx.set_trace_tiles(*self.tiles)
         self.tri_range = None
         self.connected = False
         if scene is not None:
@@ -137,9 +143,9 @@ class ShardedVoxelGI:
         if self.mode == "single":
             return "1 GPU"
         if self.mode == "replicate":
-            return f"{self.nranks} GPUs: volume replicated per rank (no exchange), trace split into {self.nranks} row bands"
+            return f"{self.nranks} GPUs: volume replicated per rank (no exchange), trace split by interleaved 8-row tiles"
         return (f"{self.nranks} GPUs: triangle ranges balanced by projected area, fragments reduced into the Z-slab owner's accumulators by peer "
-                f"atomics over NVLink, slab-local normalise/inject/mips, peer gather of the listed bricks, trace split into {self.nranks} row bands")
+                f"atomics over NVLink, slab-local normalise/inject/mips, peer gather of the listed bricks, trace split by interleaved 8-row tiles")
 
     def frame(self, voxel_cam, k):
         c = self.ctx
@@ -177,12 +183,16 @@ class ShardedVoxelGI:
             return img
         import torch
         import torch.distributed as dist
-        bands = [None] * self.nranks
-        dist.all_gather_object(bands, (self.rows, img[self.rows[0]:self.rows[1]].copy()))
+        parts = [None] * self.nranks
+        dist.all_gather_object(parts, (self.tiles, img[self.own_rows_mask()].copy()))
         out = np.zeros_like(img)
-        for (y0, y1), band in bands:
-            out[y0:y1] = band
+        for (first, stride), rows in parts:
+            out[(np.arange(self.height) // 8) % stride == first] = rows
         return out
+
+    def own_rows_mask(self):
+        first, stride = self.tiles
+        return (np.arange(self.height) // 8) % stride == first
 
     def comm_ms_per_frame(self):
         return 0.0

@@ -23,6 +23,8 @@ class Fixture:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} not built (run __graft_entry__.build())")
         self.dll = C.CDLL(LIB_PATH)
+        if hasattr(self.dll, "f184fx_set_threads"):
+            self.dll.f184fx_set_threads(C.c_int(os.cpu_count() or 1))
         self.h = C.c_void_p()
         self.dll.f184fx_create(C.byref(self.h))
         self.scene = sc

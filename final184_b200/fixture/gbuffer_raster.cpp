@@ -208,7 +208,12 @@ static void raster_band(const f184fx_ctx* c, const M4& View, const M4& Proj, flo
     }
 }
 
+#include <omp.h>
 extern "C" {
+
+// torchrun exports OMP_NUM_THREADS=1 to every rank; the caller says how many threads the synthesiser may use
+void f184fx_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
 
 int f184fx_create(f184fx_ctx** out) { *out = new f184fx_ctx(); return 0; }
 void f184fx_destroy(f184fx_ctx* c) { delete c; }

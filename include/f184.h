@@ -273,6 +273,10 @@ int f184_bind_rands(f184_ctx* ctx, const float* device_rands, size_t count);
  * [z0, z1) of every volume level and traces rows [y0, y1).  Defaults are derived from rank/nranks. */
 int f184_set_triangle_range(f184_ctx* ctx, uint32_t first, uint32_t count);
 int f184_set_trace_rows(f184_ctx* ctx, uint32_t y0, uint32_t y1);
+/* Of the rows selected above, trace only the 8-row tile rows t with t % stride == first (t counted from the top of the
+ * image; y0 must be a multiple of 8 when stride > 1).  Interleaving tile rows over the ranks balances the trace where
+ * contiguous bands do not (sky at the top, floor at the bottom).  Default: first 0, stride 1. */
+int f184_set_trace_tiles(f184_ctx* ctx, uint32_t first, uint32_t stride);
 
 /* ---- one NVLink box, one process per GPU (DESIGN.md "Multi-GPU").  The reference is single-GPU
  * (RHI/Private/Vulkan/DeviceVk.cpp:301-304); this is the north-star schedule:

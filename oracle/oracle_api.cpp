@@ -225,6 +225,12 @@ int f184o_frame_end(f184o_ctx*) { return F184_OK; }
 int f184o_bind_rands(f184o_ctx* c, const float* r, size_t n) { c->rands = r; c->n_rands = n; return F184_OK; }
 int f184o_set_triangle_range(f184o_ctx* c, uint32_t first, uint32_t count) { c->tri_first = first; c->tri_count = count; return F184_OK; }
 int f184o_set_trace_rows(f184o_ctx* c, uint32_t y0, uint32_t y1) { c->row0 = y0; c->row1 = y1; return F184_OK; }
+int f184o_set_trace_tiles(f184o_ctx* c, uint32_t first, uint32_t stride)
+{
+    if (!c || stride == 0 || first >= stride) return F184_ERR_INVALID_ARGUMENT;
+    c->tile_first = first; c->tile_stride = stride;
+    return F184_OK;
+}
 int f184o_stage_time_ms(f184o_ctx* c, uint32_t stage, float* ms)
 {
     if (!c || stage >= F184_STAGE_COUNT || !ms) return F184_ERR_INVALID_ARGUMENT;

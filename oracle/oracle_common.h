@@ -125,6 +125,7 @@ struct f184o_ctx
     std::vector<std::vector<std::vector<uint8_t>>> mips;
     uint32_t tri_first = 0, tri_count = 0xffffffffu;
     uint32_t row0 = 0, row1 = 0xffffffffu;
+    uint32_t tile_first = 0, tile_stride = 1;   // of those rows, only 8-row tile rows t with t % stride == first
     const float* rands = nullptr;
     size_t n_rands = 0;
     uint64_t counters[F184_COUNTER_COUNT] = {0};

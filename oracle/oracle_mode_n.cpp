@@ -607,6 +607,7 @@ extern "C" int orc_trace_n(f184o_ctx* c, const f184_trace_constants* k)
 #pragma omp parallel for schedule(dynamic, 2) reduction(+ : total)
     for (int64_t y = y0; y < (int64_t)y1; y++)
     {
+        if ((uint32_t)(y >> 3) % c->tile_stride != c->tile_first) continue;      // tile rows interleaved over the ranks
         ConeCtx C = C0;
         C.samples = 0;
         for (uint32_t x = 0; x < W; x++)

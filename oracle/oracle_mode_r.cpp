@@ -416,6 +416,7 @@ extern "C" int orc_trace_r(f184o_ctx* c, const f184_trace_constants* k)
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : total_steps)
     for (int64_t y = y0; y < (int64_t)y1; y++)
     {
+        if ((uint32_t)(y >> 3) % c->tile_stride != c->tile_first) continue;      // tile rows interleaved over the ranks
         TraceCtx T = T0;
         T.march_steps = 0;
         for (uint32_t x = 0; x < W; x++)

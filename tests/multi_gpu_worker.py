@@ -48,9 +48,9 @@ def main():
             for d in range(6):
                 if not np.array_equal(g.ctx.read_array(d, lvl, m), one.read_array(d, lvl, m)): bad.append(f"frame {frame}: array dir {d} level {lvl + 1}")
             m //= 2; lvl += 1
-        y0, y1 = g.rows
-        a, b = g.ctx.readback(A.SLOT_INDIRECT_OUT)[y0:y1], one.readback(A.SLOT_INDIRECT_OUT)[y0:y1]
-        if not np.array_equal(a.view(np.uint16), b.view(np.uint16)): bad.append(f"frame {frame}: image rows {y0}:{y1}")
+        m = g.own_rows_mask()
+        a, b = g.ctx.readback(A.SLOT_INDIRECT_OUT)[m], one.readback(A.SLOT_INDIRECT_OUT)[m]
+        if not np.array_equal(a.view(np.uint16), b.view(np.uint16)): bad.append(f"frame {frame}: own image tile rows")
         dist.barrier()
     frags = torch.tensor([float(g.ctx.counter(A.COUNTER_FRAGMENTS))], device=f"cuda:{local}")
     dist.all_reduce(frags)

@@ -41,6 +41,7 @@ def test_slab_row_view_ranges():
         assert rr[0][0] == 0 and rr[-1][1] == h and all(rr[i][1] == rr[i + 1][0] for i in range(n - 1))
         assert all(y0 % 8 == 0 for y0, _ in rr)
     assert D.view_ranges(64, 8) == [(8 * r, 8 * r + 8) for r in range(8)]
+    assert [D.brick_layer_owner(z, 4) for z in (0, 7, 8, 31, 32, 511)] == [0, 0, 1, 3, 0, 3]
 
 
 def test_triangle_weights_track_projected_area(proc_scene, cams):
@@ -69,7 +70,7 @@ def _worker(rank, world, port, out_dir):
         k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
         g.frame(cams["voxel"], k)
         img = g.gather_image()
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), img=img, rad=g.ctx.readback(A.SLOT_RADIANCE), tri=np.array(g.tri_range), rows=np.array(g.rows),
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), img=img, rad=g.ctx.readback(A.SLOT_RADIANCE), tri=np.array(g.tri_range), rows=g.own_rows_mask(),
                  frags=g.ctx.counter(A.COUNTER_FRAGMENTS))
     finally:
         dist.destroy_process_group()
@@ -90,7 +91,7 @@ def test_sharded_frame_world2_gloo_equals_single_process(tmp_path, oracle_lib, p
     want = o.readback(A.SLOT_INDIRECT_OUT)
     # the triangle ranges partition the scene, the row bands partition the screen
     assert r[0]["tri"][0] == 0 and r[0]["tri"].sum() == r[1]["tri"][0] and r[1]["tri"].sum() == proc_scene.n_tris
-    assert r[0]["rows"][1] == r[1]["rows"][0] and r[1]["rows"][1] == H
+    assert (r[0]["rows"] ^ r[1]["rows"]).all()                 # interleaved 8-row tiles: every row traced by exactly one rank
     assert int(r[0]["frags"]) + int(r[1]["frags"]) == o.counter(A.COUNTER_FRAGMENTS)
     for i in range(world):
         assert np.array_equal(r[i]["rad"], o.readback(A.SLOT_RADIANCE)), f"rank {i}: summed partial volumes differ from the whole"

@@ -224,3 +224,11 @@ def test_trace_bands_compose(oracle_lib, proc_scene, cams):
         o.set_trace_rows(y0, y1); o.trace_indirect(k)
         out[y0:y1] = o.readback(A.SLOT_INDIRECT_OUT)[y0:y1]
     assert np.array_equal(out.view(np.uint16), full.view(np.uint16))
+    # interleaved 8-row tiles (the multi-GPU trace split) compose as well
+    o.set_trace_rows(0, 0xffffffff)
+    out = np.zeros_like(full)
+    for first in range(3):
+        o.set_trace_tiles(first, 3); o.trace_indirect(k)
+        m = (np.arange(H) // 8) % 3 == first
+        out[m] = o.readback(A.SLOT_INDIRECT_OUT)[m]
+    assert np.array_equal(out.view(np.uint16), full.view(np.uint16))
