@@ -164,6 +164,7 @@ _PRODUCT_ONLY = {
     "gather_volume": (C.c_int, [C.c_void_p]),
     "stage_time_reset": (C.c_int, [C.c_void_p, C.c_uint32]),
     "stage_time_total": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "microbench": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_double)]),
     "debug_read_array": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "debug_detmath": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
 }
@@ -369,6 +370,12 @@ class VoxelGI:
         v, n = C.c_float(), C.c_uint32()
         self._ck(self.lib.stage_time_total(self.h, stage, C.byref(v), C.byref(n)), "stage_time_total")
         return v.value, n.value
+
+    def microbench(self, which) -> float:
+        """0: trilinear RGBA8 3D fetches / s; 1: scattered 16-byte vector reductions / s."""
+        v = C.c_double()
+        self._ck(self.lib.microbench(self.h, which, C.byref(v)), "microbench")
+        return v.value
 
     def counter(self, which) -> int:
         v = C.c_uint64()

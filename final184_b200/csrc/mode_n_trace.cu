@@ -93,7 +93,7 @@ __device__ f3 trace_cone(const ConeParams& P, f3 origin, f3 dir, float tan_half,
         const float k = 1.0f - A;
         acc = {acc.x + k * s.x, acc.y + k * s.y, acc.z + k * s.z};
         A += k * s.w;
-        t += 0.5f * diam;
+        t += diam;                   // one sample per voxel of the level along the axis
     }
     const float rem = fmaxf(0.0f, 1.0f - A);
     return {acc.x * P.exposure + 0.7f * 0.4f * rem, acc.y * P.exposure + 0.8f * 0.4f * rem, acc.z * P.exposure + 1.0f * 0.4f * rem};

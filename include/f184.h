@@ -321,6 +321,11 @@ int f184_stage_time_total(f184_ctx* ctx, uint32_t stage, float* out_ms_sum, uint
  * 5 pow(x,y), 6 f32->f16->f32); host pointers; synchronous */
 int f184_debug_detmath(f184_ctx* ctx, uint32_t op, const float* x, const float* y, float* out, size_t n);
 
+/* ---- measurement aid: device peaks MEASURED_PEAKS.json does not hold.  which = 0: trilinear RGBA8 3D texture fetches / s
+ * (bound of the cone tracer); which = 1: scattered 16-byte red.global.add.v4.f32 / s over 1 GiB (the voxelizer's
+ * accumulation path).  Synchronous; allocates and frees its own scratch. */
+int f184_microbench(f184_ctx* ctx, uint32_t which, double* out_per_second);
+
 /* ---- test hook: one level of the texture-side storage the cone tracer samples (dir < 0: the level-0 radiance
  * 3D array; dir 0..5: level `level`+1 of that direction's mipmapped 3D array); host pointer; synchronous */
 int f184_debug_read_array(f184_ctx* ctx, int32_t dir, uint32_t level, void* host, size_t bytes);
