@@ -322,16 +322,19 @@ def run_b200(args, rank, world, local_rank):
         g.ctx.stage_time_reset(False)
         counters = {"fragments": g.ctx.counter(A.COUNTER_FRAGMENTS), "bricks": g.ctx.counter(A.COUNTER_BRICKS),
                     "occupied": g.ctx.counter(A.COUNTER_OCCUPIED), "cone_samples": g.ctx.counter(A.COUNTER_MARCH_STEPS)}
-        # ---- timed region: end to end with host buffers
+        # ---- timed region: end to end with host buffers.  Every step uploads one frame's inputs from pinned host memory and
+        # reads one traced image back.  f184_upload_image double-buffers its slots on a copy stream, so the caller
+        # streams: the inputs of frame f+1 are submitted right after frame f's kernels and travel while they run.
+        upload_inputs()
         for _ in range(2):
-            upload_inputs(); frame(); g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_host.data_ptr(), d2h); g.ctx.sync()
+            frame(); upload_inputs(); g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_host.data_ptr(), d2h); g.ctx.sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t_wall0 = time.perf_counter()
         e0.record(stream)
         for _ in range(args.steps):
-            upload_inputs()
-            frame()
+            frame()                            # consumes the inputs uploaded one iteration ago
+            upload_inputs()                    # next frame's inputs (H2D, copy stream)
             g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_host.data_ptr(), d2h)
             g.ctx.sync()                       # the caller consumes the image every frame
         e1.record(stream)

@@ -81,12 +81,18 @@ static bool default_desc(const f184_config& c, int slot, f184_image_desc* d)
 int f184_ensure_image(f184_ctx* c, int slot)
 {
     DevImage& im = c->img[slot];
+    if (im.upload_pending)
+    {   // a pass (or a read-back) is about to touch the slot: order it after the upload that is in flight on the copy stream
+        CK(c, cudaStreamWaitEvent(c->stream, im.ev_up[im.cur], 0));
+        im.upload_pending = false;
+    }
     if (im.ptr) return F184_OK;
     f184_image_desc d;
     if (!default_desc(c->cfg, slot, &d)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "bad slot %d", slot);
     CK(c, cudaMalloc(&im.ptr, d.size_bytes));
     CK(c, cudaMemsetAsync(im.ptr, 0, d.size_bytes, c->stream));
     im.owned = true;
+    im.buf[0] = im.ptr; im.cur = 0;
     im.desc = d;
     im.desc.device_ptr = im.ptr;
     return F184_OK;
@@ -189,6 +195,11 @@ int f184_create(const f184_config* config, f184_ctx** out)
         return f184_fail(nullptr, F184_ERR_CUDA, "cudaStreamCreate failed");
     }
     c->stream = c->own_stream;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        delete c;
+        return f184_fail(nullptr, F184_ERR_CUDA, "cudaStreamCreate failed");
+    }
     for (int s = 0; s < F184_STAGE_COUNT; s++)
     {
         cudaEvent_t a, b;
@@ -211,10 +222,20 @@ void f184_destroy(f184_ctx* c)
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     f184_mode_n_release(c);
     for (auto& im : c->img)
     {
-        if (im.owned && im.ptr) cudaFree(im.ptr);
+        if (im.owned)
+        {
+            for (int i = 0; i < 2; i++)
+            {
+                if (im.buf[i]) cudaFree(im.buf[i]);
+                if (im.ev_up[i]) cudaEventDestroy(im.ev_up[i]);
+                if (im.ev_release[i]) cudaEventDestroy(im.ev_release[i]);
+            }
+            im.ptr = nullptr;
+        }
         if (im.ext) { if (im.ptr) cudaFree(im.ptr); cudaDestroyExternalMemory(im.ext); }
     }
     for (void* p : {(void*)c->pos, (void*)c->nrm, (void*)c->uv, (void*)c->model_mats, (void*)c->idx, (void*)c->tri_mat,
@@ -232,6 +253,7 @@ void f184_destroy(f184_ctx* c)
     if (c->sem_wait) cudaDestroyExternalSemaphore(c->sem_wait);
     if (c->sem_signal) cudaDestroyExternalSemaphore(c->sem_signal);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -346,7 +368,12 @@ int f184_bind_image(f184_ctx* c, uint32_t slot, const f184_image_desc* d)
         return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "bind_image: slot %u expects format %u %ux%ux%u", slot, want.format, want.width, want.height, want.depth);
     if (d->row_pitch_bytes != 0 && d->row_pitch_bytes != want.row_pitch_bytes)
         return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "bind_image: only tightly packed rows are supported");
-    if (im.owned && im.ptr) { cudaStreamSynchronize(c->stream); cudaFree(im.ptr); }
+    if (im.owned && im.ptr)
+    {
+        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
+        for (int i = 0; i < 2; i++) { if (im.buf[i]) cudaFree(im.buf[i]); im.buf[i] = nullptr; }
+        im.upload_pending = false;
+    }
     im.ptr = d->device_ptr;
     im.owned = false;
     im.desc = want;
@@ -368,8 +395,33 @@ int f184_upload_image(f184_ctx* c, uint32_t slot, const void* host, size_t bytes
     if (!c || slot >= F184_SLOT_COUNT || !host) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "upload_image: bad argument");
     int rc = f184_ensure_image(c, slot);
     if (rc) return rc;
-    if (bytes != c->img[slot].desc.size_bytes) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "upload_image: slot %u is %llu bytes, got %zu", slot, (unsigned long long)c->img[slot].desc.size_bytes, bytes);
-    CK(c, cudaMemcpyAsync(c->img[slot].ptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    DevImage& im = c->img[slot];
+    if (bytes != im.desc.size_bytes) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "upload_image: slot %u is %llu bytes, got %zu", slot, (unsigned long long)im.desc.size_bytes, bytes);
+    if (!im.owned || im.ext)
+    {   // caller-owned memory: plain stream-ordered copy
+        CK(c, cudaMemcpyAsync(im.ptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        return F184_OK;
+    }
+    const int nb = im.cur ^ 1;
+    if (!im.buf[nb])
+    {
+        CK(c, cudaMalloc(&im.buf[nb], im.desc.size_bytes));
+        for (int i = 0; i < 2; i++)
+        {
+            CK(c, cudaEventCreateWithFlags(&im.ev_up[i], cudaEventDisableTiming));
+            CK(c, cudaEventCreateWithFlags(&im.ev_release[i], cudaEventDisableTiming));
+        }
+    }
+    // everything enqueued so far on the pass stream may still read buf[cur]; nothing enqueued later will
+    CK(c, cudaEventRecord(im.ev_release[im.cur], c->stream));
+    im.release_valid[im.cur] = true;
+    if (im.release_valid[nb]) CK(c, cudaStreamWaitEvent(c->copy_stream, im.ev_release[nb], 0));
+    CK(c, cudaMemcpyAsync(im.buf[nb], host, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(c, cudaEventRecord(im.ev_up[nb], c->copy_stream));
+    im.cur = nb;
+    im.ptr = im.buf[nb];
+    im.desc.device_ptr = im.ptr;
+    im.upload_pending = true;
     return F184_OK;
 }
 
@@ -415,7 +467,12 @@ int f184_import_external_memory_fd(f184_ctx* c, uint32_t slot, int fd, uint64_t 
     cudaError_t e = cudaExternalMemoryGetMappedBuffer(&ptr, ext, &bd);
     if (e != cudaSuccess) { cudaDestroyExternalMemory(ext); return f184_fail(c, F184_ERR_CUDA, "cudaExternalMemoryGetMappedBuffer: %s", cudaGetErrorString(e)); }
     DevImage& im = c->img[slot];
-    if (im.owned && im.ptr) { cudaStreamSynchronize(c->stream); cudaFree(im.ptr); }
+    if (im.owned && im.ptr)
+    {
+        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
+        for (int i = 0; i < 2; i++) { if (im.buf[i]) cudaFree(im.buf[i]); im.buf[i] = nullptr; }
+        im.upload_pending = false;
+    }
     im.ptr = ptr; im.owned = false; im.ext = ext; im.desc = want; im.desc.device_ptr = ptr;
     return F184_OK;
 }

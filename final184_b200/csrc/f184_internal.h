@@ -30,10 +30,18 @@ struct M4 { float m[16]; };
 
 struct DevImage
 {
-    void* ptr = nullptr;
+    void* ptr = nullptr;                      // what passes read / write (for an uploaded slot: the most recent upload's buffer)
     bool owned = false;
     f184_image_desc desc{};
     cudaExternalMemory_t ext = nullptr;
+    // f184_upload_image on a context-owned slot: two device buffers used alternately, copies on the context's copy stream, so
+    // the upload of frame f+1 overlaps the kernels of frame f (which keep reading the other buffer)
+    void* buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    bool upload_pending = false;              // ev_up[cur] has not been joined into the pass stream yet
+    bool release_valid[2] = {false, false};
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};       // copy stream: upload into buf[i] finished
+    cudaEvent_t ev_release[2] = {nullptr, nullptr};  // pass stream: everything that could read buf[i] has been enqueued before this
 };
 
 struct MipLevelInfo
@@ -46,7 +54,7 @@ struct f184_ctx
 {
     f184_config cfg{};
     std::string err;
-    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
     // scene (device)
     float *pos = nullptr, *nrm = nullptr, *uv = nullptr;
     M4* model_mats = nullptr;
