@@ -240,7 +240,7 @@ void f184_destroy(f184_ctx* c)
     }
     for (void* p : {(void*)c->pos, (void*)c->nrm, (void*)c->uv, (void*)c->model_mats, (void*)c->idx, (void*)c->tri_mat,
                     (void*)c->tri_model, (void*)c->tex_dev, (void*)c->mat_dev, (void*)c->vox_keys, (void*)c->counters_dev,
-                    (void*)c->brick_prev, (void*)c->brick_list, (void*)c->vox_queue, (void*)c->vm_dev, (void*)c->gamma_table})
+                    (void*)c->brick_prev, (void*)c->brick_list, (void*)c->vox_queue, (void*)c->vm_dev, (void*)c->gamma_table, c->gtao_phi_table})
         if (p) cudaFree(p);
     for (uint8_t* p : c->tex_alloc) if (p) cudaFree(p);
     for (int s = 0; s < F184_STAGE_COUNT; s++)

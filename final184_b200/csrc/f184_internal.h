@@ -85,6 +85,7 @@ struct f184_ctx
     uint32_t vox_queue_cap = 0;
     M4* vm_dev = nullptr;                     // View * Model per model matrix
     uint32_t vm_cap = 0;
+    void* gtao_phi_table = nullptr;           // (cos, sin) of the 64 GTAO slice angles (gtao.cu)
     float* gamma_table = nullptr;             // pow(a/255, 2.2), a = 0..255 (mode_n_inject.cu)
     bool defer_normalise = false;             // multi-GPU: f184_voxelize stops after accumulation
     cudaSurfaceObject_t rad_surf = 0;

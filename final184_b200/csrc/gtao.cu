@@ -32,7 +32,21 @@ __device__ __forceinline__ float fastAcos2(float x)
 __device__ __forceinline__ float unorm16(uint16_t v) { return (float)v / 65535.0f; }
 __device__ __forceinline__ float sgn(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
-struct GtaoParams { M4 InvProj; const float* depth; const uint16_t* normals; uint16_t* raw; uint16_t* out; uint32_t W, H; };
+struct GtaoParams { M4 InvProj; const float* depth; const uint16_t* normals; uint16_t* raw; uint16_t* out; uint32_t W, H; const float2* phi_table; };
+
+// The slice angle takes 16 start values (4x4 interleave, gtao.frag:64) x 4 slices: phi = -(k/16) pi, then += pi/4 three times.
+// (cos, sin) of those 64 angles, evaluated once on the device with the same float additions and the same dm_cos / dm_sin the
+// per-pixel code used, so the table is bit-identical to recomputing them (8 of the ~24 range reductions per pixel).
+__global__ void k_gtao_phi_table(float2* __restrict__ table)
+{
+    const int k = threadIdx.x;               // 0..15
+    float phi = -(1.0f / 16.0f) * (float)k * PI_;
+    for (int samp = 0; samp < 4; samp++)
+    {
+        table[k * 4 + samp] = make_float2(dm_cos(phi), dm_sin(phi));
+        phi += PI_ / 4.0f;
+    }
+}
 
 __device__ __forceinline__ f3 cs_pos(const GtaoParams& G, float u, float v)
 {
@@ -44,6 +58,9 @@ __device__ __forceinline__ f3 cs_pos(const GtaoParams& G, float u, float v)
 
 __global__ void __launch_bounds__(128) k_gtao(const GtaoParams G)
 {
+    __shared__ float2 phi_cs[64];
+    if (threadIdx.x < 64) phi_cs[threadIdx.x] = G.phi_table[threadIdx.x];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const uint32_t y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
@@ -61,13 +78,13 @@ __global__ void __launch_bounds__(128) k_gtao(const GtaoParams G)
         float integral = 0.0f;
         const float radius = (float)H * 0.5f / -cur.z;
         const int cx = (int)x, cy = (int)y;
-        float phi = -(1.0f / 16.0f) * (float)((((cx + cy) & 0x3) << 2) + (cx & 0x3)) * PI_;
+        const int phi_k = (((cx + cy) & 0x3) << 2) + (cx & 0x3);      // phi = -(1/16) * phi_k * pi, + pi/4 per slice: tabulated
         const float rStep = radius / 2.0f;
 #pragma unroll 1
         for (int samp = 0; samp < 4; samp++)
         {
             float hx = -1.0f, hy = -1.0f;
-            const float cph = dm_cos(phi), sph = dm_sin(phi);
+            const float cph = phi_cs[phi_k * 4 + samp].x, sph = phi_cs[phi_k * 4 + samp].y;
             const f3 sliceDir = {cph, sph, 0.0f};
             const float sdx = cph, sdy = -sph;
             float r = rStep * (0.25f * (float)((cy - cx) & 0x3));
@@ -99,7 +116,6 @@ __global__ void __launch_bounds__(128) k_gtao(const GtaoParams G)
             const float ay = -dm_cos(2.0f * hy - n) + dm_cos(n) + 2.0f * hy * dm_sin(n);
             const float a = 0.25f * (ax * 1.0f + ay * 1.0f);
             integral += a * weight;
-            phi += PI_ / 4.0f;
         }
         vis = integral / 4.0f;
     }
@@ -146,6 +162,13 @@ int f184_gtao_impl(f184_ctx* c, const f184_view_constants* view)
     G.raw = img_ptr<uint16_t>(c, F184_SLOT_AO_RAW);
     G.out = img_ptr<uint16_t>(c, F184_SLOT_AO_OUT);
     G.W = c->cfg.width; G.H = c->cfg.height;
+    if (!c->gtao_phi_table)
+    {
+        CK(c, cudaMalloc(&c->gtao_phi_table, 64 * sizeof(float2)));
+        k_gtao_phi_table<<<1, 16, 0, c->stream>>>(reinterpret_cast<float2*>(c->gtao_phi_table));
+        CK_LAUNCH(c);
+    }
+    G.phi_table = reinterpret_cast<const float2*>(c->gtao_phi_table);
     int rc = f184_stage_begin(c, F184_STAGE_GTAO);
     if (rc) return rc;
     dim3 grid((G.W + 15) / 16, (G.H + 7) / 8);

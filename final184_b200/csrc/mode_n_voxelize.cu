@@ -256,7 +256,9 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
             dmin = fminf(dmin, xd); dmax = fmaxf(dmax, xd);
         }
     }
-    const int k0 = max(s.lo[2], (int)floorf(dmin * (1.0f / 256.0f)) - 1), k1 = min(s.hi[2], (int)floorf(dmax * (1.0f / 256.0f)) + 1);
+    // the plane crosses box kd iff [dmin, dmax] meets [256 kd, 256 kd + 256]: kd in [dmin/256 - 1, dmax/256]; the float estimate is
+    // good to ~1e-3 voxel, the 0.02-voxel margin keeps the range a superset and the exact tests below decide
+    const int k0 = max(s.lo[2], (int)ceilf(dmin * (1.0f / 256.0f) - 1.02f)), k1 = min(s.hi[2], (int)floorf(dmax * (1.0f / 256.0f) + 0.02f));
     if (k0 > k1) return 0;
     // plane: n . (v0 - c) = base - n_w * cw ; |.| <= hs (|n_u| + |n_v| + |n_w|)
     const long long plane_r = (long long)hs * (llabs(s.n[0]) + llabs(s.n[1]) + llabs(s.n[2]));
