@@ -43,14 +43,15 @@ ORACLE_SO = os.path.join(REPO, "oracle", "_build", "libf184_oracle.so")
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
-    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--grid", type=int, default=512)
     p.add_argument("--width", type=int, default=3840)
     p.add_argument("--height", type=int, default=2160)
     p.add_argument("--shadow", type=int, default=2048)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-overlap", action="store_true", help="F184_FLAG_NO_OVERLAP: every pass on one stream (A/B of the frame overlap)")
     p.add_argument("--schedule", default=None, choices=[None, "slab", "replicate"], help="multi-GPU schedule (default: slab)")
     p.add_argument("--cpu-budget-s", type=float, default=20.0, help="target CPU seconds of the cpu_baseline sample")
     return p.parse_args()
@@ -121,7 +122,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -265,7 +266,7 @@ def run_b200(args, rank, world, local_rank):
 
     from final184_b200.dist import ShardedVoxelGI
     g = ShardedVoxelGI(grid_n=N, width=W, height=H, shadow_res=args.shadow, device=local_rank, rank=rank, nranks=world, scene=sc,
-                       voxel_cam=cams["voxel"], mode=args.schedule)
+                       voxel_cam=cams["voxel"], mode=args.schedule, flags=A.FLAG_NO_OVERLAP if args.no_overlap else 0)
     stream = torch.cuda.Stream(device=local_rank)
     g.ctx.set_stream(stream.cuda_stream)
     g.connect()
@@ -323,25 +324,52 @@ def run_b200(args, rank, world, local_rank):
         counters = {"fragments": g.ctx.counter(A.COUNTER_FRAGMENTS), "bricks": g.ctx.counter(A.COUNTER_BRICKS),
                     "occupied": g.ctx.counter(A.COUNTER_OCCUPIED), "cone_samples": g.ctx.counter(A.COUNTER_MARCH_STEPS)}
         # ---- timed region: end to end with host buffers.  Every step uploads one frame's inputs from pinned host memory and
-        # reads one traced image back.  f184_upload_image double-buffers its slots on a copy stream, so the caller
-        # streams: the inputs of frame f+1 are submitted right after frame f's kernels and travel while they run.
+        # reads one traced image back into pinned host memory.  The caller keeps ONE frame in flight, as a streaming consumer
+        # does: it submits frame f (kernels), the inputs of frame f+1 (H2D on the copy stream: f184_upload_image
+        # double-buffers its slots) and the read-back of frame f (device-side snapshot + D2H on the read-back stream), then
+        # waits for the image of frame f-1 and consumes it.  All K images are on the host when the clock stops.
+        out_hosts = [out_host, torch.empty(out_info.size_bytes, dtype=torch.uint8).pin_memory()]
         upload_inputs()
-        for _ in range(2):
-            frame(); upload_inputs(); g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_host.data_ptr(), d2h); g.ctx.sync()
+        for i in range(3):
+            frame(); upload_inputs(); g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_hosts[i & 1].data_ptr(), d2h)
+        g.ctx.sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t_wall0 = time.perf_counter()
         e0.record(stream)
-        for _ in range(args.steps):
+        checksum = 0
+        for i in range(args.steps):
             frame()                            # consumes the inputs uploaded one iteration ago
             upload_inputs()                    # next frame's inputs (H2D, copy stream)
-            g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_host.data_ptr(), d2h)
-            g.ctx.sync()                       # the caller consumes the image every frame
+            g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_hosts[i & 1].data_ptr(), d2h)
+            if i:
+                g.ctx.readback_wait(1)         # the image of frame i-1 is on the host: the caller consumes it
+                checksum += int(out_hosts[(i - 1) & 1][-8])
+        g.ctx.readback_wait(0)
+        checksum += int(out_hosts[(args.steps - 1) & 1][-8])
+        g.ctx.sync()
         e1.record(stream)
         barrier()
         e2e_ms_dev = e0.elapsed_time(e1)
         e2e_ms_wall = (time.perf_counter() - t_wall0) * 1e3
         e2e_ms = max(e2e_ms_dev, e2e_ms_wall)
+        # PCIe rates of this box (explains e2e: it cannot beat bytes / rate), measured with the same pinned buffers
+        pcie = {}
+        if rank == 0:
+            big = max(pinned.values(), key=lambda t: t.numel())
+            slot_big = [s_ for s_, t in pinned.items() if t is big][0]
+            g.ctx.sync()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                g.ctx.upload_ptr(slot_big, big.data_ptr(), big.numel())
+            g.ctx.image_info(slot_big); g.ctx.sync()
+            torch.cuda.synchronize()
+            pcie["h2d_gbs"] = 4 * big.numel() / (time.perf_counter() - t0) / 1e9
+            t0 = time.perf_counter()
+            for i in range(4):
+                g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_hosts[i & 1].data_ptr(), d2h)
+            g.ctx.sync()
+            pcie["d2h_gbs"] = 4 * d2h / (time.perf_counter() - t0) / 1e9
         # secondary pass, reported beside the metric (not part of it): GTAO + its blur, and the indirect blur tail
         for _ in range(3):
             g.ctx.gtao(cams["main"]); g.ctx.blur_indirect(k)
@@ -388,12 +416,14 @@ def run_b200(args, rank, world, local_rank):
                "ms_per_step": ms_frame, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
                "dtype": "u8 volumes / i64 overlap tests / f32 shading", "data": "synthetic",
                "config": {"workload": wname, "grid": N, "width": W, "height": H, "shadow": args.shadow, "triangles": sc.n_tris,
-                          "parallelism": g.describe(), "l2": "inputs larger than L2 (volume chain %.0f MB + accumulators; no flush)" % (algorithmic_bytes("trace", args, sc, counters) / 1e6)},
+                          "parallelism": g.describe() + ("" if world > 1 or args.no_overlap else "; voxelize+normalise of frame f+1 overlap the cone trace of frame f (internal stream)"), "l2": "inputs larger than L2 (volume chain %.0f MB + accumulators; no flush)" % (algorithmic_bytes("trace", args, sc, counters) / 1e6)},
                "gvoxel_per_s": N ** 3 / (ms_frame * 1e-3) / 1e9,
                "gcone_samples_per_s": total_samples / (stage_ms.get("trace", ms_frame) * 1e-3) / 1e9,
                "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "comm_ms": comm_ms, "secondary_ms": extra_ms, "counters": counters,
                "roofline": roofline, "roofline_stages": rstages, "other_bounds": other,
-               "e2e": {"value": e2e_ms / args.steps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "e2e": {"value": e2e_ms / args.steps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "pcie": {k_: round(v_, 1) for k_, v_ in pcie.items()},
+                       "note": "one frame in flight: H2D of frame f+1 and D2H of frame f-1 overlap the kernels of frame f"},
                "gpu_launches": launches_all, "clocks": clk}
         if world == 1 and not args.no_cpu_baseline:
             cpu = CpuPath(args, sc, cams, fi, vchunks=1, tfrac=16, bands=2)

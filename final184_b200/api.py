@@ -36,6 +36,7 @@ FLAG_EXTERNAL_RANDS = 1
 FLAG_NO_TMA = 2
 FLAG_DENSE_MIPS = 4
 FLAG_GATHER_LINEAR = 8
+FLAG_NO_OVERLAP = 16
 
 (FMT_UNDEFINED, FMT_R32_SFLOAT, FMT_R16G16B16A16_UNORM, FMT_R8G8B8A8_UNORM, FMT_R16G16B16A16_SFLOAT,
  FMT_R16G16_UINT, FMT_R32G32B32A32_SFLOAT, FMT_R8G8B8A8_SNORM, FMT_R32_UINT) = range(9)
@@ -134,6 +135,7 @@ _SIGS = {
     "upload_image": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
     "readback": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
     "readback_async": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "readback_wait": (C.c_int, [C.c_void_p, C.c_uint32]),
     "set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sync": (C.c_int, [C.c_void_p]),
     "frame_begin": (C.c_int, [C.c_void_p]),
@@ -280,6 +282,9 @@ class VoxelGI:
 
     def readback_async_ptr(self, slot, host_ptr, nbytes):
         self._ck(self.lib.readback_async(self.h, slot, host_ptr, nbytes), "readback_async")
+
+    def readback_wait(self, age=0):
+        self._ck(self.lib.readback_wait(self.h, age), "readback_wait")
 
     def read_array(self, direction, level, n):
         """Texture-side storage (what the tracer samples): direction < 0 -> level-0 radiance array, else mip `level`+1."""

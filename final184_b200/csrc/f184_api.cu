@@ -125,6 +125,26 @@ int f184_stage_end(f184_ctx* c, int stage)
     return F184_OK;
 }
 
+// ---- frame overlap (f184_internal.h) --------------------------------------------------------------
+bool f184_overlap_enabled(const f184_ctx* c)
+{
+    return c->vox_stream && c->cfg.mode == F184_MODE_NORTHSTAR && c->cfg.nranks <= 1 && !(c->cfg.flags & F184_FLAG_NO_OVERLAP);
+}
+int f184_join_vox(f184_ctx* c)
+{
+    if (c->vox_pending)
+    {
+        CK(c, cudaStreamWaitEvent(c->stream, c->ev_vox_done, 0));
+        c->vox_pending = false;
+    }
+    return F184_OK;
+}
+int f184_mark_consumed(f184_ctx* c)
+{
+    if (c->vox_stream) CK(c, cudaEventRecord(c->ev_consumed, c->stream));
+    return F184_OK;
+}
+
 // ---- texture mip chain on the device ------------------------------------------------------------
 // One level per launch: mean of the 2x2 source block, rounded half-to-even back to UNORM8 — what a linear
 // 2:1 vkCmdBlitImage computes (RHI/Private/Vulkan/DeviceVk.cpp:437-465).
@@ -200,6 +220,13 @@ int f184_create(const f184_config* config, f184_ctx** out)
         delete c;
         return f184_fail(nullptr, F184_ERR_CUDA, "cudaStreamCreate failed");
     }
+    if (cudaStreamCreateWithFlags(&c->vox_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_vox_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_consumed, cudaEventDisableTiming) != cudaSuccess)
+    {
+        delete c;
+        return f184_fail(nullptr, F184_ERR_CUDA, "cudaStreamCreate failed");
+    }
     for (int s = 0; s < F184_STAGE_COUNT; s++)
     {
         cudaEvent_t a, b;
@@ -223,6 +250,8 @@ void f184_destroy(f184_ctx* c)
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->vox_stream) cudaStreamSynchronize(c->vox_stream);
+    if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
     f184_mode_n_release(c);
     for (auto& im : c->img)
     {
@@ -254,6 +283,16 @@ void f184_destroy(f184_ctx* c)
     if (c->sem_signal) cudaDestroyExternalSemaphore(c->sem_signal);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->vox_stream) cudaStreamDestroy(c->vox_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    for (int i = 0; i < 2; i++)
+    {
+        if (c->rb_stage[i]) cudaFree(c->rb_stage[i]);
+        if (c->ev_rb_snap[i]) cudaEventDestroy(c->ev_rb_snap[i]);
+        if (c->ev_rb_done[i]) cudaEventDestroy(c->ev_rb_done[i]);
+    }
+    if (c->ev_vox_done) cudaEventDestroy(c->ev_vox_done);
+    if (c->ev_consumed) cudaEventDestroy(c->ev_consumed);
     delete c;
 }
 
@@ -270,6 +309,7 @@ int f184_scene_upload(f184_ctx* c, const f184_scene_desc* s)
         if (s->tri_model[i] >= s->n_models) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "scene_upload: tri_model out of range");
     CK(c, cudaSetDevice(c->cfg.device));
     CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaStreamSynchronize(c->vox_stream));     // the voxelizer in flight reads the buffers freed below
     for (void* p : {(void*)c->pos, (void*)c->nrm, (void*)c->uv, (void*)c->model_mats, (void*)c->idx, (void*)c->tri_mat, (void*)c->tri_model})
         if (p) cudaFree(p);
     auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
@@ -321,6 +361,7 @@ int f184_texture_upload(f184_ctx* c, uint32_t id, const uint8_t* rgba, uint32_t 
         sw = dw; sh = dh;
     }
     CK(c, cudaStreamSynchronize(c->stream));     // `rgba` may be freed by the caller on return
+    CK(c, cudaStreamSynchronize(c->vox_stream));
     if (c->tex_alloc[id]) cudaFree(c->tex_alloc[id]);
     c->tex_alloc[id] = dev;
     t.base = dev;
@@ -397,6 +438,14 @@ int f184_upload_image(f184_ctx* c, uint32_t slot, const void* host, size_t bytes
     if (rc) return rc;
     DevImage& im = c->img[slot];
     if (bytes != im.desc.size_bytes) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "upload_image: slot %u is %llu bytes, got %zu", slot, (unsigned long long)im.desc.size_bytes, bytes);
+    if (slot == F184_SLOT_ACCUM_COLOR || slot == F184_SLOT_ACCUM_NORMAL || slot == F184_SLOT_VOX_ALBEDO || slot == F184_SLOT_VOX_NORMAL ||
+        slot == F184_SLOT_BRICK_FLAGS)
+    {   // the voxelizer's own slots: written in stream order behind whatever is in flight on vox_stream
+        rc = f184_join_vox(c);
+        if (rc) return rc;
+        CK(c, cudaMemcpyAsync(im.ptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        return f184_mark_consumed(c);
+    }
     if (!im.owned || im.ext)
     {   // caller-owned memory: plain stream-ordered copy
         CK(c, cudaMemcpyAsync(im.ptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -431,7 +480,47 @@ int f184_readback_async(f184_ctx* c, uint32_t slot, void* host, size_t bytes)
     int rc = f184_ensure_image(c, slot);
     if (rc) return rc;
     if (bytes > c->img[slot].desc.size_bytes) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "readback: slot %u is %llu bytes, got %zu", slot, (unsigned long long)c->img[slot].desc.size_bytes, bytes);
-    CK(c, cudaMemcpyAsync(host, c->img[slot].ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    const bool vox_slot = slot == F184_SLOT_ACCUM_COLOR || slot == F184_SLOT_ACCUM_NORMAL || slot == F184_SLOT_VOX_ALBEDO ||
+                          slot == F184_SLOT_VOX_NORMAL || slot == F184_SLOT_BRICK_FLAGS;
+    if (vox_slot) { rc = f184_join_vox(c); if (rc) return rc; }
+    if (bytes > (256ull << 20) || vox_slot)
+    {   // volume-sized slots (tests): on the pass stream
+        CK(c, cudaMemcpyAsync(host, c->img[slot].ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+        if (vox_slot) return f184_mark_consumed(c);
+        return F184_OK;
+    }
+    if (!c->d2h_stream)
+    {
+        CK(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++)
+        {
+            CK(c, cudaEventCreateWithFlags(&c->ev_rb_snap[i], cudaEventDisableTiming));
+            CK(c, cudaEventCreateWithFlags(&c->ev_rb_done[i], cudaEventDisableTiming));
+        }
+    }
+    const int b = c->rb_cur ^ 1;
+    if (c->rb_valid[b]) CK(c, cudaStreamWaitEvent(c->stream, c->ev_rb_done[b], 0));      // its previous PCIe copy has drained
+    if (c->rb_cap[b] < bytes)
+    {
+        if (c->rb_stage[b]) { CK(c, cudaEventSynchronize(c->ev_rb_done[b])); CK(c, cudaFree(c->rb_stage[b])); c->rb_stage[b] = nullptr; c->rb_cap[b] = 0; }
+        CK(c, cudaMalloc(&c->rb_stage[b], bytes));
+        c->rb_cap[b] = bytes;
+    }
+    CK(c, cudaMemcpyAsync(c->rb_stage[b], c->img[slot].ptr, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CK(c, cudaEventRecord(c->ev_rb_snap[b], c->stream));
+    CK(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_rb_snap[b], 0));
+    CK(c, cudaMemcpyAsync(host, c->rb_stage[b], bytes, cudaMemcpyDeviceToHost, c->d2h_stream));
+    CK(c, cudaEventRecord(c->ev_rb_done[b], c->d2h_stream));
+    c->rb_valid[b] = true;
+    c->rb_cur = b;
+    return F184_OK;
+}
+
+int f184_readback_wait(f184_ctx* c, uint32_t age)
+{
+    if (!c || age > 1) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "readback_wait: age must be 0 or 1");
+    const int b = age ? c->rb_cur ^ 1 : c->rb_cur;
+    if (c->rb_valid[b]) CK(c, cudaEventSynchronize(c->ev_rb_done[b]));
     return F184_OK;
 }
 
@@ -442,6 +531,7 @@ int f184_readback(f184_ctx* c, uint32_t slot, void* host, size_t bytes)
     int rc = f184_readback_async(c, slot, host, bytes);
     if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));
+    if (c->d2h_stream) CK(c, cudaStreamSynchronize(c->d2h_stream));
     return F184_OK;
 }
 
@@ -504,6 +594,8 @@ int f184_frame_begin(f184_ctx* c)
 int f184_frame_end(f184_ctx* c)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
+    int rc = f184_join_vox(c);
+    if (rc) return rc;
     if (c->sem_signal)
     {
         cudaExternalSemaphoreSignalParams p{};
@@ -516,13 +608,19 @@ int f184_set_stream(f184_ctx* c, void* s)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->vox_stream);
+    if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
+    c->vox_pending = false;
     c->stream = s ? (cudaStream_t)s : c->own_stream;
     return F184_OK;
 }
 int f184_sync(f184_ctx* c)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
+    int rc = f184_join_vox(c);
+    if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));
+    if (c->d2h_stream) CK(c, cudaStreamSynchronize(c->d2h_stream));
     return F184_OK;
 }
 
@@ -544,6 +642,8 @@ int f184_voxelize_accumulate(f184_ctx* c, const f184_view_constants* cam)
     CK(c, cudaSetDevice(c->cfg.device));
     int rc = f184_sync_tables(c);
     if (rc) return rc;
+    rc = f184_join_vox(c);
+    if (rc) return rc;
     return f184_voxelize_accumulate_n(c, cam);
 }
 int f184_normalise(f184_ctx* c)
@@ -552,6 +652,8 @@ int f184_normalise(f184_ctx* c)
     if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "normalise is a north-star stage");
     if (!c->brick_prev) return f184_fail(c, F184_ERR_NOT_READY, "normalise: call f184_voxelize_accumulate first");
     CK(c, cudaSetDevice(c->cfg.device));
+    int rc = f184_join_vox(c);
+    if (rc) return rc;
     return f184_normalise_n(c);
 }
 int f184_gather_volume(f184_ctx* c)
@@ -559,6 +661,8 @@ int f184_gather_volume(f184_ctx* c)
     if (!c) return F184_ERR_INVALID_ARGUMENT;
     if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "gather_volume is a north-star stage");
     CK(c, cudaSetDevice(c->cfg.device));
+    int rc = f184_join_vox(c);
+    if (rc) return rc;
     return f184_gather_n(c);
 }
 
@@ -570,6 +674,8 @@ int f184_ipc_export(f184_ctx* c, uint32_t buffer, f184_ipc_handle* out)
     CK(c, cudaSetDevice(c->cfg.device));
     void* p = nullptr;
     int rc = f184_ipc_buffer_ptr(c, buffer, &p);
+    if (rc) return rc;
+    rc = f184_join_vox(c);
     if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));      // the allocation's zero-fill has landed before a peer can see it
     cudaIpcMemHandle_t h;
@@ -597,14 +703,22 @@ int f184_inject(f184_ctx* c, const f184_sun* sun, const f184_extended_matrices* 
     if (!c || !sun || !m) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "inject: null argument");
     if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "inject is a north-star stage");
     CK(c, cudaSetDevice(c->cfg.device));
-    return f184_inject_n(c, sun, m);
+    int rc = f184_join_vox(c);
+    if (rc) return rc;
+    rc = f184_inject_n(c, sun, m);
+    if (rc) return rc;
+    return f184_mark_consumed(c);
 }
 int f184_build_mips(f184_ctx* c)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
     if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "mips are a north-star stage");
     CK(c, cudaSetDevice(c->cfg.device));
-    return f184_mips_n(c);
+    int rc = f184_join_vox(c);
+    if (rc) return rc;
+    rc = f184_mips_n(c);
+    if (rc) return rc;
+    return f184_mark_consumed(c);
 }
 int f184_trace_indirect(f184_ctx* c, const f184_trace_constants* k)
 {
@@ -663,6 +777,8 @@ int f184_stage_time_ms(f184_ctx* c, uint32_t stage, float* ms)
 {
     if (!c || stage >= F184_STAGE_COUNT || !ms) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "stage_time_ms: bad argument");
     if (!c->ev_valid[stage]) { *ms = 0.f; return F184_OK; }
+    int rc = f184_join_vox(c);
+    if (rc) return rc;
     CK(c, cudaEventSynchronize(c->ev[stage][1]));
     CK(c, cudaEventElapsedTime(ms, c->ev[stage][0], c->ev[stage][1]));
     return F184_OK;
@@ -670,6 +786,8 @@ int f184_stage_time_ms(f184_ctx* c, uint32_t stage, float* ms)
 int f184_stage_time_reset(f184_ctx* c, uint32_t accumulate)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
+    int rc = f184_join_vox(c);
+    if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));
     c->ev_accumulate = accumulate != 0;
     for (int s = 0; s < F184_STAGE_COUNT; s++)
@@ -686,6 +804,8 @@ int f184_stage_time_total(f184_ctx* c, uint32_t stage, float* ms_sum, uint32_t* 
     if (!c || stage >= F184_STAGE_COUNT || !ms_sum || !runs) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "stage_time_total: bad argument");
     *ms_sum = 0.f; *runs = 0;
     if (!c->ev_accumulate) return f184_fail(c, F184_ERR_NOT_READY, "stage_time_total: call f184_stage_time_reset(ctx, 1) first");
+    int rc = f184_join_vox(c);
+    if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));
     for (uint32_t r = 0; r < c->ev_runs[stage]; r++)
     {
@@ -701,6 +821,8 @@ int f184_counter_get(f184_ctx* c, uint32_t which, uint64_t* v)
     if (!c || which >= F184_COUNTER_COUNT || !v) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "counter_get: bad argument");
     if (which == F184_COUNTER_KERNEL_LAUNCHES) { *v = c->launches; return F184_OK; }
     unsigned long long t = 0;
+    int rc = f184_join_vox(c);
+    if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaMemcpy(&t, c->counters_dev + which, sizeof(t), cudaMemcpyDeviceToHost));
     *v = t;

@@ -55,6 +55,21 @@ struct f184_ctx
     f184_config cfg{};
     std::string err;
     cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
+    // frame overlap (one GPU, north-star mode): voxelize + normalise of frame f+1 run on vox_stream while the cone trace of
+    // frame f still occupies the pass stream (atomics/ALU-bound against texture-pipe-bound: they share the SMs well).
+    //   vox_stream waits ev_consumed = the last pass-stream work that reads what voxelize/normalise overwrite
+    //                                  (inject, mips, read-backs of the volume slots)
+    //   pass stream waits ev_vox_done before the first call that reads their outputs (f184_join_vox)
+    cudaStream_t vox_stream = nullptr;
+    cudaEvent_t ev_vox_done = nullptr, ev_consumed = nullptr;
+    bool vox_pending = false, vox_started = false;
+    // asynchronous read-backs (f184_readback_async): device-side snapshot on the pass stream, PCIe copy on d2h_stream
+    cudaStream_t d2h_stream = nullptr;
+    void* rb_stage[2] = {nullptr, nullptr};
+    size_t rb_cap[2] = {0, 0};
+    cudaEvent_t ev_rb_snap[2] = {nullptr, nullptr}, ev_rb_done[2] = {nullptr, nullptr};
+    bool rb_valid[2] = {false, false};
+    int rb_cur = 0;
     // scene (device)
     float *pos = nullptr, *nrm = nullptr, *uv = nullptr;
     M4* model_mats = nullptr;
@@ -138,6 +153,9 @@ int f184_fail(f184_ctx* c, int code, const char* fmt, ...);
     } while (0)
 
 int f184_ensure_image(f184_ctx* c, int slot);
+bool f184_overlap_enabled(const f184_ctx* c);
+int f184_join_vox(f184_ctx* c);           // pass stream waits for the voxelize/normalise in flight on vox_stream
+int f184_mark_consumed(f184_ctx* c);      // pass stream: everything that reads the voxelizer's outputs has been enqueued
 int f184_sync_tables(f184_ctx* c);
 int f184_stage_begin(f184_ctx* c, int stage);
 int f184_stage_end(f184_ctx* c, int stage);

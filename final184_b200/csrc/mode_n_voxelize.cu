@@ -635,9 +635,33 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
 
 int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
 {
+    if (!f184_overlap_enabled(c))
+    {
+        int rc = f184_join_vox(c);
+        if (rc) return rc;
+        rc = f184_voxelize_accumulate_n(c, cam);
+        if (rc) return rc;
+        return f184_normalise_n(c);
+    }
+    // Frame overlap: both passes go to vox_stream.  They start once the pass stream has finished everything that reads what
+    // they overwrite (ev_consumed: the previous frame's inject + mips) — NOT once it has finished the previous frame's cone
+    // trace, which reads none of it and is what these kernels run beside.
+    cudaStream_t pass = c->stream;
+    if (!c->vox_started)
+    {   // first use: order vox_stream behind everything enqueued so far (allocation clears, scene and table uploads)
+        CK(c, cudaEventRecord(c->ev_consumed, pass));
+        c->vox_started = true;
+    }
+    CK(c, cudaStreamWaitEvent(c->vox_stream, c->ev_consumed, 0));
+    c->stream = c->vox_stream;
     int rc = f184_voxelize_accumulate_n(c, cam);
+    if (rc == F184_OK) rc = f184_normalise_n(c);
+    cudaError_t e = rc == F184_OK ? cudaEventRecord(c->ev_vox_done, c->vox_stream) : cudaSuccess;
+    c->stream = pass;
     if (rc) return rc;
-    return f184_normalise_n(c);
+    CK(c, e);
+    c->vox_pending = true;
+    return F184_OK;
 }
 
 // Normalise this rank's brick layers (the whole volume on one GPU).

@@ -122,8 +122,11 @@ typedef enum f184_flags {
     F184_FLAG_EXTERNAL_RANDS = 1,  /* mode R trace: rands come from a bound buffer (march-only parity) */
     F184_FLAG_NO_TMA = 2,          /* mode N mips: dense, plain one-thread-per-texel kernel for every level (cross-check) */
     F184_FLAG_GATHER_LINEAR = 8,   /* multi-GPU: f184_gather_volume also fills the linear RADIANCE / MIPS slots (tests) */
-    F184_FLAG_DENSE_MIPS = 4       /* mode N mips: dense chain, TMA-staged tiles for the large levels (default is the sparse
+    F184_FLAG_DENSE_MIPS = 4,      /* mode N mips: dense chain, TMA-staged tiles for the large levels (default is the sparse
                                       brick-list path for levels 1-3 + one fused launch for the rest) */
+    F184_FLAG_NO_OVERLAP = 16      /* mode N, one GPU: keep f184_voxelize on the pass stream. Default: voxelize + normalise of the
+                                      next frame run on an internal stream and overlap the previous frame's cone trace; every call
+                                      that reads their outputs orders itself after them, so results are identical either way */
 } f184_flags;
 
 /* CViewConstants, Foreground/SceneGraph/SceneView.h:8-14 = GlobalConstants, Shader/EngineCommon.h:7-13. 208 B. */
@@ -233,7 +236,13 @@ int f184_bind_image(f184_ctx* ctx, uint32_t slot, const f184_image_desc* desc);
 int f184_image_info(f184_ctx* ctx, uint32_t slot, f184_image_desc* out_desc);
 int f184_upload_image(f184_ctx* ctx, uint32_t slot, const void* host, size_t bytes);      /* async H2D on the stream */
 int f184_readback(f184_ctx* ctx, uint32_t slot, void* host, size_t bytes);                /* synchronous D2H */
-int f184_readback_async(f184_ctx* ctx, uint32_t slot, void* pinned_host, size_t bytes);   /* async D2H on the stream */
+/* Asynchronous D2H.  Images up to 256 MiB are snapshotted on the pass stream (device-to-device, two alternating staging
+ * buffers) and travel to `pinned_host` on the context's read-back stream, so the next frame's passes do not wait for PCIe;
+ * larger slots are copied on the pass stream itself.  The data is on the host after f184_sync, or after
+ * f184_readback_wait(ctx, age): age 0 = the most recent asynchronous read-back, 1 = the one before it (a consumer that
+ * keeps one frame in flight submits frame f+1, then waits for the image of frame f). */
+int f184_readback_async(f184_ctx* ctx, uint32_t slot, void* pinned_host, size_t bytes);
+int f184_readback_wait(f184_ctx* ctx, uint32_t age);
 
 /* Vulkan interop: import an exported VkDeviceMemory (opaque fd) as a slot, and
  * the section wait/signal semaphores (RHI/Private/Vulkan/CommandListVk.h:17-24). */

@@ -219,6 +219,7 @@ int f184o_readback(f184o_ctx* c, uint32_t slot, void* host, size_t bytes)
 }
 int f184o_readback_async(f184o_ctx* c, uint32_t slot, void* host, size_t bytes) { return f184o_readback(c, slot, host, bytes); }
 int f184o_set_stream(f184o_ctx*, void*) { return F184_OK; }
+int f184o_readback_wait(f184o_ctx*, uint32_t) { return F184_OK; }
 int f184o_sync(f184o_ctx*) { return F184_OK; }
 int f184o_frame_begin(f184o_ctx*) { return F184_OK; }
 int f184o_frame_end(f184o_ctx*) { return F184_OK; }

@@ -107,3 +107,39 @@ def test_sponza_pipeline(cuda_lib, oracle_lib, cams):
     assert np.array_equal(g.readback(A.SLOT_MIPS), o.readback(A.SLOT_MIPS))
     ig, io = g.readback(A.SLOT_INDIRECT_OUT).astype(np.float32), o.readback(A.SLOT_INDIRECT_OUT).astype(np.float32)
     assert Hh.rel_l2(ig[..., :3], io[..., :3]) <= 1e-2
+
+
+def test_frame_overlap_is_invisible(cuda_lib, proc_scene, cams):
+    """Default single-GPU scheduling runs voxelize + normalise of frame f+1 on an internal stream beside the cone trace
+    of frame f (and read-backs travel on a third stream).  Six frames are submitted back to back without a host
+    sync, the triangle range changing every frame so each frame's volume differs and emptied bricks must be
+    cleared; every image and the last volume must equal the F184_FLAG_NO_OVERLAP run bit for bit."""
+    import torch
+    n, w, h = 128, 320, 184
+    fi = frame_inputs(proc_scene, cams["main"], cams["shadow"], w, h, 512, 0)
+    k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], w, h, 0, True)
+    T = proc_scene.n_tris
+    ranges = [(0, T), (0, T // 2), (T // 3, T // 2), (0, T), (T // 2, T), (0, T // 4)]
+    results = []
+    for flags in (A.FLAG_NO_OVERLAP, 0):
+        c = A.VoxelGI(lib=cuda_lib, grid_n=n, width=w, height=h, mode=A.MODE_NORTHSTAR, shadow_res=512, flags=flags)
+        c.upload_scene(proc_scene)
+        Hh.upload_frame(c, fi)
+        nbytes = c.image_info(A.SLOT_INDIRECT_OUT).size_bytes
+        hosts = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in ranges]
+        for i, (first, count) in enumerate(ranges):
+            c.set_triangle_range(first, count)
+            c.voxelize(cams["voxel"]); c.inject(k); c.build_mips(); c.trace_indirect(k)
+            c.readback_async_ptr(A.SLOT_INDIRECT_OUT, hosts[i].data_ptr(), nbytes)
+            if i:
+                c.readback_wait(1)
+        c.sync()
+        results.append(([t.numpy().copy() for t in hosts], c.readback(A.SLOT_VOX_ALBEDO), c.readback(A.SLOT_MIPS),
+                        c.counter(A.COUNTER_FRAGMENTS), c.counter(A.COUNTER_OCCUPIED)))
+        c.close()
+    (ia, va, ma, fa, oa), (ib, vb, mb, fb, ob) = results
+    assert fa == fb > 0 and oa == ob > 0
+    assert np.array_equal(va, vb) and np.array_equal(ma, mb)
+    for i, (x, y) in enumerate(zip(ia, ib)):
+        assert np.array_equal(x, y), f"frame {i}"
+    assert not np.array_equal(ia[0], ia[1])       # the frames really differ
