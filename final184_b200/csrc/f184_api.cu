@@ -220,7 +220,11 @@ int f184_create(const f184_config* config, f184_ctx** out)
         delete c;
         return f184_fail(nullptr, F184_ERR_CUDA, "cudaStreamCreate failed");
     }
-    if (cudaStreamCreateWithFlags(&c->vox_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // highest priority: the block scheduler hands free SM slots to a higher-priority stream's CTAs first, so the voxelizer's
+    // CTAs move in beside the resident cone-trace CTAs instead of queueing behind that kernel's whole grid
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&c->vox_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_vox_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_consumed, cudaEventDisableTiming) != cudaSuccess)
     {
