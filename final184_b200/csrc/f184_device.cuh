@@ -48,6 +48,9 @@ __device__ __forceinline__ f3 mul33(const M4& M, f3 v)
             (M.m[2] * v.x + M.m[6] * v.y) + M.m[10] * v.z};
 }
 
+// z of slice `z` of direction d inside a level of the six-direction atlas (f184_internal.h: dir_atlas); n = edge of the level
+__device__ __forceinline__ int atlas_z(int d, int n, int z) { return 2 * d * n + z; }
+
 __device__ __forceinline__ int wrap_pow2(int i, int n) { return i & (n - 1); }   // n is a power of two; works for negatives
 
 // Warp-aggregated add of a per-lane count to a global counter: one atomic per warp.

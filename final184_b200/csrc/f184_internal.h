@@ -92,8 +92,12 @@ struct f184_ctx
     // mode N
     std::vector<MipLevelInfo> mip_levels;     // index 0 = level 1
     cudaArray_t rad_array = nullptr;          // level-0 radiance as a 3D array for hardware filtering
-    cudaMipmappedArray_t dir_arrays[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaTextureObject_t rad_tex = 0, dir_tex[6] = {0, 0, 0, 0, 0, 0};
+    // levels >= 1: ONE mipmapped 3D array holds all six directions (the "atlas"): level l has extent (n, n, 12 n) and
+    // direction d lives in z = [2 d n, 2 d n + n); the n slices behind each slab stay zero, so a trilinear footprint that
+    // leaves a slab reads the same zeros border addressing would give.  One texture handle for every fetch of the cone
+    // tracer keeps the handle warp-uniform (six per-direction handles made ptxas wrap every TEX in a waterfall loop).
+    cudaMipmappedArray_t dir_atlas = nullptr;
+    cudaTextureObject_t rad_tex = 0, dir_tex = 0;
     uint32_t* brick_prev = nullptr;           // bricks written last frame (to clear what became empty)
     uint32_t* brick_list = nullptr;           // bricks processed this frame (touched now or last frame)
     uint32_t* vox_queue = nullptr;            // voxelizer pass-2 queue: uint2 (triangle, first task) per large triangle
@@ -104,7 +108,7 @@ struct f184_ctx
     float* gamma_table = nullptr;             // pow(a/255, 2.2), a = 0..255 (mode_n_inject.cu)
     bool defer_normalise = false;             // multi-GPU: f184_voxelize stops after accumulation
     cudaSurfaceObject_t rad_surf = 0;
-    cudaSurfaceObject_t dir_surf[6][12] = {};
+    cudaSurfaceObject_t dir_surf[12] = {};        // one per atlas level
     uint32_t n_mip_levels = 0;                // levels >= 1
     void* tma_maps = nullptr;                 // host array of CUtensorMap (mode_n_mips.cu)
     // one NVLink box: peer-mapped buffers (index = rank; own entry points at own memory)

@@ -133,10 +133,11 @@ __global__ void __launch_bounds__(INJECT_WARPS * 32) k_inject_n(const InjectPara
     }
 }
 
-__global__ void k_clear_array(cudaSurfaceObject_t s, int n)
+__global__ void k_clear_array(cudaSurfaceObject_t s, int n, int nz)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
-    if (x < n) surf3Dwrite(make_uchar4(0, 0, 0, 0), s, x * 4, y, z);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= n) return;
+    for (int z = blockIdx.z; z < nz; z += gridDim.z) surf3Dwrite(make_uchar4(0, 0, 0, 0), s, x * 4, y, z);
 }
 
 }  // namespace
@@ -177,8 +178,9 @@ M4 f184_invert_m4(const M4& A)
     return R;
 }
 
-// Texture-side storage: level 0 as a 3D array, levels >= 1 as six mipmapped 3D arrays (one per direction),
-// all surface-writable, sampled with normalised coordinates, trilinear + mip-linear, border addressing.
+// Texture-side storage: level 0 as a 3D array, levels >= 1 as ONE mipmapped 3D array holding the six directions as
+// z-slabs with zero padding between them (the atlas, f184_internal.h); all surface-writable, sampled with normalised
+// coordinates, trilinear, nearest mip level, border addressing.
 int f184_mode_n_alloc(f184_ctx* c)
 {
     if (c->rad_array) return F184_OK;
@@ -197,7 +199,7 @@ int f184_mode_n_alloc(f184_ctx* c)
     CK(c, cudaCreateTextureObject(&c->rad_tex, &rd, &td, nullptr));
     {
         dim3 g((N + 127) / 128, N, N);
-        k_clear_array<<<g, 128, 0, c->stream>>>(c->rad_surf, N);
+        k_clear_array<<<g, 128, 0, c->stream>>>(c->rad_surf, N, N);
         CK_LAUNCH(c);
     }
     uint32_t levels = 0;
@@ -210,30 +212,28 @@ int f184_mode_n_alloc(f184_ctx* c)
         c->mip_levels.push_back(MipLevelInfo{(uint32_t)n, off});
         off += 6ull * n * n * n;
     }
-    for (int d = 0; d < 6; d++)
+    // the six-direction atlas (f184_internal.h): extent (N/2, N/2, 12 * N/2) at its level 0, halving with the chain
+    CK(c, cudaMallocMipmappedArray(&c->dir_atlas, &ch, make_cudaExtent(N / 2, N / 2, 6 * (size_t)N), levels, cudaArraySurfaceLoadStore));
+    for (uint32_t l = 0; l < levels; l++)
     {
-        CK(c, cudaMallocMipmappedArray(&c->dir_arrays[d], &ch, make_cudaExtent(N / 2, N / 2, N / 2), levels, cudaArraySurfaceLoadStore));
-        for (uint32_t l = 0; l < levels; l++)
-        {
-            cudaArray_t la;
-            CK(c, cudaGetMipmappedArrayLevel(&la, c->dir_arrays[d], l));
-            cudaResourceDesc lrd{};
-            lrd.resType = cudaResourceTypeArray;
-            lrd.res.array.array = la;
-            CK(c, cudaCreateSurfaceObject(&c->dir_surf[d][l], &lrd));
-            const int n = std::max(1, (N / 2) >> l);      // the sparse mip builder never writes unlisted bricks: start from zero
-            k_clear_array<<<dim3((n + 127) / 128, n, n), 128, 0, c->stream>>>(c->dir_surf[d][l], n);
-            CK_LAUNCH(c);
-        }
-        cudaResourceDesc mrd{};
-        mrd.resType = cudaResourceTypeMipmappedArray;
-        mrd.res.mipmap.mipmap = c->dir_arrays[d];
-        cudaTextureDesc mtd = td;
-        mtd.mipmapFilterMode = cudaFilterModePoint;       // nearest level
-        mtd.minMipmapLevelClamp = 0.0f;
-        mtd.maxMipmapLevelClamp = (float)(levels - 1);
-        CK(c, cudaCreateTextureObject(&c->dir_tex[d], &mrd, &mtd, nullptr));
+        cudaArray_t la;
+        CK(c, cudaGetMipmappedArrayLevel(&la, c->dir_atlas, l));
+        cudaResourceDesc lrd{};
+        lrd.resType = cudaResourceTypeArray;
+        lrd.res.array.array = la;
+        CK(c, cudaCreateSurfaceObject(&c->dir_surf[l], &lrd));
+        const int n = std::max(1, (N / 2) >> l);      // the sparse mip builder never writes unlisted bricks, nobody writes the padding: start from zero
+        k_clear_array<<<dim3((n + 127) / 128, n, std::min(12 * n, 1024)), 128, 0, c->stream>>>(c->dir_surf[l], n, 12 * n);
+        CK_LAUNCH(c);
     }
+    cudaResourceDesc mrd{};
+    mrd.resType = cudaResourceTypeMipmappedArray;
+    mrd.res.mipmap.mipmap = c->dir_atlas;
+    cudaTextureDesc mtd = td;
+    mtd.mipmapFilterMode = cudaFilterModePoint;       // nearest level
+    mtd.minMipmapLevelClamp = 0.0f;
+    mtd.maxMipmapLevelClamp = (float)(levels - 1);
+    CK(c, cudaCreateTextureObject(&c->dir_tex, &mrd, &mtd, nullptr));
     return F184_OK;
 }
 
@@ -247,13 +247,14 @@ extern "C" int f184_debug_read_array(f184_ctx* c, int32_t dir, uint32_t level, v
     if (dir >= 0)
     {
         if (level >= c->n_mip_levels) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_read_array: bad level");
-        CK(c, cudaGetMipmappedArrayLevel(&a, c->dir_arrays[dir], level));
+        CK(c, cudaGetMipmappedArrayLevel(&a, c->dir_atlas, level));
         n = c->mip_levels[level].n;
     }
     if (bytes != n * n * n * 4) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_read_array: size mismatch");
     CK(c, cudaStreamSynchronize(c->stream));
     cudaMemcpy3DParms p{};
     p.srcArray = a;
+    if (dir >= 0) p.srcPos = make_cudaPos(0, 0, 2 * (size_t)dir * n);      // the direction's slab inside the atlas level
     p.dstPtr = make_cudaPitchedPtr(host, n * 4, n, n);
     p.extent = make_cudaExtent(n, n, n);
     p.kind = cudaMemcpyDeviceToHost;
@@ -266,13 +267,11 @@ int f184_mode_n_release(f184_ctx* c)
     if (c->rad_tex) cudaDestroyTextureObject(c->rad_tex);
     if (c->rad_surf) cudaDestroySurfaceObject(c->rad_surf);
     if (c->rad_array) cudaFreeArray(c->rad_array);
-    for (int d = 0; d < 6; d++)
-    {
-        if (c->dir_tex[d]) cudaDestroyTextureObject(c->dir_tex[d]);
-        for (int l = 0; l < 12; l++)
-            if (c->dir_surf[d][l]) cudaDestroySurfaceObject(c->dir_surf[d][l]);
-        if (c->dir_arrays[d]) cudaFreeMipmappedArray(c->dir_arrays[d]);
-    }
+    if (c->dir_tex) cudaDestroyTextureObject(c->dir_tex);
+    for (int l = 0; l < 12; l++)
+        if (c->dir_surf[l]) { cudaDestroySurfaceObject(c->dir_surf[l]); c->dir_surf[l] = 0; }
+    if (c->dir_atlas) cudaFreeMipmappedArray(c->dir_atlas);
+    c->dir_tex = 0; c->dir_atlas = nullptr;
     c->rad_tex = 0; c->rad_surf = 0; c->rad_array = nullptr;
     return F184_OK;
 }

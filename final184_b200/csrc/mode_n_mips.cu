@@ -15,7 +15,7 @@
 //     directions from the same tile (the isotropic source is read once).
 //   * the small tail levels (source edge < 64, < 0.1 % of the bytes) use a plain per-thread kernel.
 //   * each output is written twice: to the linear chain (source of the next level's TMA) and through a
-//     surface into the mipmapped 3D arrays the tracer's texture units filter (+12 % write traffic; level 0
+//     surface into the mipmapped 3D atlas the tracer's texture units filter (+12 % write traffic; level 0
 //     is never copied).
 #include <cuda.h>
 
@@ -59,7 +59,7 @@ __device__ __forceinline__ uint32_t reduce_dir(const uint32_t t[2][2][2], int d)
 struct MipOut
 {
     uint32_t* lin[6];
-    cudaSurfaceObject_t surf[6];
+    cudaSurfaceObject_t surf;          // the level's slice of the six-direction atlas (f184_internal.h): direction d at z + 2 d n
 };
 
 // ---- plain kernel: one thread per output texel (tail levels, and the cross-check for the TMA path) ----
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_mips_simple(const uint32_t* __restrict_
         {
             const uint32_t v = reduce_dir(t, d);
             out.lin[d][((size_t)z * n + y) * n + x] = v;
-            surf3Dwrite(v, out.surf[d], x * 4, y, z);
+            surf3Dwrite(v, out.surf, x * 4, y, atlas_z(d, n, z));
         }
     }
 }
@@ -193,7 +193,7 @@ k_mips_tma(const __grid_constant__ CUtensorMap src_map, MipOut out, int n, int i
             if (gx < n && gy < n && gz < n)
             {
                 *reinterpret_cast<uint4*>(out.lin[d] + ((size_t)gz * n + gy) * n + gx) = make_uint4(o[0], o[1], o[2], o[3]);   // 16-byte store
-                surf3Dwrite(make_uint4(o[0], o[1], o[2], o[3]), out.surf[d], gx * 4, gy, gz);   // one 16-byte surface store = 4 texels
+                surf3Dwrite(make_uint4(o[0], o[1], o[2], o[3]), out.surf, gx * 4, gy, atlas_z(d, n, gz));   // one 16-byte surface store = 4 texels
             }
         }
         __syncthreads();                       // everyone is done with this stage's tile
@@ -215,7 +215,7 @@ k_mips_tma(const __grid_constant__ CUtensorMap src_map, MipOut out, int n, int i
 struct BrickMipOut
 {
     uint32_t* lin[3][6];               // level 1..3, six directions, linear chain
-    cudaSurfaceObject_t surf[3][6];
+    cudaSurfaceObject_t surf[3];       // atlas levels 1..3
 };
 constexpr int BRICK_WARPS = 8;
 
@@ -282,7 +282,7 @@ k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ 
                 *reinterpret_cast<uint4*>(&sh1[warp][d][(oz * 4 + oy) * 4]) = v;
                 if (rec) *reinterpret_cast<uint4*>(rec + 512 + d * 64 + (oz * 4 + oy) * 4) = v;
                 *reinterpret_cast<uint4*>(out.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = v;
-                surf3Dwrite(v, out.surf[0][d], gx * 4, gy, gz);
+                surf3Dwrite(v, out.surf[0], gx * 4, gy, atlas_z(d, n1, gz));
             }
         }
         __syncwarp();
@@ -314,7 +314,7 @@ k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ 
             *reinterpret_cast<uint2*>(&sh2[warp][d][(oz * 2 + oy) * 2]) = v;
             if (rec) *reinterpret_cast<uint2*>(rec + 896 + d * 8 + (oz * 2 + oy) * 2) = v;
             *reinterpret_cast<uint2*>(out.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = v;
-            surf3Dwrite(v, out.surf[1][d], gx * 4, gy, gz);
+            surf3Dwrite(v, out.surf[1], gx * 4, gy, atlas_z(d, n2, gz));
         }
         __syncwarp();
         if (lane < 6)
@@ -328,7 +328,7 @@ k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ 
             const uint32_t v = reduce_dir(t, d);
             out.lin[2][d][((size_t)bz * n3 + by) * n3 + bx] = v;
             if (rec) rec[944 + d] = v;
-            surf3Dwrite(v, out.surf[2][d], bx * 4, by, bz);
+            surf3Dwrite(v, out.surf[2], bx * 4, by, atlas_z(d, n3, bz));
         }
         __syncwarp();
     }
@@ -341,7 +341,7 @@ k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ 
 // last CTA to arrive (ticket counter, self-resetting).
 struct TailOut
 {
-    cudaSurfaceObject_t surf[6][12];
+    cudaSurfaceObject_t surf[12];           // atlas level l
     uint64_t level_off[12];                 // texel offset of level l+1, direction 0, inside the chain allocation
     uint32_t level_n[12];
     uint32_t n_levels;
@@ -385,7 +385,7 @@ k_mips_tail(uint32_t* __restrict__ chain, TailOut out, int T, int tiles, unsigne
             b[i] = v;
             const int gx = tx * m + x, gy = ty * m + y, gz = tz * m + z;
             dst[((size_t)gz * n + gy) * n + gx] = v;
-            surf3Dwrite(v, out.surf[d][lvl], gx * 4, gy, gz);
+            surf3Dwrite(v, out.surf[lvl], gx * 4, gy, atlas_z(d, n, gz));
         }
         __syncthreads();
         uint32_t* tmp = a; a = b; b = tmp;
@@ -422,7 +422,7 @@ k_mips_tail(uint32_t* __restrict__ chain, TailOut out, int T, int tiles, unsigne
             for (int e = 0; e < 6; e++)
                 if (e == dd) v = reduce_dir(t, e);
             chain[out.level_off[lvl] + (uint64_t)dd * n * n * n + r] = v;
-            surf3Dwrite(v, out.surf[dd][lvl], x * 4, y, z);
+            surf3Dwrite(v, out.surf[lvl], x * 4, y, atlas_z(dd, n, z));
         }
         __threadfence();
         __syncthreads();
@@ -456,8 +456,7 @@ int f184_mips_tail_n(f184_ctx* c, bool own_stage)
     TailOut to{};
     to.n_levels = c->n_mip_levels;
     for (uint32_t l = 0; l < c->n_mip_levels; l++) { to.level_off[l] = c->mip_levels[l].offset_texels; to.level_n[l] = c->mip_levels[l].n; }
-    for (int d = 0; d < 6; d++)
-        for (uint32_t l = 0; l < c->n_mip_levels; l++) to.surf[d][l] = c->dir_surf[d][l];
+    for (uint32_t l = 0; l < c->n_mip_levels; l++) to.surf[l] = c->dir_surf[l];
     const int n3 = (int)c->mip_levels[2].n, T = std::min(16, n3), tiles = n3 / T;
     if (own_stage)
     {
@@ -493,12 +492,14 @@ int f184_mips_n(f184_ctx* c)
     {   // levels 1-3 from the brick list (F184_FLAG_NO_TMA keeps the all-dense plain path as the cross-check)
         BrickMipOut bo;
         for (int l = 0; l < 3; l++)
+        {
+            bo.surf[l] = c->dir_surf[l];
             for (int d = 0; d < 6; d++)
             {
                 const uint64_t n = c->mip_levels[l].n;
                 bo.lin[l][d] = mips + c->mip_levels[l].offset_texels + (uint64_t)d * n * n * n;
-                bo.surf[l][d] = c->dir_surf[d][l];
             }
+        }
         uint32_t* export_buf = nullptr;
         if (c->cfg.nranks > 1)
         {
@@ -523,11 +524,8 @@ int f184_mips_n(f184_ctx* c)
         const uint32_t* src = iso ? level0 : mips + c->mip_levels[li - 1].offset_texels;
         const uint64_t src_dir_stride = (uint64_t)sn * sn * sn;
         MipOut out;
-        for (int d = 0; d < 6; d++)
-        {
-            out.lin[d] = mips + c->mip_levels[li].offset_texels + (uint64_t)d * n * n * n;
-            out.surf[d] = c->dir_surf[d][li];
-        }
+        out.surf = c->dir_surf[li];
+        for (int d = 0; d < 6; d++) out.lin[d] = mips + c->mip_levels[li].offset_texels + (uint64_t)d * n * n * n;
         if (use_tma && sn >= 64)
         {
             CUtensorMap map;

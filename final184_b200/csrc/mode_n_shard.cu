@@ -63,7 +63,7 @@ struct GatherArgs
     cudaSurfaceObject_t rad_surf;
     uint32_t* rad_lin;
     uint32_t* lin[3][6];
-    cudaSurfaceObject_t surf[3][6];
+    cudaSurfaceObject_t surf[3];       // atlas levels 1..3 (direction d at z + 2 d n)
 };
 
 constexpr int GATHER_WARPS = 8;
@@ -103,19 +103,19 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather_bricks(const Gathe
         {
             const int j = lane + 32 * k, d = j >> 4, r = j & 15, oy = r & 3, oz = r >> 2;
             const int gx = bx * 4, gy = by * 4 + oy, gz = bz * 4 + oz;
-            surf3Dwrite(l1[k], G.surf[0][d], gx * 4, gy, gz);
+            surf3Dwrite(l1[k], G.surf[0], gx * 4, gy, atlas_z(d, n1, gz));
             if (G.write_linear) *reinterpret_cast<uint4*>(G.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = l1[k];
         }
         if (lane < 24)
         {
             const int d = lane >> 2, r = lane & 3, oy = r & 1, oz = r >> 1;
             const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
-            surf3Dwrite(l2, G.surf[1][d], gx * 4, gy, gz);
+            surf3Dwrite(l2, G.surf[1], gx * 4, gy, atlas_z(d, n2, gz));
             if (G.write_linear) *reinterpret_cast<uint2*>(G.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = l2;
         }
         if (lane < 6)
         {
-            surf3Dwrite(l3, G.surf[2][lane], bx * 4, by, bz);
+            surf3Dwrite(l3, G.surf[2], bx * 4, by, atlas_z(lane, n3, bz));
             G.lin[2][lane][((size_t)bz * n3 + by) * n3 + bx] = l3;             // level 3 is the source of the local tail: always
         }
     }
@@ -221,12 +221,14 @@ int f184_gather_n(f184_ctx* c)
     G.rad_lin = img_ptr<uint32_t>(c, F184_SLOT_RADIANCE);
     uint32_t* mips = img_ptr<uint32_t>(c, F184_SLOT_MIPS);
     for (int l = 0; l < 3; l++)
+    {
+        G.surf[l] = c->dir_surf[l];
         for (int d = 0; d < 6; d++)
         {
             const uint64_t n = c->mip_levels[l].n;
             G.lin[l][d] = mips + c->mip_levels[l].offset_texels + (uint64_t)d * n * n * n;
-            G.surf[l][d] = c->dir_surf[d][l];
         }
+    }
     rc = f184_stage_begin(c, F184_STAGE_EXCHANGE);
     if (rc) return rc;
     k_gather_bricks<<<dim3(148, c->cfg.nranks), GATHER_WARPS * 32, 0, c->stream>>>(G);

@@ -10,8 +10,8 @@
 // B200 design
 //   * tile-per-warp: a warp owns an 8x4 pixel tile, so its 32 cones of the same index leave neighbouring
 //     surface points in nearly the same direction and their texel footprints overlap in L1/tex cache.
-//   * all volume reads are hardware-filtered: level 0 is a 3D array (trilinear), levels >= 1 are six
-//     mipmapped 3D arrays sampled with tex3DLod at the NEAREST level (trilinear, point mip filter), so a cone
+//   * all volume reads are hardware-filtered: level 0 is a 3D array (trilinear), levels >= 1 are one
+//     mipmapped 3D array (six directions as z-slabs) sampled with tex3DLod at the NEAREST level (trilinear, point mip filter), so a cone
 //     sample is 3 texture instructions of 8 texels each (direction-weighted x/y/z faces), or 1 while the cone is
 //     thinner than ~1.4 voxels.  ncu on the first version (mip-linear, 16 texels per fetch) showed the kernel at
 //     87.5 % of the TEX data-pipe wavefront peak with a 99.8 % L1 hit rate: the texture pipe, not memory, is
@@ -19,6 +19,8 @@
 //   * early termination: a cone stops at alpha >= 0.95, on leaving the volume or at max distance; the loop
 //     exit reconverges per warp, i.e. the warp leaves as soon as its last lane is done (the vote).
 //   * cone-samples are counted (one warp-aggregated atomic per warp) because Gcone-samples/s is a metric.
+#include <cstdlib>
+
 #include "f184_device.cuh"
 
 namespace {
@@ -27,7 +29,7 @@ struct ConeParams
 {
     M4 InvProj, InvModelView, w2v, prevModelView, prevProjection;
     cudaTextureObject_t level0;
-    cudaTextureObject_t dir[6];
+    cudaTextureObject_t atlas;             // levels >= 1, six directions as z-slabs of one mipmapped 3D array
     const float* depth;
     const uint16_t* normals;
     const uchar4* material;
@@ -48,16 +50,22 @@ __constant__ float kDiffuseDirs[6][3] = {
 __constant__ float kDiffuseW[6] = {0.25f, 0.15f, 0.15f, 0.15f, 0.15f, 0.15f};
 constexpr float kTanHalfDiffuse = 0.57735027f;
 
-__device__ __forceinline__ float4 tex_dir(const ConeParams& P, const float w[3], const int face[3], float qx, float qy, float qz, float lod)
+// Direction-weighted fetch from the six-direction atlas: direction d of every level occupies the normalised z range
+// [d/6, d/6 + 1/12) (f184_internal.h), so a face is a per-cone z offset and all three fetches use ONE warp-uniform texture
+// handle: three independent TEX instructions back to back.  (With one texture object per direction the handle differed
+// per lane and ptxas wrapped every TEX in an R2UR/BRA.U.ANY waterfall loop whose result fed the next one.)
+__device__ __forceinline__ float4 tex_dir(cudaTextureObject_t atlas, const float w[3], const float zoff[3], float qx, float qy, float qz, float lod)
 {
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float z12 = qz * (1.0f / 12.0f);
+    float4 s[3];
 #pragma unroll
     for (int a = 0; a < 3; a++)
-    {
-        if (w[a] == 0.0f) continue;
-        const float4 s = tex3DLod<float4>(P.dir[face[a]], qx, qy, qz, lod);
-        r.x += w[a] * s.x; r.y += w[a] * s.y; r.z += w[a] * s.z; r.w += w[a] * s.w;
-    }
+        s[a] = (w[a] != 0.0f) ? tex3DLod<float4>(atlas, qx, qy, z12 + zoff[a], lod) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 r;
+    r.x = (w[0] * s[0].x + w[1] * s[1].x) + w[2] * s[2].x;
+    r.y = (w[0] * s[0].y + w[1] * s[1].y) + w[2] * s[2].y;
+    r.z = (w[0] * s[0].z + w[1] * s[1].z) + w[2] * s[2].z;
+    r.w = (w[0] * s[0].w + w[1] * s[1].w) + w[2] * s[2].w;
     return r;
 }
 
@@ -71,7 +79,7 @@ __device__ f3 trace_cone(const ConeParams& P, f3 origin, f3 dir, float tan_half,
     const float dl = length3(dv);
     const f3 du = {dv.x / dl, dv.y / dl, dv.z / dl};
     const float w[3] = {du.x * du.x, du.y * du.y, du.z * du.z};
-    const int face[3] = {du.x < 0.0f ? 1 : 0, du.y < 0.0f ? 3 : 2, du.z < 0.0f ? 5 : 4};
+    const float zoff[3] = {du.x < 0.0f ? 1.0f / 6.0f : 0.0f, du.y < 0.0f ? 3.0f / 6.0f : 2.0f / 6.0f, du.z < 0.0f ? 5.0f / 6.0f : 4.0f / 6.0f};
     // normalised volume coordinate of the origin; q(t) = q0 + dv * t (affine)
     const f3 o3 = mul43(P.w2v, origin, 1.0f);
     const f3 q0 = {o3.x * 0.5f + 0.5f, o3.y * 0.5f + 0.5f, o3.z};
@@ -89,7 +97,7 @@ __device__ f3 trace_cone(const ConeParams& P, f3 origin, f3 dir, float tan_half,
         const int L = (int)floorf(lod + 0.5f);
         float4 s;
         if (L <= 0) s = tex3D<float4>(P.level0, qx, qy, qz);
-        else s = tex_dir(P, w, face, qx, qy, qz, fminf((float)(L - 1), P.max_lod));
+        else s = tex_dir(P.atlas, w, zoff, qx, qy, qz, fminf((float)(L - 1), P.max_lod));
         const float k = 1.0f - A;
         acc = {acc.x + k * s.x, acc.y + k * s.y, acc.z + k * s.z};
         A += k * s.w;
@@ -102,7 +110,8 @@ __device__ f3 trace_cone(const ConeParams& P, f3 origin, f3 dir, float tan_half,
 __device__ __forceinline__ float unorm16(uint16_t v) { return (float)v / 65535.0f; }
 __device__ __forceinline__ int wrapn(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
 
-__global__ void __launch_bounds__(128) k_trace_n(const ConeParams P, unsigned long long* __restrict__ sample_counter)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS) k_trace_n(const ConeParams P, unsigned long long* __restrict__ sample_counter)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
@@ -213,7 +222,7 @@ int f184_trace_n(f184_ctx* c, const f184_trace_constants* k)
         P.h = sqrtf((ax * ax + ay * ay) + az * az);
     }
     P.level0 = c->rad_tex;
-    for (int d = 0; d < 6; d++) P.dir[d] = c->dir_tex[d];
+    P.atlas = c->dir_tex;
     P.depth = img_ptr<float>(c, F184_SLOT_DEPTH);
     P.normals = img_ptr<uint16_t>(c, F184_SLOT_NORMALS);
     P.material = img_ptr<uchar4>(c, F184_SLOT_MATERIAL);
@@ -234,7 +243,10 @@ int f184_trace_n(f184_ctx* c, const f184_trace_constants* k)
     if (grid_y)
     {
         dim3 grid((P.W + 15) / 16, grid_y);
-        k_trace_n<<<grid, 128, 0, c->stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+        // two register budgets of the same kernel: 8 CTAs/SM (64 registers) or 7 (72, no spill); F184_TRACE_CTAS=7 selects the latter (A/B knob)
+        static const int min_ctas = [] { const char* e = getenv("F184_TRACE_CTAS"); return e ? atoi(e) : 8; }();
+        if (min_ctas == 7) k_trace_n<7><<<grid, 128, 0, c->stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+        else k_trace_n<8><<<grid, 128, 0, c->stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
         CK_LAUNCH(c);
     }
     return f184_stage_end(c, F184_STAGE_TRACE);
