@@ -1,7 +1,9 @@
 // blur.cu — separable cross-bilateral blur of the indirect buffer (the tail of the trace).
 //
 // Replaces indirect_blurX + indirect_blurY (Foreground/Renderer/MegaPipeline.cpp:270-284):
-// Shader/Lighting/bilateralBlur.inc with DIR = x (blurX.frag) then y (blurY.frag).  13 taps per direction at
+// Shader/Lighting/bilateralBlur.inc, first along y, then along x: the pass the reference names indirect_blurX steps
+// vertically (blurX.frag:5 defines DIR(x) as vec2(0.0, x)) and indirect_blurY horizontally (blurY.frag:5); bilateral
+// weights do not commute, so the shipped order is kept.  13 taps per direction at
 // pixel offsets 0, +-2, +-4, +-6, +-8, +-11, +-15 (`invres = 2/resolution`; the outer taps' half-texel
 // offsets land on texel centres too), weight exp2(-r^2/32 - ((z0 - z)*512)^2), clamp-to-edge sampler.
 #include "f184_device.cuh"
@@ -53,10 +55,10 @@ int f184_blur_impl(f184_ctx* c, const f184_engine_miscs*)
     int rc = f184_stage_begin(c, F184_STAGE_BLUR);
     if (rc) return rc;
     dim3 grid((W + 15) / 16, (H + 7) / 8);
-    BlurParams bx{img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_OUT), img_ptr<float>(c, F184_SLOT_DEPTH), img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_BLUR_X), W, H, 1, 0};
+    BlurParams bx{img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_OUT), img_ptr<float>(c, F184_SLOT_DEPTH), img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_BLUR_X), W, H, 0, 1};
     k_blur<<<grid, 128, 0, c->stream>>>(bx);
     CK_LAUNCH(c);
-    BlurParams by{img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_BLUR_X), img_ptr<float>(c, F184_SLOT_DEPTH), img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_FINAL), W, H, 0, 1};
+    BlurParams by{img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_BLUR_X), img_ptr<float>(c, F184_SLOT_DEPTH), img_ptr<uint16_t>(c, F184_SLOT_INDIRECT_FINAL), W, H, 1, 0};
     k_blur<<<grid, 128, 0, c->stream>>>(by);
     CK_LAUNCH(c);
     return f184_stage_end(c, F184_STAGE_BLUR);

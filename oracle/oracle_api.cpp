@@ -224,6 +224,14 @@ int f184o_sync(f184o_ctx*) { return F184_OK; }
 int f184o_frame_begin(f184o_ctx*) { return F184_OK; }
 int f184o_frame_end(f184o_ctx*) { return F184_OK; }
 int f184o_bind_rands(f184o_ctx* c, const float* r, size_t n) { c->rands = r; c->n_rands = n; return F184_OK; }
+// test hook: the mode R voxel pass runs these programmable stages (the reference's own shader text, compiled into
+// oracle/_ref/libf184_refshaders.so) instead of the restated ones; NULL restores the restatement
+int f184o_debug_set_voxel_stage_hooks(f184o_ctx* c, void* gs, void* ps)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    c->gs_hook = (f184o_voxel_gs_hook)gs; c->ps_hook = (f184o_voxel_ps_hook)ps;
+    return F184_OK;
+}
 int f184o_set_triangle_range(f184o_ctx* c, uint32_t first, uint32_t count) { c->tri_first = first; c->tri_count = count; return F184_OK; }
 int f184o_set_trace_rows(f184o_ctx* c, uint32_t y0, uint32_t y1) { c->row0 = y0; c->row1 = y1; return F184_OK; }
 int f184o_set_trace_tiles(f184o_ctx* c, uint32_t first, uint32_t stride)

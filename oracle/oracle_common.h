@@ -5,11 +5,15 @@
 // CUDA path: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load it.  Nothing under final184_b200/ links, imports or executes it.
 //
-// Parity status: the reference ships no tests, golden vectors or fixtures for this path (SURVEY.md §4,
-// §8(c)) and cannot be built here (no Vulkan/glslc/Lua/SDL2), so the GLSL restatement itself is
-// "parity unpinned".  What IS pinned against the reference run here: camera/view constants (reference
-// Math library, oracle/_ref/ref_math_probe → tests/golden/ref_constants.json) and texture decode
-// (reference stb_image.h, oracle/_ref/stb_decode).
+// Parity status: mode R (the shipped shaders) is PINNED against the reference itself run here — the reference's own
+// shader text is compiled where it lies into oracle/_ref/libf184_refshaders.so (glsl_shim.h, make_ref_shaders.py,
+// ref_shaders.cpp) and oracle_mode_r.cpp reproduces its voxel volume and images bit for bit
+// (tests/test_refshader_pin.py, goldens tests/golden/refshader_*.npz); camera/view constants are pinned by the
+// reference Math library (oracle/_ref/ref_math_probe -> tests/golden/ref_constants.json) and texture decode by the
+// reference stb_image.h (oracle/_ref/stb_decode).  NOT pinned by any reference code, because the reference leaves
+// them to a GLSL compiler / Vulkan driver that is absent here: the items marked "PINNED:" in oracle_mode_r.cpp
+// (rasteriser, texture unit, transcendentals, NaN rules) — and mode N as a whole (the reference has no such stages):
+// for those this oracle is the definition ("parity unpinned").
 //
 // It mirrors the product's C-ABI (include/f184.h) one-to-one with an `f184o_` prefix so the same test
 // code drives both; "device pointers" are host pointers here.
@@ -109,6 +113,22 @@ struct Image
 
 }  // namespace orc
 
+// Programmable stages of the voxel pass as callbacks (see f184o_ctx::gs_hook).  GS: one triangle in, three vertices out.
+// PS: one fragment in; returns 1 if it stored a texel, 0 if it discarded or the store was out of range.
+struct f184o_ps_material
+{
+    float factor[4];
+    uint32_t use_textures;
+    uint32_t tex_w, tex_h, tex_levels;           // 0 levels = no texture bound
+    const uint8_t* const* level_data;            // RGBA8, level l is (w>>l) x (h>>l)
+};
+typedef void (*f184o_voxel_gs_hook)(const float* view16, const float* proj16, const float* model16, const float* pos9,
+                                    const float* nrm9, const float* uv6, float* out_clip12, float* out_nrm9, float* out_uv6,
+                                    uint32_t* out_orientation);
+typedef int (*f184o_voxel_ps_hook)(const float* fragcoord4, const float* normal3, const float* uv2, const float* duvdx2,
+                                   const float* duvdy2, uint32_t orientation, const f184o_ps_material* material,
+                                   uint16_t* voxels, uint32_t grid_n);
+
 struct f184o_ctx
 {
     f184_config cfg{};
@@ -128,6 +148,10 @@ struct f184o_ctx
     uint32_t tile_first = 0, tile_stride = 1;   // of those rows, only 8-row tile rows t with t % stride == first
     const float* rands = nullptr;
     size_t n_rands = 0;
+    // test hook (tests/test_refshader_pin.py): run the reference's own GS / PS text (oracle/_ref/libf184_refshaders.so)
+    // between this file's fixed-function stages instead of the restated stages
+    f184o_voxel_gs_hook gs_hook = nullptr;
+    f184o_voxel_ps_hook ps_hook = nullptr;
     uint64_t counters[F184_COUNTER_COUNT] = {0};
     float stage_ms[F184_STAGE_COUNT] = {0};
 };

@@ -99,30 +99,51 @@ extern "C" int orc_voxelize_r(f184o_ctx* c, const f184_view_constants* cam)
         const uint32_t* id = &c->idx[3 * t];
         const M4& vm = VM[c->tri_model[t]];
         const M4& mm = MM[c->tri_model[t]];
-        // ---- VoxelGS, main.lua:94-115
-        V3 vp[3];
-        for (int i = 0; i < 3; i++)
-        {
-            const float* p = &c->pos[3 * id[i]];
-            V4 q = mul(vm, V4{p[0], p[1], p[2], 1.0f});
-            vp[i] = {q.x, q.y, q.z};
-        }
-        V3 fn = vabs(cross(vp[1] - vp[0], vp[2] - vp[0]));
-        int orient;
-        if (fn.x > fn.y) orient = (fn.x > fn.z) ? 1 : 0;
-        else orient = (fn.y > fn.z) ? 2 : 0;
-        // ---- main.lua:116-141
         VtxOut vo[3];
-        for (int i = 0; i < 3; i++)
+        int orient;
+        if (c->gs_hook)
         {
-            V4 g = mul(Proj, V4{vp[i].x, vp[i].y, vp[i].z, 1.0f});
-            float gx = g.x / g.w, gy = g.y / g.w, gz = g.z / g.w;
-            if (orient == 1) { float nx = gz * 2.0f - 1.0f; float nz = -gx / 2.0f + 0.5f; gx = nx; gz = nz; }
-            else if (orient == 2) { float ny = 1.0f - gz * 2.0f; float nz = gy / 2.0f + 0.5f; gy = ny; gz = nz; }
-            vo[i].cx = gx; vo[i].cy = gy; vo[i].cz = gz;
-            const float* nn = &c->nrm[3 * id[i]];
-            vo[i].n = normalize(mul3(mm, V3{nn[0], nn[1], nn[2]}));
-            vo[i].u = c->uv[2 * id[i]]; vo[i].v = c->uv[2 * id[i] + 1];
+            float pos9[9], nrm9[9], uv6[6], clip[12], on[9], ouv[6];
+            for (int i = 0; i < 3; i++)
+            {
+                memcpy(&pos9[3 * i], &c->pos[3 * id[i]], 12); memcpy(&nrm9[3 * i], &c->nrm[3 * id[i]], 12);
+                memcpy(&uv6[2 * i], &c->uv[2 * id[i]], 8);
+            }
+            uint32_t o = 0;
+            c->gs_hook(cam->ViewMat, cam->ProjMat, &c->model_mats[16 * c->tri_model[t]], pos9, nrm9, uv6, clip, on, ouv, &o);
+            orient = (int)o;
+            for (int i = 0; i < 3; i++)
+            {
+                vo[i].cx = clip[4 * i]; vo[i].cy = clip[4 * i + 1]; vo[i].cz = clip[4 * i + 2];     // w = 1 after the GS's divide
+                vo[i].n = {on[3 * i], on[3 * i + 1], on[3 * i + 2]};
+                vo[i].u = ouv[2 * i]; vo[i].v = ouv[2 * i + 1];
+            }
+        }
+        else
+        {
+            // ---- VoxelGS, main.lua:94-115
+            V3 vp[3];
+            for (int i = 0; i < 3; i++)
+            {
+                const float* p = &c->pos[3 * id[i]];
+                V4 q = mul(vm, V4{p[0], p[1], p[2], 1.0f});
+                vp[i] = {q.x, q.y, q.z};
+            }
+            V3 fn = vabs(cross(vp[1] - vp[0], vp[2] - vp[0]));
+            if (fn.x > fn.y) orient = (fn.x > fn.z) ? 1 : 0;
+            else orient = (fn.y > fn.z) ? 2 : 0;
+            // ---- main.lua:116-141
+            for (int i = 0; i < 3; i++)
+            {
+                V4 g = mul(Proj, V4{vp[i].x, vp[i].y, vp[i].z, 1.0f});
+                float gx = g.x / g.w, gy = g.y / g.w, gz = g.z / g.w;
+                if (orient == 1) { float nx = gz * 2.0f - 1.0f; float nz = -gx / 2.0f + 0.5f; gx = nx; gz = nz; }
+                else if (orient == 2) { float ny = 1.0f - gz * 2.0f; float nz = gy / 2.0f + 0.5f; gy = ny; gz = nz; }
+                vo[i].cx = gx; vo[i].cy = gy; vo[i].cz = gz;
+                const float* nn = &c->nrm[3 * id[i]];
+                vo[i].n = normalize(mul3(mm, V3{nn[0], nn[1], nn[2]}));
+                vo[i].u = c->uv[2 * id[i]]; vo[i].v = c->uv[2 * id[i] + 1];
+            }
         }
         // ---- fixed-function rasteriser (viewport N x N, depth range [0,1], no cull, 1 sample)
         // PINNED: viewport transform x_f = x_ndc*N/2 + N/2, snap to 1/256 px, integer edge functions,
@@ -193,6 +214,22 @@ extern "C" int orc_voxelize_r(f184o_ctx* c, const f184_view_constants* cam)
                 float v = (A.v * b0 + B.v * b1) + C.v * b2;
                 V3 n = {(A.n.x * b0 + B.n.x * b1) + C.n.x * b2, (A.n.y * b0 + B.n.y * b1) + C.n.y * b2,
                         (A.n.z * b0 + B.n.z * b1) + C.n.z * b2};
+                if (c->ps_hook)
+                {
+                    f184o_ps_material pm{};
+                    memcpy(pm.factor, mat.factor, 16); pm.use_textures = mat.use_textures;
+                    const uint8_t* lv[16] = {nullptr};
+                    if (tex)
+                    {
+                        pm.tex_w = tex->w; pm.tex_h = tex->h; pm.tex_levels = (uint32_t)std::min<size_t>(16, tex->levels.size());
+                        for (uint32_t l = 0; l < pm.tex_levels; l++) lv[l] = tex->levels[l].data();
+                        pm.level_data = lv;
+                    }
+                    const float fc[4] = {(float)px + 0.5f, (float)py + 0.5f, z, 1.0f}, nn[3] = {n.x, n.y, n.z}, uvv[2] = {u, v};
+                    const float ddx[2] = {dudx, dvdx}, ddy[2] = {dudy, dvdy};
+                    frags += (uint64_t)c->ps_hook(fc, nn, uvv, ddx, ddy, (uint32_t)orient, &pm, vox, N);
+                    continue;
+                }
                 // ---- BasicMaterial, main.lua:188-205
                 V4 base;
                 if (!mat.use_textures) base = {mat.factor[0], mat.factor[1], mat.factor[2], mat.factor[3]};
@@ -664,10 +701,13 @@ extern "C" int f184o_blur_indirect(f184o_ctx* c, const f184_engine_miscs* miscs)
     for (int s : {F184_SLOT_DEPTH, F184_SLOT_INDIRECT_OUT, F184_SLOT_INDIRECT_BLUR_X, F184_SLOT_INDIRECT_FINAL})
     { int rc = ensure_image(c, s); if (rc) return rc; }
     const uint32_t W = c->cfg.width, H = c->cfg.height;
+    // The pass the reference NAMES indirect_blurX steps along y — blurX.frag:5 defines DIR(x) as vec2(0.0, x) — and
+    // indirect_blurY steps along x (blurY.frag:5).  The bilateral weights do not commute, so the order is kept as
+    // shipped: vertical first, then horizontal (found by running the reference's shader text, tests/test_refshader_pin.py).
     blur_pass(image_ptr<uint16_t>(c, F184_SLOT_INDIRECT_OUT), image_ptr<float>(c, F184_SLOT_DEPTH),
-              image_ptr<uint16_t>(c, F184_SLOT_INDIRECT_BLUR_X), W, H, 1, 0);
+              image_ptr<uint16_t>(c, F184_SLOT_INDIRECT_BLUR_X), W, H, 0, 1);
     blur_pass(image_ptr<uint16_t>(c, F184_SLOT_INDIRECT_BLUR_X), image_ptr<float>(c, F184_SLOT_DEPTH),
-              image_ptr<uint16_t>(c, F184_SLOT_INDIRECT_FINAL), W, H, 0, 1);
+              image_ptr<uint16_t>(c, F184_SLOT_INDIRECT_FINAL), W, H, 1, 0);
     c->stage_ms[F184_STAGE_BLUR] = (float)(now_ms() - t0);
     return F184_OK;
 }

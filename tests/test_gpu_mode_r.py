@@ -106,3 +106,20 @@ def test_detmath_device_equals_host(cuda_lib, oracle_lib):
         assert cuda_lib.debug_detmath(g.h, op, x.ctypes.data, y.ctypes.data, a.ctypes.data, x.size) == 0
         oracle_lib.dll.f184o_debug_detmath(C.c_uint32(op), C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), C.c_void_p(b.ctypes.data), C.c_size_t(x.size))
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"op {op}: {np.count_nonzero(a.view(np.uint32) != b.view(np.uint32))} differ"
+
+
+@pytest.mark.parametrize("case", ["atrium", "sponza"])
+def test_cuda_matches_reference_shader_text_golden(cuda_lib, case):
+    """The CUDA path against what the reference's OWN shader text computes (tests/golden/refshader_<case>.npz, made by
+    tools/gen_refshader_golden.py from oracle/_ref/libf184_refshaders.so — see tests/test_refshader_pin.py): voxel volume,
+    fragment count, lighting_indirect (first and temporal frame), GTAO + its blur, both bilateral passes — bit for bit.
+    The oracle is not in this comparison at all."""
+    import refshader as R
+    if not R.case_available(case):
+        pytest.skip(f"{case}: scene not staged")
+    sc, cams_, fis = R.case_inputs(case)
+    golden = R.unpack_golden(case)
+    assert R.input_digest(sc, fis) == golden["input_sha256"], "the inputs differ from those the golden file was made from"
+    got = R.run_library(cuda_lib, sc, cams_, fis)
+    assert int(got["fragments"]) == int(golden["fragments"]) > 10000
+    assert R.compare(got, golden) == []

@@ -1,7 +1,8 @@
 """The CPU oracle, reference-faithful mode, against KNOWN ANSWERS worked out by hand from the reference's shader text
 (Pipelang/Internal/main.lua:83-144 VoxelGS, :242-275 VoxelPS) — independent of the oracle's code —
-plus the properties the host logic relies on.  The reference ships no golden vectors for this path ("parity unpinned",
-oracle/oracle_common.h); these hand cases are the pin we can have."""
+plus the properties the host logic relies on.  The reference ships no golden vectors for this path; the bit-for-bit
+pin against the reference's own shader text is tests/test_refshader_pin.py, and these hand cases pin what that cannot:
+the fixed-function rasteriser between VoxelGS and VoxelPS, which the reference leaves to the Vulkan driver."""
 import numpy as np
 import pytest
 
