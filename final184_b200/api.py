@@ -146,6 +146,7 @@ _SIGS = {
     "inject": (C.c_int, [C.c_void_p, C.POINTER(SunC), C.POINTER(ExtendedMatricesC)]),
     "build_mips": (C.c_int, [C.c_void_p]),
     "trace_indirect": (C.c_int, [C.c_void_p, C.POINTER(TraceConstantsC)]),
+    "trace_views": (C.c_int, [C.c_void_p, C.POINTER(TraceConstantsC), C.c_uint32, C.c_uint32, C.c_uint32]),
     "gtao": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC)]),
     "blur_indirect": (C.c_int, [C.c_void_p, C.POINTER(EngineMiscsC)]),
     "copy_indirect_to_history": (C.c_int, [C.c_void_p]),
@@ -338,6 +339,12 @@ class VoxelGI:
 
     def trace_indirect(self, k: TraceConstantsC):
         self._ck(self.lib.trace_indirect(self.h, C.byref(k)), "trace_indirect")
+
+    def trace_views(self, ks, view_height, first=0, count=None):
+        """Probe batch: the images hold len(ks) views of `view_height` rows stacked top to bottom; view v uses ks[v]."""
+        arr = (TraceConstantsC * len(ks))(*ks)
+        count = len(ks) - first if count is None else count
+        self._ck(self.lib.trace_views(self.h, arr, view_height, first, count), "trace_views")
 
     def gtao(self, view: S.ViewConstants | ViewConstantsC):
         v = view if isinstance(view, ViewConstantsC) else view_constants_c(view)

@@ -289,6 +289,12 @@ void f184_destroy(f184_ctx* c)
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->vox_stream) cudaStreamDestroy(c->vox_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    for (int i = 0; i < 4; i++)
+    {
+        if (c->view_streams[i]) cudaStreamDestroy(c->view_streams[i]);
+        if (c->ev_view_done[i]) cudaEventDestroy(c->ev_view_done[i]);
+    }
+    if (c->ev_view_fork) cudaEventDestroy(c->ev_view_fork);
     for (int i = 0; i < 2; i++)
     {
         if (c->rb_stage[i]) cudaFree(c->rb_stage[i]);
@@ -729,6 +735,13 @@ int f184_trace_indirect(f184_ctx* c, const f184_trace_constants* k)
     if (!c || !k) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "trace_indirect: null argument");
     CK(c, cudaSetDevice(c->cfg.device));
     return c->cfg.mode == F184_MODE_REFERENCE ? f184_trace_r(c, k) : f184_trace_n(c, k);
+}
+int f184_trace_views(f184_ctx* c, const f184_trace_constants* constants, uint32_t view_height, uint32_t first, uint32_t count)
+{
+    if (!c || !constants) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "trace_views: null argument");
+    if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_UNIMPLEMENTED, "trace_views: north-star mode only");
+    CK(c, cudaSetDevice(c->cfg.device));
+    return f184_trace_views_n(c, constants, view_height, first, count);
 }
 int f184_gtao(f184_ctx* c, const f184_view_constants* view)
 {

@@ -63,6 +63,9 @@ struct f184_ctx
     cudaStream_t vox_stream = nullptr;
     cudaEvent_t ev_vox_done = nullptr, ev_consumed = nullptr;
     bool vox_pending = false, vox_started = false;
+    // probe batches (f184_trace_views): independent views round-robin over a few streams, joined back into the pass stream
+    cudaStream_t view_streams[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_view_done[4] = {nullptr, nullptr, nullptr, nullptr}, ev_view_fork = nullptr;
     // asynchronous read-backs (f184_readback_async): device-side snapshot on the pass stream, PCIe copy on d2h_stream
     cudaStream_t d2h_stream = nullptr;
     void* rb_stage[2] = {nullptr, nullptr};
@@ -193,6 +196,8 @@ int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam);
 int f184_inject_n(f184_ctx* c, const f184_sun* sun, const f184_extended_matrices* m);
 int f184_mips_n(f184_ctx* c);
 int f184_trace_n(f184_ctx* c, const f184_trace_constants* k);
+int f184_trace_views_n(f184_ctx* c, const f184_trace_constants* ks, uint32_t view_h, uint32_t first, uint32_t count);
+#define F184_VIEW_STREAMS 4
 int f184_mode_n_release(f184_ctx* c);
 int f184_mode_n_alloc(f184_ctx* c);
 int f184_normalise_n(f184_ctx* c);

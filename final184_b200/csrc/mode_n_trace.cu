@@ -38,6 +38,7 @@ struct ConeParams
     float h, max_dist, exposure, max_lod;
     f3 cam;
     uint32_t W, H, y0, y1, tile0, tile_stride;
+    uint32_t vy0, vh;                      // view window: rows [vy0, vy0 + vh) are one view (the whole image unless f184_trace_views)
 };
 
 __constant__ float kDiffuseDirs[6][3] = {
@@ -119,8 +120,8 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_trace_n(const ConeParams P, u
     unsigned int samples = 0;
     if (x < P.W && y < P.y1)
     {
-        const uint32_t W = P.W, H = P.H;
-        const float uvx = ((float)x + 0.5f) / (float)W, uvy = ((float)y + 0.5f) / (float)H;
+        const uint32_t W = P.W, H = P.vh;
+        const float uvx = ((float)x + 0.5f) / (float)W, uvy = ((float)(y - P.vy0) + 0.5f) / (float)P.vh;
         const float depth = __ldg(P.depth + (size_t)y * W + x);
         const f4 cp = mul44(P.InvProj, f4{uvx * 2.0f - 1.0f, uvy * 2.0f - 1.0f, depth, 1.0f});
         const f3 cspos = {cp.x / cp.w, cp.y / cp.w, cp.z / cp.w};
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_trace_n(const ConeParams P, u
                 const float x0f = floorf(fx), y0f = floorf(fy);
                 const float wx = fx - x0f, wy = fy - y0f;
                 const int xi0 = dm_f2i(x0f), yi0 = dm_f2i(y0f);
-                const int xa = wrapn(xi0, (int)W), xb = wrapn(xi0 + 1, (int)W), ya = wrapn(yi0, (int)H), yb = wrapn(yi0 + 1, (int)H);
+                const int xa = wrapn(xi0, (int)W), xb = wrapn(xi0 + 1, (int)W), ya = (int)P.vy0 + wrapn(yi0, (int)H), yb = (int)P.vy0 + wrapn(yi0 + 1, (int)H);
                 const ushort4 h00 = __ldg(reinterpret_cast<const ushort4*>(P.hist) + (size_t)ya * W + xa);
                 const ushort4 h10 = __ldg(reinterpret_cast<const ushort4*>(P.hist) + (size_t)ya * W + xb);
                 const ushort4 h01 = __ldg(reinterpret_cast<const ushort4*>(P.hist) + (size_t)yb * W + xa);
@@ -198,15 +199,9 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_trace_n(const ConeParams P, u
 
 }  // namespace
 
-int f184_trace_n(f184_ctx* c, const f184_trace_constants* k)
+// parameter block of one view; window = rows [vy0, vy0 + vh)
+static int trace_params(f184_ctx* c, const f184_trace_constants* k, uint32_t vy0, uint32_t vh, ConeParams& P)
 {
-    for (int s : {F184_SLOT_DEPTH, F184_SLOT_NORMALS, F184_SLOT_MATERIAL, F184_SLOT_INDIRECT_OUT, F184_SLOT_INDIRECT_HISTORY})
-    {
-        int rc = f184_ensure_image(c, s);
-        if (rc) return rc;
-    }
-    if (!c->rad_array) return f184_fail(c, F184_ERR_NOT_READY, "trace: call f184_inject and f184_build_mips first");
-    ConeParams P{};
     memcpy(P.InvProj.m, k->view.InvProj, 64);
     memcpy(P.InvModelView.m, k->ext.InvModelView, 64);
     M4 vp, vv;
@@ -233,21 +228,88 @@ int f184_trace_n(f184_ctx* c, const f184_trace_constants* k)
     P.max_lod = (float)(c->n_mip_levels - 1);
     P.cam = {P.InvModelView.m[12], P.InvModelView.m[13], P.InvModelView.m[14]};
     P.W = c->cfg.width; P.H = c->cfg.height;
+    P.vy0 = vy0; P.vh = vh;
+    return F184_OK;
+}
+
+static int trace_launch(f184_ctx* c, const ConeParams& P, uint32_t grid_y, cudaStream_t stream)
+{
+    dim3 grid((P.W + 15) / 16, grid_y);
+    // two register budgets of the same kernel: 8 CTAs/SM (64 registers) or 7 (72, no spill); F184_TRACE_CTAS=7 selects the latter (A/B knob)
+    static const int min_ctas = [] { const char* e = getenv("F184_TRACE_CTAS"); return e ? atoi(e) : 8; }();
+    if (min_ctas == 7) k_trace_n<7><<<grid, 128, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+    else k_trace_n<8><<<grid, 128, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+    CK_LAUNCH(c);
+    return F184_OK;
+}
+
+static int trace_check(f184_ctx* c)
+{
+    for (int s : {F184_SLOT_DEPTH, F184_SLOT_NORMALS, F184_SLOT_MATERIAL, F184_SLOT_INDIRECT_OUT, F184_SLOT_INDIRECT_HISTORY})
+    {
+        int rc = f184_ensure_image(c, s);
+        if (rc) return rc;
+    }
+    if (!c->rad_array) return f184_fail(c, F184_ERR_NOT_READY, "trace: call f184_inject and f184_build_mips first");
+    return F184_OK;
+}
+
+int f184_trace_n(f184_ctx* c, const f184_trace_constants* k)
+{
+    int rc = trace_check(c);
+    if (rc) return rc;
+    ConeParams P{};
+    trace_params(c, k, 0, c->cfg.height, P);
     const uint32_t grid_y = f184_trace_tiles(c, P.H, &P.y0, &P.y1, &P.tile0, &P.tile_stride);
     if (P.tile_stride > 1 && (P.y0 & 7)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "trace: row range must start on a multiple of 8 when tiles are interleaved");
-    int rc = f184_stage_begin(c, F184_STAGE_TRACE);
+    rc = f184_stage_begin(c, F184_STAGE_TRACE);
     if (rc) return rc;
     if (k->reset_history)
         CK(c, cudaMemsetAsync(c->img[F184_SLOT_INDIRECT_HISTORY].ptr, 0, c->img[F184_SLOT_INDIRECT_HISTORY].desc.size_bytes, c->stream));
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_MARCH_STEPS, 0, 8, c->stream));
-    if (grid_y)
+    if (grid_y && (rc = trace_launch(c, P, grid_y, c->stream))) return rc;
+    return f184_stage_end(c, F184_STAGE_TRACE);
+}
+
+// Probe batch (BASELINE configs[4]; f184_trace_views in f184.h): the images hold H / view_h views stacked top to bottom;
+// view v = rows [v * view_h, (v + 1) * view_h), traced with ks[v].  Views are independent (disjoint rows of every image,
+// one shared read-only volume), so they go round-robin onto a few internal streams: the ragged tail of one view's grid
+// (a 512 x 512 view is 1.7 waves of CTAs) is filled by the head of the next instead of idling the SMs.
+int f184_trace_views_n(f184_ctx* c, const f184_trace_constants* ks, uint32_t view_h, uint32_t first, uint32_t count)
+{
+    int rc = trace_check(c);
+    if (rc) return rc;
+    const uint32_t H = c->cfg.height;
+    if (view_h == 0 || H % view_h != 0 || (uint64_t)(first + (uint64_t)count) * view_h > H)
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "trace_views: %u views of %u rows from view %u do not fit %u rows", count, view_h, first, H);
+    if (!c->view_streams[0])
+        for (int i = 0; i < F184_VIEW_STREAMS; i++)
+        {
+            CK(c, cudaStreamCreateWithFlags(&c->view_streams[i], cudaStreamNonBlocking));
+            CK(c, cudaEventCreateWithFlags(&c->ev_view_done[i], cudaEventDisableTiming));
+        }
+    if (!c->ev_view_fork) CK(c, cudaEventCreateWithFlags(&c->ev_view_fork, cudaEventDisableTiming));
+    rc = f184_stage_begin(c, F184_STAGE_TRACE);
+    if (rc) return rc;
+    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_MARCH_STEPS, 0, 8, c->stream));
+    CK(c, cudaEventRecord(c->ev_view_fork, c->stream));
+    const int ns = count < (uint32_t)F184_VIEW_STREAMS ? (int)count : F184_VIEW_STREAMS;
+    for (int i = 0; i < ns; i++) CK(c, cudaStreamWaitEvent(c->view_streams[i], c->ev_view_fork, 0));
+    const size_t row_bytes = (size_t)c->cfg.width * 8;
+    for (uint32_t v = first; v < first + count; v++)
     {
-        dim3 grid((P.W + 15) / 16, grid_y);
-        // two register budgets of the same kernel: 8 CTAs/SM (64 registers) or 7 (72, no spill); F184_TRACE_CTAS=7 selects the latter (A/B knob)
-        static const int min_ctas = [] { const char* e = getenv("F184_TRACE_CTAS"); return e ? atoi(e) : 8; }();
-        if (min_ctas == 7) k_trace_n<7><<<grid, 128, 0, c->stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
-        else k_trace_n<8><<<grid, 128, 0, c->stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
-        CK_LAUNCH(c);
+        cudaStream_t st = c->view_streams[(v - first) % F184_VIEW_STREAMS];
+        ConeParams P{};
+        trace_params(c, &ks[v], v * view_h, view_h, P);
+        P.y0 = v * view_h; P.y1 = P.y0 + view_h; P.tile0 = 0; P.tile_stride = 1;
+        if (ks[v].reset_history)
+            CK(c, cudaMemsetAsync(img_ptr<uint8_t>(c, F184_SLOT_INDIRECT_HISTORY) + (size_t)P.y0 * row_bytes, 0, (size_t)view_h * row_bytes, st));
+        if ((rc = trace_launch(c, P, (view_h + 7) / 8, st))) return rc;
+    }
+    for (int i = 0; i < ns; i++)
+    {
+        CK(c, cudaEventRecord(c->ev_view_done[i], c->view_streams[i]));
+        CK(c, cudaStreamWaitEvent(c->stream, c->ev_view_done[i], 0));
     }
     return f184_stage_end(c, F184_STAGE_TRACE);
 }

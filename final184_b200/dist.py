@@ -147,7 +147,7 @@ class ShardedVoxelGI:
         return (f"{self.nranks} GPUs: triangle ranges balanced by projected area, fragments reduced into the Z-slab owner's accumulators by peer "
                 f"atomics over NVLink, slab-local normalise/inject/mips, peer gather of the listed bricks, trace split by interleaved 8-row tiles")
 
-    def frame(self, voxel_cam, k):
+    def frame(self, voxel_cam, k, trace=True):
         c = self.ctx
         if self.mode in ("single", "replicate"):
             c.voxelize(voxel_cam)
@@ -174,7 +174,8 @@ class ShardedVoxelGI:
             c.normalise()
             c.inject(k)
             c.build_mips()
-        c.trace_indirect(k)
+        if trace:
+            c.trace_indirect(k)
 
     def gather_image(self):
         """The full traced image on every rank (a consumer that wants one image; not part of the frame)."""
@@ -199,3 +200,46 @@ class ShardedVoxelGI:
 
     def close(self):
         self.ctx.close()
+
+
+class ProbeBatch:
+    """BASELINE configs[4]: `n_views` square probe views cone-traced against one volume, whole views per rank
+    (view_ranges) — no exchange for the views.  Each rank's context holds ITS views stacked top to bottom
+    (f184_trace_views); the volume is built by any ShardedVoxelGI schedule ("replicate": every rank builds it;
+    "slab": built once across the box and gathered; "host": the CPU-test stand-in)."""
+
+    def __init__(self, grid_n, view_size, n_views, shadow_res=2048, device=0, rank=0, nranks=1, scene=None, voxel_cam=None,
+                 volume_mode=None, lib=None, flags=0):
+        self.rank, self.nranks, self.n_views, self.view_size = rank, nranks, n_views, view_size
+        self.v0, self.v1 = view_ranges(n_views, nranks)[rank]
+        self.local = self.v1 - self.v0
+        mode = volume_mode or ("replicate" if nranks > 1 else None)
+        self.gi = ShardedVoxelGI(grid_n, view_size, view_size * max(self.local, 1), shadow_res=shadow_res, device=device, rank=rank,
+                                 nranks=nranks, scene=scene, mode=mode, lib=lib, voxel_cam=voxel_cam, flags=flags)
+        self.ctx = self.gi.ctx
+
+    def upload_views(self, per_view_inputs, shadow):
+        """per_view_inputs: one dict(depth, normals, material) per view of the WHOLE batch (indexed by global view);
+        only this rank's views are stacked and uploaded."""
+        mine = per_view_inputs[self.v0:self.v1]
+        if mine:
+            for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_MATERIAL, "material")):
+                self.ctx.upload(slot, np.ascontiguousarray(np.concatenate([fi[key] for fi in mine], axis=0)))
+        self.ctx.upload(A.SLOT_SHADOW, shadow)
+
+    def frame(self, voxel_cam, ks):
+        """ks: trace constants of every view of the batch (global index).  Volume once, then this rank's views."""
+        self.gi.frame(voxel_cam, ks[0], trace=False)
+        if self.local:
+            self.ctx.trace_views(list(ks[self.v0:self.v1]), self.view_size)
+
+    def own_views(self):
+        """(global view index, image) for each of this rank's views"""
+        if not self.local:
+            return []
+        img = self.ctx.readback(A.SLOT_INDIRECT_OUT)
+        s = self.view_size
+        return [(self.v0 + i, img[i * s:(i + 1) * s].copy()) for i in range(self.local)]
+
+    def close(self):
+        self.gi.close()

@@ -268,6 +268,13 @@ int f184_inject(f184_ctx* ctx, const f184_sun* sun, const f184_extended_matrices
 int f184_build_mips(f184_ctx* ctx);
 /* lighting_indirect pass, MegaPipeline.cpp:252-268 (Shader/Lighting/indirect.frag). */
 int f184_trace_indirect(f184_ctx* ctx, const f184_trace_constants* constants);
+/* Probe batch (BASELINE.json configs[4]: many views traced against one volume; the reference has one camera,
+ * App/MainBehaviour.cpp:26-32).  The context's W x H images hold H / view_height views stacked top to bottom: view v is
+ * rows [v*view_height, (v+1)*view_height) of DEPTH / NORMALS / MATERIAL / INDIRECT_OUT / INDIRECT_HISTORY and is traced
+ * exactly as f184_trace_indirect would trace a W x view_height image with constants[v] (own camera, own history rows).
+ * Views [first, first+count) are traced; `constants` is indexed by v.  North-star mode only.  Across GPUs a batch is
+ * partitioned by whole views (each rank's context holds its own views); no exchange is involved. */
+int f184_trace_views(f184_ctx* ctx, const f184_trace_constants* constants, uint32_t view_height, uint32_t first, uint32_t count);
 /* gtao_visibility + gtao_blur, MegaPipeline.cpp:225-239 (Shader/GTAO/gtao.frag, blur.frag). */
 int f184_gtao(f184_ctx* ctx, const f184_view_constants* view);
 /* indirect_blurX + indirect_blurY, MegaPipeline.cpp:270-284 (Shader/Lighting/bilateralBlur.inc). */

@@ -269,6 +269,7 @@ int orc_normalise_n(f184o_ctx*);
 int orc_inject_n(f184o_ctx*, const f184_sun*, const f184_extended_matrices*);
 int orc_mips_n(f184o_ctx*);
 int orc_trace_n(f184o_ctx*, const f184_trace_constants*);
+int orc_trace_views_n(f184o_ctx*, const f184_trace_constants*, uint32_t, uint32_t, uint32_t);
 
 int f184o_voxelize(f184o_ctx* c, const f184_view_constants* cam)
 {
@@ -302,6 +303,12 @@ int f184o_trace_indirect(f184o_ctx* c, const f184_trace_constants* k)
 {
     if (!c || !k) return F184_ERR_INVALID_ARGUMENT;
     return c->cfg.mode == F184_MODE_REFERENCE ? orc_trace_r(c, k) : orc_trace_n(c, k);
+}
+int f184o_trace_views(f184o_ctx* c, const f184_trace_constants* ks, uint32_t view_height, uint32_t first, uint32_t count)
+{
+    if (!c || !ks) return F184_ERR_INVALID_ARGUMENT;
+    if (c->cfg.mode != F184_MODE_NORTHSTAR) { c->err = "trace_views: north-star mode only"; return F184_ERR_UNIMPLEMENTED; }
+    return orc_trace_views_n(c, ks, view_height, first, count);
 }
 
 }  // extern "C"

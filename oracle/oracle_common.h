@@ -146,6 +146,8 @@ struct f184o_ctx
     uint32_t tri_first = 0, tri_count = 0xffffffffu;
     uint32_t row0 = 0, row1 = 0xffffffffu;
     uint32_t tile_first = 0, tile_stride = 1;   // of those rows, only 8-row tile rows t with t % stride == first
+    uint32_t view_y0 = 0, view_h = 0;           // f184o_trace_views: rows [view_y0, view_y0 + view_h) are one view (0 = whole image)
+    bool keep_samples = false;                   // f184o_trace_views: the cone-sample counter accumulates over the views
     const float* rands = nullptr;
     size_t n_rands = 0;
     // test hook (tests/test_refshader_pin.py): run the reference's own GS / PS text (oracle/_ref/libf184_refshaders.so)

@@ -598,8 +598,10 @@ extern "C" int orc_trace_n(f184o_ctx* c, const f184_trace_constants* k)
     const uint8_t* material = image_ptr<uint8_t>(c, F184_SLOT_MATERIAL);
     uint16_t* hist = image_ptr<uint16_t>(c, F184_SLOT_INDIRECT_HISTORY);
     uint16_t* out = image_ptr<uint16_t>(c, F184_SLOT_INDIRECT_OUT);
-    if (k->reset_history) memset(hist, 0, (size_t)W * H * 8);
-    const uint32_t y0 = c->row0, y1 = std::min(c->row1, H);
+    // view window (f184o_trace_views): the view's rows are an image of their own — uv, history addressing and history reset
+    const uint32_t vy0 = c->view_h ? c->view_y0 : 0, vh = c->view_h ? c->view_h : H;
+    if (k->reset_history) memset(hist + (size_t)4 * W * vy0, 0, (size_t)W * vh * 8);
+    const uint32_t y0 = c->view_h ? vy0 : c->row0, y1 = c->view_h ? vy0 + vh : std::min(c->row1, H);
     uint64_t total = 0;
     // camera position in world space = InvModelView * (0,0,0,1)
     const V3 cam = {InvModelView.m[12], InvModelView.m[13], InvModelView.m[14]};
@@ -607,12 +609,12 @@ extern "C" int orc_trace_n(f184o_ctx* c, const f184_trace_constants* k)
 #pragma omp parallel for schedule(dynamic, 2) reduction(+ : total)
     for (int64_t y = y0; y < (int64_t)y1; y++)
     {
-        if ((uint32_t)(y >> 3) % c->tile_stride != c->tile_first) continue;      // tile rows interleaved over the ranks
+        if (!c->view_h && (uint32_t)(y >> 3) % c->tile_stride != c->tile_first) continue;      // tile rows interleaved over the ranks
         ConeCtx C = C0;
         C.samples = 0;
         for (uint32_t x = 0; x < W; x++)
         {
-            const float uvx = ((float)x + 0.5f) / (float)W, uvy = ((float)y + 0.5f) / (float)H;
+            const float uvx = ((float)x + 0.5f) / (float)W, uvy = ((float)(y - vy0) + 0.5f) / (float)vh;
             const float depth = depthp[(size_t)y * W + x];
             V4 cp = mul(InvProj, V4{uvx * 2.0f - 1.0f, uvy * 2.0f - 1.0f, depth, 1.0f});
             V3 cspos = {cp.x / cp.w, cp.y / cp.w, cp.z / cp.w};
@@ -666,11 +668,11 @@ extern "C" int orc_trace_n(f184o_ctx* c, const f184_trace_constants* k)
             ru = ru * 0.5f + 0.5f; rv = rv * 0.5f + 0.5f;
             if (dm_clamp(ru, 0.0f, 1.0f) == ru && dm_clamp(rv, 0.0f, 1.0f) == rv)
             {
-                float fx = ru * (float)W - 0.5f, fy = rv * (float)H - 0.5f;
+                float fx = ru * (float)W - 0.5f, fy = rv * (float)vh - 0.5f;
                 float x0f = floorf(fx), y0f = floorf(fy);
                 float wx = fx - x0f, wy = fy - y0f;
                 int xi0 = dm_f2i(x0f), yi0 = dm_f2i(y0f);
-                int xa = wrapi(xi0, (int)W), xb = wrapi(xi0 + 1, (int)W), ya = wrapi(yi0, (int)H), yb = wrapi(yi0 + 1, (int)H);
+                int xa = wrapi(xi0, (int)W), xb = wrapi(xi0 + 1, (int)W), ya = (int)vy0 + wrapi(yi0, (int)vh), yb = (int)vy0 + wrapi(yi0 + 1, (int)vh);
                 float prev[4];
                 for (int ch = 0; ch < 4; ch++)
                 {
@@ -686,7 +688,24 @@ extern "C" int orc_trace_n(f184o_ctx* c, const f184_trace_constants* k)
         }
         total += C.samples;
     }
-    c->counters[F184_COUNTER_MARCH_STEPS] = total;
-    c->stage_ms[F184_STAGE_TRACE] = (float)(now_ms() - t0);
+    c->counters[F184_COUNTER_MARCH_STEPS] = (c->keep_samples ? c->counters[F184_COUNTER_MARCH_STEPS] : 0) + total;
+    c->stage_ms[F184_STAGE_TRACE] = (c->keep_samples ? c->stage_ms[F184_STAGE_TRACE] : 0.0f) + (float)(now_ms() - t0);
     return F184_OK;
+}
+
+// f184_trace_views (include/f184.h): view v = rows [v*view_h, (v+1)*view_h), traced with ks[v]
+extern "C" int orc_trace_views_n(f184o_ctx* c, const f184_trace_constants* ks, uint32_t view_h, uint32_t first, uint32_t count)
+{
+    const uint32_t H = c->cfg.height;
+    if (view_h == 0 || H % view_h != 0 || (uint64_t)(first + (uint64_t)count) * view_h > H) return F184_ERR_INVALID_ARGUMENT;
+    c->counters[F184_COUNTER_MARCH_STEPS] = 0;
+    c->stage_ms[F184_STAGE_TRACE] = 0.0f;
+    int rc = F184_OK;
+    for (uint32_t v = first; v < first + count && rc == F184_OK; v++)
+    {
+        c->view_y0 = v * view_h; c->view_h = view_h; c->keep_samples = true;
+        rc = orc_trace_n(c, &ks[v]);
+    }
+    c->view_y0 = 0; c->view_h = 0; c->keep_samples = false;
+    return rc;
 }

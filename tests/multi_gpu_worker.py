@@ -9,6 +9,7 @@ import torch.distributed as dist
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
 from final184_b200 import api as A, dist as D, scene as S   # noqa: E402
 from final184_b200.fixture import frame_inputs               # noqa: E402
 
@@ -54,6 +55,31 @@ def main():
         dist.barrier()
     frags = torch.tensor([float(g.ctx.counter(A.COUNTER_FRAGMENTS))], device=f"cuda:{local}")
     dist.all_reduce(frags)
+    # BASELINE configs[4]: a probe batch partitioned by whole views; the volume comes from the slab schedule, each rank traces
+    # its own views (f184_trace_views) — they must equal the same views traced alone on one GPU
+    import test_probe_views as P
+    one.set_triangle_range(0, 0xffffffff)
+    nv, vs = 2 * world + 1, 64
+    cams_, views, per_view, shadow, ks = P.batch_inputs(sc, nv, vs, SH, stride=7)
+    pb = D.ProbeBatch(N, vs, nv, shadow_res=SH, device=local, rank=rank, nranks=world, scene=sc, voxel_cam=cams_["voxel"], volume_mode="slab")
+    pb.gi.connect()
+    pb.upload_views(per_view, shadow)
+    pb.frame(cams_["voxel"], ks)
+    pb.ctx.sync()
+    own = pb.own_views()
+    one.upload(A.SLOT_SHADOW, shadow)
+    one.voxelize(cams_["voxel"]); one.inject(ks[0]); one.build_mips()
+    small = A.VoxelGI(N, vs, vs, A.MODE_NORTHSTAR, shadow_res=SH, device=local)
+    small.upload_scene(sc); small.upload(A.SLOT_SHADOW, shadow)
+    small.voxelize(cams_["voxel"]); small.inject(ks[0]); small.build_mips()
+    for v, img in own:
+        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_MATERIAL, "material")):
+            small.upload(slot, per_view[v][key])
+        small.trace_indirect(ks[v])
+        if not np.array_equal(small.readback(A.SLOT_INDIRECT_OUT).view(np.uint16), img.view(np.uint16)): bad.append(f"probe view {v}")
+    if [v for v, _ in own] != list(range(*D.view_ranges(nv, world)[rank])): bad.append("probe view partition")
+    dist.barrier()
+    pb.close(); small.close()
     print(f"rank {rank}: {'OK' if not bad else 'MISMATCH ' + '; '.join(bad[:6])} (fragments over ranks {int(frags.item())})", flush=True)
     g.close(); one.close()
     dist.destroy_process_group()

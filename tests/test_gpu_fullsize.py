@@ -90,3 +90,43 @@ def test_c4_tiled_sponza_1024_properties(cuda_lib, sponza):
     g.normalise()
     assert g.counter(A.COUNTER_OCCUPIED) == occ
     assert np.array_equal(g.readback(A.SLOT_VOX_NORMAL), nrm)
+
+
+def test_c5_probe_batch_64_views_512(cuda_lib, sponza, cams):
+    """configs[4]: 64 probe views (512 x 512, FovY 90, Halton positions — SURVEY.md §8(d)) cone-traced against the
+    Sponza 512^3 volume in one context.  Size-independent properties: the batch equals the same views traced alone
+    (bit for bit), the cone-sample counter is the sum over the views, tracing a sub-range leaves the other rows alone."""
+    from final184_b200 import dist as D
+    from final184_b200.fixture import Fixture
+    n, vs, nv = 512, 512, 64
+    views = [S.fixture_constants(f"probe{i:02d}") for i in range(nv)]
+    fx = Fixture(sponza)
+    per_view = [fx.gbuffer(v, vs, vs, 0) for v in views]
+    shadow = fx.shadow(cams["shadow"], 2048)
+    ks = [A.trace_constants_c(v, cams["shadow"], cams["voxel"], vs, vs, 0, True) for v in views]
+    b = D.ProbeBatch(n, vs, nv, scene=sponza, voxel_cam=cams["voxel"], lib=cuda_lib)
+    b.upload_views(per_view, shadow)
+    b.frame(cams["voxel"], ks)
+    img = b.ctx.readback(A.SLOT_INDIRECT_OUT).copy()
+    total = b.ctx.counter(A.COUNTER_MARCH_STEPS)
+    f = img.astype(np.float32)
+    assert np.isfinite(f).all() and f[..., :3].mean() > 1e-2
+    ms = b.ctx.stage_ms(A.STAGE_TRACE)
+    print(f"C5: 64 x 512^2 views, {total / 1e6:.0f} M cone-samples, trace {ms:.2f} ms = {total / ms / 1e6:.1f} Gcone-samples/s")
+    one = A.VoxelGI(n, vs, vs, A.MODE_NORTHSTAR, lib=cuda_lib)
+    one.upload_scene(sponza)
+    one.upload(A.SLOT_SHADOW, shadow)
+    one.voxelize(cams["voxel"]); one.inject(ks[0]); one.build_mips()
+    part = 0
+    for v in (0, 17, 63):
+        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_MATERIAL, "material")):
+            one.upload(slot, per_view[v][key])
+        one.trace_indirect(ks[v])
+        assert np.array_equal(one.readback(A.SLOT_INDIRECT_OUT).view(np.uint16), img[v * vs:(v + 1) * vs].view(np.uint16)), f"view {v}"
+        part += one.counter(A.COUNTER_MARCH_STEPS)
+    b.ctx.trace_views(ks, vs, first=0, count=1); s0 = b.ctx.counter(A.COUNTER_MARCH_STEPS)
+    b.ctx.trace_views(ks, vs, first=17, count=1); s17 = b.ctx.counter(A.COUNTER_MARCH_STEPS)
+    b.ctx.trace_views(ks, vs, first=63, count=1); s63 = b.ctx.counter(A.COUNTER_MARCH_STEPS)
+    assert s0 + s17 + s63 == part and 0 < part < total
+    assert np.array_equal(b.ctx.readback(A.SLOT_INDIRECT_OUT), img)          # re-tracing single views reproduced them in place
+    b.close(); one.close()

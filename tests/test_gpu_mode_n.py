@@ -143,3 +143,45 @@ def test_frame_overlap_is_invisible(cuda_lib, proc_scene, cams):
     for i, (x, y) in enumerate(zip(ia, ib)):
         assert np.array_equal(x, y), f"frame {i}"
     assert not np.array_equal(ia[0], ia[1])       # the frames really differ
+
+
+def test_probe_batch_views(cuda_lib, oracle_lib, proc_scene):
+    """BASELINE configs[4] at test size: 6 probe views stacked in one context (f184_trace_views, independent views on
+    alternating streams) — each view within the cone-trace tolerance of the oracle, the sample count within 1 %, and
+    BIT-identical to the same view traced alone as an ordinary image on the GPU; then a history frame."""
+    from final184_b200 import dist as D
+    import test_probe_views as P
+    n, vs, sh, nv = 64, 96, 256, 6
+    cams_, views, per_view, shadow, ks = P.batch_inputs(proc_scene, nv, vs, sh, stride=11)
+    res = {}
+    for name, lib in (("gpu", cuda_lib), ("cpu", oracle_lib)):
+        b = D.ProbeBatch(n, vs, nv, shadow_res=sh, scene=proc_scene, voxel_cam=cams_["voxel"], lib=lib)
+        b.upload_views(per_view, shadow)
+        b.frame(cams_["voxel"], ks)
+        res[name] = (dict(b.own_views()), b.ctx.counter(A.COUNTER_MARCH_STEPS), b)
+    (vg, sg, bg), (vo, so, bo) = res["gpu"], res["cpu"]
+    assert abs(sg - so) <= 0.01 * so, (sg, so)
+    for v in range(nv):
+        ig, io = vg[v].astype(np.float32), vo[v].astype(np.float32)
+        assert np.isfinite(ig).all() and np.array_equal(ig[..., 3], io[..., 3])
+        if io[..., :3].mean() > 1e-3:
+            assert Hh.rel_l2(ig[..., :3], io[..., :3]) <= 1e-2, v
+    one = A.VoxelGI(n, vs, vs, A.MODE_NORTHSTAR, shadow_res=sh, lib=cuda_lib)
+    one.upload_scene(proc_scene)
+    one.upload(A.SLOT_SHADOW, shadow)
+    one.voxelize(cams_["voxel"]); one.inject(ks[0]); one.build_mips()
+    for v in range(nv):
+        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_MATERIAL, "material")):
+            one.upload(slot, per_view[v][key])
+        one.trace_indirect(ks[v])
+        assert np.array_equal(one.readback(A.SLOT_INDIRECT_OUT).view(np.uint16), vg[v].view(np.uint16)), f"view {v} alone vs in the batch"
+    # history frame: every view reprojects into its own rows
+    ks2 = [A.trace_constants_c(v, cams_["shadow"], cams_["voxel"], vs, vs, 1, False) for v in views]
+    for b in (bg, bo):
+        b.ctx.copy_indirect_to_history()
+        b.ctx.trace_views(ks2, vs)
+    g2, o2 = dict(bg.own_views()), dict(bo.own_views())
+    for v in range(nv):
+        if o2[v][..., :3].astype(np.float32).mean() > 1e-3:
+            assert Hh.rel_l2(g2[v][..., :3].astype(np.float32), o2[v][..., :3].astype(np.float32)) <= 1e-2, v
+    bg.close(); bo.close(); one.close()
