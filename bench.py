@@ -221,6 +221,105 @@ class CpuPath:
         return sum(st.values()), (t4 - t0) * 1e3, st
 
 
+REFSH_SO = os.path.join(REPO, "oracle", "_ref", "libf184_refshaders.so")
+
+
+def c1_reference_mode(sc, cams, device, cpu_budget_s, gpu=True):
+    """BASELINE configs[0], the only configuration the reference itself can run and the sizes its shaders hard-code:
+    Sponza voxelized at 128^3 (centre-sample, last writer wins) + the 4 x 2 stochastic 60-step marches at 1280 x 720
+    (+ GTAO, + the bilateral blur tail) — F184_MODE_REFERENCE.  GPU: CUDA stage times over 20 frames.  CPU, beside it:
+    the reference's OWN shader text (oracle/_ref/libf184_refshaders.so: indirect.frag, gtao.frag, blur*.frag and main.lua's
+    voxel stages compiled by g++ where they lie) on the host cores, voxel pass in full, screen passes on a bounded band of
+    rows scaled to the frame.  Reported next to the headline; not part of it."""
+    import ctypes as C
+    from final184_b200 import api as A
+    from final184_b200.fixture import frame_inputs
+    N, W, H, SH = 128, 1280, 720, 2048
+    fi = frame_inputs(sc, cams["main"], cams["shadow"], W, H, SH, 0)
+    k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
+    out = {"workload": f"{'Sponza' if sc.name == 'sponza' else sc.name} 128^3 centre-sample voxelization + 8 x 60-step march at 1280x720 "
+                       "(+ GTAO, bilateral blur), reference-faithful mode"}
+    if gpu:
+        c = A.VoxelGI(N, W, H, A.MODE_REFERENCE, shadow_res=SH, device=device)
+        c.upload_scene(sc)
+        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_SHADOW, "shadow")):
+            c.upload(slot, fi[key])
+        frames = 20
+        def frame():
+            c.voxelize(cams["voxel"]); c.trace_indirect(k); c.gtao(cams["main"]); c.blur_indirect(k)
+        for _ in range(3):
+            frame()
+        c.sync()
+        c.stage_time_reset(True)
+        t0 = time.perf_counter()
+        for _ in range(frames):
+            frame()
+        c.sync()
+        wall = (time.perf_counter() - t0) * 1e3 / frames
+        st = {}
+        for s_ in range(A.STAGE_COUNT):
+            tot, runs = c.stage_total_ms(s_)
+            if runs:
+                st[A.STAGE_NAMES[s_]] = round(tot / frames, 4)
+        c.stage_time_reset(False)
+        steps = c.counter(A.COUNTER_MARCH_STEPS)
+        out["gpu"] = {"ms_per_frame": round(sum(st.values()), 4), "wall_ms_per_frame": round(wall, 4), "stages_ms": st,
+                      "fragments": c.counter(A.COUNTER_FRAGMENTS), "march_steps": steps,
+                      "gmarch_steps_per_s": round(steps / (st["trace"] * 1e-3) / 1e9, 2)}
+        c.close()
+    if os.path.exists(REFSH_SO) and cpu_budget_s > 0:
+        dll = C.CDLL(REFSH_SO)
+        vp = C.c_void_p
+        dll.refsh_indirect.argtypes = [C.POINTER(A.TraceConstantsC), vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        dll.refsh_gtao.argtypes = [C.POINTER(A.ViewConstantsC), vp, vp, C.c_int, C.c_int, vp]
+        dll.refsh_gtao_blur.argtypes = [vp, C.c_int, C.c_int, vp]
+        dll.refsh_blur.argtypes = [C.c_int, C.POINTER(A.EngineMiscsC), vp, vp, C.c_int, C.c_int, vp]
+        if not os.path.exists(ORACLE_SO):
+            subprocess.check_call(["make", "-C", os.path.join(REPO, "oracle")], stdout=subprocess.DEVNULL)
+        olib = A.Library(ORACLE_SO, "f184o_", product=False)
+        hooks = olib.dll.f184o_debug_set_voxel_stage_hooks
+        hooks.argtypes = [vp, vp, vp]
+        o = A.VoxelGI(N, W, H, A.MODE_REFERENCE, shadow_res=SH, lib=olib)
+        o.upload_scene(sc)
+        hooks(o.h, C.cast(dll.refsh_voxel_gs, vp), C.cast(dll.refsh_voxel_ps, vp))
+        t0 = time.perf_counter()
+        o.voxelize(cams["voxel"])                      # rasteriser = the oracle's fixed-function stage, shaders = the reference's text
+        t_vox = (time.perf_counter() - t0) * 1e3
+        vox = o.readback(A.SLOT_VOXELS).copy()
+        o.close()
+        depth, normals, shadow = (np.ascontiguousarray(fi[k_]) for k_ in ("depth", "normals", "shadow"))
+        hist, img = np.zeros((H, W, 4), np.uint16), np.zeros((H, W, 4), np.uint16)
+        tmp = np.zeros((H, W, 4), np.uint16)
+        ptr = lambda a: a.ctypes.data
+        vc = A.view_constants_c(cams["main"])
+        # a band of rows through the middle of the screen; grow it until the march alone has used ~half the budget
+        rows, t_ind = 4, 0.0
+        while True:
+            y0 = H // 2 - rows // 2
+            dll.refsh_set_rows(y0, y0 + rows)
+            t0 = time.perf_counter()
+            dll.refsh_indirect(C.byref(k), ptr(depth), ptr(normals), ptr(shadow), ptr(vox), ptr(hist), W, H, ptr(img))
+            t_ind = time.perf_counter() - t0
+            if t_ind > 0.35 * cpu_budget_s or rows >= H:
+                break
+            rows = min(H, rows * 2)
+        t0 = time.perf_counter()
+        dll.refsh_gtao(C.byref(vc), ptr(depth), ptr(normals), W, H, ptr(tmp))
+        t_gtao = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        dll.refsh_gtao_blur(ptr(tmp), W, H, ptr(hist))
+        dll.refsh_blur(0, C.byref(k.miscs), ptr(img), ptr(depth), W, H, ptr(tmp))
+        dll.refsh_blur(1, C.byref(k.miscs), ptr(tmp), ptr(depth), W, H, ptr(hist))
+        t_blur = time.perf_counter() - t0
+        dll.refsh_set_rows(0, 1 << 30)
+        sc_ = H / rows
+        st = {"voxelize": round(t_vox, 2), "trace": round(t_ind * 1e3 * sc_, 1), "gtao": round(t_gtao * 1e3 * sc_, 1), "blur": round(t_blur * 1e3 * sc_, 1)}
+        out["cpu_reference"] = {"ms_per_frame": round(sum(st.values()), 1), "stages_ms": st, "cores": os.cpu_count() or 1, "kind": "reference",
+                                "sample": f"the reference's own GLSL compiled by g++ (oracle/_ref/libf184_refshaders.so), OpenMP on all cores; voxel pass in full, "
+                                          f"screen passes on rows [{y0}, {y0 + rows}) of {H} scaled x{sc_:.1f}"}
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU restatement of the path, rank 0 only."""
     if rank != 0:
@@ -244,6 +343,8 @@ def run_reference(args, rank, world):
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": cpu.describe()},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "stages_ms": {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}, "gpu_launches": 0}
+    if sc.name == "sponza" and os.path.exists(REFSH_SO):
+        out["c1_reference_mode"] = c1_reference_mode(sc, cams, 0, min(10.0, per_step_budget), gpu=False)
     emit(json.dumps(out))
 
 
@@ -419,6 +520,9 @@ def run_b200(args, rank, world, local_rank):
                                   "peak": peaks_live["red_v4_per_s"] / 1e9}}
         for o in other.values():
             o["frac"] = o["achieved"] / o["peak"] if o["peak"] else None
+        if dom == "trace":
+            # the contract's roofline offers hbm|tensor; the cone tracer is bound by neither — carry the bound that applies along
+            roofline["actual_bound"] = {"name": "texture pipe (trilinear RGBA8 3D fetches, measured by f184_microbench)", **other["trace_tex"]}
         out = {"metric": METRIC, "value": ms_frame, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_frame, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
                "dtype": "u8 volumes / i64 overlap tests / f32 shading", "data": "synthetic",
@@ -442,6 +546,9 @@ def run_b200(args, rank, world, local_rank):
                 est.append(e); wall.append(w)
             out["cpu_baseline"] = {"value": float(np.mean(est)), "unit": UNIT, "cores": cpu.cores, "kind": "port",
                                    "sample": cpu.describe() + f"; {len(est)} samples, {np.mean(wall) / 1e3:.1f} s each"}
+        if world == 1 and args.grid == 512:
+            # configs[0] in the reference's own contract, beside the headline (GPU stage times always; the CPU leg with the cpu_baseline)
+            out["c1_reference_mode"] = c1_reference_mode(sc, cams, local_rank, 0.0 if args.no_cpu_baseline else 10.0)
         emit(json.dumps(out))
     g.close()
     if world > 1:

@@ -91,6 +91,11 @@ static void store_rgba16f(uint16_t* o, const vec4& c)
 
 using namespace glsl;
 
+// bench.py's bounded CPU sample: the screen passes run rows [g_row0, g_row1) only (default: all)
+static int g_row0 = 0, g_row1 = 1 << 30;
+static inline int row_begin() { return g_row0 < 0 ? 0 : g_row0; }
+static inline int row_end(int H) { return g_row1 < H ? g_row1 : H; }
+
 // indirect_blurX (dir 0) / indirect_blurY (dir 1), MegaPipeline.cpp:270-284
 template <class S> static void run_blur(const f184_engine_miscs* m, const uint16_t* src, const float* depth, int W, int H, uint16_t* out)
 {
@@ -98,7 +103,7 @@ template <class S> static void run_blur(const f184_engine_miscs* m, const uint16
     S::t_indirect = tex2d(src, W, H, TEX_RGBA16F); S::t_depth = tex2d(depth, W, H, TEX_R32F);
     S::resolution = vec2(m->resolution[0], m->resolution[1]); S::frameCount = m->frameCount; S::frameTime = m->frameTime;
 #pragma omp parallel for schedule(static)
-    for (int y = 0; y < H; y++)
+    for (int y = row_begin(); y < row_end(H); y++)
         for (int x = 0; x < W; x++)
         {
             S sh;
@@ -108,6 +113,8 @@ template <class S> static void run_blur(const f184_engine_miscs* m, const uint16
         }
 }
 extern "C" {
+
+void refsh_set_rows(int y0, int y1) { g_row0 = y0; g_row1 = y1; }
 
 // lighting_indirect, MegaPipeline.cpp:252-268.  history = indirectTemporalImage (all zero on the first frame, :197-204).
 int refsh_indirect(const f184_trace_constants* k, const float* depth, const uint16_t* normals, const float* shadow,
@@ -127,7 +134,7 @@ int refsh_indirect(const f184_trace_constants* k, const float* depth, const uint
     S::resolution = vec2(k->miscs.resolution[0], k->miscs.resolution[1]);
     S::frameCount = k->miscs.frameCount; S::frameTime = k->miscs.frameTime;
 #pragma omp parallel for schedule(dynamic, 2)
-    for (int y = 0; y < H; y++)
+    for (int y = row_begin(); y < row_end(H); y++)
         for (int x = 0; x < W; x++)
         {
             S sh;
@@ -146,7 +153,7 @@ int refsh_gtao(const f184_view_constants* view, const float* depth, const uint16
     S::t_depth = tex2d(depth, W, H, TEX_R32F); S::t_normals = tex2d(normals, W, H, TEX_RGBA16_UNORM);
     S::InvProj = M(view->InvProj); S::ViewMat = M(view->ViewMat); S::ProjMat = M(view->ProjMat);
 #pragma omp parallel for schedule(dynamic, 2)
-    for (int y = 0; y < H; y++)
+    for (int y = row_begin(); y < row_end(H); y++)
         for (int x = 0; x < W; x++)
         {
             S sh;
@@ -165,7 +172,7 @@ int refsh_gtao_blur(const uint16_t* ao_raw, int W, int H, uint16_t* out)
     S::s.wrap = 1;
     S::t_ao = tex2d(ao_raw, W, H, TEX_RGBA16F);
 #pragma omp parallel for schedule(static)
-    for (int y = 0; y < H; y++)
+    for (int y = row_begin(); y < row_end(H); y++)
         for (int x = 0; x < W; x++)
         {
             S sh;
