@@ -242,11 +242,11 @@ def c1_reference_mode(sc, cams, device, cpu_budget_s, gpu=True):
     if gpu:
         c = A.VoxelGI(N, W, H, A.MODE_REFERENCE, shadow_res=SH, device=device)
         c.upload_scene(sc)
-        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_SHADOW, "shadow")):
+        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_SHADOW, "shadow"), (A.SLOT_MATERIAL, "material")):
             c.upload(slot, fi[key])
         frames = 20
         def frame():
-            c.voxelize(cams["voxel"]); c.trace_indirect(k); c.gtao(cams["main"]); c.blur_indirect(k)
+            c.voxelize(cams["voxel"]); c.trace_indirect(k); c.gtao(cams["main"]); c.blur_indirect(k); c.lighting_deferred(k)
         for _ in range(3):
             frame()
         c.sync()
@@ -311,9 +311,18 @@ def c1_reference_mode(sc, cams, device, cpu_budget_s, gpu=True):
         dll.refsh_blur(0, C.byref(k.miscs), ptr(img), ptr(depth), W, H, ptr(tmp))
         dll.refsh_blur(1, C.byref(k.miscs), ptr(tmp), ptr(depth), W, H, ptr(hist))
         t_blur = time.perf_counter() - t0
+        dll.refsh_lighting_deferred.argtypes = [C.POINTER(A.ViewConstantsC), C.POINTER(A.ExtendedMatricesC), C.POINTER(A.LightListC),
+                                                C.POINTER(A.LightListC), vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        albedo, material = (np.ascontiguousarray(fi[k_]) for k_ in ("albedo", "material"))
+        pl, dl = A.LightListC(), A.light_list_c([(tuple(k.sun.luminance), tuple(k.sun.position))])
+        t0 = time.perf_counter()
+        dll.refsh_lighting_deferred(C.byref(k.view), C.byref(k.ext), C.byref(pl), C.byref(dl), ptr(albedo), ptr(normals), ptr(depth),
+                                    ptr(shadow), ptr(material), W, H, ptr(tmp))
+        t_light = time.perf_counter() - t0
         dll.refsh_set_rows(0, 1 << 30)
         sc_ = H / rows
-        st = {"voxelize": round(t_vox, 2), "trace": round(t_ind * 1e3 * sc_, 1), "gtao": round(t_gtao * 1e3 * sc_, 1), "blur": round(t_blur * 1e3 * sc_, 1)}
+        st = {"voxelize": round(t_vox, 2), "trace": round(t_ind * 1e3 * sc_, 1), "gtao": round(t_gtao * 1e3 * sc_, 1), "blur": round(t_blur * 1e3 * sc_, 1),
+              "lighting": round(t_light * 1e3 * sc_, 1)}
         out["cpu_reference"] = {"ms_per_frame": round(sum(st.values()), 1), "stages_ms": st, "cores": os.cpu_count() or 1, "kind": "reference",
                                 "sample": f"the reference's own GLSL compiled by g++ (oracle/_ref/libf184_refshaders.so), OpenMP on all cores; voxel pass in full, "
                                           f"screen passes on rows [{y0}, {y0 + rows}) of {H} scaled x{sc_:.1f}"}
@@ -473,9 +482,9 @@ def run_b200(args, rank, world, local_rank):
             pcie["d2h_gbs"] = 4 * d2h / (time.perf_counter() - t0) / 1e9
         # secondary pass, reported beside the metric (not part of it): GTAO + its blur, and the indirect blur tail
         for _ in range(3):
-            g.ctx.gtao(cams["main"]); g.ctx.blur_indirect(k)
+            g.ctx.gtao(cams["main"]); g.ctx.blur_indirect(k); g.ctx.lighting_deferred(k)
         g.ctx.sync()
-        extra_ms = {"gtao": g.ctx.stage_ms(A.STAGE_GTAO), "blur": g.ctx.stage_ms(A.STAGE_BLUR)}
+        extra_ms = {"gtao": g.ctx.stage_ms(A.STAGE_GTAO), "blur": g.ctx.stage_ms(A.STAGE_BLUR), "lighting_deferred": g.ctx.stage_ms(A.STAGE_LIGHTING)}
         # the two peaks MEASURED_PEAKS.json does not hold, measured live (rank 0, after the timed regions)
         peaks_live = {"tex_trilinear_per_s": g.ctx.microbench(0), "red_v4_per_s": g.ctx.microbench(1)} if rank == 0 else {}
 
@@ -500,7 +509,7 @@ def run_b200(args, rank, world, local_rank):
         # under the frame overlap the event pairs of voxelize / normalise bracket kernels that share the SMs with the previous
         # frame's cone trace: their elapsed times include that sharing and say nothing about the kernel alone, so they are
         # flagged and not candidates for the dominant kernel (the --no-overlap run and the ncu launch list give their solo times)
-        concurrent = [] if (world > 1 or args.no_overlap) else ["voxelize", "normalise"]
+        concurrent = [] if args.no_overlap else (["voxelize", "normalise"] if world == 1 else (["voxelize"] if g.mode == "slab" else []))
         for n_ in concurrent:
             if n_ in rstages:
                 rstages[n_]["concurrent_with"] = "trace of the previous frame"
@@ -527,7 +536,7 @@ def run_b200(args, rank, world, local_rank):
                "ms_per_step": ms_frame, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
                "dtype": "u8 volumes / i64 overlap tests / f32 shading", "data": "synthetic",
                "config": {"workload": wname, "grid": N, "width": W, "height": H, "shadow": args.shadow, "triangles": sc.n_tris,
-                          "parallelism": g.describe() + ("" if world > 1 or args.no_overlap else "; voxelize+normalise of frame f+1 overlap the cone trace of frame f (internal stream)"), "l2": "inputs larger than L2 (volume chain %.0f MB + accumulators; no flush)" % (algorithmic_bytes("trace", args, sc, counters) / 1e6)},
+                          "parallelism": g.describe() + ("" if args.no_overlap else ("; voxelize+normalise of frame f+1 overlap the cone trace of frame f (internal stream)" if world == 1 else "; the accumulation of frame f+1 (peer atomics) overlaps the gather + cone trace of frame f")), "l2": "inputs larger than L2 (volume chain %.0f MB + accumulators; no flush)" % (algorithmic_bytes("trace", args, sc, counters) / 1e6)},
                "gvoxel_per_s": N ** 3 / (ms_frame * 1e-3) / 1e9,
                "gcone_samples_per_s": total_samples / (stage_ms.get("trace", ms_frame) * 1e-3) / 1e9,
                "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "stages_concurrent": concurrent, "comm_ms": comm_ms, "secondary_ms": extra_ms, "counters": counters,

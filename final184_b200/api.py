@@ -26,10 +26,10 @@ MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
 (SLOT_DEPTH, SLOT_NORMALS, SLOT_ALBEDO, SLOT_MATERIAL, SLOT_SHADOW, SLOT_VOXELS, SLOT_INDIRECT_OUT,
  SLOT_INDIRECT_HISTORY, SLOT_AO_RAW, SLOT_AO_OUT, SLOT_INDIRECT_BLUR_X, SLOT_INDIRECT_FINAL,
  SLOT_ACCUM_COLOR, SLOT_ACCUM_NORMAL, SLOT_VOX_ALBEDO, SLOT_VOX_NORMAL, SLOT_RADIANCE, SLOT_MIPS,
- SLOT_BRICK_FLAGS, SLOT_COUNT) = range(20)
+ SLOT_BRICK_FLAGS, SLOT_LIGHTING, SLOT_COUNT) = range(21)
 (STAGE_CLEAR, STAGE_VOXELIZE, STAGE_NORMALISE, STAGE_INJECT, STAGE_MIPS, STAGE_TRACE, STAGE_GTAO,
- STAGE_BLUR, STAGE_EXCHANGE, STAGE_COUNT) = range(10)
-STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur", "exchange"]
+ STAGE_BLUR, STAGE_EXCHANGE, STAGE_LIGHTING, STAGE_COUNT) = range(11)
+STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur", "exchange", "lighting"]
 (COUNTER_FRAGMENTS, COUNTER_MARCH_STEPS, COUNTER_OCCUPIED, COUNTER_KERNEL_LAUNCHES, COUNTER_BRICKS) = range(5)
 (IPC_ACCUM_COLOR, IPC_ACCUM_NORMAL, IPC_BRICK_FLAGS, IPC_EXPORT, IPC_COUNTERS, IPC_BRICK_LIST, IPC_SYNC, IPC_COUNT) = range(8)
 FLAG_EXTERNAL_RANDS = 1
@@ -80,6 +80,22 @@ class SunC(C.Structure):
 
 class EngineMiscsC(C.Structure):
     _fields_ = [("resolution", C.c_float * 2), ("frameCount", C.c_uint32), ("frameTime", C.c_float)]
+
+
+class LightListC(C.Structure):
+    """LightLists, MegaPipeline.cpp:101-105"""
+    _fields_ = [("lights", SunC * 100), ("numLights", C.c_int32), ("_pad", C.c_int32 * 3)]
+
+
+def light_list_c(lights):
+    """lights: iterable of (luminance rgb, position-or-direction xyz)"""
+    ll = LightListC()
+    n = 0
+    for lum, pos in lights:
+        ll.lights[n] = SunC((C.c_float * 3)(*lum), 0.0, (C.c_float * 3)(*pos), 0.0)
+        n += 1
+    ll.numLights = n
+    return ll
 
 
 class TraceConstantsC(C.Structure):
@@ -150,6 +166,7 @@ _SIGS = {
     "gtao": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC)]),
     "blur_indirect": (C.c_int, [C.c_void_p, C.POINTER(EngineMiscsC)]),
     "copy_indirect_to_history": (C.c_int, [C.c_void_p]),
+    "lighting_deferred": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC), C.POINTER(ExtendedMatricesC), C.POINTER(LightListC), C.POINTER(LightListC)]),
     "bind_rands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "set_triangle_range": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "set_trace_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
@@ -352,6 +369,13 @@ class VoxelGI:
 
     def blur_indirect(self, k: TraceConstantsC):
         self._ck(self.lib.blur_indirect(self.h, C.byref(k.miscs)), "blur_indirect")
+
+    def lighting_deferred(self, k: TraceConstantsC, point: LightListC | None = None, directional: LightListC | None = None):
+        """lighting_deferred pass; by default one directional light = the sun of `k` (MegaPipeline.cpp:106-125)."""
+        if directional is None:
+            directional = light_list_c([(tuple(k.sun.luminance), tuple(k.sun.position))])
+        point = point if point is not None else LightListC()
+        self._ck(self.lib.lighting_deferred(self.h, C.byref(k.view), C.byref(k.ext), C.byref(point), C.byref(directional)), "lighting_deferred")
 
     def copy_indirect_to_history(self):
         self._ck(self.lib.copy_indirect_to_history(self.h), "copy_indirect_to_history")

@@ -63,6 +63,7 @@ static bool default_desc(const f184_config& c, int slot, f184_image_desc* d)
     case F184_SLOT_AO_RAW:
     case F184_SLOT_AO_OUT:
     case F184_SLOT_INDIRECT_BLUR_X:
+    case F184_SLOT_LIGHTING:
     case F184_SLOT_INDIRECT_FINAL: set(F184_FMT_R16G16B16A16_SFLOAT, W, H, 1); break;
     case F184_SLOT_ACCUM_COLOR:
     case F184_SLOT_ACCUM_NORMAL: set(F184_FMT_R32G32B32A32_SFLOAT, N, N, N); break;
@@ -129,6 +130,10 @@ int f184_stage_end(f184_ctx* c, int stage)
 bool f184_overlap_enabled(const f184_ctx* c)
 {
     return c->vox_stream && c->cfg.mode == F184_MODE_NORTHSTAR && c->cfg.nranks <= 1 && !(c->cfg.flags & F184_FLAG_NO_OVERLAP);
+}
+bool f184_overlap_multi(const f184_ctx* c)
+{
+    return c->vox_stream && c->cfg.mode == F184_MODE_NORTHSTAR && c->cfg.nranks > 1 && !(c->cfg.flags & F184_FLAG_NO_OVERLAP);
 }
 int f184_join_vox(f184_ctx* c)
 {
@@ -303,6 +308,8 @@ void f184_destroy(f184_ctx* c)
     }
     if (c->ev_vox_done) cudaEventDestroy(c->ev_vox_done);
     if (c->ev_consumed) cudaEventDestroy(c->ev_consumed);
+    if (c->ev_barrier) cudaEventDestroy(c->ev_barrier);
+    if (c->lights_dev) cudaFree(c->lights_dev);
     delete c;
 }
 
@@ -652,9 +659,35 @@ int f184_voxelize_accumulate(f184_ctx* c, const f184_view_constants* cam)
     CK(c, cudaSetDevice(c->cfg.device));
     int rc = f184_sync_tables(c);
     if (rc) return rc;
-    rc = f184_join_vox(c);
+    if (!f184_overlap_multi(c))
+    {
+        rc = f184_join_vox(c);
+        if (rc) return rc;
+        return f184_voxelize_accumulate_n(c, cam);
+    }
+    // One NVLink box, frame overlap: the accumulation of frame f+1 goes to vox_stream and runs beside the gather and the cone
+    // trace of frame f.  Its peer atomics are NVLink-bound, the trace is texture-bound: they share the SMs without competing
+    // for the same unit.  It may start once EVERY rank has normalised frame f (normalise re-zeroes the accumulators and
+    // consumes the brick flags this pass writes on the peers): that is what the last peer barrier on the pass stream — the
+    // one between mips and gather — certifies, so vox_stream waits for the event recorded behind it (ev_barrier) and for
+    // nothing later.  f184_peer_barrier joins vox_stream first, so the barrier that publishes frame f+1's fragments cannot
+    // pass before this rank's own fragments have left.
+    cudaStream_t pass = c->stream;
+    if (!c->vox_started)
+    {   // first use: behind everything enqueued so far (allocation clears, scene and table uploads)
+        CK(c, cudaEventRecord(c->ev_consumed, pass));
+        c->vox_started = true;
+    }
+    CK(c, cudaStreamWaitEvent(c->vox_stream, c->ev_consumed, 0));
+    if (c->barrier_recorded) CK(c, cudaStreamWaitEvent(c->vox_stream, c->ev_barrier, 0));
+    c->stream = c->vox_stream;
+    rc = f184_voxelize_accumulate_n(c, cam);
+    cudaError_t e = rc == F184_OK ? cudaEventRecord(c->ev_vox_done, c->vox_stream) : cudaSuccess;
+    c->stream = pass;
     if (rc) return rc;
-    return f184_voxelize_accumulate_n(c, cam);
+    CK(c, e);
+    c->vox_pending = true;
+    return F184_OK;
 }
 int f184_normalise(f184_ctx* c)
 {
@@ -754,6 +787,13 @@ int f184_blur_indirect(f184_ctx* c, const f184_engine_miscs* miscs)
     if (!c || !miscs) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "blur_indirect: null argument");
     CK(c, cudaSetDevice(c->cfg.device));
     return f184_blur_impl(c, miscs);
+}
+int f184_lighting_deferred(f184_ctx* c, const f184_view_constants* view, const f184_extended_matrices* m, const f184_light_list* point,
+                           const f184_light_list* directional)
+{
+    if (!c || !view || !m) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "lighting_deferred: null argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    return f184_lighting_impl(c, view, m, point, directional);
 }
 int f184_copy_indirect_to_history(f184_ctx* c)
 {

@@ -63,6 +63,8 @@ struct f184_ctx
     cudaStream_t vox_stream = nullptr;
     cudaEvent_t ev_vox_done = nullptr, ev_consumed = nullptr;
     bool vox_pending = false, vox_started = false;
+    cudaEvent_t ev_barrier = nullptr;         // recorded behind every f184_peer_barrier (multi-GPU frame overlap, f184_voxelize_accumulate)
+    bool barrier_recorded = false;
     // probe batches (f184_trace_views): independent views round-robin over a few streams, joined back into the pass stream
     cudaStream_t view_streams[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_view_done[4] = {nullptr, nullptr, nullptr, nullptr}, ev_view_fork = nullptr;
@@ -108,6 +110,7 @@ struct f184_ctx
     M4* vm_dev = nullptr;                     // View * Model per model matrix
     uint32_t vm_cap = 0;
     void* gtao_phi_table = nullptr;           // (cos, sin) of the 64 GTAO slice angles (gtao.cu)
+    void* lights_dev = nullptr;               // 2 x 100 lights (lighting.cu)
     float* gamma_table = nullptr;             // pow(a/255, 2.2), a = 0..255 (mode_n_inject.cu)
     bool defer_normalise = false;             // multi-GPU: f184_voxelize stops after accumulation
     cudaSurfaceObject_t rad_surf = 0;
@@ -161,6 +164,7 @@ int f184_fail(f184_ctx* c, int code, const char* fmt, ...);
 
 int f184_ensure_image(f184_ctx* c, int slot);
 bool f184_overlap_enabled(const f184_ctx* c);
+bool f184_overlap_multi(const f184_ctx* c);
 int f184_join_vox(f184_ctx* c);           // pass stream waits for the voxelize/normalise in flight on vox_stream
 int f184_mark_consumed(f184_ctx* c);      // pass stream: everything that reads the voxelizer's outputs has been enqueued
 int f184_sync_tables(f184_ctx* c);
@@ -192,6 +196,8 @@ int f184_voxelize_r(f184_ctx* c, const f184_view_constants* cam);
 int f184_trace_r(f184_ctx* c, const f184_trace_constants* k);
 int f184_gtao_impl(f184_ctx* c, const f184_view_constants* view);
 int f184_blur_impl(f184_ctx* c, const f184_engine_miscs* miscs);
+int f184_lighting_impl(f184_ctx* c, const f184_view_constants* view, const f184_extended_matrices* m, const f184_light_list* point,
+                       const f184_light_list* directional);
 int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam);
 int f184_inject_n(f184_ctx* c, const f184_sun* sun, const f184_extended_matrices* m);
 int f184_mips_n(f184_ctx* c);

@@ -74,7 +74,9 @@ typedef enum f184_slot {
     F184_SLOT_RADIANCE = 16,        /* R8G8B8A8_UNORM premultiplied radiance/exposure, mip 0 N^3   */
     F184_SLOT_MIPS = 17,            /* all levels >= 1, six directions each, one allocation        */
     F184_SLOT_BRICK_FLAGS = 18,     /* u32 per 8^3 brick: touched this frame                (N/8)^3 */
-    F184_SLOT_COUNT = 19
+    /* the consumer next to the voxel-GI section */
+    F184_SLOT_LIGHTING = 19,        /* lightingImage (lighting_deferred target), R16G16B16A16_SFLOAT  W x H */
+    F184_SLOT_COUNT = 20
 } f184_slot;
 
 typedef enum f184_format {
@@ -124,9 +126,11 @@ typedef enum f184_flags {
     F184_FLAG_GATHER_LINEAR = 8,   /* multi-GPU: f184_gather_volume also fills the linear RADIANCE / MIPS slots (tests) */
     F184_FLAG_DENSE_MIPS = 4,      /* mode N mips: dense chain, TMA-staged tiles for the large levels (default is the sparse
                                       brick-list path for levels 1-3 + one fused launch for the rest) */
-    F184_FLAG_NO_OVERLAP = 16      /* mode N, one GPU: keep f184_voxelize on the pass stream. Default: voxelize + normalise of the
-                                      next frame run on an internal stream and overlap the previous frame's cone trace; every call
-                                      that reads their outputs orders itself after them, so results are identical either way */
+    F184_FLAG_NO_OVERLAP = 16      /* mode N: keep the voxelizer on the pass stream. Default, one GPU: voxelize + normalise of the next
+                                      frame run on an internal stream and overlap the previous frame's cone trace. Default, one NVLink
+                                      box: f184_voxelize_accumulate of the next frame (peer atomics, NVLink-bound) runs on that stream
+                                      beside the previous frame's gather + cone trace, starting behind the last f184_peer_barrier.
+                                      Every call that reads the voxelizer's outputs orders itself after it: results are identical */
 } f184_flags;
 
 /* CViewConstants, Foreground/SceneGraph/SceneView.h:8-14 = GlobalConstants, Shader/EngineCommon.h:7-13. 208 B. */
@@ -160,6 +164,14 @@ typedef struct f184_sun {
     float position[3];
     float _pad1;
 } f184_sun;
+
+/* LightLists, MegaPipeline.cpp:101-105 = pointLights / directionalLights, aggregateLights.frag:36-44 (std140: 100 x 32 B, then
+ * int numLights; the C++ struct is alignas(16)). 3216 B.  `position` of a directional light is its forward direction. */
+typedef struct f184_light_list {
+    f184_sun lights[100];
+    int32_t numLights;
+    int32_t _pad[3];
+} f184_light_list;
 
 /* EngineCommonMiscs, MegaPipeline.cpp:141-146 = indirect.frag:36-40. 16 B. */
 typedef struct f184_engine_miscs {
@@ -202,7 +214,8 @@ typedef enum f184_stage_id {
     F184_STAGE_GTAO = 6,
     F184_STAGE_BLUR = 7,
     F184_STAGE_EXCHANGE = 8,       /* multi-GPU: peer barriers + gather of the other ranks' bricks */
-    F184_STAGE_COUNT = 9
+    F184_STAGE_LIGHTING = 9,       /* f184_lighting_deferred */
+    F184_STAGE_COUNT = 10
 } f184_stage_id;
 
 typedef enum f184_counter_id {
@@ -279,6 +292,11 @@ int f184_trace_views(f184_ctx* ctx, const f184_trace_constants* constants, uint3
 int f184_gtao(f184_ctx* ctx, const f184_view_constants* view);
 /* indirect_blurX + indirect_blurY, MegaPipeline.cpp:270-284 (Shader/Lighting/bilateralBlur.inc). */
 int f184_blur_indirect(f184_ctx* ctx, const f184_engine_miscs* miscs);
+/* lighting_deferred pass, MegaPipeline.cpp:286-300 (Shader/Lighting/aggregateLights.frag): Cook-Torrance direct lighting of every
+ * point and directional light over the G-buffer, directional lights through 12 x 4 bicubic-weighted shadow taps.  Reads DEPTH,
+ * NORMALS, MATERIAL, SHADOW; writes F184_SLOT_LIGHTING.  Either list may be NULL (= empty). */
+int f184_lighting_deferred(f184_ctx* ctx, const f184_view_constants* view, const f184_extended_matrices* matrices,
+                           const f184_light_list* point_lights, const f184_light_list* directional_lights);
 /* CopyImage(indirectImage -> indirectTemporalImage), MegaPipeline.cpp:211-214. */
 int f184_copy_indirect_to_history(f184_ctx* ctx);
 

@@ -93,6 +93,8 @@ struct vec2
     vec2& operator*=(const vec2& b) { x = x * b.x; y = y * b.y; return *this; }
     vec2& operator*=(float b) { x = x * b; y = y * b; return *this; }
     vec2& operator/=(float b) { x = x / b; y = y / b; return *this; }
+    void add_xy(const vec2& v) { x = x + v.x; y = y + v.y; }
+    void add_st(const vec2& v) { x = x + v.x; y = y + v.y; }
 };
 struct vec3
 {
@@ -114,6 +116,8 @@ struct vec3
     vec3 rgb() const { return *this; }
     vec3 yzx() const { return vec3(y, z, x); }
     vec3 zxy() const { return vec3(z, x, y); }
+    vec3 rrr() const { return vec3(x, x, x); }
+    vec2 zz() const { return vec2(z, z); }
     void set_xy(const vec2& v) { x = v.x; y = v.y; }
     void set_st(const vec2& v) { x = v.x; y = v.y; }
     void set_xz(const vec2& v) { x = v.x; z = v.y; }
@@ -124,6 +128,9 @@ struct vec3
     vec3& operator*=(const vec3& o) { x = x * o.x; y = y * o.y; z = z * o.z; return *this; }
     vec3& operator*=(float o) { x = x * o; y = y * o; z = z * o; return *this; }
     vec3& operator/=(float o) { x = x / o; y = y / o; z = z / o; return *this; }
+    void add_xy(const vec2& v) { x = x + v.x; y = y + v.y; }
+    void add_rgb(const vec3& v) { x = x + v.x; y = y + v.y; z = z + v.z; }
+    void add_xyz(const vec3& v) { x = x + v.x; y = y + v.y; z = z + v.z; }
 };
 struct vec4
 {
@@ -155,11 +162,18 @@ struct vec4
     void set_xz(const vec2& v) { x = v.x; z = v.y; }
     void set_yz(const vec2& v) { y = v.x; z = v.y; }
     void add_st(const vec2& v) { x = x + v.x; y = y + v.y; }
+    void add_xy(const vec2& v) { x = x + v.x; y = y + v.y; }
+    void add_rgb(const vec3& v);
+    void add_xyz(const vec3& v);
+    vec3 rrr() const;
     vec4& operator+=(const vec4& o) { x = x + o.x; y = y + o.y; z = z + o.z; w = w + o.w; return *this; }
     vec4& operator*=(float o) { x = x * o; y = y * o; z = z * o; w = w * o; return *this; }
     vec4& operator/=(float o) { x = x / o; y = y / o; z = z / o; w = w / o; return *this; }
 };
 inline vec3 vec2::xyx() const { return vec3(x, y, x); }
+inline void vec4::add_rgb(const vec3& v) { x = x + v.x; y = y + v.y; z = z + v.z; }
+inline void vec4::add_xyz(const vec3& v) { x = x + v.x; y = y + v.y; z = z + v.z; }
+inline vec3 vec4::rrr() const { return vec3(x, x, x); }
 inline vec3::vec3(const vec4& v) : x(v.x), y(v.y), z(v.z) {}
 // float -> int conversion: truncation, NaN -> 0 (PINNED)
 inline ivec2::ivec2(const vec2& v) : x(dm_f2i(v.x)), y(dm_f2i(v.y)) {}
@@ -258,6 +272,9 @@ inline float cos(float x) { return dm_cos(x); }
 inline float log(float x) { return dm_log(x); }
 inline float log2(float x) { return dm_log2(x); }
 inline float exp2(float x) { return dm_exp2(x); }
+inline float exp2(int x) { return dm_exp2((float)x); }
+// PINNED: exp(x) = exp2(x * log2(e)), the way GPU ISAs lower it (one multiply, then the exp2 unit)
+inline float exp(float x) { return dm_exp2(x * 1.4426950408889634f); }
 inline float pow(float x, float y) { return dm_pow(x, y); }
 inline float min(float a, float b) { return dm_min(a, b); }
 inline float max(float a, float b) { return dm_max(a, b); }
@@ -278,7 +295,7 @@ inline vec2 intBitsToFloat(const ivec2& v) { return vec2(intBitsToFloat(v.x), in
     inline vec2 F(const vec2& a) { return vec2(F(a.x), F(a.y)); }                                                      \
     inline vec3 F(const vec3& a) { return vec3(F(a.x), F(a.y), F(a.z)); }                                              \
     inline vec4 F(const vec4& a) { return vec4(F(a.x), F(a.y), F(a.z), F(a.w)); }
-GLSL_MAP1(abs) GLSL_MAP1(sqrt) GLSL_MAP1(floor) GLSL_MAP1(fract) GLSL_MAP1(sin) GLSL_MAP1(cos) GLSL_MAP1(sign)
+GLSL_MAP1(exp) GLSL_MAP1(abs) GLSL_MAP1(sqrt) GLSL_MAP1(floor) GLSL_MAP1(fract) GLSL_MAP1(sin) GLSL_MAP1(cos) GLSL_MAP1(sign)
 #define GLSL_MAP2(F)                                                                                                   \
     inline vec2 F(const vec2& a, const vec2& b) { return vec2(F(a.x, b.x), F(a.y, b.y)); }                             \
     inline vec3 F(const vec3& a, const vec3& b) { return vec3(F(a.x, b.x), F(a.y, b.y), F(a.z, b.z)); }                \

@@ -11,7 +11,7 @@ become static members, functions become member functions.  The rewrite is purely
   * `layout(...) uniform Block { ... } v;`  -> `struct Block_t { ... }; inline static Block_t v;`
   * floating literals get an `f` suffix (GLSL literals are fp32, C++ literals are double)
   * r-value swizzles `.xyz` -> `.xyz()`; swizzle assignment `a.xy = e;` -> `a.set_xy(e);`
-  * `inout T x` -> `T& x`; `uint(` / `int(` -> `to_uint(` / `to_int(` (saturating / NaN-safe conversions of the shim)
+  * `inout T x` / `out T x` parameters -> `T& x`; `const int N = k;` -> `static constexpr`; `T a[n] = T[](...)` -> `{...}`; `uint(` / `int(` -> `to_uint(` / `to_int(` (saturating / NaN-safe conversions of the shim)
   * `discard` -> `throw glsl_discard()`
   * PINNED operand order: in `acc += a * f(..)` where f has an inout parameter, `a` is read before the call
     (GLSL leaves the order open); the rewrite materialises `a` first.
@@ -28,7 +28,7 @@ import sys
 FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)([fF]?)(?![\w.])")
 SWZ = r"(?:[xyzw]{2,4}|[rgba]{2,4}|[stpq]{2,4})"
 SWZ_ASSIGN = re.compile(r"([A-Za-z_][\w\[\]\.]*?)\.(xy|st|xz|yz)\s*=(?!=)\s*([^;]+);")
-SWZ_ADD_ASSIGN = re.compile(r"([A-Za-z_][\w\[\]\.]*?)\.(st)\s*\+=\s*([^;]+);")
+SWZ_ADD_ASSIGN = re.compile(r"([A-Za-z_][\w\[\]\.]*?)\.(st|xy|rgb|xyz)\s*\+=\s*([^;]+);")
 SWZ_BAD_ASSIGN = re.compile(r"\.(" + SWZ + r")\s*[-+*/]?=(?!=)")
 SWZ_RVALUE = re.compile(r"\.(" + SWZ + r")\b(?!\s*\()")
 LAYOUT = r"layout\s*\([^)]*\)\s*"
@@ -46,6 +46,19 @@ def splice_includes(path, shader_root, seen=None):
     return re.sub(r'^[ \t]*#include\s+"([^"]+)"[ \t]*$', repl, text, flags=re.M)
 
 
+def array_constructors(text):
+    """`T name[n] = T [] ( a, b, ... );`  ->  `T name[n] = { a, b, ... };`"""
+    out, pos = [], 0
+    for m in re.finditer(r"=\s*\w+\s*\[\s*\]\s*\(", text):
+        depth, i = 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(text[i], 0)
+            i += 1
+        out.append(text[pos:m.start()] + "= {" + text[m.end():i - 1] + "}")
+        pos = i
+    return "".join(out) + text[pos:]
+
+
 def lexical(text, inout_fns=()):
     """the arithmetic-neutral rewrites shared by .frag files and main.lua code strings"""
     text = re.sub(r"^[ \t]*#(version|extension)[^\n]*$", "", text, flags=re.M)
@@ -57,6 +70,10 @@ def lexical(text, inout_fns=()):
         raise SystemExit(f"unhandled swizzle assignment near: {text[max(0, bad.start() - 40):bad.end() + 40]!r}")
     text = SWZ_RVALUE.sub(lambda m: f".{m.group(1)}()", text)
     text = re.sub(r"\binout\s+(\w+)\s+(\w+)", r"\1& \2", text)
+    text = re.sub(r"([(,]\s*)out\s+(\w+)\s+(\w+)", r"\1\2& \3", text)        # parameter qualifiers
+    text = re.sub(r"([(,]\s*)in\s+(\w+)\s+(\w+)", r"\1\2 \3", text)
+    text = re.sub(r"^([ \t]*)const\s+int\s+(\w+)\s*=\s*(\d+)\s*;", r"\1static constexpr int \2 = \3;", text, flags=re.M)   # usable as array bounds
+    text = array_constructors(text)
     text = re.sub(r"\buint\s*\(", "to_uint(", text)
     text = re.sub(r"(?<![\w.])int\s*\((?!\s*\))", "to_int(", text)
     text = re.sub(r"\bdiscard\b", "throw glsl_discard()", text)
@@ -148,6 +165,8 @@ def main():
         "gtao_blur_frag.inc": frag(ref, "GTAO/blur.frag"),
         "blurX_frag.inc": frag(ref, "Lighting/blurX.frag"),
         "blurY_frag.inc": frag(ref, "Lighting/blurY.frag"),
+        "aggregateLights_frag.inc": frag(ref, "Lighting/aggregateLights.frag"),
+        "color_frag.inc": frag(ref, "GTAO/color.frag"),
     }
     files["voxel_gs.inc"], files["voxel_ps.inc"] = voxel_stages(ref)
     for name, text in files.items():

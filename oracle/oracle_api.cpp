@@ -60,6 +60,7 @@ static bool default_desc(const f184_config& c, int slot, f184_image_desc* d)
     case F184_SLOT_AO_RAW:
     case F184_SLOT_AO_OUT:
     case F184_SLOT_INDIRECT_BLUR_X:
+    case F184_SLOT_LIGHTING:
     case F184_SLOT_INDIRECT_FINAL: set(F184_FMT_R16G16B16A16_SFLOAT, W, H, 1); break;
     case F184_SLOT_ACCUM_COLOR:
     case F184_SLOT_ACCUM_NORMAL: set(F184_FMT_R32G32B32A32_SFLOAT, N, N, N); break;

@@ -711,3 +711,136 @@ extern "C" int f184o_blur_indirect(f184o_ctx* c, const f184_engine_miscs* miscs)
     c->stage_ms[F184_STAGE_BLUR] = (float)(now_ms() - t0);
     return F184_OK;
 }
+
+// =================================================================================================
+// deferred direct lighting (Shader/Lighting/aggregateLights.frag; MegaPipeline.cpp:286-300)
+// =================================================================================================
+namespace {
+inline float bw0(float a) { return (1.0f / 6.0f) * (a * (a * (-a + 3.0f) - 3.0f) + 1.0f); }      // math.inc:35-49
+inline float bw1(float a) { return (1.0f / 6.0f) * (a * a * (3.0f * a - 6.0f) + 4.0f); }
+inline float bw2(float a) { return (1.0f / 6.0f) * (a * (a * (-3.0f * a + 3.0f) + 3.0f) + 1.0f); }
+inline float bw3(float a) { return (1.0f / 6.0f) * (a * a * a); }
+inline float bg0(float a) { return bw0(a) + bw1(a); }                                              // math.inc:52-66
+inline float bg1(float a) { return bw2(a) + bw3(a); }
+inline float bh0(float a) { return -1.0f + bw1(a) / (bw0(a) + bw1(a)); }
+inline float bh1(float a) { return 1.0f + bw3(a) / (bw2(a) + bw3(a)); }
+
+struct LightCtx { const float* shadow; uint32_t S; };
+inline float shadow_fetch(const LightCtx& L, float fx, float fy)
+{
+    const int x = dm_f2i(fx + 0.5f), y = dm_f2i(fy + 0.5f);
+    return (x >= 0 && y >= 0 && x < (int)L.S && y < (int)L.S) ? L.shadow[(size_t)y * L.S + x] : 0.0f;   // PINNED: out of range -> 0
+}
+// shadowTexSmooth, aggregateLights.frag:83-117
+inline float shadow_smooth(const LightCtx& L, float sx, float sy, float sz, float bias)
+{
+    const float res = (float)L.S;
+    const float ux = sx * res - 1.0f, uy = sy * res - 1.0f;
+    const float ix = floorf(ux), iy = floorf(uy);
+    const float fx = ux - ix, fy = uy - iy;
+    const float g0x = bg0(fx), g1x = bg1(fx);
+    const float h0x = bh0(fx) * 0.75f, h1x = bh1(fx) * 0.75f, h0y = bh0(fy) * 0.75f, h1y = bh1(fy) * 0.75f;
+    const float r0 = dm_step(sz, shadow_fetch(L, ix + h0x, iy + h0y) + bias);
+    const float r1 = dm_step(sz, shadow_fetch(L, ix + h1x, iy + h0y) + bias);
+    const float r2 = dm_step(sz, shadow_fetch(L, ix + h0x, iy + h1y) + bias);
+    const float r3 = dm_step(sz, shadow_fetch(L, ix + h1x, iy + h1y) + bias);
+    return bg0(fy) * (g0x * r0 + g1x * r1) + bg1(fy) * (g0x * r2 + g1x * r3);
+}
+inline float ggx_schlick(float NdotV, float roughness)          // :156-165
+{
+    const float r = roughness + 1.0f;
+    const float k = r * r / 8.0f;
+    return NdotV / (NdotV * (1.0f - k) + k);
+}
+// illumination, aggregateLights.frag:176-205
+inline V3 illumination(V3 lightVector, const float* lum, V3 cspos, V3 csnorm, float metallicity, float roughness)
+{
+    const V3 wi = normalize(lightVector), wo = normalize(neg(cspos)), halfvec = normalize(wi + wo);
+    const float distSq = dot(lightVector, lightVector);
+    const float dist = fastSqrt(distSq);
+    const V3 radiance = {lum[0] / distSq, lum[1] / distSq, lum[2] / distSq};
+    float r4 = roughness; r4 *= r4; r4 *= r4;                    // NDF :143-154
+    float cTheta = dm_max(dot(csnorm, halfvec), 0.0f);
+    cTheta *= cTheta;
+    float nd = cTheta * (r4 - 1.0f) + 1.0f;
+    nd *= nd;
+    const float normalDist = r4 / (PI_ * nd);
+    const float NdotV = dm_max(dot(csnorm, wo), 0.0f), NdotL0 = dm_max(dot(csnorm, wi), 0.0f);        // G :167-174
+    const float g = ggx_schlick(NdotL0, roughness) * ggx_schlick(NdotV, roughness);
+    const float cosTheta = dm_max(dot(wo, halfvec), 0.0f);       // metallicFresnel :134-141 (its albedo term is unused as shipped)
+    const float fresnel = 0.04f + 0.96f * O_POW(1.0f - cosTheta, 5.0f);
+    const float num = normalDist * g * fresnel;
+    const float denom = 4.0f * dm_max(dot(csnorm, wo), 0.0f) * dm_max(dot(csnorm, wi), 0.0f);
+    const float specular = num / dm_max(denom, 0.001f);
+    float diffuse = 1.0f - fresnel;
+    diffuse *= 1.0f - metallicity;
+    const V3 wid = {wi.x / dist, wi.y / dist, wi.z / dist};
+    const float NdotL = dm_max(dot(csnorm, wid), 0.0f);
+    const float ds = diffuse + specular;
+    return {ds * radiance.x * NdotL, ds * radiance.y * NdotL, ds * radiance.z * NdotL};
+}
+const float kPoisson12[12][2] = {
+    {-0.326212f, -0.40581f}, {-0.840144f, -0.07358f}, {-0.695914f, 0.457137f}, {-0.203345f, 0.620716f},
+    {0.96234f, -0.194983f},  {0.473434f, -0.480026f}, {0.519456f, 0.767022f},  {0.185461f, -0.893124f},
+    {0.507431f, 0.064425f},  {0.89642f, 0.412458f},   {-0.32194f, -0.932615f}, {-0.791559f, -0.59771f}};   // :119-132
+}  // namespace
+
+extern "C" int f184o_lighting_deferred(f184o_ctx* c, const f184_view_constants* view, const f184_extended_matrices* m,
+                                       const f184_light_list* point, const f184_light_list* directional)
+{
+    if (!c || !view || !m) return F184_ERR_INVALID_ARGUMENT;
+    double t0 = now_ms();
+    for (int s : {F184_SLOT_DEPTH, F184_SLOT_NORMALS, F184_SLOT_MATERIAL, F184_SLOT_SHADOW, F184_SLOT_LIGHTING})
+    { int rc = ensure_image(c, s); if (rc) return rc; }
+    const int np = point ? point->numLights : 0, nd = directional ? directional->numLights : 0;
+    if (np < 0 || np > 100 || nd < 0 || nd > 100) return F184_ERR_INVALID_ARGUMENT;
+    const M4 InvProj = load_m4(view->InvProj), ViewMat = load_m4(view->ViewMat), InvModelView = load_m4(m->InvModelView);
+    const M4 ShadowView = load_m4(m->ShadowView), ShadowProj = load_m4(m->ShadowProj);
+    const uint32_t W = c->cfg.width, H = c->cfg.height;
+    const float* depthp = image_ptr<float>(c, F184_SLOT_DEPTH);
+    const uint16_t* normals = image_ptr<uint16_t>(c, F184_SLOT_NORMALS);
+    const uint8_t* material = image_ptr<uint8_t>(c, F184_SLOT_MATERIAL);
+    uint16_t* out = image_ptr<uint16_t>(c, F184_SLOT_LIGHTING);
+    const LightCtx LC{image_ptr<float>(c, F184_SLOT_SHADOW), c->cfg.shadow_res};
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t y = 0; y < (int64_t)H; y++)
+        for (uint32_t x = 0; x < W; x++)
+        {
+            const float u = ((float)x + 0.5f) / (float)W, v = ((float)y + 0.5f) / (float)H;
+            const int dx = dm_f2i(u * (float)W), dy = dm_f2i(v * (float)H);
+            const float depth = (dx >= 0 && dy >= 0 && dx < (int)W && dy < (int)H) ? depthp[(size_t)dy * W + dx] : 0.0f;
+            const V4 cp = mul(InvProj, V4{u * 2.0f - 1.0f, v * 2.0f - 1.0f, depth, 1.0f});
+            const V3 cspos = {cp.x / cp.w, cp.y / cp.w, cp.z / cp.w};
+            // PINNED: texture() at a texel centre returns that texel (normals, material)
+            const uint16_t* nq = &normals[4 * ((size_t)y * W + x)];
+            const V3 csnorm = normalize(V3{fmaf(unorm16(nq[0]), 2.0f, -1.0f), fmaf(unorm16(nq[1]), 2.0f, -1.0f), fmaf(unorm16(nq[2]), 2.0f, -1.0f)});
+            const uint8_t* mq = &material[4 * ((size_t)y * W + x)];
+            const float roughness = (float)mq[1] / 255.0f, metallicity = (float)mq[2] / 255.0f;      // getMaterial = .yz, :60-70
+            V3 result = {0, 0, 0};
+            for (int i = 0; i < np; i++)
+            {
+                const f184_sun& L = point->lights[i];
+                const V4 lp = mul(ViewMat, V4{L.position[0], L.position[1], L.position[2], 1.0f});
+                result = result + illumination(V3{lp.x, lp.y, lp.z} - cspos, L.luminance, cspos, csnorm, metallicity, roughness);
+            }
+            for (int i = 0; i < nd; i++)
+            {
+                const f184_sun& L = directional->lights[i];
+                const V3 lightVector = neg(normalize(mul3(ViewMat, V3{L.position[0], L.position[1], L.position[2]})));
+                const V4 wp = mul(InvModelView, V4{cspos.x + csnorm.x * 0.01f, cspos.y + csnorm.y * 0.01f, cspos.z + csnorm.z * 0.01f, 1.0f});
+                V4 spos = mul(ShadowProj, mul(ShadowView, V4{wp.x, wp.y, wp.z, 1.0f}));                 // no divide by w, :227-229
+                spos.x = spos.x * 0.5f + 0.5f; spos.y = spos.y * 0.5f + 0.5f;
+                const float pix = 1.0f / (float)LC.S;
+                float shade = 0.0f;
+                for (int j = 0; j < 12; j++)
+                    shade += shadow_smooth(LC, spos.x + kPoisson12[j][0] * pix, spos.y + kPoisson12[j][1] * pix, spos.z + 0.0f, 0.002f);
+                shade /= 12.0f;
+                const V3 il = illumination(lightVector, L.luminance, cspos, csnorm, metallicity, roughness);
+                result = {result.x + il.x * shade, result.y + il.y * shade, result.z + il.z * shade};
+            }
+            uint16_t* o = &out[4 * ((size_t)y * W + x)];
+            o[0] = dm_f32_to_f16(result.x); o[1] = dm_f32_to_f16(result.y); o[2] = dm_f32_to_f16(result.z); o[3] = dm_f32_to_f16(1.0f);
+        }
+    (void)t0;
+    return F184_OK;
+}

@@ -47,6 +47,15 @@ struct blurY_frag
 {
 #include "_ref/gen/blurY_frag.inc"
 };
+struct aggregateLights_frag
+{
+#include "_ref/gen/aggregateLights_frag.inc"
+};
+struct color_frag
+{
+    vec4 gl_FragCoord;
+#include "_ref/gen/color_frag.inc"
+};
 struct voxel_gs
 {
     gl_in_array gl_in;
@@ -186,6 +195,40 @@ int refsh_gtao_blur(const uint16_t* ao_raw, int W, int H, uint16_t* out)
 int refsh_blur(int dir, const f184_engine_miscs* m, const uint16_t* src, const float* depth, int W, int H, uint16_t* out)
 {
     if (dir == 0) run_blur<blurX_frag>(m, src, depth, W, H, out); else run_blur<blurY_frag>(m, src, depth, W, H, out);
+    return 0;
+}
+
+// lighting_deferred, MegaPipeline.cpp:286-300.  Light lists as the reference uploads them (LightLists, :101-105).
+int refsh_lighting_deferred(const f184_view_constants* view, const f184_extended_matrices* m, const f184_light_list* point,
+                            const f184_light_list* directional, const uint8_t* albedo, const uint16_t* normals, const float* depth,
+                            const float* shadow, const uint8_t* material, int W, int H, uint16_t* out)
+{
+    typedef aggregateLights_frag S;
+    S::s.wrap = 1;                                                    // GlobalLinearSampler, MegaPipeline.cpp:287
+    S::t_albedo = tex2d(albedo, W, H, TEX_RGBA8_UNORM); S::t_normals = tex2d(normals, W, H, TEX_RGBA16_UNORM);
+    S::t_depth = tex2d(depth, W, H, TEX_R32F); S::t_shadow = tex2d(shadow, 2048, 2048, TEX_R32F);
+    S::t_material = tex2d(material, W, H, TEX_RGBA8_UNORM);
+    S::InvProj = M(view->InvProj); S::ViewMat = M(view->ViewMat); S::ProjMat = M(view->ProjMat);
+    S::InvModelView = M(m->InvModelView); S::ShadowView = M(m->ShadowView); S::ShadowProj = M(m->ShadowProj);
+    S::VoxelView = M(m->VoxelView); S::VoxelProj = M(m->VoxelProj);
+    auto fill = [](auto& dst, const f184_light_list* src) {
+        dst.numLights = src ? src->numLights : 0;
+        for (int i = 0; i < dst.numLights; i++)
+        {
+            dst.lights[i].luminance = vec3(src->lights[i].luminance[0], src->lights[i].luminance[1], src->lights[i].luminance[2]);
+            dst.lights[i].position = vec3(src->lights[i].position[0], src->lights[i].position[1], src->lights[i].position[2]);
+        }
+    };
+    fill(S::Point, point); fill(S::Directional, directional);
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int y = row_begin(); y < row_end(H); y++)
+        for (int x = 0; x < W; x++)
+        {
+            S sh;
+            sh.inUV = vec2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+            sh.main();
+            store_rgba16f(&out[4 * ((size_t)y * W + x)], sh.lightingBuffer);
+        }
     return 0;
 }
 

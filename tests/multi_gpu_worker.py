@@ -53,6 +53,35 @@ def main():
         a, b = g.ctx.readback(A.SLOT_INDIRECT_OUT)[m], one.readback(A.SLOT_INDIRECT_OUT)[m]
         if not np.array_equal(a.view(np.uint16), b.view(np.uint16)): bad.append(f"frame {frame}: own image tile rows")
         dist.barrier()
+    # back to back, no host sync between frames: the accumulation of frame f+1 runs on an internal stream beside the gather and
+    # the cone trace of frame f (f184_voxelize_accumulate, one NVLink box).  The triangle range changes every frame, so every
+    # frame's volume differs and emptied bricks must be cleared; each rank's image rows must equal the one-GPU frames.
+    T = sc.n_tris
+    f0, cnt = g.tri_range
+    own = lambda lo, hi: (max(f0, lo), max(0, min(f0 + cnt, hi) - max(f0, lo)))       # this rank's share of triangles [lo, hi)
+    spans = [(0, T), (0, T // 2), (T // 3, T), (0, T), (T // 2, T), (0, T // 4)]
+    want = []
+    for lo, hi in spans:
+        one.set_triangle_range(lo, hi - lo)
+        one.voxelize(cams["voxel"]); one.inject(k); one.build_mips(); one.trace_indirect(k)
+        want.append(one.readback(A.SLOT_INDIRECT_OUT).copy())
+    nbytes = g.ctx.image_info(A.SLOT_INDIRECT_OUT).size_bytes
+    hosts = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in spans]
+    dist.barrier()
+    for i, (lo, hi) in enumerate(spans):
+        g.ctx.set_triangle_range(*own(lo, hi))
+        g.frame(cams["voxel"], k)
+        g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, hosts[i].data_ptr(), nbytes)
+        if i:
+            g.ctx.readback_wait(1)
+    g.ctx.sync()
+    dist.barrier()
+    m = g.own_rows_mask()
+    for i in range(len(spans)):
+        got = hosts[i].numpy().view(np.uint16).reshape(H, W, 4)
+        if not np.array_equal(got[m], want[i].view(np.uint16).reshape(H, W, 4)[m]): bad.append(f"back-to-back frame {i}: own image tile rows")
+    if np.array_equal(want[0], want[1]): bad.append("back-to-back frames do not differ")
+    g.ctx.set_triangle_range(f0, cnt)
     frags = torch.tensor([float(g.ctx.counter(A.COUNTER_FRAGMENTS))], device=f"cuda:{local}")
     dist.all_reduce(frags)
     # BASELINE configs[4]: a probe batch partitioned by whole views; the volume comes from the slab schedule, each rank traces

@@ -41,7 +41,15 @@ def load():
     dll.refsh_gtao.argtypes = [C.POINTER(A.ViewConstantsC), vp, vp, C.c_int, C.c_int, vp]
     dll.refsh_gtao_blur.argtypes = [vp, C.c_int, C.c_int, vp]
     dll.refsh_blur.argtypes = [C.c_int, C.POINTER(A.EngineMiscsC), vp, vp, C.c_int, C.c_int, vp]
+    dll.refsh_lighting_deferred.argtypes = [C.POINTER(A.ViewConstantsC), C.POINTER(A.ExtendedMatricesC), C.POINTER(A.LightListC),
+                                            C.POINTER(A.LightListC), vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
     return dll
+
+
+def light_lists(k):
+    """The fixture's lights (App/MainBehaviour.cpp:34-45): one point light of luminance Color(0.1, 1.0, 0.6) * 1.0 at (0, 2, 0) and
+    the sun as the one directional light (the same PerLightConstants lighting_indirect binds as `Sun`)."""
+    return A.light_list_c([((0.1, 1.0, 0.6), (0.0, 2.0, 0.0))]), A.light_list_c([(tuple(k.sun.luminance), tuple(k.sun.position))])
 
 
 def case_inputs(case="atrium"):
@@ -49,6 +57,14 @@ def case_inputs(case="atrium"):
     sc = S.procedural_scene(seed=1) if case == "atrium" else S.load_sponza()
     cams = {n: S.fixture_constants(n) for n in ("main", "shadow", "voxel")}
     fis = [frame_inputs(sc, cams["main"], cams["shadow"], W, H, SH, f, cache=False) for f in range(FRAMES)]
+    # every Sponza material is (roughness, metallic) = (1, 1), which zeroes the diffuse term of the deferred
+    # lighting: give the pinned case a material image that sweeps both, so that whole BRDF is exercised
+    yy, xx = np.mgrid[0:H, 0:W]
+    for fi in fis:
+        m = np.zeros((H, W, 4), np.uint8)
+        m[..., 1] = (xx * 7 + yy * 3) % 256
+        m[..., 2] = (xx * 5 + yy * 11) % 256
+        fi["material"] = m
     return sc, cams, fis
 
 
@@ -57,7 +73,7 @@ def input_digest(sc, fis):
     for a in (sc.pos, sc.nrm, sc.uv, sc.idx):
         h.update(np.ascontiguousarray(a).tobytes())
     for fi in fis:
-        for k in ("depth", "normals", "shadow"):
+        for k in ("depth", "normals", "shadow", "albedo", "material"):
             h.update(np.ascontiguousarray(fi[k]).tobytes())
     return h.hexdigest()
 
@@ -90,7 +106,12 @@ def run_reference_shaders(oracle_lib, sc, cams, fis):
         bx, by = np.zeros((H, W, 4), np.uint16), np.zeros((H, W, 4), np.uint16)
         dll.refsh_blur(0, C.byref(k.miscs), ptr(ind), ptr(depth), W, H, ptr(bx))
         dll.refsh_blur(1, C.byref(k.miscs), ptr(bx), ptr(depth), W, H, ptr(by))
-        out.update({f"indirect{f}": ind, f"ao_raw{f}": raw, f"ao{f}": ao, f"blur_x{f}": bx, f"blur{f}": by})
+        lit = np.zeros((H, W, 4), np.uint16)
+        albedo, material = (np.ascontiguousarray(fi[k_]) for k_ in ("albedo", "material"))
+        pl, dl = light_lists(k)
+        dll.refsh_lighting_deferred(C.byref(k.view), C.byref(k.ext), C.byref(pl), C.byref(dl), ptr(albedo), ptr(normals), ptr(depth),
+                                    ptr(shadow), ptr(material), W, H, ptr(lit))
+        out.update({f"indirect{f}": ind, f"ao_raw{f}": raw, f"ao{f}": ao, f"blur_x{f}": bx, f"blur{f}": by, f"lighting{f}": lit})
         hist = ind.copy()                      # CopyImage(indirectImage -> indirectTemporalImage), MegaPipeline.cpp:211-214
     return out
 
@@ -103,7 +124,8 @@ def run_library(lib, sc, cams, fis):
     out = dict(voxels=c.readback(A.SLOT_VOXELS).copy(), fragments=np.int64(c.counter(A.COUNTER_FRAGMENTS)))
     u16 = lambda a: np.ascontiguousarray(a).view(np.uint16).reshape(H, W, 4).copy()
     for f, fi in enumerate(fis):
-        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_SHADOW, "shadow")):
+        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_SHADOW, "shadow"), (A.SLOT_ALBEDO, "albedo"),
+                          (A.SLOT_MATERIAL, "material")):
             c.upload(slot, fi[key])
         k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, f, f == 0)
         if f > 0:
@@ -111,7 +133,8 @@ def run_library(lib, sc, cams, fis):
         c.trace_indirect(k)
         c.gtao(cams["main"])
         c.blur_indirect(k)
-        out.update({f"indirect{f}": u16(c.readback(A.SLOT_INDIRECT_OUT)), f"ao_raw{f}": u16(c.readback(A.SLOT_AO_RAW)),
+        c.lighting_deferred(k, *light_lists(k))
+        out.update({f"lighting{f}": u16(c.readback(A.SLOT_LIGHTING)),f"indirect{f}": u16(c.readback(A.SLOT_INDIRECT_OUT)), f"ao_raw{f}": u16(c.readback(A.SLOT_AO_RAW)),
                     f"ao{f}": u16(c.readback(A.SLOT_AO_OUT)), f"blur_x{f}": u16(c.readback(A.SLOT_INDIRECT_BLUR_X)),
                     f"blur{f}": u16(c.readback(A.SLOT_INDIRECT_FINAL))})
     c.close()

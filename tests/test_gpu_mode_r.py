@@ -123,3 +123,31 @@ def test_cuda_matches_reference_shader_text_golden(cuda_lib, case):
     got = R.run_library(cuda_lib, sc, cams_, fis)
     assert int(got["fragments"]) == int(golden["fragments"]) > 10000
     assert R.compare(got, golden) == []
+
+
+def test_deferred_lighting_bit_exact(cuda_lib, oracle_lib, proc_scene, cams):
+    """lighting_deferred (aggregateLights.frag) at a non-power-of-two size with three point lights and two directional lights:
+    RGBA16F output equal bit for bit to the oracle's restatement (itself pinned to the shader text)."""
+    w, h, sh = 320, 184, 1024
+    fi = frame_inputs(proc_scene, cams["main"], cams["shadow"], w, h, sh, 0, cache=False)
+    yy, xx = np.mgrid[0:h, 0:w]
+    mat = np.zeros((h, w, 4), np.uint8); mat[..., 1] = (xx * 7 + yy * 3) % 256; mat[..., 2] = (xx * 5 + yy * 11) % 256
+    k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], w, h, 0, True)
+    point = A.light_list_c([((0.1, 1.0, 0.6), (0.0, 2.0, 0.0)), ((3.0, 0.5, 0.2), (-4.0, 1.0, -2.0)), ((0.0, 0.0, 9.0), (5.0, 6.0, 1.0))])
+    sun = (tuple(k.sun.luminance), tuple(k.sun.position))
+    directional = A.light_list_c([sun, ((0.5, 0.5, 1.5), (0.3, -0.8, 0.52))])
+    outs = []
+    for lib in (cuda_lib, oracle_lib):
+        c = A.VoxelGI(grid_n=32, width=w, height=h, mode=A.MODE_REFERENCE, shadow_res=sh, lib=lib)
+        for slot, arr in ((A.SLOT_DEPTH, fi["depth"]), (A.SLOT_NORMALS, fi["normals"]), (A.SLOT_SHADOW, fi["shadow"]), (A.SLOT_MATERIAL, mat)):
+            c.upload(slot, arr)
+        c.lighting_deferred(k, point, directional)
+        a = c.readback(A.SLOT_LIGHTING).copy()
+        c.lighting_deferred(k, A.LightListC(), A.LightListC())
+        z = c.readback(A.SLOT_LIGHTING).copy()
+        outs.append((a, z))
+        c.close()
+    (ag, zg), (ao, zo) = outs
+    assert np.array_equal(Hh.bits16(ag), Hh.bits16(ao)), f"{np.count_nonzero(Hh.bits16(ag) != Hh.bits16(ao))} values differ"
+    assert ao[..., :3].astype(np.float32).mean() > 1e-3 and np.isfinite(ao.astype(np.float32)).all()
+    assert np.array_equal(Hh.bits16(zg), Hh.bits16(zo)) and not zo[..., :3].any() and (zo[..., 3] == 1).all()     # no lights: black, alpha 1

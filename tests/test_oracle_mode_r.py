@@ -163,3 +163,51 @@ def test_gtao_range_and_blur_is_a_4x4_mean(oracle_lib, proc_scene, cams):
     # GTAO/blur.frag:12-27: mean of the 4x4 neighbourhood [x-1, x+2] x [y-1, y+2] (wrap addressing at the border)
     y, x = 10, 20
     assert abs(out[y, x] - raw[y - 1:y + 3, x - 1:x + 3].mean()) < 2e-3
+
+
+def test_deferred_lighting_properties(oracle_lib, proc_scene):
+    """lighting_deferred (aggregateLights.frag) on the oracle: no lights -> (0, 0, 0, 1); light lists add up; a fully metallic
+    material has no diffuse term, so roughness 1 + metallic 1 (every Sponza material) leaves only the weak specular lobe."""
+    cams = {n: S.fixture_constants(n) for n in ("main", "shadow", "voxel")}
+    w, h, sh = 64, 32, 256
+    fi = frame_inputs(proc_scene, cams["main"], cams["shadow"], w, h, sh, 0, cache=False)
+    k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], w, h, 0, True)
+    c = A.VoxelGI(grid_n=32, width=w, height=h, mode=A.MODE_REFERENCE, shadow_res=sh, lib=oracle_lib)
+    for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_SHADOW, "shadow")):
+        c.upload(slot, fi[key])
+    f32 = lambda: c.readback(A.SLOT_LIGHTING).astype(np.float32)
+
+    def run(material, point, directional):
+        c.upload(A.SLOT_MATERIAL, material)
+        c.lighting_deferred(k, A.light_list_c(point), A.light_list_c(directional))
+        return f32()
+
+    dielectric = np.zeros((h, w, 4), np.uint8); dielectric[..., 1] = 128
+    metal = dielectric.copy(); metal[..., 2] = 255
+    none = run(dielectric, [], [])
+    assert not none[..., :3].any() and (none[..., 3] == 1).all()
+    p1, p2 = ((2.0, 1.0, 0.5), (0.0, 2.0, 0.0)), ((0.5, 3.0, 1.0), (3.0, 4.0, -2.0))
+    a, b, ab = run(dielectric, [p1], []), run(dielectric, [p2], []), run(dielectric, [p1, p2], [])
+    assert a[..., :3].mean() > 1e-3 and b[..., :3].mean() > 1e-3
+    assert np.allclose(ab[..., :3], a[..., :3] + b[..., :3], rtol=4e-3, atol=1e-4)          # one fp16 rounding apart
+    m = run(metal, [p1], [])
+    assert m[..., :3].mean() < 0.5 * a[..., :3].mean()                                      # the diffuse term is gone
+    c.close()
+    # the sun: an open floor is lit; the same floor under a roof is in shadow everywhere (12 x 4 shadow taps all fail)
+    sun = ((4.4, 3.72, 3.24), tuple(k.sun.position))
+    floor = ((-12, 0, -12), (24, 0, 0), (0, 0, 24), (0, 1, 0))
+    roof = ((-14, 9, -14), (28, 0, 0), (0, 0, 28), (0, 1, 0))
+    means = []
+    for quads in ([floor], [floor, roof]):
+        sc = Hc.quad_scene(quads)
+        fi2 = frame_inputs(sc, cams["main"], cams["shadow"], w, h, sh, 0, cache=False)
+        c2 = A.VoxelGI(grid_n=32, width=w, height=h, mode=A.MODE_REFERENCE, shadow_res=sh, lib=oracle_lib)
+        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_SHADOW, "shadow")):
+            c2.upload(slot, fi2[key])
+        c2.upload(A.SLOT_MATERIAL, dielectric)
+        c2.lighting_deferred(k, A.light_list_c([]), A.light_list_c([sun]))
+        img = c2.readback(A.SLOT_LIGHTING).astype(np.float32)
+        on_floor = fi2["depth"] < 1.0
+        means.append(float(img[on_floor][:, :3].mean()))
+        c2.close()
+    assert means[0] > 0.05 and means[1] == 0.0, means
