@@ -26,10 +26,10 @@ MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
 (SLOT_DEPTH, SLOT_NORMALS, SLOT_ALBEDO, SLOT_MATERIAL, SLOT_SHADOW, SLOT_VOXELS, SLOT_INDIRECT_OUT,
  SLOT_INDIRECT_HISTORY, SLOT_AO_RAW, SLOT_AO_OUT, SLOT_INDIRECT_BLUR_X, SLOT_INDIRECT_FINAL,
  SLOT_ACCUM_COLOR, SLOT_ACCUM_NORMAL, SLOT_VOX_ALBEDO, SLOT_VOX_NORMAL, SLOT_RADIANCE, SLOT_MIPS,
- SLOT_BRICK_FLAGS, SLOT_LIGHTING, SLOT_COUNT) = range(21)
+ SLOT_BRICK_FLAGS, SLOT_LIGHTING, SLOT_TAA_HISTORY, SLOT_TAA_OUT, SLOT_COLOR_OUT, SLOT_COUNT) = range(24)
 (STAGE_CLEAR, STAGE_VOXELIZE, STAGE_NORMALISE, STAGE_INJECT, STAGE_MIPS, STAGE_TRACE, STAGE_GTAO,
- STAGE_BLUR, STAGE_EXCHANGE, STAGE_LIGHTING, STAGE_COUNT) = range(11)
-STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur", "exchange", "lighting"]
+ STAGE_BLUR, STAGE_EXCHANGE, STAGE_LIGHTING, STAGE_COMPOSITE, STAGE_COUNT) = range(12)
+STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur", "exchange", "lighting", "composite"]
 (COUNTER_FRAGMENTS, COUNTER_MARCH_STEPS, COUNTER_OCCUPIED, COUNTER_KERNEL_LAUNCHES, COUNTER_BRICKS) = range(5)
 (IPC_ACCUM_COLOR, IPC_ACCUM_NORMAL, IPC_BRICK_FLAGS, IPC_EXPORT, IPC_COUNTERS, IPC_BRICK_LIST, IPC_SYNC, IPC_COUNT) = range(8)
 FLAG_EXTERNAL_RANDS = 1
@@ -166,6 +166,8 @@ _SIGS = {
     "gtao": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC)]),
     "blur_indirect": (C.c_int, [C.c_void_p, C.POINTER(EngineMiscsC)]),
     "copy_indirect_to_history": (C.c_int, [C.c_void_p]),
+    "copy_taa_to_history": (C.c_int, [C.c_void_p]),
+    "composite": (C.c_int, [C.c_void_p, C.POINTER(TraceConstantsC)]),
     "lighting_deferred": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC), C.POINTER(ExtendedMatricesC), C.POINTER(LightListC), C.POINTER(LightListC)]),
     "bind_rands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "set_triangle_range": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
@@ -376,6 +378,12 @@ class VoxelGI:
             directional = light_list_c([(tuple(k.sun.luminance), tuple(k.sun.position))])
         point = point if point is not None else LightListC()
         self._ck(self.lib.lighting_deferred(self.h, C.byref(k.view), C.byref(k.ext), C.byref(point), C.byref(directional)), "lighting_deferred")
+
+    def composite(self, k: TraceConstantsC):
+        self._ck(self.lib.composite(self.h, C.byref(k)), "composite")
+
+    def copy_taa_to_history(self):
+        self._ck(self.lib.copy_taa_to_history(self.h), "copy_taa_to_history")
 
     def copy_indirect_to_history(self):
         self._ck(self.lib.copy_indirect_to_history(self.h), "copy_indirect_to_history")

@@ -21,7 +21,7 @@ OUT = os.path.join(HERE, "libf184.so")
 OBJ = os.path.join(HERE, "_obj")
 
 FAITHFUL = ["f184_api.cu", "mode_r_voxelize.cu", "mode_r_trace.cu", "gtao.cu", "blur.cu", "debug_hooks.cu",
-            "mode_n_voxelize.cu", "mode_n_inject.cu", "mode_n_mips.cu", "lighting.cu"]
+            "mode_n_voxelize.cu", "mode_n_inject.cu", "mode_n_mips.cu", "lighting.cu", "composite.cu"]
 FAST = [f for f in sorted(os.listdir(HERE)) if f.endswith(".cu") and f not in FAITHFUL]
 HEADERS = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".h", ".cuh"))] + \
           [os.path.join(HERE, "..", "..", "include", "f184.h")]

@@ -64,6 +64,9 @@ static bool default_desc(const f184_config& c, int slot, f184_image_desc* d)
     case F184_SLOT_AO_OUT:
     case F184_SLOT_INDIRECT_BLUR_X:
     case F184_SLOT_LIGHTING:
+    case F184_SLOT_TAA_HISTORY:
+    case F184_SLOT_TAA_OUT:
+    case F184_SLOT_COLOR_OUT:
     case F184_SLOT_INDIRECT_FINAL: set(F184_FMT_R16G16B16A16_SFLOAT, W, H, 1); break;
     case F184_SLOT_ACCUM_COLOR:
     case F184_SLOT_ACCUM_NORMAL: set(F184_FMT_R32G32B32A32_SFLOAT, N, N, N); break;
@@ -310,6 +313,7 @@ void f184_destroy(f184_ctx* c)
     if (c->ev_consumed) cudaEventDestroy(c->ev_consumed);
     if (c->ev_barrier) cudaEventDestroy(c->ev_barrier);
     if (c->lights_dev) cudaFree(c->lights_dev);
+    if (c->r_queue) cudaFree(c->r_queue);
     delete c;
 }
 
@@ -794,6 +798,21 @@ int f184_lighting_deferred(f184_ctx* c, const f184_view_constants* view, const f
     if (!c || !view || !m) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "lighting_deferred: null argument");
     CK(c, cudaSetDevice(c->cfg.device));
     return f184_lighting_impl(c, view, m, point, directional);
+}
+int f184_composite(f184_ctx* c, const f184_trace_constants* k)
+{
+    if (!c || !k) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "composite: null argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    return f184_composite_impl(c, k);
+}
+int f184_copy_taa_to_history(f184_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    int rc = f184_ensure_image(c, F184_SLOT_TAA_OUT); if (rc) return rc;
+    rc = f184_ensure_image(c, F184_SLOT_TAA_HISTORY); if (rc) return rc;
+    CK(c, cudaMemcpyAsync(c->img[F184_SLOT_TAA_HISTORY].ptr, c->img[F184_SLOT_TAA_OUT].ptr, c->img[F184_SLOT_TAA_OUT].desc.size_bytes,
+                          cudaMemcpyDeviceToDevice, c->stream));
+    return F184_OK;
 }
 int f184_copy_indirect_to_history(f184_ctx* c)
 {

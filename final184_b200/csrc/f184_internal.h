@@ -94,6 +94,8 @@ struct f184_ctx
     DevImage img[F184_SLOT_COUNT];
     // mode R: ordered-store keys, (draw order + 1) << 32 | texel
     unsigned long long* vox_keys = nullptr;
+    void* r_queue = nullptr;                  // mode R voxelizer: [16 B header: count] + one set-up record per large triangle
+    uint32_t r_queue_cap = 0;
     // mode N
     std::vector<MipLevelInfo> mip_levels;     // index 0 = level 1
     cudaArray_t rad_array = nullptr;          // level-0 radiance as a 3D array for hardware filtering
@@ -196,6 +198,7 @@ int f184_voxelize_r(f184_ctx* c, const f184_view_constants* cam);
 int f184_trace_r(f184_ctx* c, const f184_trace_constants* k);
 int f184_gtao_impl(f184_ctx* c, const f184_view_constants* view);
 int f184_blur_impl(f184_ctx* c, const f184_engine_miscs* miscs);
+int f184_composite_impl(f184_ctx* c, const f184_trace_constants* k);
 int f184_lighting_impl(f184_ctx* c, const f184_view_constants* view, const f184_extended_matrices* m, const f184_light_list* point,
                        const f184_light_list* directional);
 int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam);

@@ -106,6 +106,21 @@ __device__ f3 get_indirect(const TraceParams& P, f3 wpos, f3 wnorm, float seed, 
     f3 sv = voxel_pos(P.w2voxel, wpos, Nf);
     int pvx = dm_f2i(sv.x), pvy = dm_f2i(sv.y), pvz = dm_f2i(sv.z);
     uint32_t i = 0;
+    // ~15 % of the reference's rays have a NaN direction (blugausnoise2 leaves [0, 1]).  Under the pinned NaN
+    // rules such a ray never leaves the loop: every comparison is false, ivec3(NaN) = (0,0,0), so it reads voxel (0,0,0) at most
+    // once and then spins for all `steps` iterations, and its sky term is x * smoothstep(NaN) = 0.  With first-hit divergence
+    // that tail is what the other 31 lanes of the warp wait for.  It is skipped here with the same outcome: Lo = 0, no hit,
+    // `steps` counted.  (If voxel (0,0,0) is occupied the general loop below still handles the ray.)
+    if (dm_isnan(dir.x))
+    {
+        uint32_t texel0 = 0;
+        if ((pvx | pvy | pvz) != 0 && P.steps) texel0 = __ldg(P.vox);
+        if ((texel0 & 0xffffu) == 0)
+        {
+            steps_taken += P.steps;
+            return Lo;
+        }
+    }
     for (; i < P.steps; i++)
     {
         steps_taken++;

@@ -86,12 +86,81 @@ __device__ __forceinline__ f4 sample_trilinear(const TexDev& t, float u, float v
 __device__ __forceinline__ long long ceil_div256(long long a) { return (a + 255) >> 8; }     // arithmetic shift = floor
 __device__ __forceinline__ long long floor_div256(long long a) { return a >> 8; }
 
+// One candidate pixel of one set-up triangle: coverage (integer edge functions, top-left rule), depth clip, material, pack,
+// ordered store.  Returns 1 if a texel was stored.
+struct EdgeSetup { long long ex[3], ey[3]; int bias[3]; float areaf; };
+__device__ __forceinline__ EdgeSetup edge_setup(const TriShared& s)
+{
+    EdgeSetup E;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+    {
+        const int a = (k + 1) % 3, b = (k + 2) % 3;
+        E.ex[k] = (long long)s.x[b] - s.x[a]; E.ey[k] = (long long)s.y[b] - s.y[a];
+        const bool top_left = (E.ey[k] < 0) || (E.ey[k] == 0 && E.ex[k] > 0);
+        E.bias[k] = top_left ? 0 : -1;
+    }
+    E.areaf = (float)s.area;
+    return E;
+}
+__device__ __forceinline__ unsigned int shade_pixel(const TriShared& s, const EdgeSetup& E, const MatDev& mat, const TexDev* __restrict__ texs,
+                                                    int px, int py, uint32_t N, float maxDepth, unsigned long long* __restrict__ keys)
+{
+    const long long cxp = (long long)px * 256 + 128, cyp = (long long)py * 256 + 128;
+    long long w[3];
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+    {
+        const int a = (k + 1) % 3;
+        w[k] = E.ex[k] * (cyp - s.y[a]) - E.ey[k] * (cxp - s.x[a]);
+        if (w[k] + E.bias[k] < 0) inside = false;
+    }
+    if (!inside) return 0;
+    const float areaf = E.areaf;
+    const float b0 = (float)w[0] / areaf, b1 = (float)w[1] / areaf, b2 = (float)w[2] / areaf;
+    const float z = (s.cz[0] * b0 + s.cz[1] * b1) + s.cz[2] * b2;
+    if (!(z >= 0.0f && z <= 1.0f)) return 0;                    // depth clip, no clamp
+    const float u = (s.u[0] * b0 + s.u[1] * b1) + s.u[2] * b2;
+    const float v = (s.v[0] * b0 + s.v[1] * b1) + s.v[2] * b2;
+    const f3 n = {(s.n[0].x * b0 + s.n[1].x * b1) + s.n[2].x * b2, (s.n[0].y * b0 + s.n[1].y * b1) + s.n[2].y * b2,
+                  (s.n[0].z * b0 + s.n[1].z * b1) + s.n[2].z * b2};
+    // ---- BasicMaterial, main.lua:188-205
+    f4 base;
+    if (!mat.use_textures) base = {mat.factor[0], mat.factor[1], mat.factor[2], mat.factor[3]};
+    else
+    {
+        f4 sc = {0.f, 0.f, 0.f, 0.f};
+        if (mat.tex >= 0) sc = sample_trilinear(texs[mat.tex], u, v, s.dudx, s.dvdx, s.dudy, s.dvdy);
+        base = {sc.x * mat.factor[0], sc.y * mat.factor[1], sc.z * mat.factor[2], sc.w * mat.factor[3]};
+        if (base.w < 0.05f) return 0;                            // discard
+    }
+    // ---- VoxelPS, main.lua:249-273
+    const float fxc = (float)px + 0.5f, fyc = (float)py + 0.5f;
+    float vx, vy, vz;
+    if (s.orient == 0) { vx = fxc; vy = fyc; vz = z * maxDepth; }
+    else if (s.orient == 1) { vx = (1.0f - z) * maxDepth; vy = fyc; vz = fxc; }
+    else { vx = fxc; vy = z * maxDepth; vz = maxDepth - fyc; }
+    const int ix = dm_f2i(vx), iy = dm_f2i(vy), iz = dm_f2i(vz);
+    if (ix < 0 || iy < 0 || iz < 0 || ix >= (int)N || iy >= (int)N || iz >= (int)N) return 0;
+    const uint32_t pc = (dm_f2uint(base.x * 31.0f) << 11) | (dm_f2uint(base.y * 63.0f) << 5) | dm_f2uint(base.z * 31.0f);
+    const uint32_t pn = (dm_f2uint(n.x * 16.0f + 15.0f) << 11) | (dm_f2uint(n.y * 32.0f + 31.0f) << 5) | dm_f2uint(n.z * 16.0f + 15.0f);
+    const unsigned long long key = ((unsigned long long)(s.tri + 1u) << 32) | ((pn & 0xffffu) << 16) | (pc & 0xffffu);
+    atomicMax(keys + (((size_t)iz * N + iy) * N + ix), key);
+    return 1;
+}
+
+// A bounding box of more than this many pixels goes to the second launch (one CTA per triangle); below it the owning warp
+// drains it on the spot (<= 4 strides of 32 lanes).
+constexpr int BIG_BOX = 128;
+
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_voxelize_r(const float* __restrict__ pos, const float* __restrict__ nrm, const float* __restrict__ uv,
              const uint32_t* __restrict__ idx, const uint16_t* __restrict__ tri_mat, const uint16_t* __restrict__ tri_model,
              const M4* __restrict__ model_mats, const M4* __restrict__ vm_mats, M4 Proj, const TexDev* __restrict__ texs,
              const MatDev* __restrict__ mats, uint32_t tri_first, uint32_t tri_end, uint32_t N,
-             unsigned long long* __restrict__ keys, unsigned long long* __restrict__ frag_counter)
+             unsigned long long* __restrict__ keys, unsigned long long* __restrict__ frag_counter, TriShared* __restrict__ big_queue,
+             unsigned int* __restrict__ big_count)
 {
     __shared__ TriShared sh[WARPS_PER_BLOCK][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -179,6 +248,13 @@ k_voxelize_r(const float* __restrict__ pos, const float* __restrict__ nrm, const
             }
         }
     }
+    // large bounding boxes leave the warp: a floor quad covering the whole 128^2 viewport is 512 strides of this warp, and 32 of
+    // them in one warp were the kernel's long pole (6.3 ms at 128^3); they are rasterised by k_voxelize_r_big, one CTA each
+    if (active && sh[warp][lane].bw * sh[warp][lane].bh > BIG_BOX)
+    {
+        big_queue[atomicAdd(big_count, 1u)] = sh[warp][lane];
+        active = false;
+    }
     unsigned int pending = __ballot_sync(0xffffffffu, active);
     __syncwarp();
     unsigned int frags = 0;
@@ -187,64 +263,38 @@ k_voxelize_r(const float* __restrict__ pos, const float* __restrict__ nrm, const
         const int src = __ffs(pending) - 1;
         pending &= pending - 1;
         const TriShared& s = sh[warp][src];
-        long long ex[3], ey[3];
-        int bias[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-        {
-            const int a = (k + 1) % 3, b = (k + 2) % 3;
-            ex[k] = (long long)s.x[b] - s.x[a]; ey[k] = (long long)s.y[b] - s.y[a];
-            const bool top_left = (ey[k] < 0) || (ey[k] == 0 && ex[k] > 0);
-            bias[k] = top_left ? 0 : -1;
-        }
-        const float areaf = (float)s.area;
+        const EdgeSetup E = edge_setup(s);
         const MatDev mat = mats[s.mat];
         const int npix = s.bw * s.bh;
         for (int p = lane; p < npix; p += 32)
-        {
-            const int px = s.px0 + p % s.bw, py = s.py0 + p / s.bw;
-            const long long cxp = (long long)px * 256 + 128, cyp = (long long)py * 256 + 128;
-            long long w[3];
-            bool inside = true;
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-            {
-                const int a = (k + 1) % 3;
-                w[k] = ex[k] * (cyp - s.y[a]) - ey[k] * (cxp - s.x[a]);
-                if (w[k] + bias[k] < 0) inside = false;
-            }
-            if (!inside) continue;
-            const float b0 = (float)w[0] / areaf, b1 = (float)w[1] / areaf, b2 = (float)w[2] / areaf;
-            const float z = (s.cz[0] * b0 + s.cz[1] * b1) + s.cz[2] * b2;
-            if (!(z >= 0.0f && z <= 1.0f)) continue;                    // depth clip, no clamp
-            const float u = (s.u[0] * b0 + s.u[1] * b1) + s.u[2] * b2;
-            const float v = (s.v[0] * b0 + s.v[1] * b1) + s.v[2] * b2;
-            const f3 n = {(s.n[0].x * b0 + s.n[1].x * b1) + s.n[2].x * b2, (s.n[0].y * b0 + s.n[1].y * b1) + s.n[2].y * b2,
-                          (s.n[0].z * b0 + s.n[1].z * b1) + s.n[2].z * b2};
-            // ---- BasicMaterial, main.lua:188-205
-            f4 base;
-            if (!mat.use_textures) base = {mat.factor[0], mat.factor[1], mat.factor[2], mat.factor[3]};
-            else
-            {
-                f4 sc = {0.f, 0.f, 0.f, 0.f};
-                if (mat.tex >= 0) sc = sample_trilinear(texs[mat.tex], u, v, s.dudx, s.dvdx, s.dudy, s.dvdy);
-                base = {sc.x * mat.factor[0], sc.y * mat.factor[1], sc.z * mat.factor[2], sc.w * mat.factor[3]};
-                if (base.w < 0.05f) continue;                            // discard
-            }
-            // ---- VoxelPS, main.lua:249-273
-            const float fxc = (float)px + 0.5f, fyc = (float)py + 0.5f;
-            float vx, vy, vz;
-            if (s.orient == 0) { vx = fxc; vy = fyc; vz = z * maxDepth; }
-            else if (s.orient == 1) { vx = (1.0f - z) * maxDepth; vy = fyc; vz = fxc; }
-            else { vx = fxc; vy = z * maxDepth; vz = maxDepth - fyc; }
-            const int ix = dm_f2i(vx), iy = dm_f2i(vy), iz = dm_f2i(vz);
-            if (ix < 0 || iy < 0 || iz < 0 || ix >= (int)N || iy >= (int)N || iz >= (int)N) continue;
-            const uint32_t pc = (dm_f2uint(base.x * 31.0f) << 11) | (dm_f2uint(base.y * 63.0f) << 5) | dm_f2uint(base.z * 31.0f);
-            const uint32_t pn = (dm_f2uint(n.x * 16.0f + 15.0f) << 11) | (dm_f2uint(n.y * 32.0f + 31.0f) << 5) | dm_f2uint(n.z * 16.0f + 15.0f);
-            const unsigned long long key = ((unsigned long long)(s.tri + 1u) << 32) | ((pn & 0xffffu) << 16) | (pc & 0xffffu);
-            atomicMax(keys + (((size_t)iz * N + iy) * N + ix), key);
-            frags++;
-        }
+            frags += shade_pixel(s, E, mat, texs, s.px0 + p % s.bw, s.py0 + p / s.bw, N, maxDepth, keys);
+    }
+    warp_count_add(frag_counter, frags);
+}
+
+// Second launch: the queued large triangles, one CTA per triangle at a time (grid-stride over the queue), threads striding over
+// the bounding box row by row.  Scheduling is free: the 64-bit ordered store makes the result independent of it.
+constexpr int BIG_THREADS = 256;
+__global__ void __launch_bounds__(BIG_THREADS)
+k_voxelize_r_big(const TriShared* __restrict__ big_queue, const unsigned int* __restrict__ big_count, const TexDev* __restrict__ texs,
+                 const MatDev* __restrict__ mats, uint32_t N, unsigned long long* __restrict__ keys, unsigned long long* __restrict__ frag_counter)
+{
+    __shared__ TriShared s;
+    const unsigned int n = *big_count;
+    const float maxDepth = (float)(N - 1);
+    unsigned int frags = 0;
+    for (unsigned int q = blockIdx.x; q < n; q += gridDim.x)
+    {
+        __syncthreads();
+        // the record is 30 words: the first 30 threads copy it
+        if (threadIdx.x < sizeof(TriShared) / 4) reinterpret_cast<uint32_t*>(&s)[threadIdx.x] = reinterpret_cast<const uint32_t*>(big_queue + q)[threadIdx.x];
+        __syncthreads();
+        const EdgeSetup E = edge_setup(s);
+        const MatDev mat = mats[s.mat];
+        // a thread keeps its column offset and walks down rows in steps that cover BIG_THREADS pixels
+        const int npix = s.bw * s.bh;
+        for (int p = threadIdx.x; p < npix; p += BIG_THREADS)
+            frags += shade_pixel(s, E, mat, texs, s.px0 + p % s.bw, s.py0 + p / s.bw, N, maxDepth, keys);
     }
     warp_count_add(frag_counter, frags);
 }
@@ -303,11 +353,24 @@ int f184_voxelize_r(f184_ctx* c, const f184_view_constants* cam)
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_FRAGMENTS, 0, 8, c->stream));
     if (end > first)
     {
+        static_assert(sizeof(TriShared) % 4 == 0 && sizeof(TriShared) / 4 <= BIG_THREADS, "queue record is copied one word per thread");
+        if (c->r_queue_cap < c->n_tris)
+        {   // worst case every triangle is large
+            if (c->r_queue) cudaFree(c->r_queue);
+            CK(c, cudaMalloc(&c->r_queue, sizeof(TriShared) * (size_t)c->n_tris + 16));
+            c->r_queue_cap = c->n_tris;
+        }
+        TriShared* queue = reinterpret_cast<TriShared*>(reinterpret_cast<char*>(c->r_queue) + 16);
+        unsigned int* qcount = reinterpret_cast<unsigned int*>(c->r_queue);
+        CK(c, cudaMemsetAsync(qcount, 0, 4, c->stream));
         const uint32_t tris = end - first;
         const uint32_t blocks = (tris + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32);
         k_voxelize_r<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(c->pos, c->nrm, c->uv, c->idx, c->tri_mat, c->tri_model,
                                                                      c->model_mats, vm_dev, Proj, c->tex_dev, c->mat_dev, first, end, N,
-                                                                     c->vox_keys, c->counters_dev + F184_COUNTER_FRAGMENTS);
+                                                                     c->vox_keys, c->counters_dev + F184_COUNTER_FRAGMENTS, queue, qcount);
+        CK_LAUNCH(c);
+        k_voxelize_r_big<<<148 * 8, BIG_THREADS, 0, c->stream>>>(queue, qcount, c->tex_dev, c->mat_dev, N, c->vox_keys,
+                                                                 c->counters_dev + F184_COUNTER_FRAGMENTS);
         CK_LAUNCH(c);
     }
     {

@@ -76,7 +76,10 @@ typedef enum f184_slot {
     F184_SLOT_BRICK_FLAGS = 18,     /* u32 per 8^3 brick: touched this frame                (N/8)^3 */
     /* the consumer next to the voxel-GI section */
     F184_SLOT_LIGHTING = 19,        /* lightingImage (lighting_deferred target), R16G16B16A16_SFLOAT  W x H */
-    F184_SLOT_COUNT = 20
+    F184_SLOT_TAA_HISTORY = 20,     /* taaImageB: last frame's anti-aliased colour (rgb, -viewZ), RGBA16F  W x H */
+    F184_SLOT_TAA_OUT = 21,         /* taaImageA: gtao_color target 1, RGBA16F                             W x H */
+    F184_SLOT_COLOR_OUT = 22,       /* gtao_color target 0 (the reference renders it into the swap-chain image; here RGBA16F) */
+    F184_SLOT_COUNT = 23
 } f184_slot;
 
 typedef enum f184_format {
@@ -215,7 +218,8 @@ typedef enum f184_stage_id {
     F184_STAGE_BLUR = 7,
     F184_STAGE_EXCHANGE = 8,       /* multi-GPU: peer barriers + gather of the other ranks' bricks */
     F184_STAGE_LIGHTING = 9,       /* f184_lighting_deferred */
-    F184_STAGE_COUNT = 10
+    F184_STAGE_COMPOSITE = 10,     /* f184_composite */
+    F184_STAGE_COUNT = 11
 } f184_stage_id;
 
 typedef enum f184_counter_id {
@@ -297,6 +301,12 @@ int f184_blur_indirect(f184_ctx* ctx, const f184_engine_miscs* miscs);
  * NORMALS, MATERIAL, SHADOW; writes F184_SLOT_LIGHTING.  Either list may be NULL (= empty). */
 int f184_lighting_deferred(f184_ctx* ctx, const f184_view_constants* view, const f184_extended_matrices* matrices,
                            const f184_light_list* point_lights, const f184_light_list* directional_lights);
+/* gtao_color pass, MegaPipeline.cpp:302-319 (Shader/GTAO/color.frag): albedo^2.2 * (ao * indirect + lighting), sky scattering or
+ * volumetric light, tonemap, temporal AA and motion blur.  Reads ALBEDO, AO_OUT, DEPTH, LIGHTING, SHADOW, INDIRECT_FINAL and
+ * TAA_HISTORY; writes COLOR_OUT and TAA_OUT.  constants->reset_history = 1 clears TAA_HISTORY first (:197-201). */
+int f184_composite(f184_ctx* ctx, const f184_trace_constants* constants);
+/* CopyImage(taaImageA -> taaImageB), MegaPipeline.cpp:207-210. */
+int f184_copy_taa_to_history(f184_ctx* ctx);
 /* CopyImage(indirectImage -> indirectTemporalImage), MegaPipeline.cpp:211-214. */
 int f184_copy_indirect_to_history(f184_ctx* ctx);
 

@@ -61,6 +61,9 @@ static bool default_desc(const f184_config& c, int slot, f184_image_desc* d)
     case F184_SLOT_AO_OUT:
     case F184_SLOT_INDIRECT_BLUR_X:
     case F184_SLOT_LIGHTING:
+    case F184_SLOT_TAA_HISTORY:
+    case F184_SLOT_TAA_OUT:
+    case F184_SLOT_COLOR_OUT:
     case F184_SLOT_INDIRECT_FINAL: set(F184_FMT_R16G16B16A16_SFLOAT, W, H, 1); break;
     case F184_SLOT_ACCUM_COLOR:
     case F184_SLOT_ACCUM_NORMAL: set(F184_FMT_R32G32B32A32_SFLOAT, N, N, N); break;
@@ -251,6 +254,13 @@ int f184o_counter_get(f184o_ctx* c, uint32_t which, uint64_t* v)
 {
     if (!c || which >= F184_COUNTER_COUNT || !v) return F184_ERR_INVALID_ARGUMENT;
     *v = c->counters[which];
+    return F184_OK;
+}
+int f184o_copy_taa_to_history(f184o_ctx* c)
+{
+    int r = ensure_image(c, F184_SLOT_TAA_OUT); if (r) return r;
+    r = ensure_image(c, F184_SLOT_TAA_HISTORY); if (r) return r;
+    memcpy(c->img[F184_SLOT_TAA_HISTORY].ptr, c->img[F184_SLOT_TAA_OUT].ptr, c->img[F184_SLOT_TAA_OUT].desc.size_bytes);
     return F184_OK;
 }
 int f184o_copy_indirect_to_history(f184o_ctx* c)

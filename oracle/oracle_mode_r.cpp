@@ -844,3 +844,35 @@ extern "C" int f184o_lighting_deferred(f184o_ctx* c, const f184_view_constants* 
     (void)t0;
     return F184_OK;
 }
+
+// =================================================================================================
+// composite (Shader/GTAO/color.frag; MegaPipeline.cpp:302-319): the per-pixel function is
+// final184_b200/csrc/f184_composite.h, shared with the CUDA kernel the way f184_detmath.h is; what pins it is the
+// reference's shader text (tests/test_refshader_pin.py), not this wrapper.
+// =================================================================================================
+#include "../final184_b200/csrc/f184_composite.h"
+
+extern "C" int f184o_composite(f184o_ctx* c, const f184_trace_constants* k)
+{
+    if (!c || !k) return F184_ERR_INVALID_ARGUMENT;
+    for (int s : {F184_SLOT_ALBEDO, F184_SLOT_AO_OUT, F184_SLOT_DEPTH, F184_SLOT_LIGHTING, F184_SLOT_SHADOW, F184_SLOT_INDIRECT_FINAL,
+                  F184_SLOT_TAA_HISTORY, F184_SLOT_TAA_OUT, F184_SLOT_COLOR_OUT})
+    { int rc = ensure_image(c, s); if (rc) return rc; }
+    f184_composite_in I{};
+    memcpy(I.InvProj.m, k->view.InvProj, 64); memcpy(I.InvModelView.m, k->ext.InvModelView, 64);
+    memcpy(I.ShadowView.m, k->ext.ShadowView, 64); memcpy(I.ShadowProj.m, k->ext.ShadowProj, 64);
+    memcpy(I.prevModelView.m, k->prev.PrevModelView, 64); memcpy(I.prevProjection.m, k->prev.PrevProjection, 64);
+    memcpy(I.sun_luminance, k->sun.luminance, 12); memcpy(I.sun_position, k->sun.position, 12);
+    I.albedo = image_ptr<uint8_t>(c, F184_SLOT_ALBEDO); I.ao = image_ptr<uint16_t>(c, F184_SLOT_AO_OUT);
+    I.lighting = image_ptr<uint16_t>(c, F184_SLOT_LIGHTING); I.indirect = image_ptr<uint16_t>(c, F184_SLOT_INDIRECT_FINAL);
+    I.taa = image_ptr<uint16_t>(c, F184_SLOT_TAA_HISTORY); I.depth = image_ptr<float>(c, F184_SLOT_DEPTH); I.shadow = image_ptr<float>(c, F184_SLOT_SHADOW);
+    I.W = c->cfg.width; I.H = c->cfg.height; I.S = c->cfg.shadow_res;
+    if (k->reset_history) memset(c->img[F184_SLOT_TAA_HISTORY].ptr, 0, c->img[F184_SLOT_TAA_HISTORY].desc.size_bytes);
+    uint16_t* oc = image_ptr<uint16_t>(c, F184_SLOT_COLOR_OUT);
+    uint16_t* ot = image_ptr<uint16_t>(c, F184_SLOT_TAA_OUT);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t y = 0; y < (int64_t)I.H; y++)
+        for (uint32_t x = 0; x < I.W; x++)
+            f184_composite_pixel(I, x, (uint32_t)y, &oc[4 * ((size_t)y * I.W + x)], &ot[4 * ((size_t)y * I.W + x)]);
+    return F184_OK;
+}

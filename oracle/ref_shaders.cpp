@@ -232,6 +232,36 @@ int refsh_lighting_deferred(const f184_view_constants* view, const f184_extended
     return 0;
 }
 
+// gtao_color, MegaPipeline.cpp:302-319: target 0 -> out_color, target 1 (taaImageA) -> out_taa
+int refsh_composite(const f184_trace_constants* k, const uint8_t* albedo, const uint16_t* ao, const float* depth, const uint16_t* lighting,
+                    const float* shadow, const uint16_t* indirect, const uint16_t* taa, int W, int H, uint16_t* out_color, uint16_t* out_taa)
+{
+    typedef color_frag S;
+    S::s.wrap = 0;                                                    // GlobalLinearSamplerClamped, MegaPipeline.cpp:303
+    S::t_albedo = tex2d(albedo, W, H, TEX_RGBA8_UNORM); S::t_ao = tex2d(ao, W, H, TEX_RGBA16F); S::t_depth = tex2d(depth, W, H, TEX_R32F);
+    S::t_lighting = tex2d(lighting, W, H, TEX_RGBA16F); S::t_shadow = tex2d(shadow, 2048, 2048, TEX_R32F);
+    S::t_indirect = tex2d(indirect, W, H, TEX_RGBA16F); S::taaBuffer = tex2d(taa, W, H, TEX_RGBA16F);
+    S::InvProj = M(k->view.InvProj); S::ViewMat = M(k->view.ViewMat); S::ProjMat = M(k->view.ProjMat);
+    S::InvModelView = M(k->ext.InvModelView); S::ShadowView = M(k->ext.ShadowView); S::ShadowProj = M(k->ext.ShadowProj);
+    S::VoxelView = M(k->ext.VoxelView); S::VoxelProj = M(k->ext.VoxelProj);
+    S::sun.luminance = vec3(k->sun.luminance[0], k->sun.luminance[1], k->sun.luminance[2]);
+    S::sun.position = vec3(k->sun.position[0], k->sun.position[1], k->sun.position[2]);
+    S::prevProjection = M(k->prev.PrevProjection); S::prevModelView = M(k->prev.PrevModelView);
+    S::resolution = vec2(k->miscs.resolution[0], k->miscs.resolution[1]); S::frameCount = k->miscs.frameCount; S::frameTime = k->miscs.frameTime;
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int y = row_begin(); y < row_end(H); y++)
+        for (int x = 0; x < W; x++)
+        {
+            S sh;
+            sh.gl_FragCoord = vec4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);
+            sh.inUV = vec2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+            sh.main();
+            store_rgba16f(&out_color[4 * ((size_t)y * W + x)], sh.outColor);
+            store_rgba16f(&out_taa[4 * ((size_t)y * W + x)], sh.outTAA);
+        }
+    return 0;
+}
+
 // ---- voxel pass stages, signatures = f184o_voxel_gs_hook / f184o_voxel_ps_hook (oracle_common.h)
 void refsh_voxel_gs(const float* view16, const float* proj16, const float* model16, const float* pos9, const float* nrm9,
                     const float* uv6, float* out_clip12, float* out_nrm9, float* out_uv6, uint32_t* out_orientation)

@@ -19,7 +19,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(REPO, "oracle", "_ref", "libf184_refshaders.so")
 N, SH, W, H = 128, 2048, 128, 64
 FRAMES = 2
-CASES = ("atrium", "sponza")      # procedural atrium (always available); Sponza as the reference loads it (= BASELINE C1's scene)
+# procedural atrium (always available); Sponza as the reference loads it (= BASELINE C1's scene); an open floor with one wall, so
+# that half the screen is sky (the atmosphere branch of color.frag) and the sun reaches the ground
+CASES = ("atrium", "sponza", "open")
 
 
 def golden_path(case):
@@ -43,6 +45,7 @@ def load():
     dll.refsh_blur.argtypes = [C.c_int, C.POINTER(A.EngineMiscsC), vp, vp, C.c_int, C.c_int, vp]
     dll.refsh_lighting_deferred.argtypes = [C.POINTER(A.ViewConstantsC), C.POINTER(A.ExtendedMatricesC), C.POINTER(A.LightListC),
                                             C.POINTER(A.LightListC), vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+    dll.refsh_composite.argtypes = [C.POINTER(A.TraceConstantsC), vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
     return dll
 
 
@@ -54,7 +57,12 @@ def light_lists(k):
 
 def case_inputs(case="atrium"):
     """A pinned case: the scene under the reference's fixture cameras (App/MainBehaviour.cpp:19-76)."""
-    sc = S.procedural_scene(seed=1) if case == "atrium" else S.load_sponza()
+    if case == "open":
+        import cpu_helpers as Hc
+        tex = (np.arange(16 * 16 * 4, dtype=np.uint32).reshape(16, 16, 4) * 37 % 256).astype(np.uint8); tex[..., 3] = 255
+        sc = Hc.quad_scene([((-14, 0, -14), (28, 0, 0), (0, 0, 28), (0, 1, 0)), ((-6, 0, -9), (12, 0, 0), (0, 5, 0), (0, 0, 1))], tex=tex, name="open")
+    else:
+        sc = S.procedural_scene(seed=1) if case == "atrium" else S.load_sponza()
     cams = {n: S.fixture_constants(n) for n in ("main", "shadow", "voxel")}
     fis = [frame_inputs(sc, cams["main"], cams["shadow"], W, H, SH, f, cache=False) for f in range(FRAMES)]
     # every Sponza material is (roughness, metallic) = (1, 1) (SURVEY.md §8 a5), which zeroes the diffuse term of the deferred
@@ -93,6 +101,7 @@ def run_reference_shaders(oracle_lib, sc, cams, fis):
     o.close()
     out = dict(voxels=vox, fragments=np.int64(frags))
     hist = np.zeros((H, W, 4), np.uint16)
+    taa_hist = np.zeros((H, W, 4), np.uint16)
     ptr = lambda a: a.ctypes.data
     for f, fi in enumerate(fis):
         depth, normals, shadow = (np.ascontiguousarray(fi[k]) for k in ("depth", "normals", "shadow"))
@@ -111,7 +120,11 @@ def run_reference_shaders(oracle_lib, sc, cams, fis):
         pl, dl = light_lists(k)
         dll.refsh_lighting_deferred(C.byref(k.view), C.byref(k.ext), C.byref(pl), C.byref(dl), ptr(albedo), ptr(normals), ptr(depth),
                                     ptr(shadow), ptr(material), W, H, ptr(lit))
-        out.update({f"indirect{f}": ind, f"ao_raw{f}": raw, f"ao{f}": ao, f"blur_x{f}": bx, f"blur{f}": by, f"lighting{f}": lit})
+        col, taa = np.zeros((H, W, 4), np.uint16), np.zeros((H, W, 4), np.uint16)
+        dll.refsh_composite(C.byref(k), ptr(albedo), ptr(ao), ptr(depth), ptr(lit), ptr(shadow), ptr(by), ptr(taa_hist), W, H, ptr(col), ptr(taa))
+        out.update({f"indirect{f}": ind, f"ao_raw{f}": raw, f"ao{f}": ao, f"blur_x{f}": bx, f"blur{f}": by, f"lighting{f}": lit,
+                    f"color{f}": col, f"taa{f}": taa})
+        taa_hist = taa.copy()                  # CopyImage(taaImageA -> taaImageB), MegaPipeline.cpp:207-210
         hist = ind.copy()                      # CopyImage(indirectImage -> indirectTemporalImage), MegaPipeline.cpp:211-214
     return out
 
@@ -130,11 +143,14 @@ def run_library(lib, sc, cams, fis):
         k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, f, f == 0)
         if f > 0:
             c.copy_indirect_to_history()
+            c.copy_taa_to_history()
         c.trace_indirect(k)
         c.gtao(cams["main"])
         c.blur_indirect(k)
         c.lighting_deferred(k, *light_lists(k))
-        out.update({f"lighting{f}": u16(c.readback(A.SLOT_LIGHTING)),f"indirect{f}": u16(c.readback(A.SLOT_INDIRECT_OUT)), f"ao_raw{f}": u16(c.readback(A.SLOT_AO_RAW)),
+        c.composite(k)
+        out.update({f"lighting{f}": u16(c.readback(A.SLOT_LIGHTING)), f"color{f}": u16(c.readback(A.SLOT_COLOR_OUT)),
+                    f"taa{f}": u16(c.readback(A.SLOT_TAA_OUT)),f"indirect{f}": u16(c.readback(A.SLOT_INDIRECT_OUT)), f"ao_raw{f}": u16(c.readback(A.SLOT_AO_RAW)),
                     f"ao{f}": u16(c.readback(A.SLOT_AO_OUT)), f"blur_x{f}": u16(c.readback(A.SLOT_INDIRECT_BLUR_X)),
                     f"blur{f}": u16(c.readback(A.SLOT_INDIRECT_FINAL))})
     c.close()

@@ -108,7 +108,7 @@ def test_detmath_device_equals_host(cuda_lib, oracle_lib):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"op {op}: {np.count_nonzero(a.view(np.uint32) != b.view(np.uint32))} differ"
 
 
-@pytest.mark.parametrize("case", ["atrium", "sponza"])
+@pytest.mark.parametrize("case", ["atrium", "sponza", "open"])
 def test_cuda_matches_reference_shader_text_golden(cuda_lib, case):
     """The CUDA path against what the reference's OWN shader text computes (tests/golden/refshader_<case>.npz, made by
     tools/gen_refshader_golden.py from oracle/_ref/libf184_refshaders.so — see tests/test_refshader_pin.py): voxel volume,

@@ -1,15 +1,17 @@
 """The pin of the oracle: the reference's OWN shader text, compiled here, against the restatement — bit for bit.
 
 `make -C oracle ref` wraps Shader/Lighting/indirect.frag, Shader/GTAO/gtao.frag, Shader/GTAO/blur.frag,
-Shader/Lighting/blurX.frag / blurY.frag (+ bilateralBlur.inc, math.inc, EngineCommon.h) and the VoxelGS / BasicMaterial /
-VoxelPS strings of Pipelang/Internal/main.lua — read where they lie under /root/reference — into C++ over
+Shader/Lighting/blurX.frag / blurY.frag (+ bilateralBlur.inc, math.inc, EngineCommon.h), the two consumers
+Shader/Lighting/aggregateLights.frag and Shader/GTAO/color.frag, and the VoxelGS / BasicMaterial / VoxelPS strings of
+Pipelang/Internal/main.lua — read where they lie under /root/reference — into C++ over
 oracle/glsl_shim.h (purely lexical rewrite, oracle/make_ref_shaders.py) and builds oracle/_ref/libf184_refshaders.so.
-tools/gen_refshader_golden.py ran it on two scenes (procedural atrium; Sponza as the reference loads it = BASELINE C1's
-128^3 volume) for two frames each and committed the outputs as tests/golden/refshader_<case>.npz.
+tools/gen_refshader_golden.py ran it on three scenes (procedural atrium; Sponza as the reference loads it = BASELINE C1's
+128^3 volume; an open floor with a wall, 22 % sky) for two frames each and committed the outputs as tests/golden/refshader_<case>.npz.
 
   * everywhere:            the oracle's restatement (oracle_mode_r.cpp) must reproduce the golden outputs exactly —
                            voxel volume, fragment count, lighting_indirect (frame 0 and the temporal frame 1),
-                           gtao_visibility, gtao_blur, indirect_blurX, indirect_blurY
+                           gtao_visibility, gtao_blur, indirect_blurX, indirect_blurY, lighting_deferred, and both
+                           targets of gtao_color (composite + TAA, second frame through the TAA history)
   * where the .so exists:  the live shader text must reproduce the goldens too (the fixture is not stale)
   * on the GPU:            tests/test_gpu_mode_r.py holds the CUDA path to the same goldens
 
