@@ -242,11 +242,12 @@ def c1_reference_mode(sc, cams, device, cpu_budget_s, gpu=True):
     if gpu:
         c = A.VoxelGI(N, W, H, A.MODE_REFERENCE, shadow_res=SH, device=device)
         c.upload_scene(sc)
-        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_SHADOW, "shadow"), (A.SLOT_MATERIAL, "material")):
+        for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_SHADOW, "shadow"), (A.SLOT_MATERIAL, "material"),
+                          (A.SLOT_ALBEDO, "albedo")):
             c.upload(slot, fi[key])
         frames = 20
         def frame():
-            c.voxelize(cams["voxel"]); c.trace_indirect(k); c.gtao(cams["main"]); c.blur_indirect(k); c.lighting_deferred(k)
+            c.voxelize(cams["voxel"]); c.gtao(cams["main"]); c.trace_indirect(k); c.blur_indirect(k); c.lighting_deferred(k); c.composite(k)
         for _ in range(3):
             frame()
         c.sync()
@@ -319,10 +320,15 @@ def c1_reference_mode(sc, cams, device, cpu_budget_s, gpu=True):
         dll.refsh_lighting_deferred(C.byref(k.view), C.byref(k.ext), C.byref(pl), C.byref(dl), ptr(albedo), ptr(normals), ptr(depth),
                                     ptr(shadow), ptr(material), W, H, ptr(tmp))
         t_light = time.perf_counter() - t0
+        dll.refsh_composite.argtypes = [C.POINTER(A.TraceConstantsC), vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
+        col, taa_in, taa_out = (np.zeros((H, W, 4), np.uint16) for _ in range(3))
+        t0 = time.perf_counter()
+        dll.refsh_composite(C.byref(k), ptr(albedo), ptr(hist), ptr(depth), ptr(tmp), ptr(shadow), ptr(img), ptr(taa_in), W, H, ptr(col), ptr(taa_out))
+        t_comp = time.perf_counter() - t0
         dll.refsh_set_rows(0, 1 << 30)
         sc_ = H / rows
         st = {"voxelize": round(t_vox, 2), "trace": round(t_ind * 1e3 * sc_, 1), "gtao": round(t_gtao * 1e3 * sc_, 1), "blur": round(t_blur * 1e3 * sc_, 1),
-              "lighting": round(t_light * 1e3 * sc_, 1)}
+              "lighting": round(t_light * 1e3 * sc_, 1), "composite": round(t_comp * 1e3 * sc_, 1)}
         out["cpu_reference"] = {"ms_per_frame": round(sum(st.values()), 1), "stages_ms": st, "cores": os.cpu_count() or 1, "kind": "reference",
                                 "sample": f"the reference's own GLSL compiled by g++ (oracle/_ref/libf184_refshaders.so), OpenMP on all cores; voxel pass in full, "
                                           f"screen passes on rows [{y0}, {y0 + rows}) of {H} scaled x{sc_:.1f}"}

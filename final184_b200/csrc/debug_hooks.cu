@@ -17,6 +17,10 @@ __global__ void k_detmath(uint32_t op, const float* __restrict__ x, const float*
     case 4: r = dm_exp2(x[i]); break;
     case 5: r = dm_pow(x[i], y[i]); break;
     case 6: r = dm_f16_to_f32(dm_f32_to_f16(x[i])); break;
+    case 7: r = dm_u2f((uint32_t)dm_f2i(x[i])); break;                    // conversions: results returned as raw bits
+    case 8: r = dm_u2f(dm_f2uint(x[i])); break;
+    case 9: r = dm_u2f((uint32_t)dm_f32_to_f16(x[i])); break;
+    case 10: r = dm_f16_to_f32((uint16_t)(dm_f2u(x[i]) & 0xffffu)); break;
     }
     out[i] = r;
 }
@@ -24,7 +28,7 @@ __global__ void k_detmath(uint32_t op, const float* __restrict__ x, const float*
 
 extern "C" int f184_debug_detmath(f184_ctx* c, uint32_t op, const float* x, const float* y, float* out, size_t n)
 {
-    if (!c || op > 6 || !x || !out) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_detmath: bad argument");
+    if (!c || op > 10 || !x || !out) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_detmath: bad argument");
     float *dx = nullptr, *dy = nullptr, *dout = nullptr;
     CK(c, cudaMalloc(&dx, n * 4));
     CK(c, cudaMalloc(&dy, n * 4));

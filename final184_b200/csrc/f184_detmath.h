@@ -22,6 +22,9 @@
 #define DM_HD static inline
 #endif
 
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 #if defined(__CUDA_ARCH__)
 #define DM_DMUL(a, b) __dmul_rn((a), (b))
 #define DM_DSUB(a, b) __dsub_rn((a), (b))
@@ -190,6 +193,9 @@ DM_HD float dm_smoothstep(float e0, float e1, float x)
 // float -> int conversions as the GPU does them: NaN -> 0, saturating, truncate toward zero
 DM_HD int dm_f2i(float f)
 {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rz(f);            // cvt.rzi.s32.f32: NaN -> 0, saturating — the definition below, in one instruction
+#endif
     if (dm_isnan(f)) return 0;
     if (f >= 2147483648.0f) return 2147483647;
     if (f <= -2147483648.0f) return (int)0x80000000;
@@ -197,6 +203,9 @@ DM_HD int dm_f2i(float f)
 }
 DM_HD uint32_t dm_f2uint(float f)
 {
+#if defined(__CUDA_ARCH__)
+    return __float2uint_rz(f);           // cvt.rzi.u32.f32: NaN -> 0, negative -> 0, saturating
+#endif
     if (dm_isnan(f) || f <= 0.0f) return 0u;
     if (f >= 4294967296.0f) return 0xffffffffu;
     return (uint32_t)f;
@@ -205,6 +214,11 @@ DM_HD uint32_t dm_f2uint(float f)
 // ---- fp16 (RGBA16F render targets) -------------------------------------------------------------
 DM_HD uint16_t dm_f32_to_f16(float f)   // round-to-nearest-even, IEEE binary16
 {
+#if defined(__CUDA_ARCH__)
+    // cvt.rn.f16.f32 rounds exactly as below; only its NaN encoding differs (0x7fff), so NaN keeps the explicit form
+    if (dm_isnan(f)) return (uint16_t)(((dm_f2u(f) >> 16) & 0x8000u) | 0x7e00u);
+    return __half_as_ushort(__float2half_rn(f));
+#endif
     uint32_t u = dm_f2u(f);
     uint32_t sign = (u >> 16) & 0x8000u;
     uint32_t a = u & 0x7fffffffu;
@@ -226,6 +240,9 @@ DM_HD uint16_t dm_f32_to_f16(float f)   // round-to-nearest-even, IEEE binary16
 }
 DM_HD float dm_f16_to_f32(uint16_t h)
 {
+#if defined(__CUDA_ARCH__)
+    if ((h & 0x7c00u) != 0x7c00u) return __half2float(__ushort_as_half(h));      // exact for every finite half; inf/NaN keep the bit form below
+#endif
     uint32_t sign = ((uint32_t)h & 0x8000u) << 16;
     uint32_t e = (h >> 10) & 0x1fu;
     uint32_t m = h & 0x3ffu;

@@ -105,7 +105,7 @@ __device__ f3 get_indirect(const TraceParams& P, f3 wpos, f3 wnorm, float seed, 
     const float Nf = (float)P.N, hi = (float)(P.N - 1);
     f3 sv = voxel_pos(P.w2voxel, wpos, Nf);
     int pvx = dm_f2i(sv.x), pvy = dm_f2i(sv.y), pvz = dm_f2i(sv.z);
-    uint32_t i = 0;
+    uint32_t i = 0, hit_texel = 0;
     // ~15 % of the reference's rays have a NaN direction (blugausnoise2 leaves [0, 1]).  Under the pinned NaN
     // rules such a ray never leaves the loop: every comparison is false, ivec3(NaN) = (0,0,0), so it reads voxel (0,0,0) at most
     // once and then spins for all `steps` iterations, and its sky term is x * smoothstep(NaN) = 0.  With first-hit divergence
@@ -134,30 +134,33 @@ __device__ f3 get_indirect(const TraceParams& P, f3 wpos, f3 wnorm, float seed, 
             if (ix >= 0 && iy >= 0 && iz >= 0 && ix < (int)P.N && iy < (int)P.N && iz < (int)P.N)
                 texel = __ldg(P.vox + (((size_t)iz * P.N + iy) * P.N + ix));
             pvx = ix; pvy = iy; pvz = iz;
-            const uint32_t r = texel & 0xffffu, g = texel >> 16;
-            if (r != 0)
-            {
-                f3 col = {dm_pow((float)((r & 0xF800u) >> 11) / 31.0f, 2.2f), dm_pow((float)((r & 0x7E0u) >> 5) / 63.0f, 2.2f),
-                          dm_pow((float)(r & 0x1Fu) / 31.0f, 2.2f)};
-                f3 vn = normalize3(f3{(float)(g & 0x1Fu) / 16.0f - 1.0f, (float)((g & 0x7E0u) >> 5) / 32.0f - 1.0f,
-                                      (float)((g & 0xF800u) >> 11) / 16.0f - 1.0f});
-                f3 sp = {march_pos.x + vn.x * 0.06f, march_pos.y + vn.y * 0.06f, march_pos.z + vn.z * 0.06f};
-                f4 sv4 = mul44(P.ShadowProj, mul44(P.ShadowView, f4{sp.x, sp.y, sp.z, 1.0f}));
-                float spx = sv4.x / sv4.w, spy = sv4.y / sv4.w, spz = sv4.z / sv4.w;
-                spx = spx * 0.5f + 0.5f; spy = spy * 0.5f + 0.5f;
-                const int tx = dm_f2i(spx * (float)P.S), ty = dm_f2i(spy * (float)P.S);
-                float shadowZ = 0.0f;
-                if (tx >= 0 && ty >= 0 && tx < (int)P.S && ty < (int)P.S) shadowZ = __ldg(P.shadow + (size_t)ty * P.S + tx);
-                const float shade = dm_step(spz + 0.005f, shadowZ);
-                const float l = fabsf(dot3(neg3(P.sunPos), vn));
-                const float den = dm_max(0.01f, NdotD);
-                f3 rr = {l * col.x / den, l * col.y / den, l * col.z / den};
-                hit.brdf = rr;
-                Lo = {Lo.x + P.sunLum.x * shade * rr.x, Lo.y + P.sunLum.y * shade * rr.y, Lo.z + P.sunLum.z * shade * rr.z};
-                hit.wpos = march_pos; hit.wnorm = vn; hit.hit = true;
-                break;
-            }
+            if ((texel & 0xffffu) != 0) { hit_texel = texel; break; }
         }
+    }
+    // The hit is shaded AFTER the loop: inside it, lanes that hit at different steps each ran the ~500-instruction shading
+    // path on their own (ncu: 13.7 of 32 lanes active, 2.27 G warp instructions per 720p frame); here the lanes that hit
+    // run it once, together.  march_pos still holds the hit position (the loop breaks before advancing).
+    if (hit_texel != 0)
+    {
+        const uint32_t r = hit_texel & 0xffffu, g = hit_texel >> 16;
+        f3 col = {dm_pow((float)((r & 0xF800u) >> 11) / 31.0f, 2.2f), dm_pow((float)((r & 0x7E0u) >> 5) / 63.0f, 2.2f),
+                  dm_pow((float)(r & 0x1Fu) / 31.0f, 2.2f)};
+        f3 vn = normalize3(f3{(float)(g & 0x1Fu) / 16.0f - 1.0f, (float)((g & 0x7E0u) >> 5) / 32.0f - 1.0f,
+                              (float)((g & 0xF800u) >> 11) / 16.0f - 1.0f});
+        f3 sp = {march_pos.x + vn.x * 0.06f, march_pos.y + vn.y * 0.06f, march_pos.z + vn.z * 0.06f};
+        f4 sv4 = mul44(P.ShadowProj, mul44(P.ShadowView, f4{sp.x, sp.y, sp.z, 1.0f}));
+        float spx = sv4.x / sv4.w, spy = sv4.y / sv4.w, spz = sv4.z / sv4.w;
+        spx = spx * 0.5f + 0.5f; spy = spy * 0.5f + 0.5f;
+        const int tx = dm_f2i(spx * (float)P.S), ty = dm_f2i(spy * (float)P.S);
+        float shadowZ = 0.0f;
+        if (tx >= 0 && ty >= 0 && tx < (int)P.S && ty < (int)P.S) shadowZ = __ldg(P.shadow + (size_t)ty * P.S + tx);
+        const float shade = dm_step(spz + 0.005f, shadowZ);
+        const float l = fabsf(dot3(neg3(P.sunPos), vn));
+        const float den = dm_max(0.01f, NdotD);
+        f3 rr = {l * col.x / den, l * col.y / den, l * col.z / den};
+        hit.brdf = rr;
+        Lo = {Lo.x + P.sunLum.x * shade * rr.x, Lo.y + P.sunLum.y * shade * rr.y, Lo.z + P.sunLum.z * shade * rr.z};
+        hit.wpos = march_pos; hit.wnorm = vn; hit.hit = true;
     }
     if (!hit.hit && i == P.steps)
     {

@@ -362,7 +362,8 @@ int f184_stage_time_reset(f184_ctx* ctx, uint32_t accumulate);
 int f184_stage_time_total(f184_ctx* ctx, uint32_t stage, float* out_ms_sum, uint32_t* out_runs);
 
 /* ---- test hook: evaluate csrc/f184_detmath.h on the device (op: 0 sin, 1 cos, 2 log, 3 log2, 4 exp2,
- * 5 pow(x,y), 6 f32->f16->f32); host pointers; synchronous */
+ * 5 pow(x,y), 6 f32->f16->f32, 7 float->int, 8 float->uint, 9 f32->f16 bits, 10 f16 bits->f32; 7-10 return raw bits);
+ * host pointers; synchronous */
 int f184_debug_detmath(f184_ctx* ctx, uint32_t op, const float* x, const float* y, float* out, size_t n);
 
 /* ---- measurement aid: device peaks MEASURED_PEAKS.json does not hold.  which = 0: trilinear RGBA8 3D texture fetches / s

@@ -338,6 +338,10 @@ extern "C" int f184o_debug_detmath(uint32_t op, const float* x, const float* y, 
         case 4: out[i] = dm_exp2(x[i]); break;
         case 5: out[i] = dm_pow(x[i], y[i]); break;
         case 6: out[i] = dm_f16_to_f32(dm_f32_to_f16(x[i])); break;
+        case 7: out[i] = dm_u2f((uint32_t)dm_f2i(x[i])); break;                    // conversions: results returned as raw bits
+        case 8: out[i] = dm_u2f(dm_f2uint(x[i])); break;
+        case 9: out[i] = dm_u2f((uint32_t)dm_f32_to_f16(x[i])); break;
+        case 10: out[i] = dm_f16_to_f32((uint16_t)(dm_f2u(x[i]) & 0xffffu)); break;
         default: return F184_ERR_INVALID_ARGUMENT;
         }
     }

@@ -106,6 +106,22 @@ def test_detmath_device_equals_host(cuda_lib, oracle_lib):
         assert cuda_lib.debug_detmath(g.h, op, x.ctypes.data, y.ctypes.data, a.ctypes.data, x.size) == 0
         oracle_lib.dll.f184o_debug_detmath(C.c_uint32(op), C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), C.c_void_p(b.ctypes.data), C.c_size_t(x.size))
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"op {op}: {np.count_nonzero(a.view(np.uint32) != b.view(np.uint32))} differ"
+    # conversions (the device uses cvt instructions, the host the written-out definitions): every half pattern, and floats that
+    # sit on every boundary — NaN, infinities, half subnormals, the 65504/65520 overflow edge, int/uint saturation, negative zero
+    edge = np.array([0.0, -0.0, np.nan, -np.nan, np.inf, -np.inf, 65504.0, 65519.99, 65520.0, 65536.0, -65520.0, 5.96e-8, 2.98e-8, 2.9802322e-8,
+                     2.9802326e-8, 6.1e-5, 6.0975552e-5, 1e-10, 2147483520.0, 2147483648.0, 4294967040.0, 4294967296.0, -2147483648.0, -2147483904.0,
+                     -0.5, 0.99999994, 1e20, -1e20], np.float32)
+    bits = rng.integers(0, 2 ** 32, 400000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    halves = np.arange(65536, dtype=np.uint32).view(np.float32)
+    near = (rng.uniform(-70000, 70000, 200000).astype(np.float32))
+    for op, x in ((6, np.concatenate([edge, bits])), (7, np.concatenate([edge, bits, near])), (8, np.concatenate([edge, bits, near])),
+                  (9, np.concatenate([edge, bits, near, (near * 1e-6).astype(np.float32)])), (10, halves)):
+        x = np.ascontiguousarray(x, np.float32)
+        a, b = np.empty_like(x), np.empty_like(x)
+        assert cuda_lib.debug_detmath(g.h, op, x.ctypes.data, x.ctypes.data, a.ctypes.data, x.size) == 0
+        oracle_lib.dll.f184o_debug_detmath(C.c_uint32(op), C.c_void_p(x.ctypes.data), C.c_void_p(x.ctypes.data), C.c_void_p(b.ctypes.data), C.c_size_t(x.size))
+        bad = np.flatnonzero(a.view(np.uint32) != b.view(np.uint32))
+        assert bad.size == 0, f"conversion op {op}: {bad.size} differ, first x bits {x.view(np.uint32)[bad[0]]:#x}: device {a.view(np.uint32)[bad[0]]:#x} host {b.view(np.uint32)[bad[0]]:#x}"
 
 
 @pytest.mark.parametrize("case", ["atrium", "sponza", "open"])
