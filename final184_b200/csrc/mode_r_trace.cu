@@ -6,13 +6,14 @@
 // shadow-map lookup at the hit, then the temporal reprojection blend.  Noise is Shader/math.inc:83-87,
 // 107-110, 189-194, 214-219 evaluated with f184_detmath.h (see that header for why).
 //
-// B200 design: one thread per pixel, warps own 8x4 pixel tiles so the rays of a warp start from
-// neighbouring surface points and walk through neighbouring voxels (the 8 MiB..512 MiB volume is served
-// by L2/L1, 4-byte nearest fetches only when the integer voxel changes, as in the shader).  The march
-// itself is ALU: the affine world->voxel transform is applied per step exactly as the shader does (the
-// arithmetic order is part of the parity contract), so the kernel is bound by fp32 issue rate and by the
-// divergence of first-hit termination; the warp leaves a march as soon as every lane has hit, left the
-// volume or run out of steps (hardware reconvergence of the loop exit = the vote the shader cannot do).
+// B200 design: one thread per pixel, warps own 8x4 pixel tiles so the rays of a warp start from neighbouring surface points
+// and walk through neighbouring voxels (the 8 MiB..512 MiB volume is served by L2/L1, 4-byte nearest fetches only when the
+// integer voxel changes, as in the shader).  The march is ALU: the affine world->voxel transform is applied per step exactly
+// as the shader does (the arithmetic order is part of the parity contract).  What a straight transcription loses is lanes:
+// first-hit termination leaves 11 of 32 active while the warp waits for its longest ray, 8 times per pixel.  The kernel
+// therefore regroups a pixel's work — convergent set-up, one flattened loop per bounce in which every lane walks its own
+// rays back to back, convergent shading — see the block comment above ray_rands.  Results are bit-identical to the shader
+// text (tests/golden/refshader_*.npz); the cone-sample counter still counts every step the shader would take.
 #include "f184_device.cuh"
 
 namespace {
@@ -66,82 +67,140 @@ __device__ __forceinline__ f3 voxel_pos(const M4& w2v, f3 p, float Nf)
     return {(v.x * 0.5f + 0.5f) * Nf, (v.y * 0.5f + 0.5f) * Nf, v.z * Nf};
 }
 
-// indirect.frag:104-184
-__device__ f3 get_indirect(const TraceParams& P, f3 wpos, f3 wnorm, float seed, float uvx, float uvy, const float* ext,
-                           Hit& hit, unsigned int& steps_taken)
+// ---- one march (indirect.frag:104-184) in three convergent pieces and one flattened loop ------------------------------
+//
+// The shader runs, per pixel, 4 x (primary march [+ secondary march if it hit]), each a loop of up to 60 dependent steps that
+// ends at the first occupied voxel.  Executed as written, a warp pays max-over-lanes(steps) for every one of the 8 marches:
+// ncu on the straight transcription showed 60 iterations per march at 11 of 32 lanes active (some lane always runs to the
+// end), 2.27 G warp instructions per 720p frame.  Here the work of a pixel is regrouped without touching any ray's arithmetic:
+//   rands + set-up of the 4 primary rays        convergent (every lane does the same 4 set-ups)
+//   march_flat                                  ONE loop in which each lane walks its 4 rays back to back — a lane that
+//                                               finishes a ray starts its next one in the same iteration instead of idling,
+//                                               so the warp pays max-over-lanes(sum of steps), not sum of maxima
+//   shading of the hits + set-up of secondaries convergent again (lanes that hit shade together)
+//   march_flat over the secondary rays, shading, and the sum in the shader's order: ((a0 + brdf0*b0) + a1) + brdf1*b1 ...
+// Rays live in shared memory between the pieces (16 words per ray, [ray][word][thread] so a warp's accesses are conflict-free).
+constexpr int RAY_WORDS = 16;
+constexpr int TRACE_THREADS = 128;
+// words: 0-2 dir, 3-5 march position, 6 NdotD, 7-9 previous voxel; after the march: 0 hit texel, 1 "ran out of steps", 3-5 final
+// position; 10-12 radiance of the primary ray, 13-15 its brdf (kept across the secondary march)
+#define RS(k, f) S[((k) * RAY_WORDS + (f)) * TRACE_THREADS + threadIdx.x]
+
+// rands.x / rands.y, indirect.frag:111-116
+__device__ __forceinline__ void ray_rands(const TraceParams& P, float seed, float uvx, float uvy, const float* ext, float& rx, float& ry)
 {
-    hit.hit = false;
-    f3 Lo = {0.f, 0.f, 0.f};
-    const float step_size = P.step_size;
-    float rx, ry;
-    if (ext) { rx = ext[0]; ry = ext[1]; }
-    else
-    {
-        const float t0 = 0.07f * dm_fract(P.iiTime), t1 = 0.11f * dm_fract(P.iiTime + 0.573953f);
-        float ra = glsl_hash(seed, seed);
-        float ax = (uvx + ra) * P.resx, ay = (uvy + ra) * P.resy;
-        rx = blugausnoise2(-ax, -ay, t0, t1);
-        ry = blugausnoise2(ax, ay, t0, t1);
-    }
+    if (ext) { rx = ext[0]; ry = ext[1]; return; }
+    const float t0 = 0.07f * dm_fract(P.iiTime), t1 = 0.11f * dm_fract(P.iiTime + 0.573953f);
+    const float ra = glsl_hash(seed, seed);
+    const float ax = (uvx + ra) * P.resx, ay = (uvy + ra) * P.resy;
+    rx = blugausnoise2(-ax, -ay, t0, t1);
+    ry = blugausnoise2(ax, ay, t0, t1);
+}
+
+// indirect.frag:117-135: direction in the tangent frame of wnorm, first march position, starting voxel -> ray k of this thread
+__device__ void ray_setup(const TraceParams& P, float* S, int k, f3 wpos, f3 wnorm, float rx, float ry)
+{
     // hemisphereSample_cos, math.inc:76-81
-    float phi = ry * 2.0f * 3.1415926f;
-    float cosTheta = __fsqrt_rn(1.0f - rx);
-    float sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
-    f3 d = {dm_cos(phi) * sinTheta, dm_sin(phi) * sinTheta, cosTheta};
+    const float phi = ry * 2.0f * 3.1415926f;
+    const float cosTheta = __fsqrt_rn(1.0f - rx);
+    const float sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
+    const f3 d = {dm_cos(phi) * sinTheta, dm_sin(phi) * sinTheta, cosTheta};
     // make_coord_space, indirect.frag:71-86
     f3 z = wnorm, h = wnorm;
     if (fabsf(h.x) <= fabsf(h.y) && fabsf(h.x) <= fabsf(h.z)) h.x = 1.0f;
     else if (fabsf(h.y) <= fabsf(h.x) && fabsf(h.y) <= fabsf(h.z)) h.y = 1.0f;
     else h.z = 1.0f;
     z = normalize3(z);
-    f3 y = normalize3(cross3(h, z));
-    f3 x = normalize3(cross3(z, y));
+    const f3 y = normalize3(cross3(h, z));
+    const f3 x = normalize3(cross3(z, y));
     f3 dir = {(x.x * d.x + y.x * d.y) + z.x * d.z, (x.y * d.x + y.y * d.y) + z.y * d.z, (x.z * d.x + y.z * d.y) + z.z * d.z};
     if (dot3(dir, wnorm) < 0.0f) dir = neg3(dir);
     const float NdotD = dot3(dir, wnorm);
-    const float s1 = 1.0f + ry;
-    f3 march_pos = {wpos.x + dir.x * s1 * step_size / NdotD, wpos.y + dir.y * s1 * step_size / NdotD, wpos.z + dir.z * s1 * step_size / NdotD};
+    const float s1 = 1.0f + ry, step_size = P.step_size;
+    const f3 march_pos = {wpos.x + dir.x * s1 * step_size / NdotD, wpos.y + dir.y * s1 * step_size / NdotD, wpos.z + dir.z * s1 * step_size / NdotD};
+    const f3 sv = voxel_pos(P.w2voxel, wpos, (float)P.N);
+    RS(k, 0) = dir.x; RS(k, 1) = dir.y; RS(k, 2) = dir.z;
+    RS(k, 3) = march_pos.x; RS(k, 4) = march_pos.y; RS(k, 5) = march_pos.z;
+    RS(k, 6) = NdotD;
+    RS(k, 7) = __int_as_float(dm_f2i(sv.x)); RS(k, 8) = __int_as_float(dm_f2i(sv.y)); RS(k, 9) = __int_as_float(dm_f2i(sv.z));
+}
 
-    const float Nf = (float)P.N, hi = (float)(P.N - 1);
-    f3 sv = voxel_pos(P.w2voxel, wpos, Nf);
-    int pvx = dm_f2i(sv.x), pvy = dm_f2i(sv.y), pvz = dm_f2i(sv.z);
-    uint32_t i = 0, hit_texel = 0;
-    // ~15 % of the reference's rays have a NaN direction (blugausnoise2 leaves [0, 1]).  Under the pinned NaN
-    // rules such a ray never leaves the loop: every comparison is false, ivec3(NaN) = (0,0,0), so it reads voxel (0,0,0) at most
-    // once and then spins for all `steps` iterations, and its sky term is x * smoothstep(NaN) = 0.  With first-hit divergence
-    // that tail is what the other 31 lanes of the warp wait for.  It is skipped here with the same outcome: Lo = 0, no hit,
-    // `steps` counted.  (If voxel (0,0,0) is occupied the general loop below still handles the ray.)
-    if (dm_isnan(dir.x))
-    {
-        uint32_t texel0 = 0;
-        if ((pvx | pvy | pvz) != 0 && P.steps) texel0 = __ldg(P.vox);
-        if ((texel0 & 0xffffu) == 0)
+// indirect.frag:137-152, 176 for the rays of this thread whose bit is set in `need`, back to back
+__device__ void march_flat(const TraceParams& P, float* S, unsigned int need, unsigned int& steps_taken)
+{
+    const float Nf = (float)P.N, hi = (float)(P.N - 1), step_size = P.step_size;
+    const int N = (int)P.N;
+    int k = 0, pvx = 0, pvy = 0, pvz = 0;
+    uint32_t i = 0;
+    f3 dir = {0.f, 0.f, 0.f}, pos = {0.f, 0.f, 0.f};
+    bool have = false;
+    auto next_ray = [&]() {
+        have = false;
+        while (need)
         {
-            steps_taken += P.steps;
-            return Lo;
+            k = __ffs(need) - 1;
+            need &= need - 1;
+            dir = {RS(k, 0), RS(k, 1), RS(k, 2)};
+            pos = {RS(k, 3), RS(k, 4), RS(k, 5)};
+            pvx = __float_as_int(RS(k, 7)); pvy = __float_as_int(RS(k, 8)); pvz = __float_as_int(RS(k, 9));
+            i = 0;
+            bool idle = (P.steps == 0);
+            // ~15 % of the reference's rays have a NaN direction (blugausnoise2 leaves [0, 1]).  Under the pinned
+            // NaN rules such a ray never leaves the loop — every comparison is false, ivec3(NaN) = (0,0,0): it reads voxel (0,0,0)
+            // at most once, spins for all `steps` iterations, and its sky term is x * smoothstep(NaN) = 0.  Same outcome without
+            // the iterations: no hit, ran out, `steps` counted.  (If voxel (0,0,0) is occupied the loop below handles the ray.)
+            if (!idle && dm_isnan(dir.x))
+            {
+                uint32_t texel0 = 0;
+                if ((pvx | pvy | pvz) != 0) texel0 = __ldg(P.vox);
+                if ((texel0 & 0xffffu) == 0) { steps_taken += P.steps; idle = true; }
+            }
+            if (idle) { RS(k, 0) = __uint_as_float(0u); RS(k, 1) = __uint_as_float(1u); continue; }
+            have = true;
+            break;
         }
-    }
-    for (; i < P.steps; i++)
+    };
+    next_ray();
+    while (have)
     {
         steps_taken++;
-        march_pos = {march_pos.x + dir.x * step_size, march_pos.y + dir.y * step_size, march_pos.z + dir.z * step_size};
-        f3 vp = voxel_pos(P.w2voxel, march_pos, Nf);
-        if (vp.x < 0.f || vp.y < 0.f || vp.z < 0.f || vp.x > hi || vp.y > hi || vp.z > hi) break;
-        const int ix = dm_f2i(vp.x), iy = dm_f2i(vp.y), iz = dm_f2i(vp.z);       // NaN -> 0
-        if (pvx != ix || pvy != iy || pvz != iz)
+        pos = {pos.x + dir.x * step_size, pos.y + dir.y * step_size, pos.z + dir.z * step_size};
+        const f3 vp = voxel_pos(P.w2voxel, pos, Nf);
+        bool finished = false, ranout = false;
+        uint32_t hit_texel = 0;
+        if (vp.x < 0.f || vp.y < 0.f || vp.z < 0.f || vp.x > hi || vp.y > hi || vp.z > hi) finished = true;
+        else
         {
-            uint32_t texel = 0;
-            if (ix >= 0 && iy >= 0 && iz >= 0 && ix < (int)P.N && iy < (int)P.N && iz < (int)P.N)
-                texel = __ldg(P.vox + (((size_t)iz * P.N + iy) * P.N + ix));
-            pvx = ix; pvy = iy; pvz = iz;
-            if ((texel & 0xffffu) != 0) { hit_texel = texel; break; }
+            const int ix = dm_f2i(vp.x), iy = dm_f2i(vp.y), iz = dm_f2i(vp.z);       // NaN -> 0
+            if (pvx != ix || pvy != iy || pvz != iz)
+            {
+                uint32_t texel = 0;
+                if ((ix | iy | iz) >= 0 && ix < N && iy < N && iz < N) texel = __ldg(P.vox + ((uint32_t)(iz * N + iy) * (uint32_t)N + (uint32_t)ix));
+                pvx = ix; pvy = iy; pvz = iz;
+                if ((texel & 0xffffu) != 0) { hit_texel = texel; finished = true; }
+            }
+        }
+        if (!finished && ++i == P.steps) { finished = true; ranout = true; }
+        if (finished)
+        {
+            RS(k, 0) = __uint_as_float(hit_texel); RS(k, 1) = __uint_as_float(ranout ? 1u : 0u);
+            RS(k, 3) = pos.x; RS(k, 4) = pos.y; RS(k, 5) = pos.z;
+            next_ray();
         }
     }
-    // The hit is shaded AFTER the loop: inside it, lanes that hit at different steps each ran the ~500-instruction shading
-    // path on their own (ncu: 13.7 of 32 lanes active, 2.27 G warp instructions per 720p frame); here the lanes that hit
-    // run it once, together.  march_pos still holds the hit position (the loop breaks before advancing).
+}
+
+// indirect.frag:154-181 for ray k after its march: first-bounce lighting at the hit, or the sky term
+__device__ f3 ray_shade(const TraceParams& P, const float* S, int k, Hit& hit)
+{
+    hit.hit = false;
+    f3 Lo = {0.f, 0.f, 0.f};
+    const uint32_t hit_texel = __float_as_uint(RS(k, 0));
+    const bool ranout = __float_as_uint(RS(k, 1)) != 0u;
+    const float NdotD = RS(k, 6);
     if (hit_texel != 0)
     {
+        const f3 march_pos = {RS(k, 3), RS(k, 4), RS(k, 5)};
         const uint32_t r = hit_texel & 0xffffu, g = hit_texel >> 16;
         f3 col = {dm_pow((float)((r & 0xF800u) >> 11) / 31.0f, 2.2f), dm_pow((float)((r & 0x7E0u) >> 5) / 63.0f, 2.2f),
                   dm_pow((float)(r & 0x1Fu) / 31.0f, 2.2f)};
@@ -162,7 +221,7 @@ __device__ f3 get_indirect(const TraceParams& P, f3 wpos, f3 wnorm, float seed, 
         Lo = {Lo.x + P.sunLum.x * shade * rr.x, Lo.y + P.sunLum.y * shade * rr.y, Lo.z + P.sunLum.z * shade * rr.z};
         hit.wpos = march_pos; hit.wnorm = vn; hit.hit = true;
     }
-    if (!hit.hit && i == P.steps)
+    if (!hit.hit && ranout)
     {
         const float den = dm_max(0.01f, NdotD);
         const float sm = dm_smoothstep(0.0f, 0.01f, NdotD);
@@ -175,8 +234,9 @@ __device__ __forceinline__ float unorm16(uint16_t v) { return (float)v / 65535.0
 __device__ __forceinline__ int wrapn(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
 
 // 128 threads = 2x2 warps of 8x4 pixels -> a 16x8 pixel tile per block
-__global__ void __launch_bounds__(128) k_trace_r(const TraceParams P, unsigned long long* __restrict__ step_counter)
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_r(const TraceParams P, unsigned long long* __restrict__ step_counter)
 {
+    extern __shared__ float S[];          // 4 rays x RAY_WORDS x TRACE_THREADS
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const uint32_t y = P.y0 + (P.tile0 + blockIdx.y * P.tile_stride) * 8 + (warp >> 1) * 4 + (lane >> 3);
@@ -197,20 +257,44 @@ __global__ void __launch_bounds__(128) k_trace_r(const TraceParams P, unsigned l
         const f3 csnorm = normalize3(raw);
         const f3 wnorm = mul33(P.InvModelView, csnorm);
 
-        Hit st;
-        st.hit = false; st.brdf = {0.f, 0.f, 0.f}; st.wpos = {0.f, 0.f, 0.f}; st.wnorm = {0.f, 0.f, 0.f};
-        f3 ind = {0.f, 0.f, 0.f};
         const float* er = P.rands ? P.rands + 16 * ((size_t)y * W + x) : nullptr;
+        // the 4 primary rays: same origin and normal, seeds 0, 2, 4, 6 (indirect.frag:201-221)
 #pragma unroll 1
-        for (int pair = 0; pair < 4; pair++)
+        for (int k = 0; k < 4; k++)
         {
-            f3 a = get_indirect(P, wpos, wnorm, (float)(2 * pair), uvx, uvy, er ? er + 4 * pair : nullptr, st, steps_taken);
-            ind = ind + a;
+            float rx, ry;
+            ray_rands(P, (float)(2 * k), uvx, uvy, er ? er + 4 * k : nullptr, rx, ry);
+            ray_setup(P, S, k, wpos, wnorm, rx, ry);
+        }
+        march_flat(P, S, 0xfu, steps_taken);
+        // shade them; every hit spawns the secondary ray of its pair (seeds 1, 3, 5, 7) from the hit point along the voxel normal
+        unsigned int second = 0;
+#pragma unroll 1
+        for (int k = 0; k < 4; k++)
+        {
+            Hit st;
+            const f3 a = ray_shade(P, S, k, st);
+            RS(k, 10) = a.x; RS(k, 11) = a.y; RS(k, 12) = a.z;
             if (st.hit)
             {
-                const f3 brdf = st.brdf, hw = st.wpos, hn = st.wnorm;     // left operand read before the call (indirect.frag:204)
-                f3 b = get_indirect(P, hw, hn, (float)(2 * pair + 1), uvx, uvy, er ? er + 4 * pair + 2 : nullptr, st, steps_taken);
-                ind = ind + brdf * b;
+                RS(k, 13) = st.brdf.x; RS(k, 14) = st.brdf.y; RS(k, 15) = st.brdf.z;     // read before the second call (indirect.frag:204)
+                float rx, ry;
+                ray_rands(P, (float)(2 * k + 1), uvx, uvy, er ? er + 4 * k + 2 : nullptr, rx, ry);
+                ray_setup(P, S, k, st.wpos, st.wnorm, rx, ry);
+                second |= 1u << k;
+            }
+        }
+        march_flat(P, S, second, steps_taken);
+        f3 ind = {0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int k = 0; k < 4; k++)
+        {
+            ind = ind + f3{RS(k, 10), RS(k, 11), RS(k, 12)};
+            if (second & (1u << k))
+            {
+                Hit st;
+                const f3 b = ray_shade(P, S, k, st);
+                ind = ind + f3{RS(k, 13), RS(k, 14), RS(k, 15)} * b;
             }
         }
         ind = ind * 0.25f;
@@ -290,7 +374,8 @@ int f184_trace_r(f184_ctx* c, const f184_trace_constants* k)
     if (grid_y)
     {
         dim3 grid((P.W + 15) / 16, grid_y);
-        k_trace_r<<<grid, 128, 0, c->stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+        const size_t smem = 4 * RAY_WORDS * TRACE_THREADS * sizeof(float);       // 32 KB
+        k_trace_r<<<grid, TRACE_THREADS, smem, c->stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
         CK_LAUNCH(c);
     }
     return f184_stage_end(c, F184_STAGE_TRACE);
