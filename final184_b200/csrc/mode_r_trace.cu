@@ -74,11 +74,11 @@ __device__ __forceinline__ f3 voxel_pos(const M4& w2v, f3 p, float Nf)
 // ncu on the straight transcription showed 60 iterations per march at 11 of 32 lanes active (some lane always runs to the
 // end), 2.27 G warp instructions per 720p frame.  Here the work of a pixel is regrouped without touching any ray's arithmetic:
 //   rands + set-up of the 4 primary rays        convergent (every lane does the same 4 set-ups)
-//   march_flat                                  ONE loop in which each lane walks its 4 rays back to back — a lane that
-//                                               finishes a ray starts its next one in the same iteration instead of idling,
-//                                               so the warp pays max-over-lanes(sum of steps), not sum of maxima
+//   march_pool                                  ONE loop per bounce over the block's pool of rays: a lane that finishes a
+//                                               ray takes the next unmarched one in the same iteration instead of idling,
+//                                               so a warp pays about the mean ray length, not the sum of per-march maxima
 //   shading of the hits + set-up of secondaries convergent again (lanes that hit shade together)
-//   march_flat over the secondary rays, shading, and the sum in the shader's order: ((a0 + brdf0*b0) + a1) + brdf1*b1 ...
+//   march_pool over the secondary rays, shading, and the sum in the shader's order: ((a0 + brdf0*b0) + a1) + brdf1*b1 ...
 // Rays live in shared memory between the pieces (16 words per ray, [ray][word][thread] so a warp's accesses are conflict-free).
 constexpr int RAY_WORDS = 16;
 constexpr int TRACE_THREADS = 128;
@@ -125,24 +125,30 @@ __device__ void ray_setup(const TraceParams& P, float* S, int k, f3 wpos, f3 wno
     RS(k, 7) = __int_as_float(dm_f2i(sv.x)); RS(k, 8) = __int_as_float(dm_f2i(sv.y)); RS(k, 9) = __int_as_float(dm_f2i(sv.z));
 }
 
-// indirect.frag:137-152, 176 for the rays of this thread whose bit is set in `need`, back to back
-__device__ void march_flat(const TraceParams& P, float* S, unsigned int need, unsigned int& steps_taken)
+// indirect.frag:137-152, 176.  The block's 4 x TRACE_THREADS rays form a pool: a lane takes the next unmarched ray (a shared
+// cursor), walks it to its end, writes the outcome into that ray's slots and takes another — whichever pixel it belongs to.
+// Walking only its own pixel's rays left a warp waiting for its unluckiest lane (118 iterations against a mean of 44, ncu);
+// any lane can march any ray because a ray's arithmetic does not depend on who executes it.
+#define RSO(owner, k, f) S[((k) * RAY_WORDS + (f)) * TRACE_THREADS + (owner)]
+__device__ void march_pool(const TraceParams& P, float* S, const unsigned int* need, unsigned int* cursor, unsigned int& steps_taken)
 {
     const float Nf = (float)P.N, hi = (float)(P.N - 1), step_size = P.step_size;
     const int N = (int)P.N;
-    int k = 0, pvx = 0, pvy = 0, pvz = 0;
+    int k = 0, owner = 0, pvx = 0, pvy = 0, pvz = 0;
     uint32_t i = 0;
     f3 dir = {0.f, 0.f, 0.f}, pos = {0.f, 0.f, 0.f};
     bool have = false;
     auto next_ray = [&]() {
         have = false;
-        while (need)
+        for (;;)
         {
-            k = __ffs(need) - 1;
-            need &= need - 1;
-            dir = {RS(k, 0), RS(k, 1), RS(k, 2)};
-            pos = {RS(k, 3), RS(k, 4), RS(k, 5)};
-            pvx = __float_as_int(RS(k, 7)); pvy = __float_as_int(RS(k, 8)); pvz = __float_as_int(RS(k, 9));
+            const unsigned int j = atomicAdd(cursor, 1u);
+            if (j >= 4u * TRACE_THREADS) break;
+            owner = (int)(j % TRACE_THREADS); k = (int)(j / TRACE_THREADS);
+            if (!((need[owner] >> k) & 1u)) continue;
+            dir = {RSO(owner, k, 0), RSO(owner, k, 1), RSO(owner, k, 2)};
+            pos = {RSO(owner, k, 3), RSO(owner, k, 4), RSO(owner, k, 5)};
+            pvx = __float_as_int(RSO(owner, k, 7)); pvy = __float_as_int(RSO(owner, k, 8)); pvz = __float_as_int(RSO(owner, k, 9));
             i = 0;
             bool idle = (P.steps == 0);
             // ~15 % of the reference's rays have a NaN direction (blugausnoise2 leaves [0, 1]).  Under the pinned
@@ -155,7 +161,7 @@ __device__ void march_flat(const TraceParams& P, float* S, unsigned int need, un
                 if ((pvx | pvy | pvz) != 0) texel0 = __ldg(P.vox);
                 if ((texel0 & 0xffffu) == 0) { steps_taken += P.steps; idle = true; }
             }
-            if (idle) { RS(k, 0) = __uint_as_float(0u); RS(k, 1) = __uint_as_float(1u); continue; }
+            if (idle) { RSO(owner, k, 0) = __uint_as_float(0u); RSO(owner, k, 1) = __uint_as_float(1u); continue; }
             have = true;
             break;
         }
@@ -183,8 +189,8 @@ __device__ void march_flat(const TraceParams& P, float* S, unsigned int need, un
         if (!finished && ++i == P.steps) { finished = true; ranout = true; }
         if (finished)
         {
-            RS(k, 0) = __uint_as_float(hit_texel); RS(k, 1) = __uint_as_float(ranout ? 1u : 0u);
-            RS(k, 3) = pos.x; RS(k, 4) = pos.y; RS(k, 5) = pos.z;
+            RSO(owner, k, 0) = __uint_as_float(hit_texel); RSO(owner, k, 1) = __uint_as_float(ranout ? 1u : 0u);
+            RSO(owner, k, 3) = pos.x; RSO(owner, k, 4) = pos.y; RSO(owner, k, 5) = pos.z;
             next_ray();
         }
     }
@@ -237,27 +243,33 @@ __device__ __forceinline__ int wrapn(int i, int n) { int m = i % n; return m < 0
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_r(const TraceParams P, unsigned long long* __restrict__ step_counter)
 {
     extern __shared__ float S[];          // 4 rays x RAY_WORDS x TRACE_THREADS
+    __shared__ unsigned int need[TRACE_THREADS];
+    __shared__ unsigned int cursor[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const uint32_t y = P.y0 + (P.tile0 + blockIdx.y * P.tile_stride) * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t W = P.W, H = P.H;
+    const bool inside = x < P.W && y < P.y1;      // threads off the image own no rays but still march the block's pool
     unsigned int steps_taken = 0;
-    if (x < P.W && y < P.y1)
+    float uvx = 0.f, uvy = 0.f;
+    f3 cspos = {0.f, 0.f, 0.f}, wpos = {0.f, 0.f, 0.f};
+    const float* er = nullptr;
+    if (threadIdx.x == 0) { cursor[0] = 0u; cursor[1] = 0u; }
+    if (inside)
     {
-        const uint32_t W = P.W, H = P.H;
-        const float uvx = ((float)x + 0.5f) / (float)W, uvy = ((float)y + 0.5f) / (float)H;
+        uvx = ((float)x + 0.5f) / (float)W; uvy = ((float)y + 0.5f) / (float)H;
         // getCSpos, indirect.frag:44-53
         const int dx = dm_f2i(uvx * (float)W), dy = dm_f2i(uvy * (float)H);
         const float depth = (dx >= 0 && dy >= 0 && dx < (int)W && dy < (int)H) ? __ldg(P.depth + (size_t)dy * W + dx) : 0.0f;
         f4 cp = mul44(P.InvProj, f4{uvx * 2.0f - 1.0f, uvy * 2.0f - 1.0f, depth, 1.0f});
-        const f3 cspos = {cp.x / cp.w, cp.y / cp.w, cp.z / cp.w};
-        const f3 wpos = mul43(P.InvModelView, cspos, 1.0f);
+        cspos = {cp.x / cp.w, cp.y / cp.w, cp.z / cp.w};
+        wpos = mul43(P.InvModelView, cspos, 1.0f);
         // getNormal, indirect.frag:55-58 (texel-centre fetch)
         const ushort4 nq = __ldg(reinterpret_cast<const ushort4*>(P.normals) + (size_t)y * W + x);
         const f3 raw = {fmaf(unorm16(nq.x), 2.0f, -1.0f), fmaf(unorm16(nq.y), 2.0f, -1.0f), fmaf(unorm16(nq.z), 2.0f, -1.0f)};
         const f3 csnorm = normalize3(raw);
         const f3 wnorm = mul33(P.InvModelView, csnorm);
-
-        const float* er = P.rands ? P.rands + 16 * ((size_t)y * W + x) : nullptr;
+        er = P.rands ? P.rands + 16 * ((size_t)y * W + x) : nullptr;
         // the 4 primary rays: same origin and normal, seeds 0, 2, 4, 6 (indirect.frag:201-221)
 #pragma unroll 1
         for (int k = 0; k < 4; k++)
@@ -266,9 +278,15 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_r(const TraceParams P, 
             ray_rands(P, (float)(2 * k), uvx, uvy, er ? er + 4 * k : nullptr, rx, ry);
             ray_setup(P, S, k, wpos, wnorm, rx, ry);
         }
-        march_flat(P, S, 0xfu, steps_taken);
-        // shade them; every hit spawns the secondary ray of its pair (seeds 1, 3, 5, 7) from the hit point along the voxel normal
-        unsigned int second = 0;
+    }
+    need[threadIdx.x] = inside ? 0xfu : 0u;
+    __syncthreads();
+    march_pool(P, S, need, &cursor[0], steps_taken);
+    __syncthreads();
+    // shade them; every hit spawns the secondary ray of its pair (seeds 1, 3, 5, 7) from the hit point along the voxel normal
+    unsigned int second = 0;
+    if (inside)
+    {
 #pragma unroll 1
         for (int k = 0; k < 4; k++)
         {
@@ -284,7 +302,13 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_r(const TraceParams P, 
                 second |= 1u << k;
             }
         }
-        march_flat(P, S, second, steps_taken);
+    }
+    need[threadIdx.x] = second;
+    __syncthreads();
+    march_pool(P, S, need, &cursor[1], steps_taken);
+    __syncthreads();
+    if (inside)
+    {
         f3 ind = {0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int k = 0; k < 4; k++)
