@@ -395,12 +395,17 @@ def run_b200(args, rank, world, local_rank):
         pinned[slot] = t
     out_info = g.ctx.image_info(A.SLOT_INDIRECT_OUT)
     out_host = torch.empty(out_info.size_bytes, dtype=torch.uint8).pin_memory()
-    h2d = sum(int(t.numel()) for t in pinned.values())
-    d2h = int(out_host.numel())
+    # a rank of a sharded frame moves only the G-buffer rows it traces (and reads back only those rows of the image); the shadow
+    # map is needed whole by every rank
+    rows = world > 1
+    own_frac = float(g.own_rows_mask().mean()) if rows else 1.0
+    h2d = int(sum(int(t.numel()) * (own_frac if slot != A.SLOT_SHADOW else 1.0) for slot, t in pinned.items()))
+    d2h = int(out_host.numel() * own_frac)
+    full_d2h = int(out_host.numel())
 
     def upload_inputs():
         for slot, t in pinned.items():
-            g.ctx.upload_ptr(slot, t.data_ptr(), t.numel())
+            g.ctx.upload_ptr(slot, t.data_ptr(), t.numel(), rows=rows and slot != A.SLOT_SHADOW)
 
     def frame():
         g.frame(cams["voxel"], k)
@@ -447,7 +452,7 @@ def run_b200(args, rank, world, local_rank):
         out_hosts = [out_host, torch.empty(out_info.size_bytes, dtype=torch.uint8).pin_memory()]
         upload_inputs()
         for i in range(3):
-            frame(); upload_inputs(); g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_hosts[i & 1].data_ptr(), d2h)
+            frame(); upload_inputs(); g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_hosts[i & 1].data_ptr(), full_d2h, rows=rows)
         g.ctx.sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -457,7 +462,7 @@ def run_b200(args, rank, world, local_rank):
         for i in range(args.steps):
             frame()                            # consumes the inputs uploaded one iteration ago
             upload_inputs()                    # next frame's inputs (H2D, copy stream)
-            g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_hosts[i & 1].data_ptr(), d2h)
+            g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_hosts[i & 1].data_ptr(), full_d2h, rows=rows)
             if i:
                 g.ctx.readback_wait(1)         # the image of frame i-1 is on the host: the caller consumes it
                 checksum += int(out_hosts[(i - 1) & 1][-8])
@@ -483,9 +488,9 @@ def run_b200(args, rank, world, local_rank):
             pcie["h2d_gbs"] = 4 * big.numel() / (time.perf_counter() - t0) / 1e9
             t0 = time.perf_counter()
             for i in range(4):
-                g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_hosts[i & 1].data_ptr(), d2h)
+                g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, out_hosts[i & 1].data_ptr(), full_d2h)
             g.ctx.sync()
-            pcie["d2h_gbs"] = 4 * d2h / (time.perf_counter() - t0) / 1e9
+            pcie["d2h_gbs"] = 4 * full_d2h / (time.perf_counter() - t0) / 1e9
         # secondary pass, reported beside the metric (not part of it): GTAO + its blur, and the indirect blur tail
         for _ in range(3):
             g.ctx.gtao(cams["main"]); g.ctx.blur_indirect(k); g.ctx.lighting_deferred(k)
@@ -495,12 +500,13 @@ def run_b200(args, rank, world, local_rank):
         peaks_live = {"tex_trilinear_per_s": g.ctx.microbench(0), "red_v4_per_s": g.ctx.microbench(1)} if rank == 0 else {}
 
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    cs = torch.tensor([float(counters["cone_samples"]), float(launches)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    cs = torch.tensor([float(counters["cone_samples"]), float(launches), float(h2d), float(d2h)], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cs, op=dist.ReduceOp.SUM)
     ms_total, e2e_ms = float(t[0]), float(t[1])
     total_samples, launches_all = float(cs[0]), int(cs[1])
+    h2d, d2h = int(cs[2]), int(cs[3])              # whole job: every rank's own G-buffer rows + its copy of the shadow map
     ms_frame = ms_total / args.steps
     if rank == 0:
         # roofline: dominant kernel = the stage with the largest mean device time in the timed region
@@ -549,7 +555,7 @@ def run_b200(args, rank, world, local_rank):
                "roofline": roofline, "roofline_stages": rstages, "other_bounds": other,
                "e2e": {"value": e2e_ms / args.steps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "pcie": {k_: round(v_, 1) for k_, v_ in pcie.items()},
-                       "note": "one frame in flight: H2D of frame f+1 and D2H of frame f-1 overlap the kernels of frame f"},
+                       "note": "one frame in flight: H2D of frame f+1 and D2H of frame f-1 overlap the kernels of frame f" + ("" if world == 1 else "; each rank moves only the G-buffer / image rows it traces (f184_upload_image_rows), the shadow map whole")},
                "gpu_launches": launches_all, "clocks": clk}
         if world == 1 and not args.no_cpu_baseline:
             cpu = CpuPath(args, sc, cams, fi, vchunks=1, tfrac=16, bands=2)

@@ -151,6 +151,8 @@ _SIGS = {
     "upload_image": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
     "readback": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
     "readback_async": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "upload_image_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "readback_async_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
     "readback_wait": (C.c_int, [C.c_void_p, C.c_uint32]),
     "set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sync": (C.c_int, [C.c_void_p]),
@@ -286,8 +288,10 @@ class VoxelGI:
         self._keep.append(arr)
         self._ck(self.lib.upload_image(self.h, slot, arr.ctypes.data, arr.nbytes), "upload_image")
 
-    def upload_ptr(self, slot, host_ptr, nbytes):
-        self._ck(self.lib.upload_image(self.h, slot, host_ptr, nbytes), "upload_image")
+    def upload_ptr(self, slot, host_ptr, nbytes, rows=False):
+        """rows=True: only the rows this rank traces travel (f184_upload_image_rows)"""
+        fn = self.lib.upload_image_rows if rows else self.lib.upload_image
+        self._ck(fn(self.h, slot, host_ptr, nbytes), "upload_image")
 
     def readback(self, slot) -> np.ndarray:
         d = self.image_info(slot)
@@ -300,8 +304,9 @@ class VoxelGI:
         self._ck(self.lib.readback(self.h, slot, out.ctypes.data, out.nbytes), "readback")
         return out
 
-    def readback_async_ptr(self, slot, host_ptr, nbytes):
-        self._ck(self.lib.readback_async(self.h, slot, host_ptr, nbytes), "readback_async")
+    def readback_async_ptr(self, slot, host_ptr, nbytes, rows=False):
+        fn = self.lib.readback_async_rows if rows else self.lib.readback_async
+        self._ck(fn(self.h, slot, host_ptr, nbytes), "readback_async")
 
     def readback_wait(self, age=0):
         self._ck(self.lib.readback_wait(self.h, age), "readback_wait")

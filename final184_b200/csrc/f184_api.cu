@@ -452,7 +452,39 @@ int f184_image_info(f184_ctx* c, uint32_t slot, f184_image_desc* out)
     return F184_OK;
 }
 
-int f184_upload_image(f184_ctx* c, uint32_t slot, const void* host, size_t bytes)
+// Copy only the rows this rank traces (f184_set_trace_rows / f184_set_trace_tiles) of a W x H image between two buffers with
+// the same layout: the selected 8-row tile rows form a regular 2D pattern (8 rows wide, every `stride`-th tile), so one
+// cudaMemcpy2DAsync moves them; a partial last tile goes separately.  Falls back to the whole image for other shapes.
+static int copy_selected_rows(f184_ctx* c, const DevImage& im, void* dst, const void* src, cudaMemcpyKind kind, cudaStream_t st)
+{
+    const uint32_t H = c->cfg.height;
+    const size_t rb = im.desc.row_pitch_bytes;
+    uint32_t y0, y1, tile0, stride;
+    const uint32_t ntiles = f184_trace_tiles(c, H, &y0, &y1, &tile0, &stride);
+    if (im.desc.height != H || im.desc.depth != 1 || rb == 0 || (stride > 1 && (y0 & 7)))
+    {
+        CK(c, cudaMemcpyAsync(dst, src, im.desc.size_bytes, kind, st));
+        return F184_OK;
+    }
+    if (!ntiles) return F184_OK;
+    const uint32_t first_row = y0 + tile0 * 8;
+    // tiles i = 0..ntiles-1 start at row first_row + i * 8 * stride; the last one may be cut by y1
+    const uint32_t last_start = first_row + (ntiles - 1) * 8 * stride;
+    const uint32_t last_rows = (y1 - last_start) < 8 ? (y1 - last_start) : 8;
+    const uint32_t full = last_rows == 8 ? ntiles : ntiles - 1;
+    char* d = static_cast<char*>(dst);
+    const char* s_ = static_cast<const char*>(src);
+    if (full) CK(c, cudaMemcpy2DAsync(d + (size_t)first_row * rb, (size_t)8 * stride * rb, s_ + (size_t)first_row * rb, (size_t)8 * stride * rb,
+                                      (size_t)8 * rb, full, kind, st));
+    if (full != ntiles) CK(c, cudaMemcpyAsync(d + (size_t)last_start * rb, s_ + (size_t)last_start * rb, (size_t)last_rows * rb, kind, st));
+    return F184_OK;
+}
+
+static int upload_impl(f184_ctx* c, uint32_t slot, const void* host, size_t bytes, bool selected_rows);
+int f184_upload_image(f184_ctx* c, uint32_t slot, const void* host, size_t bytes) { return upload_impl(c, slot, host, bytes, false); }
+int f184_upload_image_rows(f184_ctx* c, uint32_t slot, const void* host, size_t bytes) { return upload_impl(c, slot, host, bytes, true); }
+
+static int upload_impl(f184_ctx* c, uint32_t slot, const void* host, size_t bytes, bool selected_rows)
 {
     if (!c || slot >= F184_SLOT_COUNT || !host) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "upload_image: bad argument");
     int rc = f184_ensure_image(c, slot);
@@ -469,6 +501,7 @@ int f184_upload_image(f184_ctx* c, uint32_t slot, const void* host, size_t bytes
     }
     if (!im.owned || im.ext)
     {   // caller-owned memory: plain stream-ordered copy
+        if (selected_rows) return copy_selected_rows(c, im, im.ptr, host, cudaMemcpyHostToDevice, c->stream);
         CK(c, cudaMemcpyAsync(im.ptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
         return F184_OK;
     }
@@ -486,7 +519,8 @@ int f184_upload_image(f184_ctx* c, uint32_t slot, const void* host, size_t bytes
     CK(c, cudaEventRecord(im.ev_release[im.cur], c->stream));
     im.release_valid[im.cur] = true;
     if (im.release_valid[nb]) CK(c, cudaStreamWaitEvent(c->copy_stream, im.ev_release[nb], 0));
-    CK(c, cudaMemcpyAsync(im.buf[nb], host, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    if (selected_rows) { rc = copy_selected_rows(c, im, im.buf[nb], host, cudaMemcpyHostToDevice, c->copy_stream); if (rc) return rc; }
+    else CK(c, cudaMemcpyAsync(im.buf[nb], host, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CK(c, cudaEventRecord(im.ev_up[nb], c->copy_stream));
     im.cur = nb;
     im.ptr = im.buf[nb];
@@ -495,7 +529,11 @@ int f184_upload_image(f184_ctx* c, uint32_t slot, const void* host, size_t bytes
     return F184_OK;
 }
 
-int f184_readback_async(f184_ctx* c, uint32_t slot, void* host, size_t bytes)
+static int readback_impl(f184_ctx* c, uint32_t slot, void* host, size_t bytes, bool selected_rows);
+int f184_readback_async(f184_ctx* c, uint32_t slot, void* host, size_t bytes) { return readback_impl(c, slot, host, bytes, false); }
+int f184_readback_async_rows(f184_ctx* c, uint32_t slot, void* host, size_t bytes) { return readback_impl(c, slot, host, bytes, true); }
+
+static int readback_impl(f184_ctx* c, uint32_t slot, void* host, size_t bytes, bool selected_rows)
 {
     if (!c || slot >= F184_SLOT_COUNT || !host) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "readback: bad argument");
     int rc = f184_ensure_image(c, slot);
@@ -527,10 +565,13 @@ int f184_readback_async(f184_ctx* c, uint32_t slot, void* host, size_t bytes)
         CK(c, cudaMalloc(&c->rb_stage[b], bytes));
         c->rb_cap[b] = bytes;
     }
-    CK(c, cudaMemcpyAsync(c->rb_stage[b], c->img[slot].ptr, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    const bool rows = selected_rows && bytes == c->img[slot].desc.size_bytes;
+    if (rows) { rc = copy_selected_rows(c, c->img[slot], c->rb_stage[b], c->img[slot].ptr, cudaMemcpyDeviceToDevice, c->stream); if (rc) return rc; }
+    else CK(c, cudaMemcpyAsync(c->rb_stage[b], c->img[slot].ptr, bytes, cudaMemcpyDeviceToDevice, c->stream));
     CK(c, cudaEventRecord(c->ev_rb_snap[b], c->stream));
     CK(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_rb_snap[b], 0));
-    CK(c, cudaMemcpyAsync(host, c->rb_stage[b], bytes, cudaMemcpyDeviceToHost, c->d2h_stream));
+    if (rows) { rc = copy_selected_rows(c, c->img[slot], host, c->rb_stage[b], cudaMemcpyDeviceToHost, c->d2h_stream); if (rc) return rc; }
+    else CK(c, cudaMemcpyAsync(host, c->rb_stage[b], bytes, cudaMemcpyDeviceToHost, c->d2h_stream));
     CK(c, cudaEventRecord(c->ev_rb_done[b], c->d2h_stream));
     c->rb_valid[b] = true;
     c->rb_cur = b;

@@ -259,6 +259,12 @@ int f184_readback(f184_ctx* ctx, uint32_t slot, void* host, size_t bytes);      
  * f184_readback_wait(ctx, age): age 0 = the most recent asynchronous read-back, 1 = the one before it (a consumer that
  * keeps one frame in flight submits frame f+1, then waits for the image of frame f). */
 int f184_readback_async(f184_ctx* ctx, uint32_t slot, void* pinned_host, size_t bytes);
+/* Sharded frames (one process per GPU): the same two transfers restricted to the rows this rank traces (f184_set_trace_rows /
+ * f184_set_trace_tiles).  `host` addresses the WHOLE W x H image; only the selected rows are read / written, the other rows of
+ * the device image (upload) or of the host buffer (read-back) are left as they are.  A rank of N then moves 1/N of the
+ * G-buffer bytes over its PCIe link instead of all of them.  Slots that are not W x H images are transferred whole. */
+int f184_upload_image_rows(f184_ctx* ctx, uint32_t slot, const void* host, size_t bytes);
+int f184_readback_async_rows(f184_ctx* ctx, uint32_t slot, void* pinned_host, size_t bytes);
 int f184_readback_wait(f184_ctx* ctx, uint32_t age);
 
 /* Vulkan interop: import an exported VkDeviceMemory (opaque fd) as a slot, and

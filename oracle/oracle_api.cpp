@@ -3,6 +3,8 @@
 #include <chrono>
 #include <cstdio>
 
+#include <algorithm>
+
 #include "oracle_common.h"
 
 using namespace orc;
@@ -212,6 +214,24 @@ int f184o_upload_image(f184o_ctx* c, uint32_t slot, const void* host, size_t byt
     memcpy(c->img[slot].ptr, host, bytes);
     return F184_OK;
 }
+// the rows this rank traces (set_trace_rows / set_trace_tiles) of a W x H image; other shapes whole
+static int copy_selected_rows(f184o_ctx* c, uint32_t slot, void* dst, const void* src, size_t bytes)
+{
+    if (!c || slot >= F184_SLOT_COUNT) return F184_ERR_INVALID_ARGUMENT;
+    int r = ensure_image(c, slot);
+    if (r) return r;
+    const f184_image_desc& d = c->img[slot].desc;
+    if (bytes != d.size_bytes) { c->err = "size mismatch"; return F184_ERR_INVALID_ARGUMENT; }
+    if (!dst) dst = c->img[slot].ptr;
+    if (!src) src = c->img[slot].ptr;
+    if (d.height != c->cfg.height || d.depth != 1) { memcpy(dst, src, bytes); return F184_OK; }
+    const size_t rb = d.row_pitch_bytes;
+    for (uint32_t y = c->row0; y < std::min(c->row1, d.height); y++)
+        if ((y >> 3) % c->tile_stride == c->tile_first) memcpy((char*)dst + y * rb, (const char*)src + y * rb, rb);
+    return F184_OK;
+}
+int f184o_upload_image_rows(f184o_ctx* c, uint32_t slot, const void* host, size_t bytes) { return copy_selected_rows(c, slot, nullptr, host, bytes); }
+int f184o_readback_async_rows(f184o_ctx* c, uint32_t slot, void* host, size_t bytes) { return copy_selected_rows(c, slot, host, nullptr, bytes); }
 int f184o_readback(f184o_ctx* c, uint32_t slot, void* host, size_t bytes)
 {
     if (!c || slot >= F184_SLOT_COUNT) return F184_ERR_INVALID_ARGUMENT;

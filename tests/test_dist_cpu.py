@@ -96,3 +96,28 @@ def test_sharded_frame_world2_gloo_equals_single_process(tmp_path, oracle_lib, p
     for i in range(world):
         assert np.array_equal(r[i]["rad"], o.readback(A.SLOT_RADIANCE)), f"rank {i}: summed partial volumes differ from the whole"
         assert np.array_equal(r[i]["img"].view(np.uint16), want.view(np.uint16)), f"rank {i}: assembled image differs"
+
+
+def test_row_selective_transfers(oracle_lib):
+    """f184_upload_image_rows / f184_readback_async_rows move only the rows a rank traces (interleaved 8-row tiles, ragged last
+    tile, a row window); everything else stays as it was.  Non-image slots travel whole."""
+    w, h = 24, 44                                  # 5 full tiles + one of 4 rows
+    c = A.VoxelGI(32, w, h, A.MODE_NORTHSTAR, shadow_res=16, lib=oracle_lib)
+    rng = np.random.default_rng(0)
+    old, new = (rng.random((h, w), dtype=np.float32) for _ in range(2))
+    for first, stride, y0, y1 in ((1, 4, 0, 0xffffffff), (0, 2, 0, 0xffffffff), (1, 2, 8, 40), (0, 1, 0, 0xffffffff)):
+        c.set_trace_tiles(first, stride); c.set_trace_rows(y0, y1)
+        mine = ((np.arange(h) // 8) % stride == first) & (np.arange(h) >= y0) & (np.arange(h) < min(y1, h))
+        c.upload(A.SLOT_DEPTH, old)
+        c.upload_ptr(A.SLOT_DEPTH, new.ctypes.data, new.nbytes, rows=True)
+        got = c.readback(A.SLOT_DEPTH)
+        assert np.array_equal(got[mine], new[mine]) and np.array_equal(got[~mine], old[~mine]), (first, stride)
+        host = np.full((h, w), -1.0, np.float32)
+        c.readback_async_ptr(A.SLOT_DEPTH, host.ctypes.data, host.nbytes, rows=True)
+        c.sync()
+        assert np.array_equal(host[mine], got[mine]) and (host[~mine] == -1.0).all()
+    sh = rng.random((16, 16), dtype=np.float32)
+    c.set_trace_tiles(1, 4)
+    c.upload_ptr(A.SLOT_SHADOW, sh.ctypes.data, sh.nbytes, rows=True)
+    assert np.array_equal(c.readback(A.SLOT_SHADOW), sh)
+    c.close()

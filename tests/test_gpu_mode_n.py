@@ -185,3 +185,28 @@ def test_probe_batch_views(cuda_lib, oracle_lib, proc_scene):
         if o2[v][..., :3].astype(np.float32).mean() > 1e-3:
             assert Hh.rel_l2(g2[v][..., :3].astype(np.float32), o2[v][..., :3].astype(np.float32)) <= 1e-2, v
     bg.close(); bo.close(); one.close()
+
+
+def test_row_selective_transfers_gpu(cuda_lib):
+    """Same contract as tests/test_dist_cpu.py::test_row_selective_transfers on the device (one cudaMemcpy2DAsync per transfer,
+    double-buffered upload slot, staged read-back)."""
+    import torch
+    w, h = 24, 44
+    c = A.VoxelGI(32, w, h, A.MODE_NORTHSTAR, shadow_res=16, lib=cuda_lib)
+    rng = np.random.default_rng(0)
+    for first, stride, y0, y1 in ((1, 4, 0, 0xffffffff), (0, 2, 0, 0xffffffff), (1, 2, 8, 40), (0, 1, 0, 0xffffffff)):
+        old, new = (rng.random((h, w), dtype=np.float32) for _ in range(2))
+        c.set_trace_tiles(first, stride); c.set_trace_rows(y0, y1)
+        mine = ((np.arange(h) // 8) % stride == first) & (np.arange(h) >= y0) & (np.arange(h) < min(y1, h))
+        # the upload slot is double-buffered: fill BOTH buffers with `old` so the rows that do not travel are defined
+        c.upload(A.SLOT_DEPTH, old); c.upload(A.SLOT_DEPTH, old)
+        pin = torch.from_numpy(new).pin_memory()
+        c.upload_ptr(A.SLOT_DEPTH, pin.data_ptr(), new.nbytes, rows=True)
+        got = c.readback(A.SLOT_DEPTH)
+        assert np.array_equal(got[mine], new[mine]) and np.array_equal(got[~mine], old[~mine]), (first, stride)
+        host = torch.full((h, w), -1.0, dtype=torch.float32).pin_memory()
+        c.readback_async_ptr(A.SLOT_DEPTH, host.data_ptr(), new.nbytes, rows=True)
+        c.sync()
+        hn = host.numpy()
+        assert np.array_equal(hn[mine], got[mine]) and (hn[~mine] == -1.0).all()
+    c.close()
