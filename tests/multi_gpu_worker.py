@@ -109,6 +109,35 @@ def main():
     if [v for v, _ in own] != list(range(*D.view_ranges(nv, world)[rank])): bad.append("probe view partition")
     dist.barrier()
     pb.close(); small.close()
+    # the real scene at a real size: Sponza 256^3 (BASELINE configs[1]'s volume), two frames back to back — 0.7 M fragments through
+    # peer atomics, ~8 k bricks through the gather — against one GPU
+    if S.sponza_available():
+        g.close(); one.close()
+        sp = S.load_sponza()
+        N2, W2, H2 = 256, 320, 184
+        fi2 = frame_inputs(sp, cams["main"], cams["shadow"], W2, H2, 1024, 0, cache=False)
+        k2 = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W2, H2, 0, True)
+        g = D.ShardedVoxelGI(N2, W2, H2, shadow_res=1024, device=local, rank=rank, nranks=world, scene=sp, voxel_cam=cams["voxel"], flags=A.FLAG_GATHER_LINEAR)
+        one = A.VoxelGI(N2, W2, H2, A.MODE_NORTHSTAR, shadow_res=1024, device=local)
+        one.upload_scene(sp)
+        for c in (g.ctx, one):
+            for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_MATERIAL, "material"), (A.SLOT_SHADOW, "shadow")):
+                c.upload(slot, fi2[key])
+        g.connect()
+        for frame in range(2):
+            g.frame(cams["voxel"], k2)
+        for frame in range(2):
+            one.voxelize(cams["voxel"]); one.inject(k2); one.build_mips(); one.trace_indirect(k2)
+        g.ctx.sync(); one.sync()
+        dist.barrier()
+        if not np.array_equal(g.ctx.readback(A.SLOT_RADIANCE), one.readback(A.SLOT_RADIANCE)): bad.append("sponza 256: radiance")
+        if not np.array_equal(g.ctx.readback(A.SLOT_MIPS), one.readback(A.SLOT_MIPS)): bad.append("sponza 256: mips")
+        m2 = g.own_rows_mask()
+        if not np.array_equal(g.ctx.readback(A.SLOT_INDIRECT_OUT)[m2].view(np.uint16), one.readback(A.SLOT_INDIRECT_OUT)[m2].view(np.uint16)): bad.append("sponza 256: own image tile rows")
+        fr = torch.tensor([float(g.ctx.counter(A.COUNTER_FRAGMENTS))], device=f"cuda:{local}")
+        dist.all_reduce(fr)
+        if int(fr.item()) != one.counter(A.COUNTER_FRAGMENTS): bad.append(f"sponza 256: fragments {int(fr.item())} vs {one.counter(A.COUNTER_FRAGMENTS)}")
+        dist.barrier()
     print(f"rank {rank}: {'OK' if not bad else 'MISMATCH ' + '; '.join(bad[:6])} (fragments over ranks {int(frags.item())})", flush=True)
     g.close(); one.close()
     dist.destroy_process_group()
