@@ -440,7 +440,7 @@ def run_b200(args, rank, world, local_rank):
             tot, runs = g.ctx.stage_total_ms(s)
             if runs:
                 stage_ms[A.STAGE_NAMES[s]] = tot / args.steps          # per frame (a stage may run more than once in a frame)
-        comm_ms = stage_ms.get("exchange", 0.0)
+        comm_ms = stage_ms.get("exchange", 0.0) + stage_ms.get("barrier", 0.0)
         g.ctx.stage_time_reset(False)
         counters = {"fragments": g.ctx.counter(A.COUNTER_FRAGMENTS), "bricks": g.ctx.counter(A.COUNTER_BRICKS),
                     "occupied": g.ctx.counter(A.COUNTER_OCCUPIED), "cone_samples": g.ctx.counter(A.COUNTER_MARCH_STEPS)}
@@ -499,6 +499,11 @@ def run_b200(args, rank, world, local_rank):
         # the two peaks MEASURED_PEAKS.json does not hold, measured live (rank 0, after the timed regions)
         peaks_live = {"tex_trilinear_per_s": g.ctx.microbench(0), "red_v4_per_s": g.ctx.microbench(1)} if rank == 0 else {}
 
+    stage_ranks = None
+    if world > 1:
+        every = [None] * world
+        dist.all_gather_object(every, stage_ms)
+        stage_ranks = {k_: [round(min(e.get(k_, 0.0) for e in every), 4), round(max(e.get(k_, 0.0) for e in every), 4)] for k_ in stage_ms}
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     cs = torch.tensor([float(counters["cone_samples"]), float(launches), float(h2d), float(d2h)], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
@@ -551,7 +556,7 @@ def run_b200(args, rank, world, local_rank):
                           "parallelism": g.describe() + ("" if args.no_overlap else ("; voxelize+normalise of frame f+1 overlap the cone trace of frame f (internal stream)" if world == 1 else "; the accumulation of frame f+1 (peer atomics) overlaps the gather + cone trace of frame f")), "l2": "inputs larger than L2 (volume chain %.0f MB + accumulators; no flush)" % (algorithmic_bytes("trace", args, sc, counters) / 1e6)},
                "gvoxel_per_s": N ** 3 / (ms_frame * 1e-3) / 1e9,
                "gcone_samples_per_s": total_samples / (stage_ms.get("trace", ms_frame) * 1e-3) / 1e9,
-               "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "stages_concurrent": concurrent, "comm_ms": comm_ms, "secondary_ms": extra_ms, "counters": counters,
+               "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "stages_concurrent": concurrent, "stages_ms_min_max_over_ranks": stage_ranks, "comm_ms": comm_ms, "secondary_ms": extra_ms, "counters": counters,
                "roofline": roofline, "roofline_stages": rstages, "other_bounds": other,
                "e2e": {"value": e2e_ms / args.steps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "pcie": {k_: round(v_, 1) for k_, v_ in pcie.items()},

@@ -28,8 +28,8 @@ MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
  SLOT_ACCUM_COLOR, SLOT_ACCUM_NORMAL, SLOT_VOX_ALBEDO, SLOT_VOX_NORMAL, SLOT_RADIANCE, SLOT_MIPS,
  SLOT_BRICK_FLAGS, SLOT_LIGHTING, SLOT_TAA_HISTORY, SLOT_TAA_OUT, SLOT_COLOR_OUT, SLOT_COUNT) = range(24)
 (STAGE_CLEAR, STAGE_VOXELIZE, STAGE_NORMALISE, STAGE_INJECT, STAGE_MIPS, STAGE_TRACE, STAGE_GTAO,
- STAGE_BLUR, STAGE_EXCHANGE, STAGE_LIGHTING, STAGE_COMPOSITE, STAGE_COUNT) = range(12)
-STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur", "exchange", "lighting", "composite"]
+ STAGE_BLUR, STAGE_EXCHANGE, STAGE_LIGHTING, STAGE_COMPOSITE, STAGE_BARRIER, STAGE_COUNT) = range(13)
+STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur", "exchange", "lighting", "composite", "barrier"]
 (COUNTER_FRAGMENTS, COUNTER_MARCH_STEPS, COUNTER_OCCUPIED, COUNTER_KERNEL_LAUNCHES, COUNTER_BRICKS) = range(5)
 (IPC_ACCUM_COLOR, IPC_ACCUM_NORMAL, IPC_BRICK_FLAGS, IPC_EXPORT, IPC_COUNTERS, IPC_BRICK_LIST, IPC_SYNC, IPC_COUNT) = range(8)
 FLAG_EXTERNAL_RANDS = 1

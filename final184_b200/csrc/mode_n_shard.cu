@@ -195,11 +195,11 @@ extern "C" int f184_peer_barrier(f184_ctx* c)
     B.epoch = ++c->barrier_epoch;
     int rc = f184_join_vox(c);             // this rank's fragments (possibly still in flight on vox_stream) leave before its flag does
     if (rc) return rc;
-    rc = f184_stage_begin(c, F184_STAGE_EXCHANGE);
+    rc = f184_stage_begin(c, F184_STAGE_BARRIER);
     if (rc) return rc;
     k_peer_barrier<<<1, 32, 0, c->stream>>>(B);
     CK_LAUNCH(c);
-    rc = f184_stage_end(c, F184_STAGE_EXCHANGE);
+    rc = f184_stage_end(c, F184_STAGE_BARRIER);
     if (rc) return rc;
     if (!c->ev_barrier) CK(c, cudaEventCreateWithFlags(&c->ev_barrier, cudaEventDisableTiming));
     CK(c, cudaEventRecord(c->ev_barrier, c->stream));

@@ -216,10 +216,11 @@ typedef enum f184_stage_id {
     F184_STAGE_TRACE = 5,
     F184_STAGE_GTAO = 6,
     F184_STAGE_BLUR = 7,
-    F184_STAGE_EXCHANGE = 8,       /* multi-GPU: peer barriers + gather of the other ranks' bricks */
+    F184_STAGE_EXCHANGE = 8,       /* multi-GPU: gather of the other ranks' bricks over NVLink */
     F184_STAGE_LIGHTING = 9,       /* f184_lighting_deferred */
     F184_STAGE_COMPOSITE = 10,     /* f184_composite */
-    F184_STAGE_COUNT = 11
+    F184_STAGE_BARRIER = 11,       /* multi-GPU: f184_peer_barrier (flag exchange + the wait for the slowest rank) */
+    F184_STAGE_COUNT = 12
 } f184_stage_id;
 
 typedef enum f184_counter_id {

@@ -8,7 +8,7 @@ for g in "$@"; do
 import json
 try:
     d=json.loads(open("gpurun_out/bench_${tag}_g$g.json").read().strip().splitlines()[-1])
-    print("N=$g", round(d["value"],4), "ms/frame", d["stages_ms"], "e2e", round(d["e2e"]["value"],3))
+    print("N=$g", round(d["value"],4), "ms/frame", d["stages_ms"], "e2e", round(d["e2e"]["value"],3)); print("   min/max over ranks", d.get("stages_ms_min_max_over_ranks"))
 except Exception as e:
     print("N=$g failed", e); print(open("gpurun_out/bench_${tag}_g$g.err").read()[-2500:])
 PY
