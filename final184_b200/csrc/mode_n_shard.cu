@@ -12,6 +12,8 @@
 //     mode_n_mips.cu into contiguous 4 KB records (level 0 + levels 1-3 of one 8^3 brick), with coalesced 16-byte peer
 //     loads, and writes them through surfaces into its own texture storage; only listed bricks move (Sponza at 512^3:
 //     ~0.12 GB for the whole volume instead of 1.0 GB dense).  Levels >= 4 are then finished locally (k_mips_tail).
+#include <cstdlib>
+
 #include "f184_device.cuh"
 
 int f184_mips_tail_n(f184_ctx* c, bool own_stage);      // mode_n_mips.cu
@@ -242,5 +244,9 @@ int f184_gather_n(f184_ctx* c)
     CK_LAUNCH(c);
     rc = f184_stage_end(c, F184_STAGE_EXCHANGE);
     if (rc) return rc;
+    // A/B knob F184_VOX_AFTER_GATHER=1: the next frame's accumulation (vox_stream) starts behind the gather instead of behind
+    // the barrier before it, so its peer atomics do not share NVLink and the SMs with the gather's peer loads
+    static const bool after_gather = [] { const char* e = getenv("F184_VOX_AFTER_GATHER"); return e && atoi(e) != 0; }();
+    if (after_gather && c->ev_barrier) CK(c, cudaEventRecord(c->ev_barrier, c->stream));
     return f184_mips_tail_n(c, true);
 }
