@@ -116,6 +116,7 @@ struct vec3
     vec3 rgb() const { return *this; }
     vec3 yzx() const { return vec3(y, z, x); }
     vec3 zxy() const { return vec3(z, x, y); }
+    vec3 zyx() const { return vec3(z, y, x); }
     vec3 rrr() const { return vec3(x, x, x); }
     vec2 zz() const { return vec2(z, z); }
     void set_xy(const vec2& v) { x = v.x; y = v.y; }
