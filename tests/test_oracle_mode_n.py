@@ -351,3 +351,51 @@ def test_cone_trace_equals_an_independent_float64_restatement(oracle_lib, proc_s
     assert err < 5e-3, err
     assert np.allclose(got[..., 3], want[..., 3], rtol=2e-3, atol=1e-3)
     assert abs(n_samples - samples_oracle) <= 0.01 * samples_oracle, (n_samples, samples_oracle)
+
+
+def test_injection_equals_an_independent_float64_restatement(oracle_lib, proc_scene, cams):
+    """DESIGN.md §3 B.3 again in numpy float64, vectorised over the occupied voxels: world centre through the inverse voxel
+    camera, decoded normal, albedo^2.2, the shadow test of indirect.frag:161-165, two-sided Lambert, RGBA8 quantisation by the
+    exposure.  fp32 vs fp64 may flip a value that sits on a rounding edge (+-1 LSB) or a shadow comparison on its edge; both
+    are counted and bounded."""
+    n, sh = 64, 256
+    fi = frame_inputs(proc_scene, cams["main"], cams["shadow"], 16, 16, sh, 0, cache=False)
+    k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], 16, 16, 0, True)
+    o = A.VoxelGI(grid_n=n, width=16, height=16, mode=A.MODE_NORTHSTAR, shadow_res=sh, lib=oracle_lib)
+    o.upload_scene(proc_scene)
+    o.upload(A.SLOT_SHADOW, fi["shadow"])
+    o.voxelize(cams["voxel"]); o.inject(k)
+    alb = o.readback(A.SLOT_VOX_ALBEDO).reshape(n, n, n, 4)
+    nrm = o.readback(A.SLOT_VOX_NORMAL).reshape(n, n, n, 4).astype(np.float64)
+    got = o.readback(A.SLOT_RADIANCE).reshape(n, n, n, 4).astype(np.int64)
+    o.close()
+    cm = lambda c16: np.array(list(c16), np.float64).reshape(4, 4).T
+    v2w = np.linalg.inv(cm(k.ext.VoxelProj) @ cm(k.ext.VoxelView))
+    sview, sproj = cm(k.ext.ShadowView), cm(k.ext.ShadowProj)
+    zz, yy, xx = np.nonzero(alb[..., 3])
+    assert len(zz) > 5000 and not got[alb[..., 3] == 0].any()
+    ndc = np.stack([(xx + 0.5) / n * 2 - 1, (yy + 0.5) / n * 2 - 1, (zz + 0.5) / n, np.ones(len(zz))])
+    p = v2w @ ndc
+    p = p[:3] / p[3]
+    nv = nrm[zz, yy, xx, :3].T / 127.0
+    ln = np.linalg.norm(nv, axis=0)
+    nv = np.where(ln > 0, nv / np.maximum(ln, 1e-30), nv)
+    col = (alb[zz, yy, xx, :3].T.astype(np.float64) / 255.0) ** 2.2
+    s = sproj @ (sview @ np.vstack([p + nv * 0.06, np.ones(len(zz))]))
+    s = s[:3] / s[3]
+    tx, ty = np.floor((s[0] * 0.5 + 0.5) * sh).astype(int), np.floor((s[1] * 0.5 + 0.5) * sh).astype(int)
+    inside = (tx >= 0) & (ty >= 0) & (tx < sh) & (ty < sh)
+    shz = np.where(inside, fi["shadow"][np.clip(ty, 0, sh - 1), np.clip(tx, 0, sh - 1)], 0.0)
+    margin = shz - (s[2] + 0.005)
+    shade = (margin >= 0).astype(np.float64)
+    sun_dir = np.array(list(k.sun.position), np.float64)
+    lam = np.abs(-(sun_dir[:, None] * nv).sum(0))
+    lum = np.array(list(k.sun.luminance), np.float64)
+    want = np.floor(np.clip(col * lum[:, None] * lam * shade / lum.max(), 0, 1) * 255 + 0.5).astype(np.int64).T
+    have = got[zz, yy, xx, :3]
+    assert (got[zz, yy, xx, 3] == 255).all()
+    on_edge = np.abs(margin) < 1e-5                        # the shadow comparison itself sits within fp32 noise
+    diff = np.abs(have - want)
+    assert (diff[~on_edge] <= 1).all(), int((diff[~on_edge] > 1).any(axis=1).sum())
+    assert (diff[~on_edge] == 1).mean() < 0.02 and on_edge.mean() < 0.01
+    assert have.max() > 20 and (shade == 0).any() and (shade == 1).any()       # lit and shadowed voxels both occur
