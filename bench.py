@@ -50,11 +50,19 @@ def parse():
     p.add_argument("--width", type=int, default=3840)
     p.add_argument("--height", type=int, default=2160)
     p.add_argument("--shadow", type=int, default=2048)
+    p.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"],
+                   help="c3 (default, the headline): Sponza 512^3 / 3840x2160; c2: Sponza 256^3 / 1920x1080 (BASELINE configs[1]); "
+                        "c4: 8 x tiled Sponza, 2.1 M triangles, 1024^3 / 3840x2160 (configs[3]).  The driver's bench line is c3.")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-overlap", action="store_true", help="F184_FLAG_NO_OVERLAP: every pass on one stream (A/B of the frame overlap)")
     p.add_argument("--schedule", default=None, choices=[None, "slab", "replicate"], help="multi-GPU schedule (default: slab)")
     p.add_argument("--cpu-budget-s", type=float, default=20.0, help="target CPU seconds of the cpu_baseline sample")
-    return p.parse_args()
+    a = p.parse_args()
+    if a.workload == "c2":
+        a.grid, a.width, a.height = 256, 1920, 1080
+    elif a.workload == "c4":
+        a.grid = 1024
+    return a
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -65,6 +73,9 @@ def make_workload(args, rank=0, world=1):
     from final184_b200.fixture import frame_inputs
     sc = S.get_scene(prefer_sponza=True, seed=1, n_boxes=48, tex_size=256, subdiv=8)
     cams = {n: S.fixture_constants(n) for n in ("main", "shadow", "voxel")}
+    if getattr(args, "workload", "c3") == "c4":          # 8 instances on a 2 x 2 x 2 lattice under the C4 voxel camera
+        sc = S.tile_scene(sc, S.C4_OFFSETS)
+        cams["voxel"] = S.fixture_constants("voxel_c4")
     if world > 1:
         # the G-buffer / shadow-map synthesiser is a CPU rasteriser: rank 0 renders (all cores) into the on-disk cache, the rest load it
         import torch.distributed as dist
@@ -72,7 +83,7 @@ def make_workload(args, rank=0, world=1):
             frame_inputs(sc, cams["main"], cams["shadow"], args.width, args.height, args.shadow, 0)
         dist.barrier()
     fi = frame_inputs(sc, cams["main"], cams["shadow"], args.width, args.height, args.shadow, 0)
-    name = ("Sponza" if sc.name == "sponza" else sc.name) + f" {args.grid}^3 voxel GI (voxelize+normalise+inject+6-dir mips+" \
+    name = ("8 x tiled Sponza" if getattr(args, "workload", "c3") == "c4" else ("Sponza" if sc.name == "sponza" else sc.name)) + f" {args.grid}^3 voxel GI (voxelize+normalise+inject+6-dir mips+" \
         f"6 diffuse/1 specular cones) at {args.width}x{args.height}, north-star mode"
     return sc, cams, fi, name
 
@@ -572,7 +583,7 @@ def run_b200(args, rank, world, local_rank):
                 est.append(e); wall.append(w)
             out["cpu_baseline"] = {"value": float(np.mean(est)), "unit": UNIT, "cores": cpu.cores, "kind": "port",
                                    "sample": cpu.describe() + f"; {len(est)} samples, {np.mean(wall) / 1e3:.1f} s each"}
-        if world == 1 and args.grid == 512:
+        if world == 1 and args.workload == "c3" and args.grid == 512:
             # configs[0] in the reference's own contract, beside the headline (GPU stage times always; the CPU leg with the cpu_baseline)
             out["c1_reference_mode"] = c1_reference_mode(sc, cams, local_rank, 0.0 if args.no_cpu_baseline else 10.0)
         emit(json.dumps(out))
