@@ -55,7 +55,7 @@ def light_lists(k):
     return A.light_list_c([((0.1, 1.0, 0.6), (0.0, 2.0, 0.0))]), A.light_list_c([(tuple(k.sun.luminance), tuple(k.sun.position))])
 
 
-def case_inputs(case="atrium"):
+def case_inputs(case="atrium", size=None):
     """A pinned case: the scene under the reference's fixture cameras (App/MainBehaviour.cpp:19-76)."""
     if case == "open":
         import cpu_helpers as Hc
@@ -64,6 +64,7 @@ def case_inputs(case="atrium"):
     else:
         sc = S.procedural_scene(seed=1) if case == "atrium" else S.load_sponza()
     cams = {n: S.fixture_constants(n) for n in ("main", "shadow", "voxel")}
+    W, H = size or (globals()["W"], globals()["H"])          # a power of two each (see the module docstring)
     fis = [frame_inputs(sc, cams["main"], cams["shadow"], W, H, SH, f, cache=False) for f in range(FRAMES)]
     # every Sponza material is (roughness, metallic) = (1, 1), which zeroes the diffuse term of the deferred
     # lighting: give the pinned case a material image that sweeps both, so that whole BRDF is exercised
@@ -90,6 +91,7 @@ def run_reference_shaders(oracle_lib, sc, cams, fis):
     """Mode R frames through the reference's shader text.  The voxel pass needs a rasteriser between VoxelGS and VoxelPS:
     that fixed-function stage is the oracle's (f184o_debug_set_voxel_stage_hooks); everything programmable is the reference's."""
     dll = load()
+    H, W = fis[0]["depth"].shape
     set_hooks = getattr(oracle_lib.dll, "f184o_debug_set_voxel_stage_hooks")
     set_hooks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     o = A.VoxelGI(grid_n=N, width=W, height=H, mode=A.MODE_REFERENCE, shadow_res=SH, lib=oracle_lib)
@@ -131,6 +133,7 @@ def run_reference_shaders(oracle_lib, sc, cams, fis):
 
 def run_library(lib, sc, cams, fis):
     """The same frames through a libf184-shaped library (the CUDA product or the CPU oracle), reference-faithful mode."""
+    H, W = fis[0]["depth"].shape
     c = A.VoxelGI(grid_n=N, width=W, height=H, mode=A.MODE_REFERENCE, shadow_res=SH, lib=lib)
     c.upload_scene(sc)
     c.voxelize(cams["voxel"])

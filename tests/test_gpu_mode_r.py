@@ -167,3 +167,16 @@ def test_deferred_lighting_bit_exact(cuda_lib, oracle_lib, proc_scene, cams):
     assert np.array_equal(Hh.bits16(ag), Hh.bits16(ao)), f"{np.count_nonzero(Hh.bits16(ag) != Hh.bits16(ao))} values differ"
     assert ao[..., :3].astype(np.float32).mean() > 1e-3 and np.isfinite(ao.astype(np.float32)).all()
     assert np.array_equal(Hh.bits16(zg), Hh.bits16(zo)) and not zo[..., :3].any() and (zo[..., 3] == 1).all()     # no lights: black, alpha 1
+
+
+def test_cuda_matches_live_reference_shader_text(cuda_lib, oracle_lib):
+    """Where oracle/_ref/libf184_refshaders.so travelled with the snapshot: the CUDA path against the reference's shader text run
+    live at 512 x 256 — a size no golden file holds — every mode R output bit for bit."""
+    import refshader as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libf184_refshaders.so not present on this box")
+    sc, cams_, fis = R.case_inputs("atrium", size=(512, 256))
+    ref = R.run_reference_shaders(oracle_lib, sc, cams_, fis)
+    got = R.run_library(cuda_lib, sc, cams_, fis)
+    assert int(got["fragments"]) == int(ref["fragments"])
+    assert R.compare(got, ref) == []

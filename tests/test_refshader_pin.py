@@ -69,3 +69,13 @@ def test_blur_pass_order_is_the_references(oracle_lib, case):
     by = np.ascontiguousarray(c.readback(A.SLOT_INDIRECT_FINAL)).view(np.float16).reshape(H, W, 4)
     assert np.array_equal(bx[..., :3], img[..., :3]) and not np.array_equal(by[..., :3], img[..., :3])
     c.close()
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libf184_refshaders.so not built (needs /root/reference: make -C oracle ref)")
+def test_restatement_matches_live_shader_text_at_another_size(oracle_lib):
+    """No golden file in between: the live shader text against the restatement at a size the fixtures do not hold (512 x 256,
+    16 x the pixels), so agreement is not an artefact of the committed cases."""
+    sc, cams, fis = R.case_inputs("atrium", size=(512, 256))
+    ref = R.run_reference_shaders(oracle_lib, sc, cams, fis)
+    got = R.run_library(oracle_lib, sc, cams, fis)
+    assert R.compare(got, ref) == []
