@@ -30,13 +30,14 @@ MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
 (STAGE_CLEAR, STAGE_VOXELIZE, STAGE_NORMALISE, STAGE_INJECT, STAGE_MIPS, STAGE_TRACE, STAGE_GTAO,
  STAGE_BLUR, STAGE_EXCHANGE, STAGE_LIGHTING, STAGE_COMPOSITE, STAGE_BARRIER, STAGE_COUNT) = range(13)
 STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur", "exchange", "lighting", "composite", "barrier"]
-(COUNTER_FRAGMENTS, COUNTER_MARCH_STEPS, COUNTER_OCCUPIED, COUNTER_KERNEL_LAUNCHES, COUNTER_BRICKS) = range(5)
+(COUNTER_FRAGMENTS, COUNTER_MARCH_STEPS, COUNTER_OCCUPIED, COUNTER_KERNEL_LAUNCHES, COUNTER_BRICKS, COUNTER_GATHER_BYTES) = range(6)
 (IPC_ACCUM_COLOR, IPC_ACCUM_NORMAL, IPC_BRICK_FLAGS, IPC_EXPORT, IPC_COUNTERS, IPC_BRICK_LIST, IPC_SYNC, IPC_COUNT) = range(8)
 FLAG_EXTERNAL_RANDS = 1
 FLAG_NO_TMA = 2
 FLAG_DENSE_MIPS = 4
 FLAG_GATHER_LINEAR = 8
 FLAG_NO_OVERLAP = 16
+FLAG_SPEC_APPENDIX_B = 32
 
 (FMT_UNDEFINED, FMT_R32_SFLOAT, FMT_R16G16B16A16_UNORM, FMT_R8G8B8A8_UNORM, FMT_R16G16B16A16_SFLOAT,
  FMT_R16G16_UINT, FMT_R32G32B32A32_SFLOAT, FMT_R8G8B8A8_SNORM, FMT_R32_UINT) = range(9)
@@ -191,6 +192,8 @@ _PRODUCT_ONLY = {
     "microbench": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_double)]),
     "debug_read_array": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "debug_detmath": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "debug_set_peer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "debug_get_ipc_ptr": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
 }
 EXPORTS = sorted(list(_SIGS) + list(_PRODUCT_ONLY))
 
@@ -238,7 +241,7 @@ class VoxelGI:
         rc = self.lib.create(C.byref(self.cfg), C.byref(self.h))
         if rc != 0:
             raise F184Error(f"{self.lib.prefix}create failed ({rc}): {self.lib.last_error(None).decode()}")
-        self._keep = []
+        self._keep = {}
 
     # -- helpers
     def _ck(self, rc, what):
@@ -285,7 +288,8 @@ class VoxelGI:
 
     def upload(self, slot, arr: np.ndarray):
         arr = np.ascontiguousarray(arr)
-        self._keep.append(arr)
+        # the copy is asynchronous: the array must outlive it.  Two generations per slot (uploads double-buffer) are enough.
+        self._keep[slot] = (self._keep.get(slot, ()) + (arr,))[-2:]
         self._ck(self.lib.upload_image(self.h, slot, arr.ctypes.data, arr.nbytes), "upload_image")
 
     def upload_ptr(self, slot, host_ptr, nbytes, rows=False):
@@ -348,6 +352,15 @@ class VoxelGI:
     def ipc_import(self, peer_rank, buffer, handle: bytes):
         h = (C.c_uint8 * 64).from_buffer_copy(handle)
         self._ck(self.lib.ipc_import(self.h, peer_rank, buffer, h), "ipc_import")
+
+    def ipc_ptr(self, buffer) -> int:
+        """device pointer of one of this context's shareable buffers (test hook: loopback ranks inside one process)"""
+        p = C.c_void_p()
+        self._ck(self.lib.debug_get_ipc_ptr(self.h, buffer, C.byref(p)), "debug_get_ipc_ptr")
+        return p.value
+
+    def set_peer(self, peer_rank, buffer, device_ptr):
+        self._ck(self.lib.debug_set_peer(self.h, peer_rank, buffer, device_ptr), "debug_set_peer")
 
     def peer_barrier(self):
         self._ck(self.lib.peer_barrier(self.h), "peer_barrier")

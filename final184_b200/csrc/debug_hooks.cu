@@ -42,3 +42,29 @@ extern "C" int f184_debug_detmath(f184_ctx* c, uint32_t op, const float* x, cons
     cudaFree(dx); cudaFree(dy); cudaFree(dout);
     return F184_OK;
 }
+
+// Test hook: install `device_ptr` as rank `peer_rank`'s shareable buffer `buffer` (f184_ipc_buffer) without CUDA IPC — for
+// contexts that live in ONE process (cudaIpcOpenMemHandle refuses handles of the same process).  Lets the test-suite drive the
+// multi-rank slab schedule with several contexts on a single GPU ("loopback ranks"), and a barrier with a peer that never arrives.
+extern "C" int f184_debug_set_peer(f184_ctx* c, uint32_t peer_rank, uint32_t buffer, void* device_ptr)
+{
+    if (!c || peer_rank >= 8 || peer_rank >= c->cfg.nranks || peer_rank == c->cfg.rank || buffer >= F184_IPC_COUNT || !device_ptr)
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_set_peer: bad argument");
+    c->peer[peer_rank].buf[buffer] = device_ptr;
+    c->peer[peer_rank].imported[buffer] = false;       // not ours to close
+    return F184_OK;
+}
+// own pointer of a shareable buffer (allocated on first use), the counterpart of f184_debug_set_peer
+extern "C" int f184_debug_get_ipc_ptr(f184_ctx* c, uint32_t buffer, void** out)
+{
+    if (!c || buffer >= F184_IPC_COUNT || !out) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_get_ipc_ptr: bad argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    int rc = f184_prepare_frame(c);        // loopback ranks share a device: no first-use allocation may happen while another rank waits in a barrier
+    if (rc) return rc;
+    rc = f184_ipc_buffer_ptr(c, buffer, out);
+    if (rc) return rc;
+    rc = f184_join_internal(c);
+    if (rc) return rc;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return F184_OK;
+}

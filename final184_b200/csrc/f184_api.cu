@@ -85,16 +85,18 @@ static bool default_desc(const f184_config& c, int slot, f184_image_desc* d)
 int f184_ensure_image(f184_ctx* c, int slot)
 {
     DevImage& im = c->img[slot];
-    if (im.upload_pending)
-    {   // a pass (or a read-back) is about to touch the slot: order it after the upload that is in flight on the copy stream
+    if (im.upload_pending & (1u << c->cur_sid))
+    {   // a pass (or a read-back) is about to touch the slot: order the stream it runs on after the upload that is in flight on
+        // the copy stream (each of the three streams joins the upload once)
         CK(c, cudaStreamWaitEvent(c->stream, im.ev_up[im.cur], 0));
-        im.upload_pending = false;
+        im.upload_pending &= ~(1u << c->cur_sid);
     }
     if (im.ptr) return F184_OK;
     f184_image_desc d;
     if (!default_desc(c->cfg, slot, &d)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "bad slot %d", slot);
     CK(c, cudaMalloc(&im.ptr, d.size_bytes));
     CK(c, cudaMemsetAsync(im.ptr, 0, d.size_bytes, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));     // first use only: the zero-fill has landed before ANY stream of the pipeline can touch the slot
     im.owned = true;
     im.buf[0] = im.ptr; im.cur = 0;
     im.desc = d;
@@ -129,27 +131,129 @@ int f184_stage_end(f184_ctx* c, int stage)
     return F184_OK;
 }
 
-// ---- frame overlap (f184_internal.h) --------------------------------------------------------------
-bool f184_overlap_enabled(const f184_ctx* c)
+// ---- frame pipeline (f184_internal.h; DESIGN.md "Frame pipeline") ------------------------------------
+bool f184_pipelined(const f184_ctx* c)
 {
-    return c->vox_stream && c->cfg.mode == F184_MODE_NORTHSTAR && c->cfg.nranks <= 1 && !(c->cfg.flags & F184_FLAG_NO_OVERLAP);
+    return c->vox_stream && c->build_stream && c->cfg.mode == F184_MODE_NORTHSTAR && !(c->cfg.flags & F184_FLAG_NO_OVERLAP);
 }
-bool f184_overlap_multi(const f184_ctx* c)
+int f184_enter(f184_ctx* c, int sid, F184Section* s)
 {
-    return c->vox_stream && c->cfg.mode == F184_MODE_NORTHSTAR && c->cfg.nranks > 1 && !(c->cfg.flags & F184_FLAG_NO_OVERLAP);
+    s->saved = c->stream; s->saved_sid = c->cur_sid; s->switched = false;
+    if (!f184_pipelined(c) || c->cur_sid != F184_SID_PASS) return F184_OK;
+    cudaStream_t target = sid == F184_SID_VOX ? c->vox_stream : c->build_stream;
+    if (c->pass_dirty & (1u << sid))
+    {   // the pass stream wrote something this stream reads (first use: allocation clears, scene/table uploads; later: uploads into the
+        // voxelizer's slots, an imported semaphore wait, caller-owned input images): wait for THAT point, not for the traces queued since
+        CK(c, cudaStreamWaitEvent(target, c->ev_pass_point, 0));
+        c->pass_dirty &= ~(1u << sid);
+    }
+    c->stream = target; c->cur_sid = sid; s->switched = true;
+    return F184_OK;
 }
-int f184_join_vox(f184_ctx* c)
+int f184_leave(f184_ctx* c, const F184Section& s, int rc)
 {
-    if (c->vox_pending)
+    if (!s.switched) return rc;
+    cudaError_t e = cudaSuccess;
+    if (c->cur_sid == F184_SID_VOX) { e = cudaEventRecord(c->ev_vox_done, c->stream); c->vox_pending = true; c->vox_to_build = true; }
+    else { e = cudaEventRecord(c->ev_build_tail, c->stream); c->build_pending = true; }
+    c->stream = s.saved; c->cur_sid = s.saved_sid;
+    if (rc) return rc;
+    CK(c, e);
+    return F184_OK;
+}
+int f184_build_wait_vox(f184_ctx* c)
+{
+    if (c->vox_to_build && c->cur_sid == F184_SID_BUILD)
     {
         CK(c, cudaStreamWaitEvent(c->stream, c->ev_vox_done, 0));
-        c->vox_pending = false;
+        c->vox_to_build = false;
     }
     return F184_OK;
 }
-int f184_mark_consumed(f184_ctx* c)
+int f184_join_internal(f184_ctx* c)
 {
-    if (c->vox_stream) CK(c, cudaEventRecord(c->ev_consumed, c->stream));
+    if (c->cur_sid != F184_SID_PASS) return F184_OK;
+    if (c->vox_pending) { CK(c, cudaStreamWaitEvent(c->stream, c->ev_vox_done, 0)); c->vox_pending = false; }
+    if (c->build_pending) { CK(c, cudaStreamWaitEvent(c->stream, c->ev_build_tail, 0)); c->build_pending = false; }
+    return F184_OK;
+}
+int f184_pass_wrote(f184_ctx* c)
+{
+    if (!c->ev_pass_point || c->cur_sid != F184_SID_PASS) return F184_OK;
+    CK(c, cudaEventRecord(c->ev_pass_point, c->stream));
+    c->pass_dirty = (1u << F184_SID_VOX) | (1u << F184_SID_BUILD);
+    return F184_OK;
+}
+int f184_volume_begin_write(f184_ctx* c)
+{
+    if (c->volume_open) return F184_OK;
+    VolumeSet& v = c->vs[c->build_set];
+    if (f184_pipelined(c) && v.traced_valid) CK(c, cudaStreamWaitEvent(c->stream, v.ev_traced, 0));
+    c->volume_open = true;
+    c->inject_in_volume = false;
+    return F184_OK;
+}
+int f184_volume_publish(f184_ctx* c)
+{
+    VolumeSet& v = c->vs[c->build_set];
+    if (f184_pipelined(c)) { CK(c, cudaEventRecord(v.ev_built, c->stream)); v.built_valid = true; }
+    c->trace_set = c->build_set;
+    c->build_set = (c->build_set + 1) % (c->n_sets ? c->n_sets : 1);
+    c->volume_open = false;
+    return F184_OK;
+}
+int f184_volume_acquire(f184_ctx* c, VolumeSet** out)
+{
+    VolumeSet& v = c->vs[c->trace_set];
+    if (f184_pipelined(c) && v.built_valid) CK(c, cudaStreamWaitEvent(c->stream, v.ev_built, 0));
+    *out = &v;
+    return F184_OK;
+}
+int f184_volume_release(f184_ctx* c, VolumeSet* v)
+{
+    if (f184_pipelined(c)) { CK(c, cudaEventRecord(v->ev_traced, c->stream)); v->traced_valid = true; }
+    return F184_OK;
+}
+int f184_check_device_errors(f184_ctx* c)
+{
+    if (!c->dev_state) return F184_OK;
+    uint32_t e = 0;
+    CK(c, cudaMemcpy(&e, c->dev_state + F184_DEV_ERROR, sizeof(e), cudaMemcpyDeviceToHost));
+    if (!e) return F184_OK;
+    CK(c, cudaMemset(c->dev_state + F184_DEV_ERROR, 0, sizeof(e)));       // reported once
+    if (e & F184_DEVERR_BARRIER_TIMEOUT)
+        return f184_fail(c, F184_ERR_PEER_TIMEOUT, "rank %u: a peer did not reach f184_peer_barrier within the timeout; the volumes of the frames since are undefined",
+                         c->cfg.rank);
+    return f184_fail(c, F184_ERR_NOT_READY, "rank %u: a cone sampled level 0 of the volume, which the last f184_gather_volume did not fetch from the peers "
+                                            "(the G-buffer changed between the gather and the trace)", c->cfg.rank);
+}
+
+// First frame: everything a frame allocates on first use (images, texture sets, lists, export records) is allocated HERE, on the
+// pass stream, before anything is enqueued — first-use allocations zero-fill and synchronise their stream, and a host-side wait in
+// the middle of a frame (behind a peer barrier that waits for another rank) has no place in an asynchronous schedule.
+int f184_prepare_frame(f184_ctx* c)
+{
+    if (c->prepared || c->cfg.mode != F184_MODE_NORTHSTAR) return F184_OK;
+    int rc;
+    for (int slot : {F184_SLOT_ACCUM_COLOR, F184_SLOT_ACCUM_NORMAL, F184_SLOT_VOX_ALBEDO, F184_SLOT_VOX_NORMAL, F184_SLOT_BRICK_FLAGS,
+                     F184_SLOT_RADIANCE, F184_SLOT_MIPS, F184_SLOT_SHADOW, F184_SLOT_DEPTH, F184_SLOT_NORMALS, F184_SLOT_MATERIAL,
+                     F184_SLOT_INDIRECT_OUT, F184_SLOT_INDIRECT_HISTORY})
+        if ((rc = f184_ensure_image(c, slot))) return rc;
+    if ((rc = f184_mode_n_alloc(c))) return rc;
+    void* dummy = nullptr;
+    if ((rc = f184_ipc_buffer_ptr(c, F184_IPC_BRICK_LIST, &dummy))) return rc;
+    if (c->cfg.nranks > 1)
+        for (uint32_t b : {(uint32_t)F184_IPC_EXPORT, (uint32_t)F184_IPC_SYNC})
+            if ((rc = f184_ipc_buffer_ptr(c, b, &dummy))) return rc;
+    if (!c->gamma_table) CK(c, cudaMalloc(&c->gamma_table, 256 * sizeof(float)));
+    if (!c->ev_barrier) CK(c, cudaEventCreateWithFlags(&c->ev_barrier, cudaEventDisableTiming));
+    if (c->n_tris)
+    {   // scene-sized scratch and the material / texture tables, when the scene is already there (it normally is)
+        if ((rc = f184_voxelizer_scratch_n(c))) return rc;
+        if ((rc = f184_sync_tables(c))) return rc;
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->prepared = true;
     return F184_OK;
 }
 
@@ -175,6 +279,10 @@ __global__ void k_tex_downsample(const uint8_t* __restrict__ src, uint8_t* __res
 int f184_sync_tables(f184_ctx* c)
 {
     if (!c->tables_dirty) return F184_OK;
+    // the voxelizer of a frame still in flight on vox_stream reads the tables: let it finish before they change (a material
+    // or texture change is rare; the blocking copies below then land before anything enqueued later)
+    if (c->vox_stream) CK(c, cudaStreamSynchronize(c->vox_stream));
+    CK(c, cudaStreamSynchronize(c->stream));
     if (c->tex_host.size() > c->tex_dev_cap)
     {
         if (c->tex_dev) cudaFree(c->tex_dev);
@@ -233,12 +341,17 @@ int f184_create(const f184_config* config, f184_ctx** out)
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&c->vox_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->build_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_vox_done, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_consumed, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&c->ev_normalised, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_build_tail, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_pass_point, cudaEventDisableTiming) != cudaSuccess)
     {
         delete c;
         return f184_fail(nullptr, F184_ERR_CUDA, "cudaStreamCreate failed");
     }
+    c->pass_dirty = (1u << F184_SID_VOX) | (1u << F184_SID_BUILD);       // first use of either: behind everything enqueued on the pass stream so far
+    cudaEventRecord(c->ev_pass_point, c->stream);
     for (int s = 0; s < F184_STAGE_COUNT; s++)
     {
         cudaEvent_t a, b;
@@ -252,6 +365,15 @@ int f184_create(const f184_config* config, f184_ctx** out)
         return f184_fail(nullptr, F184_ERR_OUT_OF_MEMORY, "cudaMalloc counters");
     }
     cudaMemset(c->counters_dev, 0, sizeof(unsigned long long) * (F184_COUNTER_COUNT + 4));
+    if (cudaMalloc(&c->dev_state, sizeof(uint32_t) * F184_DEV_WORDS) != cudaSuccess)
+    {
+        delete c;
+        return f184_fail(nullptr, F184_ERR_OUT_OF_MEMORY, "cudaMalloc device state");
+    }
+    {
+        const uint32_t init[F184_DEV_WORDS] = {0, 0, 1, 1, 0, 0, 0, 0};      // both texture sets start complete (all zero)
+        cudaMemcpy(c->dev_state, init, sizeof(init), cudaMemcpyHostToDevice);
+    }
     *out = c;
     return F184_OK;
 }
@@ -263,6 +385,7 @@ void f184_destroy(f184_ctx* c)
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->vox_stream) cudaStreamSynchronize(c->vox_stream);
+    if (c->build_stream) cudaStreamSynchronize(c->build_stream);
     if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
     f184_mode_n_release(c);
     for (auto& im : c->img)
@@ -273,7 +396,8 @@ void f184_destroy(f184_ctx* c)
             {
                 if (im.buf[i]) cudaFree(im.buf[i]);
                 if (im.ev_up[i]) cudaEventDestroy(im.ev_up[i]);
-                if (im.ev_release[i]) cudaEventDestroy(im.ev_release[i]);
+                for (int s = 0; s < F184_SID_COUNT; s++)
+                    if (im.ev_release[i][s]) cudaEventDestroy(im.ev_release[i][s]);
             }
             im.ptr = nullptr;
         }
@@ -281,7 +405,8 @@ void f184_destroy(f184_ctx* c)
     }
     for (void* p : {(void*)c->pos, (void*)c->nrm, (void*)c->uv, (void*)c->model_mats, (void*)c->idx, (void*)c->tri_mat,
                     (void*)c->tri_model, (void*)c->tex_dev, (void*)c->mat_dev, (void*)c->vox_keys, (void*)c->counters_dev,
-                    (void*)c->brick_prev, (void*)c->brick_list, (void*)c->vox_queue, (void*)c->vm_dev, (void*)c->gamma_table, c->gtao_phi_table})
+                    (void*)c->brick_prev, (void*)c->brick_list, (void*)c->vox_queue, (void*)c->vm_dev, (void*)c->gamma_table, c->gtao_phi_table,
+                    (void*)c->dev_state})
         if (p) cudaFree(p);
     for (uint8_t* p : c->tex_alloc) if (p) cudaFree(p);
     for (int s = 0; s < F184_STAGE_COUNT; s++)
@@ -296,6 +421,7 @@ void f184_destroy(f184_ctx* c)
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->vox_stream) cudaStreamDestroy(c->vox_stream);
+    if (c->build_stream) cudaStreamDestroy(c->build_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     for (int i = 0; i < 4; i++)
     {
@@ -309,8 +435,8 @@ void f184_destroy(f184_ctx* c)
         if (c->ev_rb_snap[i]) cudaEventDestroy(c->ev_rb_snap[i]);
         if (c->ev_rb_done[i]) cudaEventDestroy(c->ev_rb_done[i]);
     }
-    if (c->ev_vox_done) cudaEventDestroy(c->ev_vox_done);
-    if (c->ev_consumed) cudaEventDestroy(c->ev_consumed);
+    for (cudaEvent_t e : {c->ev_vox_done, c->ev_normalised, c->ev_build_tail, c->ev_pass_point})
+        if (e) cudaEventDestroy(e);
     if (c->ev_barrier) cudaEventDestroy(c->ev_barrier);
     if (c->lights_dev) cudaFree(c->lights_dev);
     if (c->r_queue) cudaFree(c->r_queue);
@@ -326,13 +452,20 @@ int f184_scene_upload(f184_ctx* c, const f184_scene_desc* s)
     if (!s->n_tris || !s->n_verts || !s->n_models) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "scene_upload: empty scene");
     for (uint64_t i = 0; i < 3ull * s->n_tris; i++)
         if (s->indices[i] >= s->n_verts) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "scene_upload: index %llu out of range", (unsigned long long)i);
+    uint32_t max_mat = 0;
     for (uint32_t i = 0; i < s->n_tris; i++)
+    {
         if (s->tri_model[i] >= s->n_models) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "scene_upload: tri_model out of range");
+        if (s->tri_material[i] > max_mat) max_mat = s->tri_material[i];
+    }
     CK(c, cudaSetDevice(c->cfg.device));
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaStreamSynchronize(c->vox_stream));     // the voxelizer in flight reads the buffers freed below
-    for (void* p : {(void*)c->pos, (void*)c->nrm, (void*)c->uv, (void*)c->model_mats, (void*)c->idx, (void*)c->tri_mat, (void*)c->tri_model})
-        if (p) cudaFree(p);
+    CK(c, cudaStreamSynchronize(c->build_stream));
+    // free and forget: if an upload below fails the context is left with NO scene (n_tris = 0), not with dangling pointers
+    for (void** p : {(void**)&c->pos, (void**)&c->nrm, (void**)&c->uv, (void**)&c->model_mats, (void**)&c->idx, (void**)&c->tri_mat, (void**)&c->tri_model})
+        if (*p) { cudaFree(*p); *p = nullptr; }
+    c->n_verts = c->n_tris = c->n_models = 0;
     auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, bytes);
         if (e != cudaSuccess) return e;
@@ -348,6 +481,7 @@ int f184_scene_upload(f184_ctx* c, const f184_scene_desc* s)
     c->model_mats_host.resize(s->n_models);
     memcpy(c->model_mats_host.data(), s->model_mats, 64ull * s->n_models);
     c->n_verts = s->n_verts; c->n_tris = s->n_tris; c->n_models = s->n_models;
+    c->max_material = max_mat;
     return F184_OK;
 }
 
@@ -371,18 +505,22 @@ int f184_texture_upload(f184_ctx* c, uint32_t id, const uint8_t* rgba, uint32_t 
     }
     uint8_t* dev = nullptr;
     CK(c, cudaMalloc(&dev, total));
-    CK(c, cudaMemcpyAsync(dev, rgba, 4ull * w * h, cudaMemcpyHostToDevice, c->stream));
-    uint32_t sw = w, sh = h;
-    for (uint32_t l = 1; l < nl; l++)
-    {
-        uint32_t dw = sw > 1 ? sw / 2 : 1, dh = sh > 1 ? sh / 2 : 1;
-        dim3 b(16, 16), g((dw + 15) / 16, (dh + 15) / 16);
-        k_tex_downsample<<<g, b, 0, c->stream>>>(dev + t.off[l - 1], dev + t.off[l], sw, dw, dh);
-        CK_LAUNCH(c);
-        sw = dw; sh = dh;
-    }
-    CK(c, cudaStreamSynchronize(c->stream));     // `rgba` may be freed by the caller on return
-    CK(c, cudaStreamSynchronize(c->vox_stream));
+    auto build_chain = [&]() -> int {
+        CK(c, cudaMemcpyAsync(dev, rgba, 4ull * w * h, cudaMemcpyHostToDevice, c->stream));
+        uint32_t sw = w, sh = h;
+        for (uint32_t l = 1; l < nl; l++)
+        {
+            uint32_t dw = sw > 1 ? sw / 2 : 1, dh = sh > 1 ? sh / 2 : 1;
+            dim3 b(16, 16), g((dw + 15) / 16, (dh + 15) / 16);
+            k_tex_downsample<<<g, b, 0, c->stream>>>(dev + t.off[l - 1], dev + t.off[l], sw, dw, dh);
+            CK_LAUNCH(c);
+            sw = dw; sh = dh;
+        }
+        CK(c, cudaStreamSynchronize(c->stream));     // `rgba` may be freed by the caller on return
+        CK(c, cudaStreamSynchronize(c->vox_stream)); // the voxelizer in flight may still sample the texture replaced below
+        return F184_OK;
+    };
+    if (int rc = build_chain()) { cudaFree(dev); return rc; }
     if (c->tex_alloc[id]) cudaFree(c->tex_alloc[id]);
     c->tex_alloc[id] = dev;
     t.base = dev;
@@ -433,8 +571,9 @@ int f184_bind_image(f184_ctx* c, uint32_t slot, const f184_image_desc* d)
     if (im.owned && im.ptr)
     {
         cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->vox_stream); cudaStreamSynchronize(c->build_stream);
         for (int i = 0; i < 2; i++) { if (im.buf[i]) cudaFree(im.buf[i]); im.buf[i] = nullptr; }
-        im.upload_pending = false;
+        im.upload_pending = 0;
     }
     im.ptr = d->device_ptr;
     im.owned = false;
@@ -480,6 +619,13 @@ static int copy_selected_rows(f184_ctx* c, const DevImage& im, void* dst, const 
     return F184_OK;
 }
 
+// slots the internal streams of the frame pipeline write (and the pass stream only reads back / uploads in tests)
+static bool volume_slot(uint32_t slot)
+{
+    return slot == F184_SLOT_ACCUM_COLOR || slot == F184_SLOT_ACCUM_NORMAL || slot == F184_SLOT_VOX_ALBEDO || slot == F184_SLOT_VOX_NORMAL ||
+           slot == F184_SLOT_BRICK_FLAGS || slot == F184_SLOT_RADIANCE || slot == F184_SLOT_MIPS;
+}
+
 static int upload_impl(f184_ctx* c, uint32_t slot, const void* host, size_t bytes, bool selected_rows);
 int f184_upload_image(f184_ctx* c, uint32_t slot, const void* host, size_t bytes) { return upload_impl(c, slot, host, bytes, false); }
 int f184_upload_image_rows(f184_ctx* c, uint32_t slot, const void* host, size_t bytes) { return upload_impl(c, slot, host, bytes, true); }
@@ -491,19 +637,20 @@ static int upload_impl(f184_ctx* c, uint32_t slot, const void* host, size_t byte
     if (rc) return rc;
     DevImage& im = c->img[slot];
     if (bytes != im.desc.size_bytes) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "upload_image: slot %u is %llu bytes, got %zu", slot, (unsigned long long)im.desc.size_bytes, bytes);
-    if (slot == F184_SLOT_ACCUM_COLOR || slot == F184_SLOT_ACCUM_NORMAL || slot == F184_SLOT_VOX_ALBEDO || slot == F184_SLOT_VOX_NORMAL ||
-        slot == F184_SLOT_BRICK_FLAGS)
-    {   // the voxelizer's own slots: written in stream order behind whatever is in flight on vox_stream
-        rc = f184_join_vox(c);
+    if (volume_slot(slot))
+    {   // the pipeline's own slots: written in stream order behind whatever is in flight on the internal streams, which then
+        // wait for this copy before their next kernel
+        rc = f184_join_internal(c);
         if (rc) return rc;
         CK(c, cudaMemcpyAsync(im.ptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
-        return f184_mark_consumed(c);
+        return f184_pass_wrote(c);
     }
     if (!im.owned || im.ext)
-    {   // caller-owned memory: plain stream-ordered copy
-        if (selected_rows) return copy_selected_rows(c, im, im.ptr, host, cudaMemcpyHostToDevice, c->stream);
-        CK(c, cudaMemcpyAsync(im.ptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
-        return F184_OK;
+    {   // caller-owned memory: plain stream-ordered copy on the pass stream; the internal streams order themselves behind it
+        if (selected_rows) rc = copy_selected_rows(c, im, im.ptr, host, cudaMemcpyHostToDevice, c->stream);
+        else { CK(c, cudaMemcpyAsync(im.ptr, host, bytes, cudaMemcpyHostToDevice, c->stream)); rc = F184_OK; }
+        if (rc) return rc;
+        return f184_pass_wrote(c);
     }
     const int nb = im.cur ^ 1;
     if (!im.buf[nb])
@@ -512,20 +659,32 @@ static int upload_impl(f184_ctx* c, uint32_t slot, const void* host, size_t byte
         for (int i = 0; i < 2; i++)
         {
             CK(c, cudaEventCreateWithFlags(&im.ev_up[i], cudaEventDisableTiming));
-            CK(c, cudaEventCreateWithFlags(&im.ev_release[i], cudaEventDisableTiming));
+            for (int s = 0; s < F184_SID_COUNT; s++) CK(c, cudaEventCreateWithFlags(&im.ev_release[i][s], cudaEventDisableTiming));
         }
     }
-    // everything enqueued so far on the pass stream may still read buf[cur]; nothing enqueued later will
-    CK(c, cudaEventRecord(im.ev_release[im.cur], c->stream));
-    im.release_valid[im.cur] = true;
-    if (im.release_valid[nb]) CK(c, cudaStreamWaitEvent(c->copy_stream, im.ev_release[nb], 0));
+    // everything enqueued so far — on the pass stream and, for the slots the build stream reads (the shadow map), on the
+    // build stream — may still read buf[cur]; nothing enqueued later will
+    {
+        const bool pipe = f184_pipelined(c);
+        cudaStream_t streams[F184_SID_COUNT] = {c->stream, pipe ? c->vox_stream : nullptr, pipe ? c->build_stream : nullptr};
+        const uint32_t readers = slot == F184_SLOT_SHADOW ? ((1u << F184_SID_PASS) | (1u << F184_SID_BUILD)) : (1u << F184_SID_PASS);
+        im.release_valid[im.cur] = 0;
+        for (int s = 0; s < F184_SID_COUNT; s++)
+            if ((readers & (1u << s)) && streams[s])
+            {
+                CK(c, cudaEventRecord(im.ev_release[im.cur][s], streams[s]));
+                im.release_valid[im.cur] |= 1u << s;
+            }
+        for (int s = 0; s < F184_SID_COUNT; s++)
+            if (im.release_valid[nb] & (1u << s)) CK(c, cudaStreamWaitEvent(c->copy_stream, im.ev_release[nb][s], 0));
+    }
     if (selected_rows) { rc = copy_selected_rows(c, im, im.buf[nb], host, cudaMemcpyHostToDevice, c->copy_stream); if (rc) return rc; }
     else CK(c, cudaMemcpyAsync(im.buf[nb], host, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CK(c, cudaEventRecord(im.ev_up[nb], c->copy_stream));
     im.cur = nb;
     im.ptr = im.buf[nb];
     im.desc.device_ptr = im.ptr;
-    im.upload_pending = true;
+    im.upload_pending = (1u << F184_SID_COUNT) - 1u;        // every stream joins the upload before its next use of the slot
     return F184_OK;
 }
 
@@ -539,13 +698,12 @@ static int readback_impl(f184_ctx* c, uint32_t slot, void* host, size_t bytes, b
     int rc = f184_ensure_image(c, slot);
     if (rc) return rc;
     if (bytes > c->img[slot].desc.size_bytes) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "readback: slot %u is %llu bytes, got %zu", slot, (unsigned long long)c->img[slot].desc.size_bytes, bytes);
-    const bool vox_slot = slot == F184_SLOT_ACCUM_COLOR || slot == F184_SLOT_ACCUM_NORMAL || slot == F184_SLOT_VOX_ALBEDO ||
-                          slot == F184_SLOT_VOX_NORMAL || slot == F184_SLOT_BRICK_FLAGS;
-    if (vox_slot) { rc = f184_join_vox(c); if (rc) return rc; }
+    const bool vox_slot = volume_slot(slot);
+    if (vox_slot) { rc = f184_join_internal(c); if (rc) return rc; }
     if (bytes > (256ull << 20) || vox_slot)
-    {   // volume-sized slots (tests): on the pass stream
+    {   // volume-sized slots (tests): on the pass stream; the internal streams wait for the copy before they overwrite the slot
         CK(c, cudaMemcpyAsync(host, c->img[slot].ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
-        if (vox_slot) return f184_mark_consumed(c);
+        if (vox_slot) return f184_pass_wrote(c);
         return F184_OK;
     }
     if (!c->d2h_stream)
@@ -622,8 +780,9 @@ int f184_import_external_memory_fd(f184_ctx* c, uint32_t slot, int fd, uint64_t 
     if (im.owned && im.ptr)
     {
         cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->vox_stream); cudaStreamSynchronize(c->build_stream);
         for (int i = 0; i < 2; i++) { if (im.buf[i]) cudaFree(im.buf[i]); im.buf[i] = nullptr; }
-        im.upload_pending = false;
+        im.upload_pending = 0;
     }
     im.ptr = ptr; im.owned = false; im.ext = ext; im.desc = want; im.desc.device_ptr = ptr;
     return F184_OK;
@@ -650,13 +809,14 @@ int f184_frame_begin(f184_ctx* c)
     {
         cudaExternalSemaphoreWaitParams p{};
         CK(c, cudaWaitExternalSemaphoresAsync(&c->sem_wait, &p, 1, c->stream));
+        return f184_pass_wrote(c);        // the internal streams of the frame pipeline start behind the wait too
     }
     return F184_OK;
 }
 int f184_frame_end(f184_ctx* c)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
-    int rc = f184_join_vox(c);
+    int rc = f184_join_internal(c);
     if (rc) return rc;
     if (c->sem_signal)
     {
@@ -671,68 +831,76 @@ int f184_set_stream(f184_ctx* c, void* s)
     if (!c) return F184_ERR_INVALID_ARGUMENT;
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->vox_stream);
+    cudaStreamSynchronize(c->build_stream);
     if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
-    c->vox_pending = false;
+    c->vox_pending = c->build_pending = false;
     c->stream = s ? (cudaStream_t)s : c->own_stream;
     return F184_OK;
 }
 int f184_sync(f184_ctx* c)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
-    int rc = f184_join_vox(c);
+    int rc = f184_join_internal(c);
     if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));
     if (c->d2h_stream) CK(c, cudaStreamSynchronize(c->d2h_stream));
-    return F184_OK;
+    return c->cfg.nranks > 1 ? f184_check_device_errors(c) : F184_OK;
 }
 
 // ---- passes (dispatch on mode) ------------------------------------------------------------------
+// every material a triangle names has a table entry, and every texture a material names has been uploaded: the kernels index
+// mats[tri_material] and texs[mat.tex] unguarded
+static int check_tables(f184_ctx* c)
+{
+    if (c->max_material >= c->mat_host.size())
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "voxelize: triangle material %u has no f184_material_set entry (%zu materials)", c->max_material, c->mat_host.size());
+    for (size_t m = 0; m < c->mat_host.size(); m++)
+    {
+        const MatDev& md = c->mat_host[m];
+        if (md.use_textures && md.tex >= 0 && ((size_t)md.tex >= c->tex_host.size() || !c->tex_host[md.tex].base))
+            return f184_fail(c, F184_ERR_NOT_READY, "voxelize: material %zu uses texture %d, which has not been uploaded (f184_texture_upload)", m, md.tex);
+    }
+    return F184_OK;
+}
+
 int f184_voxelize(f184_ctx* c, const f184_view_constants* cam)
 {
     if (!c || !cam) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "voxelize: null argument");
     if (!c->n_tris) return f184_fail(c, F184_ERR_NOT_READY, "voxelize: no scene uploaded");
     CK(c, cudaSetDevice(c->cfg.device));
-    int rc = f184_sync_tables(c);
+    int rc = check_tables(c);
     if (rc) return rc;
-    return c->cfg.mode == F184_MODE_REFERENCE ? f184_voxelize_r(c, cam) : f184_voxelize_n(c, cam);
+    rc = f184_sync_tables(c);
+    if (rc) return rc;
+    if (c->cfg.mode == F184_MODE_REFERENCE) return f184_voxelize_r(c, cam);
+    rc = f184_voxelize_accumulate(c, cam);
+    if (rc) return rc;
+    return f184_normalise(c);
 }
+// Accumulation of one frame.  Pipelined: on vox_stream, beside the build and the trace of the frames before it.  It may start once
+// this rank has re-zeroed its accumulators (ev_normalised) and, on one NVLink box, once EVERY rank has (the peers add into this
+// rank's accumulators and this rank into theirs): that is what the last f184_peer_barrier of the previous frame — the one between
+// mips and gather, reached by each rank behind its normalise — certifies (ev_barrier).
 int f184_voxelize_accumulate(f184_ctx* c, const f184_view_constants* cam)
 {
     if (!c || !cam) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "voxelize_accumulate: null argument");
     if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "voxelize_accumulate is a north-star stage");
     if (!c->n_tris) return f184_fail(c, F184_ERR_NOT_READY, "voxelize_accumulate: no scene uploaded");
     CK(c, cudaSetDevice(c->cfg.device));
-    int rc = f184_sync_tables(c);
+    int rc = check_tables(c);
     if (rc) return rc;
-    if (!f184_overlap_multi(c))
+    rc = f184_sync_tables(c);
+    if (rc) return rc;
+    if ((rc = f184_prepare_frame(c))) return rc;
+    F184Section sec;
+    rc = f184_enter(c, F184_SID_VOX, &sec);
+    if (rc) return rc;
+    if (sec.switched)
     {
-        rc = f184_join_vox(c);
-        if (rc) return rc;
-        return f184_voxelize_accumulate_n(c, cam);
+        if (c->normalised_valid) CK(c, cudaStreamWaitEvent(c->stream, c->ev_normalised, 0));
+        if (c->barrier_recorded) CK(c, cudaStreamWaitEvent(c->stream, c->ev_barrier, 0));
     }
-    // One NVLink box, frame overlap: the accumulation of frame f+1 goes to vox_stream and runs beside the gather and the cone
-    // trace of frame f.  Its peer atomics are NVLink-bound, the trace is texture-bound: they share the SMs without competing
-    // for the same unit.  It may start once EVERY rank has normalised frame f (normalise re-zeroes the accumulators and
-    // consumes the brick flags this pass writes on the peers): that is what the last peer barrier on the pass stream — the
-    // one between mips and gather — certifies, so vox_stream waits for the event recorded behind it (ev_barrier) and for
-    // nothing later.  f184_peer_barrier joins vox_stream first, so the barrier that publishes frame f+1's fragments cannot
-    // pass before this rank's own fragments have left.
-    cudaStream_t pass = c->stream;
-    if (!c->vox_started)
-    {   // first use: behind everything enqueued so far (allocation clears, scene and table uploads)
-        CK(c, cudaEventRecord(c->ev_consumed, pass));
-        c->vox_started = true;
-    }
-    CK(c, cudaStreamWaitEvent(c->vox_stream, c->ev_consumed, 0));
-    if (c->barrier_recorded) CK(c, cudaStreamWaitEvent(c->vox_stream, c->ev_barrier, 0));
-    c->stream = c->vox_stream;
-    rc = f184_voxelize_accumulate_n(c, cam);
-    cudaError_t e = rc == F184_OK ? cudaEventRecord(c->ev_vox_done, c->vox_stream) : cudaSuccess;
-    c->stream = pass;
-    if (rc) return rc;
-    CK(c, e);
-    c->vox_pending = true;
-    return F184_OK;
+    return f184_leave(c, sec, f184_voxelize_accumulate_n(c, cam));
 }
 int f184_normalise(f184_ctx* c)
 {
@@ -740,18 +908,28 @@ int f184_normalise(f184_ctx* c)
     if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "normalise is a north-star stage");
     if (!c->brick_prev) return f184_fail(c, F184_ERR_NOT_READY, "normalise: call f184_voxelize_accumulate first");
     CK(c, cudaSetDevice(c->cfg.device));
-    int rc = f184_join_vox(c);
+    F184Section sec;
+    int rc = f184_enter(c, F184_SID_BUILD, &sec);
     if (rc) return rc;
-    return f184_normalise_n(c);
+    rc = f184_build_wait_vox(c);
+    if (rc == F184_OK) rc = f184_normalise_n(c);
+    if (rc == F184_OK && sec.switched)
+    {
+        cudaError_t e = cudaEventRecord(c->ev_normalised, c->stream);
+        if (e != cudaSuccess) rc = f184_fail(c, F184_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
+        c->normalised_valid = true;
+    }
+    return f184_leave(c, sec, rc);
 }
 int f184_gather_volume(f184_ctx* c)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
     if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "gather_volume is a north-star stage");
     CK(c, cudaSetDevice(c->cfg.device));
-    int rc = f184_join_vox(c);
+    F184Section sec;
+    int rc = f184_enter(c, F184_SID_BUILD, &sec);
     if (rc) return rc;
-    return f184_gather_n(c);
+    return f184_leave(c, sec, f184_gather_n(c));
 }
 
 // ---- CUDA IPC: share a context buffer with the other ranks of the box ----------------------------------------
@@ -763,7 +941,7 @@ int f184_ipc_export(f184_ctx* c, uint32_t buffer, f184_ipc_handle* out)
     void* p = nullptr;
     int rc = f184_ipc_buffer_ptr(c, buffer, &p);
     if (rc) return rc;
-    rc = f184_join_vox(c);
+    rc = f184_join_internal(c);
     if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));      // the allocation's zero-fill has landed before a peer can see it
     cudaIpcMemHandle_t h;
@@ -791,22 +969,27 @@ int f184_inject(f184_ctx* c, const f184_sun* sun, const f184_extended_matrices* 
     if (!c || !sun || !m) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "inject: null argument");
     if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "inject is a north-star stage");
     CK(c, cudaSetDevice(c->cfg.device));
-    int rc = f184_join_vox(c);
+    int rc = F184_OK;
+    // a caller-owned shadow map is written by the caller's own work on the pass stream: the build stream starts behind it
+    if (c->img[F184_SLOT_SHADOW].ptr && (!c->img[F184_SLOT_SHADOW].owned || c->img[F184_SLOT_SHADOW].ext) && (rc = f184_pass_wrote(c))) return rc;
+    F184Section sec;
+    rc = f184_enter(c, F184_SID_BUILD, &sec);
     if (rc) return rc;
-    rc = f184_inject_n(c, sun, m);
-    if (rc) return rc;
-    return f184_mark_consumed(c);
+    rc = f184_build_wait_vox(c);
+    if (rc == F184_OK) rc = f184_inject_n(c, sun, m);
+    return f184_leave(c, sec, rc);
 }
 int f184_build_mips(f184_ctx* c)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
     if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "mips are a north-star stage");
     CK(c, cudaSetDevice(c->cfg.device));
-    int rc = f184_join_vox(c);
+    F184Section sec;
+    int rc = f184_enter(c, F184_SID_BUILD, &sec);
     if (rc) return rc;
-    rc = f184_mips_n(c);
-    if (rc) return rc;
-    return f184_mark_consumed(c);
+    rc = f184_build_wait_vox(c);
+    if (rc == F184_OK) rc = f184_mips_n(c);
+    return f184_leave(c, sec, rc);
 }
 int f184_trace_indirect(f184_ctx* c, const f184_trace_constants* k)
 {
@@ -894,7 +1077,7 @@ int f184_stage_time_ms(f184_ctx* c, uint32_t stage, float* ms)
 {
     if (!c || stage >= F184_STAGE_COUNT || !ms) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "stage_time_ms: bad argument");
     if (!c->ev_valid[stage]) { *ms = 0.f; return F184_OK; }
-    int rc = f184_join_vox(c);
+    int rc = f184_join_internal(c);
     if (rc) return rc;
     CK(c, cudaEventSynchronize(c->ev[stage][1]));
     CK(c, cudaEventElapsedTime(ms, c->ev[stage][0], c->ev[stage][1]));
@@ -903,7 +1086,7 @@ int f184_stage_time_ms(f184_ctx* c, uint32_t stage, float* ms)
 int f184_stage_time_reset(f184_ctx* c, uint32_t accumulate)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
-    int rc = f184_join_vox(c);
+    int rc = f184_join_internal(c);
     if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));
     c->ev_accumulate = accumulate != 0;
@@ -921,7 +1104,7 @@ int f184_stage_time_total(f184_ctx* c, uint32_t stage, float* ms_sum, uint32_t* 
     if (!c || stage >= F184_STAGE_COUNT || !ms_sum || !runs) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "stage_time_total: bad argument");
     *ms_sum = 0.f; *runs = 0;
     if (!c->ev_accumulate) return f184_fail(c, F184_ERR_NOT_READY, "stage_time_total: call f184_stage_time_reset(ctx, 1) first");
-    int rc = f184_join_vox(c);
+    int rc = f184_join_internal(c);
     if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));
     for (uint32_t r = 0; r < c->ev_runs[stage]; r++)
@@ -938,12 +1121,12 @@ int f184_counter_get(f184_ctx* c, uint32_t which, uint64_t* v)
     if (!c || which >= F184_COUNTER_COUNT || !v) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "counter_get: bad argument");
     if (which == F184_COUNTER_KERNEL_LAUNCHES) { *v = c->launches; return F184_OK; }
     unsigned long long t = 0;
-    int rc = f184_join_vox(c);
+    int rc = f184_join_internal(c);
     if (rc) return rc;
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaMemcpy(&t, c->counters_dev + which, sizeof(t), cudaMemcpyDeviceToHost));
     *v = t;
-    return F184_OK;
+    return c->cfg.nranks > 1 ? f184_check_device_errors(c) : F184_OK;
 }
 
 }  // extern "C"

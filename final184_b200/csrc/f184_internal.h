@@ -38,10 +38,31 @@ struct DevImage
     // the upload of frame f+1 overlaps the kernels of frame f (which keep reading the other buffer)
     void* buf[2] = {nullptr, nullptr};
     int cur = 0;
-    bool upload_pending = false;              // ev_up[cur] has not been joined into the pass stream yet
-    bool release_valid[2] = {false, false};
+    uint32_t upload_pending = 0;              // bit s: stream s (F184_SID_*) has not joined ev_up[cur] yet
+    uint32_t release_valid[2] = {0, 0};       // bit s: ev_release[i][s] has been recorded
     cudaEvent_t ev_up[2] = {nullptr, nullptr};       // copy stream: upload into buf[i] finished
-    cudaEvent_t ev_release[2] = {nullptr, nullptr};  // pass stream: everything that could read buf[i] has been enqueued before this
+    cudaEvent_t ev_release[2][3] = {};        // stream s: everything that could read buf[i] has been enqueued before this
+};
+
+// The three streams a north-star context enqueues on (DESIGN.md "Frame pipeline"); mode R and F184_FLAG_NO_OVERLAP use the pass stream only.
+enum { F184_SID_PASS = 0, F184_SID_VOX = 1, F184_SID_BUILD = 2, F184_SID_COUNT = 3 };
+
+// Texture-side storage of one volume (what the cone tracer samples).  Two sets alternate so that frame f+1 is built
+// (inject, mips, gather on the build stream) while frame f is still being traced on the pass stream.
+struct VolumeSet
+{
+    cudaArray_t rad_array = nullptr;          // level-0 radiance as a 3D array for hardware filtering
+    // levels >= 1: ONE mipmapped 3D array holds all six directions (the "atlas"): level l has extent (n, n, 12 n) and
+    // direction d lives in z = [2 d n, 2 d n + n); the n slices behind each slab stay zero, so a trilinear footprint that
+    // leaves a slab reads the same zeros border addressing would give.  One texture handle for every fetch of the cone
+    // tracer keeps the handle warp-uniform (six per-direction handles made ptxas wrap every TEX in a waterfall loop).
+    cudaMipmappedArray_t dir_atlas = nullptr;
+    cudaTextureObject_t rad_tex = 0, dir_tex = 0, dir_tex_lin = 0;   // dir_tex: nearest mip level; dir_tex_lin: linear between levels (Appendix-B spec)
+    cudaSurfaceObject_t rad_surf = 0;
+    cudaSurfaceObject_t dir_surf[12] = {};    // one per atlas level
+    cudaEvent_t ev_built = nullptr;           // build stream: the set is complete (last writer of the frame)
+    cudaEvent_t ev_traced = nullptr;          // pass stream: the last trace that reads the set has been enqueued before this
+    bool built_valid = false, traced_valid = false;
 };
 
 struct MipLevelInfo
@@ -60,10 +81,25 @@ struct f184_ctx
     //   vox_stream waits ev_consumed = the last pass-stream work that reads what voxelize/normalise overwrite
     //                                  (inject, mips, read-backs of the volume slots)
     //   pass stream waits ev_vox_done before the first call that reads their outputs (f184_join_vox)
-    cudaStream_t vox_stream = nullptr;
-    cudaEvent_t ev_vox_done = nullptr, ev_consumed = nullptr;
-    bool vox_pending = false, vox_started = false;
-    cudaEvent_t ev_barrier = nullptr;         // recorded behind every f184_peer_barrier (multi-GPU frame overlap, f184_voxelize_accumulate)
+    // Frame pipeline (north-star mode; DESIGN.md "Frame pipeline").  Three streams, one frame each in the steady state:
+    //   vox_stream    f184_voxelize_accumulate of frame f+2          (atomics / integer ALU; NVLink peer atomics on one box)
+    //   build_stream  [barrier] normalise, inject, mips, [barrier, gather], tail of frame f+1   (HBM; NVLink peer loads)
+    //   pass stream   cone trace of frame f                          (texture pipe)
+    // ordered by events only where data flows:
+    //   ev_vox_done     vox -> build    the frame's fragments are in the accumulators (this rank's share)
+    //   ev_normalised   build -> vox    this rank has re-zeroed its accumulators (normalise = next frame's clear)
+    //   ev_barrier      build -> vox    one box: EVERY rank has normalised (recorded behind each f184_peer_barrier)
+    //   VolumeSet::ev_built / ev_traced   build <-> pass, per texture set
+    //   ev_pass_point   pass -> vox/build   something the internal streams read was written on the pass stream (pass_dirty)
+    cudaStream_t vox_stream = nullptr, build_stream = nullptr;
+    cudaEvent_t ev_vox_done = nullptr, ev_normalised = nullptr, ev_build_tail = nullptr, ev_pass_point = nullptr;
+    bool vox_pending = false;                 // vox_stream has work the pass stream has not joined
+    bool build_pending = false;               // build_stream has work the pass stream has not joined (ev_build_tail)
+    bool vox_to_build = false;                // ev_vox_done not yet joined by the build stream
+    bool normalised_valid = false;
+    uint32_t pass_dirty = 0;                  // bit s: stream s must wait for ev_pass_point before its next kernel
+    int cur_sid = F184_SID_PASS;              // which of the three `stream` currently aliases
+    cudaEvent_t ev_barrier = nullptr;         // recorded behind every f184_peer_barrier (accumulate of the next frame waits for it)
     bool barrier_recorded = false;
     // probe batches (f184_trace_views): independent views round-robin over a few streams, joined back into the pass stream
     cudaStream_t view_streams[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -81,6 +117,7 @@ struct f184_ctx
     uint32_t* idx = nullptr;
     uint16_t *tri_mat = nullptr, *tri_model = nullptr;
     uint32_t n_verts = 0, n_tris = 0, n_models = 0;
+    uint32_t max_material = 0;               // largest tri_material of the uploaded scene (checked against the tables at voxelize)
     std::vector<M4> model_mats_host;
     // textures / materials
     std::vector<TexDev> tex_host;
@@ -98,14 +135,14 @@ struct f184_ctx
     uint32_t r_queue_cap = 0;
     // mode N
     std::vector<MipLevelInfo> mip_levels;     // index 0 = level 1
-    cudaArray_t rad_array = nullptr;          // level-0 radiance as a 3D array for hardware filtering
-    // levels >= 1: ONE mipmapped 3D array holds all six directions (the "atlas"): level l has extent (n, n, 12 n) and
-    // direction d lives in z = [2 d n, 2 d n + n); the n slices behind each slab stay zero, so a trilinear footprint that
-    // leaves a slab reads the same zeros border addressing would give.  One texture handle for every fetch of the cone
-    // tracer keeps the handle warp-uniform (six per-direction handles made ptxas wrap every TEX in a waterfall loop).
-    cudaMipmappedArray_t dir_atlas = nullptr;
-    cudaTextureObject_t rad_tex = 0, dir_tex = 0;
-    uint32_t* brick_prev = nullptr;           // bricks written last frame (to clear what became empty)
+    VolumeSet vs[2];
+    int n_sets = 0;                           // 0 = not allocated; 1 under F184_FLAG_NO_OVERLAP / mode R, else 2
+    int build_set = 0, trace_set = 0;         // the set the next inject/mips/gather writes; the set the next trace samples
+    bool volume_open = false;                 // a writer of the build set has been enqueued since the last publish
+    // per brick: bit 0 = touched by the previous voxelize (the linear volumes hold it), bit 1 + s = texture set s holds it.
+    // A brick is listed (normalise, inject, mips, gather) when it is touched now or any of those bits says a stale copy
+    // must be overwritten — this is what clears bricks that became empty, in the linear volumes and in BOTH texture sets.
+    uint32_t* brick_prev = nullptr;
     uint32_t* brick_list = nullptr;           // bricks processed this frame (touched now or last frame)
     uint32_t* vox_queue = nullptr;            // voxelizer pass-2 queue: uint2 (triangle, first task) per large triangle
     uint32_t vox_queue_cap = 0;
@@ -113,10 +150,9 @@ struct f184_ctx
     uint32_t vm_cap = 0;
     void* gtao_phi_table = nullptr;           // (cos, sin) of the 64 GTAO slice angles (gtao.cu)
     void* lights_dev = nullptr;               // 2 x 100 lights (lighting.cu)
+    bool gamma_ready = false;
     float* gamma_table = nullptr;             // pow(a/255, 2.2), a = 0..255 (mode_n_inject.cu)
     bool defer_normalise = false;             // multi-GPU: f184_voxelize stops after accumulation
-    cudaSurfaceObject_t rad_surf = 0;
-    cudaSurfaceObject_t dir_surf[12] = {};        // one per atlas level
     uint32_t n_mip_levels = 0;                // levels >= 1
     void* tma_maps = nullptr;                 // host array of CUtensorMap (mode_n_mips.cu)
     // one NVLink box: peer-mapped buffers (index = rank; own entry points at own memory)
@@ -128,6 +164,11 @@ struct f184_ctx
     uint32_t* export_buf = nullptr;           // 1024 words per listed brick of the own slab
     uint32_t* sync_flags = nullptr;           // [8] barrier epochs written by the peers + [8] scratch
     uint32_t barrier_epoch = 0;
+    // device-side state words (F184_DEV_*): sticky error bits and the level-0 bookkeeping of the peer gather
+    uint32_t* dev_state = nullptr;
+    bool prepared = false;                    // the first f184_voxelize_accumulate has allocated everything a frame touches
+    float voxel_h = 0.0f;                     // voxel size under the voxel camera of the last f184_voxelize (level-0 test of the gather)
+    bool inject_in_volume = false;            // f184_inject has written the open build set (its level 0 is current)
     // sharding
     uint32_t tri_first = 0, tri_count = 0xffffffffu;
     uint32_t row0 = 0, row1 = 0xffffffffu;
@@ -147,6 +188,13 @@ struct f184_ctx
     cudaExternalSemaphore_t sem_wait = nullptr, sem_signal = nullptr;
 };
 
+// dev_state words
+enum { F184_DEV_ERROR = 0,       // sticky error bits (F184_DEVERR_*), reported by the next synchronous call
+       F184_DEV_NEED_L0 = 1,     // this frame: some cone of this rank's rows samples level 0 (k_need_level0)
+       F184_DEV_L0_FULL = 2,     // [2 + s]: level 0 of texture set s holds every rank's bricks (no gather skipped it since the last clear)
+       F184_DEV_WORDS = 8 };
+enum { F184_DEVERR_BARRIER_TIMEOUT = 1u, F184_DEVERR_LEVEL0_MISSING = 2u };
+
 // Error plumbing ----------------------------------------------------------------------------------
 int f184_fail(f184_ctx* c, int code, const char* fmt, ...);
 #define CK(c, call)                                                                                         \
@@ -165,11 +213,23 @@ int f184_fail(f184_ctx* c, int code, const char* fmt, ...);
     } while (0)
 
 int f184_ensure_image(f184_ctx* c, int slot);
-bool f184_overlap_enabled(const f184_ctx* c);
-bool f184_overlap_multi(const f184_ctx* c);
-int f184_join_vox(f184_ctx* c);           // pass stream waits for the voxelize/normalise in flight on vox_stream
-int f184_mark_consumed(f184_ctx* c);      // pass stream: everything that reads the voxelizer's outputs has been enqueued
+// ---- frame pipeline plumbing (f184_api.cu) ----
+bool f184_pipelined(const f184_ctx* c);   // north-star mode without F184_FLAG_NO_OVERLAP: the three-stream pipeline is on
+// Run the rest of an entry point on internal stream `sid`: c->stream aliases it until f184_leave.  No-op when the pipeline is off
+// or the caller is already inside an internal section.  Applies the pending pass->internal dependency (pass_dirty).
+struct F184Section { cudaStream_t saved; int saved_sid; bool switched; };
+int f184_enter(f184_ctx* c, int sid, F184Section* s);
+int f184_leave(f184_ctx* c, const F184Section& s, int rc);   // records the stream's tail event, restores c->stream; returns rc
+int f184_build_wait_vox(f184_ctx* c);     // build stream: wait for the accumulation in flight on vox_stream
+int f184_join_internal(f184_ctx* c);      // pass stream waits for everything in flight on vox_stream / build_stream
+int f184_pass_wrote(f184_ctx* c);         // pass stream wrote something the internal streams read: they wait for this point
+int f184_volume_begin_write(f184_ctx* c); // before the first writer of the build set: wait for the trace that still samples it
+int f184_volume_publish(f184_ctx* c);     // behind the last writer: the build set becomes the trace set, the other one the build set
+int f184_volume_acquire(f184_ctx* c, VolumeSet** out);   // pass stream: the newest complete set, ordered behind its build
+int f184_volume_release(f184_ctx* c, VolumeSet* v);      // pass stream: a reader of the set has been enqueued
+int f184_check_device_errors(f184_ctx* c);               // sticky device error word -> F184_ERR_* (synchronous callers only)
 int f184_sync_tables(f184_ctx* c);
+int f184_prepare_frame(f184_ctx* c);                     // first-use allocations of a north-star frame, before anything is enqueued
 int f184_stage_begin(f184_ctx* c, int stage);
 int f184_stage_end(f184_ctx* c, int stage);
 template <class T> static inline T* img_ptr(f184_ctx* c, int slot) { return reinterpret_cast<T*>(c->img[slot].ptr); }
@@ -210,10 +270,22 @@ int f184_trace_views_n(f184_ctx* c, const f184_trace_constants* ks, uint32_t vie
 int f184_mode_n_release(f184_ctx* c);
 int f184_mode_n_alloc(f184_ctx* c);
 int f184_normalise_n(f184_ctx* c);
+int f184_voxelizer_scratch_n(f184_ctx* c);
 int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam);
 int f184_gather_n(f184_ctx* c);
 int f184_ipc_buffer_ptr(f184_ctx* c, uint32_t buffer, void** out);
 M4 f184_invert_m4(const M4& A);
+// world size of one voxel along voxel-x under the voxel camera (Proj * View), the `h` of the cone tracer
+static inline float f184_voxel_h(const float* proj, const float* view, uint32_t N)
+{
+    M4 vp, vv;
+    memcpy(vp.m, proj, 64);
+    memcpy(vv.m, view, 64);
+    const M4 v2w = f184_invert_m4(host_matmul(vp, vv));
+    const float s = 2.0f / (float)N;
+    const float ax = v2w.m[0] * s, ay = v2w.m[1] * s, az = v2w.m[2] * s;
+    return sqrtf((ax * ax + ay * ay) + az * az);
+}
 float f184_exposure(const f184_ctx* c, const f184_sun* sun);
 // rows/tiles selection of the trace passes: y = y0 + (tile0 + blockIdx.y * stride) * 8 + ...; returns grid.y (0 = nothing to do)
 static inline uint32_t f184_trace_tiles(const f184_ctx* c, uint32_t H, uint32_t* y0, uint32_t* y1, uint32_t* tile0, uint32_t* stride)

@@ -1,8 +1,8 @@
 // microbench.cu — the two device peaks this path is bounded by that MEASURED_PEAKS.json does not hold
 // ("L2-atomic and texture-fetch peaks ... must be established by our own microbenchmarks"):
 //   f184_microbench(ctx, 0, &rate)   trilinear RGBA8 3D texture fetches per second (the cone tracer's bound)
-//   f184_microbench(ctx, 1, &rate)   16-byte vector reductions (red.global.add.v4.f32) per second on scattered addresses
-//                                    of a buffer larger than L2 (the voxelizer's accumulation path)
+//   f184_microbench(ctx, 1, &rate)   16-byte vector reductions (red.global.add.v4.f32) per second with the voxelizer's locality:
+//                                    a warp's lanes inside one 8 KB brick, bricks scattered over a buffer larger than L2
 // Each runs its kernel a few times and reports the best CUDA-event time.  Measurement aids only: bench.py calls them to
 // put a denominator under the trace / voxelize numbers.
 #include "f184_device.cuh"
@@ -31,13 +31,20 @@ __global__ void __launch_bounds__(256) k_tex_rate(cudaTextureObject_t tex, int i
     if (r.x == -1.0f) sink[tid] = r;          // never true: keeps the fetches alive
 }
 
-__global__ void __launch_bounds__(256) k_red_rate(float4* __restrict__ buf, uint32_t mask, int iters)
+// The voxelizer's accumulation pattern: the 32 fragments a warp emits together land in ONE 8^3 brick (8 KB of contiguous
+// float4), at scattered places inside it, and consecutive bricks of a warp are far apart (a triangle's columns walk through the
+// volume).  So: per iteration a warp picks a brick out of 1 GiB by hashing, its lanes pick voxels of that brick by hashing.
+// (A first version scattered every lane over the whole GiB: the real kernel beat that "peak".)
+__global__ void __launch_bounds__(256) k_red_rate(float4* __restrict__ buf, uint32_t brick_mask, int iters)
 {
-    uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    uint32_t hb = gwarp * 2654435761u + 12345u, hv = (gwarp * 32u + lane) * 2246822519u + 977u;
     for (int i = 0; i < iters; i++)
     {
-        h = h * 1664525u + 1013904223u;
-        atomicAdd(buf + ((h >> 4) & mask), make_float4(1.0f, 2.0f, 3.0f, 1.0f));      // red.global.add.v4.f32
+        hb = hb * 1664525u + 1013904223u;
+        hv = hv * 1664525u + 1013904223u;
+        const size_t o = (size_t)((hb >> 7) & brick_mask) * 512u + ((hv >> 9) & 511u);
+        atomicAdd(buf + o, make_float4(1.0f, 2.0f, 3.0f, 1.0f));      // red.global.add.v4.f32
     }
 }
 
@@ -92,7 +99,7 @@ extern "C" int f184_microbench(f184_ctx* c, uint32_t which, double* out_per_seco
         for (int rep = 0; rep < 4; rep++)
         {
             CK(c, cudaEventRecord(e0, c->stream));
-            k_red_rate<<<blocks, 256, 0, c->stream>>>(buf, n - 1, iters);
+            k_red_rate<<<blocks, 256, 0, c->stream>>>(buf, n / 512 - 1, iters);
             CK_LAUNCH(c);
             CK(c, cudaEventRecord(e1, c->stream));
             CK(c, cudaEventSynchronize(e1));

@@ -30,6 +30,8 @@ struct InjectParams
     cudaSurfaceObject_t rad_surf;
     const uint32_t* brick_list;
     const unsigned long long* brick_count;
+    uint32_t* brick_prev;                  // per-brick history bits (f184_internal.h); set_bit = this texture set's bit
+    uint32_t set_bit;
     int N, S;
 };
 
@@ -64,7 +66,10 @@ __global__ void __launch_bounds__(INJECT_WARPS * 32) k_inject_n(const InjectPara
     uint16_t* si = sIdx[warp];
     for (uint32_t i = warp_global; i < count; i += n_warps)
     {
-        const uint32_t b = P.brick_list[i] & 0x7fffffffu;      // bit 31 = touched this frame (normalise)
+        const uint32_t entry = P.brick_list[i];                // bit 31 = touched this frame (normalise)
+        const uint32_t b = entry & 0x7fffffffu;
+        // this texture set now holds the brick iff it is occupied this frame (an emptied brick is overwritten with zeros below)
+        if (lane == 0) P.brick_prev[b] = (P.brick_prev[b] & ~P.set_bit) | ((entry >> 31) ? P.set_bit : 0u);
         const int bx = (b % NB) << 3, by = ((b / NB) % NB) << 3, bz = (b / (NB * NB)) << 3;
         // phase 1: 128 uint4 = 64 rows of 8 texels
         uint32_t nocc = 0;
@@ -180,28 +185,61 @@ M4 f184_invert_m4(const M4& A)
 
 // Texture-side storage: level 0 as a 3D array, levels >= 1 as ONE mipmapped 3D array holding the six directions as
 // z-slabs with zero padding between them (the atlas, f184_internal.h); all surface-writable, sampled with normalised
-// coordinates, trilinear, nearest mip level, border addressing.
-int f184_mode_n_alloc(f184_ctx* c)
+// coordinates, trilinear, border addressing; two texture objects on the atlas: nearest mip level (DESIGN.md B.5 as amended)
+// and linear between levels (SURVEY.md Appendix B as written, F184_FLAG_SPEC_APPENDIX_B).  Two such sets when the frame
+// pipeline is on (frame f+1 is built while frame f is traced), one otherwise.
+static int alloc_set(f184_ctx* c, VolumeSet& v, int N, uint32_t levels)
 {
-    if (c->rad_array) return F184_OK;
-    const int N = (int)c->cfg.grid_n;
     cudaChannelFormatDesc ch = cudaCreateChannelDesc<uchar4>();
-    CK(c, cudaMalloc3DArray(&c->rad_array, &ch, make_cudaExtent(N, N, N), cudaArraySurfaceLoadStore));
+    CK(c, cudaMalloc3DArray(&v.rad_array, &ch, make_cudaExtent(N, N, N), cudaArraySurfaceLoadStore));
     cudaResourceDesc rd{};
     rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = c->rad_array;
-    CK(c, cudaCreateSurfaceObject(&c->rad_surf, &rd));
+    rd.res.array.array = v.rad_array;
+    CK(c, cudaCreateSurfaceObject(&v.rad_surf, &rd));
     cudaTextureDesc td{};
     td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
     td.filterMode = cudaFilterModeLinear;
     td.readMode = cudaReadModeNormalizedFloat;
     td.normalizedCoords = 1;
-    CK(c, cudaCreateTextureObject(&c->rad_tex, &rd, &td, nullptr));
+    CK(c, cudaCreateTextureObject(&v.rad_tex, &rd, &td, nullptr));
     {
-        dim3 g((N + 127) / 128, N, N);
-        k_clear_array<<<g, 128, 0, c->stream>>>(c->rad_surf, N, N);
+        dim3 g((N + 127) / 128, N, std::min(N, 1024));
+        k_clear_array<<<g, 128, 0, c->stream>>>(v.rad_surf, N, N);
         CK_LAUNCH(c);
     }
+    // the six-direction atlas (f184_internal.h): extent (N/2, N/2, 12 * N/2) at its level 0, halving with the chain
+    CK(c, cudaMallocMipmappedArray(&v.dir_atlas, &ch, make_cudaExtent(N / 2, N / 2, 6 * (size_t)N), levels, cudaArraySurfaceLoadStore));
+    for (uint32_t l = 0; l < levels; l++)
+    {
+        cudaArray_t la;
+        CK(c, cudaGetMipmappedArrayLevel(&la, v.dir_atlas, l));
+        cudaResourceDesc lrd{};
+        lrd.resType = cudaResourceTypeArray;
+        lrd.res.array.array = la;
+        CK(c, cudaCreateSurfaceObject(&v.dir_surf[l], &lrd));
+        const int n = std::max(1, (N / 2) >> l);      // the sparse mip builder never writes unlisted bricks, nobody writes the padding: start from zero
+        k_clear_array<<<dim3((n + 127) / 128, n, std::min(12 * n, 1024)), 128, 0, c->stream>>>(v.dir_surf[l], n, 12 * n);
+        CK_LAUNCH(c);
+    }
+    cudaResourceDesc mrd{};
+    mrd.resType = cudaResourceTypeMipmappedArray;
+    mrd.res.mipmap.mipmap = v.dir_atlas;
+    cudaTextureDesc mtd = td;
+    mtd.mipmapFilterMode = cudaFilterModePoint;       // nearest level (DESIGN.md B.5)
+    mtd.minMipmapLevelClamp = 0.0f;
+    mtd.maxMipmapLevelClamp = (float)(levels - 1);
+    CK(c, cudaCreateTextureObject(&v.dir_tex, &mrd, &mtd, nullptr));
+    mtd.mipmapFilterMode = cudaFilterModeLinear;      // "hardware trilinear across level floor(lod), ceil(lod)"
+    CK(c, cudaCreateTextureObject(&v.dir_tex_lin, &mrd, &mtd, nullptr));
+    CK(c, cudaEventCreateWithFlags(&v.ev_built, cudaEventDisableTiming));
+    CK(c, cudaEventCreateWithFlags(&v.ev_traced, cudaEventDisableTiming));
+    return F184_OK;
+}
+
+int f184_mode_n_alloc(f184_ctx* c)
+{
+    if (c->n_sets) return F184_OK;
+    const int N = (int)c->cfg.grid_n;
     uint32_t levels = 0;
     for (int n = N / 2; n >= 1; n /= 2) levels++;
     c->n_mip_levels = levels;
@@ -212,42 +250,32 @@ int f184_mode_n_alloc(f184_ctx* c)
         c->mip_levels.push_back(MipLevelInfo{(uint32_t)n, off});
         off += 6ull * n * n * n;
     }
-    // the six-direction atlas (f184_internal.h): extent (N/2, N/2, 12 * N/2) at its level 0, halving with the chain
-    CK(c, cudaMallocMipmappedArray(&c->dir_atlas, &ch, make_cudaExtent(N / 2, N / 2, 6 * (size_t)N), levels, cudaArraySurfaceLoadStore));
-    for (uint32_t l = 0; l < levels; l++)
+    const int sets = f184_pipelined(c) ? 2 : 1;
+    for (int i = 0; i < sets; i++)
     {
-        cudaArray_t la;
-        CK(c, cudaGetMipmappedArrayLevel(&la, c->dir_atlas, l));
-        cudaResourceDesc lrd{};
-        lrd.resType = cudaResourceTypeArray;
-        lrd.res.array.array = la;
-        CK(c, cudaCreateSurfaceObject(&c->dir_surf[l], &lrd));
-        const int n = std::max(1, (N / 2) >> l);      // the sparse mip builder never writes unlisted bricks, nobody writes the padding: start from zero
-        k_clear_array<<<dim3((n + 127) / 128, n, std::min(12 * n, 1024)), 128, 0, c->stream>>>(c->dir_surf[l], n, 12 * n);
-        CK_LAUNCH(c);
+        int rc = alloc_set(c, c->vs[i], N, levels);
+        if (rc) return rc;
     }
-    cudaResourceDesc mrd{};
-    mrd.resType = cudaResourceTypeMipmappedArray;
-    mrd.res.mipmap.mipmap = c->dir_atlas;
-    cudaTextureDesc mtd = td;
-    mtd.mipmapFilterMode = cudaFilterModePoint;       // nearest level (DESIGN.md B.5)
-    mtd.minMipmapLevelClamp = 0.0f;
-    mtd.maxMipmapLevelClamp = (float)(levels - 1);
-    CK(c, cudaCreateTextureObject(&c->dir_tex, &mrd, &mtd, nullptr));
+    CK(c, cudaStreamSynchronize(c->stream));          // first use only: the clears have landed before any stream of the pipeline touches the sets
+    c->n_sets = sets;
+    c->build_set = c->trace_set = 0;
     return F184_OK;
 }
 
-// test hook: copy one level of the texture-side storage back (dir < 0: the level-0 radiance array)
+// test hook: copy one level of the texture-side storage back (dir < 0: the level-0 radiance array) — of the set the next trace samples
 extern "C" int f184_debug_read_array(f184_ctx* c, int32_t dir, uint32_t level, void* host, size_t bytes)
 {
     if (!c || !host || dir >= 6) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_read_array: bad argument");
-    if (!c->rad_array) return f184_fail(c, F184_ERR_NOT_READY, "debug_read_array: no volume yet");
-    cudaArray_t a = c->rad_array;
+    if (!c->n_sets) return f184_fail(c, F184_ERR_NOT_READY, "debug_read_array: no volume yet");
+    int rc = f184_join_internal(c);
+    if (rc) return rc;
+    const VolumeSet& v = c->vs[c->trace_set];
+    cudaArray_t a = v.rad_array;
     size_t n = c->cfg.grid_n;
     if (dir >= 0)
     {
         if (level >= c->n_mip_levels) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_read_array: bad level");
-        CK(c, cudaGetMipmappedArrayLevel(&a, c->dir_atlas, level));
+        CK(c, cudaGetMipmappedArrayLevel(&a, v.dir_atlas, level));
         n = c->mip_levels[level].n;
     }
     if (bytes != n * n * n * 4) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_read_array: size mismatch");
@@ -264,15 +292,21 @@ extern "C" int f184_debug_read_array(f184_ctx* c, int32_t dir, uint32_t level, v
 
 int f184_mode_n_release(f184_ctx* c)
 {
-    if (c->rad_tex) cudaDestroyTextureObject(c->rad_tex);
-    if (c->rad_surf) cudaDestroySurfaceObject(c->rad_surf);
-    if (c->rad_array) cudaFreeArray(c->rad_array);
-    if (c->dir_tex) cudaDestroyTextureObject(c->dir_tex);
-    for (int l = 0; l < 12; l++)
-        if (c->dir_surf[l]) { cudaDestroySurfaceObject(c->dir_surf[l]); c->dir_surf[l] = 0; }
-    if (c->dir_atlas) cudaFreeMipmappedArray(c->dir_atlas);
-    c->dir_tex = 0; c->dir_atlas = nullptr;
-    c->rad_tex = 0; c->rad_surf = 0; c->rad_array = nullptr;
+    for (VolumeSet& v : c->vs)
+    {
+        if (v.rad_tex) cudaDestroyTextureObject(v.rad_tex);
+        if (v.rad_surf) cudaDestroySurfaceObject(v.rad_surf);
+        if (v.rad_array) cudaFreeArray(v.rad_array);
+        if (v.dir_tex) cudaDestroyTextureObject(v.dir_tex);
+        if (v.dir_tex_lin) cudaDestroyTextureObject(v.dir_tex_lin);
+        for (int l = 0; l < 12; l++)
+            if (v.dir_surf[l]) cudaDestroySurfaceObject(v.dir_surf[l]);
+        if (v.dir_atlas) cudaFreeMipmappedArray(v.dir_atlas);
+        if (v.ev_built) cudaEventDestroy(v.ev_built);
+        if (v.ev_traced) cudaEventDestroy(v.ev_traced);
+        v = VolumeSet{};
+    }
+    c->n_sets = 0;
     return F184_OK;
 }
 
@@ -286,6 +320,9 @@ int f184_inject_n(f184_ctx* c, const f184_sun* sun, const f184_extended_matrices
     if (!c->brick_list) return f184_fail(c, F184_ERR_NOT_READY, "inject: call f184_voxelize first");
     int rc = f184_mode_n_alloc(c);
     if (rc) return rc;
+    rc = f184_volume_begin_write(c);       // the trace of two frames ago may still sample the set this frame is built into
+    if (rc) return rc;
+    c->inject_in_volume = true;
     InjectParams P{};
     M4 vp, vv;
     memcpy(vp.m, m->VoxelProj, 64);
@@ -300,15 +337,18 @@ int f184_inject_n(f184_ctx* c, const f184_sun* sun, const f184_extended_matrices
     P.nrm = img_ptr<char4>(c, F184_SLOT_VOX_NORMAL);
     P.shadow = img_ptr<float>(c, F184_SLOT_SHADOW);
     P.rad = img_ptr<uchar4>(c, F184_SLOT_RADIANCE);
-    P.rad_surf = c->rad_surf;
+    P.rad_surf = c->vs[c->build_set].rad_surf;
+    P.brick_prev = c->brick_prev;
+    P.set_bit = 2u << c->build_set;
     P.brick_list = c->brick_list;
     P.brick_count = c->counters_dev + F184_COUNTER_COUNT;
     P.N = (int)c->cfg.grid_n; P.S = (int)c->cfg.shadow_res;
-    if (!c->gamma_table)
+    if (!c->gamma_table) CK(c, cudaMalloc(&c->gamma_table, 256 * sizeof(float)));
+    if (!c->gamma_ready)
     {
-        CK(c, cudaMalloc(&c->gamma_table, 256 * sizeof(float)));
         k_gamma_table<<<1, 256, 0, c->stream>>>(c->gamma_table);
         CK_LAUNCH(c);
+        c->gamma_ready = true;
     }
     rc = f184_stage_begin(c, F184_STAGE_INJECT);
     if (rc) return rc;

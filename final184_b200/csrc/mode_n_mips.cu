@@ -221,7 +221,7 @@ constexpr int BRICK_WARPS = 8;
 
 __global__ void __launch_bounds__(BRICK_WARPS * 32)
 k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ brick_list, const unsigned long long* __restrict__ brick_count,
-              BrickMipOut out, int N, uint32_t* __restrict__ export_buf)
+              BrickMipOut out, int N, uint32_t* __restrict__ export_buf, uint32_t* __restrict__ brick_prev, uint32_t set_bit)
 {
     __shared__ __align__(16) uint32_t sh0[BRICK_WARPS][512];       // the brick, [z][y][x]
     __shared__ __align__(16) uint32_t sh1[BRICK_WARPS][6][64];     // level 1 per direction, [z][y][x] 4^3
@@ -233,7 +233,10 @@ k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ 
     uint32_t* s0 = sh0[warp];
     for (uint32_t i = warp_global; i < count; i += n_warps)
     {
-        const uint32_t b = __ldg(brick_list + i) & 0x7fffffffu;
+        const uint32_t entry = __ldg(brick_list + i);
+        const uint32_t b = entry & 0x7fffffffu;
+        // levels 1-3 of this texture set now hold the brick iff it is occupied this frame (same assignment as k_inject_n makes for level 0)
+        if (lane == 0 && brick_prev) brick_prev[b] = (brick_prev[b] & ~set_bit) | ((entry >> 31) ? set_bit : 0u);
         const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
         // level 0: 64 rows of 8 texels (one 32-byte sector each) = 128 uint4, four per lane
 #pragma unroll
@@ -456,7 +459,7 @@ int f184_mips_tail_n(f184_ctx* c, bool own_stage)
     TailOut to{};
     to.n_levels = c->n_mip_levels;
     for (uint32_t l = 0; l < c->n_mip_levels; l++) { to.level_off[l] = c->mip_levels[l].offset_texels; to.level_n[l] = c->mip_levels[l].n; }
-    for (uint32_t l = 0; l < c->n_mip_levels; l++) to.surf[l] = c->dir_surf[l];
+    for (uint32_t l = 0; l < c->n_mip_levels; l++) to.surf[l] = c->vs[c->build_set].dir_surf[l];
     const int n3 = (int)c->mip_levels[2].n, T = std::min(16, n3), tiles = n3 / T;
     if (own_stage)
     {
@@ -473,6 +476,8 @@ int f184_mips_n(f184_ctx* c)
     int rc = f184_ensure_image(c, F184_SLOT_RADIANCE); if (rc) return rc;
     rc = f184_ensure_image(c, F184_SLOT_MIPS); if (rc) return rc;
     rc = f184_mode_n_alloc(c); if (rc) return rc;
+    rc = f184_volume_begin_write(c); if (rc) return rc;
+    VolumeSet& vs = c->vs[c->build_set];
     const int N = (int)c->cfg.grid_n;
     uint32_t* mips = img_ptr<uint32_t>(c, F184_SLOT_MIPS);
     const uint32_t* level0 = img_ptr<uint32_t>(c, F184_SLOT_RADIANCE);
@@ -493,7 +498,7 @@ int f184_mips_n(f184_ctx* c)
         BrickMipOut bo;
         for (int l = 0; l < 3; l++)
         {
-            bo.surf[l] = c->dir_surf[l];
+            bo.surf[l] = vs.dir_surf[l];
             for (int d = 0; d < 6; d++)
             {
                 const uint64_t n = c->mip_levels[l].n;
@@ -508,7 +513,10 @@ int f184_mips_n(f184_ctx* c)
             if (rc) return rc;
             export_buf = reinterpret_cast<uint32_t*>(e);
         }
-        k_mips_bricks<<<148 * 4, BRICK_WARPS * 32, 0, c->stream>>>(level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N, export_buf);
+        // (the history bit is assigned only when f184_inject wrote level 0 of the same set from the same list: a build_mips on its
+        // own must not declare a stale level 0 clean)
+        k_mips_bricks<<<148 * 4, BRICK_WARPS * 32, 0, c->stream>>>(level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N, export_buf,
+                                                                   c->inject_in_volume ? c->brick_prev : nullptr, 2u << c->build_set);
         CK_LAUNCH(c);
         first_dense = c->n_mip_levels;          // the tail kernel takes every remaining level
         if (c->cfg.nranks <= 1)                 // (multi-GPU: level 3 is complete only after f184_gather_volume, which runs the tail)
@@ -524,7 +532,7 @@ int f184_mips_n(f184_ctx* c)
         const uint32_t* src = iso ? level0 : mips + c->mip_levels[li - 1].offset_texels;
         const uint64_t src_dir_stride = (uint64_t)sn * sn * sn;
         MipOut out;
-        out.surf = c->dir_surf[li];
+        out.surf = vs.dir_surf[li];
         for (int d = 0; d < 6; d++) out.lin[d] = mips + c->mip_levels[li].offset_texels + (uint64_t)d * n * n * n;
         if (use_tma && sn >= 64)
         {
@@ -550,5 +558,9 @@ int f184_mips_n(f184_ctx* c)
             CK_LAUNCH(c);
         }
     }
-    return f184_stage_end(c, F184_STAGE_MIPS);
+    rc = f184_stage_end(c, F184_STAGE_MIPS);
+    if (rc) return rc;
+    // one GPU: the volume of this frame is complete — it becomes the set the next trace samples.  One NVLink box: only after
+    // f184_gather_volume has fetched the other ranks' bricks.
+    return c->cfg.nranks <= 1 ? f184_volume_publish(c) : F184_OK;
 }

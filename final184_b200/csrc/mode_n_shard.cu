@@ -7,14 +7,20 @@
 //     peer-mapped pointer, carried by NVLink), so after one barrier each owner holds the exact sum for its slab;
 //   * k_peer_barrier: device-side flag barrier — each rank stores its epoch into every peer's flag array
 //     (st.release.sys over NVLink) and spins on its own array (ld.acquire.sys, local memory): no host round trip and
-//     no NCCL launch on the frame's critical path; a 5 s timeout turns a missing peer into an error instead of a hang;
+//     no NCCL launch on the frame's critical path; a timeout (5 s; F184_BARRIER_TIMEOUT_MS) turns a missing peer into an
+//     error instead of a hang: the kernel sets a sticky device error bit and the next synchronous call of the context
+//     (f184_sync, f184_counter_get, f184_stage_time_*) returns F184_ERR_PEER_TIMEOUT;
 //   * k_gather_bricks: the all-gather before tracing — every rank pulls the other ranks' finished bricks, packed by
 //     mode_n_mips.cu into contiguous 4 KB records (level 0 + levels 1-3 of one 8^3 brick), with coalesced 16-byte peer
 //     loads, and writes them through surfaces into its own texture storage; only listed bricks move (Sponza at 512^3:
-//     ~0.12 GB for the whole volume instead of 1.0 GB dense).  Levels >= 4 are then finished locally (k_mips_tail).
+//     ~0.12 GB for the whole volume instead of 1.0 GB dense).  Levels >= 4 are then finished locally (k_mips_tail);
+//   * level 0 travels only when a cone of this rank's rows can sample it: k_need_level0 evaluates the tracer's own level
+//     selection for the first (finest) sample of every pixel's cones; with the 60-degree diffuse cones and materials of
+//     roughness >= 0.6 no cone ever reads level 0 and the gather moves 2 KB per brick instead of 4.
 #include <cstdlib>
 
 #include "f184_device.cuh"
+#include "f184_cone.cuh"
 
 int f184_mips_tail_n(f184_ctx* c, bool own_stage);      // mode_n_mips.cu
 
@@ -39,6 +45,8 @@ struct BarrierArgs
     uint32_t* flags[8];        // flags[p] = rank p's flag array (own entry: local memory)
     int rank, nranks;
     uint32_t epoch;
+    unsigned long long timeout_ns;
+    uint32_t* dev_state;
 };
 
 __global__ void k_peer_barrier(const BarrierArgs B)
@@ -51,22 +59,95 @@ __global__ void k_peer_barrier(const BarrierArgs B)
     const unsigned long long t0 = globaltimer_ns();
     while ((int32_t)(ld_acquire_sys(mine) - B.epoch) < 0)
     {
-        if (globaltimer_ns() - t0 > 5000000000ull) { B.flags[B.rank][8 + p] = B.epoch; break; }   // timeout marker, no hang
+        if (globaltimer_ns() - t0 > B.timeout_ns)
+        {   // no hang: a sticky error bit that the next synchronous call of the context reports (F184_ERR_PEER_TIMEOUT), and a marker
+            // naming the peer
+            atomicOr(B.dev_state + F184_DEV_ERROR, F184_DEVERR_BARRIER_TIMEOUT);
+            B.flags[B.rank][8 + p] = B.epoch;
+            break;
+        }
         __nanosleep(200);
     }
 }
+
+// Does any cone of this rank's rows sample level 0 of the volume?  Evaluates the tracer's level selection (f184_cone.cuh) at the
+// first sample of each cone — the finest one: the footprint only grows with distance.  The diffuse cones are the same for
+// every pixel; the specular cone depends on the pixel's roughness.
+struct NeedArgs
+{
+    const float* depth;
+    const uchar4* material;
+    uint32_t W, y0, y1, tile0, tile_stride, n_tiles;
+    float h;
+    uint32_t spec_b;
+    uint32_t* dev_state;
+};
+__global__ void __launch_bounds__(256) k_need_level0(const NeedArgs A)
+{
+    bool need = false;
+    if (blockIdx.x == 0 && threadIdx.x == 0) need = cone_samples_level0(kTanHalfDiffuse, A.h, A.spec_b != 0);
+    for (uint32_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x)
+    {
+        const uint32_t yb = A.y0 + (A.tile0 + t * A.tile_stride) * 8;
+        for (uint32_t i = threadIdx.x; i < 8 * A.W; i += blockDim.x)
+        {
+            const uint32_t y = yb + i / A.W, x = i % A.W;
+            if (y >= A.y1) break;
+            if (__ldg(A.depth + (size_t)y * A.W + x) >= 1.0f) continue;
+            const float rough = (float)__ldg(A.material + (size_t)y * A.W + x).y / 255.0f;
+            need |= cone_samples_level0(cone_specular_tan(rough), A.h, A.spec_b != 0);
+        }
+    }
+    if (__syncthreads_or(need) && threadIdx.x == 0) A.dev_state[F184_DEV_NEED_L0] = 1u;
+}
+
+// Level 0 is about to be gathered into a set whose level 0 was skipped by an earlier gather: the bricks of the OTHER ranks may hold
+// anything (stale frames), and bricks that have emptied since are no longer on any list.  Clear them all once; own bricks are
+// always current (f184_inject writes them).  Exits at once in every other frame.
+__global__ void __launch_bounds__(256) k_clear_foreign_level0(cudaSurfaceObject_t rad_surf, int N, uint32_t G, uint32_t rank, const uint32_t* __restrict__ dev_state, int set)
+{
+    if (!dev_state[F184_DEV_NEED_L0] || dev_state[F184_DEV_L0_FULL + set]) return;
+    const uint32_t NB = (uint32_t)N >> 3, n_bricks = NB * NB * NB;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (uint32_t b = warp_global; b < n_bricks; b += n_warps)
+    {
+        const uint32_t bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
+        if (((bx + by + bz) & (G - 1)) == rank) continue;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const int q = lane + 32 * k, row = q >> 1, half = q & 1, y = row & 7, z = row >> 3;
+            surf3Dwrite(zero, rad_surf, (bx * 8 + half * 4) * 4, by * 8 + y, bz * 8 + z);
+        }
+    }
+}
+
 
 struct GatherArgs
 {
     const uint32_t* peer_export[8];
     const unsigned long long* peer_counters[8];
     const uint32_t* peer_list[8];
+    const uint32_t* dev_state;
     int rank, nranks, N, write_linear;
     cudaSurfaceObject_t rad_surf;
     uint32_t* rad_lin;
     uint32_t* lin[3][6];
     cudaSurfaceObject_t surf[3];       // atlas levels 1..3 (direction d at z + 2 d n)
 };
+
+// behind the gather: the set's level-0 bookkeeping, and the bytes that crossed NVLink (F184_COUNTER_GATHER_BYTES)
+__global__ void k_gather_state(const GatherArgs G, uint32_t* dev_state, int set, unsigned long long* counters)
+{
+    const bool level0 = dev_state[F184_DEV_NEED_L0] != 0;
+    dev_state[F184_DEV_L0_FULL + set] = level0 ? 1u : 0u;
+    unsigned long long records = 0;
+    for (int p = 0; p < G.nranks; p++)
+        if (p != G.rank) records += G.peer_counters[p][F184_COUNTER_COUNT];
+    counters[F184_COUNTER_GATHER_BYTES] = records * (4ull + (level0 ? 2048ull : 0ull) + 4ull * (384 + 48 + 6));    // list entry + record parts read
+}
 
 constexpr int GATHER_WARPS = 8;
 
@@ -82,6 +163,7 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather_bricks(const Gathe
     const uint32_t warp_global = blockIdx.y * GATHER_WARPS + warp, n_warps = gridDim.y * GATHER_WARPS;
     const uint32_t count = (uint32_t)G.peer_counters[p][F184_COUNTER_COUNT];     // that rank's brick-list cursor
     const int N = G.N, NB = N >> 3, n1 = N >> 1, n2 = N >> 2, n3 = N >> 3;
+    const bool level0 = G.dev_state[F184_DEV_NEED_L0] != 0;       // block-uniform: level 0 travels only when a cone of this rank's rows samples it
     for (uint32_t i = warp_global; i < count; i += n_warps)
     {
         const uint32_t* rec = G.peer_export[p] + (size_t)i * 1024;
@@ -89,20 +171,26 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather_bricks(const Gathe
         const uint32_t b = G.peer_list[p][i] & 0x7fffffffu;
         const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
         uint4 l0[4], l1[3];
+        if (level0)
+        {
 #pragma unroll
-        for (int k = 0; k < 4; k++) l0[k] = rec4[lane + 32 * k];               // 7 independent 16-byte peer loads in flight
+            for (int k = 0; k < 4; k++) l0[k] = rec4[lane + 32 * k];           // 7 independent 16-byte peer loads in flight
+        }
 #pragma unroll
         for (int k = 0; k < 3; k++) l1[k] = rec4[128 + lane + 32 * k];
         uint2 l2 = make_uint2(0, 0);
         if (lane < 24) l2 = reinterpret_cast<const uint2*>(rec + 896)[lane];
         uint32_t l3 = 0;
         if (lane < 6) l3 = rec[944 + lane];
-#pragma unroll
-        for (int k = 0; k < 4; k++)
+        if (level0)
         {
-            const int q = lane + 32 * k, row = q >> 1, half = q & 1, y = row & 7, z = row >> 3;
-            surf3Dwrite(l0[k], G.rad_surf, (bx * 8 + half * 4) * 4, by * 8 + y, bz * 8 + z);
-            if (G.write_linear) *reinterpret_cast<uint4*>(G.rad_lin + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4) = l0[k];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                const int q = lane + 32 * k, row = q >> 1, half = q & 1, y = row & 7, z = row >> 3;
+                surf3Dwrite(l0[k], G.rad_surf, (bx * 8 + half * 4) * 4, by * 8 + y, bz * 8 + z);
+                if (G.write_linear) *reinterpret_cast<uint4*>(G.rad_lin + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4) = l0[k];
+            }
         }
 #pragma unroll
         for (int k = 0; k < 3; k++)
@@ -199,18 +287,28 @@ extern "C" int f184_peer_barrier(f184_ctx* c)
     }
     B.rank = (int)c->cfg.rank; B.nranks = (int)c->cfg.nranks;
     B.epoch = ++c->barrier_epoch;
-    int rc = f184_join_vox(c);             // this rank's fragments (possibly still in flight on vox_stream) leave before its flag does
+    static const unsigned long long timeout_ms = [] { const char* e = getenv("F184_BARRIER_TIMEOUT_MS"); return e && atoll(e) > 0 ? (unsigned long long)atoll(e) : 5000ull; }();
+    B.timeout_ns = timeout_ms * 1000000ull;
+    B.dev_state = c->dev_state;
+    F184Section sec;
+    int rc = f184_enter(c, F184_SID_BUILD, &sec);      // the barriers belong to the build stream's chain (DESIGN.md "Frame pipeline")
     if (rc) return rc;
-    rc = f184_stage_begin(c, F184_STAGE_BARRIER);
-    if (rc) return rc;
-    k_peer_barrier<<<1, 32, 0, c->stream>>>(B);
-    CK_LAUNCH(c);
-    rc = f184_stage_end(c, F184_STAGE_BARRIER);
-    if (rc) return rc;
-    if (!c->ev_barrier) CK(c, cudaEventCreateWithFlags(&c->ev_barrier, cudaEventDisableTiming));
-    CK(c, cudaEventRecord(c->ev_barrier, c->stream));
-    c->barrier_recorded = true;
-    return F184_OK;
+    auto body = [&]() -> int {
+        int rc = f184_build_wait_vox(c);               // this rank's fragments (possibly still in flight on vox_stream) leave before its flag does
+        if (rc) return rc;
+        if (c->cur_sid == F184_SID_PASS && (rc = f184_join_internal(c))) return rc;
+        rc = f184_stage_begin(c, F184_STAGE_BARRIER);
+        if (rc) return rc;
+        k_peer_barrier<<<1, 32, 0, c->stream>>>(B);
+        CK_LAUNCH(c);
+        rc = f184_stage_end(c, F184_STAGE_BARRIER);
+        if (rc) return rc;
+        if (!c->ev_barrier) CK(c, cudaEventCreateWithFlags(&c->ev_barrier, cudaEventDisableTiming));
+        CK(c, cudaEventRecord(c->ev_barrier, c->stream));
+        c->barrier_recorded = true;
+        return F184_OK;
+    };
+    return f184_leave(c, sec, body());
 }
 
 int f184_gather_n(f184_ctx* c)
@@ -219,6 +317,10 @@ int f184_gather_n(f184_ctx* c)
     int rc = f184_mode_n_alloc(c); if (rc) return rc;
     rc = f184_ensure_image(c, F184_SLOT_RADIANCE); if (rc) return rc;
     rc = f184_ensure_image(c, F184_SLOT_MIPS); if (rc) return rc;
+    for (int s_ : {F184_SLOT_DEPTH, F184_SLOT_MATERIAL}) { rc = f184_ensure_image(c, s_); if (rc) return rc; }
+    rc = f184_volume_begin_write(c); if (rc) return rc;
+    VolumeSet& vs = c->vs[c->build_set];
+    const int set = c->build_set;
     GatherArgs G{};
     for (uint32_t p = 0; p < c->cfg.nranks; p++)
     {
@@ -230,12 +332,13 @@ int f184_gather_n(f184_ctx* c)
     }
     G.rank = (int)c->cfg.rank; G.nranks = (int)c->cfg.nranks; G.N = (int)c->cfg.grid_n;
     G.write_linear = (c->cfg.flags & F184_FLAG_GATHER_LINEAR) ? 1 : 0;
-    G.rad_surf = c->rad_surf;
+    G.dev_state = c->dev_state;
+    G.rad_surf = vs.rad_surf;
     G.rad_lin = img_ptr<uint32_t>(c, F184_SLOT_RADIANCE);
     uint32_t* mips = img_ptr<uint32_t>(c, F184_SLOT_MIPS);
     for (int l = 0; l < 3; l++)
     {
-        G.surf[l] = c->dir_surf[l];
+        G.surf[l] = vs.dir_surf[l];
         for (int d = 0; d < 6; d++)
         {
             const uint64_t n = c->mip_levels[l].n;
@@ -244,13 +347,33 @@ int f184_gather_n(f184_ctx* c)
     }
     rc = f184_stage_begin(c, F184_STAGE_EXCHANGE);
     if (rc) return rc;
+    {   // does level 0 have to travel this frame?  (F184_FLAG_GATHER_LINEAR — the tests' full comparison — and F184_GATHER_LEVEL0=1 force it)
+        static const bool force_env = [] { const char* e = getenv("F184_GATHER_LEVEL0"); return e && atoi(e) != 0; }();
+        const bool force = force_env || (c->cfg.flags & F184_FLAG_GATHER_LINEAR);
+        CK(c, cudaMemsetAsync(c->dev_state + F184_DEV_NEED_L0, force ? 0x01 : 0, 4, c->stream));     // 0x01010101 = non-zero = needed
+        if (!force)
+        {
+            NeedArgs A{};
+            A.depth = img_ptr<float>(c, F184_SLOT_DEPTH);
+            A.material = img_ptr<uchar4>(c, F184_SLOT_MATERIAL);
+            A.W = c->cfg.width;
+            A.n_tiles = f184_trace_tiles(c, c->cfg.height, &A.y0, &A.y1, &A.tile0, &A.tile_stride);
+            A.h = c->voxel_h;
+            A.spec_b = (c->cfg.flags & F184_FLAG_SPEC_APPENDIX_B) ? 1u : 0u;
+            A.dev_state = c->dev_state;
+            k_need_level0<<<148, 256, 0, c->stream>>>(A);
+            CK_LAUNCH(c);
+        }
+        k_clear_foreign_level0<<<148 * 4, 256, 0, c->stream>>>(vs.rad_surf, (int)c->cfg.grid_n, c->cfg.nranks, c->cfg.rank, c->dev_state, set);
+        CK_LAUNCH(c);
+    }
     k_gather_bricks<<<dim3(c->cfg.nranks, 148), GATHER_WARPS * 32, 0, c->stream>>>(G);
+    CK_LAUNCH(c);
+    k_gather_state<<<1, 1, 0, c->stream>>>(G, c->dev_state, set, c->counters_dev);
     CK_LAUNCH(c);
     rc = f184_stage_end(c, F184_STAGE_EXCHANGE);
     if (rc) return rc;
-    // A/B knob F184_VOX_AFTER_GATHER=1: the next frame's accumulation (vox_stream) starts behind the gather instead of behind
-    // the barrier before it, so its peer atomics do not share NVLink and the SMs with the gather's peer loads
-    static const bool after_gather = [] { const char* e = getenv("F184_VOX_AFTER_GATHER"); return e && atoi(e) != 0; }();
-    if (after_gather && c->ev_barrier) CK(c, cudaEventRecord(c->ev_barrier, c->stream));
-    return f184_mips_tail_n(c, true);
+    rc = f184_mips_tail_n(c, true);
+    if (rc) return rc;
+    return f184_volume_publish(c);        // every rank's bricks are in: this set is what the next trace samples
 }

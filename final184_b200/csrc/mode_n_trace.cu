@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "f184_device.cuh"
+#include "f184_cone.cuh"
 
 namespace {
 
@@ -29,7 +30,11 @@ struct ConeParams
 {
     M4 InvProj, InvModelView, w2v, prevModelView, prevProjection;
     cudaTextureObject_t level0;
-    cudaTextureObject_t atlas;             // levels >= 1, six directions as z-slabs of one mipmapped 3D array
+    cudaTextureObject_t atlas;             // levels >= 1, six directions as z-slabs of one mipmapped 3D array (nearest mip level)
+    cudaTextureObject_t atlas_lin;         // the same array, linear between mip levels (Appendix-B spec)
+    // one NVLink box: [0] = level 0 of the sampled set holds every rank's bricks; [1] = sticky error word.  nullptr on one GPU.
+    const uint32_t* l0_full;
+    uint32_t* dev_error;
     const float* depth;
     const uint16_t* normals;
     const uchar4* material;
@@ -49,7 +54,6 @@ __constant__ float kDiffuseDirs[6][3] = {
     {-0.70062927f, -0.50903696f, 0.5f},
     {0.26761657f, -0.82363910f, 0.5f}};
 __constant__ float kDiffuseW[6] = {0.25f, 0.15f, 0.15f, 0.15f, 0.15f, 0.15f};
-constexpr float kTanHalfDiffuse = 0.57735027f;
 
 // Direction-weighted fetch from the six-direction atlas: direction d of every level occupies the normalised z range
 // [d/6, d/6 + 1/12) (f184_internal.h), so a face is a per-cone z offset and all three fetches use ONE warp-uniform texture
@@ -70,6 +74,10 @@ __device__ __forceinline__ float4 tex_dir(cudaTextureObject_t atlas, const float
     return r;
 }
 
+// SPEC_B = false: DESIGN.md B.5 as amended (nearest mip level, one sample per voxel of the sampled level: t += diam).
+// SPEC_B = true:  SURVEY.md Appendix B.5 as written (F184_FLAG_SPEC_APPENDIX_B): mip-linear sampling — below lod 1 a blend of the
+//                 isotropic level 0 and the directional level 1, above it the hardware's linear mip filter — and t += diam / 2.
+template <bool SPEC_B>
 __device__ f3 trace_cone(const ConeParams& P, f3 origin, f3 dir, float tan_half, unsigned int& samples)
 {
     const float h = P.h;
@@ -89,20 +97,38 @@ __device__ f3 trace_cone(const ConeParams& P, f3 origin, f3 dir, float tan_half,
     const float inv_h = 1.0f / h;
     while (A < 0.95f && t < P.max_dist)
     {
-        const float diam = fmaxf(h, 2.0f * t * tan_half);
-        const float lod = __log2f(diam * inv_h);
+        float diam;
+        const float lod = cone_lod(t, tan_half, h, inv_h, &diam);
         const float qx = q0.x + dv.x * t, qy = q0.y + dv.y * t, qz = q0.z + dv.z * t;
         if (!(qx >= 0.0f && qx <= 1.0f && qy >= 0.0f && qy <= 1.0f && qz >= 0.0f && qz <= 1.0f)) break;
         samples++;
-        // nearest level (point mip filter): 0 = the isotropic radiance volume, L >= 1 = the six-direction chain
-        const int L = (int)floorf(lod + 0.5f);
         float4 s;
-        if (L <= 0) s = tex3D<float4>(P.level0, qx, qy, qz);
-        else s = tex_dir(P.atlas, w, zoff, qx, qy, qz, fminf((float)(L - 1), P.max_lod));
+        if (SPEC_B)
+        {
+            if (lod < 1.0f)
+            {   // between the isotropic level 0 and the directional level 1
+                if (P.l0_full && !*P.l0_full) atomicOr(P.dev_error, F184_DEVERR_LEVEL0_MISSING);
+                const float4 a = tex3D<float4>(P.level0, qx, qy, qz);
+                const float4 b = tex_dir(P.atlas, w, zoff, qx, qy, qz, 0.0f);
+                s = make_float4(a.x + lod * (b.x - a.x), a.y + lod * (b.y - a.y), a.z + lod * (b.z - a.z), a.w + lod * (b.w - a.w));
+            }
+            else s = tex_dir(P.atlas_lin, w, zoff, qx, qy, qz, fminf(lod - 1.0f, P.max_lod));
+        }
+        else
+        {
+            // nearest level (point mip filter): 0 = the isotropic radiance volume, L >= 1 = the six-direction chain
+            const int L = (int)floorf(lod + 0.5f);
+            if (L <= 0)
+            {   // one NVLink box: the gather fetched level 0 only if k_need_level0 saw a cone like this one; anything else is an API misuse
+                if (P.l0_full && !*P.l0_full) atomicOr(P.dev_error, F184_DEVERR_LEVEL0_MISSING);
+                s = tex3D<float4>(P.level0, qx, qy, qz);
+            }
+            else s = tex_dir(P.atlas, w, zoff, qx, qy, qz, fminf((float)(L - 1), P.max_lod));
+        }
         const float k = 1.0f - A;
         acc = {acc.x + k * s.x, acc.y + k * s.y, acc.z + k * s.z};
         A += k * s.w;
-        t += diam;                   // one sample per voxel of the level along the axis
+        t += SPEC_B ? 0.5f * diam : diam;      // amended spec: one sample per voxel of the sampled level along the axis
     }
     const float rem = fmaxf(0.0f, 1.0f - A);
     return {acc.x * P.exposure + 0.7f * 0.4f * rem, acc.y * P.exposure + 0.8f * 0.4f * rem, acc.z * P.exposure + 1.0f * 0.4f * rem};
@@ -111,7 +137,7 @@ __device__ f3 trace_cone(const ConeParams& P, f3 origin, f3 dir, float tan_half,
 __device__ __forceinline__ float unorm16(uint16_t v) { return (float)v / 65535.0f; }
 __device__ __forceinline__ int wrapn(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
 
-template <int MIN_CTAS>
+template <int MIN_CTAS, bool SPEC_B>
 __global__ void __launch_bounds__(128, MIN_CTAS) k_trace_n(const ConeParams P, unsigned long long* __restrict__ sample_counter)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -147,19 +173,19 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_trace_n(const ConeParams P, u
             {
                 const float d0 = kDiffuseDirs[i][0], d1 = kDiffuseDirs[i][1], d2 = kDiffuseDirs[i][2];
                 const f3 dir = {(tx.x * d0 + ty.x * d1) + z.x * d2, (tx.y * d0 + ty.y * d1) + z.y * d2, (tx.z * d0 + ty.z * d1) + z.z * d2};
-                const f3 r = trace_cone(P, origin, dir, kTanHalfDiffuse, samples);
+                const f3 r = trace_cone<SPEC_B>(P, origin, dir, kTanHalfDiffuse, samples);
                 const float wgt = kDiffuseW[i];
                 ind = {ind.x + wgt * r.x, ind.y + wgt * r.y, ind.z + wgt * r.z};
             }
             {
                 const float rough = (float)__ldg(P.material + (size_t)y * W + x).y / 255.0f;
-                const float tan_half = dm_clamp(rough * rough, 0.02f, 0.6f);
+                const float tan_half = cone_specular_tan(rough);
                 const f3 I = normalize3(wpos - P.cam);
                 const float ndi = dot3(z, I);
                 const f3 R = {I.x - 2.0f * ndi * z.x, I.y - 2.0f * ndi * z.y, I.z - 2.0f * ndi * z.z};
                 if (dot3(R, z) > 0.0f)
                 {
-                    const f3 r = trace_cone(P, origin, R, tan_half, samples);
+                    const f3 r = trace_cone<SPEC_B>(P, origin, R, tan_half, samples);
                     const float om = 1.0f - fmaxf(-ndi, 0.0f);
                     const float F = 0.04f + 0.96f * (om * om * om * om * om);
                     ind = {ind.x + F * r.x, ind.y + F * r.y, ind.z + F * r.z};
@@ -200,7 +226,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k_trace_n(const ConeParams P, u
 }  // namespace
 
 // parameter block of one view; window = rows [vy0, vy0 + vh)
-static int trace_params(f184_ctx* c, const f184_trace_constants* k, uint32_t vy0, uint32_t vh, ConeParams& P)
+static int trace_params(f184_ctx* c, const VolumeSet& vs, const f184_trace_constants* k, uint32_t vy0, uint32_t vh, ConeParams& P)
 {
     memcpy(P.InvProj.m, k->view.InvProj, 64);
     memcpy(P.InvModelView.m, k->ext.InvModelView, 64);
@@ -210,14 +236,15 @@ static int trace_params(f184_ctx* c, const f184_trace_constants* k, uint32_t vy0
     P.w2v = host_matmul(vp, vv);
     memcpy(P.prevModelView.m, k->prev.PrevModelView, 64);
     memcpy(P.prevProjection.m, k->prev.PrevProjection, 64);
+    P.h = f184_voxel_h(k->ext.VoxelProj, k->ext.VoxelView, c->cfg.grid_n);
+    P.level0 = vs.rad_tex;
+    P.atlas = vs.dir_tex;
+    P.atlas_lin = vs.dir_tex_lin;
+    if (c->cfg.nranks > 1)
     {
-        const M4 v2w = f184_invert_m4(P.w2v);
-        const float s = 2.0f / (float)c->cfg.grid_n;
-        const float ax = v2w.m[0] * s, ay = v2w.m[1] * s, az = v2w.m[2] * s;
-        P.h = sqrtf((ax * ax + ay * ay) + az * az);
+        P.l0_full = c->dev_state + F184_DEV_L0_FULL + (&vs - c->vs);
+        P.dev_error = c->dev_state + F184_DEV_ERROR;
     }
-    P.level0 = c->rad_tex;
-    P.atlas = c->dir_tex;
     P.depth = img_ptr<float>(c, F184_SLOT_DEPTH);
     P.normals = img_ptr<uint16_t>(c, F184_SLOT_NORMALS);
     P.material = img_ptr<uchar4>(c, F184_SLOT_MATERIAL);
@@ -237,8 +264,9 @@ static int trace_launch(f184_ctx* c, const ConeParams& P, uint32_t grid_y, cudaS
     dim3 grid((P.W + 15) / 16, grid_y);
     // two register budgets of the same kernel: 8 CTAs/SM (64 registers) or 7 (72, no spill); F184_TRACE_CTAS=7 selects the latter (A/B knob)
     static const int min_ctas = [] { const char* e = getenv("F184_TRACE_CTAS"); return e ? atoi(e) : 8; }();
-    if (min_ctas == 7) k_trace_n<7><<<grid, 128, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
-    else k_trace_n<8><<<grid, 128, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+    if (c->cfg.flags & F184_FLAG_SPEC_APPENDIX_B) k_trace_n<7, true><<<grid, 128, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+    else if (min_ctas == 7) k_trace_n<7, false><<<grid, 128, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+    else k_trace_n<8, false><<<grid, 128, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
     CK_LAUNCH(c);
     return F184_OK;
 }
@@ -250,7 +278,7 @@ static int trace_check(f184_ctx* c)
         int rc = f184_ensure_image(c, s);
         if (rc) return rc;
     }
-    if (!c->rad_array) return f184_fail(c, F184_ERR_NOT_READY, "trace: call f184_inject and f184_build_mips first");
+    if (!c->n_sets) return f184_fail(c, F184_ERR_NOT_READY, "trace: call f184_inject and f184_build_mips first");
     return F184_OK;
 }
 
@@ -258,8 +286,11 @@ int f184_trace_n(f184_ctx* c, const f184_trace_constants* k)
 {
     int rc = trace_check(c);
     if (rc) return rc;
+    VolumeSet* vs = nullptr;
+    rc = f184_volume_acquire(c, &vs);      // the newest complete set; the pass stream waits for its build (inject, mips, gather) only
+    if (rc) return rc;
     ConeParams P{};
-    trace_params(c, k, 0, c->cfg.height, P);
+    trace_params(c, *vs, k, 0, c->cfg.height, P);
     const uint32_t grid_y = f184_trace_tiles(c, P.H, &P.y0, &P.y1, &P.tile0, &P.tile_stride);
     if (P.tile_stride > 1 && (P.y0 & 7)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "trace: row range must start on a multiple of 8 when tiles are interleaved");
     rc = f184_stage_begin(c, F184_STAGE_TRACE);
@@ -268,7 +299,9 @@ int f184_trace_n(f184_ctx* c, const f184_trace_constants* k)
         CK(c, cudaMemsetAsync(c->img[F184_SLOT_INDIRECT_HISTORY].ptr, 0, c->img[F184_SLOT_INDIRECT_HISTORY].desc.size_bytes, c->stream));
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_MARCH_STEPS, 0, 8, c->stream));
     if (grid_y && (rc = trace_launch(c, P, grid_y, c->stream))) return rc;
-    return f184_stage_end(c, F184_STAGE_TRACE);
+    rc = f184_stage_end(c, F184_STAGE_TRACE);
+    if (rc) return rc;
+    return f184_volume_release(c, vs);
 }
 
 // Probe batch (BASELINE configs[4]; f184_trace_views in f184.h): the images hold H / view_h views stacked top to bottom;
@@ -289,6 +322,9 @@ int f184_trace_views_n(f184_ctx* c, const f184_trace_constants* ks, uint32_t vie
             CK(c, cudaEventCreateWithFlags(&c->ev_view_done[i], cudaEventDisableTiming));
         }
     if (!c->ev_view_fork) CK(c, cudaEventCreateWithFlags(&c->ev_view_fork, cudaEventDisableTiming));
+    VolumeSet* vs = nullptr;
+    rc = f184_volume_acquire(c, &vs);
+    if (rc) return rc;
     rc = f184_stage_begin(c, F184_STAGE_TRACE);
     if (rc) return rc;
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_MARCH_STEPS, 0, 8, c->stream));
@@ -300,7 +336,7 @@ int f184_trace_views_n(f184_ctx* c, const f184_trace_constants* ks, uint32_t vie
     {
         cudaStream_t st = c->view_streams[(v - first) % F184_VIEW_STREAMS];
         ConeParams P{};
-        trace_params(c, &ks[v], v * view_h, view_h, P);
+        trace_params(c, *vs, &ks[v], v * view_h, view_h, P);
         P.y0 = v * view_h; P.y1 = P.y0 + view_h; P.tile0 = 0; P.tile_stride = 1;
         if (ks[v].reset_history)
             CK(c, cudaMemsetAsync(img_ptr<uint8_t>(c, F184_SLOT_INDIRECT_HISTORY) + (size_t)P.y0 * row_bytes, 0, (size_t)view_h * row_bytes, st));
@@ -311,5 +347,7 @@ int f184_trace_views_n(f184_ctx* c, const f184_trace_constants* ks, uint32_t vie
         CK(c, cudaEventRecord(c->ev_view_done[i], c->view_streams[i]));
         CK(c, cudaStreamWaitEvent(c->stream, c->ev_view_done[i], 0));
     }
-    return f184_stage_end(c, F184_STAGE_TRACE);
+    rc = f184_stage_end(c, F184_STAGE_TRACE);
+    if (rc) return rc;
+    return f184_volume_release(c, vs);
 }

@@ -74,6 +74,12 @@ __device__ __forceinline__ int pick3(int a0, int a1, int a2, int k) { return k =
 __device__ __forceinline__ long long pick3l(long long a0, long long a1, long long a2, int k) { return k == 0 ? a0 : (k == 1 ? a1 : a2); }
 __device__ __forceinline__ long long wide(int a, int b) { return (long long)a * (long long)b; }   // one IMAD.WIDE
 
+// 16-byte vector reduction at system scope (sm_90+): the form of red.global.add.v4.f32 that is defined on peer memory
+__device__ __forceinline__ void red_add_v4_sys(float4* p, float a, float b, float c, float d)
+{
+    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ size_t brick_major(int x, int y, int z, int NB)
 {
     const size_t brick = ((size_t)(z >> 3) * NB + (y >> 3)) * NB + (x >> 3);
@@ -111,13 +117,14 @@ struct VoxArgs
     const MatDev* mats;
     uint32_t tri_first, tri_end;
     int N;
-    // accumulators / brick flags of the rank that owns the voxel's brick layer, owner = (z / 8) % nranks (layers are
-    // interleaved so every rank gets an even share of the occupied bricks): own memory, or a peer's memory mapped over
-    // NVLink — then the atomics below ARE the reduce-scatter of the partial volumes.  One GPU: owner_mask = 0.
+    // accumulators / brick flags of the rank that owns the voxel's 8^3 brick, owner = (bx + by + bz) % nranks (a diagonal
+    // interleave: every axis-aligned sheet of bricks — Sponza's floor is one — is dealt evenly over the ranks): own memory,
+    // or a peer's memory mapped over NVLink — then the reductions below ARE the reduce-scatter of the partial volumes.
+    // One GPU: owner_mask = 0.
     float4* accC[8];
     float4* accN[8];
     uint32_t* brick_flags[8];
-    uint32_t owner_mask;
+    uint32_t owner_mask, rank;
     unsigned long long* frag_counter;
     unsigned long long* queue_state;   // (entries << 40) | tasks, one 64-bit word so both advance together
     uint2* queue;                      // per large triangle: (triangle, first task)
@@ -335,9 +342,17 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
         const int by = s.d == 0 ? iu : (s.d == 1 ? kd : iv);
         const int bz = s.d == 0 ? iv : (s.d == 1 ? iu : kd);
         const size_t o = brick_major(bx, by, bz, A.N >> 3);
-        const uint32_t owner = ((uint32_t)bz >> 3) & A.owner_mask;
-        atomicAdd(A.accC[owner] + o, make_float4(r8, g8, b8, 1.0f));     // red.global.add.v4.f32 (peer memory when owner != this rank)
-        atomicAdd(A.accN[owner] + o, make_float4(nx8, ny8, nz8, 0.0f));
+        const uint32_t owner = (uint32_t)((bx >> 3) + (by >> 3) + (bz >> 3)) & A.owner_mask;
+        if (owner == A.rank)
+        {   // own memory: red.global.add.v4.f32 at device scope
+            atomicAdd(A.accC[owner] + o, make_float4(r8, g8, b8, 1.0f));
+            atomicAdd(A.accN[owner] + o, make_float4(nx8, ny8, nz8, 0.0f));
+        }
+        else
+        {   // a peer's memory over NVLink: the CUDA memory model guarantees inter-GPU atomicity at SYSTEM scope only
+            red_add_v4_sys(A.accC[owner] + o, r8, g8, b8, 1.0f);
+            red_add_v4_sys(A.accN[owner] + o, nx8, ny8, nz8, 0.0f);
+        }
         A.brick_flags[owner][o >> 9] = 1u;
         frags++;
     }
@@ -463,16 +478,21 @@ __global__ void k_view_model_n(M4 View, const M4* __restrict__ model, M4* __rest
 
 // ---- B.2 normalise, sparse: only bricks touched this frame or last frame ---------------------------------
 // pass 1: one thread per brick flag -> compact list (warp-aggregated append).  Entry = brick | touched << 31.
+// `prev` bits (f184_internal.h: brick_prev): bit 0 = touched by the previous voxelize, bit 1 + s = texture set s holds the brick.
+// Any of them lists the brick, so whichever copy is stale gets overwritten (with zeros if the brick is empty now).
 __global__ void __launch_bounds__(256)
 k_brick_compact(uint32_t* __restrict__ brick_flags, uint32_t* __restrict__ brick_prev, uint32_t* __restrict__ brick_list,
-                unsigned long long* __restrict__ counters, uint32_t n_own, uint32_t NB2, uint32_t G, uint32_t rank)
+                unsigned long long* __restrict__ counters, uint32_t n_own, uint32_t NB, uint32_t G, uint32_t rank)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;             // j-th brick of this rank: layers rank, rank + G, ...
-    const uint32_t bi = ((j / NB2) * G + rank) * NB2 + j % NB2;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;             // j-th brick of this rank
+    // own bricks of row (by, bz): bx = (rank - by - bz) mod G, + G, + 2G, ...   (owner = (bx + by + bz) % G)
+    const uint32_t per_row = NB / G, row = j / per_row, by = row % NB, bz = row / NB;
+    const uint32_t bx = ((rank + 2u * G - (by % G) - (bz % G)) % G) + (j % per_row) * G;
+    const uint32_t bi = (bz * NB + by) * NB + bx;
     uint32_t flag = 0, prev = 0;
     if (j < n_own) { flag = brick_flags[bi]; prev = brick_prev[bi]; }
-    if (flag | prev) { brick_flags[bi] = 0; brick_prev[bi] = flag; }
+    if (flag | prev) { brick_flags[bi] = 0; brick_prev[bi] = (prev & ~1u) | (flag ? 1u : 0u); }
     const unsigned int todo = __ballot_sync(0xffffffffu, (flag | prev) != 0);
     const unsigned int touched = __ballot_sync(0xffffffffu, flag != 0);
     if (!todo) return;
@@ -554,6 +574,26 @@ k_normalise_n(float4* __restrict__ accC, float4* __restrict__ accN, uchar4* __re
 
 }  // namespace
 
+// scratch sized by the scene: the pass-2 queue and the View * Model matrices (re-allocated only when the scene grows)
+int f184_voxelizer_scratch_n(f184_ctx* c)
+{
+    if (c->vox_queue_cap < c->n_tris)
+    {   // worst case every triangle is large: (8 + 192) B per triangle
+        if (c->vox_queue) cudaFree(c->vox_queue);
+        c->vox_queue = nullptr; c->vox_queue_cap = 0;
+        CK(c, cudaMalloc(&c->vox_queue, (8ull + sizeof(TriS)) * c->n_tris));
+        c->vox_queue_cap = c->n_tris;
+    }
+    if (c->vm_cap < c->n_models)
+    {
+        if (c->vm_dev) cudaFree(c->vm_dev);
+        c->vm_dev = nullptr; c->vm_cap = 0;
+        CK(c, cudaMalloc(&c->vm_dev, sizeof(M4) * c->n_models));
+        c->vm_cap = c->n_models;
+    }
+    return F184_OK;
+}
+
 int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
 {
     for (int s : {F184_SLOT_ACCUM_COLOR, F184_SLOT_ACCUM_NORMAL, F184_SLOT_VOX_ALBEDO, F184_SLOT_VOX_NORMAL, F184_SLOT_BRICK_FLAGS})
@@ -569,17 +609,9 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
         int rc = f184_ipc_buffer_ptr(c, F184_IPC_BRICK_LIST, &dummy);      // brick_prev / brick_list
         if (rc) return rc;
     }
-    if (c->vox_queue_cap < c->n_tris)
-    {   // worst case every triangle is large: (8 + 192) B per triangle
-        if (c->vox_queue) cudaFree(c->vox_queue);
-        CK(c, cudaMalloc(&c->vox_queue, (8ull + sizeof(TriS)) * c->n_tris));
-        c->vox_queue_cap = c->n_tris;
-    }
-    if (c->vm_cap < c->n_models)
     {
-        if (c->vm_dev) cudaFree(c->vm_dev);
-        CK(c, cudaMalloc(&c->vm_dev, sizeof(M4) * c->n_models));
-        c->vm_cap = c->n_models;
+        int rc = f184_voxelizer_scratch_n(c);
+        if (rc) return rc;
     }
     VoxArgs A{};
     for (uint32_t p = 0; p < (G ? G : 1); p++)
@@ -599,6 +631,8 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
         }
     }
     A.owner_mask = G > 1 ? G - 1 : 0;
+    A.rank = G > 1 ? c->cfg.rank : 0;
+    c->voxel_h = f184_voxel_h(cam->ProjMat, cam->ViewMat, c->cfg.grid_n);
     M4 View;
     memcpy(View.m, cam->ViewMat, 64);
     k_view_model_n<<<(c->n_models * 16 + 127) / 128, 128, 0, c->stream>>>(View, c->model_mats, c->vm_dev, c->n_models);
@@ -633,38 +667,7 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
     return f184_stage_end(c, F184_STAGE_VOXELIZE);
 }
 
-int f184_voxelize_n(f184_ctx* c, const f184_view_constants* cam)
-{
-    if (!f184_overlap_enabled(c))
-    {
-        int rc = f184_join_vox(c);
-        if (rc) return rc;
-        rc = f184_voxelize_accumulate_n(c, cam);
-        if (rc) return rc;
-        return f184_normalise_n(c);
-    }
-    // Frame overlap: both passes go to vox_stream.  They start once the pass stream has finished everything that reads what
-    // they overwrite (ev_consumed: the previous frame's inject + mips) — NOT once it has finished the previous frame's cone
-    // trace, which reads none of it and is what these kernels run beside.
-    cudaStream_t pass = c->stream;
-    if (!c->vox_started)
-    {   // first use: order vox_stream behind everything enqueued so far (allocation clears, scene and table uploads)
-        CK(c, cudaEventRecord(c->ev_consumed, pass));
-        c->vox_started = true;
-    }
-    CK(c, cudaStreamWaitEvent(c->vox_stream, c->ev_consumed, 0));
-    c->stream = c->vox_stream;
-    int rc = f184_voxelize_accumulate_n(c, cam);
-    if (rc == F184_OK) rc = f184_normalise_n(c);
-    cudaError_t e = rc == F184_OK ? cudaEventRecord(c->ev_vox_done, c->vox_stream) : cudaSuccess;
-    c->stream = pass;
-    if (rc) return rc;
-    CK(c, e);
-    c->vox_pending = true;
-    return F184_OK;
-}
-
-// Normalise this rank's brick layers (the whole volume on one GPU).
+// Normalise this rank's bricks (the whole volume on one GPU).
 int f184_normalise_n(f184_ctx* c)
 {
     const int N = (int)c->cfg.grid_n;
@@ -673,9 +676,10 @@ int f184_normalise_n(f184_ctx* c)
     int rc = f184_stage_begin(c, F184_STAGE_NORMALISE);
     if (rc) return rc;
     CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_OCCUPIED, 0, 8, c->stream));
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_BRICKS, 0, 16, c->stream));        // BRICKS + the list cursor
+    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_BRICKS, 0, 8, c->stream));
+    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_COUNT, 0, 8, c->stream));          // the list cursor
     k_brick_compact<<<(n_own + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,
-                                                              c->counters_dev, n_own, NB * NB, G, c->cfg.rank % G);
+                                                              c->counters_dev, n_own, NB, G, c->cfg.rank % G);
     CK_LAUNCH(c);
     k_normalise_n<<<148 * 8, 256, 0, c->stream>>>(img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
                                                   img_ptr<uchar4>(c, F184_SLOT_VOX_ALBEDO), img_ptr<char4>(c, F184_SLOT_VOX_NORMAL),

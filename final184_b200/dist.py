@@ -11,7 +11,7 @@ Partitioning helpers
   row_ranges(H, n, tile)        screen bands, multiples of the tracer's 8-row tile
   view_ranges(n_views, n)       whole views per rank (probe batches)
 
-  brick_layer_owner(z, n)       owner of voxel layer z when the 8-voxel brick layers are dealt round-robin
+  brick_owner(x, y, z, n)       owner of the 8^3 brick holding voxel (x, y, z): bricks are dealt over the ranks along diagonals
 
 Frame schedules: see ShardedVoxelGI.
 """
@@ -67,10 +67,12 @@ def slab_ranges(n: int, nranks: int):
     return [(r * n // nranks, (r + 1) * n // nranks) for r in range(nranks)]
 
 
-def brick_layer_owner(z: int, nranks: int) -> int:
-    """Rank that owns voxel layer z: 8-voxel brick layers are dealt round-robin, owner = (z // 8) % nranks.  (Contiguous
-    slabs left the ranks holding Sponza's floor and arcades with 40 % of the bricks and the top slab with none.)"""
-    return (z // 8) % nranks
+def brick_owner(x: int, y: int, z: int, nranks: int) -> int:
+    """Rank that owns the 8^3 brick of voxel (x, y, z): owner = (x//8 + y//8 + z//8) % nranks, a diagonal interleave.
+    (Contiguous Z slabs left the ranks holding Sponza's floor and arcades with 40 % of the bricks and the top slab with none;
+    whole brick LAYERS dealt round-robin still gave the rank holding the floor layer 3x the bricks of the lightest rank at
+    8 GPUs — every axis-aligned sheet of bricks now lands evenly on all ranks.)"""
+    return (x // 8 + y // 8 + z // 8) % nranks
 
 
 def row_ranges(height: int, nranks: int, tile: int = 8):
@@ -138,6 +140,21 @@ class ShardedVoxelGI:
                 self.ctx.ipc_import(p, b, h)
         dist.barrier()
         self.connected = True
+
+    @staticmethod
+    def connect_loopback(shards):
+        """Several ranks inside ONE process (tests on a one-GPU box): cudaIpcOpenMemHandle refuses handles of the own process, so
+        the peers' buffers are installed as plain device pointers (f184_debug_get_ipc_ptr / f184_debug_set_peer).  The contexts
+        may share a device; their barrier kernels then wait for each other on the same GPU, so the caller must enqueue every
+        rank's frame before synchronising any of them."""
+        ptrs = [{b: s.ctx.ipc_ptr(b) for b in range(A.IPC_COUNT)} for s in shards]
+        for s in shards:
+            for p, other in enumerate(shards):
+                if other is s:
+                    continue
+                for b, ptr in ptrs[p].items():
+                    s.ctx.set_peer(p, b, ptr)
+            s.connected = True
 
     def describe(self):
         if self.mode == "single":

@@ -42,7 +42,8 @@ typedef enum f184_status {
     F184_ERR_CUDA = -3,
     F184_ERR_OUT_OF_MEMORY = -4,
     F184_ERR_NOT_READY = -5,       /* a required image/scene has not been provided */
-    F184_ERR_UNIMPLEMENTED = -6
+    F184_ERR_UNIMPLEMENTED = -6,
+    F184_ERR_PEER_TIMEOUT = -7     /* one NVLink box: a rank did not reach f184_peer_barrier in time (reported by the next synchronous call) */
 } f184_status;
 
 typedef enum f184_mode {
@@ -129,11 +130,15 @@ typedef enum f184_flags {
     F184_FLAG_GATHER_LINEAR = 8,   /* multi-GPU: f184_gather_volume also fills the linear RADIANCE / MIPS slots (tests) */
     F184_FLAG_DENSE_MIPS = 4,      /* mode N mips: dense chain, TMA-staged tiles for the large levels (default is the sparse
                                       brick-list path for levels 1-3 + one fused launch for the rest) */
-    F184_FLAG_NO_OVERLAP = 16      /* mode N: keep the voxelizer on the pass stream. Default, one GPU: voxelize + normalise of the next
-                                      frame run on an internal stream and overlap the previous frame's cone trace. Default, one NVLink
-                                      box: f184_voxelize_accumulate of the next frame (peer atomics, NVLink-bound) runs on that stream
-                                      beside the previous frame's gather + cone trace, starting behind the last f184_peer_barrier.
-                                      Every call that reads the voxelizer's outputs orders itself after it: results are identical */
+    F184_FLAG_NO_OVERLAP = 16,     /* mode N: every pass on the pass stream, one texture set.  Default: the frame pipeline — the accumulation of
+                                      frame f+2 (internal stream 1), normalise / inject / mips [/ barriers / gather] of frame f+1 (internal stream 2)
+                                      and the cone trace of frame f (pass stream) run side by side, ordered by events where data flows, the
+                                      texture-side volume double-buffered.  Every call that reads a stage's outputs orders itself after it:
+                                      results are identical */
+    F184_FLAG_SPEC_APPENDIX_B = 32 /* mode N cone tracer as SURVEY.md Appendix B.5 writes it: mip-LINEAR sampling (level 0 / level 1 blend below
+                                      lod 1, the hardware's linear mip filter above) and half-diameter steps.  Default is the amended spec of
+                                      DESIGN.md B.5: nearest mip level, one sample per voxel of the sampled level.  bench.py reports the image
+                                      difference between the two as `spec_delta` */
 } f184_flags;
 
 /* CViewConstants, Foreground/SceneGraph/SceneView.h:8-14 = GlobalConstants, Shader/EngineCommon.h:7-13. 208 B. */
@@ -229,7 +234,8 @@ typedef enum f184_counter_id {
     F184_COUNTER_OCCUPIED = 2,      /* occupied voxels after the last normalise */
     F184_COUNTER_KERNEL_LAUNCHES = 3, /* kernels launched by this context since creation */
     F184_COUNTER_BRICKS = 4,        /* touched 8^3 bricks in the last f184_voxelize (mode N) */
-    F184_COUNTER_COUNT = 5
+    F184_COUNTER_GATHER_BYTES = 5,  /* bytes the last f184_gather_volume fetched from the other ranks over NVLink */
+    F184_COUNTER_COUNT = 6
 } f184_counter_id;
 
 /* ---- lifetime: CMegaPipeline ctor + CreateVoxelizePass/CreateScreenPass, MegaPipeline.cpp:27-60, 470-590 */
@@ -381,6 +387,13 @@ int f184_microbench(f184_ctx* ctx, uint32_t which, double* out_per_second);
 /* ---- test hook: one level of the texture-side storage the cone tracer samples (dir < 0: the level-0 radiance
  * 3D array; dir 0..5: level `level`+1 of that direction's mipmapped 3D array); host pointer; synchronous */
 int f184_debug_read_array(f184_ctx* ctx, int32_t dir, uint32_t level, void* host, size_t bytes);
+
+/* ---- test hooks: several contexts of ONE process as the ranks of a box ("loopback ranks": cudaIpcOpenMemHandle refuses handles of
+ * the own process).  f184_debug_get_ipc_ptr returns the device pointer f184_ipc_export would share; f184_debug_set_peer installs such a
+ * pointer as rank `peer_rank`'s buffer in place of f184_ipc_import.  The test-suite drives the multi-rank schedule on a single GPU
+ * with them, and a barrier whose peer never arrives (F184_ERR_PEER_TIMEOUT). */
+int f184_debug_get_ipc_ptr(f184_ctx* ctx, uint32_t buffer, void** out_device_ptr);
+int f184_debug_set_peer(f184_ctx* ctx, uint32_t peer_rank, uint32_t buffer, void* device_ptr);
 
 #ifdef __cplusplus
 }

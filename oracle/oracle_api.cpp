@@ -5,6 +5,8 @@
 
 #include <algorithm>
 
+#include <omp.h>
+
 #include "oracle_common.h"
 
 using namespace orc;
@@ -302,15 +304,40 @@ int orc_mips_n(f184o_ctx*);
 int orc_trace_n(f184o_ctx*, const f184_trace_constants*);
 int orc_trace_views_n(f184o_ctx*, const f184_trace_constants*, uint32_t, uint32_t, uint32_t);
 
+// same table checks as libf184 (f184_api.cu check_tables): the voxelizers index materials[tri_mat] and textures[mat.tex] unguarded
+static int check_tables(f184o_ctx* c)
+{
+    uint32_t max_mat = 0;
+    for (uint16_t m : c->tri_mat) if (m > max_mat) max_mat = m;
+    if (max_mat >= c->materials.size()) { c->err = "voxelize: a triangle's material has no material_set entry"; return F184_ERR_INVALID_ARGUMENT; }
+    for (const auto& m : c->materials)
+        if (m.use_textures && m.tex >= 0 && ((size_t)m.tex >= c->textures.size() || c->textures[m.tex].levels.empty()))
+        { c->err = "voxelize: a material uses a texture that has not been uploaded"; return F184_ERR_NOT_READY; }
+    return F184_OK;
+}
 int f184o_voxelize(f184o_ctx* c, const f184_view_constants* cam)
 {
     if (!c || !cam) return F184_ERR_INVALID_ARGUMENT;
     if (!c->n_tris) { c->err = "no scene"; return F184_ERR_NOT_READY; }
+    if (int rc = check_tables(c)) return rc;
     return c->cfg.mode == F184_MODE_REFERENCE ? orc_voxelize_r(c, cam) : orc_voxelize_n(c, cam);
+}
+// threads the oracle's parallel loops actually run on (bench.py prints it beside the CPU baseline); set > 0 first asks for that many
+int f184o_omp_threads(int set)
+{
+    if (set > 0) omp_set_num_threads(set);
+    int n = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+    return n;
 }
 int f184o_voxelize_accumulate(f184o_ctx* c, const f184_view_constants* cam)
 {
     if (!c || !cam || c->cfg.mode != F184_MODE_NORTHSTAR) return F184_ERR_INVALID_ARGUMENT;
+    if (int rc = check_tables(c)) return rc;
     return orc_voxelize_accumulate_n(c, cam);
 }
 int f184o_normalise(f184o_ctx* c)

@@ -493,6 +493,7 @@ struct ConeCtx
     M4 w2v;
     float h, max_dist, exposure;
     uint64_t samples;
+    bool spec_b;                 // F184_FLAG_SPEC_APPENDIX_B: SURVEY.md Appendix B.5 as written (mip-linear, half-diameter steps)
 };
 
 // direction-weighted fetch from the six-direction chain at mip index `l` (0 = level 1), nearest level: one
@@ -511,6 +512,21 @@ V4 fetch_dir(const ConeCtx& C, const float w[3], const int face[3], float qx, fl
         r = {r.x + w[a] * s0.x, r.y + w[a] * s0.y, r.z + w[a] * s0.z, r.w + w[a] * s0.w};
     }
     return r;
+}
+
+// Appendix-B sampling above lod 1: the hardware's linear mip filter between level floor(lod) and the next one of the
+// six-direction chain (level fraction with 8 fractional bits, like the texel weights); lodp = lod - 1 indexes the chain
+V4 fetch_dir_linear(const ConeCtx& C, const float w[3], const int face[3], float qx, float qy, float qz, float lodp)
+{
+    const int maxl = (int)C.dir[0].size() - 1;
+    if (lodp >= (float)maxl) return fetch_dir(C, w, face, qx, qy, qz, maxl);
+    const float lf = floorf(lodp);
+    const int l = (int)lf;
+    const float f = q8(lodp - lf);
+    V4 a = fetch_dir(C, w, face, qx, qy, qz, l);
+    if (f == 0.0f) return a;
+    V4 b = fetch_dir(C, w, face, qx, qy, qz, l + 1);
+    return {a.x + f * (b.x - a.x), a.y + f * (b.y - a.y), a.z + f * (b.z - a.z), a.w + f * (b.w - a.w)};
 }
 
 // one cone; returns radiance (world units) including the sky term for the unoccluded remainder
@@ -537,13 +553,25 @@ V3 trace_cone(ConeCtx& C, V3 origin, V3 dir, float tan_half)
         const float qx = q4.x * 0.5f + 0.5f, qy = q4.y * 0.5f + 0.5f, qz = q4.z;
         if (!(qx >= 0.0f && qx <= 1.0f && qy >= 0.0f && qy <= 1.0f && qz >= 0.0f && qz <= 1.0f)) break;
         C.samples++;
-        // nearest level: 0 = the isotropic radiance volume, L >= 1 = the six-direction chain
-        const int L = (int)floorf(lod + 0.5f);
-        V4 s = (L <= 0) ? fetch_trilinear(C.level0, qx, qy, qz) : fetch_dir(C, w, face, qx, qy, qz, L - 1);
+        V4 s;
+        if (C.spec_b)
+        {   // SURVEY.md Appendix B.5 as written: mip-linear — below lod 1 between the isotropic level 0 and the directional level 1
+            if (lod < 1.0f)
+            {
+                V4 a = fetch_trilinear(C.level0, qx, qy, qz), b = fetch_dir(C, w, face, qx, qy, qz, 0);
+                s = {a.x + lod * (b.x - a.x), a.y + lod * (b.y - a.y), a.z + lod * (b.z - a.z), a.w + lod * (b.w - a.w)};
+            }
+            else s = fetch_dir_linear(C, w, face, qx, qy, qz, lod - 1.0f);
+        }
+        else
+        {   // nearest level: 0 = the isotropic radiance volume, L >= 1 = the six-direction chain
+            const int L = (int)floorf(lod + 0.5f);
+            s = (L <= 0) ? fetch_trilinear(C.level0, qx, qy, qz) : fetch_dir(C, w, face, qx, qy, qz, L - 1);
+        }
         const float k = 1.0f - A;
         acc = {acc.x + k * s.x, acc.y + k * s.y, acc.z + k * s.z};
         A += k * s.w;
-        t += diam;                   // one sample per voxel of the level along the axis
+        t += C.spec_b ? 0.5f * diam : diam;      // amended spec: one sample per voxel of the level along the axis
     }
     const float rem = std::max(0.0f, 1.0f - A);
     return {acc.x * C.exposure + 0.7f * 0.4f * rem, acc.y * C.exposure + 0.8f * 0.4f * rem, acc.z * C.exposure + 1.0f * 0.4f * rem};
@@ -591,6 +619,7 @@ extern "C" int orc_trace_n(f184o_ctx* c, const f184_trace_constants* k)
     C0.max_dist = c->cfg.cone_max_distance;
     C0.exposure = exposure_of(c, &k->sun);
     C0.samples = 0;
+    C0.spec_b = (c->cfg.flags & F184_FLAG_SPEC_APPENDIX_B) != 0;
     const M4 InvProj = load_m4(k->view.InvProj), InvModelView = load_m4(k->ext.InvModelView);
     const M4 prevModelView = load_m4(k->prev.PrevModelView), prevProjection = load_m4(k->prev.PrevProjection);
     const float* depthp = image_ptr<float>(c, F184_SLOT_DEPTH);

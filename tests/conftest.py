@@ -19,7 +19,7 @@ def oracle_lib():
     from final184_b200 import api as A
     so = os.path.join(REPO, "oracle", "_build", "libf184_oracle.so")
     r = subprocess.run(["make", "-C", os.path.join(REPO, "oracle")], capture_output=True, text=True)
-    if r.returncode != 0 and not os.path.exists(so):
+    if r.returncode != 0:        # never fall back to a stale .so: the parity tests would then pass against an out-of-date checker
         pytest.fail("oracle build failed:\n" + r.stdout + r.stderr)
     return A.Library(so, "f184o_", product=False)
 

@@ -1,0 +1,229 @@
+"""Worker for tests/test_gpu_loopback.py: the multi-rank slab schedule (include/f184.h "one NVLink box") driven on ONE GPU.
+
+G contexts of this process act as the ranks of a box ("loopback ranks": the peers' buffers are installed as plain device
+pointers, final184_b200.dist.ShardedVoxelGI.connect_loopback).  Everything the real schedule does happens — triangle-range
+voxelization with the reduction into the owner's accumulators (peer reductions at system scope, here on the same device), the
+device-side flag barriers (the ranks' barrier kernels wait for each other while they share the GPU), owner-side normalise /
+inject / mips with the packed export records, the gather, the level-0 skip, the three-stream frame pipeline — and every rank's
+volume, texture storage and image rows must equal the frame one context computes alone, bit for bit.
+
+Run with CUDA_DEVICE_MAX_CONNECTIONS=32 so that every stream has its own hardware queue (a kernel that waits in a barrier must
+never sit in front of another rank's work).  Every rank's frame is enqueued before any rank is synchronised.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+from final184_b200 import api as A, dist as D, scene as S   # noqa: E402
+from final184_b200.fixture import frame_inputs               # noqa: E402
+
+SLOTS = ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_MATERIAL, "material"), (A.SLOT_SHADOW, "shadow"))
+
+
+def make_box(G, N, W, H, SH, sc, cams, fi, flags):
+    ranks = [D.ShardedVoxelGI(N, W, H, shadow_res=SH, device=0, rank=r, nranks=G, scene=sc, voxel_cam=cams["voxel"], mode="slab", flags=flags)
+             for r in range(G)]
+    for g in ranks:
+        for slot, key in SLOTS:
+            g.ctx.upload(slot, fi[key])
+    D.ShardedVoxelGI.connect_loopback(ranks)
+    return ranks
+
+
+def box_frame(ranks, cam, k):
+    for g in ranks:                 # enqueue every rank's frame before synchronising any of them
+        g.frame(cam, k)
+
+
+def box_sync(ranks):
+    for g in ranks:
+        g.ctx.sync()
+
+
+def single(N, W, H, SH, sc, fi, flags=0):
+    one = A.VoxelGI(N, W, H, A.MODE_NORTHSTAR, shadow_res=SH, device=0, flags=flags)
+    one.upload_scene(sc)
+    for slot, key in SLOTS:
+        one.upload(slot, fi[key])
+    return one
+
+
+def one_frame(one, cam, k):
+    one.voxelize(cam); one.inject(k); one.build_mips(); one.trace_indirect(k)
+
+
+def compare_arrays(bad, tag, g, one, N, level0=True):
+    if level0 and not np.array_equal(g.ctx.read_array(-1, 0, N), one.read_array(-1, 0, N)):
+        bad.append(f"{tag}: level-0 array")
+    m, lvl = N // 2, 0
+    while m >= 1:
+        for d in range(6):
+            if not np.array_equal(g.ctx.read_array(d, lvl, m), one.read_array(d, lvl, m)):
+                bad.append(f"{tag}: array dir {d} level {lvl + 1}")
+        m //= 2; lvl += 1
+
+
+def compare_rows(bad, tag, g, one):
+    m = g.own_rows_mask()
+    a, b = g.ctx.readback(A.SLOT_INDIRECT_OUT)[m], one.readback(A.SLOT_INDIRECT_OUT)[m]
+    if not np.array_equal(a.view(np.uint16), b.view(np.uint16)):
+        bad.append(f"{tag}: own image tile rows")
+
+
+def set_ranges(ranks, one, lo, hi):
+    """triangles [lo, hi) of the scene: each rank takes its share, the single context all of them"""
+    for g in ranks:
+        f0, cnt = g.tri_range
+        a, b = max(f0, lo), min(f0 + cnt, hi)
+        g.ctx.set_triangle_range(a, max(0, b - a))
+    one.set_triangle_range(lo, hi - lo)
+
+
+def run_box(G, sc, cams, N, W, H, SH, bad, sponza=False):
+    tag = f"G={G} {'sponza' if sponza else 'procedural'} {N}^3"
+    fi = frame_inputs(sc, cams["main"], cams["shadow"], W, H, SH, 0, cache=False)
+    k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
+    T = sc.n_tris
+    # ---- (1) full comparison: F184_FLAG_GATHER_LINEAR also fills the linear slots and always moves level 0
+    ranks = make_box(G, N, W, H, SH, sc, cams, fi, A.FLAG_GATHER_LINEAR)
+    one = single(N, W, H, SH, sc, fi)
+    for frame, (lo, hi) in enumerate(((0, T), (0, T), (0, T // 2))):      # the last frame empties bricks: they must be cleared on every rank
+        set_ranges(ranks, one, lo, hi)
+        box_frame(ranks, cams["voxel"], k)
+        one_frame(one, cams["voxel"], k)
+        box_sync(ranks); one.sync()
+        for r, g in enumerate(ranks):
+            t = f"{tag} frame {frame} rank {r}"
+            if not np.array_equal(g.ctx.readback(A.SLOT_RADIANCE), one.readback(A.SLOT_RADIANCE)): bad.append(t + ": radiance")
+            if not np.array_equal(g.ctx.readback(A.SLOT_MIPS), one.readback(A.SLOT_MIPS)): bad.append(t + ": mips")
+            compare_arrays(bad, t, g, one, N)
+            compare_rows(bad, t, g, one)
+    frags = sum(g.ctx.counter(A.COUNTER_FRAGMENTS) for g in ranks)
+    if frags != one.counter(A.COUNTER_FRAGMENTS): bad.append(f"{tag}: fragments {frags} vs {one.counter(A.COUNTER_FRAGMENTS)}")
+    for g in ranks: g.close()
+    if sponza:
+        one.close()
+        return
+    # ---- (2) the product path: level 0 travels only when a cone of the rank's rows samples it.  The fixture's materials are
+    # rough (roughness 1: no cone reads level 0); a glossy G-buffer (roughness 0.2) makes the specular cones read it.
+    ranks = make_box(G, N, W, H, SH, sc, cams, fi, 0)
+    glossy = fi["material"].copy(); glossy[..., 1] = 51
+    schedule = [("rough", 0, T), ("rough", 0, T), ("glossy", 0, T), ("rough", T // 3, T), ("rough", 0, T // 2), ("glossy", T // 4, T), ("glossy", 0, T)]
+    for frame, (mat, lo, hi) in enumerate(schedule):
+        set_ranges(ranks, one, lo, hi)
+        m_ = glossy if mat == "glossy" else fi["material"]
+        for c in [g.ctx for g in ranks] + [one]:
+            c.upload(A.SLOT_MATERIAL, m_)
+        box_frame(ranks, cams["voxel"], k)
+        one_frame(one, cams["voxel"], k)
+        box_sync(ranks); one.sync()
+        for r, g in enumerate(ranks):
+            t = f"{tag} skip-path frame {frame} ({mat}) rank {r}"
+            compare_arrays(bad, t, g, one, N, level0=(mat == "glossy"))
+            compare_rows(bad, t, g, one)
+    # ---- (3) the frame pipeline: frames back to back, no host synchronisation in between, a different triangle range each
+    # (every frame's volume differs, emptied bricks must be cleared in BOTH texture sets); read-backs staged asynchronously
+    for c in [g.ctx for g in ranks] + [one]:
+        c.upload(A.SLOT_MATERIAL, fi["material"])
+    spans = [(0, T), (0, T // 2), (T // 3, T), (0, T), (T // 2, T), (0, T // 4), (0, T)]
+    want = []
+    for lo, hi in spans:
+        one.set_triangle_range(lo, hi - lo)
+        one_frame(one, cams["voxel"], k)
+        want.append(one.readback(A.SLOT_INDIRECT_OUT).copy())
+    if np.array_equal(want[0], want[1]): bad.append(f"{tag}: back-to-back frames do not differ")
+    nbytes = ranks[0].ctx.image_info(A.SLOT_INDIRECT_OUT).size_bytes
+    hosts = [[torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in spans] for _ in ranks]
+    for i, (lo, hi) in enumerate(spans):
+        set_ranges(ranks, one, lo, hi)
+        box_frame(ranks, cams["voxel"], k)
+        for r, g in enumerate(ranks):
+            g.ctx.readback_async_ptr(A.SLOT_INDIRECT_OUT, hosts[r][i].data_ptr(), nbytes)
+    box_sync(ranks)
+    for r, g in enumerate(ranks):
+        m = g.own_rows_mask()
+        for i in range(len(spans)):
+            got = hosts[r][i].numpy().view(np.uint16).reshape(H, W, 4)
+            if not np.array_equal(got[m], want[i].view(np.uint16).reshape(H, W, 4)[m]): bad.append(f"{tag}: back-to-back frame {i} rank {r}: own image tile rows")
+    for g in ranks: g.close()
+    one.close()
+
+
+def run_single_pipeline(sc, cams, bad):
+    """one GPU: pipelined frames back to back == the same frames with every pass on one stream (F184_FLAG_NO_OVERLAP)"""
+    N, W, H, SH = 64, 160, 96, 256
+    fi = frame_inputs(sc, cams["main"], cams["shadow"], W, H, SH, 0, cache=False)
+    k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
+    T = sc.n_tris
+    spans = [(0, T), (0, T // 2), (T // 3, T), (0, T), (T // 2, T), (0, T // 4), (0, T), (0, T)]
+    outs = []
+    for flags in (A.FLAG_NO_OVERLAP, 0):
+        c = single(N, W, H, SH, sc, fi, flags)
+        nbytes = c.image_info(A.SLOT_INDIRECT_OUT).size_bytes
+        hosts = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in spans]
+        for i, (lo, hi) in enumerate(spans):
+            c.set_triangle_range(lo, hi - lo)
+            one_frame(c, cams["voxel"], k)
+            c.readback_async_ptr(A.SLOT_INDIRECT_OUT, hosts[i].data_ptr(), nbytes)
+        c.sync()
+        outs.append([h.numpy().copy() for h in hosts])
+        # the volume of the last frame, both storages
+        outs[-1].append(c.readback(A.SLOT_MIPS).copy().view(np.uint8).reshape(-1))
+        outs[-1].append(c.read_array(0, 0, N // 2).copy().reshape(-1))
+        c.close()
+    for i, (a, b) in enumerate(zip(*outs)):
+        if not np.array_equal(a, b): bad.append(f"single-GPU pipeline: output {i} differs from the one-stream frames")
+
+
+def run_barrier_timeout(bad):
+    """a barrier whose peer never arrives must surface as F184_ERR_PEER_TIMEOUT from the next synchronous call, not as a silently
+    wrong volume (F184_BARRIER_TIMEOUT_MS shortens the 5 s default)"""
+    N, W, H = 32, 32, 16
+    sc = S.procedural_scene(seed=2)
+    cam = S.fixture_constants("voxel")
+    c = A.VoxelGI(N, W, H, A.MODE_NORTHSTAR, shadow_res=64, device=0, rank=0, nranks=2)
+    c.upload_scene(sc)
+    sizes = {A.IPC_ACCUM_COLOR: N ** 3 * 16, A.IPC_ACCUM_NORMAL: N ** 3 * 16, A.IPC_BRICK_FLAGS: (N // 8) ** 3 * 4, A.IPC_EXPORT: (N // 8) ** 3 * 4096,
+             A.IPC_COUNTERS: 128, A.IPC_BRICK_LIST: (N // 8) ** 3 * 4, A.IPC_SYNC: 64}
+    fake = {b: torch.zeros(n, dtype=torch.uint8, device="cuda:0") for b, n in sizes.items()}     # a "peer" nobody runs
+    for b, t in fake.items():
+        c.ipc_ptr(b)
+        c.set_peer(1, b, t.data_ptr())
+    c.voxelize_accumulate(cam)
+    c.peer_barrier()
+    try:
+        c.sync()
+        bad.append("barrier timeout: f184_sync returned OK although the peer never arrived")
+    except A.F184Error as e:
+        if "(-7)" not in str(e) or "peer" not in str(e): bad.append(f"barrier timeout: unexpected error {e}")
+    c.sync()      # reported once: the context stays usable
+    c.close()
+
+
+def main():
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    torch.cuda.set_device(0)
+    sc = S.procedural_scene(seed=1)
+    cams = {n: S.fixture_constants(n) for n in ("main", "shadow", "voxel")}
+    bad = []
+    if which in ("all", "timeout"):
+        run_barrier_timeout(bad)
+    if which in ("all", "single"):
+        run_single_pipeline(sc, cams, bad)
+    if which in ("all", "box2"):
+        run_box(2, sc, cams, 64, 160, 96, 256, bad)
+    if which in ("all", "box4"):
+        run_box(4, sc, cams, 64, 160, 96, 256, bad)
+    if which in ("all", "sponza") and S.sponza_available():
+        run_box(4, S.load_sponza(), cams, 256, 320, 184, 1024, bad, sponza=True)
+    print(("OK" if not bad else "MISMATCH " + "; ".join(bad[:8])) + f" [{which}]", flush=True)
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()

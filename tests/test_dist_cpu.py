@@ -41,7 +41,14 @@ def test_slab_row_view_ranges():
         assert rr[0][0] == 0 and rr[-1][1] == h and all(rr[i][1] == rr[i + 1][0] for i in range(n - 1))
         assert all(y0 % 8 == 0 for y0, _ in rr)
     assert D.view_ranges(64, 8) == [(8 * r, 8 * r + 8) for r in range(8)]
-    assert [D.brick_layer_owner(z, 4) for z in (0, 7, 8, 31, 32, 511)] == [0, 0, 1, 3, 0, 3]
+    assert [D.brick_owner(0, 0, z, 4) for z in (0, 7, 8, 31, 32, 511)] == [0, 0, 1, 3, 0, 3]
+    assert D.brick_owner(8, 16, 24, 4) == 2 and D.brick_owner(7, 7, 7, 8) == 0
+    # every axis-aligned sheet of bricks is dealt evenly
+    import numpy as np
+    b = np.arange(64)
+    for fixed in range(3):
+        own = (b[:, None] + b[None, :] + 5) % 8
+        assert (np.bincount(own.ravel(), minlength=8) == 512).all()
 
 
 def test_triangle_weights_track_projected_area(proc_scene, cams):

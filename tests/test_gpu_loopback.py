@@ -1,0 +1,39 @@
+"""The multi-rank schedule on ONE GPU (tests/loopback_worker.py): G contexts of one process as the ranks of a box.  This is
+the N > 1 parity evidence a one-GPU box can produce — tests/test_gpu_multi.py repeats it across real GPUs over NVLink when the box
+has them.  Each case runs in its own process with one hardware queue per stream (CUDA_DEVICE_MAX_CONNECTIONS=32)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(which, timeout=600, **env):
+    e = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", **env)
+    r = subprocess.run([sys.executable, os.path.join(REPO, "tests", "loopback_worker.py"), which], capture_output=True, text=True, timeout=timeout, env=e)
+    assert r.returncode == 0 and f"OK [{which}]" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_pipelined_frames_equal_one_stream_frames():
+    """one context: eight frames back to back through the three-stream pipeline (double-buffered texture sets) == F184_FLAG_NO_OVERLAP"""
+    run("single")
+
+
+def test_two_loopback_ranks_equal_one_context():
+    """volumes, both texture sets, image rows; the level-0 skip of the gather incl. its rough -> glossy transitions; pipelined frames"""
+    run("box2")
+
+
+def test_four_loopback_ranks_equal_one_context():
+    run("box4")
+
+
+def test_four_loopback_ranks_sponza_256():
+    run("sponza")
+
+
+def test_barrier_with_a_missing_peer_is_an_error():
+    run("timeout", F184_BARRIER_TIMEOUT_MS="300")

@@ -234,16 +234,19 @@ def test_trace_bands_compose(oracle_lib, proc_scene, cams):
     assert np.array_equal(out.view(np.uint16), full.view(np.uint16))
 
 
-def test_cone_trace_equals_an_independent_float64_restatement(oracle_lib, proc_scene, cams):
+@pytest.mark.parametrize("spec_b", [False, True], ids=["amended", "appendix_b"])
+def test_cone_trace_equals_an_independent_float64_restatement(oracle_lib, proc_scene, cams, spec_b):
     """DESIGN.md §3 B.5 written out again in plain Python / float64, straight from the prose — tangent frame, 6 + 1 cones,
     nearest-level direction-weighted trilinear sampling with zero border, front-to-back compositing, one sample per voxel of
     the level, sky term, Schlick-weighted specular, the temporal blend against an empty history — over the volumes the oracle
     built.  The oracle works in fp32 with 8-bit filter weights, so agreement is asserted per image (5e-3 rel. L2) and on the
-    cone-sample count (a sample is gained or lost only where a float comparison sits on its edge)."""
+    cone-sample count (a sample is gained or lost only where a float comparison sits on its edge).
+    spec_b: the same for SURVEY.md Appendix B.5 as written (F184_FLAG_SPEC_APPENDIX_B): mip-linear sampling — a blend of the isotropic
+    level 0 and the directional level 1 below lod 1, of two adjacent levels of the chain above — and half-diameter steps."""
     n, w, h, sh = 32, 24, 16, 128
     fi = frame_inputs(proc_scene, cams["main"], cams["shadow"], w, h, sh, 0, cache=False)
     k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], w, h, 0, True)
-    o = A.VoxelGI(grid_n=n, width=w, height=h, mode=A.MODE_NORTHSTAR, shadow_res=sh, lib=oracle_lib)
+    o = A.VoxelGI(grid_n=n, width=w, height=h, mode=A.MODE_NORTHSTAR, shadow_res=sh, lib=oracle_lib, flags=A.FLAG_SPEC_APPENDIX_B if spec_b else 0)
     o.upload_scene(proc_scene)
     for slot, key in ((A.SLOT_DEPTH, "depth"), (A.SLOT_NORMALS, "normals"), (A.SLOT_SHADOW, "shadow"), (A.SLOT_MATERIAL, "material")):
         o.upload(slot, fi[key])
@@ -297,15 +300,22 @@ def test_cone_trace_equals_an_independent_float64_restatement(oracle_lib, proc_s
             if (q < 0).any() or (q > 1).any():
                 break
             n_samples += 1
-            level = int(np.floor(np.log2(diam / hvox) + 0.5))
-            if level <= 0:
-                s = trilinear(rad, q)
+            lod = np.log2(diam / hvox)
+            directional = lambda lv: sum(du[a] ** 2 * trilinear(lv[2 * a + (1 if du[a] < 0 else 0)], q) for a in range(3) if du[a] != 0)
+            if spec_b:
+                if lod < 1.0:
+                    s = (1 - lod) * trilinear(rad, q) + lod * directional(levels[0])
+                else:
+                    lp = min(lod - 1.0, len(levels) - 1.0)
+                    l0_ = int(np.floor(lp))
+                    f_ = lp - l0_
+                    s = directional(levels[l0_]) if f_ == 0 else (1 - f_) * directional(levels[l0_]) + f_ * directional(levels[l0_ + 1])
             else:
-                lv = levels[min(level, len(levels)) - 1]
-                s = sum(du[a] ** 2 * trilinear(lv[2 * a + (1 if du[a] < 0 else 0)], q) for a in range(3) if du[a] != 0)
+                level = int(np.floor(lod + 0.5))
+                s = trilinear(rad, q) if level <= 0 else directional(levels[min(level, len(levels)) - 1])
             acc += (1 - alpha) * s[:3]
             alpha += (1 - alpha) * s[3]
-            t += diam
+            t += 0.5 * diam if spec_b else diam
         return acc * exposure + np.array([0.7, 0.8, 1.0]) * 0.4 * max(0.0, 1 - alpha)
 
     diffuse = [(0.0, 0.0, 1.0, 0.25)] + [(np.sin(np.pi / 3) * np.cos(2 * np.pi * j / 5), np.sin(np.pi / 3) * np.sin(2 * np.pi * j / 5), 0.5, 0.15) for j in range(5)]
