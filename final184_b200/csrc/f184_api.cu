@@ -1,6 +1,7 @@
 // f184_api.cu — the C-ABI of libf184 (include/f184.h): context, scene/texture upload, image slots,
 // stream/interop plumbing, stage timing.  The passes themselves live in the mode_*.cu / gtao.cu / blur.cu
 // translation units.  There is deliberately no host fallback anywhere in this library.
+#include <algorithm>
 #include <cstdarg>
 
 #include "f184_internal.h"
@@ -254,6 +255,41 @@ int f184_prepare_frame(f184_ctx* c)
     }
     CK(c, cudaStreamSynchronize(c->stream));
     c->prepared = true;
+    return F184_OK;
+}
+
+__global__ void k_zero_counters(unsigned long long* __restrict__ counters, uint32_t mask)
+{
+    if ((mask >> threadIdx.x) & 1u) counters[threadIdx.x] = 0ull;
+}
+__global__ void __launch_bounds__(256) k_fill_words(uint32_t* __restrict__ p, uint32_t v, size_t n_words)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)
+    {
+        uint4* p4 = reinterpret_cast<uint4*>(p);
+        const size_t n4 = n_words / 4;
+        const uint4 v4 = make_uint4(v, v, v, v);
+        for (size_t j = i; j < n4; j += stride) p4[j] = v4;
+        for (size_t j = n4 * 4 + i; j < n_words; j += stride) p[j] = v;
+    }
+    else
+        for (; i < n_words; i += stride) p[i] = v;
+}
+int f184_zero_counters(f184_ctx* c, uint32_t mask)
+{
+    k_zero_counters<<<1, 32, 0, c->stream>>>(c->counters_dev, mask);
+    CK_LAUNCH(c);
+    return F184_OK;
+}
+int f184_fill_async(f184_ctx* c, void* ptr, uint32_t value32, size_t bytes, cudaStream_t stream)
+{
+    const size_t n_words = bytes / 4;
+    if (!n_words) return F184_OK;
+    const unsigned blocks = (unsigned)std::min<size_t>((n_words / 4 + 255) / 256 + 1, 148 * 8);
+    k_fill_words<<<blocks, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(ptr), value32, n_words);
+    CK_LAUNCH(c);
     return F184_OK;
 }
 

@@ -230,6 +230,10 @@ int f184_volume_release(f184_ctx* c, VolumeSet* v);      // pass stream: a reade
 int f184_check_device_errors(f184_ctx* c);               // sticky device error word -> F184_ERR_* (synchronous callers only)
 int f184_sync_tables(f184_ctx* c);
 int f184_prepare_frame(f184_ctx* c);                     // first-use allocations of a north-star frame, before anything is enqueued
+// Per-frame clears are KERNELS, not cudaMemsetAsync: a memset travels through the copy-engine queue, which all streams of a process
+// share — one that waits (in stream order) behind a peer barrier would hold up every other stream's memsets behind it.
+int f184_zero_counters(f184_ctx* c, uint32_t mask);                       // zero counters_dev[i] for every bit i of mask, on c->stream
+int f184_fill_async(f184_ctx* c, void* ptr, uint32_t value32, size_t bytes, cudaStream_t stream);   // bytes: multiple of 4
 int f184_stage_begin(f184_ctx* c, int stage);
 int f184_stage_end(f184_ctx* c, int stage);
 template <class T> static inline T* img_ptr(f184_ctx* c, int slot) { return reinterpret_cast<T*>(c->img[slot].ptr); }

@@ -350,7 +350,7 @@ int f184_gather_n(f184_ctx* c)
     {   // does level 0 have to travel this frame?  (F184_FLAG_GATHER_LINEAR — the tests' full comparison — and F184_GATHER_LEVEL0=1 force it)
         static const bool force_env = [] { const char* e = getenv("F184_GATHER_LEVEL0"); return e && atoi(e) != 0; }();
         const bool force = force_env || (c->cfg.flags & F184_FLAG_GATHER_LINEAR);
-        CK(c, cudaMemsetAsync(c->dev_state + F184_DEV_NEED_L0, force ? 0x01 : 0, 4, c->stream));     // 0x01010101 = non-zero = needed
+        if ((rc = f184_fill_async(c, c->dev_state + F184_DEV_NEED_L0, force ? 1u : 0u, 4, c->stream))) return rc;
         if (!force)
         {
             NeedArgs A{};

@@ -295,9 +295,8 @@ int f184_trace_n(f184_ctx* c, const f184_trace_constants* k)
     if (P.tile_stride > 1 && (P.y0 & 7)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "trace: row range must start on a multiple of 8 when tiles are interleaved");
     rc = f184_stage_begin(c, F184_STAGE_TRACE);
     if (rc) return rc;
-    if (k->reset_history)
-        CK(c, cudaMemsetAsync(c->img[F184_SLOT_INDIRECT_HISTORY].ptr, 0, c->img[F184_SLOT_INDIRECT_HISTORY].desc.size_bytes, c->stream));
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_MARCH_STEPS, 0, 8, c->stream));
+    if (k->reset_history && (rc = f184_fill_async(c, c->img[F184_SLOT_INDIRECT_HISTORY].ptr, 0u, c->img[F184_SLOT_INDIRECT_HISTORY].desc.size_bytes, c->stream))) return rc;
+    if ((rc = f184_zero_counters(c, 1u << F184_COUNTER_MARCH_STEPS))) return rc;
     if (grid_y && (rc = trace_launch(c, P, grid_y, c->stream))) return rc;
     rc = f184_stage_end(c, F184_STAGE_TRACE);
     if (rc) return rc;
@@ -327,7 +326,7 @@ int f184_trace_views_n(f184_ctx* c, const f184_trace_constants* ks, uint32_t vie
     if (rc) return rc;
     rc = f184_stage_begin(c, F184_STAGE_TRACE);
     if (rc) return rc;
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_MARCH_STEPS, 0, 8, c->stream));
+    if ((rc = f184_zero_counters(c, 1u << F184_COUNTER_MARCH_STEPS))) return rc;
     CK(c, cudaEventRecord(c->ev_view_fork, c->stream));
     const int ns = count < (uint32_t)F184_VIEW_STREAMS ? (int)count : F184_VIEW_STREAMS;
     for (int i = 0; i < ns; i++) CK(c, cudaStreamWaitEvent(c->view_streams[i], c->ev_view_fork, 0));
@@ -338,8 +337,7 @@ int f184_trace_views_n(f184_ctx* c, const f184_trace_constants* ks, uint32_t vie
         ConeParams P{};
         trace_params(c, *vs, &ks[v], v * view_h, view_h, P);
         P.y0 = v * view_h; P.y1 = P.y0 + view_h; P.tile0 = 0; P.tile_stride = 1;
-        if (ks[v].reset_history)
-            CK(c, cudaMemsetAsync(img_ptr<uint8_t>(c, F184_SLOT_INDIRECT_HISTORY) + (size_t)P.y0 * row_bytes, 0, (size_t)view_h * row_bytes, st));
+        if (ks[v].reset_history && (rc = f184_fill_async(c, img_ptr<uint8_t>(c, F184_SLOT_INDIRECT_HISTORY) + (size_t)P.y0 * row_bytes, 0u, (size_t)view_h * row_bytes, st))) return rc;
         if ((rc = trace_launch(c, P, (view_h + 7) / 8, st))) return rc;
     }
     for (int i = 0; i < ns; i++)

@@ -645,8 +645,7 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
     int rc = f184_stage_begin(c, F184_STAGE_VOXELIZE);
     if (rc) return rc;
     // device words after the public counters: [COUNT] brick-list cursor, [COUNT+1] voxelizer queue state, [COUNT+2] mip tail ticket
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_FRAGMENTS, 0, 8, c->stream));
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_COUNT + 1, 0, 8, c->stream));
+    if ((rc = f184_zero_counters(c, (1u << F184_COUNTER_FRAGMENTS) | (1u << (F184_COUNTER_COUNT + 1))))) return rc;
     if (end > first)
     {
         A.pos = c->pos; A.nrm = c->nrm; A.uv = c->uv; A.idx = c->idx; A.tri_mat = c->tri_mat; A.tri_model = c->tri_model;
@@ -675,9 +674,7 @@ int f184_normalise_n(f184_ctx* c)
     const uint32_t n_own = (NB / G) * NB * NB;
     int rc = f184_stage_begin(c, F184_STAGE_NORMALISE);
     if (rc) return rc;
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_OCCUPIED, 0, 8, c->stream));
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_BRICKS, 0, 8, c->stream));
-    CK(c, cudaMemsetAsync(c->counters_dev + F184_COUNTER_COUNT, 0, 8, c->stream));          // the list cursor
+    if ((rc = f184_zero_counters(c, (1u << F184_COUNTER_OCCUPIED) | (1u << F184_COUNTER_BRICKS) | (1u << F184_COUNTER_COUNT)))) return rc;   // COUNT = the list cursor
     k_brick_compact<<<(n_own + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,
                                                               c->counters_dev, n_own, NB, G, c->cfg.rank % G);
     CK_LAUNCH(c);

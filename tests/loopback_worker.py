@@ -8,7 +8,9 @@ inject / mips with the packed export records, the gather, the level-0 skip, the 
 volume, texture storage and image rows must equal the frame one context computes alone, bit for bit.
 
 Run with CUDA_DEVICE_MAX_CONNECTIONS=32 so that every stream has its own hardware queue (a kernel that waits in a barrier must
-never sit in front of another rank's work).  Every rank's frame is enqueued before any rank is synchronised.
+never sit in front of another rank's work) and CUDA_MODULE_LOADING=EAGER (the first launch of a lazily loaded kernel waits for the
+device to drain, which a barrier waiting for a rank not yet enqueued never lets happen).  Every rank's frame is enqueued before
+any rank is synchronised.  None of this concerns the real schedule: one process per GPU, every rank with its own host thread.
 """
 import os
 import sys
@@ -208,6 +210,8 @@ def run_barrier_timeout(bad):
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.cuda.set_device(0)
+    if os.environ.get("CUDA_MODULE_LOADING") != "EAGER":
+        print("warning: CUDA_MODULE_LOADING is not EAGER: loopback ranks may time out in their first barrier", file=sys.stderr)
     sc = S.procedural_scene(seed=1)
     cams = {n: S.fixture_constants(n) for n in ("main", "shadow", "voxel")}
     bad = []

@@ -1,6 +1,7 @@
 """The multi-rank schedule on ONE GPU (tests/loopback_worker.py): G contexts of one process as the ranks of a box.  This is
 the N > 1 parity evidence a one-GPU box can produce — tests/test_gpu_multi.py repeats it across real GPUs over NVLink when the box
-has them.  Each case runs in its own process with one hardware queue per stream (CUDA_DEVICE_MAX_CONNECTIONS=32)."""
+has them.  Each case runs in its own process with one hardware queue per stream (CUDA_DEVICE_MAX_CONNECTIONS=32) and eager module
+loading (CUDA_MODULE_LOADING=EAGER)."""
 import os
 import subprocess
 import sys
@@ -12,7 +13,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def run(which, timeout=600, **env):
-    e = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", **env)
+    # one hardware queue per stream, and every kernel loaded up front: with lazy module loading the FIRST launch of a kernel waits
+    # for the device to drain — forever, if what runs there is a barrier waiting for a rank this very host thread has yet to enqueue
+    e = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER", **env)
     r = subprocess.run([sys.executable, os.path.join(REPO, "tests", "loopback_worker.py"), which], capture_output=True, text=True, timeout=timeout, env=e)
     assert r.returncode == 0 and f"OK [{which}]" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
