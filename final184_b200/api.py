@@ -38,6 +38,7 @@ FLAG_DENSE_MIPS = 4
 FLAG_GATHER_LINEAR = 8
 FLAG_NO_OVERLAP = 16
 FLAG_SPEC_APPENDIX_B = 32
+FLAG_EXACT_SECONDARY = 64
 
 (FMT_UNDEFINED, FMT_R32_SFLOAT, FMT_R16G16B16A16_UNORM, FMT_R8G8B8A8_UNORM, FMT_R16G16B16A16_SFLOAT,
  FMT_R16G16_UINT, FMT_R32G32B32A32_SFLOAT, FMT_R8G8B8A8_SNORM, FMT_R32_UINT) = range(9)

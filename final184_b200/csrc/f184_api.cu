@@ -1044,13 +1044,16 @@ int f184_gtao(f184_ctx* c, const f184_view_constants* view)
 {
     if (!c || !view) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "gtao: null argument");
     CK(c, cudaSetDevice(c->cfg.device));
-    return f184_gtao_impl(c, view);
+    // mode R: every pixel pinned to the shader text; mode N: north_star's 1e-2 tolerance, on the hardware's own units
+    const bool fast = c->cfg.mode == F184_MODE_NORTHSTAR && !(c->cfg.flags & F184_FLAG_EXACT_SECONDARY);
+    return fast ? f184_gtao_fast_impl(c, view) : f184_gtao_impl(c, view);
 }
 int f184_blur_indirect(f184_ctx* c, const f184_engine_miscs* miscs)
 {
     if (!c || !miscs) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "blur_indirect: null argument");
     CK(c, cudaSetDevice(c->cfg.device));
-    return f184_blur_impl(c, miscs);
+    const bool fast = c->cfg.mode == F184_MODE_NORTHSTAR && !(c->cfg.flags & F184_FLAG_EXACT_SECONDARY);
+    return fast ? f184_blur_fast_impl(c, miscs) : f184_blur_impl(c, miscs);
 }
 int f184_lighting_deferred(f184_ctx* c, const f184_view_constants* view, const f184_extended_matrices* m, const f184_light_list* point,
                            const f184_light_list* directional)

@@ -262,6 +262,8 @@ int f184_voxelize_r(f184_ctx* c, const f184_view_constants* cam);
 int f184_trace_r(f184_ctx* c, const f184_trace_constants* k);
 int f184_gtao_impl(f184_ctx* c, const f184_view_constants* view);
 int f184_blur_impl(f184_ctx* c, const f184_engine_miscs* miscs);
+int f184_gtao_fast_impl(f184_ctx* c, const f184_view_constants* view);     // secondary_fast.cu: north-star contract (1e-2), hardware units
+int f184_blur_fast_impl(f184_ctx* c, const f184_engine_miscs* miscs);
 int f184_composite_impl(f184_ctx* c, const f184_trace_constants* k);
 int f184_lighting_impl(f184_ctx* c, const f184_view_constants* view, const f184_extended_matrices* m, const f184_light_list* point,
                        const f184_light_list* directional);

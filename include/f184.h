@@ -135,10 +135,12 @@ typedef enum f184_flags {
                                       and the cone trace of frame f (pass stream) run side by side, ordered by events where data flows, the
                                       texture-side volume double-buffered.  Every call that reads a stage's outputs orders itself after it:
                                       results are identical */
-    F184_FLAG_SPEC_APPENDIX_B = 32 /* mode N cone tracer as SURVEY.md Appendix B.5 writes it: mip-LINEAR sampling (level 0 / level 1 blend below
+    F184_FLAG_SPEC_APPENDIX_B = 32,/* mode N cone tracer as SURVEY.md Appendix B.5 writes it: mip-LINEAR sampling (level 0 / level 1 blend below
                                       lod 1, the hardware's linear mip filter above) and half-diameter steps.  Default is the amended spec of
                                       DESIGN.md B.5: nearest mip level, one sample per voxel of the sampled level.  bench.py reports the image
                                       difference between the two as `spec_delta` */
+    F184_FLAG_EXACT_SECONDARY = 64 /* mode N: f184_gtao / f184_blur_indirect use the reference-faithful kernels (bit-exact against the shader text,
+                                      IEEE divisions, pinned transcendentals) instead of the fast ones north_star's 1e-2 tolerance allows */
 } f184_flags;
 
 /* CViewConstants, Foreground/SceneGraph/SceneView.h:8-14 = GlobalConstants, Shader/EngineCommon.h:7-13. 208 B. */

@@ -210,3 +210,29 @@ def test_row_selective_transfers_gpu(cuda_lib):
         hn = host.numpy()
         assert np.array_equal(hn[mine], got[mine]) and (hn[~mine] == -1.0).all()
     c.close()
+
+
+def test_secondary_passes_fast_within_tolerance_and_exact_on_request(cuda_lib, oracle_lib, proc_scene, cams):
+    """Mode N's GTAO (+ 4x4 blur) and bilateral blur run on the hardware's own units (MUFU rcp / rsqrt / sin / cos / ex2, FMA): the
+    oracle's reference-faithful restatement bounds them within north_star's 1e-2 relative L2 per image; F184_FLAG_EXACT_SECONDARY
+    selects the pinned kernels, which equal the oracle bit for bit (as in mode R)."""
+    w, h = 320, 184
+    for flags, exact in ((0, False), (A.FLAG_EXACT_SECONDARY, True)):
+        g, o, k = _pipeline(cuda_lib, oracle_lib, proc_scene, cams, 64, w, h, flags=flags)
+        for c in (g, o):
+            c.gtao(cams["main"])
+            c.blur_indirect(k)
+        ao_g, ao_o = g.readback(A.SLOT_AO_OUT).astype(np.float32)[..., 0], o.readback(A.SLOT_AO_OUT).astype(np.float32)[..., 0]
+        raw_g, raw_o = g.readback(A.SLOT_AO_RAW).astype(np.float32)[..., 0], o.readback(A.SLOT_AO_RAW).astype(np.float32)[..., 0]
+        # the blur's input is the GPU's own traced image (itself within tolerance of the oracle's): compare blur(GPU image) on both sides
+        o.upload(A.SLOT_INDIRECT_OUT, g.readback(A.SLOT_INDIRECT_OUT))
+        o.blur_indirect(k)
+        bl_g, bl_o = g.readback(A.SLOT_INDIRECT_FINAL).astype(np.float32)[..., :3], o.readback(A.SLOT_INDIRECT_FINAL).astype(np.float32)[..., :3]
+        assert ao_o.std() > 1e-3 and bl_o.mean() > 1e-3
+        if exact:
+            assert np.array_equal(ao_g, ao_o) and np.array_equal(raw_g, raw_o) and np.array_equal(bl_g, bl_o)
+        else:
+            e_raw, e_ao, e_bl = Hh.rel_l2(raw_g, raw_o), Hh.rel_l2(ao_g, ao_o), Hh.rel_l2(bl_g, bl_o)
+            print(f"fast secondary passes: rel. L2 gtao {e_raw:.2e}, gtao+blur {e_ao:.2e}, bilateral blur {e_bl:.2e}")
+            assert e_raw <= 1e-2 and e_ao <= 1e-2 and e_bl <= 1e-2, (e_raw, e_ao, e_bl)
+        g.close(); o.close()
