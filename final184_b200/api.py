@@ -175,6 +175,7 @@ _SIGS = {
     "lighting_deferred": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC), C.POINTER(ExtendedMatricesC), C.POINTER(LightListC), C.POINTER(LightListC)]),
     "bind_rands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "set_triangle_range": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "set_triangle_chunks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "set_trace_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "set_trace_tiles": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "stage_time_ms": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]),
@@ -412,6 +413,11 @@ class VoxelGI:
 
     def set_triangle_range(self, first, count):
         self._ck(self.lib.set_triangle_range(self.h, first, count), "set_triangle_range")
+
+    def set_triangle_chunks(self, chunk_ids):
+        """128-triangle chunks this context voxelizes (None / empty: every triangle of the range)"""
+        a = np.ascontiguousarray(chunk_ids if chunk_ids is not None else [], np.uint32)
+        self._ck(self.lib.set_triangle_chunks(self.h, a.ctypes.data if len(a) else None, len(a)), "set_triangle_chunks")
 
     def set_trace_rows(self, y0, y1):
         self._ck(self.lib.set_trace_rows(self.h, y0, y1), "set_trace_rows")

@@ -442,7 +442,7 @@ void f184_destroy(f184_ctx* c)
     for (void* p : {(void*)c->pos, (void*)c->nrm, (void*)c->uv, (void*)c->model_mats, (void*)c->idx, (void*)c->tri_mat,
                     (void*)c->tri_model, (void*)c->tex_dev, (void*)c->mat_dev, (void*)c->vox_keys, (void*)c->counters_dev,
                     (void*)c->brick_prev, (void*)c->brick_list, (void*)c->vox_queue, (void*)c->vm_dev, (void*)c->gamma_table, c->gtao_phi_table,
-                    (void*)c->dev_state})
+                    (void*)c->dev_state, (void*)c->chunk_list})
         if (p) cudaFree(p);
     for (uint8_t* p : c->tex_alloc) if (p) cudaFree(p);
     for (int s = 0; s < F184_STAGE_COUNT; s++)
@@ -1096,6 +1096,20 @@ int f184_set_triangle_range(f184_ctx* c, uint32_t first, uint32_t count)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
     c->tri_first = first; c->tri_count = count;
+    return F184_OK;
+}
+int f184_set_triangle_chunks(f184_ctx* c, const uint32_t* chunk_ids, uint32_t n_chunks)
+{
+    if (!c || (n_chunks && !chunk_ids)) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "set_triangle_chunks: bad argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (c->vox_stream) CK(c, cudaStreamSynchronize(c->vox_stream));       // the voxelizer in flight reads the list replaced below
+    if (c->chunk_list) { cudaFree(c->chunk_list); c->chunk_list = nullptr; }
+    c->n_chunks = 0;
+    if (!n_chunks) return F184_OK;
+    CK(c, cudaMalloc(&c->chunk_list, 4ull * n_chunks));
+    CK(c, cudaMemcpy(c->chunk_list, chunk_ids, 4ull * n_chunks, cudaMemcpyHostToDevice));
+    c->n_chunks = n_chunks;
     return F184_OK;
 }
 int f184_set_trace_rows(f184_ctx* c, uint32_t y0, uint32_t y1)

@@ -171,6 +171,8 @@ struct f184_ctx
     bool inject_in_volume = false;            // f184_inject has written the open build set (its level 0 is current)
     // sharding
     uint32_t tri_first = 0, tri_count = 0xffffffffu;
+    uint32_t* chunk_list = nullptr;           // device: 128-triangle chunks this rank voxelizes (nullptr = every triangle of the range)
+    uint32_t n_chunks = 0;
     uint32_t row0 = 0, row1 = 0xffffffffu;
     uint32_t tile_first = 0, tile_stride = 1;
     const float* rands = nullptr;

@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "f184_device.cuh"
 
@@ -121,6 +122,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 // Source tensor: 4-D (x, y, z, dir) of uint32 texels; dir extent is 1 for the isotropic level 0.
 // Work items: (dir_src, tile).  iso: one item yields six outputs; else item's dir yields one.
 __global__ void __launch_bounds__(MIPS_THREADS)
@@ -218,39 +225,83 @@ struct BrickMipOut
     cudaSurfaceObject_t surf[3];       // atlas levels 1..3
 };
 constexpr int BRICK_WARPS = 8;
+constexpr int BRICK_STAGES = 3;                                   // TMA ring per warp: 3 x 2 KB bricks in flight
+constexpr int BRICK_RING_BYTES = BRICK_WARPS * BRICK_STAGES * 2048;
 
+// TMA = true (default): each warp stages its bricks through a ring in shared memory — one cp.async.bulk.tensor.3d per 8x8x8 box
+// of the level-0 volume, completion on an mbarrier — so the 64 row fetches of a brick cost the warp one instruction and the next
+// bricks are in flight while this one is reduced.  TMA = false: the same kernel with per-lane 16-byte loads (F184_MIPS_BRICKS_LDG=1;
+// also what runs when the driver has no cuTensorMapEncodeTiled).
+template <bool TMA>
 __global__ void __launch_bounds__(BRICK_WARPS * 32)
-k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ brick_list, const unsigned long long* __restrict__ brick_count,
-              BrickMipOut out, int N, uint32_t* __restrict__ export_buf, uint32_t* __restrict__ brick_prev, uint32_t set_bit)
+k_mips_bricks(const __grid_constant__ CUtensorMap level0_map, const uint32_t* __restrict__ level0, const uint32_t* __restrict__ brick_list,
+              const unsigned long long* __restrict__ brick_count, BrickMipOut out, int N, uint32_t* __restrict__ export_buf,
+              uint32_t* __restrict__ brick_prev, uint32_t set_bit)
 {
-    __shared__ __align__(16) uint32_t sh0[BRICK_WARPS][512];       // the brick, [z][y][x]
+    extern __shared__ __align__(128) uint8_t ring_raw[];            // TMA: [warp][stage][512 texels]; LDG: [warp][512 texels]
     __shared__ __align__(16) uint32_t sh1[BRICK_WARPS][6][64];     // level 1 per direction, [z][y][x] 4^3
     __shared__ __align__(16) uint32_t sh2[BRICK_WARPS][6][8];      // level 2 per direction, 2^3
+    __shared__ __align__(8) uint64_t bars[BRICK_WARPS][BRICK_STAGES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t warp_global = blockIdx.x * BRICK_WARPS + warp, n_warps = gridDim.x * BRICK_WARPS;
     const uint32_t count = (uint32_t)*brick_count;
     const int NB = N >> 3, n1 = N >> 1, n2 = N >> 2, n3 = N >> 3;
-    uint32_t* s0 = sh0[warp];
-    for (uint32_t i = warp_global; i < count; i += n_warps)
+    uint32_t* ring = reinterpret_cast<uint32_t*>(ring_raw) + (size_t)warp * (TMA ? BRICK_STAGES : 1) * 512;
+    auto issue = [&](uint32_t i, int stage) {       // lane 0: fetch brick i of the list into `stage`
+        const uint32_t b = __ldg(brick_list + i) & 0x7fffffffu;
+        mbar_expect_tx(&bars[warp][stage], 2048);
+        tma_load_3d(ring + stage * 512, &level0_map, &bars[warp][stage], (int)(b % NB) * 8, (int)((b / NB) % NB) * 8, (int)(b / (NB * NB)) * 8);
+    };
+    if (TMA)
+    {
+        if (lane == 0)
+        {
+            for (int s_ = 0; s_ < BRICK_STAGES; s_++) mbar_init(&bars[warp][s_], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (lane == 0)
+            for (int s_ = 0; s_ < BRICK_STAGES; s_++)
+            {
+                const uint32_t i = warp_global + (uint32_t)s_ * n_warps;
+                if (i < count) issue(i, s_);
+            }
+    }
+    uint32_t it = 0;
+    for (uint32_t i = warp_global; i < count; i += n_warps, it++)
     {
         const uint32_t entry = __ldg(brick_list + i);
         const uint32_t b = entry & 0x7fffffffu;
         // levels 1-3 of this texture set now hold the brick iff it is occupied this frame (same assignment as k_inject_n makes for level 0)
         if (lane == 0 && brick_prev) brick_prev[b] = (brick_prev[b] & ~set_bit) | ((entry >> 31) ? set_bit : 0u);
         const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
-        // level 0: 64 rows of 8 texels (one 32-byte sector each) = 128 uint4, four per lane
-#pragma unroll
-        for (int k = 0; k < 4; k++)
+        const int stage = TMA ? (int)(it % BRICK_STAGES) : 0;
+        uint32_t* s0 = ring + stage * 512;                          // the brick, [z][y][x]
+        if (TMA)
         {
-            const int q = lane + 32 * k, row = q >> 1, half = q & 1;
-            const int y = row & 7, z = row >> 3;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(level0 + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4));
-            *reinterpret_cast<uint4*>(s0 + row * 8 + half * 4) = v;
+            mbar_wait(&bars[warp][stage], (it / BRICK_STAGES) & 1u);
             // multi-GPU: the brick's packed record (1024 words: level 0 | level 1 | level 2 | level 3) that the other
             // ranks pull over NVLink (mode_n_shard.cu)
-            if (export_buf) reinterpret_cast<uint4*>(export_buf + (size_t)i * 1024)[q] = v;
+            if (export_buf)
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    reinterpret_cast<uint4*>(export_buf + (size_t)i * 1024)[lane + 32 * k] = reinterpret_cast<const uint4*>(s0)[lane + 32 * k];
+        }
+        else
+        {
+            // level 0: 64 rows of 8 texels (one 32-byte sector each) = 128 uint4, four per lane
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                const int q = lane + 32 * k, row = q >> 1, half = q & 1;
+                const int y = row & 7, z = row >> 3;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(level0 + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4));
+                *reinterpret_cast<uint4*>(s0 + row * 8 + half * 4) = v;
+                if (export_buf) reinterpret_cast<uint4*>(export_buf + (size_t)i * 1024)[q] = v;
+            }
         }
         uint32_t* rec = export_buf ? export_buf + (size_t)i * 1024 : nullptr;
+        if (rec && lane == 0) rec[950] = b;            // the record names its brick: the TMA-fed gather reads nothing but records over NVLink
         __syncwarp();
         {   // level 1: lane -> output row (oy, oz) = lane & 15 and three of the six directions
             const int p = lane & 15, oy = p & 3, oz = p >> 2, d0 = (lane >> 4) * 3;
@@ -333,7 +384,16 @@ k_mips_bricks(const uint32_t* __restrict__ level0, const uint32_t* __restrict__ 
             if (rec) rec[944 + d] = v;
             surf3Dwrite(v, out.surf[2], bx * 4, by, atlas_z(d, n3, bz));
         }
-        __syncwarp();
+        __syncwarp();                              // every lane is done with this stage's brick (and with sh1 / sh2)
+        if (TMA && lane == 0)
+        {
+            const uint32_t next = i + (uint32_t)BRICK_STAGES * n_warps;
+            if (next < count)
+            {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the warp's reads of the stage before the async proxy overwrites it
+                issue(next, stage);
+            }
+        }
     }
 }
 
@@ -515,8 +575,34 @@ int f184_mips_n(f184_ctx* c)
         }
         // (the history bit is assigned only when f184_inject wrote level 0 of the same set from the same list: a build_mips on its
         // own must not declare a stale level 0 clean)
-        k_mips_bricks<<<148 * 4, BRICK_WARPS * 32, 0, c->stream>>>(level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N, export_buf,
-                                                                   c->inject_in_volume ? c->brick_prev : nullptr, 2u << c->build_set);
+        static const bool force_ldg = [] { const char* e = getenv("F184_MIPS_BRICKS_LDG"); return e && atoi(e) != 0; }();
+        uint32_t* prev = c->inject_in_volume ? c->brick_prev : nullptr;
+        CUtensorMap map{};
+        bool tma_bricks = get_encode() != nullptr && !force_ldg;
+        if (tma_bricks)
+        {   // the level-0 volume as a 3-D tensor of texels, fetched in 8 x 8 x 8 boxes
+            const cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)N, (cuuint64_t)N};
+            const cuuint64_t gstride[2] = {(cuuint64_t)N * 4, (cuuint64_t)N * N * 4};
+            const cuuint32_t box[3] = {8, 8, 8};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = get_encode()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)level0, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) tma_bricks = false;
+        }
+        if (tma_bricks)
+        {
+            static bool brick_attr = false;
+            if (!brick_attr)
+            {
+                CK(c, cudaFuncSetAttribute(k_mips_bricks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BRICK_RING_BYTES));
+                brick_attr = true;
+            }
+            k_mips_bricks<true><<<148 * 2, BRICK_WARPS * 32, BRICK_RING_BYTES, c->stream>>>(map, level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N,
+                                                                                           export_buf, prev, 2u << c->build_set);
+        }
+        else
+            k_mips_bricks<false><<<148 * 4, BRICK_WARPS * 32, BRICK_WARPS * 2048, c->stream>>>(map, level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N,
+                                                                                              export_buf, prev, 2u << c->build_set);
         CK_LAUNCH(c);
         first_dense = c->n_mip_levels;          // the tail kernel takes every remaining level
         if (c->cfg.nranks <= 1)                 // (multi-GPU: level 3 is complete only after f184_gather_volume, which runs the tail)

@@ -139,14 +139,14 @@ struct GatherArgs
 };
 
 // behind the gather: the set's level-0 bookkeeping, and the bytes that crossed NVLink (F184_COUNTER_GATHER_BYTES)
-__global__ void k_gather_state(const GatherArgs G, uint32_t* dev_state, int set, unsigned long long* counters)
+__global__ void k_gather_state(const GatherArgs G, uint32_t* dev_state, int set, unsigned long long* counters, uint32_t bytes_with_l0, uint32_t bytes_without)
 {
     const bool level0 = dev_state[F184_DEV_NEED_L0] != 0;
     dev_state[F184_DEV_L0_FULL + set] = level0 ? 1u : 0u;
     unsigned long long records = 0;
     for (int p = 0; p < G.nranks; p++)
         if (p != G.rank) records += G.peer_counters[p][F184_COUNTER_COUNT];
-    counters[F184_COUNTER_GATHER_BYTES] = records * (4ull + (level0 ? 2048ull : 0ull) + 4ull * (384 + 48 + 6));    // list entry + record parts read
+    counters[F184_COUNTER_GATHER_BYTES] = records * (unsigned long long)(level0 ? bytes_with_l0 : bytes_without);
 }
 
 constexpr int GATHER_WARPS = 8;
@@ -213,6 +213,144 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather_bricks(const Gathe
             G.lin[2][lane][((size_t)bz * n3 + by) * n3 + bx] = l3;             // level 3 is the source of the local tail: always
         }
     }
+}
+
+// ---- the gather, TMA-fed (default) ---------------------------------------------------------------------------------------------
+// The per-lane peer loads above keep 7 x 16 bytes per lane in flight and need every warp of the GPU to cover NVLink's ~2 us: fine
+// when the gather has the GPU to itself (630 GB/s at 2 GPUs), but inside the frame pipeline it shares the SMs with the cone trace
+// of the previous frame and ran at 70 GB/s.  Here ONE thread per CTA issues bulk copies (cp.async.bulk: the TMA engine moves a
+// brick's whole record, 1.7 KB or 3.7 KB, peer HBM -> shared memory over NVLink, completion on an mbarrier) into a 16-slot ring —
+// 28-60 KB in flight per CTA whatever else runs on the SM — and four consumer warps write the landed records through surfaces into
+// the texture storage.  Records carry their brick index (word 950, written by k_mips_bricks), so nothing but bulk copies crosses
+// NVLink.
+constexpr int G2_SLOTS = 16;
+constexpr int G2_CONSUMERS = 4;                  // warps; + 1 producer warp
+constexpr int G2_SLOT_BYTES = 4096;
+constexpr int G2_REC_BYTES = 1760;               // levels 1-3 + brick index: words [512, 952)
+constexpr int G2_REC0_BYTES = 3808;              // with level 0: words [0, 952)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+// bounded wait: a protocol error or a dead peer becomes a sticky device error (reported by the next synchronous call), not a hung GPU
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, uint32_t* dev_state)
+{
+    unsigned long long t0 = 0;
+    for (uint32_t tries = 0;; tries++)
+    {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return true;
+        if ((tries & 255u) == 255u)
+        {
+            const unsigned long long now = globaltimer_ns();
+            if (!t0) t0 = now;
+            else if (now - t0 > 2000000000ull) break;               // 2 s
+        }
+    }
+    atomicOr(dev_state + F184_DEV_ERROR, F184_DEVERR_BARRIER_TIMEOUT);
+    return false;
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__((G2_CONSUMERS + 1) * 32) k_gather_bricks_tma(const GatherArgs G, uint32_t* dev_state)
+{
+    extern __shared__ __align__(128) uint8_t ring[];                // G2_SLOTS x 4 KB
+    __shared__ __align__(8) uint64_t full[G2_SLOTS], empty[G2_SLOTS];
+    __shared__ uint32_t counts[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0)
+    {
+        for (int s_ = 0; s_ < G2_SLOTS; s_++) { mbar_init(&full[s_], 1); mbar_init(&empty[s_], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 8) counts[threadIdx.x] = ((int)threadIdx.x < G.nranks && (int)threadIdx.x != G.rank) ? (uint32_t)G.peer_counters[threadIdx.x][F184_COUNTER_COUNT] : 0u;
+    __syncthreads();
+    const bool level0 = G.dev_state[F184_DEV_NEED_L0] != 0;
+    uint32_t max_count = 0;
+    for (int p = 0; p < G.nranks; p++) max_count = max(max_count, counts[p]);
+    const int N = G.N, NB = N >> 3, n1 = N >> 1, n2 = N >> 2, n3 = N >> 3;
+    // both roles walk the same item sequence: j = blockIdx.x, + gridDim.x, ...; for each j the peers in an order rotated by the
+    // reader's rank (so the box's readers do not all start on the same peer); an item exists where j < that peer's count
+    uint32_t n = 0;                                                  // sequence number of the next item
+    if (warp == G2_CONSUMERS)
+    {   // ---- producer
+        if (lane == 0)
+            for (uint32_t j = blockIdx.x; j < max_count; j += gridDim.x)
+                for (int q = 1; q < G.nranks; q++)
+                {
+                    const int p = (G.rank + q) % G.nranks;
+                    if (j >= counts[p]) continue;
+                    const int slot = (int)(n % G2_SLOTS);
+                    if (!mbar_wait_bounded(&empty[slot], ((n / G2_SLOTS) & 1u) ^ 1u, dev_state)) return;
+                    const uint8_t* rec = reinterpret_cast<const uint8_t*>(G.peer_export[p]) + (size_t)j * 4096;
+                    uint8_t* dst = ring + (size_t)slot * G2_SLOT_BYTES;
+                    if (level0) { mbar_expect_tx(&full[slot], G2_REC0_BYTES); bulk_load(dst, rec, G2_REC0_BYTES, &full[slot]); }
+                    else { mbar_expect_tx(&full[slot], G2_REC_BYTES); bulk_load(dst + 2048, rec + 2048, G2_REC_BYTES, &full[slot]); }
+                    n++;
+                }
+        return;
+    }
+    // ---- consumers: warp w takes the items with n % G2_CONSUMERS == w
+    for (uint32_t j = blockIdx.x; j < max_count; j += gridDim.x)
+        for (int q = 1; q < G.nranks; q++)
+        {
+            const int p = (G.rank + q) % G.nranks;
+            if (j >= counts[p]) continue;
+            const uint32_t mine = n++;
+            if ((int)(mine % G2_CONSUMERS) != warp) continue;
+            const int slot = (int)(mine % G2_SLOTS);
+            if (!mbar_wait_bounded(&full[slot], (mine / G2_SLOTS) & 1u, dev_state)) return;
+            const uint32_t* rec = reinterpret_cast<const uint32_t*>(ring + (size_t)slot * G2_SLOT_BYTES);
+            const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
+            const uint32_t b = rec[950] & 0x7fffffffu;
+            const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
+            if (level0)
+            {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                {
+                    const int qq = lane + 32 * k, row = qq >> 1, half = qq & 1, y = row & 7, z = row >> 3;
+                    const uint4 v = rec4[qq];
+                    surf3Dwrite(v, G.rad_surf, (bx * 8 + half * 4) * 4, by * 8 + y, bz * 8 + z);
+                    if (G.write_linear) *reinterpret_cast<uint4*>(G.rad_lin + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4) = v;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+            {
+                const int jj = lane + 32 * k, d = jj >> 4, r = jj & 15, oy = r & 3, oz = r >> 2;
+                const int gx = bx * 4, gy = by * 4 + oy, gz = bz * 4 + oz;
+                const uint4 v = rec4[128 + jj];
+                surf3Dwrite(v, G.surf[0], gx * 4, gy, atlas_z(d, n1, gz));
+                if (G.write_linear) *reinterpret_cast<uint4*>(G.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = v;
+            }
+            if (lane < 24)
+            {
+                const int d = lane >> 2, r = lane & 3, oy = r & 1, oz = r >> 1;
+                const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
+                const uint2 v = reinterpret_cast<const uint2*>(rec + 896)[lane];
+                surf3Dwrite(v, G.surf[1], gx * 4, gy, atlas_z(d, n2, gz));
+                if (G.write_linear) *reinterpret_cast<uint2*>(G.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = v;
+            }
+            if (lane < 6)
+            {
+                const uint32_t v = rec[944 + lane];
+                surf3Dwrite(v, G.surf[2], bx * 4, by, atlas_z(lane, n3, bz));
+                G.lin[2][lane][((size_t)bz * n3 + by) * n3 + bx] = v;             // level 3 is the source of the local tail: always
+            }
+            __syncwarp();                                            // the whole warp has read the slot
+            if (lane == 0) mbar_arrive(&empty[slot]);
+        }
 }
 
 }  // namespace
@@ -367,9 +505,22 @@ int f184_gather_n(f184_ctx* c)
         k_clear_foreign_level0<<<148 * 4, 256, 0, c->stream>>>(vs.rad_surf, (int)c->cfg.grid_n, c->cfg.nranks, c->cfg.rank, c->dev_state, set);
         CK_LAUNCH(c);
     }
-    k_gather_bricks<<<dim3(c->cfg.nranks, 148), GATHER_WARPS * 32, 0, c->stream>>>(G);
+    static const bool gather_ldg = [] { const char* e = getenv("F184_GATHER_LDG"); return e && atoi(e) != 0; }();
+    if (gather_ldg) k_gather_bricks<<<dim3(c->cfg.nranks, 148), GATHER_WARPS * 32, 0, c->stream>>>(G);
+    else
+    {
+        static bool attr = false;
+        if (!attr)
+        {
+            CK(c, cudaFuncSetAttribute(k_gather_bricks_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SLOTS * G2_SLOT_BYTES));
+            attr = true;
+        }
+        k_gather_bricks_tma<<<148 * 2, (G2_CONSUMERS + 1) * 32, G2_SLOTS * G2_SLOT_BYTES, c->stream>>>(G, c->dev_state);
+    }
     CK_LAUNCH(c);
-    k_gather_state<<<1, 1, 0, c->stream>>>(G, c->dev_state, set, c->counters_dev);
+    // bytes per record that cross NVLink: the bulk copies of the TMA-fed kernel, or list entry + the record parts the per-lane loads read
+    k_gather_state<<<1, 1, 0, c->stream>>>(G, c->dev_state, set, c->counters_dev, gather_ldg ? 4 + 2048 + 4 * (384 + 48 + 6) : G2_REC0_BYTES,
+                                           gather_ldg ? 4 + 4 * (384 + 48 + 6) : G2_REC_BYTES);
     CK_LAUNCH(c);
     rc = f184_stage_end(c, F184_STAGE_EXCHANGE);
     if (rc) return rc;

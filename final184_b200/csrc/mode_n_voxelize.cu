@@ -116,6 +116,7 @@ struct VoxArgs
     const TexDev* texs;
     const MatDev* mats;
     uint32_t tri_first, tri_end;
+    const uint32_t* chunks;            // 128-triangle chunks of this rank (one per CTA of the set-up pass), or nullptr
     int N;
     // accumulators / brick flags of the rank that owns the voxel's 8^3 brick, owner = (bx + by + bz) % nranks (a diagonal
     // interleave: every axis-aligned sheet of bricks — Sponza's floor is one — is dealt evenly over the ranks): own memory,
@@ -368,10 +369,11 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
 __global__ void __launch_bounds__(SETUP_THREADS) k_voxelize_setup(const VoxArgs A)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t t = A.tri_first + blockIdx.x * SETUP_THREADS + threadIdx.x;
+    static_assert(SETUP_THREADS == F184_TRIANGLE_CHUNK, "one CTA of the set-up pass = one chunk");
+    const uint32_t t = A.chunks ? __ldg(A.chunks + blockIdx.x) * SETUP_THREADS + threadIdx.x : A.tri_first + blockIdx.x * SETUP_THREADS + threadIdx.x;
     TriS s;
     bool active = false;
-    if (t < A.tri_end) active = setup_triangle(A, t, s);
+    if (t >= A.tri_first && t < A.tri_end) active = setup_triangle(A, t, s);
     unsigned int frags = 0;
     uint32_t ntasks = 0;
     if (active)
@@ -658,7 +660,8 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
         A.queue_tris = reinterpret_cast<uint4*>(c->vox_queue);                      // 192 B records first (16-byte aligned)
         A.queue = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(c->vox_queue) + sizeof(TriS) * (size_t)c->vox_queue_cap);
         const uint32_t tris = end - first;
-        k_voxelize_setup<<<(tris + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, c->stream>>>(A);
+        A.chunks = c->n_chunks ? c->chunk_list : nullptr;
+        k_voxelize_setup<<<c->n_chunks ? c->n_chunks : (tris + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, c->stream>>>(A);
         CK_LAUNCH(c);
         k_voxelize_raster<<<148 * 4 * 4, RASTER_THREADS, 0, c->stream>>>(A);
         CK_LAUNCH(c);

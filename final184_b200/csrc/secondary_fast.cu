@@ -82,6 +82,11 @@ __global__ void __launch_bounds__(128) k_gtao_fast(const GtaoFastParams G)
         const float rStep = radius * 0.5f;
         float phi = -(1.0f / 16.0f) * (float)((((x + y) & 0x3) << 2) + (x & 0x3)) * PI_;
         const float r0 = rStep * (0.25f * (float)((y - x) & 0x3));
+        // On the diagonal of the 4x4 interleave r0 = 0: the first tap of BOTH sides is the pixel itself, normalize(0) is NaN, the NaN
+        // survives the horizon blend (mix(..)*0 + ..), and the reference's max(NaN, -pi/2) / min(NaN, pi/2) then open the horizon
+        // completely (min/max return the non-NaN operand).  Said outright here instead of left to NaN propagation
+        // through approximate units: those pixels need no depth taps at all.
+        const bool open = ((y - x) & 0x3) == 0;
         float integral = 0.0f;
 #pragma unroll 1
         for (int samp = 0; samp < 4; samp++)
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(128) k_gtao_fast(const GtaoFastParams G)
             float hx = -1.0f, hy = -1.0f;
             float r = r0;
 #pragma unroll
-            for (int j = 0; j < 2; j++)
+            for (int j = 0; j < 2 && !open; j++)
             {
                 const float ox = r * cph * G.invW, oy = -r * sph * G.invH;
                 r += rStep;
@@ -104,7 +109,6 @@ __global__ void __launch_bounds__(128) k_gtao_fast(const GtaoFastParams G)
                 hx = hx >= hsx ? hx : 0.5f * (hx + hsx);          // mix(mix(h, hs, .5), max(h, hs), step(hs, h))   gtao.frag:90-93
                 hy = hy >= hsy ? hy : 0.5f * (hy + hsy);
             }
-            hx = fastAcos(hx); hy = fastAcos(hy);
             const f3 sliceDir = {cph, sph, 0.0f};
             const f3 sliceNormal = norm_fast(cross3(Vv, sliceDir));
             const f3 sliceBitangent = norm_fast(cross3(sliceNormal, Vv));
@@ -115,8 +119,8 @@ __global__ void __launch_bounds__(128) k_gtao_fast(const GtaoFastParams G)
             projNorm = {projNorm.x * rwgt, projNorm.y * rwgt, projNorm.z * rwgt};
             const float cosn = dot3(projNorm, Vv), sinn = dot3(projNorm, sliceBitangent);
             const float n = fastAcos(cosn) * (sinn > 0.0f ? 1.0f : (sinn < 0.0f ? -1.0f : 0.0f));
-            hx = n + fmaxf(-hx - n, -half_PI_);
-            hy = n + fminf(hy - n, half_PI_);
+            hx = open ? n - half_PI_ : n + fmaxf(-fastAcos(hx) - n, -half_PI_);
+            hy = open ? n + half_PI_ : n + fminf(fastAcos(hy) - n, half_PI_);
             float sn, cn_;
             __sincosf(n, &sn, &cn_);
             const float ax = -__cosf(2.0f * hx - n) + cn_ + 2.0f * hx * sn;

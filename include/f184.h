@@ -331,6 +331,12 @@ int f184_bind_rands(f184_ctx* ctx, const float* device_rands, size_t count);
 /* ---- sharding.  A rank voxelizes triangles [first, first+count), owns Z-slab
  * [z0, z1) of every volume level and traces rows [y0, y1).  Defaults are derived from rank/nranks. */
 int f184_set_triangle_range(f184_ctx* ctx, uint32_t first, uint32_t count);
+/* Mode N: the triangles this rank voxelizes as a list of 128-triangle chunks (chunk c = triangles [128 c, 128 c + 128)), on top of which
+ * the range above still filters.  Chunks let a cost model deal the scene over the ranks in small pieces (largest first, to the least loaded
+ * rank): every rank gets the same mix of wall-sized and sub-voxel triangles, which a contiguous cut cannot give (Sponza's primitives run
+ * from 5 to 27,796 triangles).  `chunk_ids` is a host array, copied; NULL / 0 returns to "every triangle of the range".  Synchronous. */
+#define F184_TRIANGLE_CHUNK 128
+int f184_set_triangle_chunks(f184_ctx* ctx, const uint32_t* chunk_ids, uint32_t n_chunks);
 int f184_set_trace_rows(f184_ctx* ctx, uint32_t y0, uint32_t y1);
 /* Of the rows selected above, trace only the 8-row tile rows t with t % stride == first (t counted from the top of the
  * image; y0 must be a multiple of 8 when stride > 1).  Interleaving tile rows over the ranks balances the trace where

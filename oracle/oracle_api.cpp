@@ -259,6 +259,17 @@ int f184o_debug_set_voxel_stage_hooks(f184o_ctx* c, void* gs, void* ps)
     return F184_OK;
 }
 int f184o_set_triangle_range(f184o_ctx* c, uint32_t first, uint32_t count) { c->tri_first = first; c->tri_count = count; return F184_OK; }
+int f184o_set_triangle_chunks(f184o_ctx* c, const uint32_t* chunk_ids, uint32_t n_chunks)
+{
+    if (!c || (n_chunks && !chunk_ids)) return F184_ERR_INVALID_ARGUMENT;
+    c->chunk_mask.clear();
+    if (!n_chunks) return F184_OK;
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i < n_chunks; i++) mx = std::max(mx, chunk_ids[i]);
+    c->chunk_mask.assign((size_t)mx + 1, 0);
+    for (uint32_t i = 0; i < n_chunks; i++) c->chunk_mask[chunk_ids[i]] = 1;
+    return F184_OK;
+}
 int f184o_set_trace_rows(f184o_ctx* c, uint32_t y0, uint32_t y1) { c->row0 = y0; c->row1 = y1; return F184_OK; }
 int f184o_set_trace_tiles(f184o_ctx* c, uint32_t first, uint32_t stride)
 {

@@ -144,6 +144,7 @@ struct f184o_ctx
     // mode N mip chain: level l>=1, direction d: mips[l][d] is RGBA8 (N>>l)^3
     std::vector<std::vector<std::vector<uint8_t>>> mips;
     uint32_t tri_first = 0, tri_count = 0xffffffffu;
+    std::vector<uint8_t> chunk_mask;      // f184o_set_triangle_chunks: chunk_mask[t / 128] != 0 selects triangle t (empty = all)
     uint32_t row0 = 0, row1 = 0xffffffffu;
     uint32_t tile_first = 0, tile_stride = 1;   // of those rows, only 8-row tile rows t with t % stride == first
     uint32_t view_y0 = 0, view_h = 0;           // f184o_trace_views: rows [view_y0, view_y0 + view_h) are one view (0 = whole image)

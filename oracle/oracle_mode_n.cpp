@@ -175,6 +175,7 @@ extern "C" int orc_voxelize_accumulate_n(f184o_ctx* c, const f184_view_constants
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : frags)
     for (uint32_t t = first; t < last; t++)
     {
+        if (!c->chunk_mask.empty() && (t / F184_TRIANGLE_CHUNK >= c->chunk_mask.size() || !c->chunk_mask[t / F184_TRIANGLE_CHUNK])) continue;
         const uint32_t* id = &c->idx[3 * t];
         const M4& vm = VM[c->tri_model[t]];
         const M4& mm = MM[c->tri_model[t]];

@@ -41,10 +41,19 @@ def test_slab_row_view_ranges():
         assert rr[0][0] == 0 and rr[-1][1] == h and all(rr[i][1] == rr[i + 1][0] for i in range(n - 1))
         assert all(y0 % 8 == 0 for y0, _ in rr)
     assert D.view_ranges(64, 8) == [(8 * r, 8 * r + 8) for r in range(8)]
+    # chunk lists: every chunk exactly once, sorted, loads within a chunk of each other even for a heavy-tailed cost
+    rng = np.random.default_rng(5)
+    wts = rng.pareto(1.2, 262267) + 4.0
+    parts = D.triangle_chunks(wts, 8)
+    allc = np.concatenate(parts)
+    assert sorted(allc.tolist()) == list(range((262267 + 127) // 128)) and all((np.diff(p) > 0).all() for p in parts)
+    cost = np.add.reduceat(wts, np.arange(0, len(wts), 128))
+    loads = np.array([cost[p].sum() for p in parts])
+    assert loads.max() - loads.min() <= cost.max() + 1e-9 and loads.max() / loads.mean() < 1.05
+    assert [len(p) for p in D.triangle_chunks(wts, 1)] == [(262267 + 127) // 128]
     assert [D.brick_owner(0, 0, z, 4) for z in (0, 7, 8, 31, 32, 511)] == [0, 0, 1, 3, 0, 3]
     assert D.brick_owner(8, 16, 24, 4) == 2 and D.brick_owner(7, 7, 7, 8) == 0
     # every axis-aligned sheet of bricks is dealt evenly
-    import numpy as np
     b = np.arange(64)
     for fixed in range(3):
         own = (b[:, None] + b[None, :] + 5) % 8
@@ -77,7 +86,7 @@ def _worker(rank, world, port, out_dir):
         k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
         g.frame(cams["voxel"], k)
         img = g.gather_image()
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), img=img, rad=g.ctx.readback(A.SLOT_RADIANCE), tri=np.array(g.tri_range), rows=g.own_rows_mask(),
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), img=img, rad=g.ctx.readback(A.SLOT_RADIANCE), chunks=g.chunks, rows=g.own_rows_mask(),
                  frags=g.ctx.counter(A.COUNTER_FRAGMENTS))
     finally:
         dist.destroy_process_group()
@@ -96,8 +105,9 @@ def test_sharded_frame_world2_gloo_equals_single_process(tmp_path, oracle_lib, p
     k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
     o.voxelize(cams["voxel"]); o.inject(k); o.build_mips(); o.trace_indirect(k)
     want = o.readback(A.SLOT_INDIRECT_OUT)
-    # the triangle ranges partition the scene, the row bands partition the screen
-    assert r[0]["tri"][0] == 0 and r[0]["tri"].sum() == r[1]["tri"][0] and r[1]["tri"].sum() == proc_scene.n_tris
+    # the chunk lists partition the scene, the row bands partition the screen
+    assert sorted(np.concatenate([r[0]["chunks"], r[1]["chunks"]]).tolist()) == list(range((proc_scene.n_tris + D.CHUNK - 1) // D.CHUNK))
+    assert min(int(r[0]["frags"]), int(r[1]["frags"])) > 0
     assert (r[0]["rows"] ^ r[1]["rows"]).all()                 # interleaved 8-row tiles: every row traced by exactly one rank
     assert int(r[0]["frags"]) + int(r[1]["frags"]) == o.counter(A.COUNTER_FRAGMENTS)
     for i in range(world):
