@@ -31,7 +31,8 @@ MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
  STAGE_BLUR, STAGE_EXCHANGE, STAGE_LIGHTING, STAGE_COMPOSITE, STAGE_BARRIER, STAGE_COUNT) = range(13)
 STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur", "exchange", "lighting", "composite", "barrier"]
 (COUNTER_FRAGMENTS, COUNTER_MARCH_STEPS, COUNTER_OCCUPIED, COUNTER_KERNEL_LAUNCHES, COUNTER_BRICKS, COUNTER_GATHER_BYTES) = range(6)
-(IPC_ACCUM_COLOR, IPC_ACCUM_NORMAL, IPC_BRICK_FLAGS, IPC_EXPORT, IPC_COUNTERS, IPC_BRICK_LIST, IPC_SYNC, IPC_COUNT) = range(8)
+(IPC_ACCUM_COLOR, IPC_ACCUM_NORMAL, IPC_BRICK_FLAGS, IPC_EXPORT, IPC_COUNTERS, IPC_BRICK_LIST, IPC_SYNC, IPC_FRAG_QUEUE, IPC_FRAG_COUNTS,
+ IPC_COUNT) = range(10)
 FLAG_EXTERNAL_RANDS = 1
 FLAG_NO_TMA = 2
 FLAG_DENSE_MIPS = 4

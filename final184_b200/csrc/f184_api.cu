@@ -244,7 +244,7 @@ int f184_prepare_frame(f184_ctx* c)
     void* dummy = nullptr;
     if ((rc = f184_ipc_buffer_ptr(c, F184_IPC_BRICK_LIST, &dummy))) return rc;
     if (c->cfg.nranks > 1)
-        for (uint32_t b : {(uint32_t)F184_IPC_EXPORT, (uint32_t)F184_IPC_SYNC})
+        for (uint32_t b : {(uint32_t)F184_IPC_EXPORT, (uint32_t)F184_IPC_SYNC, (uint32_t)F184_IPC_FRAG_QUEUE})
             if ((rc = f184_ipc_buffer_ptr(c, b, &dummy))) return rc;
     if (!c->gamma_table) CK(c, cudaMalloc(&c->gamma_table, 256 * sizeof(float)));
     if (!c->ev_barrier) CK(c, cudaEventCreateWithFlags(&c->ev_barrier, cudaEventDisableTiming));
@@ -451,6 +451,8 @@ void f184_destroy(f184_ctx* c)
         for (int b = 0; b < F184_IPC_COUNT; b++)
             if (pr.imported[b] && pr.buf[b]) cudaIpcCloseMemHandle(pr.buf[b]);
     if (c->export_buf) cudaFree(c->export_buf);
+    for (void* p : {(void*)c->frag_queue, (void*)c->frag_counts, (void*)c->frag_cursor})
+        if (p) cudaFree(p);
     if (c->sync_flags) cudaFree(c->sync_flags);
     if (c->sem_wait) cudaDestroyExternalSemaphore(c->sem_wait);
     if (c->sem_signal) cudaDestroyExternalSemaphore(c->sem_signal);

@@ -161,6 +161,14 @@ struct f184_ctx
         void* buf[F184_IPC_COUNT] = {};
         bool imported[F184_IPC_COUNT] = {};
     } peer[8];
+    // fragment queues (one NVLink box): frag_queue = nranks regions of frag_cap 16-byte records, region s written by rank s over
+    // NVLink; frag_counts[s] = records rank s wrote this frame (published by the sender before the barrier); frag_cursor = this
+    // rank's own append cursors, one per destination (local)
+    uint4* frag_queue = nullptr;
+    uint32_t* frag_counts = nullptr;
+    uint32_t* frag_cursor = nullptr;
+    uint32_t frag_cap = 0;
+    bool frag_sent_applied = false;           // a peer barrier has followed the last accumulation: the next one starts the queues over
     uint32_t* export_buf = nullptr;           // 1024 words per listed brick of the own slab
     uint32_t* sync_flags = nullptr;           // [8] barrier epochs written by the peers + [8] scratch
     uint32_t barrier_epoch = 0;

@@ -17,6 +17,7 @@
 //   * level 0 travels only when a cone of this rank's rows can sample it: k_need_level0 evaluates the tracer's own level
 //     selection for the first (finest) sample of every pixel's cones; with the 60-degree diffuse cones and materials of
 //     roughness >= 0.6 no cone ever reads level 0 and the gather moves 2 KB per brick instead of 4.
+#include <algorithm>
 #include <cstdlib>
 
 #include "f184_device.cuh"
@@ -390,6 +391,23 @@ int f184_ipc_buffer_ptr(f184_ctx* c, uint32_t buffer, void** out)
         }
         *out = c->brick_list;
         return F184_OK;
+    case F184_IPC_FRAG_QUEUE:
+    case F184_IPC_FRAG_COUNTS:
+        if (!c->frag_queue)
+        {   // capacity per sender: generous (4 records per triangle of the scene, 1 Mi..8 Mi); a full region is not an error, the
+            // sender falls back to remote reductions
+            static const long env_cap = [] { const char* e = getenv("F184_FRAG_QUEUE_RECORDS"); return e ? atol(e) : 0l; }();
+            uint64_t cap = env_cap > 0 ? (uint64_t)env_cap : std::min<uint64_t>(std::max<uint64_t>(4ull * c->n_tris, 1ull << 20), 8ull << 20);
+            c->frag_cap = (uint32_t)cap;
+            const uint32_t G = c->cfg.nranks ? c->cfg.nranks : 1;
+            CK(c, cudaMalloc(&c->frag_queue, sizeof(uint4) * cap * G));
+            CK(c, cudaMalloc(&c->frag_counts, 16 * sizeof(uint32_t)));
+            CK(c, cudaMalloc(&c->frag_cursor, 16 * sizeof(uint32_t)));
+            CK(c, cudaMemsetAsync(c->frag_counts, 0, 16 * sizeof(uint32_t), c->stream));
+            CK(c, cudaMemsetAsync(c->frag_cursor, 0, 16 * sizeof(uint32_t), c->stream));
+        }
+        *out = buffer == F184_IPC_FRAG_QUEUE ? (void*)c->frag_queue : (void*)c->frag_counts;
+        return F184_OK;
     case F184_IPC_SYNC:
         if (!c->sync_flags)
         {
@@ -444,6 +462,7 @@ extern "C" int f184_peer_barrier(f184_ctx* c)
         if (!c->ev_barrier) CK(c, cudaEventCreateWithFlags(&c->ev_barrier, cudaEventDisableTiming));
         CK(c, cudaEventRecord(c->ev_barrier, c->stream));
         c->barrier_recorded = true;
+        c->frag_sent_applied = true;
         return F184_OK;
     };
     return f184_leave(c, sec, body());

@@ -126,6 +126,11 @@ struct VoxArgs
     float4* accN[8];
     uint32_t* brick_flags[8];
     uint32_t owner_mask, rank;
+    // fragments of bricks another rank owns: 16-byte records appended to that rank's receive queue (this rank's region of it),
+    // coalesced stores over NVLink; cursor[p] = this rank's append position in rank p's queue (local memory)
+    uint4* peer_queue[8];
+    uint32_t* cursor;
+    uint32_t queue_cap;
     unsigned long long* frag_counter;
     unsigned long long* queue_state;   // (entries << 40) | tasks, one 64-bit word so both advance together
     uint2* queue;                      // per large triangle: (triangle, first task)
@@ -350,7 +355,25 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
             atomicAdd(A.accN[owner] + o, make_float4(nx8, ny8, nz8, 0.0f));
         }
         else
-        {   // a peer's memory over NVLink: the CUDA memory model guarantees inter-GPU atomicity at SYSTEM scope only
+        {   // another rank's brick: send the fragment.  The lanes executing this together that share a destination reserve their slots
+            // with ONE local atomic (opportunistic warp aggregation) and store their records side by side.
+            const unsigned lane = threadIdx.x & 31u;
+            const unsigned grp = __match_any_sync(__activemask(), owner);
+            const int leader = __ffs(grp) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(A.cursor + owner, (uint32_t)__popc(grp));
+            base = __shfl_sync(grp, base, leader);
+            const uint32_t slot = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+            if (slot < A.queue_cap)
+            {   // every component is an integer: 0..255 colour, -127..127 normal — a record loses nothing
+                const uint32_t rgb = (uint32_t)r8 | ((uint32_t)g8 << 8) | ((uint32_t)b8 << 16);
+                const uint32_t nrm = ((uint32_t)(int)nx8 & 255u) | (((uint32_t)(int)ny8 & 255u) << 8) | (((uint32_t)(int)nz8 & 255u) << 16);
+                A.peer_queue[owner][slot] = make_uint4((uint32_t)o, rgb, nrm, 0u);
+                frags++;
+                continue;
+            }
+            // queue full: reduce straight into the owner's memory over NVLink.  The CUDA memory model guarantees inter-GPU atomicity
+            // at SYSTEM scope only.
             red_add_v4_sys(A.accC[owner] + o, r8, g8, b8, 1.0f);
             red_add_v4_sys(A.accN[owner] + o, nx8, ny8, nz8, 0.0f);
         }
@@ -467,6 +490,41 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_voxelize_raster(const Vox
     }
     warp_count_add(A.frag_counter, frags);
 }
+
+// behind the rasteriser: tell every owner how many records this rank appended to its queue (clamped to the capacity; what did not fit
+// went over as remote reductions)
+struct PublishArgs { uint32_t* peer_counts[8]; const uint32_t* cursor; uint32_t rank, nranks, cap; };
+__global__ void k_publish_counts(const PublishArgs P)
+{
+    const uint32_t p = threadIdx.x;
+    if (p >= P.nranks || p == P.rank) return;
+    const uint32_t n = P.cursor[p];
+    P.peer_counts[p][P.rank] = n < P.cap ? n : P.cap;
+}
+__global__ void k_reset_cursors(uint32_t* cursor) { cursor[threadIdx.x] = 0u; }
+
+// owner side, at the head of normalise: apply the records the other ranks sent — two local 16-byte reductions and the brick flag per
+// record, exactly what the sender would have done to its own memory
+struct ApplyArgs { const uint4* queue; uint32_t* counts; float4 *accC, *accN; uint32_t* brick_flags; uint32_t rank, nranks, cap; };
+__global__ void __launch_bounds__(256) k_apply_fragments(const ApplyArgs P)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t s = 0; s < P.nranks; s++)
+    {
+        if (s == P.rank) continue;
+        const uint32_t n = min(P.counts[s], P.cap);
+        const uint4* q = P.queue + (size_t)s * P.cap;
+        for (uint32_t i = tid; i < n; i += stride)
+        {
+            const uint4 r = q[i];
+            const size_t o = r.x;
+            atomicAdd(P.accC + o, make_float4((float)(r.y & 255u), (float)((r.y >> 8) & 255u), (float)((r.y >> 16) & 255u), 1.0f));
+            atomicAdd(P.accN + o, make_float4((float)(int8_t)(r.z & 255u), (float)(int8_t)((r.z >> 8) & 255u), (float)(int8_t)((r.z >> 16) & 255u), 0.0f));
+            P.brick_flags[o >> 9] = 1u;
+        }
+    }
+}
+__global__ void k_clear_counts(uint32_t* counts) { counts[threadIdx.x] = 0u; }
 
 // vm[m] = View * Model[m] (same association as mode R)
 __global__ void k_view_model_n(M4 View, const M4* __restrict__ model, M4* __restrict__ vm, uint32_t n)
@@ -634,6 +692,24 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
     }
     A.owner_mask = G > 1 ? G - 1 : 0;
     A.rank = G > 1 ? c->cfg.rank : 0;
+    PublishArgs PA{};
+    if (G > 1)
+    {
+        void* dummy = nullptr;
+        int rc = f184_ipc_buffer_ptr(c, F184_IPC_FRAG_QUEUE, &dummy);
+        if (rc) return rc;
+        for (uint32_t p = 0; p < G; p++)
+        {
+            if (p == c->cfg.rank) continue;
+            if (!c->peer[p].buf[F184_IPC_FRAG_QUEUE] || !c->peer[p].buf[F184_IPC_FRAG_COUNTS])
+                return f184_fail(c, F184_ERR_NOT_READY, "voxelize: fragment queue of rank %u was not imported (f184_ipc_import)", p);
+            A.peer_queue[p] = reinterpret_cast<uint4*>(c->peer[p].buf[F184_IPC_FRAG_QUEUE]) + (size_t)c->cfg.rank * c->frag_cap;
+            PA.peer_counts[p] = reinterpret_cast<uint32_t*>(c->peer[p].buf[F184_IPC_FRAG_COUNTS]);
+        }
+        A.cursor = c->frag_cursor;
+        A.queue_cap = c->frag_cap;
+        PA.cursor = c->frag_cursor; PA.rank = c->cfg.rank; PA.nranks = G; PA.cap = c->frag_cap;
+    }
     c->voxel_h = f184_voxel_h(cam->ProjMat, cam->ViewMat, c->cfg.grid_n);
     M4 View;
     memcpy(View.m, cam->ViewMat, 64);
@@ -648,6 +724,13 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
     if (rc) return rc;
     // device words after the public counters: [COUNT] brick-list cursor, [COUNT+1] voxelizer queue state, [COUNT+2] mip tail ticket
     if ((rc = f184_zero_counters(c, (1u << F184_COUNTER_FRAGMENTS) | (1u << (F184_COUNTER_COUNT + 1))))) return rc;
+    if (G > 1 && c->frag_sent_applied)
+    {   // the owners have applied (or are about to apply, behind the barrier that followed) what this rank sent last time: start the
+        // queues over.  Accumulations that follow each other WITHOUT a barrier in between keep appending (partial volumes add up).
+        k_reset_cursors<<<1, 16, 0, c->stream>>>(c->frag_cursor);
+        CK_LAUNCH(c);
+        c->frag_sent_applied = false;
+    }
     if (end > first)
     {
         A.pos = c->pos; A.nrm = c->nrm; A.uv = c->uv; A.idx = c->idx; A.tri_mat = c->tri_mat; A.tri_model = c->tri_model;
@@ -666,6 +749,11 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
         k_voxelize_raster<<<148 * 4 * 4, RASTER_THREADS, 0, c->stream>>>(A);
         CK_LAUNCH(c);
     }
+    if (G > 1)
+    {
+        k_publish_counts<<<1, 32, 0, c->stream>>>(PA);
+        CK_LAUNCH(c);
+    }
     return f184_stage_end(c, F184_STAGE_VOXELIZE);
 }
 
@@ -677,6 +765,15 @@ int f184_normalise_n(f184_ctx* c)
     const uint32_t n_own = (NB / G) * NB * NB;
     int rc = f184_stage_begin(c, F184_STAGE_NORMALISE);
     if (rc) return rc;
+    if (G > 1 && c->frag_queue)
+    {   // the fragments the other ranks sent (their counts were published before the barrier this call follows)
+        ApplyArgs P{c->frag_queue, c->frag_counts, img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
+                    img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->cfg.rank, G, c->frag_cap};
+        k_apply_fragments<<<148 * 8, 256, 0, c->stream>>>(P);
+        CK_LAUNCH(c);
+        k_clear_counts<<<1, 16, 0, c->stream>>>(c->frag_counts);      // applied once
+        CK_LAUNCH(c);
+    }
     if ((rc = f184_zero_counters(c, (1u << F184_COUNTER_OCCUPIED) | (1u << F184_COUNTER_BRICKS) | (1u << F184_COUNTER_COUNT)))) return rc;   // COUNT = the list cursor
     k_brick_compact<<<(n_own + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,
                                                               c->counters_dev, n_own, NB, G, c->cfg.rank % G);

@@ -34,6 +34,11 @@ def test_four_loopback_ranks_equal_one_context():
     run("box4")
 
 
+def test_full_fragment_queues_fall_back_to_remote_reductions():
+    """a receive queue of 2000 records overflows at once: everything beyond it takes the system-scope reduction path, same volume"""
+    run("box2", F184_FRAG_QUEUE_RECORDS="2000")
+
+
 def test_four_loopback_ranks_sponza_256():
     run("sponza")
 
