@@ -164,6 +164,8 @@ struct f184_ctx
     // fragment queues (one NVLink box): frag_queue = nranks regions of frag_cap 16-byte records, region s written by rank s over
     // NVLink; frag_counts[s] = records rank s wrote this frame (published by the sender before the barrier); frag_cursor = this
     // rank's own append cursors, one per destination (local)
+    // Each sender's region is split into F184_FRAG_SUBQUEUES sub-queues with a cursor of their own (a warp uses the one its index
+    // selects): one cursor per destination made every warp of the GPU hammer the same address with returning atomics.
     uint4* frag_queue = nullptr;
     uint32_t* frag_counts = nullptr;
     uint32_t* frag_cursor = nullptr;
@@ -197,6 +199,8 @@ struct f184_ctx
     // interop
     cudaExternalSemaphore_t sem_wait = nullptr, sem_signal = nullptr;
 };
+
+#define F184_FRAG_SUBQUEUES 32
 
 // dev_state words
 enum { F184_DEV_ERROR = 0,       // sticky error bits (F184_DEVERR_*), reported by the next synchronous call

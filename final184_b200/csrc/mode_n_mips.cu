@@ -224,7 +224,7 @@ struct BrickMipOut
     uint32_t* lin[3][6];               // level 1..3, six directions, linear chain
     cudaSurfaceObject_t surf[3];       // atlas levels 1..3
 };
-constexpr int BRICK_WARPS = 8;
+constexpr int BRICK_WARPS = 4;                                    // 128 threads x 128 registers = 16 K: fits the hole a retiring trace CTA leaves
 constexpr int BRICK_STAGES = 3;                                   // TMA ring per warp: 3 x 2 KB bricks in flight
 constexpr int BRICK_RING_BYTES = BRICK_WARPS * BRICK_STAGES * 2048;
 
@@ -597,11 +597,11 @@ int f184_mips_n(f184_ctx* c)
                 CK(c, cudaFuncSetAttribute(k_mips_bricks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BRICK_RING_BYTES));
                 brick_attr = true;
             }
-            k_mips_bricks<true><<<148 * 2, BRICK_WARPS * 32, BRICK_RING_BYTES, c->stream>>>(map, level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N,
+            k_mips_bricks<true><<<148 * 4, BRICK_WARPS * 32, BRICK_RING_BYTES, c->stream>>>(map, level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N,
                                                                                            export_buf, prev, 2u << c->build_set);
         }
         else
-            k_mips_bricks<false><<<148 * 4, BRICK_WARPS * 32, BRICK_WARPS * 2048, c->stream>>>(map, level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N,
+            k_mips_bricks<false><<<148 * 8, BRICK_WARPS * 32, BRICK_WARPS * 2048, c->stream>>>(map, level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N,
                                                                                               export_buf, prev, 2u << c->build_set);
         CK_LAUNCH(c);
         first_dense = c->n_mip_levels;          // the tail kernel takes every remaining level

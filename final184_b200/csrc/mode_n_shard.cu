@@ -398,13 +398,14 @@ int f184_ipc_buffer_ptr(f184_ctx* c, uint32_t buffer, void** out)
             // sender falls back to remote reductions
             static const long env_cap = [] { const char* e = getenv("F184_FRAG_QUEUE_RECORDS"); return e ? atol(e) : 0l; }();
             uint64_t cap = env_cap > 0 ? (uint64_t)env_cap : std::min<uint64_t>(std::max<uint64_t>(4ull * c->n_tris, 1ull << 20), 8ull << 20);
+            cap = (cap + F184_FRAG_SUBQUEUES - 1) / F184_FRAG_SUBQUEUES * F184_FRAG_SUBQUEUES;
             c->frag_cap = (uint32_t)cap;
             const uint32_t G = c->cfg.nranks ? c->cfg.nranks : 1;
             CK(c, cudaMalloc(&c->frag_queue, sizeof(uint4) * cap * G));
-            CK(c, cudaMalloc(&c->frag_counts, 16 * sizeof(uint32_t)));
-            CK(c, cudaMalloc(&c->frag_cursor, 16 * sizeof(uint32_t)));
-            CK(c, cudaMemsetAsync(c->frag_counts, 0, 16 * sizeof(uint32_t), c->stream));
-            CK(c, cudaMemsetAsync(c->frag_cursor, 0, 16 * sizeof(uint32_t), c->stream));
+            CK(c, cudaMalloc(&c->frag_counts, 8 * F184_FRAG_SUBQUEUES * sizeof(uint32_t)));
+            CK(c, cudaMalloc(&c->frag_cursor, 8 * F184_FRAG_SUBQUEUES * sizeof(uint32_t)));
+            CK(c, cudaMemsetAsync(c->frag_counts, 0, 8 * F184_FRAG_SUBQUEUES * sizeof(uint32_t), c->stream));
+            CK(c, cudaMemsetAsync(c->frag_cursor, 0, 8 * F184_FRAG_SUBQUEUES * sizeof(uint32_t), c->stream));
         }
         *out = buffer == F184_IPC_FRAG_QUEUE ? (void*)c->frag_queue : (void*)c->frag_counts;
         return F184_OK;

@@ -137,12 +137,18 @@ __device__ f3 trace_cone(const ConeParams& P, f3 origin, f3 dir, float tan_half,
 __device__ __forceinline__ float unorm16(uint16_t v) { return (float)v / 65535.0f; }
 __device__ __forceinline__ int wrapn(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
 
+// CTA = 256 threads = a 32 x 8 pixel strip of eight 8 x 4 warp tiles, 64 registers per thread: FOUR CTAs fill an SM's register
+// file, so every CTA that retires leaves a hole of 16 K registers — and every kernel of the build stream (frame pipeline) is
+// shaped to fit that hole (<= 16 K registers per CTA).  With 128-thread CTAs the holes were 8 K registers, no build kernel fitted
+// one, the block scheduler back-filled them with the next trace CTA, and the "concurrent" build kernels waited for the trace grid
+// to drain (the gather took 4.0 ms beside the trace, 0.6 ms alone).
+constexpr int TRACE_THREADS = 256;
 template <int MIN_CTAS, bool SPEC_B>
-__global__ void __launch_bounds__(128, MIN_CTAS) k_trace_n(const ConeParams P, unsigned long long* __restrict__ sample_counter)
+__global__ void __launch_bounds__(TRACE_THREADS, MIN_CTAS) k_trace_n(const ConeParams P, unsigned long long* __restrict__ sample_counter)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const uint32_t y = P.y0 + (P.tile0 + blockIdx.y * P.tile_stride) * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const uint32_t y = P.y0 + (P.tile0 + blockIdx.y * P.tile_stride) * 8 + (warp >> 2) * 4 + (lane >> 3);
     unsigned int samples = 0;
     if (x < P.W && y < P.y1)
     {
@@ -261,12 +267,12 @@ static int trace_params(f184_ctx* c, const VolumeSet& vs, const f184_trace_const
 
 static int trace_launch(f184_ctx* c, const ConeParams& P, uint32_t grid_y, cudaStream_t stream)
 {
-    dim3 grid((P.W + 15) / 16, grid_y);
-    // two register budgets of the same kernel: 8 CTAs/SM (64 registers) or 7 (72, no spill); F184_TRACE_CTAS=7 selects the latter (A/B knob)
-    static const int min_ctas = [] { const char* e = getenv("F184_TRACE_CTAS"); return e ? atoi(e) : 8; }();
-    if (c->cfg.flags & F184_FLAG_SPEC_APPENDIX_B) k_trace_n<7, true><<<grid, 128, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
-    else if (min_ctas == 7) k_trace_n<7, false><<<grid, 128, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
-    else k_trace_n<8, false><<<grid, 128, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+    dim3 grid((P.W + 31) / 32, grid_y);
+    // two register budgets of the same kernel: 4 CTAs/SM (64 registers) or 3 (80, no spill); F184_TRACE_CTAS=3 selects the latter (A/B knob)
+    static const int min_ctas = [] { const char* e = getenv("F184_TRACE_CTAS"); return e ? atoi(e) : 4; }();
+    if (c->cfg.flags & F184_FLAG_SPEC_APPENDIX_B) k_trace_n<3, true><<<grid, TRACE_THREADS, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+    else if (min_ctas == 3) k_trace_n<3, false><<<grid, TRACE_THREADS, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
+    else k_trace_n<4, false><<<grid, TRACE_THREADS, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
     CK_LAUNCH(c);
     return F184_OK;
 }

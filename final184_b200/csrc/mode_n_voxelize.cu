@@ -127,10 +127,11 @@ struct VoxArgs
     uint32_t* brick_flags[8];
     uint32_t owner_mask, rank;
     // fragments of bricks another rank owns: 16-byte records appended to that rank's receive queue (this rank's region of it),
-    // coalesced stores over NVLink; cursor[p] = this rank's append position in rank p's queue (local memory)
+    // coalesced stores over NVLink; cursor[p][s] = this rank's append position in sub-queue s of its region of rank p's queue
+    // (local memory; a warp appends to the sub-queue its index selects)
     uint4* peer_queue[8];
     uint32_t* cursor;
-    uint32_t queue_cap;
+    uint32_t sub_cap;                  // records per sub-queue
     unsigned long long* frag_counter;
     unsigned long long* queue_state;   // (entries << 40) | tasks, one 64-bit word so both advance together
     uint2* queue;                      // per large triangle: (triangle, first task)
@@ -358,17 +359,18 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
         {   // another rank's brick: send the fragment.  The lanes executing this together that share a destination reserve their slots
             // with ONE local atomic (opportunistic warp aggregation) and store their records side by side.
             const unsigned lane = threadIdx.x & 31u;
+            const unsigned sub = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) & (F184_FRAG_SUBQUEUES - 1u);
             const unsigned grp = __match_any_sync(__activemask(), owner);
             const int leader = __ffs(grp) - 1;
             uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(A.cursor + owner, (uint32_t)__popc(grp));
+            if ((int)lane == leader) base = atomicAdd(A.cursor + owner * F184_FRAG_SUBQUEUES + sub, (uint32_t)__popc(grp));
             base = __shfl_sync(grp, base, leader);
             const uint32_t slot = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-            if (slot < A.queue_cap)
+            if (slot < A.sub_cap)
             {   // every component is an integer: 0..255 colour, -127..127 normal — a record loses nothing
                 const uint32_t rgb = (uint32_t)r8 | ((uint32_t)g8 << 8) | ((uint32_t)b8 << 16);
                 const uint32_t nrm = ((uint32_t)(int)nx8 & 255u) | (((uint32_t)(int)ny8 & 255u) << 8) | (((uint32_t)(int)nz8 & 255u) << 16);
-                A.peer_queue[owner][slot] = make_uint4((uint32_t)o, rgb, nrm, 0u);
+                A.peer_queue[owner][(size_t)sub * A.sub_cap + slot] = make_uint4((uint32_t)o, rgb, nrm, 0u);
                 frags++;
                 continue;
             }
@@ -389,7 +391,7 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
 // whole chip instead of serialising one warp.  Queue slots and task numbers are reserved by ONE 64-bit atomic per
 // warp, (entries << 40) | tasks, which keeps `first task` monotone in the entry index: pass 2 finds the triangle of
 // a task by binary search, no prefix-sum pass needed.  The set-up travels with the queue entry (192 B).
-__global__ void __launch_bounds__(SETUP_THREADS) k_voxelize_setup(const VoxArgs A)
+__global__ void __launch_bounds__(SETUP_THREADS, 4) k_voxelize_setup(const VoxArgs A)
 {
     const int lane = threadIdx.x & 31;
     static_assert(SETUP_THREADS == F184_TRIANGLE_CHUNK, "one CTA of the set-up pass = one chunk");
@@ -493,38 +495,35 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_voxelize_raster(const Vox
 
 // behind the rasteriser: tell every owner how many records this rank appended to its queue (clamped to the capacity; what did not fit
 // went over as remote reductions)
-struct PublishArgs { uint32_t* peer_counts[8]; const uint32_t* cursor; uint32_t rank, nranks, cap; };
-__global__ void k_publish_counts(const PublishArgs P)
+struct PublishArgs { uint32_t* peer_counts[8]; const uint32_t* cursor; uint32_t rank, nranks, sub_cap; };
+__global__ void k_publish_counts(const PublishArgs P)           // <<<nranks, F184_FRAG_SUBQUEUES>>>
 {
-    const uint32_t p = threadIdx.x;
+    const uint32_t p = blockIdx.x, s = threadIdx.x;
     if (p >= P.nranks || p == P.rank) return;
-    const uint32_t n = P.cursor[p];
-    P.peer_counts[p][P.rank] = n < P.cap ? n : P.cap;
+    const uint32_t n = P.cursor[p * F184_FRAG_SUBQUEUES + s];
+    P.peer_counts[p][P.rank * F184_FRAG_SUBQUEUES + s] = n < P.sub_cap ? n : P.sub_cap;
 }
-__global__ void k_reset_cursors(uint32_t* cursor) { cursor[threadIdx.x] = 0u; }
+__global__ void k_reset_cursors(uint32_t* cursor) { cursor[threadIdx.x] = 0u; }           // <<<1, 8 * F184_FRAG_SUBQUEUES>>>
 
 // owner side, at the head of normalise: apply the records the other ranks sent — two local 16-byte reductions and the brick flag per
 // record, exactly what the sender would have done to its own memory
-struct ApplyArgs { const uint4* queue; uint32_t* counts; float4 *accC, *accN; uint32_t* brick_flags; uint32_t rank, nranks, cap; };
-__global__ void __launch_bounds__(256) k_apply_fragments(const ApplyArgs P)
+struct ApplyArgs { const uint4* queue; uint32_t* counts; float4 *accC, *accN; uint32_t* brick_flags; uint32_t rank, nranks, cap, sub_cap; };
+__global__ void __launch_bounds__(256) k_apply_fragments(const ApplyArgs P)     // grid (16, nranks * F184_FRAG_SUBQUEUES): blockIdx.y = one sub-queue
 {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (uint32_t s = 0; s < P.nranks; s++)
+    const uint32_t s = blockIdx.y / F184_FRAG_SUBQUEUES, sub = blockIdx.y % F184_FRAG_SUBQUEUES;
+    if (s == P.rank) return;
+    const uint32_t n = min(P.counts[blockIdx.y], P.sub_cap);
+    const uint4* q = P.queue + (size_t)s * P.cap + (size_t)sub * P.sub_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
-        if (s == P.rank) continue;
-        const uint32_t n = min(P.counts[s], P.cap);
-        const uint4* q = P.queue + (size_t)s * P.cap;
-        for (uint32_t i = tid; i < n; i += stride)
-        {
-            const uint4 r = q[i];
-            const size_t o = r.x;
-            atomicAdd(P.accC + o, make_float4((float)(r.y & 255u), (float)((r.y >> 8) & 255u), (float)((r.y >> 16) & 255u), 1.0f));
-            atomicAdd(P.accN + o, make_float4((float)(int8_t)(r.z & 255u), (float)(int8_t)((r.z >> 8) & 255u), (float)(int8_t)((r.z >> 16) & 255u), 0.0f));
-            P.brick_flags[o >> 9] = 1u;
-        }
+        const uint4 r = q[i];
+        const size_t o = r.x;
+        atomicAdd(P.accC + o, make_float4((float)(r.y & 255u), (float)((r.y >> 8) & 255u), (float)((r.y >> 16) & 255u), 1.0f));
+        atomicAdd(P.accN + o, make_float4((float)(int8_t)(r.z & 255u), (float)(int8_t)((r.z >> 8) & 255u), (float)(int8_t)((r.z >> 16) & 255u), 0.0f));
+        P.brick_flags[o >> 9] = 1u;
     }
 }
-__global__ void k_clear_counts(uint32_t* counts) { counts[threadIdx.x] = 0u; }
+__global__ void k_clear_counts(uint32_t* counts) { counts[threadIdx.x] = 0u; }           // <<<1, 8 * F184_FRAG_SUBQUEUES>>>
 
 // vm[m] = View * Model[m] (same association as mode R)
 __global__ void k_view_model_n(M4 View, const M4* __restrict__ model, M4* __restrict__ vm, uint32_t n)
@@ -707,8 +706,8 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
             PA.peer_counts[p] = reinterpret_cast<uint32_t*>(c->peer[p].buf[F184_IPC_FRAG_COUNTS]);
         }
         A.cursor = c->frag_cursor;
-        A.queue_cap = c->frag_cap;
-        PA.cursor = c->frag_cursor; PA.rank = c->cfg.rank; PA.nranks = G; PA.cap = c->frag_cap;
+        A.sub_cap = c->frag_cap / F184_FRAG_SUBQUEUES;
+        PA.cursor = c->frag_cursor; PA.rank = c->cfg.rank; PA.nranks = G; PA.sub_cap = A.sub_cap;
     }
     c->voxel_h = f184_voxel_h(cam->ProjMat, cam->ViewMat, c->cfg.grid_n);
     M4 View;
@@ -727,7 +726,7 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
     if (G > 1 && c->frag_sent_applied)
     {   // the owners have applied (or are about to apply, behind the barrier that followed) what this rank sent last time: start the
         // queues over.  Accumulations that follow each other WITHOUT a barrier in between keep appending (partial volumes add up).
-        k_reset_cursors<<<1, 16, 0, c->stream>>>(c->frag_cursor);
+        k_reset_cursors<<<1, 8 * F184_FRAG_SUBQUEUES, 0, c->stream>>>(c->frag_cursor);
         CK_LAUNCH(c);
         c->frag_sent_applied = false;
     }
@@ -751,7 +750,7 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
     }
     if (G > 1)
     {
-        k_publish_counts<<<1, 32, 0, c->stream>>>(PA);
+        k_publish_counts<<<G, F184_FRAG_SUBQUEUES, 0, c->stream>>>(PA);
         CK_LAUNCH(c);
     }
     return f184_stage_end(c, F184_STAGE_VOXELIZE);
@@ -768,17 +767,17 @@ int f184_normalise_n(f184_ctx* c)
     if (G > 1 && c->frag_queue)
     {   // the fragments the other ranks sent (their counts were published before the barrier this call follows)
         ApplyArgs P{c->frag_queue, c->frag_counts, img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
-                    img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->cfg.rank, G, c->frag_cap};
-        k_apply_fragments<<<148 * 8, 256, 0, c->stream>>>(P);
+                    img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->cfg.rank, G, c->frag_cap, c->frag_cap / F184_FRAG_SUBQUEUES};
+        k_apply_fragments<<<dim3(16, G * F184_FRAG_SUBQUEUES), 256, 0, c->stream>>>(P);
         CK_LAUNCH(c);
-        k_clear_counts<<<1, 16, 0, c->stream>>>(c->frag_counts);      // applied once
+        k_clear_counts<<<1, 8 * F184_FRAG_SUBQUEUES, 0, c->stream>>>(c->frag_counts);      // applied once
         CK_LAUNCH(c);
     }
     if ((rc = f184_zero_counters(c, (1u << F184_COUNTER_OCCUPIED) | (1u << F184_COUNTER_BRICKS) | (1u << F184_COUNTER_COUNT)))) return rc;   // COUNT = the list cursor
     k_brick_compact<<<(n_own + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,
                                                               c->counters_dev, n_own, NB, G, c->cfg.rank % G);
     CK_LAUNCH(c);
-    k_normalise_n<<<148 * 8, 256, 0, c->stream>>>(img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
+    k_normalise_n<<<148 * 16, 128, 0, c->stream>>>(img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
                                                   img_ptr<uchar4>(c, F184_SLOT_VOX_ALBEDO), img_ptr<char4>(c, F184_SLOT_VOX_NORMAL),
                                                   c->brick_list, c->counters_dev, N);
     CK_LAUNCH(c);

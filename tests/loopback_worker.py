@@ -191,7 +191,7 @@ def run_barrier_timeout(bad):
     c = A.VoxelGI(N, W, H, A.MODE_NORTHSTAR, shadow_res=64, device=0, rank=0, nranks=2)
     c.upload_scene(sc)
     sizes = {A.IPC_ACCUM_COLOR: N ** 3 * 16, A.IPC_ACCUM_NORMAL: N ** 3 * 16, A.IPC_BRICK_FLAGS: (N // 8) ** 3 * 4, A.IPC_EXPORT: (N // 8) ** 3 * 4096,
-             A.IPC_COUNTERS: 128, A.IPC_BRICK_LIST: (N // 8) ** 3 * 4, A.IPC_SYNC: 64}
+             A.IPC_COUNTERS: 128, A.IPC_BRICK_LIST: (N // 8) ** 3 * 4, A.IPC_SYNC: 64, A.IPC_FRAG_QUEUE: 2 * (1 << 20) * 16, A.IPC_FRAG_COUNTS: 8 * 32 * 4}
     fake = {b: torch.zeros(n, dtype=torch.uint8, device="cuda:0") for b, n in sizes.items()}     # a "peer" nobody runs
     for b, t in fake.items():
         c.ipc_ptr(b)
