@@ -535,7 +535,8 @@ class Arm:
     def parity_vs_1gpu(self, levels_from=1):
         """Every rank computes the whole frame alone (one context, the whole scene, every row) and compares it with what the sharded
         schedule left on this rank: the texture-side storage the tracer samples (all six directions of every level >= levels_from;
-        level 0 travels only when a cone needs it) and this rank's image rows — equal bits or a named mismatch."""
+        level 0 travels only when a cone needs it, level 1 only for the bricks this rank's cones sample — their correctness shows in the
+        rows) and this rank's image rows — equal bits or a named mismatch."""
         A, torch, dist, g = self.A, self.torch, self.dist, self.g
         one = A.VoxelGI(self.N, self.W, self.H, A.MODE_NORTHSTAR, shadow_res=g.ctx.cfg.shadow_res, device=self.local_rank, flags=A.FLAG_NO_OVERLAP)
         one.upload_scene(self.sc)
@@ -642,7 +643,7 @@ def run_b200(args, rank, world, local_rank):
     arm = Arm(A, torch, dist, N, W, H, args.shadow, sc, cams, fi, rank, world, local_rank, stream, schedule=args.schedule,
               flags=A.FLAG_NO_OVERLAP if args.no_overlap else 0)
     g = arm.g
-    parity = arm.parity_vs_1gpu() if (world > 1 and not args.no_extras) else None
+    parity = arm.parity_vs_1gpu(levels_from=2) if (world > 1 and not args.no_extras) else None
 
     # ---- timed region 1: device-resident inputs
     r = arm.timed(args.steps, args.warmup, clocks=True)

@@ -190,6 +190,7 @@ _PRODUCT_ONLY = {
     "ipc_import": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "peer_barrier": (C.c_int, [C.c_void_p]),
     "gather_volume": (C.c_int, [C.c_void_p]),
+    "gather_volume_view": (C.c_int, [C.c_void_p, C.POINTER(TraceConstantsC)]),
     "stage_time_reset": (C.c_int, [C.c_void_p, C.c_uint32]),
     "stage_time_total": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "microbench": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_double)]),
@@ -368,8 +369,12 @@ class VoxelGI:
     def peer_barrier(self):
         self._ck(self.lib.peer_barrier(self.h), "peer_barrier")
 
-    def gather_volume(self):
-        self._ck(self.lib.gather_volume(self.h), "gather_volume")
+    def gather_volume(self, k: TraceConstantsC | None = None):
+        """k: the constants of the trace that follows — level 1 then travels only where its cones sample it"""
+        if k is None:
+            self._ck(self.lib.gather_volume(self.h), "gather_volume")
+        else:
+            self._ck(self.lib.gather_volume_view(self.h, C.byref(k)), "gather_volume_view")
 
     def inject(self, k: TraceConstantsC):
         self._ck(self.lib.inject(self.h, C.byref(k.sun), C.byref(k.ext)), "inject")

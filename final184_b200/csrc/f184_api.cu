@@ -442,7 +442,7 @@ void f184_destroy(f184_ctx* c)
     for (void* p : {(void*)c->pos, (void*)c->nrm, (void*)c->uv, (void*)c->model_mats, (void*)c->idx, (void*)c->tri_mat,
                     (void*)c->tri_model, (void*)c->tex_dev, (void*)c->mat_dev, (void*)c->vox_keys, (void*)c->counters_dev,
                     (void*)c->brick_prev, (void*)c->brick_list, (void*)c->vox_queue, (void*)c->vm_dev, (void*)c->gamma_table, c->gtao_phi_table,
-                    (void*)c->dev_state, (void*)c->chunk_list})
+                    (void*)c->dev_state, (void*)c->chunk_list, (void*)c->need1, (void*)c->l1_nonzero[0], (void*)c->l1_nonzero[1]})
         if (p) cudaFree(p);
     for (uint8_t* p : c->tex_alloc) if (p) cudaFree(p);
     for (int s = 0; s < F184_STAGE_COUNT; s++)
@@ -959,16 +959,22 @@ int f184_normalise(f184_ctx* c)
     }
     return f184_leave(c, sec, rc);
 }
-int f184_gather_volume(f184_ctx* c)
+int f184_gather_volume_view(f184_ctx* c, const f184_trace_constants* view)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
     if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "gather_volume is a north-star stage");
     CK(c, cudaSetDevice(c->cfg.device));
+    int rc = F184_OK;
+    // the gather looks at the G-buffer (which levels / bricks do this rank's cones sample?): caller-owned images are written by the
+    // caller's own work on the pass stream, the build stream starts behind it
+    for (int s : {F184_SLOT_DEPTH, F184_SLOT_NORMALS, F184_SLOT_MATERIAL})
+        if (c->img[s].ptr && (!c->img[s].owned || c->img[s].ext)) { if ((rc = f184_pass_wrote(c))) return rc; break; }
     F184Section sec;
-    int rc = f184_enter(c, F184_SID_BUILD, &sec);
+    rc = f184_enter(c, F184_SID_BUILD, &sec);
     if (rc) return rc;
-    return f184_leave(c, sec, f184_gather_n(c));
+    return f184_leave(c, sec, f184_gather_n(c, view));
 }
+int f184_gather_volume(f184_ctx* c) { return f184_gather_volume_view(c, nullptr); }
 
 // ---- CUDA IPC: share a context buffer with the other ranks of the box ----------------------------------------
 int f184_ipc_export(f184_ctx* c, uint32_t buffer, f184_ipc_handle* out)

@@ -161,21 +161,24 @@ struct f184_ctx
         void* buf[F184_IPC_COUNT] = {};
         bool imported[F184_IPC_COUNT] = {};
     } peer[8];
-    // fragment queues (one NVLink box): frag_queue = nranks regions of frag_cap 16-byte records, region s written by rank s over
-    // NVLink; frag_counts[s] = records rank s wrote this frame (published by the sender before the barrier); frag_cursor = this
-    // rank's own append cursors, one per destination (local)
+    // fragment queues (one NVLink box), all in THIS rank's memory: frag_queue = nranks regions of frag_cap 16-byte records, region p =
+    // the fragments this rank rasterised for rank p, which p reads over NVLink behind the barrier; frag_cursor = the append cursors
+    // (= record counts, what p reads first); frag_counts: unused scratch
     // Each sender's region is split into F184_FRAG_SUBQUEUES sub-queues with a cursor of their own (a warp uses the one its index
     // selects): one cursor per destination made every warp of the GPU hammer the same address with returning atomics.
     uint4* frag_queue = nullptr;
     uint32_t* frag_counts = nullptr;
     uint32_t* frag_cursor = nullptr;
     uint32_t frag_cap = 0;
+    bool frag_pending = false;                // an accumulation has run since the last normalise: the peers' queues hold fragments for this rank
     bool frag_sent_applied = false;           // a peer barrier has followed the last accumulation: the next one starts the queues over
     uint32_t* export_buf = nullptr;           // 1024 words per listed brick of the own slab
     uint32_t* sync_flags = nullptr;           // [8] barrier epochs written by the peers + [8] scratch
     uint32_t barrier_epoch = 0;
     // device-side state words (F184_DEV_*): sticky error bits and the level-0 bookkeeping of the peer gather
     uint32_t* dev_state = nullptr;
+    uint32_t* need1 = nullptr;                // bit per brick: level 1 of the brick is sampled by a cone of this rank's rows (k_need_bricks)
+    uint32_t* l1_nonzero[2] = {nullptr, nullptr};   // per texture set, bit per brick: this rank's copy of a foreign brick's level 1 is not zero
     bool prepared = false;                    // the first f184_voxelize_accumulate has allocated everything a frame touches
     float voxel_h = 0.0f;                     // voxel size under the voxel camera of the last f184_voxelize (level-0 test of the gather)
     bool inject_in_volume = false;            // f184_inject has written the open build set (its level 0 is current)
@@ -292,7 +295,7 @@ int f184_mode_n_alloc(f184_ctx* c);
 int f184_normalise_n(f184_ctx* c);
 int f184_voxelizer_scratch_n(f184_ctx* c);
 int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam);
-int f184_gather_n(f184_ctx* c);
+int f184_gather_n(f184_ctx* c, const f184_trace_constants* view);
 int f184_ipc_buffer_ptr(f184_ctx* c, uint32_t buffer, void** out);
 M4 f184_invert_m4(const M4& A);
 // world size of one voxel along voxel-x under the voxel camera (Proj * View), the `h` of the cone tracer

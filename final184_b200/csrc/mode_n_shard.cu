@@ -71,35 +71,124 @@ __global__ void k_peer_barrier(const BarrierArgs B)
     }
 }
 
-// Does any cone of this rank's rows sample level 0 of the volume?  Evaluates the tracer's level selection (f184_cone.cuh) at the
-// first sample of each cone — the finest one: the footprint only grows with distance.  The diffuse cones are the same for
-// every pixel; the specular cone depends on the pixel's roughness.
+// What does the cone trace of this rank's rows need from the OTHER ranks?  Replays the tracer's per-pixel set-up and level selection
+// (mode_n_trace.cu; same expressions) without touching the volume:
+//   * level 0 at all?  (dev_state[F184_DEV_NEED_L0]: some cone's first — finest — sample selects it.)  With 60-degree diffuse cones and
+//     rough materials none does, and level 0 (2 KB of every 4 KB record) stays home;
+//   * level 1 of WHICH bricks?  A cone reads level 1 only while its footprint is under ~3 voxels: the first sample of a diffuse
+//     cone, 2.3 voxels above the surface the pixel shows.  So level 1 is needed exactly around the surfaces this rank's pixels see —
+//     a fraction of the scene (the interiors of seven of C4's eight buildings are invisible from the camera) — and every sample a
+//     cone takes at level <= 1 marks the bricks under its trilinear footprint (1/16-texel margin) in a bit mask the gather consults.
+// No early termination on opacity here (it would need the volume): the marching stops where the tracer's level selection passes 1.
 struct NeedArgs
 {
+    M4 InvProj, InvModelView, w2v;
     const float* depth;
+    const uint16_t* normals;
     const uchar4* material;
-    uint32_t W, y0, y1, tile0, tile_stride, n_tiles;
-    float h;
-    uint32_t spec_b;
+    uint32_t W, H, y0, y1, tile0, tile_stride, n_tiles;
+    float h, max_dist;
+    f3 cam;
+    uint32_t spec_b, N, no_view;       // no_view: no camera given — only the level-0 question is answered (it needs the roughness alone)
     uint32_t* dev_state;
+    uint32_t* need1;                   // bit per brick: level 1 of the brick is sampled by a cone of this rank's rows
 };
-__global__ void __launch_bounds__(256) k_need_level0(const NeedArgs A)
+
+__device__ __forceinline__ void mark_brick(uint32_t* need1, int bx, int by, int bz, int NB)
 {
-    bool need = false;
-    if (blockIdx.x == 0 && threadIdx.x == 0) need = cone_samples_level0(kTanHalfDiffuse, A.h, A.spec_b != 0);
-    for (uint32_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x)
+    if ((unsigned)bx >= (unsigned)NB || (unsigned)by >= (unsigned)NB || (unsigned)bz >= (unsigned)NB) return;
+    const uint32_t b = ((uint32_t)bz * NB + by) * NB + bx, bit = 1u << (b & 31u);
+    if (!(need1[b >> 5] & bit)) atomicOr(need1 + (b >> 5), bit);
+}
+
+// one cone: every sample it takes while its level is <= 1; returns whether it touches level 0
+__device__ bool mark_cone(const NeedArgs& A, f3 origin, f3 dir, float tan_half)
+{
+    const float h = A.h, inv_h = 1.0f / h;
+    const f3 dv = {(A.w2v.m[0] * dir.x + A.w2v.m[4] * dir.y + A.w2v.m[8] * dir.z) * 0.5f,
+                   (A.w2v.m[1] * dir.x + A.w2v.m[5] * dir.y + A.w2v.m[9] * dir.z) * 0.5f,
+                   (A.w2v.m[2] * dir.x + A.w2v.m[6] * dir.y + A.w2v.m[10] * dir.z)};
+    const f3 o3 = mul43(A.w2v, origin, 1.0f);
+    const f3 q0 = {o3.x * 0.5f + 0.5f, o3.y * 0.5f + 0.5f, o3.z};
+    const float n1 = (float)(A.N >> 1);
+    const int NB = (int)(A.N >> 3);
+    bool level0 = false;
+    float t = 2.0f * h;
+    while (t < A.max_dist)
     {
-        const uint32_t yb = A.y0 + (A.tile0 + t * A.tile_stride) * 8;
-        for (uint32_t i = threadIdx.x; i < 8 * A.W; i += blockDim.x)
-        {
-            const uint32_t y = yb + i / A.W, x = i % A.W;
-            if (y >= A.y1) break;
-            if (__ldg(A.depth + (size_t)y * A.W + x) >= 1.0f) continue;
+        float diam;
+        const float lod = cone_lod(t, tan_half, h, inv_h, &diam);
+        // level 1 (atlas level 0) is read while: nearest spec L = floor(lod + .5) <= 1; Appendix-B spec: the mip-linear fetch at lod - 1 < 1
+        if (lod >= (A.spec_b ? 2.0f : 1.5f) + 1e-3f) break;
+        const float qx = q0.x + dv.x * t, qy = q0.y + dv.y * t, qz = q0.z + dv.z * t;
+        if (!(qx >= 0.0f && qx <= 1.0f && qy >= 0.0f && qy <= 1.0f && qz >= 0.0f && qz <= 1.0f)) break;
+        if (lod < (A.spec_b ? 1.0f : 0.5f) + 1e-3f) level0 = true;
+        // bricks under the trilinear footprint in level-1 texel space (a brick = 4 level-1 texels per axis), with a margin
+        const float px = qx * n1 - 0.5f, py = qy * n1 - 0.5f, pz = qz * n1 - 0.5f, e = 1.0f / 16.0f;
+        const int x0 = (int)floorf(px - e) >> 2, x1 = ((int)floorf(px + e) + 1) >> 2;
+        const int y0 = (int)floorf(py - e) >> 2, y1 = ((int)floorf(py + e) + 1) >> 2;
+        const int z0 = (int)floorf(pz - e) >> 2, z1 = ((int)floorf(pz + e) + 1) >> 2;
+        for (int bz = z0; bz <= z1; bz++)
+            for (int by = y0; by <= y1; by++)
+                for (int bx = x0; bx <= x1; bx++) mark_brick(A.need1, bx, by, bz, NB);
+        t += A.spec_b ? 0.5f * diam : diam;
+    }
+    return level0;
+}
+
+__constant__ float kNeedDiffuseDirs[6][3] = {
+    {0.0f, 0.0f, 1.0f},
+    {0.8660254f, 0.0f, 0.5f},
+    {0.26761657f, 0.82363910f, 0.5f},
+    {-0.70062927f, 0.50903696f, 0.5f},
+    {-0.70062927f, -0.50903696f, 0.5f},
+    {0.26761657f, -0.82363910f, 0.5f}};
+
+__global__ void __launch_bounds__(128) k_need_bricks(const NeedArgs A)
+{
+    // pixel mapping of the tracer's CTA, 128 threads = 16 x 8 pixels of one 8-row tile row
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const uint32_t y = A.y0 + (A.tile0 + blockIdx.y * A.tile_stride) * 8 + (warp >> 1) * 4 + (lane >> 3);
+    bool level0 = false;
+    if (x < A.W && y < A.y1)
+    {
+        const float depth = __ldg(A.depth + (size_t)y * A.W + x);
+        if (depth < 1.0f && A.no_view)
+            level0 = cone_samples_level0(kTanHalfDiffuse, A.h, A.spec_b != 0) ||
+                     cone_samples_level0(cone_specular_tan((float)__ldg(A.material + (size_t)y * A.W + x).y / 255.0f), A.h, A.spec_b != 0);
+        else if (depth < 1.0f)
+        {   // -- the tracer's set-up (k_trace_n), expression for expression
+            const float uvx = ((float)x + 0.5f) / (float)A.W, uvy = ((float)y + 0.5f) / (float)A.H;
+            const f4 cp = mul44(A.InvProj, f4{uvx * 2.0f - 1.0f, uvy * 2.0f - 1.0f, depth, 1.0f});
+            const f3 cspos = {cp.x / cp.w, cp.y / cp.w, cp.z / cp.w};
+            const f3 wpos = mul43(A.InvModelView, cspos, 1.0f);
+            const ushort4 nq = __ldg(reinterpret_cast<const ushort4*>(A.normals) + (size_t)y * A.W + x);
+            const f3 csnorm = normalize3(f3{fmaf((float)nq.x / 65535.0f, 2.0f, -1.0f), fmaf((float)nq.y / 65535.0f, 2.0f, -1.0f), fmaf((float)nq.z / 65535.0f, 2.0f, -1.0f)});
+            const f3 wnorm = mul33(A.InvModelView, csnorm);
+            f3 z = wnorm, hh = wnorm;
+            if (fabsf(hh.x) <= fabsf(hh.y) && fabsf(hh.x) <= fabsf(hh.z)) hh.x = 1.0f;
+            else if (fabsf(hh.y) <= fabsf(hh.x) && fabsf(hh.y) <= fabsf(hh.z)) hh.y = 1.0f;
+            else hh.z = 1.0f;
+            z = normalize3(z);
+            const f3 ty = normalize3(cross3(hh, z));
+            const f3 tx = normalize3(cross3(z, ty));
+            const f3 origin = {wpos.x + z.x * A.h, wpos.y + z.y * A.h, wpos.z + z.z * A.h};
+#pragma unroll 1
+            for (int i = 0; i < 6; i++)
+            {
+                const float d0 = kNeedDiffuseDirs[i][0], d1 = kNeedDiffuseDirs[i][1], d2 = kNeedDiffuseDirs[i][2];
+                const f3 dir = {(tx.x * d0 + ty.x * d1) + z.x * d2, (tx.y * d0 + ty.y * d1) + z.y * d2, (tx.z * d0 + ty.z * d1) + z.z * d2};
+                level0 |= mark_cone(A, origin, dir, kTanHalfDiffuse);
+            }
             const float rough = (float)__ldg(A.material + (size_t)y * A.W + x).y / 255.0f;
-            need |= cone_samples_level0(cone_specular_tan(rough), A.h, A.spec_b != 0);
+            const f3 I = normalize3(wpos - A.cam);
+            const float ndi = dot3(z, I);
+            const f3 R = {I.x - 2.0f * ndi * z.x, I.y - 2.0f * ndi * z.y, I.z - 2.0f * ndi * z.z};
+            if (dot3(R, z) > -1e-3f) level0 |= mark_cone(A, origin, R, cone_specular_tan(rough));
         }
     }
-    if (__syncthreads_or(need) && threadIdx.x == 0) A.dev_state[F184_DEV_NEED_L0] = 1u;
+    if (__syncthreads_or(level0) && threadIdx.x == 0) A.dev_state[F184_DEV_NEED_L0] = 1u;
 }
 
 // Level 0 is about to be gathered into a set whose level 0 was skipped by an earlier gather: the bricks of the OTHER ranks may hold
@@ -132,6 +221,7 @@ struct GatherArgs
     const unsigned long long* peer_counters[8];
     const uint32_t* peer_list[8];
     const uint32_t* dev_state;
+    unsigned long long* gather_bytes;  // F184_COUNTER_GATHER_BYTES: what the TMA-fed kernel's bulk copies move over NVLink (summed by its producers)
     int rank, nranks, N, write_linear;
     cudaSurfaceObject_t rad_surf;
     uint32_t* rad_lin;
@@ -140,14 +230,17 @@ struct GatherArgs
 };
 
 // behind the gather: the set's level-0 bookkeeping, and the bytes that crossed NVLink (F184_COUNTER_GATHER_BYTES)
-__global__ void k_gather_state(const GatherArgs G, uint32_t* dev_state, int set, unsigned long long* counters, uint32_t bytes_with_l0, uint32_t bytes_without)
+__global__ void k_gather_state(const GatherArgs G, uint32_t* dev_state, int set, unsigned long long* counters, uint32_t ldg_bytes_with_l0, uint32_t ldg_bytes_without)
 {
     const bool level0 = dev_state[F184_DEV_NEED_L0] != 0;
     dev_state[F184_DEV_L0_FULL + set] = level0 ? 1u : 0u;
-    unsigned long long records = 0;
-    for (int p = 0; p < G.nranks; p++)
-        if (p != G.rank) records += G.peer_counters[p][F184_COUNTER_COUNT];
-    counters[F184_COUNTER_GATHER_BYTES] = records * (unsigned long long)(level0 ? bytes_with_l0 : bytes_without);
+    if (ldg_bytes_without)
+    {   // the per-lane-load variant moves the same bytes for every record
+        unsigned long long records = 0;
+        for (int p = 0; p < G.nranks; p++)
+            if (p != G.rank) records += G.peer_counters[p][F184_COUNTER_COUNT];
+        counters[F184_COUNTER_GATHER_BYTES] = records * (unsigned long long)(level0 ? ldg_bytes_with_l0 : ldg_bytes_without);
+    }
 }
 
 constexpr int GATHER_WARPS = 8;
@@ -263,94 +356,160 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__((G2_CONSUMERS + 1) * 32) k_gather_bricks_tma(const GatherArgs G, uint32_t* dev_state)
+constexpr int G2_UNIT = 128;                      // bricks per work unit: the producer fetches a unit's 128 brick indices (512 B) with one bulk copy
+
+// Work = units of G2_UNIT consecutive records of one peer, walked in the same order by both roles: u = 0, 1, ...; for each u the peers in
+// an order rotated by the reader's rank (so the box's readers do not all start on the same peer); CTA c takes every gridDim.x-th unit.
+// Per record the producer looks the brick up in the need mask (k_need_bricks) and fetches
+//     level 0 needed by some cone (glossy scene): words [0, 952)      3808 B
+//     level 1 of this brick needed:               words [512, 952)    1760 B
+//     otherwise (levels 2, 3 + brick index):      words [896, 952)     224 B
+// and the consumers write what arrived; a brick whose level 1 did not travel gets zeros there IF this rank's copy of it is not zero
+// already (one bit per brick and texture set) — so a foreign brick's level 1 on this rank is always either current or zero, never stale.
+__global__ void __launch_bounds__((G2_CONSUMERS + 1) * 32) k_gather_bricks_tma(const GatherArgs G, uint32_t* dev_state, const uint32_t* __restrict__ need1,
+                                                                               uint32_t* __restrict__ l1_nonzero)
 {
-    extern __shared__ __align__(128) uint8_t ring[];                // G2_SLOTS x 4 KB
-    __shared__ __align__(8) uint64_t full[G2_SLOTS], empty[G2_SLOTS];
+    extern __shared__ __align__(128) uint8_t ring[];                // G2_SLOTS x 4 KB, then 2 x G2_UNIT brick indices
+    __shared__ __align__(8) uint64_t full[G2_SLOTS], empty[G2_SLOTS], idbar[2];
     __shared__ uint32_t counts[8];
+    uint32_t* idbuf = reinterpret_cast<uint32_t*>(ring + G2_SLOTS * G2_SLOT_BYTES);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0)
     {
         for (int s_ = 0; s_ < G2_SLOTS; s_++) { mbar_init(&full[s_], 1); mbar_init(&empty[s_], 1); }
+        mbar_init(&idbar[0], 1); mbar_init(&idbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 8) counts[threadIdx.x] = ((int)threadIdx.x < G.nranks && (int)threadIdx.x != G.rank) ? (uint32_t)G.peer_counters[threadIdx.x][F184_COUNTER_COUNT] : 0u;
     __syncthreads();
     const bool level0 = G.dev_state[F184_DEV_NEED_L0] != 0;
-    uint32_t max_count = 0;
-    for (int p = 0; p < G.nranks; p++) max_count = max(max_count, counts[p]);
+    uint32_t max_units = 0;
+    for (int p = 0; p < G.nranks; p++) max_units = max(max_units, (counts[p] + G2_UNIT - 1) / G2_UNIT);
     const int N = G.N, NB = N >> 3, n1 = N >> 1, n2 = N >> 2, n3 = N >> 3;
-    // both roles walk the same item sequence: j = blockIdx.x, + gridDim.x, ...; for each j the peers in an order rotated by the
-    // reader's rank (so the box's readers do not all start on the same peer); an item exists where j < that peer's count
-    uint32_t n = 0;                                                  // sequence number of the next item
+    uint32_t n = 0;                                                  // sequence number of the next record of this CTA
+    uint32_t unit_no = 0;                                            // valid units seen so far (all CTAs count alike)
     if (warp == G2_CONSUMERS)
-    {   // ---- producer
-        if (lane == 0)
-            for (uint32_t j = blockIdx.x; j < max_count; j += gridDim.x)
-                for (int q = 1; q < G.nranks; q++)
+    {   // ---- producer (one thread)
+        if (lane != 0) return;
+        // first pass over the unit sequence only to find this CTA's units: (peer, u) pairs, visited again below with their indices prefetched
+        uint32_t k = 0;                                              // this CTA's units so far (id buffer = k & 1)
+        // prefetch helper: the indices of unit (p, u) into idbuf[k & 1]
+        auto fetch_ids = [&](int p, uint32_t u, uint32_t kk) {
+            const uint32_t first = u * G2_UNIT, cnt = min((uint32_t)G2_UNIT, counts[p] - first);
+            const uint32_t bytes = ((cnt * 4u) + 15u) & ~15u;        // the list allocation is a multiple of 16 bytes long
+            mbar_expect_tx(&idbar[kk & 1], bytes);
+            bulk_load(idbuf + (kk & 1) * G2_UNIT, G.peer_list[p] + first, bytes, &idbar[kk & 1]);
+        };
+        // walk: find the next unit of this CTA after position (u, q)
+        uint32_t u = 0; int q = 1;
+        auto next_unit = [&](int& p_out, uint32_t& u_out) -> bool {
+            for (; u < max_units; u++, q = 1)
+                for (; q < G.nranks; q++)
                 {
                     const int p = (G.rank + q) % G.nranks;
-                    if (j >= counts[p]) continue;
-                    const int slot = (int)(n % G2_SLOTS);
-                    if (!mbar_wait_bounded(&empty[slot], ((n / G2_SLOTS) & 1u) ^ 1u, dev_state)) return;
-                    const uint8_t* rec = reinterpret_cast<const uint8_t*>(G.peer_export[p]) + (size_t)j * 4096;
-                    uint8_t* dst = ring + (size_t)slot * G2_SLOT_BYTES;
-                    if (level0) { mbar_expect_tx(&full[slot], G2_REC0_BYTES); bulk_load(dst, rec, G2_REC0_BYTES, &full[slot]); }
-                    else { mbar_expect_tx(&full[slot], G2_REC_BYTES); bulk_load(dst + 2048, rec + 2048, G2_REC_BYTES, &full[slot]); }
-                    n++;
+                    if (u * G2_UNIT >= counts[p]) continue;
+                    const bool take = (unit_no++ % gridDim.x) == blockIdx.x;
+                    if (take) { p_out = p; u_out = u; q++; return true; }
                 }
+            return false;
+        };
+        unsigned long long sent = 0;
+        int p_cur = 0, p_nxt = 0; uint32_t u_cur = 0, u_nxt = 0;
+        bool have = next_unit(p_cur, u_cur);
+        if (have) fetch_ids(p_cur, u_cur, 0);
+        while (have)
+        {
+            const bool have_nxt = next_unit(p_nxt, u_nxt);
+            if (have_nxt) fetch_ids(p_nxt, u_nxt, k + 1);            // the buffer of unit k - 1: its indices were all consumed (by this thread) already
+            if (!mbar_wait_bounded(&idbar[k & 1], (k >> 1) & 1u, dev_state)) return;
+            const uint32_t* ids = idbuf + (k & 1) * G2_UNIT;
+            const uint32_t first = u_cur * G2_UNIT, cnt = min((uint32_t)G2_UNIT, counts[p_cur] - first);
+            for (uint32_t j = 0; j < cnt; j++)
+            {
+                const uint32_t b = ids[j] & 0x7fffffffu;
+                const int slot = (int)(n % G2_SLOTS);
+                if (!mbar_wait_bounded(&empty[slot], ((n / G2_SLOTS) & 1u) ^ 1u, dev_state)) return;
+                const uint8_t* rec = reinterpret_cast<const uint8_t*>(G.peer_export[p_cur]) + (size_t)(first + j) * 4096;
+                uint8_t* dst = ring + (size_t)slot * G2_SLOT_BYTES;
+                const bool l1 = (need1[b >> 5] >> (b & 31u)) & 1u;
+                const uint32_t off = level0 ? 0u : (l1 ? 2048u : 3584u), bytes = G2_REC0_BYTES - off;
+                mbar_expect_tx(&full[slot], bytes);
+                bulk_load(dst + off, rec + off, bytes, &full[slot]);
+                sent += bytes + 4u;
+                n++;
+            }
+            // the id buffer k & 1 may be refilled two units later: nothing to release, this thread is its only reader
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            have = have_nxt; p_cur = p_nxt; u_cur = u_nxt; k++;
+        }
+        if (sent) atomicAdd(G.gather_bytes, sent);
         return;
     }
-    // ---- consumers: warp w takes the items with n % G2_CONSUMERS == w
-    for (uint32_t j = blockIdx.x; j < max_count; j += gridDim.x)
+    // ---- consumers: warp w takes the records with n % G2_CONSUMERS == w
+    for (uint32_t u = 0; u < max_units; u++)
         for (int q = 1; q < G.nranks; q++)
         {
             const int p = (G.rank + q) % G.nranks;
-            if (j >= counts[p]) continue;
-            const uint32_t mine = n++;
-            if ((int)(mine % G2_CONSUMERS) != warp) continue;
-            const int slot = (int)(mine % G2_SLOTS);
-            if (!mbar_wait_bounded(&full[slot], (mine / G2_SLOTS) & 1u, dev_state)) return;
-            const uint32_t* rec = reinterpret_cast<const uint32_t*>(ring + (size_t)slot * G2_SLOT_BYTES);
-            const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
-            const uint32_t b = rec[950] & 0x7fffffffu;
-            const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
-            if (level0)
+            if (u * G2_UNIT >= counts[p]) continue;
+            if ((unit_no++ % gridDim.x) != blockIdx.x) continue;
+            const uint32_t cnt = min((uint32_t)G2_UNIT, counts[p] - u * G2_UNIT);
+            for (uint32_t j = 0; j < cnt; j++)
             {
-#pragma unroll
-                for (int k = 0; k < 4; k++)
+                const uint32_t mine = n++;
+                if ((int)(mine % G2_CONSUMERS) != warp) continue;
+                const int slot = (int)(mine % G2_SLOTS);
+                if (!mbar_wait_bounded(&full[slot], (mine / G2_SLOTS) & 1u, dev_state)) return;
+                const uint32_t* rec = reinterpret_cast<const uint32_t*>(ring + (size_t)slot * G2_SLOT_BYTES);
+                const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
+                const uint32_t b = rec[950] & 0x7fffffffu;
+                const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
+                const uint32_t word = b >> 5, bit = 1u << (b & 31u);
+                const bool l1 = level0 || ((need1[word] & bit) != 0);
+                const bool was_nonzero = (l1_nonzero[word] & bit) != 0;
+                if (level0)
                 {
-                    const int qq = lane + 32 * k, row = qq >> 1, half = qq & 1, y = row & 7, z = row >> 3;
-                    const uint4 v = rec4[qq];
-                    surf3Dwrite(v, G.rad_surf, (bx * 8 + half * 4) * 4, by * 8 + y, bz * 8 + z);
-                    if (G.write_linear) *reinterpret_cast<uint4*>(G.rad_lin + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4) = v;
-                }
-            }
 #pragma unroll
-            for (int k = 0; k < 3; k++)
-            {
-                const int jj = lane + 32 * k, d = jj >> 4, r = jj & 15, oy = r & 3, oz = r >> 2;
-                const int gx = bx * 4, gy = by * 4 + oy, gz = bz * 4 + oz;
-                const uint4 v = rec4[128 + jj];
-                surf3Dwrite(v, G.surf[0], gx * 4, gy, atlas_z(d, n1, gz));
-                if (G.write_linear) *reinterpret_cast<uint4*>(G.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = v;
+                    for (int k = 0; k < 4; k++)
+                    {
+                        const int qq = lane + 32 * k, row = qq >> 1, half = qq & 1, y = row & 7, z = row >> 3;
+                        const uint4 v = rec4[qq];
+                        surf3Dwrite(v, G.rad_surf, (bx * 8 + half * 4) * 4, by * 8 + y, bz * 8 + z);
+                        if (G.write_linear) *reinterpret_cast<uint4*>(G.rad_lin + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4) = v;
+                    }
+                }
+                if (l1 || was_nonzero)
+                {   // the brick's level 1, or zeros over a copy of it that no cone of this rank needs any more
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+                    {
+                        const int jj = lane + 32 * k, d = jj >> 4, r = jj & 15, oy = r & 3, oz = r >> 2;
+                        const int gx = bx * 4, gy = by * 4 + oy, gz = bz * 4 + oz;
+                        const uint4 v = l1 ? rec4[128 + jj] : make_uint4(0, 0, 0, 0);
+                        surf3Dwrite(v, G.surf[0], gx * 4, gy, atlas_z(d, n1, gz));
+                        if (G.write_linear) *reinterpret_cast<uint4*>(G.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = v;
+                    }
+                    if (lane == 0 && l1 != was_nonzero)
+                    {
+                        if (l1) atomicOr(l1_nonzero + word, bit); else atomicAnd(l1_nonzero + word, ~bit);
+                    }
+                }
+                if (lane < 24)
+                {
+                    const int d = lane >> 2, r = lane & 3, oy = r & 1, oz = r >> 1;
+                    const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
+                    const uint2 v = reinterpret_cast<const uint2*>(rec + 896)[lane];
+                    surf3Dwrite(v, G.surf[1], gx * 4, gy, atlas_z(d, n2, gz));
+                    if (G.write_linear) *reinterpret_cast<uint2*>(G.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = v;
+                }
+                if (lane < 6)
+                {
+                    const uint32_t v = rec[944 + lane];
+                    surf3Dwrite(v, G.surf[2], bx * 4, by, atlas_z(lane, n3, bz));
+                    G.lin[2][lane][((size_t)bz * n3 + by) * n3 + bx] = v;             // level 3 is the source of the local tail: always
+                }
+                __syncwarp();                                            // the whole warp has read the slot
+                if (lane == 0) mbar_arrive(&empty[slot]);
             }
-            if (lane < 24)
-            {
-                const int d = lane >> 2, r = lane & 3, oy = r & 1, oz = r >> 1;
-                const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
-                const uint2 v = reinterpret_cast<const uint2*>(rec + 896)[lane];
-                surf3Dwrite(v, G.surf[1], gx * 4, gy, atlas_z(d, n2, gz));
-                if (G.write_linear) *reinterpret_cast<uint2*>(G.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = v;
-            }
-            if (lane < 6)
-            {
-                const uint32_t v = rec[944 + lane];
-                surf3Dwrite(v, G.surf[2], bx * 4, by, atlas_z(lane, n3, bz));
-                G.lin[2][lane][((size_t)bz * n3 + by) * n3 + bx] = v;             // level 3 is the source of the local tail: always
-            }
-            __syncwarp();                                            // the whole warp has read the slot
-            if (lane == 0) mbar_arrive(&empty[slot]);
         }
 }
 
@@ -407,7 +566,7 @@ int f184_ipc_buffer_ptr(f184_ctx* c, uint32_t buffer, void** out)
             CK(c, cudaMemsetAsync(c->frag_counts, 0, 8 * F184_FRAG_SUBQUEUES * sizeof(uint32_t), c->stream));
             CK(c, cudaMemsetAsync(c->frag_cursor, 0, 8 * F184_FRAG_SUBQUEUES * sizeof(uint32_t), c->stream));
         }
-        *out = buffer == F184_IPC_FRAG_QUEUE ? (void*)c->frag_queue : (void*)c->frag_counts;
+        *out = buffer == F184_IPC_FRAG_QUEUE ? (void*)c->frag_queue : (void*)c->frag_cursor;
         return F184_OK;
     case F184_IPC_SYNC:
         if (!c->sync_flags)
@@ -469,13 +628,13 @@ extern "C" int f184_peer_barrier(f184_ctx* c)
     return f184_leave(c, sec, body());
 }
 
-int f184_gather_n(f184_ctx* c)
+int f184_gather_n(f184_ctx* c, const f184_trace_constants* view)
 {
     if (c->cfg.nranks <= 1) return F184_OK;
     int rc = f184_mode_n_alloc(c); if (rc) return rc;
     rc = f184_ensure_image(c, F184_SLOT_RADIANCE); if (rc) return rc;
     rc = f184_ensure_image(c, F184_SLOT_MIPS); if (rc) return rc;
-    for (int s_ : {F184_SLOT_DEPTH, F184_SLOT_MATERIAL}) { rc = f184_ensure_image(c, s_); if (rc) return rc; }
+    for (int s_ : {F184_SLOT_DEPTH, F184_SLOT_NORMALS, F184_SLOT_MATERIAL}) { rc = f184_ensure_image(c, s_); if (rc) return rc; }
     rc = f184_volume_begin_write(c); if (rc) return rc;
     VolumeSet& vs = c->vs[c->build_set];
     const int set = c->build_set;
@@ -491,6 +650,7 @@ int f184_gather_n(f184_ctx* c)
     G.rank = (int)c->cfg.rank; G.nranks = (int)c->cfg.nranks; G.N = (int)c->cfg.grid_n;
     G.write_linear = (c->cfg.flags & F184_FLAG_GATHER_LINEAR) ? 1 : 0;
     G.dev_state = c->dev_state;
+    G.gather_bytes = c->counters_dev + F184_COUNTER_GATHER_BYTES;
     G.rad_surf = vs.rad_surf;
     G.rad_lin = img_ptr<uint32_t>(c, F184_SLOT_RADIANCE);
     uint32_t* mips = img_ptr<uint32_t>(c, F184_SLOT_MIPS);
@@ -505,42 +665,76 @@ int f184_gather_n(f184_ctx* c)
     }
     rc = f184_stage_begin(c, F184_STAGE_EXCHANGE);
     if (rc) return rc;
-    {   // does level 0 have to travel this frame?  (F184_FLAG_GATHER_LINEAR — the tests' full comparison — and F184_GATHER_LEVEL0=1 force it)
-        static const bool force_env = [] { const char* e = getenv("F184_GATHER_LEVEL0"); return e && atoi(e) != 0; }();
-        const bool force = force_env || (c->cfg.flags & F184_FLAG_GATHER_LINEAR);
+    const uint32_t n_words = ((uint32_t)(c->cfg.grid_n / 8) * (c->cfg.grid_n / 8) * (c->cfg.grid_n / 8) + 31) / 32;
+    if (!c->need1)
+    {
+        CK(c, cudaMalloc(&c->need1, 4ull * n_words));
+        for (int i = 0; i < 2; i++)
+        {
+            CK(c, cudaMalloc(&c->l1_nonzero[i], 4ull * n_words));
+            CK(c, cudaMemset(c->l1_nonzero[i], 0, 4ull * n_words));
+        }
+    }
+    {   // What has to travel this frame?  Level 0: only if a cone of this rank's rows samples it.  Level 1: only the bricks such a cone
+        // samples (needs the camera: f184_gather_volume_view).  F184_FLAG_GATHER_LINEAR — the tests' full comparison — and
+        // F184_GATHER_LEVEL0=1 / F184_GATHER_ALL=1 force everything.
+        static const bool force_l0 = [] { const char* e = getenv("F184_GATHER_LEVEL0"); return e && atoi(e) != 0; }();
+        static const bool force_all = [] { const char* e = getenv("F184_GATHER_ALL"); return e && atoi(e) != 0; }();
+        const bool force = force_l0 || (c->cfg.flags & F184_FLAG_GATHER_LINEAR);
+        const bool all_l1 = force || force_all || !view;
         if ((rc = f184_fill_async(c, c->dev_state + F184_DEV_NEED_L0, force ? 1u : 0u, 4, c->stream))) return rc;
+        if ((rc = f184_fill_async(c, c->need1, all_l1 ? 0xffffffffu : 0u, 4ull * n_words, c->stream))) return rc;
         if (!force)
         {
             NeedArgs A{};
             A.depth = img_ptr<float>(c, F184_SLOT_DEPTH);
+            A.normals = img_ptr<uint16_t>(c, F184_SLOT_NORMALS);
             A.material = img_ptr<uchar4>(c, F184_SLOT_MATERIAL);
-            A.W = c->cfg.width;
+            A.W = c->cfg.width; A.H = c->cfg.height;
             A.n_tiles = f184_trace_tiles(c, c->cfg.height, &A.y0, &A.y1, &A.tile0, &A.tile_stride);
             A.h = c->voxel_h;
+            A.max_dist = c->cfg.cone_max_distance;
             A.spec_b = (c->cfg.flags & F184_FLAG_SPEC_APPENDIX_B) ? 1u : 0u;
+            A.N = c->cfg.grid_n;
+            A.no_view = all_l1 ? 1u : 0u;
             A.dev_state = c->dev_state;
-            k_need_level0<<<148, 256, 0, c->stream>>>(A);
-            CK_LAUNCH(c);
+            A.need1 = c->need1;
+            if (!all_l1)
+            {
+                memcpy(A.InvProj.m, view->view.InvProj, 64);
+                memcpy(A.InvModelView.m, view->ext.InvModelView, 64);
+                M4 vp, vv;
+                memcpy(vp.m, view->ext.VoxelProj, 64);
+                memcpy(vv.m, view->ext.VoxelView, 64);
+                A.w2v = host_matmul(vp, vv);
+                A.h = f184_voxel_h(view->ext.VoxelProj, view->ext.VoxelView, c->cfg.grid_n);      // the tracer's own h
+                A.cam = {A.InvModelView.m[12], A.InvModelView.m[13], A.InvModelView.m[14]};
+            }
+            if (A.n_tiles)
+            {
+                k_need_bricks<<<dim3((A.W + 15) / 16, A.n_tiles), 128, 0, c->stream>>>(A);
+                CK_LAUNCH(c);
+            }
         }
         k_clear_foreign_level0<<<148 * 4, 256, 0, c->stream>>>(vs.rad_surf, (int)c->cfg.grid_n, c->cfg.nranks, c->cfg.rank, c->dev_state, set);
         CK_LAUNCH(c);
     }
     static const bool gather_ldg = [] { const char* e = getenv("F184_GATHER_LDG"); return e && atoi(e) != 0; }();
+    if ((rc = f184_zero_counters(c, 1u << F184_COUNTER_GATHER_BYTES))) return rc;
     if (gather_ldg) k_gather_bricks<<<dim3(c->cfg.nranks, 148), GATHER_WARPS * 32, 0, c->stream>>>(G);
     else
     {
         static bool attr = false;
         if (!attr)
         {
-            CK(c, cudaFuncSetAttribute(k_gather_bricks_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SLOTS * G2_SLOT_BYTES));
+            CK(c, cudaFuncSetAttribute(k_gather_bricks_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SLOTS * G2_SLOT_BYTES + 2 * G2_UNIT * 4));
             attr = true;
         }
-        k_gather_bricks_tma<<<148 * 2, (G2_CONSUMERS + 1) * 32, G2_SLOTS * G2_SLOT_BYTES, c->stream>>>(G, c->dev_state);
+        k_gather_bricks_tma<<<148 * 2, (G2_CONSUMERS + 1) * 32, G2_SLOTS * G2_SLOT_BYTES + 2 * G2_UNIT * 4, c->stream>>>(G, c->dev_state, c->need1, c->l1_nonzero[set]);
     }
     CK_LAUNCH(c);
     // bytes per record that cross NVLink: the bulk copies of the TMA-fed kernel, or list entry + the record parts the per-lane loads read
-    k_gather_state<<<1, 1, 0, c->stream>>>(G, c->dev_state, set, c->counters_dev, gather_ldg ? 4 + 2048 + 4 * (384 + 48 + 6) : G2_REC0_BYTES,
-                                           gather_ldg ? 4 + 4 * (384 + 48 + 6) : G2_REC_BYTES);
+    k_gather_state<<<1, 1, 0, c->stream>>>(G, c->dev_state, set, c->counters_dev, gather_ldg ? 4 + 2048 + 4 * (384 + 48 + 6) : 0, gather_ldg ? 4 + 4 * (384 + 48 + 6) : 0);
     CK_LAUNCH(c);
     rc = f184_stage_end(c, F184_STAGE_EXCHANGE);
     if (rc) return rc;

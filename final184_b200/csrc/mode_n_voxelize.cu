@@ -126,9 +126,9 @@ struct VoxArgs
     float4* accN[8];
     uint32_t* brick_flags[8];
     uint32_t owner_mask, rank;
-    // fragments of bricks another rank owns: 16-byte records appended to that rank's receive queue (this rank's region of it),
-    // coalesced stores over NVLink; cursor[p][s] = this rank's append position in sub-queue s of its region of rank p's queue
-    // (local memory; a warp appends to the sub-queue its index selects)
+    // fragments of bricks another rank owns: 16-byte records appended to THIS rank's queue for that rank (local memory; the
+    // owner reads it over NVLink behind the barrier); cursor[p][s] = append position in sub-queue s of the region for rank p
+    // (a warp appends to the sub-queue its index selects)
     uint4* peer_queue[8];
     uint32_t* cursor;
     uint32_t sub_cap;                  // records per sub-queue
@@ -493,27 +493,25 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_voxelize_raster(const Vox
     warp_count_add(A.frag_counter, frags);
 }
 
-// behind the rasteriser: tell every owner how many records this rank appended to its queue (clamped to the capacity; what did not fit
-// went over as remote reductions)
-struct PublishArgs { uint32_t* peer_counts[8]; const uint32_t* cursor; uint32_t rank, nranks, sub_cap; };
-__global__ void k_publish_counts(const PublishArgs P)           // <<<nranks, F184_FRAG_SUBQUEUES>>>
-{
-    const uint32_t p = blockIdx.x, s = threadIdx.x;
-    if (p >= P.nranks || p == P.rank) return;
-    const uint32_t n = P.cursor[p * F184_FRAG_SUBQUEUES + s];
-    P.peer_counts[p][P.rank * F184_FRAG_SUBQUEUES + s] = n < P.sub_cap ? n : P.sub_cap;
-}
 __global__ void k_reset_cursors(uint32_t* cursor) { cursor[threadIdx.x] = 0u; }           // <<<1, 8 * F184_FRAG_SUBQUEUES>>>
 
-// owner side, at the head of normalise: apply the records the other ranks sent — two local 16-byte reductions and the brick flag per
-// record, exactly what the sender would have done to its own memory
-struct ApplyArgs { const uint4* queue; uint32_t* counts; float4 *accC, *accN; uint32_t* brick_flags; uint32_t rank, nranks, cap, sub_cap; };
+// Owner side, at the head of normalise: fetch the records the other ranks hold for this rank — coalesced 16-byte loads out of the
+// senders' memory over NVLink, 512 bytes per warp instruction — and apply them: two local 16-byte reductions and the brick flag per
+// record, exactly what the sender would have done to its own memory.
+struct ApplyArgs
+{
+    const uint4* peer_queue[8];        // sender s: its region for this rank
+    const uint32_t* peer_cursor[8];    // sender s: its cursors for this rank (F184_FRAG_SUBQUEUES of them)
+    float4 *accC, *accN;
+    uint32_t* brick_flags;
+    uint32_t rank, nranks, sub_cap;
+};
 __global__ void __launch_bounds__(256) k_apply_fragments(const ApplyArgs P)     // grid (16, nranks * F184_FRAG_SUBQUEUES): blockIdx.y = one sub-queue
 {
     const uint32_t s = blockIdx.y / F184_FRAG_SUBQUEUES, sub = blockIdx.y % F184_FRAG_SUBQUEUES;
     if (s == P.rank) return;
-    const uint32_t n = min(P.counts[blockIdx.y], P.sub_cap);
-    const uint4* q = P.queue + (size_t)s * P.cap + (size_t)sub * P.sub_cap;
+    const uint32_t n = min(P.peer_cursor[s][sub], P.sub_cap);
+    const uint4* q = P.peer_queue[s] + (size_t)sub * P.sub_cap;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const uint4 r = q[i];
@@ -523,7 +521,6 @@ __global__ void __launch_bounds__(256) k_apply_fragments(const ApplyArgs P)     
         P.brick_flags[o >> 9] = 1u;
     }
 }
-__global__ void k_clear_counts(uint32_t* counts) { counts[threadIdx.x] = 0u; }           // <<<1, 8 * F184_FRAG_SUBQUEUES>>>
 
 // vm[m] = View * Model[m] (same association as mode R)
 __global__ void k_view_model_n(M4 View, const M4* __restrict__ model, M4* __restrict__ vm, uint32_t n)
@@ -691,23 +688,15 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
     }
     A.owner_mask = G > 1 ? G - 1 : 0;
     A.rank = G > 1 ? c->cfg.rank : 0;
-    PublishArgs PA{};
     if (G > 1)
     {
         void* dummy = nullptr;
         int rc = f184_ipc_buffer_ptr(c, F184_IPC_FRAG_QUEUE, &dummy);
         if (rc) return rc;
         for (uint32_t p = 0; p < G; p++)
-        {
-            if (p == c->cfg.rank) continue;
-            if (!c->peer[p].buf[F184_IPC_FRAG_QUEUE] || !c->peer[p].buf[F184_IPC_FRAG_COUNTS])
-                return f184_fail(c, F184_ERR_NOT_READY, "voxelize: fragment queue of rank %u was not imported (f184_ipc_import)", p);
-            A.peer_queue[p] = reinterpret_cast<uint4*>(c->peer[p].buf[F184_IPC_FRAG_QUEUE]) + (size_t)c->cfg.rank * c->frag_cap;
-            PA.peer_counts[p] = reinterpret_cast<uint32_t*>(c->peer[p].buf[F184_IPC_FRAG_COUNTS]);
-        }
+            if (p != c->cfg.rank) A.peer_queue[p] = c->frag_queue + (size_t)p * c->frag_cap;      // own memory: the region for rank p
         A.cursor = c->frag_cursor;
         A.sub_cap = c->frag_cap / F184_FRAG_SUBQUEUES;
-        PA.cursor = c->frag_cursor; PA.rank = c->cfg.rank; PA.nranks = G; PA.sub_cap = A.sub_cap;
     }
     c->voxel_h = f184_voxel_h(cam->ProjMat, cam->ViewMat, c->cfg.grid_n);
     M4 View;
@@ -730,6 +719,7 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
         CK_LAUNCH(c);
         c->frag_sent_applied = false;
     }
+    c->frag_pending = true;
     if (end > first)
     {
         A.pos = c->pos; A.nrm = c->nrm; A.uv = c->uv; A.idx = c->idx; A.tri_mat = c->tri_mat; A.tri_model = c->tri_model;
@@ -748,11 +738,6 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
         k_voxelize_raster<<<148 * 4 * 4, RASTER_THREADS, 0, c->stream>>>(A);
         CK_LAUNCH(c);
     }
-    if (G > 1)
-    {
-        k_publish_counts<<<G, F184_FRAG_SUBQUEUES, 0, c->stream>>>(PA);
-        CK_LAUNCH(c);
-    }
     return f184_stage_end(c, F184_STAGE_VOXELIZE);
 }
 
@@ -764,14 +749,23 @@ int f184_normalise_n(f184_ctx* c)
     const uint32_t n_own = (NB / G) * NB * NB;
     int rc = f184_stage_begin(c, F184_STAGE_NORMALISE);
     if (rc) return rc;
-    if (G > 1 && c->frag_queue)
-    {   // the fragments the other ranks sent (their counts were published before the barrier this call follows)
-        ApplyArgs P{c->frag_queue, c->frag_counts, img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
-                    img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->cfg.rank, G, c->frag_cap, c->frag_cap / F184_FRAG_SUBQUEUES};
+    if (G > 1 && c->frag_queue && c->frag_pending)
+    {   // the fragments the other ranks hold for this rank (their kernels finished before the barrier this call follows)
+        ApplyArgs P{};
+        for (uint32_t p = 0; p < G; p++)
+        {
+            if (p == c->cfg.rank) continue;
+            if (!c->peer[p].buf[F184_IPC_FRAG_QUEUE] || !c->peer[p].buf[F184_IPC_FRAG_COUNTS])
+                return f184_fail(c, F184_ERR_NOT_READY, "normalise: fragment queue of rank %u was not imported (f184_ipc_import)", p);
+            P.peer_queue[p] = reinterpret_cast<const uint4*>(c->peer[p].buf[F184_IPC_FRAG_QUEUE]) + (size_t)c->cfg.rank * c->frag_cap;
+            P.peer_cursor[p] = reinterpret_cast<const uint32_t*>(c->peer[p].buf[F184_IPC_FRAG_COUNTS]) + (size_t)c->cfg.rank * F184_FRAG_SUBQUEUES;
+        }
+        P.accC = img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR); P.accN = img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL);
+        P.brick_flags = img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS);
+        P.rank = c->cfg.rank; P.nranks = G; P.sub_cap = c->frag_cap / F184_FRAG_SUBQUEUES;
         k_apply_fragments<<<dim3(16, G * F184_FRAG_SUBQUEUES), 256, 0, c->stream>>>(P);
         CK_LAUNCH(c);
-        k_clear_counts<<<1, 8 * F184_FRAG_SUBQUEUES, 0, c->stream>>>(c->frag_counts);      // applied once
-        CK_LAUNCH(c);
+        c->frag_pending = false;          // applied once: a second normalise without a new accumulation must not add them again
     }
     if ((rc = f184_zero_counters(c, (1u << F184_COUNTER_OCCUPIED) | (1u << F184_COUNTER_BRICKS) | (1u << F184_COUNTER_COUNT)))) return rc;   // COUNT = the list cursor
     k_brick_compact<<<(n_own + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,

@@ -207,7 +207,7 @@ class ShardedVoxelGI:
             c.inject(k)
             c.build_mips()                       # levels 1-3 of the own slab + packed export records
             c.peer_barrier()
-            c.gather_volume()                    # pull the other slabs' bricks, finish the small levels
+            c.gather_volume(k if trace else None)    # fetch the other ranks' bricks (level 1 only where this rank's cones sample it), finish the small levels
         else:                                    # "host": same order, exchange through torch.distributed on host arrays
             import torch
             import torch.distributed as dist

@@ -346,12 +346,13 @@ int f184_set_trace_tiles(f184_ctx* ctx, uint32_t first, uint32_t stride);
 /* ---- one NVLink box, one process per GPU (DESIGN.md "Multi-GPU").  The reference is single-GPU
  * (RHI/Private/Vulkan/DeviceVk.cpp:301-304); this is the north-star schedule:
  *   f184_voxelize_accumulate  rank r rasterises ITS triangles; a fragment whose 8^3 brick this rank owns is reduced into the own
- *                             accumulators (red.global.add.v4.f32), any other fragment is sent to the brick's owner as a 16-byte
- *                             record — warp-aggregated appends to the owner's receive queue, plain coalesced stores over NVLink
- *                             (remote 16-byte reductions were measured at 4.6 G/s per GPU, a tenth of coalesced stores); the
- *                             owner applies the records with local reductions at the head of f184_normalise: the reduce-scatter
- *                             is fused into the voxelizer, as an all-to-all of fragments.  A full queue falls back to the remote
- *                             reduction (system scope)
+ *                             accumulators (red.global.add.v4.f32), any other fragment becomes a 16-byte record in a LOCAL queue
+ *                             for the brick's owner (warp-aggregated appends); behind the barrier the owner reads its queues out
+ *                             of the senders' memory with coalesced 16-byte loads over NVLink and applies them with local
+ *                             reductions, at the head of f184_normalise.  (Small remote writes — 16-byte reductions or stores
+ *                             alike — were measured at 4.6 G packets/s per GPU: two GPUs voxelized slower than one.)  The
+ *                             reduce-scatter is an all-to-all of fragments; a full queue falls back to the remote reduction
+ *                             (system scope)
  *   f184_peer_barrier         device-side flag barrier over peer memory (no host round trip, no NCCL launch)
  *   f184_normalise / f184_inject / f184_build_mips   owner works on its slab's bricks only
  *   f184_peer_barrier
@@ -367,8 +368,8 @@ typedef enum f184_ipc_buffer {
     F184_IPC_COUNTERS = 4,
     F184_IPC_BRICK_LIST = 5,
     F184_IPC_SYNC = 6,          /* barrier flags */
-    F184_IPC_FRAG_QUEUE = 7,    /* fragment records the other ranks send this rank (one region per sender) */
-    F184_IPC_FRAG_COUNTS = 8,   /* how many records each sender wrote */
+    F184_IPC_FRAG_QUEUE = 7,    /* fragment records this rank has for the other ranks (one region per destination; the destination reads it) */
+    F184_IPC_FRAG_COUNTS = 8,   /* how many records each region holds (this rank's append cursors) */
     F184_IPC_COUNT = 9
 } f184_ipc_buffer;
 typedef struct f184_ipc_handle { uint8_t opaque[64]; } f184_ipc_handle;
@@ -378,6 +379,11 @@ int f184_voxelize_accumulate(f184_ctx* ctx, const f184_view_constants* voxel_cam
 int f184_normalise(f184_ctx* ctx);
 int f184_peer_barrier(f184_ctx* ctx);
 int f184_gather_volume(f184_ctx* ctx);
+/* The same, told which view the following f184_trace_indirect will trace (its constants): level 1 of a brick — 1.5 KB of its 1.7 KB —
+ * then travels only if a cone of this rank's rows samples it there, i.e. only around the surfaces this rank's pixels show (cones leave
+ * level 1 within ~3 voxels of their origin); elsewhere this rank keeps zeros.  Without a view (NULL, or f184_gather_volume) every
+ * listed brick travels whole.  The G-buffer bound at the time of the call must be the one the trace will read. */
+int f184_gather_volume_view(f184_ctx* ctx, const f184_trace_constants* view);
 
 /* ---- measurement */
 int f184_stage_time_ms(f184_ctx* ctx, uint32_t stage, float* out_ms);   /* last run of the stage; synchronous */

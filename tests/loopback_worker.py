@@ -59,13 +59,13 @@ def one_frame(one, cam, k):
     one.voxelize(cam); one.inject(k); one.build_mips(); one.trace_indirect(k)
 
 
-def compare_arrays(bad, tag, g, one, N, level0=True):
+def compare_arrays(bad, tag, g, one, N, level0=True, level1=True):
     if level0 and not np.array_equal(g.ctx.read_array(-1, 0, N), one.read_array(-1, 0, N)):
         bad.append(f"{tag}: level-0 array")
     m, lvl = N // 2, 0
     while m >= 1:
         for d in range(6):
-            if not np.array_equal(g.ctx.read_array(d, lvl, m), one.read_array(d, lvl, m)):
+            if (lvl or level1) and not np.array_equal(g.ctx.read_array(d, lvl, m), one.read_array(d, lvl, m)):
                 bad.append(f"{tag}: array dir {d} level {lvl + 1}")
         m //= 2; lvl += 1
 
@@ -111,23 +111,37 @@ def run_box(G, sc, cams, N, W, H, SH, bad, sponza=False):
     if sponza:
         one.close()
         return
-    # ---- (2) the product path: level 0 travels only when a cone of the rank's rows samples it.  The fixture's materials are
-    # rough (roughness 1: no cone reads level 0); a glossy G-buffer (roughness 0.2) makes the specular cones read it.
+    # ---- (2) the product path: only what this rank's cones sample travels.  Level 0: the fixture's materials are rough (roughness 1:
+    # no cone reads level 0); a glossy G-buffer (roughness 0.2) makes the specular cones read it, and then every listed brick travels
+    # whole.  Level 1: only the bricks around the surfaces the rank's pixels show — so the camera moves between frames (two fixture
+    # cameras, each with its own G-buffer): bricks needed for one view and not for the next must read zero, not the stale copy, when a
+    # later view needs them again after they have changed.  The image rows are the check (bit for bit against one context).
     ranks = make_box(G, N, W, H, SH, sc, cams, fi, 0)
     glossy = fi["material"].copy(); glossy[..., 1] = 51
-    schedule = [("rough", 0, T), ("rough", 0, T), ("glossy", 0, T), ("rough", T // 3, T), ("rough", 0, T // 2), ("glossy", T // 4, T), ("glossy", 0, T)]
-    for frame, (mat, lo, hi) in enumerate(schedule):
+    cam_b = S.fixture_constants("probe05")
+    views = {"a": (fi, k), "b": (frame_inputs(sc, cam_b, cams["shadow"], W, H, SH, 0, cache=False), A.trace_constants_c(cam_b, cams["shadow"], cams["voxel"], W, H, 0, True))}
+    schedule = [("rough", "a", 0, T), ("rough", "a", 0, T), ("glossy", "a", 0, T), ("rough", "b", T // 3, T), ("rough", "a", 0, T // 2), ("rough", "b", 0, T),
+                ("glossy", "b", T // 4, T), ("glossy", "a", 0, T), ("rough", "b", 0, T // 2), ("rough", "a", 0, T)]
+    for frame, (mat, view, lo, hi) in enumerate(schedule):
         set_ranges(ranks, one, lo, hi)
-        m_ = glossy if mat == "glossy" else fi["material"]
+        vfi, vk = views[view]
+        m_ = vfi["material"].copy()
+        if mat == "glossy":
+            m_[..., 1] = 51
         for c in [g.ctx for g in ranks] + [one]:
+            for slot, key in SLOTS[:2]:
+                c.upload(slot, vfi[key])
             c.upload(A.SLOT_MATERIAL, m_)
-        box_frame(ranks, cams["voxel"], k)
-        one_frame(one, cams["voxel"], k)
+        box_frame(ranks, cams["voxel"], vk)
+        one_frame(one, cams["voxel"], vk)
         box_sync(ranks); one.sync()
         for r, g in enumerate(ranks):
-            t = f"{tag} skip-path frame {frame} ({mat}) rank {r}"
-            compare_arrays(bad, t, g, one, N, level0=(mat == "glossy"))
+            t = f"{tag} skip-path frame {frame} ({mat}, view {view}) rank {r}"
+            compare_arrays(bad, t, g, one, N, level0=(mat == "glossy"), level1=(mat == "glossy"))
             compare_rows(bad, t, g, one)
+    for c in [g.ctx for g in ranks] + [one]:
+        for slot, key in SLOTS[:2]:
+            c.upload(slot, fi[key])
     # ---- (3) the frame pipeline: frames back to back, no host synchronisation in between, a different triangle range each
     # (every frame's volume differs, emptied bricks must be cleared in BOTH texture sets); read-backs staged asynchronously
     for c in [g.ctx for g in ranks] + [one]:
