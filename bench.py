@@ -562,7 +562,7 @@ class Arm:
         dist.all_gather_object(every, (bad, rows_ok))
         dist.barrier()
         vol_bad = [x for e in every for x in e[0]]
-        return {"volumes": "bit-exact" if not vol_bad else "MISMATCH: " + "; ".join(vol_bad[:4]),
+        return {"volumes": "bit-exact" if not vol_bad else f"MISMATCH ({len(vol_bad)} arrays): " + "; ".join(vol_bad[:3] + vol_bad[-3:]),
                 "rows": "bit-exact" if all(e[1] for e in every) else "MISMATCH on rank(s) " + ",".join(str(i) for i, e in enumerate(every) if not e[1]),
                 "checked": f"on every rank before the timed region: six-direction texture arrays of levels >= {levels_from} and the rank's own 8-row tile rows of the traced "
                            f"image against a one-GPU frame computed on the same device"}

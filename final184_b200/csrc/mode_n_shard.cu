@@ -389,12 +389,13 @@ __global__ void __launch_bounds__((G2_CONSUMERS + 1) * 32) k_gather_bricks_tma(c
     uint32_t n = 0;                                                  // sequence number of the next record of this CTA
     uint32_t unit_no = 0;                                            // valid units seen so far (all CTAs count alike)
     if (warp == G2_CONSUMERS)
-    {   // ---- producer (one thread)
-        if (lane != 0) return;
+    {   // ---- producer: the whole warp walks the units; the lanes look up the need bits of 32 records at a time (one round of loads
+        // instead of one dependent L2 access per record), lane 0 issues the copies
         // first pass over the unit sequence only to find this CTA's units: (peer, u) pairs, visited again below with their indices prefetched
         uint32_t k = 0;                                              // this CTA's units so far (id buffer = k & 1)
         // prefetch helper: the indices of unit (p, u) into idbuf[k & 1]
         auto fetch_ids = [&](int p, uint32_t u, uint32_t kk) {
+            if (lane != 0) return;
             const uint32_t first = u * G2_UNIT, cnt = min((uint32_t)G2_UNIT, counts[p] - first);
             const uint32_t bytes = ((cnt * 4u) + 15u) & ~15u;        // the list allocation is a multiple of 16 bytes long
             mbar_expect_tx(&idbar[kk & 1], bytes);
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__((G2_CONSUMERS + 1) * 32) k_gather_bricks_tma(c
             return false;
         };
         unsigned long long sent = 0;
+        bool off_fail = false;
         int p_cur = 0, p_nxt = 0; uint32_t u_cur = 0, u_nxt = 0;
         bool have = next_unit(p_cur, u_cur);
         if (have) fetch_ids(p_cur, u_cur, 0);
@@ -421,28 +423,49 @@ __global__ void __launch_bounds__((G2_CONSUMERS + 1) * 32) k_gather_bricks_tma(c
         {
             const bool have_nxt = next_unit(p_nxt, u_nxt);
             if (have_nxt) fetch_ids(p_nxt, u_nxt, k + 1);            // the buffer of unit k - 1: its indices were all consumed (by this thread) already
-            if (!mbar_wait_bounded(&idbar[k & 1], (k >> 1) & 1u, dev_state)) return;
+            {   // every lane waits for the indices itself (the wait is what makes the bulk copy's bytes visible to the waiting thread)
+                const bool ok = mbar_wait_bounded(&idbar[k & 1], (k >> 1) & 1u, dev_state);
+                if (!__all_sync(0xffffffffu, ok)) return;
+            }
             const uint32_t* ids = idbuf + (k & 1) * G2_UNIT;
             const uint32_t first = u_cur * G2_UNIT, cnt = min((uint32_t)G2_UNIT, counts[p_cur] - first);
-            for (uint32_t j = 0; j < cnt; j++)
+            for (uint32_t j0 = 0; j0 < cnt; j0 += 32)
             {
-                const uint32_t b = ids[j] & 0x7fffffffu;
-                const int slot = (int)(n % G2_SLOTS);
-                if (!mbar_wait_bounded(&empty[slot], ((n / G2_SLOTS) & 1u) ^ 1u, dev_state)) return;
-                const uint8_t* rec = reinterpret_cast<const uint8_t*>(G.peer_export[p_cur]) + (size_t)(first + j) * 4096;
-                uint8_t* dst = ring + (size_t)slot * G2_SLOT_BYTES;
-                const bool l1 = (need1[b >> 5] >> (b & 31u)) & 1u;
-                const uint32_t off = level0 ? 0u : (l1 ? 2048u : 3584u), bytes = G2_REC0_BYTES - off;
-                mbar_expect_tx(&full[slot], bytes);
-                bulk_load(dst + off, rec + off, bytes, &full[slot]);
-                sent += bytes + 4u;
-                n++;
+                uint32_t my_off = 3584u;
+                if (j0 + lane < cnt)
+                {
+                    const uint32_t b = ids[j0 + lane] & 0x7fffffffu;
+                    const bool l1 = (__ldg(need1 + (b >> 5)) >> (b & 31u)) & 1u;
+                    my_off = level0 ? 0u : (l1 ? 2048u : 3584u);
+                }
+                const uint32_t batch = min(32u, cnt - j0);
+                for (uint32_t i = 0; i < batch; i++)
+                {
+                    const uint32_t off = __shfl_sync(0xffffffffu, my_off, (int)i);
+                    if (lane == 0)
+                    {
+                        const int slot = (int)(n % G2_SLOTS);
+                        if (!mbar_wait_bounded(&empty[slot], ((n / G2_SLOTS) & 1u) ^ 1u, dev_state)) off_fail = true;
+                        else
+                        {
+                            const uint8_t* rec = reinterpret_cast<const uint8_t*>(G.peer_export[p_cur]) + (size_t)(first + j0 + i) * 4096;
+                            uint8_t* dst = ring + (size_t)slot * G2_SLOT_BYTES;
+                            const uint32_t bytes = G2_REC0_BYTES - off;
+                            mbar_expect_tx(&full[slot], bytes);
+                            bulk_load(dst + off, rec + off, bytes, &full[slot]);
+                            sent += bytes + 4u;
+                        }
+                    }
+                    n++;
+                }
+                if (__any_sync(0xffffffffu, off_fail)) return;
             }
             // the id buffer k & 1 may be refilled two units later: nothing to release, this thread is its only reader
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();                                                // every lane has read this unit's indices ...
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // ... before a bulk copy may overwrite them (unit k + 2)
             have = have_nxt; p_cur = p_nxt; u_cur = u_nxt; k++;
         }
-        if (sent) atomicAdd(G.gather_bytes, sent);
+        if (lane == 0 && sent) atomicAdd(G.gather_bytes, sent);
         return;
     }
     // ---- consumers: warp w takes the records with n % G2_CONSUMERS == w
@@ -556,7 +579,10 @@ int f184_ipc_buffer_ptr(f184_ctx* c, uint32_t buffer, void** out)
         {   // capacity per sender: generous (4 records per triangle of the scene, 1 Mi..8 Mi); a full region is not an error, the
             // sender falls back to remote reductions
             static const long env_cap = [] { const char* e = getenv("F184_FRAG_QUEUE_RECORDS"); return e ? atol(e) : 0l; }();
-            uint64_t cap = env_cap > 0 ? (uint64_t)env_cap : std::min<uint64_t>(std::max<uint64_t>(4ull * c->n_tris, 1ull << 20), 8ull << 20);
+            // per destination: 16 records per triangle of this rank's share of the scene (Sponza at 512^3 makes 18 fragments per triangle,
+            // of which (G - 1) / G leave the rank, spread over G - 1 destinations), 1 Mi at least
+            const uint64_t G_ = c->cfg.nranks ? c->cfg.nranks : 1;
+            uint64_t cap = env_cap > 0 ? (uint64_t)env_cap : std::max<uint64_t>(16ull * c->n_tris / G_, 1ull << 20);
             cap = (cap + F184_FRAG_SUBQUEUES - 1) / F184_FRAG_SUBQUEUES * F184_FRAG_SUBQUEUES;
             c->frag_cap = (uint32_t)cap;
             const uint32_t G = c->cfg.nranks ? c->cfg.nranks : 1;
@@ -730,7 +756,8 @@ int f184_gather_n(f184_ctx* c, const f184_trace_constants* view)
             CK(c, cudaFuncSetAttribute(k_gather_bricks_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SLOTS * G2_SLOT_BYTES + 2 * G2_UNIT * 4));
             attr = true;
         }
-        k_gather_bricks_tma<<<148 * 2, (G2_CONSUMERS + 1) * 32, G2_SLOTS * G2_SLOT_BYTES + 2 * G2_UNIT * 4, c->stream>>>(G, c->dev_state, c->need1, c->l1_nonzero[set]);
+        static const int gather_ctas = [] { const char* e = getenv("F184_GATHER_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 148 * 2; }();     // (tests: few CTAs = many units each)
+        k_gather_bricks_tma<<<gather_ctas, (G2_CONSUMERS + 1) * 32, G2_SLOTS * G2_SLOT_BYTES + 2 * G2_UNIT * 4, c->stream>>>(G, c->dev_state, c->need1, c->l1_nonzero[set]);
     }
     CK_LAUNCH(c);
     // bytes per record that cross NVLink: the bulk copies of the TMA-fed kernel, or list entry + the record parts the per-lane loads read

@@ -270,6 +270,20 @@ static int trace_launch(f184_ctx* c, const ConeParams& P, uint32_t grid_y, cudaS
     dim3 grid((P.W + 31) / 32, grid_y);
     // two register budgets of the same kernel: 4 CTAs/SM (64 registers) or 3 (80, no spill); F184_TRACE_CTAS=3 selects the latter (A/B knob)
     static const int min_ctas = [] { const char* e = getenv("F184_TRACE_CTAS"); return e ? atoi(e) : 4; }();
+    // The tracer uses no shared memory, so by default its launch configures the SMs with the smallest shared-memory carve-out (all of
+    // the unified array as L1 / texture cache) — and a kernel that NEEDS shared memory (every kernel of the build stream: brick rings,
+    // the gather's 64 KB ring) cannot become resident on an SM until the tracer's CTAs have drained from it and the SM is reconfigured:
+    // the frame pipeline's streams would take turns instead of running side by side.  Ask for a carve-out that leaves room for them
+    // (F184_TRACE_CARVEOUT, per cent of the maximum; the tracer's texel working set is a few KB per warp and keeps its hit rate).
+    static const int carveout = [] { const char* e = getenv("F184_TRACE_CARVEOUT"); return e ? atoi(e) : 44; }();
+    static bool carveout_set = false;
+    if (!carveout_set && carveout >= 0)
+    {
+        CK(c, cudaFuncSetAttribute(k_trace_n<3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+        CK(c, cudaFuncSetAttribute(k_trace_n<3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+        CK(c, cudaFuncSetAttribute(k_trace_n<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+        carveout_set = true;
+    }
     if (c->cfg.flags & F184_FLAG_SPEC_APPENDIX_B) k_trace_n<3, true><<<grid, TRACE_THREADS, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
     else if (min_ctas == 3) k_trace_n<3, false><<<grid, TRACE_THREADS, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
     else k_trace_n<4, false><<<grid, TRACE_THREADS, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);

@@ -34,6 +34,11 @@ def test_four_loopback_ranks_equal_one_context():
     run("box4")
 
 
+def test_gather_with_many_units_per_cta():
+    """three CTAs instead of 296 make every gather CTA walk many 128-record units (what a 1024^3 volume does to the full grid)"""
+    run("sponza", F184_GATHER_CTAS="3")
+
+
 def test_full_fragment_queues_fall_back_to_remote_reductions():
     """a receive queue of 2000 records overflows at once: everything beyond it takes the system-scope reduction path, same volume"""
     run("box2", F184_FRAG_QUEUE_RECORDS="2000")

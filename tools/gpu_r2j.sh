@@ -1,0 +1,24 @@
+#!/bin/bash
+# Round-2 session J (gpurun --gpus 8): the scaling run — multi-GPU parity worker (4 ranks), then the bench line at 4 and 8 ranks (C3 headline + c4_scaling),
+# and at 8 ranks once more with every pass on one stream (solo stage times).
+tag=${1:-r02q}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv,noheader | wc -l; free -g | head -2 | tail -1; nproc
+timeout 300 python -m pytest tests/test_gpu_multi.py -m gpu -q 2>&1 | tail -5
+run() { # n extra suffix
+  timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $1 --steps 50 --warmup 5 --no-cpu-baseline $2 > gpurun_out/bench_${tag}_g$1$3.json 2> gpurun_out/bench_${tag}_g$1$3.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/bench_${tag}_g$1$3.json").read().strip().splitlines()[-1])
+    print("N=$1 $2 c3", round(d["value"],4), "ms/frame", d["stages_ms"], "e2e", round(d["e2e"]["value"],3))
+    print("   min/max", d.get("stages_ms_min_max_over_ranks")); g=d.get("gather") or {}; print("   gather", g.get("gbs_per_rank_min_max"), g.get("bytes_per_rank_min_max")); print("   parity", {k:v for k,v in (d.get("parity_vs_1gpu") or {}).items() if k!="checked"})
+    c=d.get("c4_scaling") or {}
+    print("   c4", c.get("ms_per_frame"), c.get("stages_ms")); print("   c4 min/max", c.get("stages_ms_min_max_over_ranks")); g=c.get("gather") or {}; print("   c4 gather", g.get("gbs_per_rank_min_max"), g.get("bytes_per_rank_min_max")); print("   c4 parity", {k:v for k,v in (c.get("parity_vs_1gpu") or {}).items() if k!="checked"})
+except Exception as e:
+    print("N=$1 failed", e); print(open("gpurun_out/bench_${tag}_g$1$3.err").read()[-3000:])
+PY
+}
+run 8 "" ""
+run 8 "--no-overlap" "_nooverlap"
+run 4 "" ""
