@@ -551,8 +551,13 @@ class Arm:
         while m >= 1:
             if lvl + 1 >= levels_from:
                 for d in range(6):
-                    if not np.array_equal(g.ctx.read_array(d, lvl, m), one.read_array(d, lvl, m)):
+                    ga, oa = g.ctx.read_array(d, lvl, m), one.read_array(d, lvl, m)
+                    if not np.array_equal(ga, oa):
                         bad.append(f"rank {self.rank}: texture array level {lvl + 1} direction {d}")
+                        if os.environ.get("F184_PARITY_DEBUG"):
+                            idx = np.argwhere((ga != oa).any(-1))
+                            print(f"[parity debug] rank {self.rank} level {lvl + 1} dir {d}: {len(idx)} texels differ; first (z,y,x): {idx[:6].tolist()} "
+                                  f"got {[ga[tuple(i)].tolist() for i in idx[:3]]} want {[oa[tuple(i)].tolist() for i in idx[:3]]}", file=sys.stderr, flush=True)
             m //= 2; lvl += 1
         mask = g.own_rows_mask()
         a, b = g.ctx.readback(A.SLOT_INDIRECT_OUT)[mask], one.readback(A.SLOT_INDIRECT_OUT)[mask]

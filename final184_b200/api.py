@@ -319,10 +319,12 @@ class VoxelGI:
     def readback_wait(self, age=0):
         self._ck(self.lib.readback_wait(self.h, age), "readback_wait")
 
-    def read_array(self, direction, level, n):
-        """Texture-side storage (what the tracer samples): direction < 0 -> level-0 radiance array, else mip `level`+1."""
+    def read_array(self, direction, level, n, copy_out=False):
+        """Texture-side storage (what the tracer samples): direction < 0 -> level-0 radiance array (copied out), else mip `level`+1 of
+        that direction as the texture units return it at the texel centres.  copy_out: cudaMemcpy3D from the level's array instead
+        (wrong for atlases beyond 4 GiB, i.e. 1024^3 — kept to show it)."""
         out = np.empty((n, n, n, 4), np.uint8)
-        self._ck(self.lib.debug_read_array(self.h, direction, level, out.ctypes.data, out.nbytes), "debug_read_array")
+        self._ck(self.lib.debug_read_array(self.h, direction, level | (0x40000000 if copy_out and direction >= 0 else 0), out.ctypes.data, out.nbytes), "debug_read_array")
         return out
 
     def bind(self, slot, device_ptr, fmt, width, height, depth=1):

@@ -395,12 +395,12 @@ int f184_create(const f184_config* config, f184_ctx** out)
         c->ev_pool[s].push_back(a); c->ev_pool[s].push_back(b);
         c->ev[s][0] = a; c->ev[s][1] = b;
     }
-    if (cudaMalloc(&c->counters_dev, sizeof(unsigned long long) * (F184_COUNTER_COUNT + 4)) != cudaSuccess)
+    if (cudaMalloc(&c->counters_dev, sizeof(unsigned long long) * 32) != cudaSuccess)
     {
         delete c;
         return f184_fail(nullptr, F184_ERR_OUT_OF_MEMORY, "cudaMalloc counters");
     }
-    cudaMemset(c->counters_dev, 0, sizeof(unsigned long long) * (F184_COUNTER_COUNT + 4));
+    cudaMemset(c->counters_dev, 0, sizeof(unsigned long long) * 32);       // public counters, internal cursors (F184_COUNTER_COUNT + 0..3), diagnostics
     if (cudaMalloc(&c->dev_state, sizeof(uint32_t) * F184_DEV_WORDS) != cudaSuccess)
     {
         delete c;

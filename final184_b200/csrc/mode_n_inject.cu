@@ -262,6 +262,18 @@ int f184_mode_n_alloc(f184_ctx* c)
     return F184_OK;
 }
 
+// test hook: what the TEXTURE UNITS return for every texel centre of one direction of one atlas level — the fetch the cone tracer
+// makes, at weights 1/0.  (A copy-out with cudaMemcpy3D from the array of a mip level is not used: for the 7.4 GB atlas of a 1024^3
+// volume it returns bytes of the wrong level — levels that start beyond 4 GiB inside the mipmapped allocation — while surface
+// writes and texture fetches address them correctly: measured, tools/debug_arrays_1024.py.)
+__global__ void k_read_atlas_tex(cudaTextureObject_t atlas, float lod, int dir, int n, uchar4* __restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    if (x >= n) return;
+    const float4 t = tex3DLod<float4>(atlas, ((float)x + 0.5f) / (float)n, ((float)y + 0.5f) / (float)n, ((float)(2 * dir * n + z) + 0.5f) / (float)(12 * n), lod);
+    out[((size_t)z * n + y) * n + x] = make_uchar4((unsigned char)(t.x * 255.0f + 0.5f), (unsigned char)(t.y * 255.0f + 0.5f), (unsigned char)(t.z * 255.0f + 0.5f), (unsigned char)(t.w * 255.0f + 0.5f));
+}
+
 // test hook: copy one level of the texture-side storage back (dir < 0: the level-0 radiance array) — of the set the next trace samples
 extern "C" int f184_debug_read_array(f184_ctx* c, int32_t dir, uint32_t level, void* host, size_t bytes)
 {
@@ -272,8 +284,25 @@ extern "C" int f184_debug_read_array(f184_ctx* c, int32_t dir, uint32_t level, v
     const VolumeSet& v = c->vs[c->trace_set];
     cudaArray_t a = v.rad_array;
     size_t n = c->cfg.grid_n;
-    if (dir >= 0)
+    if (dir >= 0 && !(level & 0x40000000u))
     {
+        level &= 0x3fffffffu;
+        if (level >= c->n_mip_levels) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_read_array: bad level");
+        n = c->mip_levels[level].n;
+        if (bytes != n * n * n * 4) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_read_array: size mismatch");
+        uchar4* dev = nullptr;
+        CK(c, cudaMalloc(&dev, bytes));
+        const int bx = (int)std::min<size_t>(n, 128);
+        k_read_atlas_tex<<<dim3((unsigned)((n + bx - 1) / bx), (unsigned)n, (unsigned)n), bx, 0, c->stream>>>(v.dir_tex, (float)level, dir, (int)n, dev);
+        CK_LAUNCH(c);
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost));
+        cudaFree(dev);
+        return F184_OK;
+    }
+    if (dir >= 0)
+    {   // level | 0x40000000: the cudaMemcpy3D copy-out, kept to demonstrate the discrepancy above
+        level &= 0x3fffffffu;
         if (level >= c->n_mip_levels) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "debug_read_array: bad level");
         CK(c, cudaGetMipmappedArrayLevel(&a, v.dir_atlas, level));
         n = c->mip_levels[level].n;

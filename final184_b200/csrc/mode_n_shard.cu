@@ -321,7 +321,7 @@ constexpr int G2_SLOTS = 16;
 constexpr int G2_CONSUMERS = 4;                  // warps; + 1 producer warp
 constexpr int G2_SLOT_BYTES = 4096;
 constexpr int G2_REC_BYTES = 1760;               // levels 1-3 + brick index: words [512, 952)
-constexpr int G2_REC0_BYTES = 3808;              // with level 0: words [0, 952)
+constexpr int G2_REC0_BYTES = 3840;              // with level 0: words [0, 960) — copies end on a 128-byte line (the record is 4096 bytes; words 951.. are padding)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -698,7 +698,7 @@ int f184_gather_n(f184_ctx* c, const f184_trace_constants* view)
         for (int i = 0; i < 2; i++)
         {
             CK(c, cudaMalloc(&c->l1_nonzero[i], 4ull * n_words));
-            CK(c, cudaMemset(c->l1_nonzero[i], 0, 4ull * n_words));
+            if ((rc = f184_fill_async(c, c->l1_nonzero[i], 0u, 4ull * n_words, c->stream))) return rc;      // in stream order, ahead of the gather below
         }
     }
     {   // What has to travel this frame?  Level 0: only if a cone of this rank's rows samples it.  Level 1: only the bricks such a cone

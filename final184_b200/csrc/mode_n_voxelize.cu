@@ -25,6 +25,7 @@
 //     per listed brick) reads, converts and re-zeroes only those — the dense 32 B/voxel volume is never
 //     streamed (at 512^3 that alone would be 1.3 ms of HBM time).
 #include <algorithm>
+#include <cstdlib>
 
 #include "f184_device.cuh"
 
@@ -132,6 +133,7 @@ struct VoxArgs
     uint4* peer_queue[8];
     uint32_t* cursor;
     uint32_t sub_cap;                  // records per sub-queue
+    uint32_t no_aggregate;             // A/B knob (F184_FRAG_NO_AGG=1): every lane reserves its own slot
     unsigned long long* frag_counter;
     unsigned long long* queue_state;   // (entries << 40) | tasks, one 64-bit word so both advance together
     uint2* queue;                      // per large triangle: (triangle, first task)
@@ -360,12 +362,17 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
             // with ONE local atomic (opportunistic warp aggregation) and store their records side by side.
             const unsigned lane = threadIdx.x & 31u;
             const unsigned sub = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) & (F184_FRAG_SUBQUEUES - 1u);
-            const unsigned grp = __match_any_sync(__activemask(), owner);
-            const int leader = __ffs(grp) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(A.cursor + owner * F184_FRAG_SUBQUEUES + sub, (uint32_t)__popc(grp));
-            base = __shfl_sync(grp, base, leader);
-            const uint32_t slot = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+            uint32_t slot;
+            if (A.no_aggregate) slot = atomicAdd(A.cursor + owner * F184_FRAG_SUBQUEUES + sub, 1u);
+            else
+            {
+                const unsigned grp = __match_any_sync(__activemask(), owner);
+                const int leader = __ffs(grp) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(A.cursor + owner * F184_FRAG_SUBQUEUES + sub, (uint32_t)__popc(grp));
+                base = __shfl_sync(grp, base, leader);
+                slot = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+            }
             if (slot < A.sub_cap)
             {   // every component is an integer: 0..255 colour, -127..127 normal — a record loses nothing
                 const uint32_t rgb = (uint32_t)r8 | ((uint32_t)g8 << 8) | ((uint32_t)b8 << 16);
@@ -697,6 +704,8 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
             if (p != c->cfg.rank) A.peer_queue[p] = c->frag_queue + (size_t)p * c->frag_cap;      // own memory: the region for rank p
         A.cursor = c->frag_cursor;
         A.sub_cap = c->frag_cap / F184_FRAG_SUBQUEUES;
+        static const bool no_agg = [] { const char* e = getenv("F184_FRAG_NO_AGG"); return e && atoi(e) != 0; }();
+        A.no_aggregate = no_agg ? 1u : 0u;
     }
     c->voxel_h = f184_voxel_h(cam->ProjMat, cam->ViewMat, c->cfg.grid_n);
     M4 View;

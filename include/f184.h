@@ -404,8 +404,9 @@ int f184_debug_detmath(f184_ctx* ctx, uint32_t op, const float* x, const float* 
  * accumulation path).  Synchronous; allocates and frees its own scratch. */
 int f184_microbench(f184_ctx* ctx, uint32_t which, double* out_per_second);
 
-/* ---- test hook: one level of the texture-side storage the cone tracer samples (dir < 0: the level-0 radiance
- * 3D array; dir 0..5: level `level`+1 of that direction's mipmapped 3D array); host pointer; synchronous */
+/* ---- test hook: one level of the texture-side storage the cone tracer samples (dir < 0: the level-0 radiance 3D array, copied out;
+ * dir 0..5: level `level`+1 of that direction, as the texture units return it at every texel centre — the tracer's own fetch path);
+ * host pointer; synchronous */
 int f184_debug_read_array(f184_ctx* ctx, int32_t dir, uint32_t level, void* host, size_t bytes);
 
 /* ---- test hooks: several contexts of ONE process as the ranks of a box ("loopback ranks": cudaIpcOpenMemHandle refuses handles of

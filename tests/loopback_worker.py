@@ -109,6 +109,18 @@ def run_box(G, sc, cams, N, W, H, SH, bad, sponza=False):
     if frags != one.counter(A.COUNTER_FRAGMENTS): bad.append(f"{tag}: fragments {frags} vs {one.counter(A.COUNTER_FRAGMENTS)}")
     for g in ranks: g.close()
     if sponza:
+        # the product path at a real size: view-driven gather (records of three sizes in one ring), two frames so both texture sets are used
+        ranks = make_box(G, N, W, H, SH, sc, cams, fi, 0)
+        set_ranges(ranks, one, 0, T)
+        for frame in range(2):
+            box_frame(ranks, cams["voxel"], k)
+            one_frame(one, cams["voxel"], k)
+            box_sync(ranks); one.sync()
+            for r, g in enumerate(ranks):
+                t = f"{tag} view-driven frame {frame} rank {r}"
+                compare_arrays(bad, t, g, one, N, level0=False, level1=False)
+                compare_rows(bad, t, g, one)
+        for g in ranks: g.close()
         one.close()
         return
     # ---- (2) the product path: only what this rank's cones sample travels.  Level 0: the fixture's materials are rough (roughness 1:
