@@ -654,7 +654,7 @@ def run_b200(args, rank, world, local_rank):
     r = arm.timed(args.steps, args.warmup, clocks=True)
     red = arm.reduce(r, args.steps)
     stage_ms, counters, clk = r["stage_ms"], r["counters"], r["clocks"]
-    comm_ms = stage_ms.get("exchange", 0.0) + stage_ms.get("barrier", 0.0)
+    comm_ms = stage_ms.get("exchange", 0.0) + stage_ms.get("barrier", 0.0) + stage_ms.get("apply", 0.0) + stage_ms.get("need", 0.0)
     ms_frame = red["ms_frame"]
 
     # ---- timed region 2: end to end with host buffers.  Every step uploads one frame's G-buffer (depth, normals, material) from

@@ -28,8 +28,9 @@ MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
  SLOT_ACCUM_COLOR, SLOT_ACCUM_NORMAL, SLOT_VOX_ALBEDO, SLOT_VOX_NORMAL, SLOT_RADIANCE, SLOT_MIPS,
  SLOT_BRICK_FLAGS, SLOT_LIGHTING, SLOT_TAA_HISTORY, SLOT_TAA_OUT, SLOT_COLOR_OUT, SLOT_COUNT) = range(24)
 (STAGE_CLEAR, STAGE_VOXELIZE, STAGE_NORMALISE, STAGE_INJECT, STAGE_MIPS, STAGE_TRACE, STAGE_GTAO,
- STAGE_BLUR, STAGE_EXCHANGE, STAGE_LIGHTING, STAGE_COMPOSITE, STAGE_BARRIER, STAGE_COUNT) = range(13)
-STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur", "exchange", "lighting", "composite", "barrier"]
+ STAGE_BLUR, STAGE_EXCHANGE, STAGE_LIGHTING, STAGE_COMPOSITE, STAGE_BARRIER, STAGE_APPLY, STAGE_NEED, STAGE_TAIL, STAGE_COUNT) = range(16)
+STAGE_NAMES = ["clear", "voxelize", "normalise", "inject", "mips", "trace", "gtao", "blur", "exchange", "lighting", "composite", "barrier",
+               "apply", "need", "tail"]
 (COUNTER_FRAGMENTS, COUNTER_MARCH_STEPS, COUNTER_OCCUPIED, COUNTER_KERNEL_LAUNCHES, COUNTER_BRICKS, COUNTER_GATHER_BYTES) = range(6)
 (IPC_ACCUM_COLOR, IPC_ACCUM_NORMAL, IPC_BRICK_FLAGS, IPC_EXPORT, IPC_COUNTERS, IPC_BRICK_LIST, IPC_SYNC, IPC_FRAG_QUEUE, IPC_FRAG_COUNTS,
  IPC_COUNT) = range(10)

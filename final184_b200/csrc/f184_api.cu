@@ -244,8 +244,13 @@ int f184_prepare_frame(f184_ctx* c)
     void* dummy = nullptr;
     if ((rc = f184_ipc_buffer_ptr(c, F184_IPC_BRICK_LIST, &dummy))) return rc;
     if (c->cfg.nranks > 1)
+    {
         for (uint32_t b : {(uint32_t)F184_IPC_EXPORT, (uint32_t)F184_IPC_SYNC, (uint32_t)F184_IPC_FRAG_QUEUE})
             if ((rc = f184_ipc_buffer_ptr(c, b, &dummy))) return rc;
+        if ((rc = f184_gather_init_n(c))) return rc;
+    }
+    if ((rc = f184_mips_init_n(c))) return rc;         // kernel attributes (dynamic shared memory, carve-out): set before the first frame, not inside it
+    if ((rc = f184_trace_init_n(c))) return rc;
     if (!c->gamma_table) CK(c, cudaMalloc(&c->gamma_table, 256 * sizeof(float)));
     if (!c->ev_barrier) CK(c, cudaEventCreateWithFlags(&c->ev_barrier, cudaEventDisableTiming));
     if (c->n_tris)

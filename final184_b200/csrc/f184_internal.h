@@ -296,6 +296,9 @@ int f184_normalise_n(f184_ctx* c);
 int f184_voxelizer_scratch_n(f184_ctx* c);
 int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam);
 int f184_gather_n(f184_ctx* c, const f184_trace_constants* view);
+int f184_gather_init_n(f184_ctx* c);
+int f184_mips_init_n(f184_ctx* c);
+int f184_trace_init_n(f184_ctx* c);
 int f184_ipc_buffer_ptr(f184_ctx* c, uint32_t buffer, void** out);
 M4 f184_invert_m4(const M4& A);
 // world size of one voxel along voxel-x under the voxel camera (Proj * View), the `h` of the cone tracer

@@ -531,6 +531,19 @@ int f184_mips_tail_n(f184_ctx* c, bool own_stage)
     return own_stage ? f184_stage_end(c, F184_STAGE_MIPS) : F184_OK;
 }
 
+int f184_mips_init_n(f184_ctx* c)
+{
+    static bool done = false;
+    if (done) return F184_OK;
+    if (get_encode() != nullptr)
+    {
+        CK(c, cudaFuncSetAttribute(k_mips_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * TILE_BYTES + 64));
+        CK(c, cudaFuncSetAttribute(k_mips_bricks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BRICK_RING_BYTES));
+    }
+    done = true;
+    return F184_OK;
+}
+
 int f184_mips_n(f184_ctx* c)
 {
     int rc = f184_ensure_image(c, F184_SLOT_RADIANCE); if (rc) return rc;
@@ -542,13 +555,8 @@ int f184_mips_n(f184_ctx* c)
     uint32_t* mips = img_ptr<uint32_t>(c, F184_SLOT_MIPS);
     const uint32_t* level0 = img_ptr<uint32_t>(c, F184_SLOT_RADIANCE);
     const bool use_tma = !(c->cfg.flags & F184_FLAG_NO_TMA) && get_encode() != nullptr;
-    static bool attr_set = false;
     const int smem = STAGES * TILE_BYTES + 64;
-    if (use_tma && !attr_set)
-    {
-        CK(c, cudaFuncSetAttribute(k_mips_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    rc = f184_mips_init_n(c); if (rc) return rc;
     rc = f184_stage_begin(c, F184_STAGE_MIPS);
     if (rc) return rc;
     uint32_t first_dense = 0;
@@ -591,12 +599,6 @@ int f184_mips_n(f184_ctx* c)
         }
         if (tma_bricks)
         {
-            static bool brick_attr = false;
-            if (!brick_attr)
-            {
-                CK(c, cudaFuncSetAttribute(k_mips_bricks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BRICK_RING_BYTES));
-                brick_attr = true;
-            }
             k_mips_bricks<true><<<148 * 4, BRICK_WARPS * 32, BRICK_RING_BYTES, c->stream>>>(map, level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N,
                                                                                            export_buf, prev, 2u << c->build_set);
         }

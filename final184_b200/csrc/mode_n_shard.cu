@@ -318,7 +318,11 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather_bricks(const Gathe
 // the texture storage.  Records carry their brick index (word 950, written by k_mips_bricks), so nothing but bulk copies crosses
 // NVLink.
 constexpr int G2_SLOTS = 16;
-constexpr int G2_CONSUMERS = 4;                  // warps; + 1 producer warp
+constexpr int G2_CONSUMERS = 8;                  // warps; + 1 producer warp
+// A slot must always be consumed by the SAME warp (record n goes to warp n % G2_CONSUMERS and to slot n % G2_SLOTS): a parity wait
+// only tells "one phase ago" from "now", so a warp that ran a whole lap ahead of the slot's previous consumer would see the phase
+// it waits for as already complete and read the old record.  (Seven consumers did exactly that.)
+static_assert(G2_SLOTS % G2_CONSUMERS == 0, "every ring slot is owned by one consumer warp");
 constexpr int G2_SLOT_BYTES = 4096;
 constexpr int G2_REC_BYTES = 1760;               // levels 1-3 + brick index: words [512, 952)
 constexpr int G2_REC0_BYTES = 3840;              // with level 0: words [0, 960) — copies end on a 128-byte line (the record is 4096 bytes; words 951.. are padding)
@@ -372,6 +376,7 @@ __global__ void __launch_bounds__((G2_CONSUMERS + 1) * 32) k_gather_bricks_tma(c
     extern __shared__ __align__(128) uint8_t ring[];                // G2_SLOTS x 4 KB, then 2 x G2_UNIT brick indices
     __shared__ __align__(8) uint64_t full[G2_SLOTS], empty[G2_SLOTS], idbar[2];
     __shared__ uint32_t counts[8];
+    __shared__ uint32_t slot_info[G2_SLOTS];     // what the producer decided for the record in the slot: bit 0 = level 1 travels, bit 1 = this rank's copy of it was non-zero
     uint32_t* idbuf = reinterpret_cast<uint32_t*>(ring + G2_SLOTS * G2_SLOT_BYTES);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0)
@@ -431,23 +436,26 @@ __global__ void __launch_bounds__((G2_CONSUMERS + 1) * 32) k_gather_bricks_tma(c
             const uint32_t first = u_cur * G2_UNIT, cnt = min((uint32_t)G2_UNIT, counts[p_cur] - first);
             for (uint32_t j0 = 0; j0 < cnt; j0 += 32)
             {
-                uint32_t my_off = 3584u;
+                uint32_t my_off = 3584u, my_info = 0u;
                 if (j0 + lane < cnt)
-                {
+                {   // the two bits the consumers need about the brick, looked up here for 32 records in one round of loads
                     const uint32_t b = ids[j0 + lane] & 0x7fffffffu;
-                    const bool l1 = (__ldg(need1 + (b >> 5)) >> (b & 31u)) & 1u;
+                    const bool l1 = level0 || ((__ldg(need1 + (b >> 5)) >> (b & 31u)) & 1u);
+                    const bool nz = (l1_nonzero[b >> 5] >> (b & 31u)) & 1u;
                     my_off = level0 ? 0u : (l1 ? 2048u : 3584u);
+                    my_info = (l1 ? 1u : 0u) | (nz ? 2u : 0u);
                 }
                 const uint32_t batch = min(32u, cnt - j0);
                 for (uint32_t i = 0; i < batch; i++)
                 {
-                    const uint32_t off = __shfl_sync(0xffffffffu, my_off, (int)i);
+                    const uint32_t off = __shfl_sync(0xffffffffu, my_off, (int)i), info = __shfl_sync(0xffffffffu, my_info, (int)i);
                     if (lane == 0)
                     {
                         const int slot = (int)(n % G2_SLOTS);
                         if (!mbar_wait_bounded(&empty[slot], ((n / G2_SLOTS) & 1u) ^ 1u, dev_state)) off_fail = true;
                         else
                         {
+                            slot_info[slot] = info;                      // published by the arrive below, read behind the wait on `full`
                             const uint8_t* rec = reinterpret_cast<const uint8_t*>(G.peer_export[p_cur]) + (size_t)(first + j0 + i) * 4096;
                             uint8_t* dst = ring + (size_t)slot * G2_SLOT_BYTES;
                             const uint32_t bytes = G2_REC0_BYTES - off;
@@ -487,8 +495,8 @@ __global__ void __launch_bounds__((G2_CONSUMERS + 1) * 32) k_gather_bricks_tma(c
                 const uint32_t b = rec[950] & 0x7fffffffu;
                 const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
                 const uint32_t word = b >> 5, bit = 1u << (b & 31u);
-                const bool l1 = level0 || ((need1[word] & bit) != 0);
-                const bool was_nonzero = (l1_nonzero[word] & bit) != 0;
+                const uint32_t info = slot_info[slot];
+                const bool l1 = (info & 1u) != 0, was_nonzero = (info & 2u) != 0;
                 if (level0)
                 {
 #pragma unroll
@@ -654,6 +662,29 @@ extern "C" int f184_peer_barrier(f184_ctx* c)
     return f184_leave(c, sec, body());
 }
 
+// first-use set-up of the gather (called from f184_prepare_frame, i.e. before anything of a frame is enqueued: no allocation in the
+// middle of a frame, where a peer barrier may be waiting)
+int f184_gather_init_n(f184_ctx* c)
+{
+    static bool attr = false;
+    if (!attr)
+    {
+        CK(c, cudaFuncSetAttribute(k_gather_bricks_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SLOTS * G2_SLOT_BYTES + 2 * G2_UNIT * 4));
+        attr = true;
+    }
+    if (c->need1) return F184_OK;
+    const uint32_t n_words = ((uint32_t)(c->cfg.grid_n / 8) * (c->cfg.grid_n / 8) * (c->cfg.grid_n / 8) + 31) / 32;
+    CK(c, cudaMalloc(&c->need1, 4ull * n_words));
+    for (int i = 0; i < 2; i++)
+    {
+        CK(c, cudaMalloc(&c->l1_nonzero[i], 4ull * n_words));
+        int rc = f184_fill_async(c, c->l1_nonzero[i], 0u, 4ull * n_words, c->stream);
+        if (rc) return rc;
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return F184_OK;
+}
+
 int f184_gather_n(f184_ctx* c, const f184_trace_constants* view)
 {
     if (c->cfg.nranks <= 1) return F184_OK;
@@ -689,18 +720,10 @@ int f184_gather_n(f184_ctx* c, const f184_trace_constants* view)
             G.lin[l][d] = mips + c->mip_levels[l].offset_texels + (uint64_t)d * n * n * n;
         }
     }
-    rc = f184_stage_begin(c, F184_STAGE_EXCHANGE);
+    rc = f184_stage_begin(c, F184_STAGE_NEED);
     if (rc) return rc;
     const uint32_t n_words = ((uint32_t)(c->cfg.grid_n / 8) * (c->cfg.grid_n / 8) * (c->cfg.grid_n / 8) + 31) / 32;
-    if (!c->need1)
-    {
-        CK(c, cudaMalloc(&c->need1, 4ull * n_words));
-        for (int i = 0; i < 2; i++)
-        {
-            CK(c, cudaMalloc(&c->l1_nonzero[i], 4ull * n_words));
-            if ((rc = f184_fill_async(c, c->l1_nonzero[i], 0u, 4ull * n_words, c->stream))) return rc;      // in stream order, ahead of the gather below
-        }
-    }
+    if ((rc = f184_gather_init_n(c))) return rc;
     {   // What has to travel this frame?  Level 0: only if a cone of this rank's rows samples it.  Level 1: only the bricks such a cone
         // samples (needs the camera: f184_gather_volume_view).  F184_FLAG_GATHER_LINEAR — the tests' full comparison — and
         // F184_GATHER_LEVEL0=1 / F184_GATHER_ALL=1 force everything.
@@ -745,17 +768,13 @@ int f184_gather_n(f184_ctx* c, const f184_trace_constants* view)
         k_clear_foreign_level0<<<148 * 4, 256, 0, c->stream>>>(vs.rad_surf, (int)c->cfg.grid_n, c->cfg.nranks, c->cfg.rank, c->dev_state, set);
         CK_LAUNCH(c);
     }
+    if ((rc = f184_stage_end(c, F184_STAGE_NEED))) return rc;
+    if ((rc = f184_stage_begin(c, F184_STAGE_EXCHANGE))) return rc;
     static const bool gather_ldg = [] { const char* e = getenv("F184_GATHER_LDG"); return e && atoi(e) != 0; }();
     if ((rc = f184_zero_counters(c, 1u << F184_COUNTER_GATHER_BYTES))) return rc;
     if (gather_ldg) k_gather_bricks<<<dim3(c->cfg.nranks, 148), GATHER_WARPS * 32, 0, c->stream>>>(G);
     else
     {
-        static bool attr = false;
-        if (!attr)
-        {
-            CK(c, cudaFuncSetAttribute(k_gather_bricks_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SLOTS * G2_SLOT_BYTES + 2 * G2_UNIT * 4));
-            attr = true;
-        }
         static const int gather_ctas = [] { const char* e = getenv("F184_GATHER_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 148 * 2; }();     // (tests: few CTAs = many units each)
         k_gather_bricks_tma<<<gather_ctas, (G2_CONSUMERS + 1) * 32, G2_SLOTS * G2_SLOT_BYTES + 2 * G2_UNIT * 4, c->stream>>>(G, c->dev_state, c->need1, c->l1_nonzero[set]);
     }
@@ -765,7 +784,9 @@ int f184_gather_n(f184_ctx* c, const f184_trace_constants* view)
     CK_LAUNCH(c);
     rc = f184_stage_end(c, F184_STAGE_EXCHANGE);
     if (rc) return rc;
-    rc = f184_mips_tail_n(c, true);
+    if ((rc = f184_stage_begin(c, F184_STAGE_TAIL))) return rc;
+    rc = f184_mips_tail_n(c, false);
     if (rc) return rc;
+    if ((rc = f184_stage_end(c, F184_STAGE_TAIL))) return rc;
     return f184_volume_publish(c);        // every rank's bricks are in: this set is what the next trace samples
 }

@@ -265,11 +265,8 @@ static int trace_params(f184_ctx* c, const VolumeSet& vs, const f184_trace_const
     return F184_OK;
 }
 
-static int trace_launch(f184_ctx* c, const ConeParams& P, uint32_t grid_y, cudaStream_t stream)
+int f184_trace_init_n(f184_ctx* c)
 {
-    dim3 grid((P.W + 31) / 32, grid_y);
-    // two register budgets of the same kernel: 4 CTAs/SM (64 registers) or 3 (80, no spill); F184_TRACE_CTAS=3 selects the latter (A/B knob)
-    static const int min_ctas = [] { const char* e = getenv("F184_TRACE_CTAS"); return e ? atoi(e) : 4; }();
     // The tracer uses no shared memory, so by default its launch configures the SMs with the smallest shared-memory carve-out (all of
     // the unified array as L1 / texture cache) — and a kernel that NEEDS shared memory (every kernel of the build stream: brick rings,
     // the gather's 64 KB ring) cannot become resident on an SM until the tracer's CTAs have drained from it and the SM is reconfigured:
@@ -284,6 +281,14 @@ static int trace_launch(f184_ctx* c, const ConeParams& P, uint32_t grid_y, cudaS
         CK(c, cudaFuncSetAttribute(k_trace_n<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
         carveout_set = true;
     }
+    return F184_OK;
+}
+
+static int trace_launch(f184_ctx* c, const ConeParams& P, uint32_t grid_y, cudaStream_t stream)
+{
+    dim3 grid((P.W + 31) / 32, grid_y);
+    // two register budgets of the same kernel: 4 CTAs/SM (64 registers) or 3 (80, no spill); F184_TRACE_CTAS=3 selects the latter (A/B knob)
+    static const int min_ctas = [] { const char* e = getenv("F184_TRACE_CTAS"); return e ? atoi(e) : 4; }();
     if (c->cfg.flags & F184_FLAG_SPEC_APPENDIX_B) k_trace_n<3, true><<<grid, TRACE_THREADS, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
     else if (min_ctas == 3) k_trace_n<3, false><<<grid, TRACE_THREADS, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);
     else k_trace_n<4, false><<<grid, TRACE_THREADS, 0, stream>>>(P, c->counters_dev + F184_COUNTER_MARCH_STEPS);

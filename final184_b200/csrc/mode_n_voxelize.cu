@@ -519,13 +519,22 @@ __global__ void __launch_bounds__(256) k_apply_fragments(const ApplyArgs P)     
     if (s == P.rank) return;
     const uint32_t n = min(P.peer_cursor[s][sub], P.sub_cap);
     const uint4* q = P.peer_queue[s] + (size_t)sub * P.sub_cap;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        const uint4 r = q[i];
-        const size_t o = r.x;
-        atomicAdd(P.accC + o, make_float4((float)(r.y & 255u), (float)((r.y >> 8) & 255u), (float)((r.y >> 16) & 255u), 1.0f));
-        atomicAdd(P.accN + o, make_float4((float)(int8_t)(r.z & 255u), (float)(int8_t)((r.z >> 8) & 255u), (float)(int8_t)((r.z >> 16) & 255u), 0.0f));
-        P.brick_flags[o >> 9] = 1u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride)
+    {   // four peer loads in flight per thread (each is an NVLink round trip), then the local reductions
+        uint4 r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (i0 + k * stride < n) r[k] = q[i0 + k * stride];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            if (i0 + k * stride >= n) break;
+            const size_t o = r[k].x;
+            atomicAdd(P.accC + o, make_float4((float)(r[k].y & 255u), (float)((r[k].y >> 8) & 255u), (float)((r[k].y >> 16) & 255u), 1.0f));
+            atomicAdd(P.accN + o, make_float4((float)(int8_t)(r[k].z & 255u), (float)(int8_t)((r[k].z >> 8) & 255u), (float)(int8_t)((r[k].z >> 16) & 255u), 0.0f));
+            P.brick_flags[o >> 9] = 1u;
+        }
     }
 }
 
@@ -756,10 +765,10 @@ int f184_normalise_n(f184_ctx* c)
     const int N = (int)c->cfg.grid_n;
     const uint32_t NB = (uint32_t)N / 8, G = c->cfg.nranks > 1 ? c->cfg.nranks : 1;
     const uint32_t n_own = (NB / G) * NB * NB;
-    int rc = f184_stage_begin(c, F184_STAGE_NORMALISE);
-    if (rc) return rc;
+    int rc = F184_OK;
     if (G > 1 && c->frag_queue && c->frag_pending)
-    {   // the fragments the other ranks hold for this rank (their kernels finished before the barrier this call follows)
+    {
+        if ((rc = f184_stage_begin(c, F184_STAGE_APPLY))) return rc;   // the fragments the other ranks hold for this rank (their kernels finished before the barrier this call follows)
         ApplyArgs P{};
         for (uint32_t p = 0; p < G; p++)
         {
@@ -772,10 +781,13 @@ int f184_normalise_n(f184_ctx* c)
         P.accC = img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR); P.accN = img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL);
         P.brick_flags = img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS);
         P.rank = c->cfg.rank; P.nranks = G; P.sub_cap = c->frag_cap / F184_FRAG_SUBQUEUES;
-        k_apply_fragments<<<dim3(16, G * F184_FRAG_SUBQUEUES), 256, 0, c->stream>>>(P);
+        k_apply_fragments<<<dim3(8, G * F184_FRAG_SUBQUEUES), 256, 0, c->stream>>>(P);
         CK_LAUNCH(c);
         c->frag_pending = false;          // applied once: a second normalise without a new accumulation must not add them again
+        if ((rc = f184_stage_end(c, F184_STAGE_APPLY))) return rc;
     }
+    rc = f184_stage_begin(c, F184_STAGE_NORMALISE);
+    if (rc) return rc;
     if ((rc = f184_zero_counters(c, (1u << F184_COUNTER_OCCUPIED) | (1u << F184_COUNTER_BRICKS) | (1u << F184_COUNTER_COUNT)))) return rc;   // COUNT = the list cursor
     k_brick_compact<<<(n_own + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,
                                                               c->counters_dev, n_own, NB, G, c->cfg.rank % G);

@@ -227,7 +227,10 @@ typedef enum f184_stage_id {
     F184_STAGE_LIGHTING = 9,       /* f184_lighting_deferred */
     F184_STAGE_COMPOSITE = 10,     /* f184_composite */
     F184_STAGE_BARRIER = 11,       /* multi-GPU: f184_peer_barrier (flag exchange + the wait for the slowest rank) */
-    F184_STAGE_COUNT = 12
+    F184_STAGE_APPLY = 12,         /* multi-GPU: the owner fetches and applies the fragments the other ranks rasterised for it (head of f184_normalise) */
+    F184_STAGE_NEED = 13,          /* multi-GPU: which levels / bricks do this rank's cones sample? (head of f184_gather_volume) */
+    F184_STAGE_TAIL = 14,          /* multi-GPU: the dense levels below level 3, rebuilt locally behind the gather */
+    F184_STAGE_COUNT = 15
 } f184_stage_id;
 
 typedef enum f184_counter_id {

@@ -38,6 +38,22 @@ def make_box(G, N, W, H, SH, sc, cams, fi, flags):
 
 
 def box_frame(ranks, cam, k):
+    if os.environ.get("LOOPBACK_PHASED"):
+        # diagnostics: the same frame phase by phase, every rank synchronised after each phase — a failing kernel names its phase
+        phases = [("accumulate", lambda c: c.voxelize_accumulate(cam)), ("barrier 1", lambda c: c.peer_barrier()), ("normalise", lambda c: c.normalise()),
+                  ("inject", lambda c: c.inject(k)), ("mips", lambda c: c.build_mips()), ("barrier 2", lambda c: c.peer_barrier()),
+                  ("gather", lambda c: c.gather_volume(k)), ("trace", lambda c: c.trace_indirect(k))]
+        for name, fn in phases:
+            if name.startswith("barrier") and os.environ.get("LOOPBACK_PHASED") == "2":
+                continue                # (under compute-sanitizer kernels run one at a time: the host synchronisation between the phases stands in)
+            for g in ranks:
+                fn(g.ctx)
+            for r, g in enumerate(ranks):
+                try:
+                    g.ctx.sync()
+                except A.F184Error as e:
+                    raise SystemExit(f"phase '{name}' failed on rank {r}: {e}")
+        return
     for g in ranks:                 # enqueue every rank's frame before synchronising any of them
         g.frame(cam, k)
 

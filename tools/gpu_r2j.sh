@@ -1,10 +1,7 @@
 #!/bin/bash
-# Round-2 session J (gpurun --gpus 8): the scaling run — multi-GPU parity worker (4 ranks), then the bench line at 4 and 8 ranks (C3 headline + c4_scaling),
-# and at 8 ranks once more with every pass on one stream (solo stage times).
+# Round-2 session J (gpurun --gpus 8): the scaling run — the bench line at 8 ranks (C3 headline + c4_scaling), pipelined and with every pass on one stream (solo stage times).
 tag=${1:-r02q}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv,noheader | wc -l; free -g | head -2 | tail -1; nproc
-timeout 300 python -m pytest tests/test_gpu_multi.py -m gpu -q 2>&1 | tail -5
 run() { # n extra suffix
   timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $1 --steps 50 --warmup 5 --no-cpu-baseline $2 > gpurun_out/bench_${tag}_g$1$3.json 2> gpurun_out/bench_${tag}_g$1$3.err
   python - <<PY
@@ -19,6 +16,5 @@ except Exception as e:
     print("N=$1 failed", e); print(open("gpurun_out/bench_${tag}_g$1$3.err").read()[-3000:])
 PY
 }
-run 8 "" ""
-run 8 "--no-overlap" "_nooverlap"
-run 4 "" ""
+run ${2:-8} "--no-overlap" "_nooverlap"
+run ${2:-8} "" ""
