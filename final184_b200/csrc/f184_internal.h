@@ -172,7 +172,7 @@ struct f184_ctx
     uint32_t frag_cap = 0;
     bool frag_pending = false;                // an accumulation has run since the last normalise: the peers' queues hold fragments for this rank
     bool frag_sent_applied = false;           // a peer barrier has followed the last accumulation: the next one starts the queues over
-    uint32_t* export_buf = nullptr;           // 1024 words per listed brick of the own slab
+    uint32_t* export_buf = nullptr;           // the own bricks' export arrays (k_mips_bricks): level 0 | level 1 | levels 2, 3 + brick index; 1024 words of room per brick
     uint32_t* sync_flags = nullptr;           // [8] barrier epochs written by the peers + [8] scratch
     uint32_t barrier_epoch = 0;
     // device-side state words (F184_DEV_*): sticky error bits and the level-0 bookkeeping of the peer gather

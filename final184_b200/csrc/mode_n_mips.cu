@@ -235,7 +235,7 @@ constexpr int BRICK_RING_BYTES = BRICK_WARPS * BRICK_STAGES * 2048;
 template <bool TMA>
 __global__ void __launch_bounds__(BRICK_WARPS * 32)
 k_mips_bricks(const __grid_constant__ CUtensorMap level0_map, const uint32_t* __restrict__ level0, const uint32_t* __restrict__ brick_list,
-              const unsigned long long* __restrict__ brick_count, BrickMipOut out, int N, uint32_t* __restrict__ export_buf,
+              const unsigned long long* __restrict__ brick_count, BrickMipOut out, int N, uint32_t* __restrict__ export_buf, uint32_t export_cap,
               uint32_t* __restrict__ brick_prev, uint32_t set_bit)
 {
     extern __shared__ __align__(128) uint8_t ring_raw[];            // TMA: [warp][stage][512 texels]; LDG: [warp][512 texels]
@@ -280,12 +280,11 @@ k_mips_bricks(const __grid_constant__ CUtensorMap level0_map, const uint32_t* __
         if (TMA)
         {
             mbar_wait(&bars[warp][stage], (it / BRICK_STAGES) & 1u);
-            // multi-GPU: the brick's packed record (1024 words: level 0 | level 1 | level 2 | level 3) that the other
-            // ranks pull over NVLink (mode_n_shard.cu)
+            // multi-GPU: the brick's level 0 into the export array the other ranks pull from (see below)
             if (export_buf)
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    reinterpret_cast<uint4*>(export_buf + (size_t)i * 1024)[lane + 32 * k] = reinterpret_cast<const uint4*>(s0)[lane + 32 * k];
+                    reinterpret_cast<uint4*>(export_buf + (size_t)i * 512)[lane + 32 * k] = reinterpret_cast<const uint4*>(s0)[lane + 32 * k];
         }
         else
         {
@@ -297,11 +296,16 @@ k_mips_bricks(const __grid_constant__ CUtensorMap level0_map, const uint32_t* __
                 const int y = row & 7, z = row >> 3;
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(level0 + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4));
                 *reinterpret_cast<uint4*>(s0 + row * 8 + half * 4) = v;
-                if (export_buf) reinterpret_cast<uint4*>(export_buf + (size_t)i * 1024)[q] = v;
+                if (export_buf) reinterpret_cast<uint4*>(export_buf + (size_t)i * 512)[q] = v;
             }
         }
-        uint32_t* rec = export_buf ? export_buf + (size_t)i * 1024 : nullptr;
-        if (rec && lane == 0) rec[950] = b;            // the record names its brick: the TMA-fed gather reads nothing but records over NVLink
+        // multi-GPU: what the other ranks fetch over NVLink (mode_n_shard.cu), three arrays indexed by the brick's position in the list —
+        // level 0 (512 words per brick; only glossy scenes make anybody read it), level 1 (`fine`, 384 words; read by the ranks whose
+        // cones sample it) and a 64-word `coarse` block everybody reads: level 2, level 3, the brick's index.  Coarse blocks of
+        // consecutive bricks are contiguous, so a reader moves 64 of them with one bulk copy.
+        uint32_t* fine = export_buf ? export_buf + (size_t)export_cap * 512 + (size_t)i * 384 : nullptr;
+        uint32_t* coarse = export_buf ? export_buf + (size_t)export_cap * 896 + (size_t)i * 64 : nullptr;
+        if (coarse && lane == 0) coarse[54] = b;
         __syncwarp();
         {   // level 1: lane -> output row (oy, oz) = lane & 15 and three of the six directions
             const int p = lane & 15, oy = p & 3, oz = p >> 2, d0 = (lane >> 4) * 3;
@@ -334,7 +338,7 @@ k_mips_bricks(const __grid_constant__ CUtensorMap level0_map, const uint32_t* __
                 }
                 const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<uint4*>(&sh1[warp][d][(oz * 4 + oy) * 4]) = v;
-                if (rec) *reinterpret_cast<uint4*>(rec + 512 + d * 64 + (oz * 4 + oy) * 4) = v;
+                if (fine) *reinterpret_cast<uint4*>(fine + d * 64 + (oz * 4 + oy) * 4) = v;
                 *reinterpret_cast<uint4*>(out.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = v;
                 surf3Dwrite(v, out.surf[0], gx * 4, gy, atlas_z(d, n1, gz));
             }
@@ -366,7 +370,7 @@ k_mips_bricks(const __grid_constant__ CUtensorMap level0_map, const uint32_t* __
             const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
             const uint2 v = make_uint2(o[0], o[1]);
             *reinterpret_cast<uint2*>(&sh2[warp][d][(oz * 2 + oy) * 2]) = v;
-            if (rec) *reinterpret_cast<uint2*>(rec + 896 + d * 8 + (oz * 2 + oy) * 2) = v;
+            if (coarse) *reinterpret_cast<uint2*>(coarse + d * 8 + (oz * 2 + oy) * 2) = v;
             *reinterpret_cast<uint2*>(out.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = v;
             surf3Dwrite(v, out.surf[1], gx * 4, gy, atlas_z(d, n2, gz));
         }
@@ -381,7 +385,7 @@ k_mips_bricks(const __grid_constant__ CUtensorMap level0_map, const uint32_t* __
                 for (int j = 0; j < 2; j++) { t[k][j][0] = sh2[warp][d][(k * 2 + j) * 2]; t[k][j][1] = sh2[warp][d][(k * 2 + j) * 2 + 1]; }
             const uint32_t v = reduce_dir(t, d);
             out.lin[2][d][((size_t)bz * n3 + by) * n3 + bx] = v;
-            if (rec) rec[944 + d] = v;
+            if (coarse) coarse[48 + d] = v;
             surf3Dwrite(v, out.surf[2], bx * 4, by, atlas_z(d, n3, bz));
         }
         __syncwarp();                              // every lane is done with this stage's brick (and with sh1 / sh2)
@@ -574,6 +578,7 @@ int f184_mips_n(f184_ctx* c)
             }
         }
         uint32_t* export_buf = nullptr;
+        const uint32_t export_cap = ((uint32_t)(N / 8) * (N / 8) * (N / 8)) / (c->cfg.nranks ? c->cfg.nranks : 1);       // bricks the export arrays hold
         if (c->cfg.nranks > 1)
         {
             void* e = nullptr;
@@ -600,11 +605,11 @@ int f184_mips_n(f184_ctx* c)
         if (tma_bricks)
         {
             k_mips_bricks<true><<<148 * 4, BRICK_WARPS * 32, BRICK_RING_BYTES, c->stream>>>(map, level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N,
-                                                                                           export_buf, prev, 2u << c->build_set);
+                                                                                           export_buf, export_cap, prev, 2u << c->build_set);
         }
         else
             k_mips_bricks<false><<<148 * 8, BRICK_WARPS * 32, BRICK_WARPS * 2048, c->stream>>>(map, level0, c->brick_list, c->counters_dev + F184_COUNTER_COUNT, bo, N,
-                                                                                              export_buf, prev, 2u << c->build_set);
+                                                                                              export_buf, export_cap, prev, 2u << c->build_set);
         CK_LAUNCH(c);
         first_dense = c->n_mip_levels;          // the tail kernel takes every remaining level
         if (c->cfg.nranks <= 1)                 // (multi-GPU: level 3 is complete only after f184_gather_volume, which runs the tail)

@@ -217,11 +217,11 @@ __global__ void __launch_bounds__(256) k_clear_foreign_level0(cudaSurfaceObject_
 
 struct GatherArgs
 {
-    const uint32_t* peer_export[8];
+    const uint32_t* peer_export[8];    // each rank's export arrays (k_mips_bricks): level 0 | fine (level 1) | coarse (levels 2, 3, brick index)
     const unsigned long long* peer_counters[8];
-    const uint32_t* peer_list[8];
     const uint32_t* dev_state;
-    unsigned long long* gather_bytes;  // F184_COUNTER_GATHER_BYTES: what the TMA-fed kernel's bulk copies move over NVLink (summed by its producers)
+    unsigned long long* gather_bytes;  // F184_COUNTER_GATHER_BYTES: what the bulk copies move over NVLink (summed by the producers)
+    uint32_t export_cap;               // bricks per export array
     int rank, nranks, N, write_linear;
     cudaSurfaceObject_t rad_surf;
     uint32_t* rad_lin;
@@ -229,103 +229,31 @@ struct GatherArgs
     cudaSurfaceObject_t surf[3];       // atlas levels 1..3 (direction d at z + 2 d n)
 };
 
-// behind the gather: the set's level-0 bookkeeping, and the bytes that crossed NVLink (F184_COUNTER_GATHER_BYTES)
-__global__ void k_gather_state(const GatherArgs G, uint32_t* dev_state, int set, unsigned long long* counters, uint32_t ldg_bytes_with_l0, uint32_t ldg_bytes_without)
+// behind the gather: the set's level-0 bookkeeping
+__global__ void k_gather_state(uint32_t* dev_state, int set)
 {
-    const bool level0 = dev_state[F184_DEV_NEED_L0] != 0;
-    dev_state[F184_DEV_L0_FULL + set] = level0 ? 1u : 0u;
-    if (ldg_bytes_without)
-    {   // the per-lane-load variant moves the same bytes for every record
-        unsigned long long records = 0;
-        for (int p = 0; p < G.nranks; p++)
-            if (p != G.rank) records += G.peer_counters[p][F184_COUNTER_COUNT];
-        counters[F184_COUNTER_GATHER_BYTES] = records * (unsigned long long)(level0 ? ldg_bytes_with_l0 : ldg_bytes_without);
-    }
+    dev_state[F184_DEV_L0_FULL + set] = dev_state[F184_DEV_NEED_L0] != 0 ? 1u : 0u;
 }
 
-constexpr int GATHER_WARPS = 8;
-
-__global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather_bricks(const GatherArgs G)
-{
-    // grid = (nranks, slices): consecutive CTAs read from DIFFERENT peers, and the peer order is rotated by the reader's rank.
-    // With the peer in the slow grid dimension every GPU of the box read from peer 0 first, then from peer 1, ... : seven
-    // readers on one GPU's NVLink egress at a time while the other links idled (111 MB per rank at ~320 GB/s at 8 GPUs against
-    // 630 GB/s at 2).  Now each wave of CTAs covers all peers, and reader r starts at peer r+1.
-    const int p = (int)((blockIdx.x + (unsigned)G.rank) % (unsigned)G.nranks);
-    if (p == G.rank) return;                                   // blockIdx.x == 0
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t warp_global = blockIdx.y * GATHER_WARPS + warp, n_warps = gridDim.y * GATHER_WARPS;
-    const uint32_t count = (uint32_t)G.peer_counters[p][F184_COUNTER_COUNT];     // that rank's brick-list cursor
-    const int N = G.N, NB = N >> 3, n1 = N >> 1, n2 = N >> 2, n3 = N >> 3;
-    const bool level0 = G.dev_state[F184_DEV_NEED_L0] != 0;       // block-uniform: level 0 travels only when a cone of this rank's rows samples it
-    for (uint32_t i = warp_global; i < count; i += n_warps)
-    {
-        const uint32_t* rec = G.peer_export[p] + (size_t)i * 1024;
-        const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
-        const uint32_t b = G.peer_list[p][i] & 0x7fffffffu;
-        const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
-        uint4 l0[4], l1[3];
-        if (level0)
-        {
-#pragma unroll
-            for (int k = 0; k < 4; k++) l0[k] = rec4[lane + 32 * k];           // 7 independent 16-byte peer loads in flight
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) l1[k] = rec4[128 + lane + 32 * k];
-        uint2 l2 = make_uint2(0, 0);
-        if (lane < 24) l2 = reinterpret_cast<const uint2*>(rec + 896)[lane];
-        uint32_t l3 = 0;
-        if (lane < 6) l3 = rec[944 + lane];
-        if (level0)
-        {
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                const int q = lane + 32 * k, row = q >> 1, half = q & 1, y = row & 7, z = row >> 3;
-                surf3Dwrite(l0[k], G.rad_surf, (bx * 8 + half * 4) * 4, by * 8 + y, bz * 8 + z);
-                if (G.write_linear) *reinterpret_cast<uint4*>(G.rad_lin + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4) = l0[k];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-        {
-            const int j = lane + 32 * k, d = j >> 4, r = j & 15, oy = r & 3, oz = r >> 2;
-            const int gx = bx * 4, gy = by * 4 + oy, gz = bz * 4 + oz;
-            surf3Dwrite(l1[k], G.surf[0], gx * 4, gy, atlas_z(d, n1, gz));
-            if (G.write_linear) *reinterpret_cast<uint4*>(G.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = l1[k];
-        }
-        if (lane < 24)
-        {
-            const int d = lane >> 2, r = lane & 3, oy = r & 1, oz = r >> 1;
-            const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
-            surf3Dwrite(l2, G.surf[1], gx * 4, gy, atlas_z(d, n2, gz));
-            if (G.write_linear) *reinterpret_cast<uint2*>(G.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = l2;
-        }
-        if (lane < 6)
-        {
-            surf3Dwrite(l3, G.surf[2], bx * 4, by, atlas_z(lane, n3, bz));
-            G.lin[2][lane][((size_t)bz * n3 + by) * n3 + bx] = l3;             // level 3 is the source of the local tail: always
-        }
-    }
-}
-
-// ---- the gather, TMA-fed (default) ---------------------------------------------------------------------------------------------
-// The per-lane peer loads above keep 7 x 16 bytes per lane in flight and need every warp of the GPU to cover NVLink's ~2 us: fine
-// when the gather has the GPU to itself (630 GB/s at 2 GPUs), but inside the frame pipeline it shares the SMs with the cone trace
-// of the previous frame and ran at 70 GB/s.  Here ONE thread per CTA issues bulk copies (cp.async.bulk: the TMA engine moves a
-// brick's whole record, 1.7 KB or 3.7 KB, peer HBM -> shared memory over NVLink, completion on an mbarrier) into a 16-slot ring —
-// 28-60 KB in flight per CTA whatever else runs on the SM — and four consumer warps write the landed records through surfaces into
-// the texture storage.  Records carry their brick index (word 950, written by k_mips_bricks), so nothing but bulk copies crosses
-// NVLink.
-constexpr int G2_SLOTS = 16;
-constexpr int G2_CONSUMERS = 8;                  // warps; + 1 producer warp
-// A slot must always be consumed by the SAME warp (record n goes to warp n % G2_CONSUMERS and to slot n % G2_SLOTS): a parity wait
+// ---- the gather ------------------------------------------------------------------------------------------------------------------
+// Nothing but bulk copies (cp.async.bulk: the TMA engine moves peer HBM -> shared memory over NVLink, completion on an mbarrier)
+// crosses NVLink, issued by one producer warp per CTA, so the bytes in flight do not depend on how many warps of the SM the
+// gather gets while the cone trace of the previous frame runs beside it.  (Per-lane peer loads ran at 70 GB/s inside the frame;
+// one 1.7 KB record per brick in one copy ran at 460 GB/s where level 1 was needed, but the 224-byte copies of the bricks whose
+// level 1 no cone needs — most of them, at 8 GPUs — were bound by copies in flight, not bytes: 86 GB/s.)  So the owner exports
+// three arrays, and what every rank needs of EVERY brick — levels 2 and 3 and the brick's index, 256 bytes — is contiguous over
+// consecutive bricks: one 16 KB copy moves a work unit's 64 bricks.  Level 1 (1536 B) and, in a glossy scene, level 0 (2048 B)
+// follow per brick through a ring, only for the bricks k_need_bricks marked.
+constexpr int G4_CONSUMERS = 8;                  // warps; + 1 producer warp
+constexpr int G4_SLOTS = 16;                     // ring of per-brick fine copies
+// A slot must always be consumed by the SAME warp (fine record n goes to warp n % G4_CONSUMERS and to slot n % G4_SLOTS): a parity wait
 // only tells "one phase ago" from "now", so a warp that ran a whole lap ahead of the slot's previous consumer would see the phase
 // it waits for as already complete and read the old record.  (Seven consumers did exactly that.)
-static_assert(G2_SLOTS % G2_CONSUMERS == 0, "every ring slot is owned by one consumer warp");
-constexpr int G2_SLOT_BYTES = 4096;
-constexpr int G2_REC_BYTES = 1760;               // levels 1-3 + brick index: words [512, 952)
-constexpr int G2_REC0_BYTES = 3840;              // with level 0: words [0, 960) — copies end on a 128-byte line (the record is 4096 bytes; words 951.. are padding)
+static_assert(G4_SLOTS % G4_CONSUMERS == 0, "every ring slot is owned by one consumer warp");
+constexpr int G4_SLOT_BYTES = 3584;              // level 0 at [0, 2048), level 1 at [2048, 3584)
+constexpr int G4_UNIT = 64;                      // bricks per work unit
+constexpr int G4_COARSE_BUFS = 3;                // unit k + 1 is prefetched while unit k is worked on and the consumers may still be on k - 1
+constexpr int G4_SMEM_BYTES = G4_COARSE_BUFS * G4_UNIT * 256 + G4_SLOTS * G4_SLOT_BYTES + G4_COARSE_BUFS * G4_UNIT * 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -360,188 +288,199 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int G2_UNIT = 128;                      // bricks per work unit: the producer fetches a unit's 128 brick indices (512 B) with one bulk copy
-
-// Work = units of G2_UNIT consecutive records of one peer, walked in the same order by both roles: u = 0, 1, ...; for each u the peers in
-// an order rotated by the reader's rank (so the box's readers do not all start on the same peer); CTA c takes every gridDim.x-th unit.
-// Per record the producer looks the brick up in the need mask (k_need_bricks) and fetches
-//     level 0 needed by some cone (glossy scene): words [0, 952)      3808 B
-//     level 1 of this brick needed:               words [512, 952)    1760 B
-//     otherwise (levels 2, 3 + brick index):      words [896, 952)     224 B
-// and the consumers write what arrived; a brick whose level 1 did not travel gets zeros there IF this rank's copy of it is not zero
-// already (one bit per brick and texture set) — so a foreign brick's level 1 on this rank is always either current or zero, never stale.
-__global__ void __launch_bounds__((G2_CONSUMERS + 1) * 32) k_gather_bricks_tma(const GatherArgs G, uint32_t* dev_state, const uint32_t* __restrict__ need1,
+// Work = units of G4_UNIT consecutive bricks of one peer's list, walked in the same order by both roles: u = 0, 1, ...; for each u the
+// peers in an order rotated by the reader's rank (so the box's readers do not all start on the same peer); CTA c takes every
+// gridDim.x-th unit.  Per unit the producer fetches the coarse blocks, looks every brick up in the need mask (k_need_bricks) and in
+// this rank's "my copy of its level 1 is not zero" bits, publishes per brick
+//     info = level 1 travels | (my copy is non-zero) << 1 | (sequence number among this CTA's fine copies) << 2
+// and issues the fine copies.  The consumers write what arrived; a brick whose level 1 did not travel gets zeros there IF this
+// rank's copy of it is not zero already — so a foreign brick's level 1 on this rank is always either current or zero, never stale.
+__global__ void __launch_bounds__((G4_CONSUMERS + 1) * 32) k_gather_bricks_tma(const GatherArgs G, uint32_t* dev_state, const uint32_t* __restrict__ need1,
                                                                                uint32_t* __restrict__ l1_nonzero)
 {
-    extern __shared__ __align__(128) uint8_t ring[];                // G2_SLOTS x 4 KB, then 2 x G2_UNIT brick indices
-    __shared__ __align__(8) uint64_t full[G2_SLOTS], empty[G2_SLOTS], idbar[2];
+    extern __shared__ __align__(128) uint8_t gsm[];
+    __shared__ __align__(8) uint64_t full[G4_SLOTS], empty[G4_SLOTS], coarse_full[G4_COARSE_BUFS], coarse_free[G4_COARSE_BUFS], info_ready[G4_COARSE_BUFS];
     __shared__ uint32_t counts[8];
-    __shared__ uint32_t slot_info[G2_SLOTS];     // what the producer decided for the record in the slot: bit 0 = level 1 travels, bit 1 = this rank's copy of it was non-zero
-    uint32_t* idbuf = reinterpret_cast<uint32_t*>(ring + G2_SLOTS * G2_SLOT_BYTES);
+    uint32_t* coarse = reinterpret_cast<uint32_t*>(gsm);                                            // [buf][brick][64]
+    uint8_t* ring = gsm + G4_COARSE_BUFS * G4_UNIT * 256;
+    uint32_t* info = reinterpret_cast<uint32_t*>(ring + G4_SLOTS * G4_SLOT_BYTES);                  // [buf][brick]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0)
     {
-        for (int s_ = 0; s_ < G2_SLOTS; s_++) { mbar_init(&full[s_], 1); mbar_init(&empty[s_], 1); }
-        mbar_init(&idbar[0], 1); mbar_init(&idbar[1], 1);
+        for (int s_ = 0; s_ < G4_SLOTS; s_++) { mbar_init(&full[s_], 1); mbar_init(&empty[s_], 1); }
+        for (int s_ = 0; s_ < G4_COARSE_BUFS; s_++) { mbar_init(&coarse_full[s_], 1); mbar_init(&coarse_free[s_], G4_CONSUMERS); mbar_init(&info_ready[s_], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 8) counts[threadIdx.x] = ((int)threadIdx.x < G.nranks && (int)threadIdx.x != G.rank) ? (uint32_t)G.peer_counters[threadIdx.x][F184_COUNTER_COUNT] : 0u;
     __syncthreads();
     const bool level0 = G.dev_state[F184_DEV_NEED_L0] != 0;
     uint32_t max_units = 0;
-    for (int p = 0; p < G.nranks; p++) max_units = max(max_units, (counts[p] + G2_UNIT - 1) / G2_UNIT);
+    for (int p = 0; p < G.nranks; p++) max_units = max(max_units, (counts[p] + G4_UNIT - 1) / G4_UNIT);
     const int N = G.N, NB = N >> 3, n1 = N >> 1, n2 = N >> 2, n3 = N >> 3;
-    uint32_t n = 0;                                                  // sequence number of the next record of this CTA
     uint32_t unit_no = 0;                                            // valid units seen so far (all CTAs count alike)
-    if (warp == G2_CONSUMERS)
-    {   // ---- producer: the whole warp walks the units; the lanes look up the need bits of 32 records at a time (one round of loads
-        // instead of one dependent L2 access per record), lane 0 issues the copies
-        // first pass over the unit sequence only to find this CTA's units: (peer, u) pairs, visited again below with their indices prefetched
-        uint32_t k = 0;                                              // this CTA's units so far (id buffer = k & 1)
-        // prefetch helper: the indices of unit (p, u) into idbuf[k & 1]
-        auto fetch_ids = [&](int p, uint32_t u, uint32_t kk) {
-            if (lane != 0) return;
-            const uint32_t first = u * G2_UNIT, cnt = min((uint32_t)G2_UNIT, counts[p] - first);
-            const uint32_t bytes = ((cnt * 4u) + 15u) & ~15u;        // the list allocation is a multiple of 16 bytes long
-            mbar_expect_tx(&idbar[kk & 1], bytes);
-            bulk_load(idbuf + (kk & 1) * G2_UNIT, G.peer_list[p] + first, bytes, &idbar[kk & 1]);
-        };
-        // walk: find the next unit of this CTA after position (u, q)
-        uint32_t u = 0; int q = 1;
-        auto next_unit = [&](int& p_out, uint32_t& u_out) -> bool {
-            for (; u < max_units; u++, q = 1)
-                for (; q < G.nranks; q++)
-                {
-                    const int p = (G.rank + q) % G.nranks;
-                    if (u * G2_UNIT >= counts[p]) continue;
-                    const bool take = (unit_no++ % gridDim.x) == blockIdx.x;
-                    if (take) { p_out = p; u_out = u; q++; return true; }
-                }
-            return false;
-        };
+    uint32_t u = 0; int q = 1;
+    // the walk: the next unit of this CTA
+    auto next_unit = [&](int& p_out, uint32_t& u_out) -> bool {
+        for (; u < max_units; u++, q = 1)
+            for (; q < G.nranks; q++)
+            {
+                const int p = (G.rank + q) % G.nranks;
+                if (u * G4_UNIT >= counts[p]) continue;
+                const bool take = (unit_no++ % gridDim.x) == blockIdx.x;
+                if (take) { p_out = p; u_out = u; q++; return true; }
+            }
+        return false;
+    };
+    uint32_t k = 0;                                                  // this CTA's units so far (coarse buffer = k % G4_COARSE_BUFS)
+    if (warp == G4_CONSUMERS)
+    {   // ---- producer
         unsigned long long sent = 0;
-        bool off_fail = false;
+        uint32_t fine_n = 0;                                         // fine copies of this CTA so far
+        bool fail = false;
+        auto fetch_coarse = [&](int p, uint32_t uu, uint32_t kk) {   // lane 0: the coarse blocks of unit (p, uu) into buffer kk % G4_COARSE_BUFS
+            const uint32_t buf = kk % G4_COARSE_BUFS, use = kk / G4_COARSE_BUFS;
+            if (use && !mbar_wait_bounded(&coarse_free[buf], (use - 1u) & 1u, dev_state)) { fail = true; return; }
+            const uint32_t first = uu * G4_UNIT, cnt = min((uint32_t)G4_UNIT, counts[p] - first);
+            mbar_expect_tx(&coarse_full[buf], cnt * 256u);
+            bulk_load(coarse + (size_t)buf * G4_UNIT * 64, G.peer_export[p] + (size_t)G.export_cap * 896 + (size_t)first * 64, cnt * 256u, &coarse_full[buf]);
+            sent += cnt * 256u;
+        };
         int p_cur = 0, p_nxt = 0; uint32_t u_cur = 0, u_nxt = 0;
         bool have = next_unit(p_cur, u_cur);
-        if (have) fetch_ids(p_cur, u_cur, 0);
+        if (have && lane == 0) fetch_coarse(p_cur, u_cur, 0);
         while (have)
         {
             const bool have_nxt = next_unit(p_nxt, u_nxt);
-            if (have_nxt) fetch_ids(p_nxt, u_nxt, k + 1);            // the buffer of unit k - 1: its indices were all consumed (by this thread) already
-            {   // every lane waits for the indices itself (the wait is what makes the bulk copy's bytes visible to the waiting thread)
-                const bool ok = mbar_wait_bounded(&idbar[k & 1], (k >> 1) & 1u, dev_state);
+            if (have_nxt && lane == 0) fetch_coarse(p_nxt, u_nxt, k + 1);
+            const uint32_t buf = k % G4_COARSE_BUFS, use = k / G4_COARSE_BUFS;
+            {   // every lane waits for the coarse blocks itself (the wait is what makes the bulk copy's bytes visible to the waiting thread)
+                const bool ok = !fail && mbar_wait_bounded(&coarse_full[buf], use & 1u, dev_state);
                 if (!__all_sync(0xffffffffu, ok)) return;
             }
-            const uint32_t* ids = idbuf + (k & 1) * G2_UNIT;
-            const uint32_t first = u_cur * G2_UNIT, cnt = min((uint32_t)G2_UNIT, counts[p_cur] - first);
-            for (uint32_t j0 = 0; j0 < cnt; j0 += 32)
-            {
-                uint32_t my_off = 3584u, my_info = 0u;
-                if (j0 + lane < cnt)
-                {   // the two bits the consumers need about the brick, looked up here for 32 records in one round of loads
-                    const uint32_t b = ids[j0 + lane] & 0x7fffffffu;
-                    const bool l1 = level0 || ((__ldg(need1 + (b >> 5)) >> (b & 31u)) & 1u);
-                    const bool nz = (l1_nonzero[b >> 5] >> (b & 31u)) & 1u;
-                    my_off = level0 ? 0u : (l1 ? 2048u : 3584u);
-                    my_info = (l1 ? 1u : 0u) | (nz ? 2u : 0u);
-                }
-                const uint32_t batch = min(32u, cnt - j0);
-                for (uint32_t i = 0; i < batch; i++)
+            const uint32_t* cb = coarse + (size_t)buf * G4_UNIT * 64;
+            const uint32_t first = u_cur * G4_UNIT, cnt = min((uint32_t)G4_UNIT, counts[p_cur] - first);
+            bool my_l1[G4_UNIT / 32]; uint32_t my_n[G4_UNIT / 32];
+#pragma unroll
+            for (int bi = 0; bi < G4_UNIT / 32; bi++)
+            {   // the two bits the consumers need about each brick, looked up for 32 bricks in one round of loads
+                const uint32_t j = bi * 32 + lane;
+                bool l1 = false, nz = false;
+                if (j < cnt)
                 {
-                    const uint32_t off = __shfl_sync(0xffffffffu, my_off, (int)i), info = __shfl_sync(0xffffffffu, my_info, (int)i);
-                    if (lane == 0)
+                    const uint32_t b = cb[j * 64 + 54] & 0x7fffffffu;
+                    l1 = level0 || ((__ldg(need1 + (b >> 5)) >> (b & 31u)) & 1u);
+                    nz = (l1_nonzero[b >> 5] >> (b & 31u)) & 1u;
+                }
+                const uint32_t ball = __ballot_sync(0xffffffffu, l1);
+                my_l1[bi] = l1;
+                my_n[bi] = fine_n + __popc(ball & ((1u << lane) - 1u));
+                fine_n += __popc(ball);
+                if (j < cnt) info[buf * G4_UNIT + j] = (l1 ? 1u : 0u) | (nz ? 2u : 0u) | (my_n[bi] << 2);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&info_ready[buf]);            // (before the copies: a ring slot this unit waits for may hold a record of this unit)
+#pragma unroll
+            for (int bi = 0; bi < G4_UNIT / 32; bi++)
+            {
+                const uint32_t base_n = __shfl_sync(0xffffffffu, my_n[bi], 0);
+                for (uint32_t round = 0; round < 32 / G4_SLOTS; round++)
+                {   // G4_SLOTS lanes at a time: their slots are distinct, and every slot's previous record was issued in an earlier round
+                    if (my_l1[bi] && (my_n[bi] - base_n) / G4_SLOTS == round)
                     {
-                        const int slot = (int)(n % G2_SLOTS);
-                        if (!mbar_wait_bounded(&empty[slot], ((n / G2_SLOTS) & 1u) ^ 1u, dev_state)) off_fail = true;
+                        const uint32_t n = my_n[bi], slot = n % G4_SLOTS;
+                        if (!mbar_wait_bounded(&empty[slot], ((n / G4_SLOTS) & 1u) ^ 1u, dev_state)) fail = true;
                         else
                         {
-                            slot_info[slot] = info;                      // published by the arrive below, read behind the wait on `full`
-                            const uint8_t* rec = reinterpret_cast<const uint8_t*>(G.peer_export[p_cur]) + (size_t)(first + j0 + i) * 4096;
-                            uint8_t* dst = ring + (size_t)slot * G2_SLOT_BYTES;
-                            const uint32_t bytes = G2_REC0_BYTES - off;
+                            const size_t i = (size_t)first + bi * 32 + lane;
+                            uint8_t* dst = ring + (size_t)slot * G4_SLOT_BYTES;
+                            const uint32_t bytes = level0 ? 3584u : 1536u;
                             mbar_expect_tx(&full[slot], bytes);
-                            bulk_load(dst + off, rec + off, bytes, &full[slot]);
-                            sent += bytes + 4u;
+                            if (level0) bulk_load(dst, G.peer_export[p_cur] + i * 512, 2048u, &full[slot]);
+                            bulk_load(dst + 2048, G.peer_export[p_cur] + (size_t)G.export_cap * 512 + i * 384, 1536u, &full[slot]);
+                            sent += bytes;
                         }
                     }
-                    n++;
+                    if (__any_sync(0xffffffffu, fail)) return;
                 }
-                if (__any_sync(0xffffffffu, off_fail)) return;
             }
-            // the id buffer k & 1 may be refilled two units later: nothing to release, this thread is its only reader
-            __syncwarp();                                                // every lane has read this unit's indices ...
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // ... before a bulk copy may overwrite them (unit k + 2)
             have = have_nxt; p_cur = p_nxt; u_cur = u_nxt; k++;
         }
+        for (int o = 16; o; o >>= 1) sent += __shfl_xor_sync(0xffffffffu, sent, o);
         if (lane == 0 && sent) atomicAdd(G.gather_bytes, sent);
         return;
     }
-    // ---- consumers: warp w takes the records with n % G2_CONSUMERS == w
-    for (uint32_t u = 0; u < max_units; u++)
-        for (int q = 1; q < G.nranks; q++)
+    // ---- consumers: a brick with a fine copy goes to the warp that owns the copy's slot, any other to warp j % G4_CONSUMERS
+    int p_cur = 0; uint32_t u_cur = 0;
+    while (next_unit(p_cur, u_cur))
+    {
+        const uint32_t buf = k % G4_COARSE_BUFS, use = k / G4_COARSE_BUFS;
+        const uint32_t cnt = min((uint32_t)G4_UNIT, counts[p_cur] - u_cur * G4_UNIT);
+        if (!mbar_wait_bounded(&info_ready[buf], use & 1u, dev_state)) return;
+        if (!mbar_wait_bounded(&coarse_full[buf], use & 1u, dev_state)) return;
+        for (uint32_t j = 0; j < cnt; j++)
         {
-            const int p = (G.rank + q) % G.nranks;
-            if (u * G2_UNIT >= counts[p]) continue;
-            if ((unit_no++ % gridDim.x) != blockIdx.x) continue;
-            const uint32_t cnt = min((uint32_t)G2_UNIT, counts[p] - u * G2_UNIT);
-            for (uint32_t j = 0; j < cnt; j++)
+            const uint32_t inf = info[buf * G4_UNIT + j];
+            const bool l1 = (inf & 1u) != 0, was_nonzero = (inf & 2u) != 0;
+            const uint32_t fn = inf >> 2;
+            if ((int)((l1 ? fn : j) % G4_CONSUMERS) != warp) continue;
+            const uint32_t* rec = coarse + ((size_t)buf * G4_UNIT + j) * 64;
+            const uint32_t b = rec[54] & 0x7fffffffu;
+            const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
+            const uint32_t word = b >> 5, bit = 1u << (b & 31u);
+            const uint32_t slot = fn % G4_SLOTS;
+            const uint4* fine4 = reinterpret_cast<const uint4*>(ring + (size_t)slot * G4_SLOT_BYTES);
+            if (l1 && !mbar_wait_bounded(&full[slot], (fn / G4_SLOTS) & 1u, dev_state)) return;
+            if (level0)
             {
-                const uint32_t mine = n++;
-                if ((int)(mine % G2_CONSUMERS) != warp) continue;
-                const int slot = (int)(mine % G2_SLOTS);
-                if (!mbar_wait_bounded(&full[slot], (mine / G2_SLOTS) & 1u, dev_state)) return;
-                const uint32_t* rec = reinterpret_cast<const uint32_t*>(ring + (size_t)slot * G2_SLOT_BYTES);
-                const uint4* rec4 = reinterpret_cast<const uint4*>(rec);
-                const uint32_t b = rec[950] & 0x7fffffffu;
-                const int bx = b % NB, by = (b / NB) % NB, bz = b / (NB * NB);
-                const uint32_t word = b >> 5, bit = 1u << (b & 31u);
-                const uint32_t info = slot_info[slot];
-                const bool l1 = (info & 1u) != 0, was_nonzero = (info & 2u) != 0;
-                if (level0)
-                {
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                    {
-                        const int qq = lane + 32 * k, row = qq >> 1, half = qq & 1, y = row & 7, z = row >> 3;
-                        const uint4 v = rec4[qq];
-                        surf3Dwrite(v, G.rad_surf, (bx * 8 + half * 4) * 4, by * 8 + y, bz * 8 + z);
-                        if (G.write_linear) *reinterpret_cast<uint4*>(G.rad_lin + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4) = v;
-                    }
+                for (int kk = 0; kk < 4; kk++)
+                {
+                    const int qq = lane + 32 * kk, row = qq >> 1, half = qq & 1, y = row & 7, z = row >> 3;
+                    const uint4 v = fine4[qq];
+                    surf3Dwrite(v, G.rad_surf, (bx * 8 + half * 4) * 4, by * 8 + y, bz * 8 + z);
+                    if (G.write_linear) *reinterpret_cast<uint4*>(G.rad_lin + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4) = v;
                 }
-                if (l1 || was_nonzero)
-                {   // the brick's level 1, or zeros over a copy of it that no cone of this rank needs any more
+            }
+            if (l1 || was_nonzero)
+            {   // the brick's level 1, or zeros over a copy of it that no cone of this rank needs any more
 #pragma unroll
-                    for (int k = 0; k < 3; k++)
-                    {
-                        const int jj = lane + 32 * k, d = jj >> 4, r = jj & 15, oy = r & 3, oz = r >> 2;
-                        const int gx = bx * 4, gy = by * 4 + oy, gz = bz * 4 + oz;
-                        const uint4 v = l1 ? rec4[128 + jj] : make_uint4(0, 0, 0, 0);
-                        surf3Dwrite(v, G.surf[0], gx * 4, gy, atlas_z(d, n1, gz));
-                        if (G.write_linear) *reinterpret_cast<uint4*>(G.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = v;
-                    }
-                    if (lane == 0 && l1 != was_nonzero)
-                    {
-                        if (l1) atomicOr(l1_nonzero + word, bit); else atomicAnd(l1_nonzero + word, ~bit);
-                    }
-                }
-                if (lane < 24)
+                for (int kk = 0; kk < 3; kk++)
                 {
-                    const int d = lane >> 2, r = lane & 3, oy = r & 1, oz = r >> 1;
-                    const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
-                    const uint2 v = reinterpret_cast<const uint2*>(rec + 896)[lane];
-                    surf3Dwrite(v, G.surf[1], gx * 4, gy, atlas_z(d, n2, gz));
-                    if (G.write_linear) *reinterpret_cast<uint2*>(G.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = v;
+                    const int jj = lane + 32 * kk, d = jj >> 4, r = jj & 15, oy = r & 3, oz = r >> 2;
+                    const int gx = bx * 4, gy = by * 4 + oy, gz = bz * 4 + oz;
+                    const uint4 v = l1 ? fine4[128 + jj] : make_uint4(0, 0, 0, 0);
+                    surf3Dwrite(v, G.surf[0], gx * 4, gy, atlas_z(d, n1, gz));
+                    if (G.write_linear) *reinterpret_cast<uint4*>(G.lin[0][d] + ((size_t)gz * n1 + gy) * n1 + gx) = v;
                 }
-                if (lane < 6)
+                if (lane == 0 && l1 != was_nonzero)
                 {
-                    const uint32_t v = rec[944 + lane];
-                    surf3Dwrite(v, G.surf[2], bx * 4, by, atlas_z(lane, n3, bz));
-                    G.lin[2][lane][((size_t)bz * n3 + by) * n3 + bx] = v;             // level 3 is the source of the local tail: always
+                    if (l1) atomicOr(l1_nonzero + word, bit); else atomicAnd(l1_nonzero + word, ~bit);
                 }
-                __syncwarp();                                            // the whole warp has read the slot
+            }
+            if (lane < 24)
+            {
+                const int d = lane >> 2, r = lane & 3, oy = r & 1, oz = r >> 1;
+                const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
+                const uint2 v = reinterpret_cast<const uint2*>(rec)[lane];
+                surf3Dwrite(v, G.surf[1], gx * 4, gy, atlas_z(d, n2, gz));
+                if (G.write_linear) *reinterpret_cast<uint2*>(G.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = v;
+            }
+            if (lane < 6)
+            {
+                const uint32_t v = rec[48 + lane];
+                surf3Dwrite(v, G.surf[2], bx * 4, by, atlas_z(lane, n3, bz));
+                G.lin[2][lane][((size_t)bz * n3 + by) * n3 + bx] = v;             // level 3 is the source of the local tail: always
+            }
+            if (l1)
+            {
+                __syncwarp();                                        // the whole warp has read the slot
                 if (lane == 0) mbar_arrive(&empty[slot]);
             }
         }
+        __syncwarp();                                                // the whole warp has read the unit's coarse blocks and info words
+        if (lane == 0) mbar_arrive(&coarse_free[buf]);
+        k++;
+    }
 }
 
 }  // namespace
@@ -669,7 +608,7 @@ int f184_gather_init_n(f184_ctx* c)
     static bool attr = false;
     if (!attr)
     {
-        CK(c, cudaFuncSetAttribute(k_gather_bricks_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SLOTS * G2_SLOT_BYTES + 2 * G2_UNIT * 4));
+        CK(c, cudaFuncSetAttribute(k_gather_bricks_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_BYTES));
         attr = true;
     }
     if (c->need1) return F184_OK;
@@ -698,12 +637,12 @@ int f184_gather_n(f184_ctx* c, const f184_trace_constants* view)
     GatherArgs G{};
     for (uint32_t p = 0; p < c->cfg.nranks; p++)
     {
-        void *e = nullptr, *k = nullptr, *l = nullptr;
-        if ((rc = peer_ptr(c, p, F184_IPC_EXPORT, &e)) || (rc = peer_ptr(c, p, F184_IPC_COUNTERS, &k)) || (rc = peer_ptr(c, p, F184_IPC_BRICK_LIST, &l))) return rc;
+        void *e = nullptr, *k = nullptr;
+        if ((rc = peer_ptr(c, p, F184_IPC_EXPORT, &e)) || (rc = peer_ptr(c, p, F184_IPC_COUNTERS, &k))) return rc;
         G.peer_export[p] = reinterpret_cast<const uint32_t*>(e);
         G.peer_counters[p] = reinterpret_cast<const unsigned long long*>(k);
-        G.peer_list[p] = reinterpret_cast<const uint32_t*>(l);
     }
+    G.export_cap = ((uint32_t)(c->cfg.grid_n / 8) * (c->cfg.grid_n / 8) * (c->cfg.grid_n / 8)) / c->cfg.nranks;
     G.rank = (int)c->cfg.rank; G.nranks = (int)c->cfg.nranks; G.N = (int)c->cfg.grid_n;
     G.write_linear = (c->cfg.flags & F184_FLAG_GATHER_LINEAR) ? 1 : 0;
     G.dev_state = c->dev_state;
@@ -770,17 +709,13 @@ int f184_gather_n(f184_ctx* c, const f184_trace_constants* view)
     }
     if ((rc = f184_stage_end(c, F184_STAGE_NEED))) return rc;
     if ((rc = f184_stage_begin(c, F184_STAGE_EXCHANGE))) return rc;
-    static const bool gather_ldg = [] { const char* e = getenv("F184_GATHER_LDG"); return e && atoi(e) != 0; }();
     if ((rc = f184_zero_counters(c, 1u << F184_COUNTER_GATHER_BYTES))) return rc;
-    if (gather_ldg) k_gather_bricks<<<dim3(c->cfg.nranks, 148), GATHER_WARPS * 32, 0, c->stream>>>(G);
-    else
     {
         static const int gather_ctas = [] { const char* e = getenv("F184_GATHER_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 148 * 2; }();     // (tests: few CTAs = many units each)
-        k_gather_bricks_tma<<<gather_ctas, (G2_CONSUMERS + 1) * 32, G2_SLOTS * G2_SLOT_BYTES + 2 * G2_UNIT * 4, c->stream>>>(G, c->dev_state, c->need1, c->l1_nonzero[set]);
+        k_gather_bricks_tma<<<gather_ctas, (G4_CONSUMERS + 1) * 32, G4_SMEM_BYTES, c->stream>>>(G, c->dev_state, c->need1, c->l1_nonzero[set]);
     }
     CK_LAUNCH(c);
-    // bytes per record that cross NVLink: the bulk copies of the TMA-fed kernel, or list entry + the record parts the per-lane loads read
-    k_gather_state<<<1, 1, 0, c->stream>>>(G, c->dev_state, set, c->counters_dev, gather_ldg ? 4 + 2048 + 4 * (384 + 48 + 6) : 0, gather_ldg ? 4 + 4 * (384 + 48 + 6) : 0);
+    k_gather_state<<<1, 1, 0, c->stream>>>(c->dev_state, set);
     CK_LAUNCH(c);
     rc = f184_stage_end(c, F184_STAGE_EXCHANGE);
     if (rc) return rc;
