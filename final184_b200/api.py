@@ -192,6 +192,7 @@ _PRODUCT_ONLY = {
     "peer_barrier": (C.c_int, [C.c_void_p]),
     "gather_volume": (C.c_int, [C.c_void_p]),
     "gather_volume_view": (C.c_int, [C.c_void_p, C.POINTER(TraceConstantsC)]),
+    "microbench_peer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_double)]),
     "stage_time_reset": (C.c_int, [C.c_void_p, C.c_uint32]),
     "stage_time_total": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "microbench": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_double)]),
@@ -453,6 +454,12 @@ class VoxelGI:
         """0: trilinear RGBA8 3D fetches / s; 1: scattered 16-byte vector reductions / s."""
         v = C.c_double()
         self._ck(self.lib.microbench(self.h, which, C.byref(v)), "microbench")
+        return v.value
+
+    def microbench_peer(self, peer, mode, copy_bytes, depth, ctas, total_bytes) -> float:
+        """GB/s of reading rank `peer`'s export buffer over NVLink (mode 0/1: bulk copies from 1/32 lanes per CTA, 2: per-lane loads)"""
+        v = C.c_double()
+        self._ck(self.lib.microbench_peer(self.h, peer, mode, copy_bytes, depth, ctas, total_bytes, C.byref(v)), "microbench_peer")
         return v.value
 
     def counter(self, which) -> int:

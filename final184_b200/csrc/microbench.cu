@@ -48,6 +48,65 @@ __global__ void __launch_bounds__(256) k_red_rate(float4* __restrict__ buf, uint
     }
 }
 
+
+// ---- peer reads over NVLink: what shape of read does the gather (mode_n_shard.cu) want? -------------------------------------------
+__device__ __forceinline__ uint32_t mb_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mb_smem(bar)), "r"(parity) : "memory");
+}
+
+// one warp per CTA; `issuers` lanes (1 or 32) issue bulk copies of `copy_bytes` into a ring of `depth` slots and recycle a slot as soon
+// as its copy has landed (nobody reads the data: this is the transfer alone)
+__global__ void __launch_bounds__(32) k_peer_bulk(const uint8_t* __restrict__ src, uint32_t n_copies, uint32_t copy_bytes, uint32_t depth, uint32_t issuers)
+{
+    extern __shared__ __align__(128) uint8_t mb_ring[];
+    __shared__ __align__(8) uint64_t bar[512];
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t s_ = lane; s_ < depth; s_ += 32) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb_smem(&bar[s_])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    if (lane >= issuers) return;
+    uint32_t k = lane;
+    for (;; k += issuers)
+    {
+        const uint32_t i = blockIdx.x + k * gridDim.x;
+        if (i >= n_copies) break;
+        const uint32_t slot = k % depth, use = k / depth;
+        if (use) mb_wait(&bar[slot], (use - 1u) & 1u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb_smem(&bar[slot])), "r"(copy_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(mb_smem(mb_ring + (size_t)slot * copy_bytes)), "l"(src + (size_t)i * copy_bytes), "r"(copy_bytes), "r"(mb_smem(&bar[slot])) : "memory");
+    }
+    // drain: the last use of every slot this lane owns
+    for (uint32_t slot = lane; slot < depth; slot += issuers)
+    {
+        // uses of this slot = number of k' < k_end with k' % depth == slot and k' % issuers == lane (depth % issuers == 0: all of the slot's uses are this lane's)
+        const uint32_t per_cta = (n_copies > blockIdx.x) ? (n_copies - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+        if (slot >= per_cta) continue;
+        const uint32_t uses = (per_cta - slot + depth - 1) / depth;
+        mb_wait(&bar[slot], (uses - 1u) & 1u);
+    }
+}
+
+// per-lane 16-byte loads, `U` in flight per thread
+__global__ void __launch_bounds__(256) k_peer_ldg(const uint4* __restrict__ src, size_t n_vec, uint4* __restrict__ sink)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (size_t i = tid; i + 7 * stride < n_vec; i += 8 * stride)
+    {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = __ldg(src + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 8; u++) { acc.x ^= v[u].x; acc.y ^= v[u].y; acc.z ^= v[u].z; acc.w ^= v[u].w; }
+    }
+    if (acc.x == 0x12345678u && acc.y == 0x9abcdef0u) sink[tid & 255] = acc;      // (keeps the loads alive)
+}
+
 }  // namespace
 
 extern "C" int f184_microbench(f184_ctx* c, uint32_t which, double* out_per_second)
@@ -110,5 +169,52 @@ extern "C" int f184_microbench(f184_ctx* c, uint32_t which, double* out_per_seco
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *out_per_second = ops / ((double)best * 1e-3);
+    return F184_OK;
+}
+
+// Peer-read shapes over NVLink (measurement aid; the context must have rank `peer`'s export buffer imported): mode 0 = bulk copies
+// issued by one lane per CTA, 1 = by 32 lanes per CTA, 2 = per-lane 16-byte loads (256-thread CTAs, 8 loads in flight per thread).
+// Reads `total_bytes` (<= the export buffer's size) once; reports GB/s of the best of three runs.
+extern "C" int f184_microbench_peer(f184_ctx* c, uint32_t peer, uint32_t mode, uint32_t copy_bytes, uint32_t depth, uint32_t ctas, uint64_t total_bytes, double* out_gbs)
+{
+    if (!c || !out_gbs || mode > 2 || peer >= c->cfg.nranks || !ctas) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "microbench_peer: bad argument");
+    if (mode < 2 && (copy_bytes % 16 || !copy_bytes || !depth || depth > 512 || depth % (mode == 0 ? 1u : 32u) || (uint64_t)depth * copy_bytes > 200 * 1024))
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "microbench_peer: copy size / ring depth");
+    CK(c, cudaSetDevice(c->cfg.device));
+    const void* src = peer == c->cfg.rank ? (const void*)c->export_buf : (const void*)c->peer[peer].buf[F184_IPC_EXPORT];
+    if (!src) return f184_fail(c, F184_ERR_NOT_READY, "microbench_peer: export buffer of rank %u not imported", peer);
+    const uint64_t N = c->cfg.grid_n, cap_bytes = 4096ull * ((N / 8) * (N / 8) * (N / 8) / (c->cfg.nranks ? c->cfg.nranks : 1));
+    if (total_bytes > cap_bytes) total_bytes = cap_bytes;
+    cudaEvent_t e0, e1;
+    CK(c, cudaEventCreate(&e0));
+    CK(c, cudaEventCreate(&e1));
+    uint4* sink = nullptr;
+    CK(c, cudaMalloc(&sink, 256 * sizeof(uint4)));
+    if (mode < 2) CK(c, cudaFuncSetAttribute(k_peer_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    float best = 1e30f;
+    double moved = 0;
+    for (int rep = 0; rep < 4; rep++)
+    {
+        CK(c, cudaEventRecord(e0, c->stream));
+        if (mode < 2)
+        {
+            const uint32_t n_copies = (uint32_t)(total_bytes / copy_bytes);
+            moved = (double)n_copies * copy_bytes;
+            k_peer_bulk<<<ctas, 32, (size_t)depth * copy_bytes, c->stream>>>(reinterpret_cast<const uint8_t*>(src), n_copies, copy_bytes, depth, mode == 0 ? 1u : 32u);
+        }
+        else
+        {
+            const size_t n_vec = total_bytes / 16;
+            moved = (double)(n_vec / ((size_t)ctas * 256 * 8) * ((size_t)ctas * 256 * 8)) * 16.0;
+            k_peer_ldg<<<ctas, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(src), n_vec, sink);
+        }
+        CK_LAUNCH(c);
+        CK(c, cudaEventRecord(e1, c->stream));
+        CK(c, cudaEventSynchronize(e1));
+        float ms; CK(c, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep && ms < best) best = ms;
+    }
+    cudaFree(sink); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *out_gbs = moved / ((double)best * 1e-3) * 1e-9;
     return F184_OK;
 }

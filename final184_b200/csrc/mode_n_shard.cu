@@ -94,15 +94,22 @@ struct NeedArgs
     uint32_t* need1;                   // bit per brick: level 1 of the brick is sampled by a cone of this rank's rows
 };
 
-__device__ __forceinline__ void mark_brick(uint32_t* need1, int bx, int by, int bz, int NB)
+// A pixel's seven cones take their few fine samples inside the same one to three bricks, and so do its neighbours: the thread remembers
+// the last two bricks it marked, and of the lanes that arrive together with the same brick one sends the (fire-and-forget) reduction.
+// (Testing the bit first — a load, a branch, then the atomic — made every sample wait for an L2 round trip: 0.14 ms per frame.)
+struct MarkCache { uint32_t last0 = 0xffffffffu, last1 = 0xffffffffu; };
+__device__ __forceinline__ void mark_brick(uint32_t* need1, int bx, int by, int bz, int NB, MarkCache& mc)
 {
     if ((unsigned)bx >= (unsigned)NB || (unsigned)by >= (unsigned)NB || (unsigned)bz >= (unsigned)NB) return;
-    const uint32_t b = ((uint32_t)bz * NB + by) * NB + bx, bit = 1u << (b & 31u);
-    if (!(need1[b >> 5] & bit)) atomicOr(need1 + (b >> 5), bit);
+    const uint32_t b = ((uint32_t)bz * NB + by) * NB + bx;
+    if (b == mc.last0 || b == mc.last1) return;
+    mc.last1 = mc.last0; mc.last0 = b;
+    const uint32_t same = __match_any_sync(__activemask(), b);
+    if ((uint32_t)(__ffs(same) - 1) == (threadIdx.x & 31u)) atomicOr(need1 + (b >> 5), 1u << (b & 31u));
 }
 
 // one cone: every sample it takes while its level is <= 1; returns whether it touches level 0
-__device__ bool mark_cone(const NeedArgs& A, f3 origin, f3 dir, float tan_half)
+__device__ bool mark_cone(const NeedArgs& A, f3 origin, f3 dir, float tan_half, MarkCache& mc)
 {
     const float h = A.h, inv_h = 1.0f / h;
     const f3 dv = {(A.w2v.m[0] * dir.x + A.w2v.m[4] * dir.y + A.w2v.m[8] * dir.z) * 0.5f,
@@ -130,7 +137,7 @@ __device__ bool mark_cone(const NeedArgs& A, f3 origin, f3 dir, float tan_half)
         const int z0 = (int)floorf(pz - e) >> 2, z1 = ((int)floorf(pz + e) + 1) >> 2;
         for (int bz = z0; bz <= z1; bz++)
             for (int by = y0; by <= y1; by++)
-                for (int bx = x0; bx <= x1; bx++) mark_brick(A.need1, bx, by, bz, NB);
+                for (int bx = x0; bx <= x1; bx++) mark_brick(A.need1, bx, by, bz, NB, mc);
         t += A.spec_b ? 0.5f * diam : diam;
     }
     return level0;
@@ -174,18 +181,19 @@ __global__ void __launch_bounds__(128) k_need_bricks(const NeedArgs A)
             const f3 ty = normalize3(cross3(hh, z));
             const f3 tx = normalize3(cross3(z, ty));
             const f3 origin = {wpos.x + z.x * A.h, wpos.y + z.y * A.h, wpos.z + z.z * A.h};
+            MarkCache mc;
 #pragma unroll 1
             for (int i = 0; i < 6; i++)
             {
                 const float d0 = kNeedDiffuseDirs[i][0], d1 = kNeedDiffuseDirs[i][1], d2 = kNeedDiffuseDirs[i][2];
                 const f3 dir = {(tx.x * d0 + ty.x * d1) + z.x * d2, (tx.y * d0 + ty.y * d1) + z.y * d2, (tx.z * d0 + ty.z * d1) + z.z * d2};
-                level0 |= mark_cone(A, origin, dir, kTanHalfDiffuse);
+                level0 |= mark_cone(A, origin, dir, kTanHalfDiffuse, mc);
             }
             const float rough = (float)__ldg(A.material + (size_t)y * A.W + x).y / 255.0f;
             const f3 I = normalize3(wpos - A.cam);
             const float ndi = dot3(z, I);
             const f3 R = {I.x - 2.0f * ndi * z.x, I.y - 2.0f * ndi * z.y, I.z - 2.0f * ndi * z.z};
-            if (dot3(R, z) > -1e-3f) level0 |= mark_cone(A, origin, R, cone_specular_tan(rough));
+            if (dot3(R, z) > -1e-3f) level0 |= mark_cone(A, origin, R, cone_specular_tan(rough), mc);
         }
     }
     if (__syncthreads_or(level0) && threadIdx.x == 0) A.dev_state[F184_DEV_NEED_L0] = 1u;
@@ -223,6 +231,7 @@ struct GatherArgs
     unsigned long long* gather_bytes;  // F184_COUNTER_GATHER_BYTES: what the bulk copies move over NVLink (summed by the producers)
     uint32_t export_cap;               // bricks per export array
     int rank, nranks, N, write_linear;
+    int dry;                           // measurement aid (F184_GATHER_DRY): 1 = skip the level 2/3 stores, 2 = skip the level 0/1 stores
     cudaSurfaceObject_t rad_surf;
     uint32_t* rad_lin;
     uint32_t* lin[3][6];
@@ -290,7 +299,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 
 // Work = units of G4_UNIT consecutive bricks of one peer's list, walked in the same order by both roles: u = 0, 1, ...; for each u the
 // peers in an order rotated by the reader's rank (so the box's readers do not all start on the same peer); CTA c takes every
-// gridDim.x-th unit.  Per unit the producer fetches the coarse blocks, looks every brick up in the need mask (k_need_bricks) and in
+// gridDim.x-th unit number.  Per unit the producer fetches the coarse blocks, looks every brick up in the need mask (k_need_bricks) and in
 // this rank's "my copy of its level 1 is not zero" bits, publishes per brick
 //     info = level 1 travels | (my copy is non-zero) << 1 | (sequence number among this CTA's fine copies) << 2
 // and issues the fine copies.  The consumers write what arrived; a brick whose level 1 did not travel gets zeros there IF this
@@ -317,18 +326,20 @@ __global__ void __launch_bounds__((G4_CONSUMERS + 1) * 32) k_gather_bricks_tma(c
     uint32_t max_units = 0;
     for (int p = 0; p < G.nranks; p++) max_units = max(max_units, (counts[p] + G4_UNIT - 1) / G4_UNIT);
     const int N = G.N, NB = N >> 3, n1 = N >> 1, n2 = N >> 2, n3 = N >> 3;
-    uint32_t unit_no = 0;                                            // valid units seen so far (all CTAs count alike)
-    uint32_t u = 0; int q = 1;
-    // the walk: the next unit of this CTA
+    // the walk: unit number g = u * (nranks - 1) + (q - 1) names unit u of the q-th peer after this rank; CTA c takes g = c, c + gridDim.x, ...
+    // and skips the numbers past the end of a peer's list.  (Cost per CTA ~ its own units.  Walking ALL units in every warp and counting
+    // the valid ones — two runtime divisions each — was 0.3-0.6 ms of serial latency at 1024^3: most of what the exchange took.)
+    uint32_t g_next = blockIdx.x;
+    const uint32_t g_end = max_units * (uint32_t)(G.nranks - 1);
     auto next_unit = [&](int& p_out, uint32_t& u_out) -> bool {
-        for (; u < max_units; u++, q = 1)
-            for (; q < G.nranks; q++)
-            {
-                const int p = (G.rank + q) % G.nranks;
-                if (u * G4_UNIT >= counts[p]) continue;
-                const bool take = (unit_no++ % gridDim.x) == blockIdx.x;
-                if (take) { p_out = p; u_out = u; q++; return true; }
-            }
+        for (; g_next < g_end; g_next += gridDim.x)
+        {
+            const uint32_t uu = g_next / (uint32_t)(G.nranks - 1), qq = 1u + g_next % (uint32_t)(G.nranks - 1);
+            const int p = (int)((G.rank + qq) % (uint32_t)G.nranks);
+            if (uu * G4_UNIT >= counts[p]) continue;
+            p_out = p; u_out = uu; g_next += gridDim.x;
+            return true;
+        }
         return false;
     };
     uint32_t k = 0;                                                  // this CTA's units so far (coarse buffer = k % G4_COARSE_BUFS)
@@ -430,7 +441,7 @@ __global__ void __launch_bounds__((G4_CONSUMERS + 1) * 32) k_gather_bricks_tma(c
             const uint32_t slot = fn % G4_SLOTS;
             const uint4* fine4 = reinterpret_cast<const uint4*>(ring + (size_t)slot * G4_SLOT_BYTES);
             if (l1 && !mbar_wait_bounded(&full[slot], (fn / G4_SLOTS) & 1u, dev_state)) return;
-            if (level0)
+            if (level0 && !(G.dry & 2))
             {
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++)
@@ -441,7 +452,7 @@ __global__ void __launch_bounds__((G4_CONSUMERS + 1) * 32) k_gather_bricks_tma(c
                     if (G.write_linear) *reinterpret_cast<uint4*>(G.rad_lin + ((size_t)(bz * 8 + z) * N + (by * 8 + y)) * N + bx * 8 + half * 4) = v;
                 }
             }
-            if (l1 || was_nonzero)
+            if ((l1 || was_nonzero) && !(G.dry & 2))
             {   // the brick's level 1, or zeros over a copy of it that no cone of this rank needs any more
 #pragma unroll
                 for (int kk = 0; kk < 3; kk++)
@@ -457,7 +468,7 @@ __global__ void __launch_bounds__((G4_CONSUMERS + 1) * 32) k_gather_bricks_tma(c
                     if (l1) atomicOr(l1_nonzero + word, bit); else atomicAnd(l1_nonzero + word, ~bit);
                 }
             }
-            if (lane < 24)
+            if (lane < 24 && !(G.dry & 1))
             {
                 const int d = lane >> 2, r = lane & 3, oy = r & 1, oz = r >> 1;
                 const int gx = bx * 2, gy = by * 2 + oy, gz = bz * 2 + oz;
@@ -465,7 +476,7 @@ __global__ void __launch_bounds__((G4_CONSUMERS + 1) * 32) k_gather_bricks_tma(c
                 surf3Dwrite(v, G.surf[1], gx * 4, gy, atlas_z(d, n2, gz));
                 if (G.write_linear) *reinterpret_cast<uint2*>(G.lin[1][d] + ((size_t)gz * n2 + gy) * n2 + gx) = v;
             }
-            if (lane < 6)
+            if (lane < 6 && !(G.dry & 1))
             {
                 const uint32_t v = rec[48 + lane];
                 surf3Dwrite(v, G.surf[2], bx * 4, by, atlas_z(lane, n3, bz));
@@ -645,6 +656,8 @@ int f184_gather_n(f184_ctx* c, const f184_trace_constants* view)
     G.export_cap = ((uint32_t)(c->cfg.grid_n / 8) * (c->cfg.grid_n / 8) * (c->cfg.grid_n / 8)) / c->cfg.nranks;
     G.rank = (int)c->cfg.rank; G.nranks = (int)c->cfg.nranks; G.N = (int)c->cfg.grid_n;
     G.write_linear = (c->cfg.flags & F184_FLAG_GATHER_LINEAR) ? 1 : 0;
+    static const int dry = [] { const char* e = getenv("F184_GATHER_DRY"); return e ? atoi(e) : 0; }();
+    G.dry = dry;
     G.dev_state = c->dev_state;
     G.gather_bytes = c->counters_dev + F184_COUNTER_GATHER_BYTES;
     G.rad_surf = vs.rad_surf;

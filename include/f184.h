@@ -406,6 +406,10 @@ int f184_debug_detmath(f184_ctx* ctx, uint32_t op, const float* x, const float* 
  * (bound of the cone tracer); which = 1: scattered 16-byte red.global.add.v4.f32 / s over 1 GiB (the voxelizer's
  * accumulation path).  Synchronous; allocates and frees its own scratch. */
 int f184_microbench(f184_ctx* ctx, uint32_t which, double* out_per_second);
+/* peer reads over NVLink from rank `peer`'s export buffer (imported with f184_ipc_import): mode 0 = bulk copies (cp.async.bulk) of
+ * `copy_bytes` issued by one lane per CTA into a ring of `depth` slots, 1 = issued by 32 lanes per CTA, 2 = per-lane 16-byte loads.
+ * The numbers behind the gather's design (DESIGN.md "Gather").  Synchronous. */
+int f184_microbench_peer(f184_ctx* ctx, uint32_t peer, uint32_t mode, uint32_t copy_bytes, uint32_t depth, uint32_t ctas, uint64_t total_bytes, double* out_gbs);
 
 /* ---- test hook: one level of the texture-side storage the cone tracer samples (dir < 0: the level-0 radiance 3D array, copied out;
  * dir 0..5: level `level`+1 of that direction, as the texture units return it at every texel centre — the tracer's own fetch path);
