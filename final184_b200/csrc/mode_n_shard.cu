@@ -76,9 +76,13 @@ __global__ void k_peer_barrier(const BarrierArgs B)
 //   * level 0 at all?  (dev_state[F184_DEV_NEED_L0]: some cone's first — finest — sample selects it.)  With 60-degree diffuse cones and
 //     rough materials none does, and level 0 (2 KB of every 4 KB record) stays home;
 //   * level 1 of WHICH bricks?  A cone reads level 1 only while its footprint is under ~3 voxels: the first sample of a diffuse
-//     cone, 2.3 voxels above the surface the pixel shows.  So level 1 is needed exactly around the surfaces this rank's pixels see —
-//     a fraction of the scene (the interiors of seven of C4's eight buildings are invisible from the camera) — and every sample a
-//     cone takes at level <= 1 marks the bricks under its trilinear footprint (1/16-texel margin) in a bit mask the gather consults.
+//     cone, 2.3 voxels above the surface the pixel shows.  So level 1 is needed only around the surfaces this rank's pixels see —
+//     a fraction of the scene (the interiors of seven of C4's eight buildings are invisible from the camera).  The mask may be a
+//     SUPERSET of what the cones read (a brick too many costs 1.5 KB of NVLink; a brick too few is a wrong image), so the six diffuse
+//     cones are not marched: their fine samples lie within (normal offset h) + (the diffuse cone's fine reach) of the pixel's world
+//     position, and every brick under that box — plus the trilinear footprint and a quarter texel of slack — is marked.  The
+//     specular cone is marched sample by sample, and only where its fine reach exceeds the diffuse one (glossy materials).
+//     (Marching all seven cones was ~2600 instructions per pixel: 0.3 ms per frame at 2 GPUs, 0.14 at 8 — a third of the trace itself.)
 // No early termination on opacity here (it would need the volume): the marching stops where the tracer's level selection passes 1.
 struct NeedArgs
 {
@@ -90,22 +94,56 @@ struct NeedArgs
     float h, max_dist;
     f3 cam;
     uint32_t spec_b, N, no_view;       // no_view: no camera given — only the level-0 question is answered (it needs the roughness alone)
+    float texel_per_world[3];          // level-1 texels per world unit along each volume axis (row norms of w2v)
     uint32_t* dev_state;
     uint32_t* need1;                   // bit per brick: level 1 of the brick is sampled by a cone of this rank's rows
 };
 
-// A pixel's seven cones take their few fine samples inside the same one to three bricks, and so do its neighbours: the thread remembers
-// the last two bricks it marked, and of the lanes that arrive together with the same brick one sends the (fire-and-forget) reduction.
-// (Testing the bit first — a load, a branch, then the atomic — made every sample wait for an L2 round trip: 0.14 ms per frame.)
-struct MarkCache { uint32_t last0 = 0xffffffffu, last1 = 0xffffffffu; };
+// A pixel's seven cones take their few fine samples inside the same one to three bricks, and so do its neighbours — and a word of
+// the mask is 32 bricks along x, half the width of a 512^3 volume: a wall along x sends every pixel that shows it to the same few
+// words.  Reductions on one address are serialised by the L2 slice that owns it (the kernel took 0.14-0.2 ms per frame, slower the
+// COARSER the volume).  So: the thread remembers the last two bricks it marked; new ones go into a small per-CTA hash set in shared
+// memory (16 x 8 pixels see a handful of bricks); at the end the CTA sends one reduction per brick of the set whose bit is not set yet.
+constexpr int MARK_SET = 256;
+struct MarkCache
+{
+    uint32_t last0 = 0xffffffffu, last1 = 0xffffffffu;
+    uint32_t* set;                        // shared memory, MARK_SET entries, 0xffffffff = free
+};
 __device__ __forceinline__ void mark_brick(uint32_t* need1, int bx, int by, int bz, int NB, MarkCache& mc)
 {
     if ((unsigned)bx >= (unsigned)NB || (unsigned)by >= (unsigned)NB || (unsigned)bz >= (unsigned)NB) return;
     const uint32_t b = ((uint32_t)bz * NB + by) * NB + bx;
     if (b == mc.last0 || b == mc.last1) return;
     mc.last1 = mc.last0; mc.last0 = b;
-    const uint32_t same = __match_any_sync(__activemask(), b);
-    if ((uint32_t)(__ffs(same) - 1) == (threadIdx.x & 31u)) atomicOr(need1 + (b >> 5), 1u << (b & 31u));
+    uint32_t hsh = (b * 2654435761u) >> 24;
+    for (int probe = 0; probe < 4; probe++, hsh = (hsh + 1u) & (MARK_SET - 1))
+    {
+        uint32_t cur = reinterpret_cast<volatile uint32_t*>(mc.set)[hsh];
+        if (cur == b) return;
+        if (cur == 0xffffffffu)
+        {
+            cur = atomicCAS(mc.set + hsh, 0xffffffffu, b);
+            if (cur == 0xffffffffu || cur == b) return;
+        }
+    }
+    atomicOr(need1 + (b >> 5), 1u << (b & 31u));                               // four occupied places in a row: straight to the mask
+}
+
+// how far along a cone its last sample at level <= 1 lies (0: none) — the loop of mark_cone without the marking, same arithmetic
+__device__ float cone_fine_reach(const NeedArgs& A, float tan_half)
+{
+    const float h = A.h, inv_h = 1.0f / h;
+    float t = 2.0f * h, last = 0.0f;
+    while (t < A.max_dist)
+    {
+        float diam;
+        const float lod = cone_lod(t, tan_half, h, inv_h, &diam);
+        if (lod >= (A.spec_b ? 2.0f : 1.5f) + 1e-3f) break;
+        last = t;
+        t += A.spec_b ? 0.5f * diam : diam;
+    }
+    return last;
 }
 
 // one cone: every sample it takes while its level is <= 1; returns whether it touches level 0
@@ -143,14 +181,6 @@ __device__ bool mark_cone(const NeedArgs& A, f3 origin, f3 dir, float tan_half, 
     return level0;
 }
 
-__constant__ float kNeedDiffuseDirs[6][3] = {
-    {0.0f, 0.0f, 1.0f},
-    {0.8660254f, 0.0f, 0.5f},
-    {0.26761657f, 0.82363910f, 0.5f},
-    {-0.70062927f, 0.50903696f, 0.5f},
-    {-0.70062927f, -0.50903696f, 0.5f},
-    {0.26761657f, -0.82363910f, 0.5f}};
-
 __global__ void __launch_bounds__(128) k_need_bricks(const NeedArgs A)
 {
     // pixel mapping of the tracer's CTA, 128 threads = 16 x 8 pixels of one 8-row tile row
@@ -158,6 +188,9 @@ __global__ void __launch_bounds__(128) k_need_bricks(const NeedArgs A)
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const uint32_t y = A.y0 + (A.tile0 + blockIdx.y * A.tile_stride) * 8 + (warp >> 1) * 4 + (lane >> 3);
     bool level0 = false;
+    __shared__ uint32_t mark_set[MARK_SET];
+    for (int i = threadIdx.x; i < MARK_SET; i += blockDim.x) mark_set[i] = 0xffffffffu;
+    __syncthreads();
     if (x < A.W && y < A.y1)
     {
         const float depth = __ldg(A.depth + (size_t)y * A.W + x);
@@ -170,33 +203,46 @@ __global__ void __launch_bounds__(128) k_need_bricks(const NeedArgs A)
             const f4 cp = mul44(A.InvProj, f4{uvx * 2.0f - 1.0f, uvy * 2.0f - 1.0f, depth, 1.0f});
             const f3 cspos = {cp.x / cp.w, cp.y / cp.w, cp.z / cp.w};
             const f3 wpos = mul43(A.InvModelView, cspos, 1.0f);
-            const ushort4 nq = __ldg(reinterpret_cast<const ushort4*>(A.normals) + (size_t)y * A.W + x);
-            const f3 csnorm = normalize3(f3{fmaf((float)nq.x / 65535.0f, 2.0f, -1.0f), fmaf((float)nq.y / 65535.0f, 2.0f, -1.0f), fmaf((float)nq.z / 65535.0f, 2.0f, -1.0f)});
-            const f3 wnorm = mul33(A.InvModelView, csnorm);
-            f3 z = wnorm, hh = wnorm;
-            if (fabsf(hh.x) <= fabsf(hh.y) && fabsf(hh.x) <= fabsf(hh.z)) hh.x = 1.0f;
-            else if (fabsf(hh.y) <= fabsf(hh.x) && fabsf(hh.y) <= fabsf(hh.z)) hh.y = 1.0f;
-            else hh.z = 1.0f;
-            z = normalize3(z);
-            const f3 ty = normalize3(cross3(hh, z));
-            const f3 tx = normalize3(cross3(z, ty));
-            const f3 origin = {wpos.x + z.x * A.h, wpos.y + z.y * A.h, wpos.z + z.z * A.h};
+            const float tan_s = cone_specular_tan((float)__ldg(A.material + (size_t)y * A.W + x).y / 255.0f);
+            level0 = cone_samples_level0(kTanHalfDiffuse, A.h, A.spec_b != 0) || cone_samples_level0(tan_s, A.h, A.spec_b != 0);
             MarkCache mc;
-#pragma unroll 1
-            for (int i = 0; i < 6; i++)
-            {
-                const float d0 = kNeedDiffuseDirs[i][0], d1 = kNeedDiffuseDirs[i][1], d2 = kNeedDiffuseDirs[i][2];
-                const f3 dir = {(tx.x * d0 + ty.x * d1) + z.x * d2, (tx.y * d0 + ty.y * d1) + z.y * d2, (tx.z * d0 + ty.z * d1) + z.z * d2};
-                level0 |= mark_cone(A, origin, dir, kTanHalfDiffuse, mc);
+            mc.set = mark_set;
+            const float reach_d = cone_fine_reach(A, kTanHalfDiffuse);
+            {   // the diffuse cones: the box around the pixel's position that holds all their fine samples
+                const f3 o3 = mul43(A.w2v, wpos, 1.0f);
+                const float n1 = (float)(A.N >> 1);
+                const float px = (o3.x * 0.5f + 0.5f) * n1 - 0.5f, py = (o3.y * 0.5f + 0.5f) * n1 - 0.5f, pz = o3.z * n1 - 0.5f;
+                const float r = (A.h + reach_d) * 1.0001f, e = 1.0f / 16.0f + 0.25f;
+                const float rx = r * A.texel_per_world[0] + e, ry = r * A.texel_per_world[1] + e, rz = r * A.texel_per_world[2] + e;
+                const int NB = (int)(A.N >> 3);
+                const int x0 = max((int)floorf(px - rx) >> 2, 0), x1 = min(((int)floorf(px + rx) + 1) >> 2, NB - 1);
+                const int y0 = max((int)floorf(py - ry) >> 2, 0), y1 = min(((int)floorf(py + ry) + 1) >> 2, NB - 1);
+                const int z0 = max((int)floorf(pz - rz) >> 2, 0), z1 = min(((int)floorf(pz + rz) + 1) >> 2, NB - 1);
+                if (reach_d > 0.0f)
+                    for (int bz = z0; bz <= z1; bz++)
+                        for (int by = y0; by <= y1; by++)
+                            for (int bx = x0; bx <= x1; bx++) mark_brick(A.need1, bx, by, bz, NB, mc);
             }
-            const float rough = (float)__ldg(A.material + (size_t)y * A.W + x).y / 255.0f;
-            const f3 I = normalize3(wpos - A.cam);
-            const float ndi = dot3(z, I);
-            const f3 R = {I.x - 2.0f * ndi * z.x, I.y - 2.0f * ndi * z.y, I.z - 2.0f * ndi * z.z};
-            if (dot3(R, z) > -1e-3f) level0 |= mark_cone(A, origin, R, cone_specular_tan(rough), mc);
+            if (cone_fine_reach(A, tan_s) > reach_d)
+            {   // a glossy pixel: its specular cone stays fine beyond the box
+                const ushort4 nq = __ldg(reinterpret_cast<const ushort4*>(A.normals) + (size_t)y * A.W + x);
+                const f3 csnorm = normalize3(f3{fmaf((float)nq.x / 65535.0f, 2.0f, -1.0f), fmaf((float)nq.y / 65535.0f, 2.0f, -1.0f), fmaf((float)nq.z / 65535.0f, 2.0f, -1.0f)});
+                const f3 z = normalize3(mul33(A.InvModelView, csnorm));
+                const f3 origin = {wpos.x + z.x * A.h, wpos.y + z.y * A.h, wpos.z + z.z * A.h};
+                const f3 I = normalize3(wpos - A.cam);
+                const float ndi = dot3(z, I);
+                const f3 R = {I.x - 2.0f * ndi * z.x, I.y - 2.0f * ndi * z.y, I.z - 2.0f * ndi * z.z};
+                if (dot3(R, z) > -1e-3f) mark_cone(A, origin, R, tan_s, mc);
+            }
         }
     }
     if (__syncthreads_or(level0) && threadIdx.x == 0) A.dev_state[F184_DEV_NEED_L0] = 1u;
+    // (the barrier above also orders the insertions before these reads)
+    for (int i = threadIdx.x; i < MARK_SET; i += blockDim.x)
+    {
+        const uint32_t b = mark_set[i];
+        if (b != 0xffffffffu && !((__ldcg(A.need1 + (b >> 5)) >> (b & 31u)) & 1u)) atomicOr(A.need1 + (b >> 5), 1u << (b & 31u));
+    }
 }
 
 // Level 0 is about to be gathered into a set whose level 0 was skipped by an earlier gather: the bricks of the OTHER ranks may hold
@@ -708,6 +754,11 @@ int f184_gather_n(f184_ctx* c, const f184_trace_constants* view)
                 memcpy(vp.m, view->ext.VoxelProj, 64);
                 memcpy(vv.m, view->ext.VoxelView, 64);
                 A.w2v = host_matmul(vp, vv);
+                for (int i = 0; i < 3; i++)
+                {   // |d(texel_i)| per unit of world distance, at most: the norm of row i of the linear part (x and y are mapped [-1, 1] -> [0, 1])
+                    const float* m = A.w2v.m;
+                    A.texel_per_world[i] = sqrtf(m[i] * m[i] + m[4 + i] * m[4 + i] + m[8 + i] * m[8 + i]) * (i < 2 ? 0.5f : 1.0f) * (float)(c->cfg.grid_n >> 1);
+                }
                 A.h = f184_voxel_h(view->ext.VoxelProj, view->ext.VoxelView, c->cfg.grid_n);      // the tracer's own h
                 A.cam = {A.InvModelView.m[12], A.InvModelView.m[13], A.InvModelView.m[14]};
             }
