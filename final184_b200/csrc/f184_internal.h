@@ -165,7 +165,9 @@ struct f184_ctx
     // the fragments this rank rasterised for rank p, which p reads over NVLink behind the barrier; frag_cursor = the append cursors
     // (= record counts, what p reads first); frag_counts: unused scratch
     // Each sender's region is split into F184_FRAG_SUBQUEUES sub-queues with a cursor of their own (a warp uses the one its index
-    // selects): one cursor per destination made every warp of the GPU hammer the same address with returning atomics.
+    // selects): one cursor per destination made every warp of the GPU hammer the same address with returning atomics.  Each cursor
+    // sits in a 128-byte line of its own (F184_FRAG_CURSOR_STRIDE words apart): with the 32 cursors of a destination in ONE line, one L2
+    // slice served every append of the GPU — at 2 GPUs (one destination) the voxelizer took 3.4 ms for half the triangles of C4.
     uint4* frag_queue = nullptr;
     uint32_t* frag_counts = nullptr;
     uint32_t* frag_cursor = nullptr;
@@ -204,6 +206,7 @@ struct f184_ctx
 };
 
 #define F184_FRAG_SUBQUEUES 32
+#define F184_FRAG_CURSOR_STRIDE 32        /* words between two cursors: a 128-byte line each */
 
 // dev_state words
 enum { F184_DEV_ERROR = 0,       // sticky error bits (F184_DEVERR_*), reported by the next synchronous call

@@ -218,7 +218,12 @@ __global__ void __launch_bounds__(128) k_need_bricks(const NeedArgs A)
                 const int x0 = max((int)floorf(px - rx) >> 2, 0), x1 = min(((int)floorf(px + rx) + 1) >> 2, NB - 1);
                 const int y0 = max((int)floorf(py - ry) >> 2, 0), y1 = min(((int)floorf(py + ry) + 1) >> 2, NB - 1);
                 const int z0 = max((int)floorf(pz - rz) >> 2, 0), z1 = min(((int)floorf(pz + rz) + 1) >> 2, NB - 1);
-                if (reach_d > 0.0f)
+                // neighbouring pixels mostly land on the same box of bricks: one lane per distinct box of the warp walks it
+                const bool small = x1 - x0 <= 3 && y1 - y0 <= 3 && z1 - z0 <= 3 && x0 <= x1 && y0 <= y1 && z0 <= z1;
+                const uint32_t key = small ? ((uint32_t)x0 | ((uint32_t)y0 << 7) | ((uint32_t)z0 << 14) | ((uint32_t)(x1 - x0) << 21) | ((uint32_t)(y1 - y0) << 23) | ((uint32_t)(z1 - z0) << 25))
+                                           : (0x80000000u | (uint32_t)lane);
+                const uint32_t same = __match_any_sync(__activemask(), key);
+                if (reach_d > 0.0f && (__ffs(same) - 1) == lane)
                     for (int bz = z0; bz <= z1; bz++)
                         for (int by = y0; by <= y1; by++)
                             for (int bx = x0; bx <= x1; bx++) mark_brick(A.need1, bx, by, bz, NB, mc);
@@ -592,9 +597,9 @@ int f184_ipc_buffer_ptr(f184_ctx* c, uint32_t buffer, void** out)
             const uint32_t G = c->cfg.nranks ? c->cfg.nranks : 1;
             CK(c, cudaMalloc(&c->frag_queue, sizeof(uint4) * cap * G));
             CK(c, cudaMalloc(&c->frag_counts, 8 * F184_FRAG_SUBQUEUES * sizeof(uint32_t)));
-            CK(c, cudaMalloc(&c->frag_cursor, 8 * F184_FRAG_SUBQUEUES * sizeof(uint32_t)));
+            CK(c, cudaMalloc(&c->frag_cursor, 8 * F184_FRAG_SUBQUEUES * F184_FRAG_CURSOR_STRIDE * sizeof(uint32_t)));
             CK(c, cudaMemsetAsync(c->frag_counts, 0, 8 * F184_FRAG_SUBQUEUES * sizeof(uint32_t), c->stream));
-            CK(c, cudaMemsetAsync(c->frag_cursor, 0, 8 * F184_FRAG_SUBQUEUES * sizeof(uint32_t), c->stream));
+            CK(c, cudaMemsetAsync(c->frag_cursor, 0, 8 * F184_FRAG_SUBQUEUES * F184_FRAG_CURSOR_STRIDE * sizeof(uint32_t), c->stream));
         }
         *out = buffer == F184_IPC_FRAG_QUEUE ? (void*)c->frag_queue : (void*)c->frag_cursor;
         return F184_OK;

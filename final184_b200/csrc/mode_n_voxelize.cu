@@ -363,13 +363,13 @@ __device__ __forceinline__ unsigned int process_column(const VoxArgs& A, const T
             const unsigned lane = threadIdx.x & 31u;
             const unsigned sub = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) & (F184_FRAG_SUBQUEUES - 1u);
             uint32_t slot;
-            if (A.no_aggregate) slot = atomicAdd(A.cursor + owner * F184_FRAG_SUBQUEUES + sub, 1u);
+            if (A.no_aggregate) slot = atomicAdd(A.cursor + (owner * F184_FRAG_SUBQUEUES + sub) * F184_FRAG_CURSOR_STRIDE, 1u);
             else
             {
                 const unsigned grp = __match_any_sync(__activemask(), owner);
                 const int leader = __ffs(grp) - 1;
                 uint32_t base = 0;
-                if ((int)lane == leader) base = atomicAdd(A.cursor + owner * F184_FRAG_SUBQUEUES + sub, (uint32_t)__popc(grp));
+                if ((int)lane == leader) base = atomicAdd(A.cursor + (owner * F184_FRAG_SUBQUEUES + sub) * F184_FRAG_CURSOR_STRIDE, (uint32_t)__popc(grp));
                 base = __shfl_sync(grp, base, leader);
                 slot = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
             }
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_voxelize_raster(const Vox
     warp_count_add(A.frag_counter, frags);
 }
 
-__global__ void k_reset_cursors(uint32_t* cursor) { cursor[threadIdx.x] = 0u; }           // <<<1, 8 * F184_FRAG_SUBQUEUES>>>
+__global__ void k_reset_cursors(uint32_t* cursor) { cursor[threadIdx.x * F184_FRAG_CURSOR_STRIDE] = 0u; }           // <<<1, 8 * F184_FRAG_SUBQUEUES>>>
 
 // Owner side, at the head of normalise: fetch the records the other ranks hold for this rank — coalesced 16-byte loads out of the
 // senders' memory over NVLink, 512 bytes per warp instruction — and apply them: two local 16-byte reductions and the brick flag per
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(256) k_apply_fragments(const ApplyArgs P)     
 {
     const uint32_t s = blockIdx.y / F184_FRAG_SUBQUEUES, sub = blockIdx.y % F184_FRAG_SUBQUEUES;
     if (s == P.rank) return;
-    const uint32_t n = min(P.peer_cursor[s][sub], P.sub_cap);
+    const uint32_t n = min(P.peer_cursor[s][sub * F184_FRAG_CURSOR_STRIDE], P.sub_cap);
     const uint4* q = P.peer_queue[s] + (size_t)sub * P.sub_cap;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride)
@@ -776,7 +776,7 @@ int f184_normalise_n(f184_ctx* c)
             if (!c->peer[p].buf[F184_IPC_FRAG_QUEUE] || !c->peer[p].buf[F184_IPC_FRAG_COUNTS])
                 return f184_fail(c, F184_ERR_NOT_READY, "normalise: fragment queue of rank %u was not imported (f184_ipc_import)", p);
             P.peer_queue[p] = reinterpret_cast<const uint4*>(c->peer[p].buf[F184_IPC_FRAG_QUEUE]) + (size_t)c->cfg.rank * c->frag_cap;
-            P.peer_cursor[p] = reinterpret_cast<const uint32_t*>(c->peer[p].buf[F184_IPC_FRAG_COUNTS]) + (size_t)c->cfg.rank * F184_FRAG_SUBQUEUES;
+            P.peer_cursor[p] = reinterpret_cast<const uint32_t*>(c->peer[p].buf[F184_IPC_FRAG_COUNTS]) + (size_t)c->cfg.rank * F184_FRAG_SUBQUEUES * F184_FRAG_CURSOR_STRIDE;
         }
         P.accC = img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR); P.accN = img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL);
         P.brick_flags = img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS);
