@@ -58,12 +58,19 @@ def host_threads():
 
 def timing_oracle():
     """The copy of the oracle that is TIMED: same sources, -O3 -march=native, built on the box it runs on (a stamp
-    of the CPU model keeps a copy built elsewhere from being reused).  Falls back to the checker build (-O2) if the compiler is
+    of the CPU's model + flags and of the sources keeps a copy built elsewhere, or from older sources, from being reused).  Falls back to the checker build (-O2) if the compiler is
     not there.  -> (path, flags description)"""
-    try:
-        model = [l for l in open("/proc/cpuinfo") if l.startswith("model name")][0].strip()
+    import glob
+    import hashlib
+    try:       # the CPU the copy was built for: model AND instruction-set flags (cloud CPUs share a generic model name)
+        info = [l.strip() for l in open("/proc/cpuinfo") if l.startswith(("model name", "flags"))][:2]
     except Exception:
-        model = "unknown"
+        info = ["unknown"]
+    hsh = hashlib.sha1("\n".join(info).encode())
+    for f in sorted(glob.glob(os.path.join(REPO, "oracle", "*.cpp")) + glob.glob(os.path.join(REPO, "oracle", "*.h")) + [os.path.join(REPO, "oracle", "Makefile")]
+                    + glob.glob(os.path.join(REPO, "include", "*.h")) + glob.glob(os.path.join(REPO, "final184_b200", "csrc", "*.h"))):
+        hsh.update(open(f, "rb").read())           # ... and the sources it was built from (a stale copy lacks newer entry points)
+    model = hsh.hexdigest()
     stamp = ORACLE_NATIVE_SO + ".host"
     fresh = os.path.exists(ORACLE_NATIVE_SO) and os.path.exists(stamp) and open(stamp).read() == model
     if not fresh:

@@ -205,7 +205,7 @@ struct f184_ctx
     cudaExternalSemaphore_t sem_wait = nullptr, sem_signal = nullptr;
 };
 
-#define F184_FRAG_SUBQUEUES 32
+#define F184_FRAG_SUBQUEUES 128
 #define F184_FRAG_CURSOR_STRIDE 32        /* words between two cursors: a 128-byte line each */
 
 // dev_state words

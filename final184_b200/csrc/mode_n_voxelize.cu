@@ -513,7 +513,7 @@ struct ApplyArgs
     uint32_t* brick_flags;
     uint32_t rank, nranks, sub_cap;
 };
-__global__ void __launch_bounds__(256) k_apply_fragments(const ApplyArgs P)     // grid (16, nranks * F184_FRAG_SUBQUEUES): blockIdx.y = one sub-queue
+__global__ void __launch_bounds__(256) k_apply_fragments(const ApplyArgs P)     // grid (2, nranks * F184_FRAG_SUBQUEUES): blockIdx.y = one sub-queue
 {
     const uint32_t s = blockIdx.y / F184_FRAG_SUBQUEUES, sub = blockIdx.y % F184_FRAG_SUBQUEUES;
     if (s == P.rank) return;
@@ -781,7 +781,7 @@ int f184_normalise_n(f184_ctx* c)
         P.accC = img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR); P.accN = img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL);
         P.brick_flags = img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS);
         P.rank = c->cfg.rank; P.nranks = G; P.sub_cap = c->frag_cap / F184_FRAG_SUBQUEUES;
-        k_apply_fragments<<<dim3(8, G * F184_FRAG_SUBQUEUES), 256, 0, c->stream>>>(P);
+        k_apply_fragments<<<dim3(2, G * F184_FRAG_SUBQUEUES), 256, 0, c->stream>>>(P);
         CK_LAUNCH(c);
         c->frag_pending = false;          // applied once: a second normalise without a new accumulation must not add them again
         if ((rc = f184_stage_end(c, F184_STAGE_APPLY))) return rc;

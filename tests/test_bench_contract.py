@@ -37,3 +37,22 @@ def test_bench_refuses_to_run_the_product_arm_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
     assert not r.stdout.strip().startswith("{")                   # no JSON line from a path that did not run
+
+
+def test_timed_oracle_copy_is_rebuilt_when_stale_and_exports_the_whole_interface(tmp_path):
+    """bench.py times a -O3 -march=native copy of the oracle.  A copy left over from older sources (it travels to the GPU box with the
+    snapshot) lacked a newer entry point and took the whole bench line down: the stamp covers the sources, and what comes back
+    loads through the same ctypes table as the checker build."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(REPO, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    stamp = b.ORACLE_NATIVE_SO + ".host"
+    so, flags = b.timing_oracle()
+    if so == b.ORACLE_NATIVE_SO:
+        open(stamp, "w").write("somebody else's build")            # as if the copy had come from another box / older sources
+        before = os.path.getmtime(so)
+        so2, _ = b.timing_oracle()
+        assert so2 == so and open(stamp).read() != "somebody else's build" and os.path.getmtime(so) >= before
+    from final184_b200 import api as A
+    A.Library(so, "f184o_", product=False)                         # raises on a missing symbol
