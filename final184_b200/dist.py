@@ -9,7 +9,7 @@ Partitioning helpers
                                 (Sponza's primitives range from 5 to 27,796 triangles; a contiguous cut by the same cost model left
                                 one of two ranks with 0.50 ms of voxelization and the other with 0.32)
   triangle_ranges(weights, n)   contiguous triangle ranges balanced by the cost model (kept for callers that want one range)
-  slab_ranges(N, n)             Z-slab [z0, z1) of every volume level owned by each rank
+  slab_ranges(N, n)             contiguous Z ranges of a level (host-mode tests; the device schedule owns bricks by diagonals: brick_owner)
   row_ranges(H, n, tile)        screen bands, multiples of the tracer's 8-row tile
   view_ranges(n_views, n)       whole views per rank (probe batches)
 
@@ -116,10 +116,11 @@ class ShardedVoxelGI:
     """The voxel/indirect section of one frame on rank `rank` of `nranks` GPUs of one NVLink box.
 
     mode "single"     one GPU.
-         "slab"       the north-star schedule (include/f184.h "one NVLink box"): triangle-range voxelization with the
-                      reduce-scatter fused into the voxelizer as peer atomics, the owners of the (interleaved) Z brick
-                      layers normalise / inject / build levels 1-3, a peer gather of the finished bricks, tracing of
-                      interleaved 8-row screen tiles.  Needs connect().
+         "slab"       the north-star schedule (include/f184.h "one NVLink box"): every rank voxelizes its triangle chunks; fragments
+                      of bricks another rank owns (diagonal ownership) go into local queues the owner pulls over NVLink
+                      (an all-to-all of fragments = the reduce-scatter); the owners normalise / inject / build levels 1-3 of
+                      their bricks; a peer gather of the finished bricks (bulk copies, level 1 only where this rank's cones
+                      need it); tracing of interleaved 8-row screen tiles.  Needs connect().
          "replicate"  no exchange at all: every rank builds the whole volume, only the trace is split.
          "host"       the slab schedule's HOST logic with the exchange done by torch.distributed on host arrays
                       (all_reduce of the partial accumulators): what the CPU tests drive with the gloo backend and the
@@ -189,8 +190,9 @@ class ShardedVoxelGI:
             return "1 GPU"
         if self.mode == "replicate":
             return f"{self.nranks} GPUs: volume replicated per rank (no exchange), trace split by interleaved 8-row tiles"
-        return (f"{self.nranks} GPUs: 128-triangle chunks dealt over the ranks by projected area (largest first), fragments reduced into the Z-slab owner's accumulators by peer "
-                f"atomics over NVLink, slab-local normalise/inject/mips, peer gather of the listed bricks, trace split by interleaved 8-row tiles")
+        return (f"{self.nranks} GPUs: 128-triangle chunks dealt over the ranks by projected area (largest first); 8^3 bricks owned along diagonals; fragments of foreign bricks queued "
+                f"locally and pulled by the owner over NVLink; owner-local normalise/inject/mips; view-driven peer gather of the listed bricks (TMA bulk copies); "
+                f"trace split by interleaved 8-row tiles")
 
     def frame(self, voxel_cam, k, trace=True):
         c = self.ctx
@@ -201,11 +203,11 @@ class ShardedVoxelGI:
         elif self.mode == "slab":
             if not self.connected:
                 raise A.F184Error("ShardedVoxelGI.frame: call connect() first (slab mode shares buffers between ranks)")
-            c.voxelize_accumulate(voxel_cam)     # peer atomics: the reduce-scatter happens here
-            c.peer_barrier()                     # every rank's fragments have landed in their owners
+            c.voxelize_accumulate(voxel_cam)     # own bricks: local reductions; foreign bricks: records in local queues
+            c.peer_barrier()                     # every rank's queues are complete; normalise starts by pulling and applying them
             c.normalise()
             c.inject(k)
-            c.build_mips()                       # levels 1-3 of the own slab + packed export records
+            c.build_mips()                       # levels 1-3 of the own bricks + the export arrays
             c.peer_barrier()
             c.gather_volume(k if trace else None)    # fetch the other ranks' bricks (level 1 only where this rank's cones sample it), finish the small levels
         else:                                    # "host": same order, exchange through torch.distributed on host arrays

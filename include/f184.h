@@ -331,8 +331,9 @@ int f184_copy_indirect_to_history(f184_ctx* ctx);
 /* mode R trace with F184_FLAG_EXTERNAL_RANDS: 8 x (u, v) floats per pixel, seed-major (parity aid) */
 int f184_bind_rands(f184_ctx* ctx, const float* device_rands, size_t count);
 
-/* ---- sharding.  A rank voxelizes triangles [first, first+count), owns Z-slab
- * [z0, z1) of every volume level and traces rows [y0, y1).  Defaults are derived from rank/nranks. */
+/* ---- sharding.  A rank voxelizes triangles [first, first+count) (or a chunk list, below), owns the 8^3 bricks
+ * (bx, by, bz) with (bx + by + bz) % nranks == rank — diagonals, so every axis-aligned wall is dealt evenly — and traces rows
+ * [y0, y1) / the tile rows below.  Defaults are derived from rank/nranks. */
 int f184_set_triangle_range(f184_ctx* ctx, uint32_t first, uint32_t count);
 /* Mode N: the triangles this rank voxelizes as a list of 128-triangle chunks (chunk c = triangles [128 c, 128 c + 128)), on top of which
  * the range above still filters.  Chunks let a cost model deal the scene over the ranks in small pieces (largest first, to the least loaded
@@ -357,19 +358,22 @@ int f184_set_trace_tiles(f184_ctx* ctx, uint32_t first, uint32_t stride);
  *                             reduce-scatter is an all-to-all of fragments; a full queue falls back to the remote reduction
  *                             (system scope)
  *   f184_peer_barrier         device-side flag barrier over peer memory (no host round trip, no NCCL launch)
- *   f184_normalise / f184_inject / f184_build_mips   owner works on its slab's bricks only
+ *   f184_normalise / f184_inject / f184_build_mips   owner works on its own bricks only; build_mips also writes them into the
+ *                             export arrays (level 0 | level 1 | "coarse" = levels 2, 3 + brick index, contiguous over bricks)
  *   f184_peer_barrier
- *   f184_gather_volume        every rank pulls the other ranks' finished bricks (packed 4 KB records, levels 0-3) over
- *                             NVLink straight into its own texture storage, then finishes the small levels locally
- *   f184_trace_indirect       rows [y0, y1) of the screen
+ *   f184_gather_volume[_view] every rank pulls the other ranks' finished bricks over NVLink with bulk copies (cp.async.bulk into
+ *                             shared memory: one 16 KB copy moves the coarse blocks of 64 bricks; level 1 and level 0 follow per
+ *                             brick, only where this rank's cones sample them) and stores them into its own texture storage,
+ *                             then finishes the small levels locally
+ *   f184_trace_indirect       the 8-row tile rows t of the screen with t % nranks == rank
  * Buffers are shared between processes with CUDA IPC handles, exchanged by the caller (torch.distributed). */
 typedef enum f184_ipc_buffer {
     F184_IPC_ACCUM_COLOR = 0,
     F184_IPC_ACCUM_NORMAL = 1,
     F184_IPC_BRICK_FLAGS = 2,
-    F184_IPC_EXPORT = 3,        /* packed per-brick records written by f184_build_mips */
+    F184_IPC_EXPORT = 3,        /* the export arrays written by f184_build_mips (1024 words of room per own brick) */
     F184_IPC_COUNTERS = 4,
-    F184_IPC_BRICK_LIST = 5,
+    F184_IPC_BRICK_LIST = 5,    /* (not read by peers any more: a brick's index travels in its coarse block) */
     F184_IPC_SYNC = 6,          /* barrier flags */
     F184_IPC_FRAG_QUEUE = 7,    /* fragment records this rank has for the other ranks (one region per destination; the destination reads it) */
     F184_IPC_FRAG_COUNTS = 8,   /* how many records each region holds (this rank's append cursors) */
