@@ -165,6 +165,8 @@ _SIGS = {
     "voxelize": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC)]),
     "voxelize_accumulate": (C.c_int, [C.c_void_p, C.POINTER(ViewConstantsC)]),
     "normalise": (C.c_int, [C.c_void_p]),
+    "static_cache_capture": (C.c_int, [C.c_void_p]),
+    "static_cache_clear": (C.c_int, [C.c_void_p]),
     "inject": (C.c_int, [C.c_void_p, C.POINTER(SunC), C.POINTER(ExtendedMatricesC)]),
     "build_mips": (C.c_int, [C.c_void_p]),
     "trace_indirect": (C.c_int, [C.c_void_p, C.POINTER(TraceConstantsC)]),
@@ -350,6 +352,13 @@ class VoxelGI:
 
     def normalise(self):
         self._ck(self.lib.normalise(self.h), "normalise")
+
+    def static_cache_capture(self):
+        """keep what the accumulators hold (the static triangles, just accumulated) as the static cache — include/f184.h"""
+        self._ck(self.lib.static_cache_capture(self.h), "static_cache_capture")
+
+    def static_cache_clear(self):
+        self._ck(self.lib.static_cache_clear(self.h), "static_cache_clear")
 
     # -- one NVLink box (product library only)
     def ipc_export(self, buffer) -> bytes:

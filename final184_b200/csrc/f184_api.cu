@@ -456,6 +456,8 @@ void f184_destroy(f184_ctx* c)
         for (int b = 0; b < F184_IPC_COUNT; b++)
             if (pr.imported[b] && pr.buf[b]) cudaIpcCloseMemHandle(pr.buf[b]);
     if (c->export_buf) cudaFree(c->export_buf);
+    for (void* p : {(void*)c->cacheC, (void*)c->cacheN, (void*)c->cache_slot, (void*)c->cache_occ})
+        if (p) cudaFree(p);
     for (void* p : {(void*)c->frag_queue, (void*)c->frag_counts, (void*)c->frag_cursor})
         if (p) cudaFree(p);
     if (c->sync_flags) cudaFree(c->sync_flags);
@@ -964,6 +966,34 @@ int f184_normalise(f184_ctx* c)
     }
     return f184_leave(c, sec, rc);
 }
+// Static / dynamic split: keep what the accumulators hold now (the static geometry, accumulated by the caller) instead of normalising it.
+int f184_static_cache_capture(f184_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    if (c->cfg.mode != F184_MODE_NORTHSTAR) return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "static_cache_capture is a north-star stage");
+    if (!c->brick_prev) return f184_fail(c, F184_ERR_NOT_READY, "static_cache_capture: call f184_voxelize_accumulate (static triangles) first");
+    CK(c, cudaSetDevice(c->cfg.device));
+    F184Section sec;
+    int rc = f184_enter(c, F184_SID_BUILD, &sec);
+    if (rc) return rc;
+    rc = f184_build_wait_vox(c);
+    if (rc == F184_OK) rc = f184_static_cache_capture_n(c);
+    if (rc == F184_OK && sec.switched)
+    {   // the accumulators are clear again: the next accumulation may start (what f184_normalise signals)
+        cudaError_t e = cudaEventRecord(c->ev_normalised, c->stream);
+        if (e != cudaSuccess) rc = f184_fail(c, F184_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
+        c->normalised_valid = true;
+    }
+    rc = f184_leave(c, sec, rc);
+    return rc ? rc : f184_sync(c);
+}
+int f184_static_cache_clear(f184_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->cfg.device));
+    int rc = f184_sync(c);
+    return rc ? rc : f184_static_cache_clear_n(c);
+}
 int f184_gather_volume_view(f184_ctx* c, const f184_trace_constants* view)
 {
     if (!c) return F184_ERR_INVALID_ARGUMENT;
@@ -1192,6 +1222,7 @@ int f184_counter_get(f184_ctx* c, uint32_t which, uint64_t* v)
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaMemcpy(&t, c->counters_dev + which, sizeof(t), cudaMemcpyDeviceToHost));
     *v = t;
+    if (which == F184_COUNTER_FRAGMENTS && c->cache_slot) *v += c->cache_fragments;       // the cached static geometry's share
     return c->cfg.nranks > 1 ? f184_check_device_errors(c) : F184_OK;
 }
 

@@ -172,6 +172,16 @@ struct f184_ctx
     uint32_t* frag_counts = nullptr;
     uint32_t* frag_cursor = nullptr;
     uint32_t frag_cap = 0;
+    // static / dynamic split (f184_static_cache_capture): the accumulators of the bricks the static geometry touches, kept sparse
+    // (16 KB per brick), added to the frame's accumulators inside normalise.  cache_slot: per brick, its place in the cache or -1.
+    float4* cacheC = nullptr;
+    float4* cacheN = nullptr;
+    int32_t* cache_slot = nullptr;
+    uint32_t* cache_occ = nullptr;            // occupied voxels per cached brick (F184_COUNTER_OCCUPIED stays what a full voxelization counts)
+    uint32_t n_cached = 0;
+    uint64_t cache_fragments = 0;             // fragments the cached geometry made (added to F184_COUNTER_FRAGMENTS)
+    float cache_cam[32] = {0};                // ViewMat | ProjMat of the voxel camera the cache was captured with
+    float last_vox_cam[32] = {0};             // ... and of the last accumulation
     bool frag_pending = false;                // an accumulation has run since the last normalise: the peers' queues hold fragments for this rank
     bool frag_sent_applied = false;           // a peer barrier has followed the last accumulation: the next one starts the queues over
     uint32_t* export_buf = nullptr;           // the own bricks' export arrays (k_mips_bricks): level 0 | level 1 | levels 2, 3 + brick index; 1024 words of room per brick
@@ -296,6 +306,8 @@ int f184_trace_views_n(f184_ctx* c, const f184_trace_constants* ks, uint32_t vie
 int f184_mode_n_release(f184_ctx* c);
 int f184_mode_n_alloc(f184_ctx* c);
 int f184_normalise_n(f184_ctx* c);
+int f184_static_cache_capture_n(f184_ctx* c);
+int f184_static_cache_clear_n(f184_ctx* c);
 int f184_voxelizer_scratch_n(f184_ctx* c);
 int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam);
 int f184_gather_n(f184_ctx* c, const f184_trace_constants* view);

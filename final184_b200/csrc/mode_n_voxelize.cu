@@ -554,7 +554,7 @@ __global__ void k_view_model_n(M4 View, const M4* __restrict__ model, M4* __rest
 // Any of them lists the brick, so whichever copy is stale gets overwritten (with zeros if the brick is empty now).
 __global__ void __launch_bounds__(256)
 k_brick_compact(uint32_t* __restrict__ brick_flags, uint32_t* __restrict__ brick_prev, uint32_t* __restrict__ brick_list,
-                unsigned long long* __restrict__ counters, uint32_t n_own, uint32_t NB, uint32_t G, uint32_t rank)
+                unsigned long long* __restrict__ counters, uint32_t n_own, uint32_t NB, uint32_t G, uint32_t rank, const int32_t* __restrict__ cache_slot)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;             // j-th brick of this rank
@@ -562,11 +562,25 @@ k_brick_compact(uint32_t* __restrict__ brick_flags, uint32_t* __restrict__ brick
     const uint32_t per_row = NB / G, row = j / per_row, by = row % NB, bz = row / NB;
     const uint32_t bx = ((rank + 2u * G - (by % G) - (bz % G)) % G) + (j % per_row) * G;
     const uint32_t bi = (bz * NB + by) * NB + bx;
-    uint32_t flag = 0, prev = 0;
-    if (j < n_own) { flag = brick_flags[bi]; prev = brick_prev[bi]; }
-    if (flag | prev) { brick_flags[bi] = 0; brick_prev[bi] = (prev & ~1u) | (flag ? 1u : 0u); }
-    const unsigned int todo = __ballot_sync(0xffffffffu, (flag | prev) != 0);
-    const unsigned int touched = __ballot_sync(0xffffffffu, flag != 0);
+    // With a static cache (f184_static_cache_capture): a cached brick always has content — it is listed every frame for inject and
+    // mips — but normalise has to look at it only if this frame's or the previous frame's (dynamic) fragments touched it: history
+    // bit 3, valid for this frame only, says so.  (Without a cache bit 3 is never set and nothing below differs from before.)
+    uint32_t flag = 0, prev = 0, cached = 0;
+    if (j < n_own)
+    {
+        flag = brick_flags[bi];
+        prev = brick_prev[bi] & ~8u;
+        if (cache_slot) cached = cache_slot[bi] >= 0 ? 1u : 0u;
+    }
+    if (flag | prev | cached)
+    {
+        const uint32_t redo = (cache_slot && (flag | (prev & 1u))) ? 8u : 0u;
+        brick_flags[bi] = 0;
+        brick_prev[bi] = (prev & ~1u) | (flag ? 1u : 0u) | redo;
+    }
+    const bool content = (flag | cached) != 0;
+    const unsigned int todo = __ballot_sync(0xffffffffu, (flag | prev | cached) != 0);
+    const unsigned int touched = __ballot_sync(0xffffffffu, content);
     if (!todo) return;
     unsigned long long slot = 0;
     if (lane == 0)
@@ -575,14 +589,16 @@ k_brick_compact(uint32_t* __restrict__ brick_flags, uint32_t* __restrict__ brick
         if (touched) atomicAdd(counters + F184_COUNTER_BRICKS, (unsigned long long)__popc(touched));
     }
     slot = __shfl_sync(0xffffffffu, slot, 0);
-    if (flag | prev) brick_list[(uint32_t)slot + __popc(todo & ((1u << lane) - 1u))] = bi | (flag ? 0x80000000u : 0u);
+    if (flag | prev | cached) brick_list[(uint32_t)slot + __popc(todo & ((1u << lane) - 1u))] = bi | (content ? 0x80000000u : 0u);
 }
 
 // pass 2: one warp per listed brick, 16 passes of 32 voxels: 512 B coalesced accumulator reads, 32 B output runs.
 // Reads the sums, writes mean albedo / unit normal as RGBA8 and re-zeroes the accumulators (= next frame's clear).
 __global__ void __launch_bounds__(256)
 k_normalise_n(float4* __restrict__ accC, float4* __restrict__ accN, uchar4* __restrict__ alb, char4* __restrict__ nrm,
-              const uint32_t* __restrict__ brick_list, unsigned long long* __restrict__ counters, int N)
+              const uint32_t* __restrict__ brick_list, unsigned long long* __restrict__ counters, int N,
+              const int32_t* __restrict__ cache_slot, const float4* __restrict__ cacheC, const float4* __restrict__ cacheN,
+              const uint32_t* __restrict__ cache_occ, const uint32_t* __restrict__ brick_prev)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -593,7 +609,22 @@ k_normalise_n(float4* __restrict__ accC, float4* __restrict__ accN, uchar4* __re
     {
         const uint32_t entry = __ldg(brick_list + i);
         const uint32_t b = entry & 0x7fffffffu;
-        const bool is_touched = (entry >> 31) != 0;
+        bool is_touched = (entry >> 31) != 0;                         // the accumulators hold fragments of this frame
+        int slot = -1;
+        if (cache_slot)
+        {   // static cache: sums = this frame's accumulators (if any fragment landed: history bit 0, just set by the compaction) + the
+            // cached static sums.  A cached brick no dynamic fragment touched now or last frame keeps what the volumes hold already.
+            slot = cache_slot[b];
+            const uint32_t hist = brick_prev[b];
+            is_touched = (hist & 1u) != 0;
+            if (slot >= 0 && !(hist & 8u))
+            {
+                if (lane == 0) occ += cache_occ[slot];
+                continue;
+            }
+        }
+        const float4* kc = slot >= 0 ? cacheC + (size_t)slot * 512 : nullptr;
+        const float4* kn = slot >= 0 ? cacheN + (size_t)slot * 512 : nullptr;
         const int bx = (b % NB) << 3, by = ((b / NB) % NB) << 3, bz = (b / (NB * NB)) << 3;
         // two halves of 8 passes: all 8 colour loads, then the 8 normal loads predicated on occupancy (no branch around
         // them, so they are all in flight together), then the arithmetic and the stores
@@ -606,12 +637,14 @@ k_normalise_n(float4* __restrict__ accC, float4* __restrict__ accN, uchar4* __re
             {
                 const size_t o = (size_t)b * 512 + (half * 8 + k) * 32 + lane;
                 cs[k] = is_touched ? accC[o] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kc) { const float4 q = __ldg(kc + (half * 8 + k) * 32 + lane); cs[k].x += q.x; cs[k].y += q.y; cs[k].z += q.z; cs[k].w += q.w; }
             }
 #pragma unroll
             for (int k = 0; k < 8; k++)
             {
                 const size_t o = (size_t)b * 512 + (half * 8 + k) * 32 + lane;
-                ns[k] = cs[k].w > 0.0f ? accN[o] : make_float4(0.f, 0.f, 0.f, 0.f);
+                ns[k] = (cs[k].w > 0.0f && is_touched) ? accN[o] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kn && cs[k].w > 0.0f) { const float4 q = __ldg(kn + (half * 8 + k) * 32 + lane); ns[k].x += q.x; ns[k].y += q.y; ns[k].z += q.z; }
             }
 #pragma unroll
             for (int k = 0; k < 8; k++)
@@ -630,8 +663,11 @@ k_normalise_n(float4* __restrict__ accC, float4* __restrict__ accN, uchar4* __re
                     if (len > 0.0f)
                         n8 = make_char4((signed char)rintf(nn.x / len * 127.0f), (signed char)rintf(nn.y / len * 127.0f),
                                         (signed char)rintf(nn.z / len * 127.0f), 0);
-                    accC[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    accN[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (is_touched)
+                    {
+                        accC[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        accN[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                     occ++;
                 }
                 const int x = bx + (local & 7), y = by + ((local >> 3) & 7), z = bz + (local >> 6);
@@ -668,6 +704,10 @@ int f184_voxelizer_scratch_n(f184_ctx* c)
 
 int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
 {
+    memcpy(c->last_vox_cam, cam->ViewMat, 64);
+    memcpy(c->last_vox_cam + 16, cam->ProjMat, 64);
+    if (c->cache_slot && memcmp(c->last_vox_cam, c->cache_cam, sizeof(c->cache_cam)) != 0)
+        return f184_fail(c, F184_ERR_INVALID_ARGUMENT, "voxelize: the static cache was captured with another voxel camera (f184_static_cache_clear, or capture again)");
     for (int s : {F184_SLOT_ACCUM_COLOR, F184_SLOT_ACCUM_NORMAL, F184_SLOT_VOX_ALBEDO, F184_SLOT_VOX_NORMAL, F184_SLOT_BRICK_FLAGS})
     {
         int rc = f184_ensure_image(c, s);
@@ -759,12 +799,11 @@ int f184_voxelize_accumulate_n(f184_ctx* c, const f184_view_constants* cam)
     return f184_stage_end(c, F184_STAGE_VOXELIZE);
 }
 
-// Normalise this rank's bricks (the whole volume on one GPU).
-int f184_normalise_n(f184_ctx* c)
+// The fragments the other ranks hold for this rank (their kernels finished before the barrier this call follows): pulled and reduced
+// into the own accumulators.  Once per accumulation.
+static int apply_pending_fragments(f184_ctx* c)
 {
-    const int N = (int)c->cfg.grid_n;
-    const uint32_t NB = (uint32_t)N / 8, G = c->cfg.nranks > 1 ? c->cfg.nranks : 1;
-    const uint32_t n_own = (NB / G) * NB * NB;
+    const uint32_t G = c->cfg.nranks > 1 ? c->cfg.nranks : 1;
     int rc = F184_OK;
     if (G > 1 && c->frag_queue && c->frag_pending)
     {
@@ -786,15 +825,129 @@ int f184_normalise_n(f184_ctx* c)
         c->frag_pending = false;          // applied once: a second normalise without a new accumulation must not add them again
         if ((rc = f184_stage_end(c, F184_STAGE_APPLY))) return rc;
     }
+    return F184_OK;
+}
+
+// Normalise this rank's bricks (the whole volume on one GPU).
+int f184_normalise_n(f184_ctx* c)
+{
+    const int N = (int)c->cfg.grid_n;
+    const uint32_t NB = (uint32_t)N / 8, G = c->cfg.nranks > 1 ? c->cfg.nranks : 1;
+    const uint32_t n_own = (NB / G) * NB * NB;
+    int rc = apply_pending_fragments(c);
+    if (rc) return rc;
     rc = f184_stage_begin(c, F184_STAGE_NORMALISE);
     if (rc) return rc;
     if ((rc = f184_zero_counters(c, (1u << F184_COUNTER_OCCUPIED) | (1u << F184_COUNTER_BRICKS) | (1u << F184_COUNTER_COUNT)))) return rc;   // COUNT = the list cursor
     k_brick_compact<<<(n_own + 255) / 256, 256, 0, c->stream>>>(img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS), c->brick_prev, c->brick_list,
-                                                              c->counters_dev, n_own, NB, G, c->cfg.rank % G);
+                                                              c->counters_dev, n_own, NB, G, c->cfg.rank % G, c->cache_slot);
     CK_LAUNCH(c);
     k_normalise_n<<<148 * 16, 128, 0, c->stream>>>(img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL),
                                                   img_ptr<uchar4>(c, F184_SLOT_VOX_ALBEDO), img_ptr<char4>(c, F184_SLOT_VOX_NORMAL),
-                                                  c->brick_list, c->counters_dev, N);
+                                                  c->brick_list, c->counters_dev, N, c->cache_slot, c->cacheC, c->cacheN, c->cache_occ, c->brick_prev);
     CK_LAUNCH(c);
     return f184_stage_end(c, F184_STAGE_NORMALISE);
+}
+
+// ---- static / dynamic split ---------------------------------------------------------------------------
+// Geometry that never moves need not be rasterised every frame.  After an accumulation of the STATIC triangles (and, on several
+// ranks, the barrier that completes it) f184_static_cache_capture moves the accumulators of every touched brick of this rank into a
+// sparse cache — 16 KB per brick — instead of normalising them.  From then on the caller accumulates only the DYNAMIC triangles;
+// normalise adds a brick's cached sums to whatever the frame's fragments left in its accumulators.  Sums of integer-valued floats
+// are exact in any order, so the volumes are bit-identical to voxelizing everything every frame.  A cached brick that no dynamic
+// fragment touches (now or in the previous frame) is not read at all: the linear volumes hold its values already.
+static __global__ void __launch_bounds__(256) k_cache_count(const uint32_t* __restrict__ flags, uint32_t n_bricks, unsigned int* __restrict__ out)
+{
+    unsigned int n = 0;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_bricks; b += gridDim.x * blockDim.x) n += flags[b] ? 1u : 0u;
+    for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
+}
+static __global__ void __launch_bounds__(256)
+k_cache_capture(float4* __restrict__ accC, float4* __restrict__ accN, uint32_t* __restrict__ flags, uint32_t* __restrict__ brick_prev, uint32_t n_bricks,
+                float4* __restrict__ cacheC, float4* __restrict__ cacheN, int32_t* __restrict__ cache_slot, uint32_t* __restrict__ cache_occ,
+                unsigned int* __restrict__ cursor)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp_global; b < n_bricks; b += n_warps)
+    {
+        if (!flags[b]) continue;                                      // (warp-uniform: every lane reads the same word)
+        unsigned int slot = 0;
+        if (lane == 0) slot = atomicAdd(cursor, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        unsigned int occ = 0;
+#pragma unroll 4
+        for (int k = 0; k < 16; k++)
+        {
+            const size_t o = (size_t)b * 512 + k * 32 + lane;
+            const float4 cc = accC[o], nn = accN[o];
+            cacheC[(size_t)slot * 512 + k * 32 + lane] = cc;
+            cacheN[(size_t)slot * 512 + k * 32 + lane] = nn;
+            if (cc.w > 0.0f)
+            {
+                occ++;
+                accC[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                accN[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        for (int o = 16; o; o >>= 1) occ += __shfl_xor_sync(0xffffffffu, occ, o);
+        if (lane == 0)
+        {
+            cache_slot[b] = (int32_t)slot;
+            cache_occ[slot] = occ;
+            flags[b] = 0;
+            brick_prev[b] |= 1u;                                      // "touched by the previous voxelize": the next normalise writes the brick's static values
+        }
+    }
+}
+
+static void cache_free(f184_ctx* c)
+{
+    for (void* p : {(void*)c->cacheC, (void*)c->cacheN, (void*)c->cache_slot, (void*)c->cache_occ})
+        if (p) cudaFree(p);
+    c->cacheC = c->cacheN = nullptr; c->cache_slot = nullptr; c->cache_occ = nullptr;
+    c->n_cached = 0; c->cache_fragments = 0;
+}
+
+int f184_static_cache_capture_n(f184_ctx* c)
+{
+    const uint32_t N = c->cfg.grid_n, n_bricks = (N / 8) * (N / 8) * (N / 8);
+    int rc = apply_pending_fragments(c);
+    if (rc) return rc;
+    CK(c, cudaStreamSynchronize(c->stream));
+    cache_free(c);
+    uint32_t* flags = img_ptr<uint32_t>(c, F184_SLOT_BRICK_FLAGS);
+    unsigned int* counter = nullptr;
+    CK(c, cudaMalloc(&counter, 2 * sizeof(unsigned int)));
+    CK(c, cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), c->stream));
+    k_cache_count<<<148 * 4, 256, 0, c->stream>>>(flags, n_bricks, counter);
+    CK_LAUNCH(c);
+    unsigned int n = 0;
+    CK(c, cudaMemcpyAsync(&n, counter, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaMalloc(&c->cache_slot, sizeof(int32_t) * (size_t)n_bricks));
+    if ((rc = f184_fill_async(c, c->cache_slot, 0xffffffffu, sizeof(int32_t) * (size_t)n_bricks, c->stream))) return rc;
+    const size_t slots = n ? n : 1;
+    CK(c, cudaMalloc(&c->cacheC, sizeof(float4) * 512 * slots));
+    CK(c, cudaMalloc(&c->cacheN, sizeof(float4) * 512 * slots));
+    CK(c, cudaMalloc(&c->cache_occ, sizeof(uint32_t) * slots));
+    k_cache_capture<<<148 * 8, 256, 0, c->stream>>>(img_ptr<float4>(c, F184_SLOT_ACCUM_COLOR), img_ptr<float4>(c, F184_SLOT_ACCUM_NORMAL), flags, c->brick_prev, n_bricks,
+                                                   c->cacheC, c->cacheN, c->cache_slot, c->cache_occ, counter + 1);
+    CK_LAUNCH(c);
+    unsigned long long frags = 0;
+    CK(c, cudaMemcpyAsync(&frags, c->counters_dev + F184_COUNTER_FRAGMENTS, sizeof(frags), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(counter);
+    c->n_cached = n;
+    c->cache_fragments = frags;
+    memcpy(c->cache_cam, c->last_vox_cam, sizeof(c->cache_cam));
+    return F184_OK;
+}
+
+int f184_static_cache_clear_n(f184_ctx* c)
+{
+    CK(c, cudaStreamSynchronize(c->stream));
+    cache_free(c);            // the bricks it held carry their history bits: the next frames list them and write what is left (zeros, or the dynamic part)
+    return F184_OK;
 }

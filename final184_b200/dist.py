@@ -224,6 +224,27 @@ class ShardedVoxelGI:
         if trace:
             c.trace_indirect(k)
 
+    def capture_static(self, voxel_cam):
+        """Static / dynamic split (include/f184.h): the CURRENT triangle selection (set_triangle_range on top of this rank's chunks) is
+        the geometry that never moves — accumulate it once, complete it across the ranks, and keep every rank's own bricks of it
+        (f184_static_cache_capture).  Afterwards select the dynamic triangles and call frame() as usual."""
+        c = self.ctx
+        c.voxelize_accumulate(voxel_cam)
+        if self.mode == "slab":
+            if not self.connected:
+                raise A.F184Error("ShardedVoxelGI.capture_static: call connect() first")
+            c.peer_barrier()
+        elif self.mode == "host":
+            import torch
+            import torch.distributed as dist
+            for slot in (A.SLOT_ACCUM_COLOR, A.SLOT_ACCUM_NORMAL):
+                t = torch.from_numpy(c.readback(slot))
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                c.upload(slot, t.numpy())
+        c.static_cache_capture()
+        if self.mode == "slab":
+            c.peer_barrier()              # every rank has pulled its fragments out of the others' queues: they may be started over
+
     def gather_image(self):
         """The full traced image on every rank (a consumer that wants one image; not part of the frame)."""
         img = self.ctx.readback(A.SLOT_INDIRECT_OUT)

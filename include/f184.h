@@ -392,6 +392,20 @@ int f184_gather_volume(f184_ctx* ctx);
  * listed brick travels whole.  The G-buffer bound at the time of the call must be the one the trace will read. */
 int f184_gather_volume_view(f184_ctx* ctx, const f184_trace_constants* view);
 
+/* ---- static / dynamic split (mode N).  The reference re-voxelizes the whole scene every frame
+ * (MegaPipeline.cpp:196, 218-223) although Sponza never moves.  Usage:
+ *     select the STATIC triangles (f184_set_triangle_range / f184_set_triangle_chunks); f184_voxelize_accumulate(voxel_cam);
+ *     [several ranks: f184_peer_barrier;]  f184_static_cache_capture(ctx);  [several ranks: f184_peer_barrier again — the capture pulls
+ *     the fragments the other ranks hold for this rank, and nobody may start over its queues before everybody has]
+ *     every frame: select the DYNAMIC triangles (possibly none: count 0) and run the frame as usual.
+ * Capture moves the accumulators of every brick the static geometry touched (this rank's bricks) into a sparse cache, 16 KB per brick,
+ * and leaves the accumulators clear; f184_normalise then adds a brick's cached sums to the frame's.  The sums are integer-valued, so every
+ * volume, texture level and counter is bit-identical to voxelizing all triangles every frame — without the static share of voxelize
+ * (and, on several ranks, of the fragment exchange), and without normalise reading static bricks no dynamic fragment touched.
+ * The voxel camera must stay the one the cache was captured with (F184_ERR_INVALID_ARGUMENT otherwise).  Both calls are synchronous. */
+int f184_static_cache_capture(f184_ctx* ctx);
+int f184_static_cache_clear(f184_ctx* ctx);
+
 /* ---- measurement */
 int f184_stage_time_ms(f184_ctx* ctx, uint32_t stage, float* out_ms);   /* last run of the stage; synchronous */
 int f184_counter_get(f184_ctx* ctx, uint32_t which, uint64_t* out_value);    /* synchronous */

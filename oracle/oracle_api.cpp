@@ -287,6 +287,7 @@ int f184o_counter_get(f184o_ctx* c, uint32_t which, uint64_t* v)
 {
     if (!c || which >= F184_COUNTER_COUNT || !v) return F184_ERR_INVALID_ARGUMENT;
     *v = c->counters[which];
+    if (which == F184_COUNTER_FRAGMENTS && c->cache_held) *v += c->cache_fragments;
     return F184_OK;
 }
 int f184o_copy_taa_to_history(f184o_ctx* c)
@@ -355,6 +356,19 @@ int f184o_normalise(f184o_ctx* c)
 {
     if (!c || c->cfg.mode != F184_MODE_NORTHSTAR) return F184_ERR_INVALID_ARGUMENT;
     return orc_normalise_n(c);
+}
+extern "C" int orc_static_cache_capture_n(f184o_ctx*);
+int f184o_static_cache_capture(f184o_ctx* c)
+{
+    if (!c || c->cfg.mode != F184_MODE_NORTHSTAR) return F184_ERR_INVALID_ARGUMENT;
+    return orc_static_cache_capture_n(c);
+}
+int f184o_static_cache_clear(f184o_ctx* c)
+{
+    if (!c) return F184_ERR_INVALID_ARGUMENT;
+    c->cacheC.clear(); c->cacheC.shrink_to_fit(); c->cacheN.clear(); c->cacheN.shrink_to_fit();
+    c->cache_held = false; c->cache_fragments = 0;
+    return F184_OK;
 }
 int f184o_inject(f184o_ctx* c, const f184_sun* sun, const f184_extended_matrices* m)
 {

@@ -155,6 +155,11 @@ struct f184o_ctx
     // between this file's fixed-function stages instead of the restated stages
     f184o_voxel_gs_hook gs_hook = nullptr;
     f184o_voxel_ps_hook ps_hook = nullptr;
+    // static / dynamic split (f184o_static_cache_capture): the accumulator sums of the static geometry, dense here
+    std::vector<float> cacheC, cacheN;
+    bool cache_held = false;
+    uint64_t cache_fragments = 0;
+    float cache_cam[32] = {0}, last_vox_cam[32] = {0};
     uint64_t counters[F184_COUNTER_COUNT] = {0};
     float stage_ms[F184_STAGE_COUNT] = {0};
 };

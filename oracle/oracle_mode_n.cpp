@@ -162,6 +162,10 @@ extern "C" int orc_voxelize_accumulate_n(f184o_ctx* c, const f184_view_constants
     float* accN = image_ptr<float>(c, F184_SLOT_ACCUM_NORMAL);
     memset(accC, 0, nvox * 16);
     memset(accN, 0, nvox * 16);
+    memcpy(c->last_vox_cam, cam->ViewMat, 64);
+    memcpy(c->last_vox_cam + 16, cam->ProjMat, 64);
+    if (c->cache_held && memcmp(c->last_vox_cam, c->cache_cam, sizeof(c->cache_cam)) != 0)
+    { c->err = "voxelize: the static cache was captured with another voxel camera"; return F184_ERR_INVALID_ARGUMENT; }
 
     const M4 View = load_m4(cam->ViewMat), Proj = load_m4(cam->ProjMat);
     std::vector<M4> VM(c->n_models), MM(c->n_models);
@@ -311,6 +315,16 @@ extern "C" int orc_normalise_n(f184o_ctx* c)
     const size_t nvox = (size_t)N * N * N;
     float* accC = image_ptr<float>(c, F184_SLOT_ACCUM_COLOR);
     float* accN = image_ptr<float>(c, F184_SLOT_ACCUM_NORMAL);
+    // static cache (include/f184.h "static / dynamic split"): the sums normalise sees are the frame's plus the cached static ones —
+    // integer-valued floats, exact in any order
+    std::vector<float> sumC, sumN;
+    if (c->cache_held)
+    {
+        sumC.resize(nvox * 4); sumN.resize(nvox * 4);
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < nvox * 4; i++) { sumC[i] = accC[i] + c->cacheC[i]; sumN[i] = accN[i] + c->cacheN[i]; }
+        accC = sumC.data(); accN = sumN.data();
+    }
     double t1 = now_ms();
     uint8_t* alb = image_ptr<uint8_t>(c, F184_SLOT_VOX_ALBEDO);
     int8_t* nrm = image_ptr<int8_t>(c, F184_SLOT_VOX_NORMAL);
@@ -347,6 +361,24 @@ extern "C" int orc_normalise_n(f184o_ctx* c)
     c->counters[F184_COUNTER_OCCUPIED] = occ;
     c->counters[F184_COUNTER_BRICKS] = nb;
     c->stage_ms[F184_STAGE_NORMALISE] = (float)(now_ms() - t1);
+    return F184_OK;
+}
+
+// static / dynamic split: keep the accumulators as the static cache (dense here; sparse on the device), leave them clear
+extern "C" int orc_static_cache_capture_n(f184o_ctx* c)
+{
+    for (int s : {F184_SLOT_ACCUM_COLOR, F184_SLOT_ACCUM_NORMAL})
+    { int rc = ensure_image(c, s); if (rc) return rc; }
+    const size_t nvox = (size_t)c->cfg.grid_n * c->cfg.grid_n * c->cfg.grid_n;
+    float* accC = image_ptr<float>(c, F184_SLOT_ACCUM_COLOR);
+    float* accN = image_ptr<float>(c, F184_SLOT_ACCUM_NORMAL);
+    c->cacheC.assign(accC, accC + nvox * 4);
+    c->cacheN.assign(accN, accN + nvox * 4);
+    memset(accC, 0, nvox * 16);
+    memset(accN, 0, nvox * 16);
+    c->cache_fragments = c->counters[F184_COUNTER_FRAGMENTS];
+    memcpy(c->cache_cam, c->last_vox_cam, sizeof(c->cache_cam));
+    c->cache_held = true;
     return F184_OK;
 }
 

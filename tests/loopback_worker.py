@@ -233,7 +233,7 @@ def run_barrier_timeout(bad):
     c = A.VoxelGI(N, W, H, A.MODE_NORTHSTAR, shadow_res=64, device=0, rank=0, nranks=2)
     c.upload_scene(sc)
     sizes = {A.IPC_ACCUM_COLOR: N ** 3 * 16, A.IPC_ACCUM_NORMAL: N ** 3 * 16, A.IPC_BRICK_FLAGS: (N // 8) ** 3 * 4, A.IPC_EXPORT: (N // 8) ** 3 * 4096,
-             A.IPC_COUNTERS: 128, A.IPC_BRICK_LIST: (N // 8) ** 3 * 4, A.IPC_SYNC: 64, A.IPC_FRAG_QUEUE: 2 * (1 << 20) * 16, A.IPC_FRAG_COUNTS: 8 * 32 * 4}
+             A.IPC_COUNTERS: 256, A.IPC_BRICK_LIST: (N // 8) ** 3 * 4, A.IPC_SYNC: 64, A.IPC_FRAG_QUEUE: 2 * (1 << 20) * 16, A.IPC_FRAG_COUNTS: 8 * 128 * 128}
     fake = {b: torch.zeros(n, dtype=torch.uint8, device="cuda:0") for b, n in sizes.items()}     # a "peer" nobody runs
     for b, t in fake.items():
         c.ipc_ptr(b)
@@ -249,6 +249,101 @@ def run_barrier_timeout(bad):
     c.close()
 
 
+def run_static_cache(sc, cams, bad):
+    """Static / dynamic split (include/f184.h): triangles [0, S) are accumulated once and captured; every frame
+    voxelizes only a dynamic range [S, end).  Volumes, texture sets, image and counters must equal a context that voxelizes [0, end)
+    every frame — on one context (synchronised frames, then frames back to back through the pipeline) and on two loopback ranks."""
+    N, W, H, SH = 64, 160, 96, 256
+    fi = frame_inputs(sc, cams["main"], cams["shadow"], W, H, SH, 0, cache=False)
+    k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
+    cam = cams["voxel"]
+    T = sc.n_tris
+    S_ = (2 * T) // 3
+    ends = [T, S_ + (T - S_) // 2, S_, T, S_ + (T - S_) // 4, S_, S_, T]          # S_: a frame without any dynamic triangle
+
+    class Shim:                       # compare_arrays / compare_rows take a sharded rank
+        def __init__(self, ctx): self.ctx = ctx
+        def own_rows_mask(self): return np.ones(H, bool)
+
+    def check(tag, c, ref, counters=True):
+        for slot, name in ((A.SLOT_VOX_ALBEDO, "albedo"), (A.SLOT_VOX_NORMAL, "normal"), (A.SLOT_RADIANCE, "radiance"), (A.SLOT_MIPS, "mips")):
+            if not np.array_equal(c.readback(slot), ref.readback(slot)): bad.append(f"{tag}: {name}")
+        compare_arrays(bad, tag, Shim(c), ref, N)
+        compare_rows(bad, tag, Shim(c), ref)
+        if counters:
+            for w, name in ((A.COUNTER_FRAGMENTS, "fragments"), (A.COUNTER_OCCUPIED, "occupied"), (A.COUNTER_BRICKS, "bricks")):
+                if c.counter(w) != ref.counter(w): bad.append(f"{tag}: counter {name} {c.counter(w)} vs {ref.counter(w)}")
+
+    # ---- (a) one context, a synchronised comparison after every frame
+    ref, c = single(N, W, H, SH, sc, fi), single(N, W, H, SH, sc, fi)
+    c.set_triangle_range(0, S_)
+    c.voxelize_accumulate(cam)
+    c.static_cache_capture()
+    for i, end in enumerate(ends):
+        ref.set_triangle_range(0, end); one_frame(ref, cam, k)
+        c.set_triangle_range(S_, end - S_); one_frame(c, cam, k)
+        ref.sync(); c.sync()
+        check(f"static cache frame {i} (dynamic triangles {end - S_})", c, ref)
+    # another voxel camera: refused, and the context stays usable
+    try:
+        c.voxelize_accumulate(cams["main"])
+        bad.append("static cache: accumulation with another voxel camera was accepted")
+    except A.F184Error as e:
+        if "another voxel camera" not in str(e): bad.append(f"static cache: unexpected error {e}")
+    # capture again with a different split, then drop the cache: both back to the reference
+    S2 = T // 3
+    c.set_triangle_range(0, S2); c.voxelize_accumulate(cam); c.static_cache_capture()
+    for i, end in enumerate((T, S2, S2 + 5)):
+        ref.set_triangle_range(0, end); one_frame(ref, cam, k)
+        c.set_triangle_range(S2, end - S2); one_frame(c, cam, k)
+        ref.sync(); c.sync()
+        check(f"static cache, second capture, frame {i}", c, ref)
+    c.static_cache_clear()
+    for i, end in enumerate((T // 2, T)):
+        ref.set_triangle_range(0, end); one_frame(ref, cam, k)
+        c.set_triangle_range(0, end); one_frame(c, cam, k)
+        ref.sync(); c.sync()
+        check(f"static cache cleared, frame {i}", c, ref)
+    # ---- (b) frames back to back (three-stream pipeline, both texture sets), images staged asynchronously
+    c.set_triangle_range(0, S_); c.voxelize_accumulate(cam); c.static_cache_capture()
+    nbytes = c.image_info(A.SLOT_INDIRECT_OUT).size_bytes
+    want = []
+    for end in ends:
+        ref.set_triangle_range(0, end); one_frame(ref, cam, k)
+        want.append(ref.readback(A.SLOT_INDIRECT_OUT).copy())
+    hosts = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in ends]
+    for i, end in enumerate(ends):
+        c.set_triangle_range(S_, end - S_); one_frame(c, cam, k)
+        c.readback_async_ptr(A.SLOT_INDIRECT_OUT, hosts[i].data_ptr(), nbytes)
+    c.sync()
+    for i in range(len(ends)):
+        if not np.array_equal(hosts[i].numpy().view(np.uint16), want[i].view(np.uint16).reshape(-1)): bad.append(f"static cache: back-to-back frame {i}")
+    c.close()
+    # ---- (c) two loopback ranks: every rank captures its own bricks (after the barrier that completes the static accumulation)
+    ranks = make_box(2, N, W, H, SH, sc, cams, fi, A.FLAG_GATHER_LINEAR)
+    set_ranges(ranks, ref, 0, S_)
+    for g in ranks: g.ctx.voxelize_accumulate(cam)
+    for g in ranks: g.ctx.peer_barrier()
+    box_sync(ranks)
+    for g in ranks: g.ctx.static_cache_capture()
+    for g in ranks: g.ctx.peer_barrier()
+    box_sync(ranks)
+    for i, end in enumerate(ends[:5]):
+        set_ranges(ranks, ref, S_, end)
+        ref.set_triangle_range(0, end)
+        box_frame(ranks, cam, k); one_frame(ref, cam, k)
+        box_sync(ranks); ref.sync()
+        for r, g in enumerate(ranks):
+            t = f"static cache, 2 ranks, frame {i} rank {r}"
+            if not np.array_equal(g.ctx.readback(A.SLOT_RADIANCE), ref.readback(A.SLOT_RADIANCE)): bad.append(t + ": radiance")
+            if not np.array_equal(g.ctx.readback(A.SLOT_MIPS), ref.readback(A.SLOT_MIPS)): bad.append(t + ": mips")
+            compare_arrays(bad, t, g, ref, N)
+            compare_rows(bad, t, g, ref)
+        if sum(g.ctx.counter(A.COUNTER_FRAGMENTS) for g in ranks) != ref.counter(A.COUNTER_FRAGMENTS): bad.append(f"static cache, 2 ranks, frame {i}: fragments")
+    for g in ranks: g.close()
+    ref.close()
+
+
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.cuda.set_device(0)
@@ -261,6 +356,8 @@ def main():
         run_barrier_timeout(bad)
     if which in ("all", "single"):
         run_single_pipeline(sc, cams, bad)
+    if which in ("all", "static"):
+        run_static_cache(sc, cams, bad)
     if which in ("all", "box2"):
         run_box(2, sc, cams, 64, 160, 96, 256, bad)
     if which in ("all", "box4"):

@@ -86,8 +86,15 @@ def _worker(rank, world, port, out_dir):
         k = A.trace_constants_c(cams["main"], cams["shadow"], cams["voxel"], W, H, 0, True)
         g.frame(cams["voxel"], k)
         img = g.gather_image()
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), img=img, rad=g.ctx.readback(A.SLOT_RADIANCE), chunks=g.chunks, rows=g.own_rows_mask(),
-                 frags=g.ctx.counter(A.COUNTER_FRAGMENTS))
+        rad, frags = g.ctx.readback(A.SLOT_RADIANCE).copy(), g.ctx.counter(A.COUNTER_FRAGMENTS)
+        # static / dynamic split across the ranks: the first two thirds of the scene captured once, the rest voxelized per frame
+        s_ = (2 * sc.n_tris) // 3
+        g.ctx.set_triangle_range(0, s_)
+        g.capture_static(cams["voxel"])
+        g.ctx.set_triangle_range(s_, sc.n_tris - s_)
+        g.frame(cams["voxel"], k)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), img=img, rad=rad, chunks=g.chunks, rows=g.own_rows_mask(), frags=frags,
+                 img_split=g.gather_image(), rad_split=g.ctx.readback(A.SLOT_RADIANCE), frags_split=g.ctx.counter(A.COUNTER_FRAGMENTS))
     finally:
         dist.destroy_process_group()
 
@@ -113,6 +120,8 @@ def test_sharded_frame_world2_gloo_equals_single_process(tmp_path, oracle_lib, p
     for i in range(world):
         assert np.array_equal(r[i]["rad"], o.readback(A.SLOT_RADIANCE)), f"rank {i}: summed partial volumes differ from the whole"
         assert np.array_equal(r[i]["img"].view(np.uint16), want.view(np.uint16)), f"rank {i}: assembled image differs"
+        assert np.array_equal(r[i]["rad_split"], r[i]["rad"]) and np.array_equal(r[i]["img_split"].view(np.uint16), want.view(np.uint16)), f"rank {i}: static/dynamic split"
+    assert int(r[0]["frags_split"]) + int(r[1]["frags_split"]) == o.counter(A.COUNTER_FRAGMENTS)
 
 
 def test_row_selective_transfers(oracle_lib):

@@ -35,7 +35,7 @@ def test_four_loopback_ranks_equal_one_context():
 
 
 def test_gather_with_many_units_per_cta():
-    """three CTAs instead of 296 make every gather CTA walk many 128-record units (what a 1024^3 volume does to the full grid)"""
+    """three CTAs instead of 296 make every gather CTA walk many 64-brick units (what a 1024^3 volume does to the full grid)"""
     run("sponza", F184_GATHER_CTAS="3")
 
 
@@ -50,3 +50,9 @@ def test_four_loopback_ranks_sponza_256():
 
 def test_barrier_with_a_missing_peer_is_an_error():
     run("timeout", F184_BARRIER_TIMEOUT_MS="300")
+
+
+def test_static_cache_equals_full_voxelization():
+    """static / dynamic split (f184_static_cache_capture): one context (synchronised and pipelined frames, re-capture, clear, camera
+    check) and two loopback ranks, bit for bit against voxelizing everything every frame"""
+    run("static")
