@@ -2,21 +2,22 @@
 // (include/f184.h "one NVLink box"; DESIGN.md "Multi-GPU").  The reference is single-GPU and single-queue
 // (RHI/Private/Vulkan/DeviceVk.cpp:301-304); nothing here has a counterpart in it.
 //
-//   * the reduce-scatter of the partial volumes is not a separate collective: mode_n_voxelize.cu reduces every fragment
-//     straight into the accumulators of the rank that owns the fragment's Z-slab (red.global.add.v4.f32 on a
-//     peer-mapped pointer, carried by NVLink), so after one barrier each owner holds the exact sum for its slab;
+//   * the reduce-scatter of the partial volumes is an all-to-all of FRAGMENTS (mode_n_voxelize.cu): a fragment of a brick another
+//     rank owns — bricks are owned along diagonals, (bx + by + bz) % G — becomes a 16-byte record in a queue in the sender's own
+//     memory; behind one barrier the owner pulls its queues over NVLink and reduces locally.  The queues and their cursors are
+//     allocated here (f184_ipc_buffer_ptr);
 //   * k_peer_barrier: device-side flag barrier — each rank stores its epoch into every peer's flag array
 //     (st.release.sys over NVLink) and spins on its own array (ld.acquire.sys, local memory): no host round trip and
 //     no NCCL launch on the frame's critical path; a timeout (5 s; F184_BARRIER_TIMEOUT_MS) turns a missing peer into an
 //     error instead of a hang: the kernel sets a sticky device error bit and the next synchronous call of the context
 //     (f184_sync, f184_counter_get, f184_stage_time_*) returns F184_ERR_PEER_TIMEOUT;
-//   * k_gather_bricks: the all-gather before tracing — every rank pulls the other ranks' finished bricks, packed by
-//     mode_n_mips.cu into contiguous 4 KB records (level 0 + levels 1-3 of one 8^3 brick), with coalesced 16-byte peer
-//     loads, and writes them through surfaces into its own texture storage; only listed bricks move (Sponza at 512^3:
-//     ~0.12 GB for the whole volume instead of 1.0 GB dense).  Levels >= 4 are then finished locally (k_mips_tail);
-//   * level 0 travels only when a cone of this rank's rows can sample it: k_need_level0 evaluates the tracer's own level
-//     selection for the first (finest) sample of every pixel's cones; with the 60-degree diffuse cones and materials of
-//     roughness >= 0.6 no cone ever reads level 0 and the gather moves 2 KB per brick instead of 4.
+//   * k_need_bricks: what do the cones of THIS rank's rows sample?  Level 0 at all (glossy pixels only), and level 1 of which
+//     bricks (a conservative box around every pixel's world position; the specular cone marched where it stays fine longer);
+//   * k_gather_bricks_tma: the all-gather before tracing — every rank pulls the other ranks' finished bricks out of the export
+//     arrays mode_n_mips.cu writes (level 0 | level 1 | "coarse": levels 2, 3 + brick index) with bulk copies (cp.async.bulk
+//     into shared memory, mbarrier completion): one 16 KB copy per 64 bricks for the coarse blocks, level 1 / level 0 per marked
+//     brick, and stores them through surfaces into its own texture set.  Levels >= 4 are then finished locally (k_mips_tail).
+//     C4 at 8 GPUs: 73 MB per rank instead of 1.1 GB, 0.19 ms.
 #include <algorithm>
 #include <cstdlib>
 
