@@ -285,6 +285,10 @@ class ProbeBatch:
         self.gi = ShardedVoxelGI(grid_n, view_size, view_size * max(self.local, 1), shadow_res=shadow_res, device=device, rank=rank,
                                  nranks=nranks, scene=scene, mode=mode, lib=lib, voxel_cam=voxel_cam, flags=flags)
         self.ctx = self.gi.ctx
+        # a rank traces ALL rows of its views (whole views per rank), not interleaved tile rows: the gather's "what do my cones sample"
+        # pass (level 0 for glossy pixels) must look at every row of this context's image
+        self.gi.tiles = (0, 1)
+        self.ctx.set_trace_tiles(0, 1)
 
     def upload_views(self, per_view_inputs, shadow):
         """per_view_inputs: one dict(depth, normals, material) per view of the WHOLE batch (indexed by global view);
